@@ -1,0 +1,256 @@
+/*
+ * vqcuda.h — C-ABI of the B200 (sm_100a) headless shading backend.
+ *
+ * One entry point per GPU program the engine dispatches for its per-pixel passes.
+ * The reference has no FFI of its own; each function below names
+ * the reference dispatch site + HLSL entry point it replaces. Conventions mirror the
+ * engine's (SURVEY.md §8(b) "Conventions"):
+ *   - resources are caller-owned (the engine passes integer IDs; here: device pointers
+ *     described by {ptr, width, height, pitch}); the library never frees caller memory;
+ *   - nothing throws across the boundary: every call returns 0 (VQ_OK) or a negative
+ *     VqStatus; vq_last_error() gives a thread-local message;
+ *   - calls only ENQUEUE work on `stream` (== recording into a command list); they are
+ *     thread-safe when callers use distinct streams (== per-thread command lists,
+ *     SceneRendering.cpp:197-207). Synchronisation is the caller's (cudaStreamSynchronize
+ *     == fence wait), except the *_host convenience calls which block.
+ *   - there is NO CPU fallback: without a CUDA device every device call fails with
+ *     VQ_ERR_NO_DEVICE.
+ *
+ * All pixel data is linear fp32: RGBA32F (`float4`, 16 B) unless stated otherwise.
+ * `stream` is a cudaStream_t passed as void* so that this header needs no CUDA headers.
+ */
+#ifndef VQCUDA_H
+#define VQCUDA_H
+
+#include "vq_shader_data.h"
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#if defined(_WIN32)
+#  define VQ_API __declspec(dllexport)
+#else
+#  define VQ_API __attribute__((visibility("default")))
+#endif
+
+typedef enum VqStatus {
+    VQ_OK               =  0,
+    VQ_ERR_INVALID_ARG  = -1,
+    VQ_ERR_CUDA         = -2,
+    VQ_ERR_UNSUPPORTED  = -3,
+    VQ_ERR_NO_DEVICE    = -4,
+    VQ_ERR_OUT_OF_MEMORY= -5
+} VqStatus;
+
+/* ------------------------------------------------------------------------------------------
+ * Resource descriptors (replace TextureID/SRV_ID/UAV_ID/RTV_ID, EnvironmentMapRendering.h:28-48)
+ * ------------------------------------------------------------------------------------------ */
+
+/* 2-D image of float4 texels (float2 where stated). pitch_bytes is a multiple of 16. */
+typedef struct VqImage {
+    void*   ptr;
+    int32_t width, height;
+    size_t  pitch_bytes;
+} VqImage;
+
+/* Cubemap with a mip chain, float4 texels, tightly packed, mip-major / face-minor:
+ *   offset_texels(mip, face) = sum_{m<mip} 6*(res>>m)^2 + face*(res>>mip)^2
+ * Face order = D3D / CubemapUtility.h:31-41: +X(RIGHT) -X(LEFT) +Y(UP) -Y(DOWN) +Z(FRONT) -Z(BACK). */
+typedef struct VqCubemap {
+    void*   ptr;
+    int32_t res;   /* edge length of mip 0 */
+    int32_t mips;
+} VqCubemap;
+
+/* Equirectangular HDRI with its CPU-style mip pyramid (TextureManager.cpp:714-727), float4,
+ * tightly packed levels: level l is (width>>l) x (height>>l); levels <= vq_mip_level_count(). */
+typedef struct VqPyramid {
+    void*   ptr;
+    int32_t width, height;
+    int32_t levels;
+} VqPyramid;
+
+/* The surface record PSMain consumes after material-texture sampling (BRDF.hlsl:50-58,
+ * ForwardLighting.hlsl:245-285) as three (optionally four) float4 planes:
+ *   position_ao      = { P.xyz (world space), ao }   ao = fAmbientLightingFactor*localAO*SSAO
+ *   normal_roughness = { N.xyz (unit, world space), roughness }
+ *   albedo_metalness = { diffuseColor.rgb, metalness }
+ *   emissive         = { emissiveColor.rgb, emissiveIntensity }   (ptr == NULL -> no emissive) */
+typedef struct VqGBuffer {
+    VqImage position_ao;
+    VqImage normal_roughness;
+    VqImage albedo_metalness;
+    VqImage emissive;
+} VqGBuffer;
+
+/* The three IBL inputs PSMain binds (SceneRendering.cpp:1690-1717). brdf_lut holds float2 texels. */
+typedef struct VqEnvironmentMaps {
+    VqCubemap irradiance_diffuse;   /* blurred diffuse irradiance, 1 mip */
+    VqCubemap irradiance_specular;  /* prefiltered specular, `mips` levels */
+    VqImage   brdf_lut;             /* float2 (scale,bias), CubemapConvolution.hlsl:227-240 */
+} VqEnvironmentMaps;
+
+typedef struct VqContext VqContext;
+
+/* ------------------------------------------------------------------------------------------
+ * Lifetime  (IRenderPass::Initialize / Destroy / OnCreateWindowSizeDependentResources,
+ *            RenderPass.h:44-59)
+ * ------------------------------------------------------------------------------------------ */
+VQ_API int  vq_ctx_create(int device, VqContext** out_ctx);
+VQ_API int  vq_ctx_destroy(VqContext* ctx);
+/* Pre-sizes internal scratch (SPD counters, host-call staging) for a render resolution. Optional. */
+VQ_API int  vq_ctx_resize(VqContext* ctx, int width, int height);
+VQ_API const char* vq_last_error(void);
+VQ_API const char* vq_version(void);
+/* Number of kernels this library has launched in this process (all contexts). */
+VQ_API uint64_t vq_launch_count(void);
+
+/* ------------------------------------------------------------------------------------------
+ * K1  Forward PBR lighting.  Replaces VQRenderer::RenderSceneColor (SceneRendering.cpp:1619-1851)
+ *     + PSMain (ForwardLighting.hlsl:222-391) over a G-buffer instead of rasterised draws.
+ *     Shades rows [row_begin,row_end) of the image (row tiling for multi-GPU); out = {I.rgb, roughness}.
+ *     Shadow maps do not exist headless: caster lists are lit with shadow factor 1 (no occlusion).
+ * ------------------------------------------------------------------------------------------ */
+VQ_API int vq_forward_lighting(VqContext* ctx,
+                               const VqPerFrameData* per_frame,
+                               const VqPerViewLightingData* per_view,
+                               const VqGBuffer* gbuffer,
+                               const VqEnvironmentMaps* env,
+                               VqImage out_color,
+                               int row_begin, int row_end,
+                               void* stream);
+
+/* ------------------------------------------------------------------------------------------
+ * K11 HDRI mip pyramid, 2x2 MIN filter, alpha = 1.  Replaces VQ_DXGI_UTILS::MipImage
+ *     (DXGIUtils.cpp:289-317) called from TextureManager.cpp:714-727. Level 0 must be filled.
+ * ------------------------------------------------------------------------------------------ */
+VQ_API int vq_hdri_build_mips(VqContext* ctx, VqPyramid hdri, void* stream);
+
+/* ------------------------------------------------------------------------------------------
+ * K2  Diffuse irradiance convolution.  Replaces the per-face draws at
+ *     EnvironmentMapRendering.cpp:221-240 + PSMain_DiffuseIrradiance (CubemapConvolution.hlsl:112-163).
+ *     Two sampling modes:
+ *       step  > 0 : the reference's float-accumulated (phi,theta) loops with that step
+ *                   (INTEGRATION_STEP_DIFFUSE_IRRADIANCE; 0.010/0.025/0.050, PipelineStateObjects.cpp:1298-1306)
+ *       step == 0 : an integer n_phi x n_theta grid, phi_i = i*(2pi/n_phi), theta_j = j*(pi/2/n_theta)
+ *     Source level is HDRI mip `src_mip` (reference: 3). Computes texel rows [row_begin,row_end)
+ *     of the flattened (face, row) space, face*res + row; out.mips must be 1.
+ * ------------------------------------------------------------------------------------------ */
+typedef struct VqDiffuseIrradianceParams {
+    float   step;
+    int32_t n_phi, n_theta;
+    int32_t src_mip;
+} VqDiffuseIrradianceParams;
+VQ_API int vq_diffuse_irradiance(VqContext* ctx, const VqDiffuseIrradianceParams* params,
+                                 VqPyramid hdri, VqCubemap out,
+                                 int row_begin, int row_end, void* stream);
+
+/* ------------------------------------------------------------------------------------------
+ * K3  Specular prefilter (GGX importance sampling, 512 Hammersley samples, PDF-based source mip).
+ *     Replaces the mip x face draw loop at EnvironmentMapRendering.cpp:413-465 +
+ *     PSMain_SpecularIrradiance (CubemapConvolution.hlsl:168-223). For every mip m of `out`:
+ *     Roughness = m/(mips-1), ViewDim = HDRI dims (EnvironmentMapRendering.cpp:432-434).
+ *     Computes texel rows [row_begin,row_end) of the flattened (mip, face, row) space
+ *     (vq_cubemap_row_count rows in total).
+ * ------------------------------------------------------------------------------------------ */
+VQ_API int vq_specular_prefilter(VqContext* ctx, VqPyramid hdri, VqCubemap out,
+                                 int num_samples, int row_begin, int row_end, void* stream);
+
+/* ------------------------------------------------------------------------------------------
+ * K4  BRDF integration LUT (split-sum scale,bias).  Replaces ComputeBRDFIntegrationLUT
+ *     (Renderer.cpp:871-909) + CSMain_BRDFIntegration (CubemapConvolution.hlsl:227-240).
+ *     out holds float2 texels; NdotV = (x+.5)/W, roughness = (y+.5)/H; reference: 1024^2, 2048 samples.
+ * ------------------------------------------------------------------------------------------ */
+VQ_API int vq_brdf_integration_lut(VqContext* ctx, VqImage out_rg, int num_samples,
+                                   int row_begin, int row_end, void* stream);
+
+/* ------------------------------------------------------------------------------------------
+ * K5  Separable 21-tap Gaussian blur, clamp-to-edge, alpha = 1.  Replaces the dispatches at
+ *     EnvironmentMapRendering.cpp:341-372 / SceneRendering.cpp:2582-2638 + CSMain_X / CSMain_Y
+ *     (GaussianBlur.hlsl:119-186).
+ * ------------------------------------------------------------------------------------------ */
+VQ_API int vq_gaussian_blur_x(VqContext* ctx, const VqBlurParams* params, VqImage in, VqImage out, void* stream);
+VQ_API int vq_gaussian_blur_y(VqContext* ctx, const VqBlurParams* params, VqImage in, VqImage out, void* stream);
+
+/* ------------------------------------------------------------------------------------------
+ * K6  Tonemapper.  Replaces the dispatch at SceneRendering.cpp:2640-2656 + CSMain (Tonemapper.hlsl:110-151).
+ * ------------------------------------------------------------------------------------------ */
+VQ_API int vq_tonemap(VqContext* ctx, const VqTonemapperParams* params, VqImage in, VqImage out, void* stream);
+
+/* ------------------------------------------------------------------------------------------
+ * K7  FidelityFX CAS, sharpen-only path.  Replaces SceneRendering.cpp:2658-2693 + CAS_CSMain
+ *     (AMDFidelityFX.hlsl:122-174) -> CasFilter(noScaling) (CAS/ffx_cas.h:408-537).
+ *     cas_const = the 8 words CasSetup wrote (FFFXCAS::CASConstantBlock, PostProcess.h:104-112).
+ *     Reads outside the image return 0 (D3D Texture.Load). Output alpha is 1.
+ * ------------------------------------------------------------------------------------------ */
+VQ_API int vq_cas(VqContext* ctx, const uint32_t cas_const[8], VqImage in, VqImage out, void* stream);
+
+/* ------------------------------------------------------------------------------------------
+ * K8  FSR1 EASU.  Replaces SceneRendering.cpp:2711-2734 + FSR_EASU_CSMain (AMDFidelityFX.hlsl:247-288)
+ *     -> FsrEasuF (FSR1.0/ffx_fsr1.h:315-437). easu_const = FFSR1_EASU::EASUConstantBlock (16 words).
+ *     Gathers use the engine's sampler addressing: VQ_ADDRESS_WRAP (RootSignatures.cpp:525) by default.
+ * ------------------------------------------------------------------------------------------ */
+enum { VQ_ADDRESS_WRAP = 0, VQ_ADDRESS_CLAMP = 1 };
+VQ_API int vq_fsr_easu(VqContext* ctx, const uint32_t easu_const[16], int address_mode,
+                       VqImage in, VqImage out, void* stream);
+
+/* ------------------------------------------------------------------------------------------
+ * K9  FSR1 RCAS.  Replaces SceneRendering.cpp:2735-2781 + FSR_RCAS_CSMain (AMDFidelityFX.hlsl:335-376)
+ *     -> FsrRcasF (ffx_fsr1.h:684-769). rcas_const = FFSR1_RCAS::RCASConstantBlock (4 words).
+ * ------------------------------------------------------------------------------------------ */
+VQ_API int vq_fsr_rcas(VqContext* ctx, const uint32_t rcas_const[4], VqImage in, VqImage out, void* stream);
+
+/* ------------------------------------------------------------------------------------------
+ * K10 FidelityFX SPD: the whole mip chain in one launch.  Replaces SPD_CSMain
+ *     (AMDFidelityFX.hlsl:525-545) -> SpdDownsample (SPD/ffx_spd.h:811-835), reduction =
+ *     (v0+v1+v2+v3)*0.25 (AMDFidelityFX.hlsl:463-466). `mips` are the destination levels
+ *     1..constants->mips (mips[i] is level i+1, floor-halved sizes); src is level 0.
+ * ------------------------------------------------------------------------------------------ */
+VQ_API int vq_spd_downsample(VqContext* ctx, const VqSpdConstants* constants,
+                             VqImage src, const VqImage* mips, void* stream);
+
+/* ------------------------------------------------------------------------------------------
+ * Host-side constant setup == the FidelityFX `A_CPU` functions the engine calls
+ * (PostProcess.cpp:39-99): bit-identical results.
+ * ------------------------------------------------------------------------------------------ */
+/* FsrEasuCon (ffx_fsr1.h:156-202) -> con[16] = con0|con1|con2|con3 */
+VQ_API void vq_fsr_easu_con(uint32_t con[16],
+                            float input_viewport_w, float input_viewport_h,
+                            float input_size_w, float input_size_h,
+                            float output_w, float output_h);
+/* FsrRcasCon (ffx_fsr1.h:662-672) */
+VQ_API void vq_fsr_rcas_con(uint32_t con[4], float sharpness_stops);
+/* CasSetup (ffx_cas.h:375-394) -> con[8] = const0|const1 */
+VQ_API void vq_cas_setup(uint32_t con[8], float sharpness,
+                         float input_w, float input_h, float output_w, float output_h);
+/* SpdSetup (ffx_spd.h:327-351); rect = {left, top, width, height}; mips < 0 -> derive from rect */
+VQ_API void vq_spd_setup(uint32_t dispatch_xy[2], VqSpdConstants* constants,
+                         const uint32_t rect[4], int mips);
+/* Image::CalculateMipLevelCount (Libs/VQUtils/Source/Image.cpp:231-241) */
+VQ_API int  vq_mip_level_count(uint64_t w, uint64_t h);
+
+/* Layout helpers for the packed descriptors above (host-side arithmetic only). */
+VQ_API uint64_t vq_cubemap_texel_count(int res, int mips);             /* total float4 texels */
+VQ_API uint64_t vq_cubemap_offset(int res, int mip, int face);         /* texel offset of (mip,face) */
+VQ_API int      vq_cubemap_row_count(int res, int mips);               /* rows in flattened (mip,face,row) */
+VQ_API uint64_t vq_pyramid_texel_count(int width, int height, int levels);
+VQ_API uint64_t vq_pyramid_offset(int width, int height, int level);   /* texel offset of a level */
+
+/* ------------------------------------------------------------------------------------------
+ * Blocking host-buffer entry points: the same passes called with HOST pointers (what an engine
+ * integration that keeps its frame data in system memory would call). Each call uploads the
+ * inputs, runs the kernel(s), downloads the result and returns when the result is in `out`.
+ * Transfers are chunked by rows and overlapped with compute on internal streams.
+ * ------------------------------------------------------------------------------------------ */
+VQ_API int vq_forward_lighting_host(VqContext* ctx,
+                                    const VqPerFrameData* per_frame,
+                                    const VqPerViewLightingData* per_view,
+                                    const VqGBuffer* host_gbuffer,
+                                    const VqEnvironmentMaps* device_env,
+                                    VqImage host_out_color);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* VQCUDA_H */

@@ -1,0 +1,257 @@
+// ORACLE — TEST INFRASTRUCTURE ONLY. Not part of the product; never linked into libvqcuda.
+//
+// oracle_capi.cpp — extern "C" drivers over the scalar oracle so that tests/ (ctypes) and
+// bench.py's cpu_baseline / `--impl reference` leg can run whole passes on host buffers.
+// All images are tightly pitched float4 (float2 for the BRDF LUT). `threads` = std::thread count
+// (row partition); the per-texel arithmetic is single-threaded scalar code.
+#include "oracle.h"
+
+using namespace orc;
+
+namespace {
+template <class F>
+void par_rows(int n, int threads, F&& f) {
+    struct Ctx { F* f; } ctx{&f};
+    ParallelRows(n, threads, [](int r, void* u) { (*static_cast<Ctx*>(u)->f)(r); }, &ctx);
+}
+inline float4 ld(const float* p) { return {p[0], p[1], p[2], p[3]}; }
+inline void st(float* p, float4 v) { p[0] = v.x; p[1] = v.y; p[2] = v.z; p[3] = v.w; }
+inline Image img4(const float* d, int w, int h) { return {d, w, h, (size_t)w * 4, 4}; }
+
+// flattened (mip, face, row) -> components
+inline void decode_cube_row(int res, int mips, int r, int* mip, int* face, int* row) {
+    for (int m = 0; m < mips; ++m) {
+        const int n = res >> m;
+        if (r < 6 * n) { *mip = m; *face = r / n; *row = r % n; return; }
+        r -= 6 * n;
+    }
+    *mip = -1; *face = 0; *row = 0;
+}
+}  // namespace
+
+extern "C" {
+
+int orc_mip_level_count(uint64_t w, uint64_t h) { return mip_level_count(w, h); }
+uint64_t orc_cubemap_texel_count(int res, int mips) { return cubemap_texel_count(res, mips); }
+int orc_cubemap_row_count(int res, int mips) { return cubemap_row_count(res, mips); }
+uint64_t orc_pyramid_texel_count(int w, int h, int levels) { return pyramid_texel_count(w, h, levels); }
+
+// ---- K1 ---------------------------------------------------------------------------------------
+void orc_forward_lighting(const VqPerFrameData* pf, const VqPerViewLightingData* pv,
+                          const float* position_ao, const float* normal_roughness, const float* albedo_metalness,
+                          const float* emissive, int width, int height,
+                          const float* diff_cube, int diff_res,
+                          const float* spec_cube, int spec_res, int spec_mips,
+                          const float* lut, int lut_w, int lut_h,
+                          float* out, int row_begin, int row_end, int threads) {
+    const Cubemap cd{diff_cube, diff_res, 1};
+    const Cubemap cs{spec_cube, spec_res, spec_mips};
+    const Image lutImg{lut, lut_w, lut_h, (size_t)lut_w * 2, 2};
+    (void)height;
+    par_rows(row_end - row_begin, threads, [&](int r) {
+        const int y = row_begin + r;
+        for (int x = 0; x < width; ++x) {
+            const size_t o = ((size_t)y * width + x) * 4;
+            float4 em;
+            if (emissive) em = ld(emissive + o);
+            st(out + o, ForwardLighting_PSMain(*pf, *pv, ld(position_ao + o), ld(normal_roughness + o),
+                                               ld(albedo_metalness + o), emissive ? &em : nullptr, cd, cs, lutImg));
+        }
+    });
+}
+
+// ---- K11 --------------------------------------------------------------------------------------
+void orc_hdri_build_mips(float* pyramid, int w, int h, int levels) {
+    Pyramid p{pyramid, w, h, levels};
+    for (int l = 1; l < levels; ++l)
+        MipImage_MinFilter(pyramid + 4 * p.offset(l - 1), pyramid + 4 * p.offset(l), w >> (l - 1), h >> (l - 1));
+}
+
+// ---- K2 ---------------------------------------------------------------------------------------
+int orc_diffuse_angle_counts(float step, int n_phi, int n_theta, int* out_phi, int* out_theta) {
+    std::vector<float> ph, th;
+    DiffuseIrradianceAngles(step, n_phi, n_theta, ph, th);
+    *out_phi = (int)ph.size(); *out_theta = (int)th.size();
+    return (int)(ph.size() * th.size());
+}
+void orc_diffuse_irradiance(const float* pyramid, int w, int h, int levels,
+                            float step, int n_phi, int n_theta, int src_mip,
+                            float* out_cube, int res, int row_begin, int row_end, int threads) {
+    const Pyramid p{pyramid, w, h, levels};
+    std::vector<float> phis, thetas;
+    DiffuseIrradianceAngles(step, n_phi, n_theta, phis, thetas);
+    par_rows(row_end - row_begin, threads, [&](int r) {
+        const int fr = row_begin + r, face = fr / res, py = fr % res;
+        for (int px = 0; px < res; ++px) {
+            const float3 dir = CubeTexelDirection(face, px, py, res);
+            st(out_cube + 4 * ((size_t)face * res * res + (size_t)py * res + px),
+               DiffuseIrradiance_PSMain(p, dir, phis, thetas, src_mip));
+        }
+    });
+}
+
+// ---- K3 ---------------------------------------------------------------------------------------
+void orc_specular_prefilter(const float* pyramid, int w, int h, int levels,
+                            float* out_cube, int res, int mips, int num_samples,
+                            int row_begin, int row_end, int threads) {
+    const Pyramid p{pyramid, w, h, levels};
+    const Cubemap cm{out_cube, res, mips};
+    par_rows(row_end - row_begin, threads, [&](int r) {
+        int mip, face, py;
+        decode_cube_row(res, mips, row_begin + r, &mip, &face, &py);
+        if (mip < 0) return;
+        const int n = res >> mip;
+        // EnvironmentMapRendering.cpp:432: Roughness = mip / (NUM_MIPS - 1)
+        const float roughness = (float)mip / (float)(mips - 1);
+        for (int px = 0; px < n; ++px) {
+            const float3 dir = CubeTexelDirection(face, px, py, n);
+            st(out_cube + 4 * (cm.offset(mip, face) + (size_t)py * n + px),
+               SpecularIrradiance_PSMain(p, dir, roughness, make2((float)w, (float)h), (uint32_t)num_samples));
+        }
+    });
+}
+
+// ---- K4 ---------------------------------------------------------------------------------------
+void orc_brdf_integration_lut(float* out_rg, int w, int h, int samples, int row_begin, int row_end, int threads) {
+    par_rows(row_end - row_begin, threads, [&](int r) {
+        const int y = row_begin + r;
+        for (int x = 0; x < w; ++x) {
+            // CubemapConvolution.hlsl:234-239
+            const float u = ((float)x + 0.5f) / (float)w, v = ((float)y + 0.5f) / (float)h;
+            const float2 sb = IntegrateBRDF(u, v, samples);
+            out_rg[((size_t)y * w + x) * 2 + 0] = sb.x;
+            out_rg[((size_t)y * w + x) * 2 + 1] = sb.y;
+        }
+    });
+}
+
+// ---- K5 / K6 ----------------------------------------------------------------------------------
+void orc_gaussian_blur(const float* in, float* out, int w, int h, int vertical, int threads) {
+    const Image I = img4(in, w, h);
+    par_rows(h, threads, [&](int y) {
+        for (int x = 0; x < w; ++x) st(out + ((size_t)y * w + x) * 4, GaussianBlur_CSMain(I, x, y, vertical != 0, w, h));
+    });
+}
+void orc_tonemap(const VqTonemapperParams* p, const float* in, float* out, int w, int h, int threads) {
+    par_rows(h, threads, [&](int y) {
+        for (int x = 0; x < w; ++x) {
+            const size_t o = ((size_t)y * w + x) * 4;
+            st(out + o, Tonemapper_CSMain(*p, ld(in + o)));
+        }
+    });
+}
+
+// ---- K7 / K8 / K9 -----------------------------------------------------------------------------
+void orc_cas(const uint32_t c[8], const float* in, float* out, int w, int h, int threads) {
+    const Image I = img4(in, w, h);
+    par_rows(h, threads, [&](int y) {
+        for (int x = 0; x < w; ++x) st(out + ((size_t)y * w + x) * 4, make4(CasFilter_NoScaling(I, x, y, c + 4), 1.0f));
+    });
+}
+void orc_fsr_easu(const uint32_t c[16], int address_mode, const float* in, int in_w, int in_h,
+                  float* out, int out_w, int out_h, int threads) {
+    const Image I = img4(in, in_w, in_h);
+    par_rows(out_h, threads, [&](int y) {
+        for (int x = 0; x < out_w; ++x) st(out + ((size_t)y * out_w + x) * 4, make4(FsrEasuF(I, x, y, c, address_mode), 1.0f));
+    });
+}
+void orc_fsr_rcas(const uint32_t c[4], const float* in, float* out, int w, int h, int threads) {
+    const Image I = img4(in, w, h);
+    par_rows(h, threads, [&](int y) {
+        for (int x = 0; x < w; ++x) st(out + ((size_t)y * w + x) * 4, make4(FsrRcasF(I, x, y, c), 1.0f));
+    });
+}
+
+// ---- K10: dst levels 1..mips packed back to back, level i is (w>>i) x (h>>i) --------------------
+void orc_spd_downsample(const float* src, int w, int h, int mips, float* out_packed) {
+    Image cur = img4(src, w, h);
+    float* o = out_packed;
+    for (int l = 1; l <= mips; ++l) {
+        const int lw = w >> l, lh = h >> l;
+        if (lw < 1 || lh < 1) break;
+        MutImage d{o, lw, lh, (size_t)lw * 4, 4};
+        SpdDownsampleLevel(cur, d, l);
+        cur = d.view();
+        o += (size_t)lw * lh * 4;
+    }
+}
+
+// ---- setup functions --------------------------------------------------------------------------
+void orc_cas_setup(uint32_t con[8], float sharpness, float in_w, float in_h, float out_w, float out_h) {
+    CasSetup(con, con + 4, sharpness, in_w, in_h, out_w, out_h);
+}
+void orc_fsr_easu_con(uint32_t con[16], float vp_w, float vp_h, float in_w, float in_h, float out_w, float out_h) {
+    FsrEasuCon(con, con + 4, con + 8, con + 12, vp_w, vp_h, in_w, in_h, out_w, out_h);
+}
+void orc_fsr_rcas_con(uint32_t con[4], float stops) { FsrRcasCon(con, stops); }
+void orc_spd_setup(uint32_t dispatch_xy[2], uint32_t wg_offset[2], uint32_t nwg_mips[2], const uint32_t rect[4], int mips) {
+    SpdSetup(dispatch_xy, wg_offset, nwg_mips, rect, mips);
+}
+
+// ---- scalar probes for known-answer tests -------------------------------------------------------
+void orc_brdf(const float N[3], const float V[3], const float Wi[3], const float albedo[3],
+              float roughness, float metalness, float out[3]) {
+    BRDF_Surface s{};
+    s.N = make3(N[0], N[1], N[2]); s.roughness = roughness; s.metalness = metalness;
+    s.diffuseColor = make3(albedo[0], albedo[1], albedo[2]);
+    const float3 r = BRDF(s, make3(Wi[0], Wi[1], Wi[2]), make3(V[0], V[1], V[2]));
+    out[0] = r.x; out[1] = r.y; out[2] = r.z;
+}
+float orc_ndf_ggx(float NdotH, float roughness) { return NormalDistributionGGX(NdotH, roughness); }
+float orc_geometry_smith(const float N[3], const float V[3], const float L[3], float roughness) {
+    return Geometry_Smith(make3(N[0], N[1], N[2]), make3(V[0], V[1], V[2]), make3(L[0], L[1], L[2]), roughness);
+}
+void orc_fresnel_schlick(const float H[3], const float V[3], const float F0[3], float out[3]) {
+    const float3 r = Fresnel_Schlick(make3(H[0], H[1], H[2]), make3(V[0], V[1], V[2]), make3(F0[0], F0[1], F0[2]));
+    out[0] = r.x; out[1] = r.y; out[2] = r.z;
+}
+void orc_fresnel_gaussian(const float H[3], const float V[3], const float F0[3], float out[3]) {
+    const float3 r = Fresnel_Gaussian(make3(H[0], H[1], H[2]), make3(V[0], V[1], V[2]), make3(F0[0], F0[1], F0[2]));
+    out[0] = r.x; out[1] = r.y; out[2] = r.z;
+}
+void orc_point_light(const VqPointLight* l, const float P[3], const float N[3], const float V[3],
+                     const float albedo[3], float roughness, float metalness, float out[3]) {
+    BRDF_Surface s{};
+    s.N = make3(N[0], N[1], N[2]); s.roughness = roughness; s.metalness = metalness;
+    s.diffuseColor = make3(albedo[0], albedo[1], albedo[2]);
+    const float3 r = CalculatePointLightIllumination(*l, s, make3(P[0], P[1], P[2]), make3(V[0], V[1], V[2]));
+    out[0] = r.x; out[1] = r.y; out[2] = r.z;
+}
+float orc_spotlight_intensity(const VqSpotLight* l, const float P[3]) { return SpotlightIntensity(*l, make3(P[0], P[1], P[2])); }
+void orc_hammersley(uint32_t i, uint32_t n, float out[2]) { const float2 h = Hammersley(i, n); out[0] = h.x; out[1] = h.y; }
+void orc_importance_sample_ggx(const float Xi[2], const float N[3], float roughness, float out[3]) {
+    const float3 h = ImportanceSampleGGX(make2(Xi[0], Xi[1]), make3(N[0], N[1], N[2]), roughness);
+    out[0] = h.x; out[1] = h.y; out[2] = h.z;
+}
+void orc_integrate_brdf(float NdotV, float roughness, int samples, float out[2]) {
+    const float2 r = IntegrateBRDF(NdotV, roughness, samples); out[0] = r.x; out[1] = r.y;
+}
+void orc_direction_to_equirect_uv(const float d[3], float out[2]) {
+    const float2 uv = DirectionToEquirectUV(make3(d[0], d[1], d[2])); out[0] = uv.x; out[1] = uv.y;
+}
+void orc_cube_texel_direction(int face, int px, int py, int res, float out[3]) {
+    const float3 d = CubeTexelDirection(face, px, py, res); out[0] = d.x; out[1] = d.y; out[2] = d.z;
+}
+void orc_direction_to_cube_face(const float d[3], int* face, float* sx, float* sy) {
+    DirectionToCubeFace(make3(d[0], d[1], d[2]), face, sx, sy);
+}
+void orc_cube_resolve_edge_tap(int N, int face, int i, int j, int out[3]) {
+    CubeResolveEdgeTap(N, face, i, j, &out[0], &out[1], &out[2]);
+}
+void orc_sample_cube(const float* cube, int res, int mips, const float d[3], int mip, float out[4]) {
+    const float4 r = SampleCubeLevel(Cubemap{cube, res, mips}, make3(d[0], d[1], d[2]), mip);
+    out[0] = r.x; out[1] = r.y; out[2] = r.z; out[3] = r.w;
+}
+void orc_sample_equirect(const float* pyr, int w, int h, int levels, float u, float v, float lod, float out[4]) {
+    const float4 r = SampleEquirectLevel(Pyramid{pyr, w, h, levels}, make2(u, v), lod);
+    out[0] = r.x; out[1] = r.y; out[2] = r.z; out[3] = r.w;
+}
+void orc_tonemap_pixel(const VqTonemapperParams* p, const float in[4], float out[4]) {
+    const float4 r = Tonemapper_CSMain(*p, make4(in[0], in[1], in[2], in[3]));
+    out[0] = r.x; out[1] = r.y; out[2] = r.z; out[3] = r.w;
+}
+float orc_aprx(int which, float a) {
+    switch (which) { case 0: return APrxLoSqrtF1(a); case 1: return APrxLoRcpF1(a); case 2: return APrxMedRcpF1(a); default: return APrxLoRsqF1(a); }
+}
+
+}  // extern "C"
