@@ -1,0 +1,400 @@
+#!/usr/bin/env python
+"""bench.py — headline benchmark of the B200 shading backend (contract: task brief + BASELINE.json).
+
+A "step" is ONE forward-PBR lighting pass (K1) over a 3840x2160 synthetic G-buffer with 4 point lights,
+1 directional light and IBL (BASELINE.json metric "Mpixels/s forward-PBR @4K"), inputs resident in HBM.
+  value      = Mpixels/s over all ranks (weak scaling: every rank shades its own 3840x2160 row tile)
+  e2e        = the same pass through the blocking host-buffer C-ABI call (pinned host G-buffer in,
+               host image out; H2D/D2H inside the timed region)
+  roofline   = algorithmic 64 B/pixel / kernel time, against the measured HBM copy peak
+  cpu_baseline = the scalar oracle (CPU port of the HLSL) on this box's host cores, bounded row sample
+  extra      = per-kernel timings for the other SURVEY.md §8 rows (post chain @4K, IBL integrals)
+`--impl reference` times the CPU oracle instead (the reference's D3D12/HLSL path cannot run here).
+"""
+from __future__ import annotations
+
+import argparse
+import ctypes as C
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+for _p in (ROOT, os.path.join(ROOT, "tests")):
+    if _p not in sys.path:
+        sys.path.insert(0, _p)
+
+W4K, H4K = 3840, 2160
+BYTES_PER_PX = 64          # 3 x float4 in + 1 x float4 out
+METRIC = "forward_pbr_4k_mpixels_per_s"
+UNIT = "Mpixels/s"
+WORKLOAD = "forward-PBR 3840x2160 G-buffer (3 float4 planes), 4 point + 1 directional + IBL (64^2 diffuse, 512^2 x9 specular, 1024^2 LUT)"
+
+
+def hbm_peak():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        try:
+            return float(json.load(open(p))["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
+        except Exception:
+            pass
+    return 6650.0, "fallback (B200_PROFILING.md)"
+
+
+class ClockSampler:
+    """nvidia-smi clocks/throttle reasons sampled DURING the timed region."""
+    Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index: int):
+        self.rows, self.proc, self.index = [], None, index
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--id={self.index}", f"--query-gpu={self.Q}",
+                                          "--format=csv,noheader,nounits", "-lms", "50"],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.t = threading.Thread(target=self._read, daemon=True)
+            self.t.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append([c.strip() for c in line.split(",")])
+
+    def stop(self):
+        if not self.proc:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=2)
+        except Exception:
+            self.proc.kill()
+        sm, mx, reasons, pw = [], [], set(), []
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for r in self.rows:
+            try:
+                sm.append(float(r[0])); mx.append(float(r[1])); pw.append(float(r[2]))
+                for n, v in zip(names, r[3:7]):
+                    if v.lower().startswith("active"):
+                        reasons.add(n)
+            except Exception:
+                pass
+        sm.sort()
+        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "power_w_max": max(pw) if pw else None, "samples": len(sm), "reasons": sorted(reasons)}
+
+
+# ------------------------------------------------------------------------------------------------
+def build_env_maps_gpu(ctx, vq, torch, hdri_w=2048, hdri_h=1024, diff_res=64, spec_res=512, spec_mips=9, lut=1024):
+    """IBL inputs of the forward pass, produced by OUR kernels from a synthetic HDRI (setup, untimed)."""
+    from vqengine_b200 import synth
+    levels = vq.mip_level_count(hdri_w, hdri_h)
+    pyr_t = torch.zeros((vq.pyramid_texel_count(hdri_w, hdri_h, levels), 4), dtype=torch.float32, device="cuda")
+    pyr_t[: hdri_w * hdri_h] = torch.from_numpy(synth.hdri(hdri_w, hdri_h)).cuda().reshape(-1, 4)
+    pyr = vq.pyramid_of(pyr_t, hdri_w, hdri_h, levels)
+    ctx.hdri_build_mips(pyr)
+    diff = torch.zeros((6 * diff_res * diff_res, 4), dtype=torch.float32, device="cuda")
+    ctx.diffuse_irradiance(pyr, vq.cubemap_of(diff, diff_res, 1), n_phi=64, n_theta=16, src_mip=3)
+    # per-face Gaussian blur (EnvironmentMapRendering.cpp:279-373)
+    faces = diff.view(6, diff_res, diff_res, 4)
+    tmp = torch.empty_like(faces[0]); blurred = torch.empty_like(faces)
+    for f in range(6):
+        ctx.gaussian_blur(faces[f], tmp, False)
+        ctx.gaussian_blur(tmp, blurred[f], True)
+    spec = torch.zeros((vq.cubemap_texel_count(spec_res, spec_mips), 4), dtype=torch.float32, device="cuda")
+    ctx.specular_prefilter(pyr, vq.cubemap_of(spec, spec_res, spec_mips), 512)
+    lut_t = torch.zeros((lut, lut, 2), dtype=torch.float32, device="cuda")
+    ctx.brdf_integration_lut(lut_t, 2048)
+    torch.cuda.synchronize()
+    keep = dict(pyr_t=pyr_t, pyr=pyr, diff=blurred.reshape(-1, 4).contiguous(), spec=spec, lut=lut_t,
+                diff_res=diff_res, spec_res=spec_res, spec_mips=spec_mips, levels=levels, hdri_w=hdri_w, hdri_h=hdri_h)
+    keep["env"] = vq.EnvironmentMaps(vq.cubemap_of(keep["diff"], diff_res, 1), vq.cubemap_of(spec, spec_res, spec_mips),
+                                     vq.image_of(lut_t, 2))
+    return keep
+
+
+def time_gpu(torch, fn, iters, warmup=3):
+    """median-free simple timing: warmup, then `iters` launches between two CUDA events on the current stream."""
+    for _ in range(warmup):
+        fn()
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(iters):
+        fn()
+    e1.record()
+    torch.cuda.synchronize()
+    return e0.elapsed_time(e1) / iters   # ms
+
+
+def extra_passes(ctx, vq, torch, envk, peak):
+    """Per-kernel numbers for the other SURVEY.md §8 rows (single GPU; not part of `value`)."""
+    from vqengine_b200 import synth
+    out = {}
+    w, h = W4K, H4K
+    px = w * h
+    img = torch.from_numpy(synth.hdr_image(w, h)).cuda()
+    a, b, t, c = (torch.empty_like(img) for _ in range(4))
+    e = torch.empty((2 * h, 2 * w, 4), dtype=torch.float32, device="cuda")
+    r = torch.empty_like(e)
+    (dx, dy), sc = vq.spd_setup(w, h)
+    mips = [torch.empty((h >> l, w >> l, 4), dtype=torch.float32, device="cuda") for l in range(1, sc.mips + 1)]
+    tm = synth.default_tonemapper()
+    cas_c, easu_c, rcas_c = vq.cas_setup(0.8, w, h, w, h), vq.fsr_easu_con(w, h, w, h, 2 * w, 2 * h), vq.fsr_rcas_con(0.2)
+    passes = [
+        ("spd", lambda: ctx.spd_downsample(sc, img, mips), px * (16 + 16 / 3)),
+        ("blur_x", lambda: ctx.gaussian_blur(img, a, False), px * 32),
+        ("blur_y", lambda: ctx.gaussian_blur(a, b, True), px * 32),
+        ("tonemap", lambda: ctx.tonemap(tm, b, t), px * 32),
+        ("cas", lambda: ctx.cas(cas_c, t, c), px * 32),
+        ("fsr_easu_2x", lambda: ctx.fsr_easu(easu_c, c, e), px * 16 + 4 * px * 16),
+        ("fsr_rcas_8k", lambda: ctx.fsr_rcas(rcas_c, e, r), 4 * px * 32),
+    ]
+    chain_ms, chain_bytes = 0.0, 0.0
+    for name, fn, nbytes in passes:
+        ms = time_gpu(torch, fn, 10)
+        gbs = nbytes / ms / 1e6
+        out[name] = {"ms": round(ms, 4), "algorithmic_GBps": round(gbs, 1), "hbm_frac": round(gbs / peak, 3)}
+        chain_ms += ms; chain_bytes += nbytes
+    out["post_chain_4k"] = {"ms": round(chain_ms, 4), "input_Mpixels_per_s": round(px / chain_ms / 1e3, 1),
+                            "algorithmic_GBps": round(chain_bytes / chain_ms / 1e6, 1),
+                            "hbm_frac": round(chain_bytes / chain_ms / 1e6 / peak, 3)}
+    del img, a, b, t, c, e, r, mips
+    # IBL integrals (bound: SFU/FP32 + L1/L2, not HBM; texels/s and samples/s are the honest figures)
+    pyr = envk["pyr"]
+    res, nm = envk["spec_res"], envk["spec_mips"]
+    spec = torch.empty_like(envk["spec"])
+    ms = time_gpu(torch, lambda: ctx.specular_prefilter(pyr, vq.cubemap_of(spec, res, nm), 512), 3, warmup=1)
+    texels = vq.cubemap_texel_count(res, nm)
+    out["ibl_specular_prefilter"] = {"config": f"{envk['hdri_w']}x{envk['hdri_h']} HDRI -> {res}^2 x6 x{nm} mips, 512 samples",
+                                     "ms": round(ms, 3), "texels_per_s": round(texels / ms * 1e3),
+                                     "samples_per_s": round(texels * 512 / ms * 1e3)}
+    diff = torch.empty((6 * 64 * 64, 4), dtype=torch.float32, device="cuda")
+    ms = time_gpu(torch, lambda: ctx.diffuse_irradiance(pyr, vq.cubemap_of(diff, 64, 1), n_phi=64, n_theta=16, src_mip=3), 5, warmup=1)
+    out["ibl_diffuse_irradiance"] = {"config": "2048x1024 HDRI -> 64^2 x6, 64x16 = 1024 samples (BASELINE config 2)",
+                                     "ms": round(ms, 4), "texels_per_s": round(6 * 64 * 64 / ms * 1e3),
+                                     "samples_per_s": round(6 * 64 * 64 * 1024 / ms * 1e3)}
+    ms = time_gpu(torch, lambda: ctx.diffuse_irradiance(pyr, vq.cubemap_of(diff, 64, 1), step=0.01, src_mip=3), 1, warmup=1)
+    out["ibl_diffuse_irradiance_reference_step"] = {"config": "step 0.010 -> 629x158 = 99382 samples/texel (engine default)",
+                                                    "ms": round(ms, 3), "samples_per_s": round(6 * 64 * 64 * 99382 / ms * 1e3)}
+    lut = torch.empty((1024, 1024, 2), dtype=torch.float32, device="cuda")
+    ms = time_gpu(torch, lambda: ctx.brdf_integration_lut(lut, 2048), 2, warmup=1)
+    out["brdf_lut"] = {"config": "1024^2, 2048 samples", "ms": round(ms, 3), "samples_per_s": round(1024 * 1024 * 2048 / ms * 1e3)}
+    ms = time_gpu(torch, lambda: ctx.hdri_build_mips(pyr), 5, warmup=1)
+    nb = envk["hdri_w"] * envk["hdri_h"] * (16 * 4 / 3 + 16 / 3)
+    out["hdri_min_pyramid"] = {"ms": round(ms, 4), "algorithmic_GBps": round(nb / ms / 1e6, 1)}
+    return out
+
+
+# ------------------------------------------------------------------------------------------------
+def cpu_reference_forward(planes, rows_target_s=12.0, env=None, threads=None):
+    """The scalar oracle on `threads` host threads over a bounded row sample of the 4K workload."""
+    import oracle_lib as orc
+    from vqengine_b200 import synth
+    threads = threads or orc.cpu_threads()
+    probe_rows = 16
+    pf, pv = synth.scene_constants(W4K, H4K, env["spec_mips"])
+    args = (env["diff"], env["diff_res"], env["spec"], env["spec_res"], env["spec_mips"], env["lut"])
+    t0 = time.perf_counter()
+    orc.forward_lighting(pf, pv, planes, *args, 0, probe_rows, threads)
+    rate = probe_rows * W4K / (time.perf_counter() - t0)
+    rows = int(min(planes[0].shape[0], max(probe_rows, rows_target_s * rate / W4K)))
+    t0 = time.perf_counter()
+    orc.forward_lighting(pf, pv, planes, *args, 0, rows, threads)
+    dt = time.perf_counter() - t0
+    return {"value": round(rows * W4K / dt / 1e6, 4), "unit": UNIT, "cores": threads, "kind": "port",
+            "sample": f"{rows} of {H4K} rows x {W4K} px of the same 4K G-buffer ({rows * W4K} px in {dt:.1f} s), scalar C++ oracle, std::thread row split"}
+
+
+def cpu_env():
+    """IBL maps for the CPU arm, built by the ORACLE at reduced sizes (the full-size maps would cost the scalar CPU
+    code minutes; map size does not change the per-pixel work of the forward pass)."""
+    from envmaps import small_env
+    return small_env(hdri_w=256, hdri_h=128, diff_res=16, spec_res=64, spec_mips=6, lut=64, seed=77)
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    import oracle_lib as orc
+    from vqengine_b200 import synth
+    env = cpu_env()
+    threads = orc.cpu_threads()
+    planes = synth.gbuffer(W4K, 512, seed=synth.SEED_BASE + 3)   # a 512-row band of the 4K G-buffer
+    pf, pv = synth.scene_constants(W4K, H4K, env["spec_mips"])
+    a = (env["diff"], env["diff_res"], env["spec"], env["spec_res"], env["spec_mips"], env["lut"])
+    # bounded sample: size the per-step row count so that warmup+steps take about a minute in total
+    t0 = time.perf_counter()
+    orc.forward_lighting(pf, pv, planes, *a, 0, 16, threads)
+    rate = 16 * W4K / (time.perf_counter() - t0)
+    rows = int(min(512, max(16, 60.0 * rate / W4K / (args.steps + args.warmup))))
+    for _ in range(args.warmup):
+        orc.forward_lighting(pf, pv, planes, *a, 0, rows, threads)
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        orc.forward_lighting(pf, pv, planes, *a, 0, rows, threads)
+    dt = (time.perf_counter() - t0) / args.steps
+    v = rows * W4K / dt / 1e6
+    sample = f"each step = {rows} rows x {W4K} px of the 4K G-buffer through the scalar C++ oracle on {threads} host threads"
+    print(json.dumps({"impl": "reference", "metric": METRIC, "value": round(v, 4), "unit": UNIT, "n_gpus": args.gpus,
+                      "steps": args.steps, "warmup": args.warmup, "ms_per_step": round(dt * 1e3, 3),
+                      "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+                      "config": {"workload": WORKLOAD, "note": "the reference's D3D12/HLSL path needs Windows; this arm is the CPU port (oracle) of the identical math"},
+                      "cpu_baseline": {"value": round(v, 4), "unit": UNIT, "cores": threads, "kind": "port", "sample": sample},
+                      "e2e": {"value": round(v, 4), "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+                      "gpu_launches": 0}))
+
+
+# ------------------------------------------------------------------------------------------------
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=50)
+    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--no-extra", action="store_true", help="skip the per-kernel extra section")
+    ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
+    args = ap.parse_args()
+    args.warmup = max(args.warmup, 3)
+    if args.impl == "reference":
+        return run_reference(args)
+
+    import numpy as np
+    import torch
+    import vqengine_b200 as vq
+    from vqengine_b200 import synth
+
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    assert torch.cuda.is_available(), "bench.py needs a CUDA device: the product has no CPU path"
+    torch.cuda.set_device(local)
+    dist = None
+    if world > 1:
+        import torch.distributed as dist
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    peak, peak_src = hbm_peak()
+    ctx = vq.Context(local)
+    envk = build_env_maps_gpu(ctx, vq, torch)
+
+    # this rank's row tile of the 3840 x (2160*world) frame: weak scaling, fixed work per GPU
+    planes = synth.gbuffer(W4K, H4K, seed=synth.SEED_BASE + 3 + rank)
+    pf, pv = synth.scene_constants(W4K, H4K, envk["spec_mips"])
+    dpl = [torch.from_numpy(p).cuda() for p in planes]
+    gb = vq.GBuffer(vq.image_of(dpl[0]), vq.image_of(dpl[1]), vq.image_of(dpl[2]), vq.null_image())
+    out = torch.zeros((H4K, W4K, 4), dtype=torch.float32, device="cuda")
+    step = lambda: ctx.forward_lighting(pf, pv, gb, envk["env"], out)
+
+    launches0 = vq.launch_count()
+    for _ in range(args.warmup):
+        step()
+    torch.cuda.synchronize()
+    if dist: dist.barrier()
+    torch.cuda.synchronize()
+    sampler = ClockSampler(local); sampler.start()
+    time.sleep(0.15)
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    lt0 = vq.launch_count()
+    e0.record()
+    for _ in range(args.steps):
+        step()
+    e1.record()
+    torch.cuda.synchronize()
+    if dist: dist.barrier()
+    torch.cuda.synchronize()
+    timed_launches = vq.launch_count() - lt0
+    ms_total = e0.elapsed_time(e1)
+    # keep the GPU busy a little longer so that the clock sampler sees the load even for short runs
+    t_end = time.time() + 0.4
+    while time.time() < t_end:
+        step()
+    torch.cuda.synchronize()
+    clocks = sampler.stop()
+    t = torch.tensor([ms_total], dtype=torch.float64, device="cuda")
+    if dist: dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    ms_step = float(t.item()) / args.steps
+    px_all = W4K * H4K * world
+    value = px_all / ms_step / 1e3   # Mpixels/s
+
+    # ---- e2e: the blocking host-buffer call, pinned host memory, H2D + D2H inside the timed region ----
+    hpl = [torch.from_numpy(p).pin_memory() for p in planes]
+    hgb = vq.GBuffer(vq.image_of(hpl[0]), vq.image_of(hpl[1]), vq.image_of(hpl[2]), vq.null_image())
+    hout = torch.zeros((H4K, W4K, 4), dtype=torch.float32).pin_memory()
+    ctx.resize(W4K, H4K)
+    e2e_steps = max(3, min(args.steps, 10))
+    for _ in range(2):
+        ctx.forward_lighting_host(pf, pv, hgb, envk["env"], hout)
+    torch.cuda.synchronize()
+    if dist: dist.barrier()
+    t0 = time.perf_counter()
+    for _ in range(e2e_steps):
+        ctx.forward_lighting_host(pf, pv, hgb, envk["env"], hout)
+    torch.cuda.synchronize()
+    dt = (time.perf_counter() - t0) / e2e_steps
+    t = torch.tensor([dt], dtype=torch.float64, device="cuda")
+    if dist: dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    e2e_val = px_all / float(t.item()) / 1e6
+    assert torch.equal(hout.cuda(), out), "host-buffer path and device path disagree"
+    h2d, d2h = 3 * W4K * H4K * 16, W4K * H4K * 16
+
+    # ---- multi-GPU: one all-gather of the shaded tiles over NVLink (reported separately) ----
+    gather = None
+    if dist:
+        full = torch.empty((world * H4K, W4K, 4), dtype=torch.float32, device="cuda")
+        for _ in range(2):
+            dist.all_gather_into_tensor(full, out)
+        torch.cuda.synchronize(); dist.barrier(); torch.cuda.synchronize()
+        g0, g1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        g0.record()
+        for _ in range(5):
+            step()
+            dist.all_gather_into_tensor(full, out)
+        g1.record(); torch.cuda.synchronize()
+        tg = torch.tensor([g0.elapsed_time(g1) / 5], dtype=torch.float64, device="cuda")
+        dist.all_reduce(tg, op=dist.ReduceOp.MAX)
+        gather = {"ms_per_step_with_allgather": round(float(tg.item()), 4),
+                  "value_with_allgather": round(px_all / float(tg.item()) / 1e3, 1),
+                  "allgather_bytes_per_rank_in": (world - 1) * H4K * W4K * 16}
+        del full
+
+    line = None
+    if rank == 0:
+        achieved = BYTES_PER_PX * W4K * H4K / (ms_step * 1e-3) / 1e9   # per-GPU GB/s of the dominant (only) kernel
+        traffic = None
+        tp = os.path.join(ROOT, "profiles", "forward_traffic.json")
+        if os.path.exists(tp):
+            try: traffic = json.load(open(tp)).get("dram_bytes_per_launch")
+            except Exception: pass
+        line = {"metric": METRIC, "value": round(value, 1), "unit": UNIT, "n_gpus": world, "steps": args.steps,
+                "warmup": args.warmup, "ms_per_step": round(ms_step, 5), "higher_is_better": True, "scaling": "weak",
+                "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+                "config": {"workload": WORKLOAD, "tile_per_gpu": f"{W4K}x{H4K}", "frame": f"{W4K}x{H4K * world}",
+                           "parallelism": f"row-tiles x{world}", "l2_policy": "inputs (398 MB) + output (133 MB) per step exceed the 126 MB L2; no flush needed"},
+                "roofline": {"bound": "hbm", "kernel": "forward_kernel", "achieved": round(achieved, 1), "peak": peak, "unit": "GB/s",
+                             "frac": round(achieved / peak, 4), "traffic": traffic, "peak_source": peak_src,
+                             "algorithmic_bytes_per_launch": BYTES_PER_PX * W4K * H4K},
+                "e2e": {"value": round(e2e_val, 1), "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
+                        "api": "vq_forward_lighting_host (pinned host buffers, 16 row chunks pipelined over 3 streams)"},
+                "gpu_launches": int(timed_launches), "clocks": clocks}
+        if gather: line["allgather"] = gather
+    if world == 1 and rank == 0:
+        del hpl, hout
+        if not args.no_extra:
+            line["extra"] = extra_passes(ctx, vq, torch, envk, peak)
+        if not args.no_cpu:
+            line["cpu_baseline"] = cpu_reference_forward(planes, env=cpu_env())
+    if rank == 0:
+        print(json.dumps(line))
+    if dist:
+        dist.barrier()
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

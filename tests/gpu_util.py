@@ -1,0 +1,37 @@
+"""Helpers shared by the -m gpu parity tests."""
+import numpy as np
+import torch
+
+TOL = 1e-4   # BASELINE.json north_star: |delta| <= 1e-4 per channel (fp32)
+
+
+def dev(a: np.ndarray) -> torch.Tensor:
+    return torch.from_numpy(np.ascontiguousarray(a, dtype=np.float32)).cuda()
+
+
+def host(t: torch.Tensor) -> np.ndarray:
+    torch.cuda.synchronize()
+    return t.detach().cpu().numpy()
+
+
+def report(name, got, ref):
+    d = np.abs(got.astype(np.float64) - ref.astype(np.float64))
+    scale = np.maximum(1.0, np.abs(ref.astype(np.float64)))
+    return {"name": name, "max_abs": float(d.max()), "max_scaled": float((d / scale).max()),
+            "frac_abs_le_tol": float((d <= TOL).mean()), "ref_max": float(np.abs(ref).max())}
+
+
+def assert_abs(name, got, ref, tol=TOL):
+    """strict: |delta| <= tol per channel"""
+    r = report(name, got, ref)
+    assert np.isfinite(got).all(), f"{name}: non-finite output"
+    assert r["max_abs"] <= tol, f"{name}: max |delta| = {r['max_abs']:.3e} > {tol} ({r})"
+    return r
+
+
+def assert_scaled(name, got, ref, tol=TOL):
+    """HDR outputs: |delta| <= tol * max(1, |ref|)  (fp32 cannot hold an absolute 1e-4 above ~1e3)"""
+    r = report(name, got, ref)
+    assert np.isfinite(got).all(), f"{name}: non-finite output"
+    assert r["max_scaled"] <= tol, f"{name}: max scaled |delta| = {r['max_scaled']:.3e} > {tol} ({r})"
+    return r

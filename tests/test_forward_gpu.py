@@ -1,0 +1,119 @@
+"""-m gpu parity: K1 forward PBR lighting against the scalar oracle, through the C-ABI."""
+import ctypes as C
+
+import numpy as np
+import pytest
+import torch
+
+from gpu_util import dev, host, assert_scaled, report, TOL
+from envmaps import small_env
+
+pytestmark = pytest.mark.gpu
+
+
+def _run(ctx, vq, orc, w, h, *, n_point=4, n_spot=0, directional=True, emissive=False, offset=0.0, casters=False,
+         diffuse_only=False, point_range=50.0, seed=3, rows=None):
+    from vqengine_b200 import synth
+    env = small_env()
+    planes = synth.gbuffer(w, h, seed=seed, emissive=emissive)
+    pf, pv = synth.scene_constants(w, h, env["spec_mips"], seed=seed, n_point=n_point, n_spot=n_spot,
+                                   directional=directional, hdri_offset=offset, casters=casters, point_range=point_range)
+    pv.EnvironmentMapDiffuseOnlyIllumination = int(diffuse_only)
+    dplanes = [dev(p) for p in planes]
+    gb = vq.GBuffer(vq.image_of(dplanes[0]), vq.image_of(dplanes[1]), vq.image_of(dplanes[2]),
+                    vq.image_of(dplanes[3]) if emissive else vq.null_image())
+    dd, ds, dl = dev(env["diff"]), dev(env["spec"]), dev(env["lut"])
+    em = vq.EnvironmentMaps(vq.cubemap_of(dd, env["diff_res"], 1), vq.cubemap_of(ds, env["spec_res"], env["spec_mips"]),
+                            vq.image_of(dl, 2))
+    out = torch.zeros((h, w, 4), dtype=torch.float32, device="cuda")
+    rb, re = rows if rows else (0, h)
+    ctx.forward_lighting(pf, pv, gb, em, out, rb, re)
+    ref = orc.forward_lighting(pf, pv, planes, env["diff"], env["diff_res"], env["spec"], env["spec_res"],
+                               env["spec_mips"], env["lut"], rb, re)
+    return host(out), ref
+
+
+@pytest.mark.parametrize("w,h", [(64, 36), (1, 1), (257, 3), (480, 270)])
+def test_forward_config3_shape(ctx, vq, orc, w, h):
+    """4 point + 1 directional + IBL (BASELINE config 3 lighting) at small sizes."""
+    got, ref = _run(ctx, vq, orc, w, h)
+    r = assert_scaled(f"forward{w}x{h}", got, ref)
+    assert (got[..., 3] == ref[..., 3]).all()      # alpha = roughness passthrough
+    print(r)
+
+
+def test_forward_all_light_types(ctx, vq, orc):
+    got, ref = _run(ctx, vq, orc, 160, 90, n_point=7, n_spot=3, emissive=True, offset=0.7, casters=True)
+    assert_scaled("forward_all", got, ref)
+
+
+def test_forward_no_lights_ibl_only(ctx, vq, orc):
+    got, ref = _run(ctx, vq, orc, 96, 54, n_point=0, directional=False)
+    assert_scaled("forward_ibl", got, ref)
+
+
+def test_forward_diffuse_only_flag(ctx, vq, orc):
+    got, ref = _run(ctx, vq, orc, 96, 54, diffuse_only=True)
+    assert_scaled("forward_diffonly", got, ref)
+
+
+def test_forward_range_cut(ctx, vq, orc):
+    """`D < l.range` is a discontinuity: a range that cuts through the field must give the same mask."""
+    got, ref = _run(ctx, vq, orc, 320, 180, point_range=14.0, directional=False)
+    assert_scaled("forward_range", got, ref)
+
+
+def test_forward_max_lights(ctx, vq, orc):
+    got, ref = _run(ctx, vq, orc, 48, 27, n_point=100, n_spot=20)
+    assert_scaled("forward_maxlights", got, ref)
+
+
+def test_forward_row_tiles(ctx, vq, orc):
+    """rows [a,b) only: untouched rows stay zero, touched rows equal the full-frame result."""
+    full, _ = _run(ctx, vq, orc, 64, 40)
+    part, ref = _run(ctx, vq, orc, 64, 40, rows=(13, 29))
+    assert np.array_equal(part[13:29], full[13:29])
+    assert (part[:13] == 0).all() and (part[29:] == 0).all()
+
+
+def test_single_pixel_kat(ctx, vq):
+    """BASELINE config 1 / SURVEY.md §8(c): N=V=Wi=(0,0,1), albedo .5, rough .5, metal 0, white point light
+    at distance 2, brightness 10 -> 0.50927037 per channel (ambient 0, IBL maps = 0)."""
+    pf = vq.PerFrameData(); pv = vq.PerViewLightingData()
+    pf.Lights.numPointLights = 1
+    l = pf.Lights.point_lights[0]
+    l.position.z = 2.0; l.range = 100.0; l.brightness = 10.0
+    l.color.x = l.color.y = l.color.z = 1.0
+    pv.CameraPosition.z = 5.0; pv.MaxEnvMapLODLevels = 2.0
+    pos = dev(np.array([[[0, 0, 0, 0]]], np.float32)); nrm = dev(np.array([[[0, 0, 1, 0.5]]], np.float32))
+    alb = dev(np.array([[[0.5, 0.5, 0.5, 0.0]]], np.float32))
+    zeros_d = torch.zeros((6 * 4, 4), device="cuda"); zeros_s = torch.zeros((6 * 4 + 6, 4), device="cuda")
+    lut = torch.zeros((2, 2, 2), device="cuda")
+    gb = vq.GBuffer(vq.image_of(pos), vq.image_of(nrm), vq.image_of(alb), vq.null_image())
+    em = vq.EnvironmentMaps(vq.cubemap_of(zeros_d, 2, 1), vq.cubemap_of(zeros_s, 2, 2), vq.image_of(lut, 2))
+    out = torch.zeros((1, 1, 4), device="cuda")
+    ctx.forward_lighting(pf, pv, gb, em, out)
+    o = host(out)[0, 0]
+    assert np.allclose(o[:3], 0.50927037, atol=3e-7), o
+    assert o[3] == 0.5
+
+
+def test_forward_host_entry(ctx, vq, orc):
+    """the blocking host-buffer call (uploads, shades, downloads) equals the device call."""
+    from vqengine_b200 import synth
+    env = small_env()
+    w, h = 200, 300
+    planes = synth.gbuffer(w, h, seed=8)
+    pf, pv = synth.scene_constants(w, h, env["spec_mips"], seed=8)
+    hp = [torch.from_numpy(p).pin_memory() for p in planes]
+    gbh = vq.GBuffer(vq.image_of(hp[0]), vq.image_of(hp[1]), vq.image_of(hp[2]), vq.null_image())
+    dd, ds, dl = dev(env["diff"]), dev(env["spec"]), dev(env["lut"])
+    em = vq.EnvironmentMaps(vq.cubemap_of(dd, env["diff_res"], 1), vq.cubemap_of(ds, env["spec_res"], env["spec_mips"]),
+                            vq.image_of(dl, 2))
+    hout = torch.zeros((h, w, 4), dtype=torch.float32).pin_memory()
+    ctx.forward_lighting_host(pf, pv, gbh, em, hout)
+    dplanes = [dev(p) for p in planes]
+    gb = vq.GBuffer(vq.image_of(dplanes[0]), vq.image_of(dplanes[1]), vq.image_of(dplanes[2]), vq.null_image())
+    out = torch.zeros((h, w, 4), dtype=torch.float32, device="cuda")
+    ctx.forward_lighting(pf, pv, gb, em, out)
+    assert np.array_equal(hout.numpy(), host(out))

@@ -1,0 +1,118 @@
+"""-m gpu parity: environment-map kernels (K11, K2, K3, K4) against the scalar oracle, through the C-ABI."""
+import numpy as np
+import pytest
+import torch
+
+from gpu_util import dev, host, assert_abs, report
+
+pytestmark = pytest.mark.gpu
+
+
+def _pyr(ctx, vq, orc, w, h, seed=2, const=None):
+    from vqengine_b200 import synth
+    img = synth.hdri(w, h, seed=seed) if const is None else np.tile(np.array(const + [1.0], np.float32), (h, w, 1))
+    levels = vq.mip_level_count(w, h)
+    n = vq.pyramid_texel_count(w, h, levels)
+    d = torch.zeros((n, 4), dtype=torch.float32, device="cuda")
+    d[: w * h] = dev(img).reshape(-1, 4)
+    p = vq.pyramid_of(d, w, h, levels)
+    ctx.hdri_build_mips(p)
+    return img, levels, d, p
+
+
+@pytest.mark.parametrize("w,h", [(128, 64), (256, 256), (96, 40), (2, 1), (2048, 1024)])
+def test_hdri_min_pyramid(ctx, vq, orc, w, h):
+    img, levels, d, _ = _pyr(ctx, vq, orc, w, h)
+    ref = orc.hdri_build_mips(img, levels)
+    assert levels == orc.lib().orc_mip_level_count(w, h)
+    assert np.array_equal(host(d), ref)          # min filter: bit-exact
+
+
+@pytest.mark.parametrize("res,kw", [(16, dict(n_phi=64, n_theta=16, src_mip=3)), (8, dict(step=0.05, src_mip=1)),
+                                    (4, dict(step=0.025, src_mip=0)), (32, dict(n_phi=16, n_theta=8, src_mip=2))])
+def test_diffuse_irradiance(ctx, vq, orc, res, kw):
+    w, h = 256, 128
+    img, levels, d, p = _pyr(ctx, vq, orc, w, h)
+    out = torch.zeros((6 * res * res, 4), dtype=torch.float32, device="cuda")
+    ctx.diffuse_irradiance(p, vq.cubemap_of(out, res, 1), **kw)
+    ref = orc.diffuse_irradiance(host(d), w, h, levels, res, **kw)
+    print(assert_abs(f"diffuse{res}", host(out), ref))
+
+
+def test_diffuse_irradiance_reference_step_constant(ctx, vq, orc):
+    """constant radiance L, reference step 0.010 (629 x 158 samples): pi*mean(cos sin)*L ~= 0.99415 L."""
+    w, h = 64, 32
+    _, levels, d, p = _pyr(ctx, vq, orc, w, h, const=[2.0, 1.0, 0.5])
+    res = 4
+    out = torch.zeros((6 * res * res, 4), dtype=torch.float32, device="cuda")
+    ctx.diffuse_irradiance(p, vq.cubemap_of(out, res, 1), step=0.01, src_mip=3)
+    o = host(out)
+    assert np.allclose(o[:, 0] / 2.0, 0.99415, atol=2e-4) and np.allclose(o[:, 2] / 0.5, 0.99415, atol=2e-4)
+    assert (o[:, 3] == 1.0).all()
+    ref = orc.diffuse_irradiance(host(d), w, h, levels, res, step=0.01, src_mip=3)
+    assert_abs("diffuse_ref_step", o, ref)
+
+
+def test_diffuse_row_ranges(ctx, vq, orc):
+    w, h, res = 128, 64, 8
+    _, levels, d, p = _pyr(ctx, vq, orc, w, h)
+    full = torch.zeros((6 * res * res, 4), device="cuda"); parts = torch.zeros_like(full)
+    ctx.diffuse_irradiance(p, vq.cubemap_of(full, res, 1), src_mip=2)
+    for a, b in [(0, 5), (5, 6), (6, 31), (31, 48)]:
+        ctx.diffuse_irradiance(p, vq.cubemap_of(parts, res, 1), src_mip=2, row_begin=a, row_end=b)
+    assert np.array_equal(host(full), host(parts))
+
+
+@pytest.mark.parametrize("res,mips,samples", [(32, 5, 512), (16, 4, 64), (64, 7, 512)])
+def test_specular_prefilter(ctx, vq, orc, res, mips, samples):
+    w, h = 256, 128
+    img, levels, d, p = _pyr(ctx, vq, orc, w, h)
+    out = torch.zeros((vq.cubemap_texel_count(res, mips), 4), dtype=torch.float32, device="cuda")
+    ctx.specular_prefilter(p, vq.cubemap_of(out, res, mips), num_samples=samples)
+    ref = orc.specular_prefilter(host(d), w, h, levels, res, mips, num_samples=samples)
+    r = report("spec", host(out), ref)
+    print(r)
+    for m in range(mips):
+        a, b = vq.cubemap_offset(res, m, 0), vq.cubemap_offset(res, m, 0) + 6 * (res >> m) ** 2
+        print(m, report(f"mip{m}", host(out)[a:b], ref[a:b]))
+    assert_abs(f"spec{res}", host(out), ref)
+
+
+def test_specular_constant_radiance(ctx, vq, orc):
+    """constant-radiance HDRI: the prefilter is a normalised weighted mean -> exactly L."""
+    w, h = 64, 32
+    _, levels, d, p = _pyr(ctx, vq, orc, w, h, const=[3.0, 0.25, 1.5])
+    res, mips = 16, 4
+    out = torch.zeros((vq.cubemap_texel_count(res, mips), 4), device="cuda")
+    ctx.specular_prefilter(p, vq.cubemap_of(out, res, mips))
+    o = host(out)
+    assert np.allclose(o[:, :3], [3.0, 0.25, 1.5], rtol=2e-6) and (o[:, 3] == 1.0).all()
+
+
+def test_specular_row_ranges(ctx, vq, orc):
+    w, h, res, mips = 128, 64, 16, 4
+    _, levels, d, p = _pyr(ctx, vq, orc, w, h)
+    n = vq.cubemap_texel_count(res, mips)
+    full = torch.zeros((n, 4), device="cuda"); parts = torch.zeros_like(full)
+    ctx.specular_prefilter(p, vq.cubemap_of(full, res, mips), 128)
+    total = vq.cubemap_row_count(res, mips)
+    cuts = [0, 7, 96, 97, 150, total]
+    for a, b in zip(cuts[:-1], cuts[1:]):
+        ctx.specular_prefilter(p, vq.cubemap_of(parts, res, mips), 128, a, b)
+    assert np.array_equal(host(full), host(parts))
+
+
+@pytest.mark.parametrize("w,h,samples", [(64, 64, 2048), (33, 17, 256)])
+def test_brdf_lut(ctx, vq, orc, w, h, samples):
+    out = torch.zeros((h, w, 2), dtype=torch.float32, device="cuda")
+    ctx.brdf_integration_lut(out, samples)
+    ref = orc.brdf_integration_lut(w, h, samples)
+    print(assert_abs("lut", host(out), ref))
+
+
+def test_brdf_lut_sanity_corner(ctx, vq):
+    """roughness -> 0, NdotV -> 1 => (scale, bias) -> (~1, ~0)"""
+    out = torch.zeros((256, 256, 2), device="cuda")
+    ctx.brdf_integration_lut(out, 512)
+    o = host(out)
+    assert abs(o[0, 255, 0] - 1.0) < 0.02 and abs(o[0, 255, 1]) < 0.02

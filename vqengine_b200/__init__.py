@@ -1,0 +1,365 @@
+"""vqengine_b200 — B200 (sm_100a) headless shading backend for VQEngine's per-pixel passes.
+
+The product is the C-ABI shared library ``libvqcuda.so`` (include/vqcuda.h), built in-tree from
+``vqengine_b200/csrc`` by ``__graft_entry__.build()``. This Python package is only the thin ctypes
+driver used by the tests and ``bench.py``: it mirrors the C structs, loads the library and turns
+torch CUDA tensors into the ``{ptr, width, height, pitch}`` descriptors the ABI takes. torch is used
+for device memory, streams and torch.distributed — plumbing, not compute.
+
+There is NO CPU fallback: importing works without a GPU (so symbols/struct layouts can be checked),
+but every device call fails with VQ_ERR_NO_DEVICE, and a missing library raises ImportError.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "libvqcuda.so")
+
+VQ_OK = 0
+VQ_ERR_INVALID_ARG = -1
+VQ_ERR_CUDA = -2
+VQ_ERR_UNSUPPORTED = -3
+VQ_ERR_NO_DEVICE = -4
+VQ_ERR_OUT_OF_MEMORY = -5
+
+VQ_ADDRESS_WRAP, VQ_ADDRESS_CLAMP = 0, 1
+COLOR_SPACE_REC_709, COLOR_SPACE_REC_2020 = 0, 1
+DISPLAY_CURVE_SRGB, DISPLAY_CURVE_ST2084, DISPLAY_CURVE_LINEAR = 0, 1, 2
+
+f32 = C.c_float
+i32 = C.c_int32
+u32 = C.c_uint32
+
+
+# ---- include/vq_shader_data.h ---------------------------------------------------------------
+class Float2(C.Structure):
+    _fields_ = [("x", f32), ("y", f32)]
+
+
+class Float3(C.Structure):
+    _fields_ = [("x", f32), ("y", f32), ("z", f32)]
+
+
+class Float4(C.Structure):
+    _fields_ = [("x", f32), ("y", f32), ("z", f32), ("w", f32)]
+
+
+class Matrix(C.Structure):
+    _fields_ = [("m", f32 * 16)]
+
+
+class PointLight(C.Structure):
+    _fields_ = [("position", Float3), ("range", f32), ("color", Float3), ("brightness", f32),
+                ("attenuation", Float3), ("depthBias", f32)]
+
+
+class SpotLight(C.Structure):
+    _fields_ = [("position", Float3), ("outerConeAngle", f32), ("color", Float3), ("brightness", f32),
+                ("spotDir", Float3), ("depthBias", f32), ("innerConeAngle", f32), ("range", f32),
+                ("dummy1", f32), ("dummy2", f32)]
+
+
+class DirectionalLight(C.Structure):
+    _fields_ = [("lightDirection", Float3), ("brightness", f32), ("color", Float3), ("depthBias", f32),
+                ("shadowing", i32), ("enabled", i32)]
+
+
+class SceneLighting(C.Structure):
+    _fields_ = [("numPointLights", i32), ("numSpotLights", i32), ("numPointCasters", i32), ("numSpotCasters", i32),
+                ("directional", DirectionalLight), ("_pad_matrix_align", u32 * 2),
+                ("shadowViewDirectional", Matrix),
+                ("point_lights", PointLight * 100), ("point_casters", PointLight * 5),
+                ("spot_lights", SpotLight * 20), ("spot_casters", SpotLight * 5),
+                ("shadowViews", Matrix * 5)]
+
+
+class PerFrameData(C.Structure):
+    _fields_ = [("Lights", SceneLighting),
+                ("f2PointLightShadowMapDimensions", Float2), ("f2SpotLightShadowMapDimensions", Float2),
+                ("f2DirectionalLightShadowMapDimensions", Float2),
+                ("fAmbientLightingFactor", f32), ("fHDRIOffsetInRadians", f32)]
+
+
+class PerViewLightingData(C.Structure):
+    _fields_ = [("matView", Matrix), ("matViewToWorld", Matrix), ("matProjInverse", Matrix),
+                ("WorldFrustumPlanes", Float4 * 6), ("CameraPosition", Float3), ("MaxEnvMapLODLevels", f32),
+                ("ScreenDimensions", Float2), ("EnvironmentMapDiffuseOnlyIllumination", i32), ("pad1", f32)]
+
+
+class TonemapperParams(C.Structure):
+    _fields_ = [("ContentColorSpace", i32), ("OutputDisplayCurve", i32),
+                ("DisplayReferenceBrightnessLevel", f32), ("ToggleGammaCorrection", i32), ("UIHDRBrightness", f32)]
+
+
+class BlurParams(C.Structure):
+    _fields_ = [("iImageSizeX", i32), ("iImageSizeY", i32)]
+
+
+class SpdConstants(C.Structure):
+    _fields_ = [("mips", u32), ("numWorkGroups", u32), ("workGroupOffset", u32 * 2)]
+
+
+class DiffuseIrradianceParams(C.Structure):
+    _fields_ = [("step", f32), ("n_phi", i32), ("n_theta", i32), ("src_mip", i32)]
+
+
+assert C.sizeof(PointLight) == 48 and C.sizeof(SpotLight) == 64 and C.sizeof(DirectionalLight) == 40
+assert C.sizeof(SceneLighting) == 7088 and C.sizeof(PerFrameData) == 7120 and C.sizeof(PerViewLightingData) == 320
+
+
+# ---- include/vqcuda.h -----------------------------------------------------------------------
+class Image(C.Structure):
+    _fields_ = [("ptr", C.c_void_p), ("width", i32), ("height", i32), ("pitch_bytes", C.c_size_t)]
+
+
+class Cubemap(C.Structure):
+    _fields_ = [("ptr", C.c_void_p), ("res", i32), ("mips", i32)]
+
+
+class Pyramid(C.Structure):
+    _fields_ = [("ptr", C.c_void_p), ("width", i32), ("height", i32), ("levels", i32)]
+
+
+class GBuffer(C.Structure):
+    _fields_ = [("position_ao", Image), ("normal_roughness", Image), ("albedo_metalness", Image), ("emissive", Image)]
+
+
+class EnvironmentMaps(C.Structure):
+    _fields_ = [("irradiance_diffuse", Cubemap), ("irradiance_specular", Cubemap), ("brdf_lut", Image)]
+
+
+# every symbol include/vqcuda.h declares (tests/test_abi.py checks the library exports all of them)
+ABI_SYMBOLS = [
+    "vq_ctx_create", "vq_ctx_destroy", "vq_ctx_resize", "vq_last_error", "vq_version", "vq_launch_count",
+    "vq_forward_lighting", "vq_hdri_build_mips", "vq_diffuse_irradiance", "vq_specular_prefilter",
+    "vq_brdf_integration_lut", "vq_gaussian_blur_x", "vq_gaussian_blur_y", "vq_tonemap", "vq_cas",
+    "vq_fsr_easu", "vq_fsr_rcas", "vq_spd_downsample", "vq_fsr_easu_con", "vq_fsr_rcas_con", "vq_cas_setup",
+    "vq_spd_setup", "vq_mip_level_count", "vq_cubemap_texel_count", "vq_cubemap_offset", "vq_cubemap_row_count",
+    "vq_pyramid_texel_count", "vq_pyramid_offset", "vq_forward_lighting_host",
+]
+
+
+class VqError(RuntimeError):
+    def __init__(self, code: int, msg: str):
+        super().__init__(f"vqcuda error {code}: {msg}")
+        self.code = code
+
+
+def _load() -> C.CDLL:
+    if not os.path.exists(LIB_PATH):
+        raise ImportError(
+            f"{LIB_PATH} is missing: build it with `python -c 'import __graft_entry__ as g; g.build()'` "
+            "(nvcc, sm_100a). There is no CPU fallback.")
+    lib = C.CDLL(LIB_PATH)
+    vp = C.c_void_p
+    P = C.POINTER
+    lib.vq_ctx_create.argtypes = [C.c_int, P(vp)]
+    lib.vq_ctx_destroy.argtypes = [vp]
+    lib.vq_ctx_resize.argtypes = [vp, C.c_int, C.c_int]
+    lib.vq_last_error.restype = C.c_char_p
+    lib.vq_version.restype = C.c_char_p
+    lib.vq_launch_count.restype = C.c_uint64
+    lib.vq_forward_lighting.argtypes = [vp, P(PerFrameData), P(PerViewLightingData), P(GBuffer), P(EnvironmentMaps),
+                                        Image, C.c_int, C.c_int, vp]
+    lib.vq_forward_lighting_host.argtypes = [vp, P(PerFrameData), P(PerViewLightingData), P(GBuffer),
+                                             P(EnvironmentMaps), Image]
+    lib.vq_hdri_build_mips.argtypes = [vp, Pyramid, vp]
+    lib.vq_diffuse_irradiance.argtypes = [vp, P(DiffuseIrradianceParams), Pyramid, Cubemap, C.c_int, C.c_int, vp]
+    lib.vq_specular_prefilter.argtypes = [vp, Pyramid, Cubemap, C.c_int, C.c_int, C.c_int, vp]
+    lib.vq_brdf_integration_lut.argtypes = [vp, Image, C.c_int, C.c_int, C.c_int, vp]
+    lib.vq_gaussian_blur_x.argtypes = [vp, P(BlurParams), Image, Image, vp]
+    lib.vq_gaussian_blur_y.argtypes = [vp, P(BlurParams), Image, Image, vp]
+    lib.vq_tonemap.argtypes = [vp, P(TonemapperParams), Image, Image, vp]
+    lib.vq_cas.argtypes = [vp, P(u32), Image, Image, vp]
+    lib.vq_fsr_easu.argtypes = [vp, P(u32), C.c_int, Image, Image, vp]
+    lib.vq_fsr_rcas.argtypes = [vp, P(u32), Image, Image, vp]
+    lib.vq_spd_downsample.argtypes = [vp, P(SpdConstants), Image, P(Image), vp]
+    lib.vq_fsr_easu_con.argtypes = [P(u32), f32, f32, f32, f32, f32, f32]
+    lib.vq_fsr_easu_con.restype = None
+    lib.vq_fsr_rcas_con.argtypes = [P(u32), f32]
+    lib.vq_fsr_rcas_con.restype = None
+    lib.vq_cas_setup.argtypes = [P(u32), f32, f32, f32, f32, f32]
+    lib.vq_cas_setup.restype = None
+    lib.vq_spd_setup.argtypes = [P(u32), P(SpdConstants), P(u32), C.c_int]
+    lib.vq_spd_setup.restype = None
+    lib.vq_mip_level_count.argtypes = [C.c_uint64, C.c_uint64]
+    lib.vq_cubemap_texel_count.argtypes = [C.c_int, C.c_int]
+    lib.vq_cubemap_texel_count.restype = C.c_uint64
+    lib.vq_cubemap_offset.argtypes = [C.c_int, C.c_int, C.c_int]
+    lib.vq_cubemap_offset.restype = C.c_uint64
+    lib.vq_cubemap_row_count.argtypes = [C.c_int, C.c_int]
+    lib.vq_pyramid_texel_count.argtypes = [C.c_int, C.c_int, C.c_int]
+    lib.vq_pyramid_texel_count.restype = C.c_uint64
+    lib.vq_pyramid_offset.argtypes = [C.c_int, C.c_int, C.c_int]
+    lib.vq_pyramid_offset.restype = C.c_uint64
+    return lib
+
+
+lib = _load()
+
+
+def _check(rc: int) -> None:
+    if rc != VQ_OK:
+        raise VqError(rc, (lib.vq_last_error() or b"").decode())
+
+
+# ---- host-side helpers (no GPU needed) ---------------------------------------------------------
+def fsr_easu_con(vp_w, vp_h, in_w, in_h, out_w, out_h):
+    con = (u32 * 16)()
+    lib.vq_fsr_easu_con(con, vp_w, vp_h, in_w, in_h, out_w, out_h)
+    return con
+
+
+def fsr_rcas_con(stops: float):
+    con = (u32 * 4)()
+    lib.vq_fsr_rcas_con(con, stops)
+    return con
+
+
+def cas_setup(sharpness, in_w, in_h, out_w, out_h):
+    con = (u32 * 8)()
+    lib.vq_cas_setup(con, sharpness, in_w, in_h, out_w, out_h)
+    return con
+
+
+def spd_setup(width: int, height: int, mips: int = -1, left: int = 0, top: int = 0):
+    d = (u32 * 2)()
+    c = SpdConstants()
+    rect = (u32 * 4)(left, top, width, height)
+    lib.vq_spd_setup(d, C.byref(c), rect, mips)
+    return (d[0], d[1]), c
+
+
+def mip_level_count(w: int, h: int) -> int:
+    return lib.vq_mip_level_count(w, h)
+
+
+def cubemap_texel_count(res: int, mips: int) -> int:
+    return lib.vq_cubemap_texel_count(res, mips)
+
+
+def cubemap_offset(res: int, mip: int, face: int) -> int:
+    return lib.vq_cubemap_offset(res, mip, face)
+
+
+def cubemap_row_count(res: int, mips: int) -> int:
+    return lib.vq_cubemap_row_count(res, mips)
+
+
+def pyramid_texel_count(w: int, h: int, levels: int) -> int:
+    return lib.vq_pyramid_texel_count(w, h, levels)
+
+
+def pyramid_offset(w: int, h: int, level: int) -> int:
+    return lib.vq_pyramid_offset(w, h, level)
+
+
+# ---- descriptors from torch tensors ------------------------------------------------------------
+def image_of(t, channels: int = 4) -> Image:
+    """[H, W, channels] float32 tensor (CUDA, or pinned/pageable host for the *_host calls)."""
+    assert t.dim() == 3 and t.shape[2] == channels and t.dtype.is_floating_point and t.element_size() == 4
+    assert t.stride(2) == 1 and t.stride(1) == channels, "rows must be dense"
+    return Image(t.data_ptr(), t.shape[1], t.shape[0], t.stride(0) * 4)
+
+
+def null_image() -> Image:
+    return Image(None, 0, 0, 0)
+
+
+def cubemap_of(t, res: int, mips: int) -> Cubemap:
+    assert t.is_contiguous() and t.numel() == cubemap_texel_count(res, mips) * 4
+    return Cubemap(t.data_ptr(), res, mips)
+
+
+def pyramid_of(t, w: int, h: int, levels: int) -> Pyramid:
+    assert t.is_contiguous() and t.numel() == pyramid_texel_count(w, h, levels) * 4
+    return Pyramid(t.data_ptr(), w, h, levels)
+
+
+def _stream_ptr(stream) -> C.c_void_p:
+    if stream is None:
+        import torch
+        stream = torch.cuda.current_stream()
+    return C.c_void_p(stream.cuda_stream)
+
+
+class Context:
+    """Owns a VqContext (IRenderPass::Initialize / Destroy)."""
+
+    def __init__(self, device: int = 0):
+        self._h = C.c_void_p()
+        _check(lib.vq_ctx_create(device, C.byref(self._h)))
+        self.device = device
+
+    def close(self):
+        if self._h:
+            lib.vq_ctx_destroy(self._h)
+            self._h = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def resize(self, w: int, h: int):
+        _check(lib.vq_ctx_resize(self._h, w, h))
+
+    # K1
+    def forward_lighting(self, per_frame, per_view, gbuffer: GBuffer, env: EnvironmentMaps, out, row_begin=0,
+                         row_end=None, stream=None):
+        o = image_of(out)
+        _check(lib.vq_forward_lighting(self._h, C.byref(per_frame), C.byref(per_view), C.byref(gbuffer), C.byref(env), o,
+                                       row_begin, o.height if row_end is None else row_end, _stream_ptr(stream)))
+
+    def forward_lighting_host(self, per_frame, per_view, host_gbuffer: GBuffer, env: EnvironmentMaps, host_out):
+        _check(lib.vq_forward_lighting_host(self._h, C.byref(per_frame), C.byref(per_view), C.byref(host_gbuffer),
+                                            C.byref(env), image_of(host_out)))
+
+    # K11 / K2 / K3 / K4
+    def hdri_build_mips(self, pyr: Pyramid, stream=None):
+        _check(lib.vq_hdri_build_mips(self._h, pyr, _stream_ptr(stream)))
+
+    def diffuse_irradiance(self, pyr: Pyramid, cube: Cubemap, step=0.0, n_phi=64, n_theta=16, src_mip=3,
+                           row_begin=0, row_end=None, stream=None):
+        p = DiffuseIrradianceParams(step, n_phi, n_theta, src_mip)
+        _check(lib.vq_diffuse_irradiance(self._h, C.byref(p), pyr, cube, row_begin,
+                                         6 * cube.res if row_end is None else row_end, _stream_ptr(stream)))
+
+    def specular_prefilter(self, pyr: Pyramid, cube: Cubemap, num_samples=512, row_begin=0, row_end=None, stream=None):
+        _check(lib.vq_specular_prefilter(self._h, pyr, cube, num_samples, row_begin,
+                                         cubemap_row_count(cube.res, cube.mips) if row_end is None else row_end,
+                                         _stream_ptr(stream)))
+
+    def brdf_integration_lut(self, out, num_samples=2048, row_begin=0, row_end=None, stream=None):
+        o = image_of(out, 2)
+        _check(lib.vq_brdf_integration_lut(self._h, o, num_samples, row_begin,
+                                           o.height if row_end is None else row_end, _stream_ptr(stream)))
+
+    # post chain
+    def gaussian_blur(self, src, dst, vertical: bool, stream=None):
+        p = BlurParams(src.shape[1], src.shape[0])
+        fn = lib.vq_gaussian_blur_y if vertical else lib.vq_gaussian_blur_x
+        _check(fn(self._h, C.byref(p), image_of(src), image_of(dst), _stream_ptr(stream)))
+
+    def tonemap(self, params: TonemapperParams, src, dst, stream=None):
+        _check(lib.vq_tonemap(self._h, C.byref(params), image_of(src), image_of(dst), _stream_ptr(stream)))
+
+    def cas(self, con, src, dst, stream=None):
+        _check(lib.vq_cas(self._h, con, image_of(src), image_of(dst), _stream_ptr(stream)))
+
+    def fsr_easu(self, con, src, dst, address_mode=VQ_ADDRESS_WRAP, stream=None):
+        _check(lib.vq_fsr_easu(self._h, con, address_mode, image_of(src), image_of(dst), _stream_ptr(stream)))
+
+    def fsr_rcas(self, con, src, dst, stream=None):
+        _check(lib.vq_fsr_rcas(self._h, con, image_of(src), image_of(dst), _stream_ptr(stream)))
+
+    def spd_downsample(self, constants: SpdConstants, src, mips, stream=None):
+        arr = (Image * len(mips))(*[image_of(m) for m in mips])
+        _check(lib.vq_spd_downsample(self._h, C.byref(constants), image_of(src), arr, _stream_ptr(stream)))
+
+
+def launch_count() -> int:
+    return int(lib.vq_launch_count())

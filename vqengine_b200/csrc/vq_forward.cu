@@ -1,0 +1,388 @@
+// vq_forward.cu — K1 forward PBR lighting for sm_100a.
+//
+// Replaces VQRenderer::RenderSceneColor (SceneRendering.cpp:1619-1851) + PSMain
+// (ForwardLighting.hlsl:285-380) over a G-buffer of three float4 planes (+ optional emissive):
+//   64 B/pixel of HBM traffic (3 x LDG.128 + 1 x STG.128, all coalesced, streaming);
+//   the light array is staged once per block into shared memory; the IBL cubemaps and the BRDF LUT
+//   are read through L1/L2 (they are L2-resident side data: <= 42 MB at the reference sizes).
+// The math is PSMain's with per-pixel invariants hoisted out of the light loops (N, V, N.V, the
+// Smith-G term of V, F0, kD factors). Discontinuities are evaluated exactly as the oracle does:
+//   * `D < l.range` uses an unfused |L-P|^2 and a per-light threshold on the squared distance that is
+//     equivalent to the correctly-rounded sqrt compare;
+//   * the specular mip is int(roughness * MAX_LOD) (one fp32 multiply);
+//   * cubemap taps are seamless across face edges, so face selection is not a discontinuity.
+#include "vq_common.cuh"
+
+using namespace vq;
+
+namespace {
+
+constexpr int FWD_THREADS = 256;
+constexpr int MAX_POINT = VQ_NUM_LIGHTS_POINT + VQ_NUM_SHADOWING_LIGHTS_POINT;   // casters appended (shadow factor 1)
+constexpr int MAX_SPOT = VQ_NUM_LIGHTS_SPOT + VQ_NUM_SHADOWING_LIGHTS_SPOT;
+
+struct CubeV { const float4* p; int res, mips; uint32_t mipOffset[16]; };
+struct LutV { const float2* p; int w, h, pitch2; };
+
+struct FwdParams {
+    VqSceneLighting lights;            // 7088 B, read once per block into shared memory
+    float3 cam;
+    float cosB, sinB;                  // GetHDRIRotationMatrix (Lighting.hlsl:348-358), cos/sin(-offset)
+    int maxLod;                        // int(MaxEnvMapLODLevels)
+    int diffuseOnly;
+    int hasEmissive;
+    ImgV pos, nrm, alb, emi, out;
+    CubeV diff, spec;
+    LutV lut;
+    int rowBegin, rows, width;
+};
+
+struct SPoint { float3 pos; float d2Limit; float3 color; float brightness; };
+struct SSpot { float3 pos; float outer; float3 color; float brightness; float3 dir; float inner; float invCone; float pad[3]; };
+
+// ---------------------------------------------------------------------------------------------
+// cubemap sampling: bilinear, seamless (identical rule in oracle/oracle_shading.cpp)
+// ---------------------------------------------------------------------------------------------
+__device__ __forceinline__ void dir_to_face(float3 d, int& face, float& sx, float& sy) {
+    const float ax = fabsf(d.x), ay = fabsf(d.y), az = fabsf(d.z);
+    if (ax >= ay && ax >= az) {
+        const float r = 1.0f / ax;     // IEEE division, as the oracle
+        if (d.x > 0) { face = 0; sx = -d.z * r; sy = d.y * r; } else { face = 1; sx = d.z * r; sy = d.y * r; }
+    } else if (ay >= az) {
+        const float r = 1.0f / ay;
+        if (d.y > 0) { face = 2; sx = d.x * r; sy = -d.z * r; } else { face = 3; sx = d.x * r; sy = d.z * r; }
+    } else {
+        const float r = 1.0f / az;
+        if (d.z > 0) { face = 4; sx = d.x * r; sy = d.y * r; } else { face = 5; sx = -d.x * r; sy = d.y * r; }
+    }
+}
+
+// integer-only neighbour lookup for a tap one texel outside the face (see DESIGN.md "cube edges")
+__device__ __noinline__ void cube_resolve_edge(int N, int face, int i, int j, int& of, int& oi, int& oj) {
+    const int A = 2 * i + 1 - N, B = N - 1 - 2 * j, C = N;
+    int dx, dy, dz;
+    switch (face) {
+        case 0: dx = C;  dy = B;  dz = -A; break;
+        case 1: dx = -C; dy = B;  dz = A;  break;
+        case 2: dx = A;  dy = C;  dz = -B; break;
+        case 3: dx = A;  dy = -C; dz = B;  break;
+        case 4: dx = A;  dy = B;  dz = C;  break;
+        default: dx = -A; dy = B; dz = -C; break;
+    }
+    const int M = N + 1;
+    int nsx, nsy;
+    if (dx == M)       { of = 0; nsx = -dz; nsy = dy; }
+    else if (dx == -M) { of = 1; nsx = dz;  nsy = dy; }
+    else if (dy == M)  { of = 2; nsx = dx;  nsy = -dz; }
+    else if (dy == -M) { of = 3; nsx = dx;  nsy = dz; }
+    else if (dz == M)  { of = 4; nsx = dx;  nsy = dy; }
+    else               { of = 5; nsx = -dx; nsy = dy; }
+    oi = min(max(((nsx + M) * N) / (2 * M), 0), N - 1);
+    oj = min(max(((M - nsy) * N) / (2 * M), 0), N - 1);
+}
+
+__device__ __forceinline__ float3 sample_cube(const CubeV& c, float3 dir, int mip) {
+    mip = min(max(mip, 0), c.mips - 1);
+    const int N = c.res >> mip;
+    int face; float sx, sy;
+    dir_to_face(dir, face, sx, sy);
+    const float x = fmaf(fmaf(sx, 0.5f, 0.5f), (float)N, -0.5f);
+    const float y = fmaf(fmaf(-sy, 0.5f, 0.5f), (float)N, -0.5f);
+    const int i0 = min(max((int)floorf(x), -1), N - 1);
+    const int j0 = min(max((int)floorf(y), -1), N - 1);
+    const float fx = x - (float)i0, fy = y - (float)j0;
+    const float4* base = c.p + c.mipOffset[mip];
+    const size_t faceSz = (size_t)N * N;
+    float4 t[4];
+    if (i0 >= 0 && j0 >= 0 && i0 + 1 < N && j0 + 1 < N) {     // interior: the common case
+        const float4* p = base + face * faceSz + (size_t)j0 * N + i0;
+        t[0] = __ldg(p); t[1] = __ldg(p + 1); t[2] = __ldg(p + N); t[3] = __ldg(p + N + 1);
+    } else {
+        bool corner[4]; bool any = false;
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+            const int i = i0 + (k & 1), j = j0 + (k >> 1);
+            const bool oi = (i < 0 || i >= N), oj = (j < 0 || j >= N);
+            corner[k] = oi && oj;
+            if (corner[k]) { any = true; t[k] = make_float4(0, 0, 0, 0); continue; }
+            int f2 = face, i2 = i, j2 = j;
+            if (oi || oj) cube_resolve_edge(N, face, i, j, f2, i2, j2);
+            t[k] = __ldg(base + f2 * faceSz + (size_t)j2 * N + i2);
+        }
+        if (any) {
+            float4 s = make_float4(0, 0, 0, 0);
+#pragma unroll
+            for (int k = 0; k < 4; ++k) if (!corner[k]) s = s + t[k];
+            s = s * (1.0f / 3.0f);
+#pragma unroll
+            for (int k = 0; k < 4; ++k) if (corner[k]) t[k] = s;
+        }
+    }
+    const float4 top = lerp(t[0], t[1], fx), bot = lerp(t[2], t[3], fx);
+    return xyz(lerp(top, bot, fy));
+}
+
+__device__ __forceinline__ float2 sample_lut(const LutV& l, float u, float v) {   // bilinear, CLAMP
+    const float x = fmaf(u, (float)l.w, -0.5f), y = fmaf(v, (float)l.h, -0.5f);
+    const float x0 = floorf(x), y0 = floorf(y);
+    const float fx = x - x0, fy = y - y0;
+    const int ix0 = min(max((int)x0, 0), l.w - 1), ix1 = min(max((int)x0 + 1, 0), l.w - 1);
+    const int iy0 = min(max((int)y0, 0), l.h - 1), iy1 = min(max((int)y0 + 1, 0), l.h - 1);
+    const float2 p00 = __ldg(l.p + (size_t)iy0 * l.pitch2 + ix0), p10 = __ldg(l.p + (size_t)iy0 * l.pitch2 + ix1);
+    const float2 p01 = __ldg(l.p + (size_t)iy1 * l.pitch2 + ix0), p11 = __ldg(l.p + (size_t)iy1 * l.pitch2 + ix1);
+    return make_float2(lerp(lerp(p00.x, p10.x, fx), lerp(p01.x, p11.x, fx), fy),
+                       lerp(lerp(p00.y, p10.y, fx), lerp(p01.y, p11.y, fx), fy));
+}
+
+// ---------------------------------------------------------------------------------------------
+// per-pixel shading state with everything that does not depend on the light hoisted
+// ---------------------------------------------------------------------------------------------
+struct Px {
+    float3 P, Ns, Nn, V, albedo, F0, oneMinusF0;
+    float roughness, metalness;
+    float a2, a2m1, k, omk, NdotV, gV, diffScale;   // diffScale = (1-metal)/PI applied to (1-F)*albedo
+    float3 albedoOverPi;
+};
+
+// BRDF(s, Wi, V) * NdotL_surface, BRDF.hlsl:163-194 with the V-only terms precomputed
+__device__ __forceinline__ float3 brdf_times_ndotl(const Px& s, float3 Wi) {
+    const float3 H = normalize(s.V + Wi);
+    const float NdotH = saturate(dot(s.Nn, H));
+    const float NL_raw = dot(s.Nn, Wi);
+    const float NdotL = saturate(NL_raw);
+    const float NL = fmaxf(0.0f, NL_raw);
+    const float HV = fmaxf(0.0f, dot(H, s.V));
+    const float fc = pow5(1.0f - HV);                            // Fresnel_Schlick, BRDF.hlsl:132-136
+    const float3 F = f3(fmaf(s.oneMinusF0.x, fc, s.F0.x), fmaf(s.oneMinusF0.y, fc, s.F0.y), fmaf(s.oneMinusF0.z, fc, s.F0.z));
+    // D = a2 / (PI * (nh2*(a2-1)+1)^2)   (BRDF.hlsl:65-79),  G = gV * NL/((NL*(1-k)+k)+1e-4)  (:82-97,118-121)
+    const float t = fmaf(NdotH * NdotH, s.a2m1, 1.0f);
+    const float dDen = PI * (t * t);
+    const float gDen = fmaf(NL, s.omk, s.k) + 0.0001f;
+    const float sDen = fmaxf(4.0f * s.NdotV * NdotL, 0.0001f);
+    // D*G/denom with ONE reciprocal; `denom < EPSILON -> D = 1` (BRDF.hlsl:77) kept as a select
+    const bool tiny = dDen < 0.000000000001f;
+    const float num = (tiny ? 1.0f : s.a2) * s.gV * NL;
+    const float den = (tiny ? 1.0f : dDen) * gDen * sDen;
+    const float spec = __fdividef(num, den);
+    const float NdotLs = saturate(dot(s.Ns, Wi));                // Lighting.hlsl:316: un-normalised s.N
+    // Id = (1-F)*(1-metal)*albedo/PI
+    float3 r;
+    r.x = fmaf(1.0f - F.x, s.albedoOverPi.x, F.x * spec);
+    r.y = fmaf(1.0f - F.y, s.albedoOverPi.y, F.y * spec);
+    r.z = fmaf(1.0f - F.z, s.albedoOverPi.z, F.z * spec);
+    return r * NdotLs;
+}
+
+__global__ void __launch_bounds__(FWD_THREADS) forward_kernel(const __grid_constant__ FwdParams P) {
+    __shared__ SPoint sPoint[MAX_POINT];
+    __shared__ SSpot sSpot[MAX_SPOT];
+    __shared__ int sCounts[2];
+
+    // ---- stage the light arrays (Scene::GatherLightData layout) into shared memory, once per block ----
+    const VqSceneLighting& L = P.lights;
+    const int nP = L.numPointLights, nPC = L.numPointCasters, nS = L.numSpotLights, nSC = L.numSpotCasters;
+    for (int i = threadIdx.x; i < nP + nPC; i += FWD_THREADS) {
+        const VqPointLight& l = i < nP ? L.point_lights[i] : L.point_casters[i - nP];
+        SPoint s;
+        s.pos = f3(l.position.x, l.position.y, l.position.z);
+        s.color = f3(l.color.x, l.color.y, l.color.z);
+        s.brightness = l.brightness;
+        // smallest d2 with sqrt_rn(d2) >= range: then (d2 < limit) == (sqrt_rn(d2) < range) exactly
+        float lim = l.range * l.range;
+        if (!(l.range > 0.0f)) lim = 0.0f;
+        else {
+            while (sqrtf(lim) >= l.range && lim > 0.0f) lim = __uint_as_float(__float_as_uint(lim) - 1u);
+            while (sqrtf(lim) < l.range) lim = __uint_as_float(__float_as_uint(lim) + 1u);
+        }
+        s.d2Limit = lim;
+        sPoint[i] = s;
+    }
+    for (int i = threadIdx.x; i < nS + nSC; i += FWD_THREADS) {
+        const VqSpotLight& l = i < nS ? L.spot_lights[i] : L.spot_casters[i - nS];
+        SSpot s;
+        s.pos = f3(l.position.x, l.position.y, l.position.z);
+        s.color = f3(l.color.x, l.color.y, l.color.z);
+        s.brightness = l.brightness;
+        const float3 d = f3(l.spotDir.x, l.spotDir.y, l.spotDir.z);
+        const float dl = sqrtf(dot(d, d));
+        s.dir = f3(d.x / dl, d.y / dl, d.z / dl);               // normalize(l.spotDir), Lighting.hlsl:60
+        s.outer = l.outerConeAngle; s.inner = l.innerConeAngle;
+        s.invCone = l.outerConeAngle - l.innerConeAngle;        // divisor kept as-is (IEEE division below)
+        sSpot[i] = s;
+    }
+    if (threadIdx.x == 0) { sCounts[0] = nP + nPC; sCounts[1] = nS + nSC; }
+    __syncthreads();
+    const int numPoint = sCounts[0], numSpot = sCounts[1];
+    const bool dirEnabled = L.directional.enabled != 0;
+    float3 dirWi = f3(0.0f), dirRadiance = f3(0.0f);
+    if (dirEnabled) {                                            // Lighting.hlsl:334-345
+        const float3 nd = f3(-L.directional.lightDirection.x, -L.directional.lightDirection.y, -L.directional.lightDirection.z);
+        const float dl = sqrtf(dot(nd, nd));
+        dirWi = f3(nd.x / dl, nd.y / dl, nd.z / dl);
+        dirRadiance = f3(L.directional.color.x, L.directional.color.y, L.directional.color.z) * L.directional.brightness;
+    }
+
+    const long long total = (long long)P.rows * P.width;
+    for (long long idx = (long long)blockIdx.x * FWD_THREADS + threadIdx.x; idx < total; idx += (long long)gridDim.x * FWD_THREADS) {
+        const int y = P.rowBegin + (int)(idx / P.width);
+        const int x = (int)(idx % P.width);
+        const float4 pa = ld_stream(P.pos.row(y) + x);
+        const float4 nr = ld_stream(P.nrm.row(y) + x);
+        const float4 am = ld_stream(P.alb.row(y) + x);
+
+        Px s;
+        s.P = xyz(pa); s.Ns = xyz(nr); s.albedo = xyz(am);
+        s.roughness = nr.w; s.metalness = am.w;
+        const float ao = pa.w;
+        s.V = normalize(P.cam - s.P);                            // ForwardLighting.hlsl:285
+        s.Nn = normalize(s.Ns);                                  // BRDF.hlsl:167
+        s.F0 = lerp(f3(0.04f), s.albedo, s.metalness);           // BRDF.hlsl:177
+        s.oneMinusF0 = f3(1.0f) - s.F0;
+        const float a = s.roughness * s.roughness;
+        s.a2 = a * a; s.a2m1 = s.a2 - 1.0f;
+        const float rp1 = s.roughness + 1.0f;
+        s.k = (rp1 * rp1) * 0.125f; s.omk = 1.0f - s.k;
+        const float nv = dot(s.Nn, s.V);
+        s.NdotV = saturate(nv);
+        const float NV = fmaxf(0.0f, nv);
+        s.gV = NV / (fmaf(NV, s.omk, s.k) + 0.0001f);
+        s.albedoOverPi = s.albedo * ((1.0f - s.metalness) * (1.0f / PI));
+
+        float3 I = s.albedo * ao;                                // ForwardLighting.hlsl:290-293
+        if (P.hasEmissive) {
+            const float4 em = ld_stream(P.emi.row(y) + x);
+            I += xyz(em) * em.w;
+        }
+
+        // ---- environment map (Lighting.hlsl:360-395, BRDF.hlsl:196-207) ----
+        {
+            const float NdotVs = saturate(dot(s.Ns, s.V));
+            const float3 Nr = f3(s.Ns.x * P.cosB - s.Ns.z * P.sinB, s.Ns.y, s.Ns.x * P.sinB + s.Ns.z * P.cosB);
+            const float3 diffIrr = sample_cube(P.diff, Nr, 0);
+            float3 specCol = f3(0.0f); float2 sb = make_float2(0.0f, 0.0f);
+            if (!P.diffuseOnly) {
+                const float3 R0 = reflect(-s.V, s.Ns);
+                const float3 R = f3(R0.x * P.cosB - R0.z * P.sinB, R0.y, R0.x * P.sinB + R0.z * P.cosB);
+                const int mip = (int)(s.roughness * (float)P.maxLod);
+                specCol = sample_cube(P.spec, R, mip);
+                sb = sample_lut(P.lut, NdotVs, s.roughness);
+            }
+            const float fr = pow5(1.0f - NdotVs);                // FresnelWithRoughness, BRDF.hlsl:152-156
+            const float omr = 1.0f - s.roughness;
+            const float3 Ks = f3(fmaf(fmaxf(omr, s.F0.x) - s.F0.x, fr, s.F0.x),
+                                 fmaf(fmaxf(omr, s.F0.y) - s.F0.y, fr, s.F0.y),
+                                 fmaf(fmaxf(omr, s.F0.z) - s.F0.z, fr, s.F0.z));
+            const float om = 1.0f - s.metalness;
+            I.x += (1.0f - Ks.x) * om * (diffIrr.x * s.albedo.x) + specCol.x * fmaf(Ks.x, sb.x, sb.y);
+            I.y += (1.0f - Ks.y) * om * (diffIrr.y * s.albedo.y) + specCol.y * fmaf(Ks.y, sb.x, sb.y);
+            I.z += (1.0f - Ks.z) * om * (diffIrr.z * s.albedo.z) + specCol.z * fmaf(Ks.z, sb.x, sb.y);
+        }
+
+        // ---- point lights, then unshadowed point casters (Lighting.hlsl:308-322; PSMain :310-313,321-340) ----
+        for (int i = 0; i < numPoint; ++i) {
+            const SPoint l = sPoint[i];
+            const float3 Lv = l.pos - s.P;
+            // |L-P|^2 exactly as the oracle's dot(): (x*x + y*y) + z*z, no contraction
+            const float d2 = __fadd_rn(__fadd_rn(__fmul_rn(Lv.x, Lv.x), __fmul_rn(Lv.y, Lv.y)), __fmul_rn(Lv.z, Lv.z));
+            if (d2 < l.d2Limit) {
+                const float invD = rsqrtf(d2);
+                const float3 Wi = Lv * invD;
+                const float3 radiance = l.color * ((invD * invD) * l.brightness);   // AttenuationBRDF = 1/D^2
+                I += brdf_times_ndotl(s, Wi) * radiance;
+            }
+        }
+        // ---- spot lights, then unshadowed spot casters (Lighting.hlsl:57-73,323-333) ----
+        for (int i = 0; i < numSpot; ++i) {
+            const SSpot l = sSpot[i];
+            const float3 Lv = l.pos - s.P;
+            const float d2 = dot(Lv, Lv);
+            const float invD = rsqrtf(d2);
+            const float3 Wi = Lv * invD;
+            const float theta = acosf(dot(-Wi, l.dir));          // pixelDirection = normalize(P - l.position)
+            float inten;
+            if (theta > l.outer) inten = 0.0f;
+            else if (theta <= l.inner) inten = 1.0f;
+            else inten = 1.0f - (theta - l.inner) / l.invCone;
+            const float3 radiance = l.color * (inten * l.brightness * (invD * invD));
+            I += brdf_times_ndotl(s, Wi) * radiance;
+        }
+        // ---- directional (PSMain :360-377 with ShadowingFactor = 1) ----
+        if (dirEnabled) I += brdf_times_ndotl(s, dirWi) * dirRadiance;
+
+        st_stream(P.out.row(y) + x, make_float4(I.x, I.y, I.z, s.roughness));   // :380
+    }
+}
+
+int fill_cube(const VqCubemap& c, CubeV& v, const char* what) {
+    if (!c.ptr || c.res < 1 || c.mips < 1 || c.mips > 16 || (c.res >> (c.mips - 1)) < 1) {
+        vq_set_error("invalid argument: bad cubemap descriptor (%s)", what);
+        return VQ_ERR_INVALID_ARG;
+    }
+    v.p = (const float4*)c.ptr; v.res = c.res; v.mips = c.mips;
+    for (int m = 0; m < 16; ++m) v.mipOffset[m] = m < c.mips ? (uint32_t)vq_cubemap_offset(c.res, m, 0) : 0u;
+    return VQ_OK;
+}
+
+}  // namespace
+
+int vq_forward_launch(VqContext* ctx, const VqPerFrameData* pf, const VqPerViewLightingData* pv,
+                      const VqGBuffer* gb, const VqEnvironmentMaps* env, VqImage out,
+                      int row_begin, int row_end, cudaStream_t stream) {
+    VQ_REQUIRE(pf && pv && gb && env, "null parameter block");
+    VQ_REQUIRE(vq_image_ok(gb->position_ao) && vq_image_ok(gb->normal_roughness) && vq_image_ok(gb->albedo_metalness) && vq_image_ok(out),
+               "bad image descriptor");
+    const int W = out.width, H = out.height;
+    VQ_REQUIRE(gb->position_ao.width == W && gb->normal_roughness.width == W && gb->albedo_metalness.width == W &&
+               gb->position_ao.height == H && gb->normal_roughness.height == H && gb->albedo_metalness.height == H,
+               "G-buffer planes and output must have the same size");
+    VQ_REQUIRE(row_begin >= 0 && row_end <= H && row_begin <= row_end, "row range out of bounds");
+    const VqSceneLighting& L = pf->Lights;
+    VQ_REQUIRE(L.numPointLights >= 0 && L.numPointLights <= VQ_NUM_LIGHTS_POINT &&
+               L.numSpotLights >= 0 && L.numSpotLights <= VQ_NUM_LIGHTS_SPOT &&
+               L.numPointCasters >= 0 && L.numPointCasters <= VQ_NUM_SHADOWING_LIGHTS_POINT &&
+               L.numSpotCasters >= 0 && L.numSpotCasters <= VQ_NUM_SHADOWING_LIGHTS_SPOT, "light counts exceed the cbuffer arrays");
+    if (row_begin == row_end) return VQ_OK;
+
+    FwdParams P;
+    memset(&P, 0, sizeof(P));
+    P.lights = L;
+    P.cam = make_float3(pv->CameraPosition.x, pv->CameraPosition.y, pv->CameraPosition.z);
+    P.cosB = cosf(-pf->fHDRIOffsetInRadians);
+    P.sinB = sinf(-pf->fHDRIOffsetInRadians);
+    P.maxLod = (int)pv->MaxEnvMapLODLevels;
+    P.diffuseOnly = pv->EnvironmentMapDiffuseOnlyIllumination != 0;
+    P.pos = make_view(gb->position_ao); P.nrm = make_view(gb->normal_roughness); P.alb = make_view(gb->albedo_metalness);
+    P.out = make_view(out);
+    P.hasEmissive = gb->emissive.ptr != nullptr;
+    if (P.hasEmissive) {
+        VQ_REQUIRE(vq_image_ok(gb->emissive) && gb->emissive.width == W && gb->emissive.height == H, "bad emissive plane");
+        P.emi = make_view(gb->emissive);
+    }
+    int rc = fill_cube(env->irradiance_diffuse, P.diff, "irradiance_diffuse"); if (rc) return rc;
+    if (!P.diffuseOnly) {
+        rc = fill_cube(env->irradiance_specular, P.spec, "irradiance_specular"); if (rc) return rc;
+        VQ_REQUIRE(vq_image_ok(env->brdf_lut, 8), "bad BRDF LUT descriptor");
+        P.lut.p = (const float2*)env->brdf_lut.ptr; P.lut.w = env->brdf_lut.width; P.lut.h = env->brdf_lut.height;
+        P.lut.pitch2 = (int)(env->brdf_lut.pitch_bytes / 8);
+    }
+    P.rowBegin = row_begin; P.rows = row_end - row_begin; P.width = W;
+
+    static int blocksPerSM = 0;
+    if (!blocksPerSM) {
+        VQ_CUDA_OK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&blocksPerSM, forward_kernel, FWD_THREADS, 0));
+        if (blocksPerSM < 1) blocksPerSM = 1;
+    }
+    const long long total = (long long)P.rows * W;
+    long long blocks = (total + FWD_THREADS - 1) / FWD_THREADS;
+    const long long persistent = (long long)ctx->sm_count * blocksPerSM;   // one wave of resident CTAs
+    if (blocks > persistent) blocks = persistent;
+    forward_kernel<<<(unsigned)blocks, FWD_THREADS, 0, stream>>>(P);
+    return vq_check_launch("forward_lighting");
+}
+
+extern "C" int vq_forward_lighting(VqContext* ctx, const VqPerFrameData* pf, const VqPerViewLightingData* pv,
+                                   const VqGBuffer* gb, const VqEnvironmentMaps* env, VqImage out,
+                                   int row_begin, int row_end, void* stream) {
+    int rc = vq_enter(ctx); if (rc) return rc;
+    return vq_forward_launch(ctx, pf, pv, gb, env, out, row_begin, row_end, (cudaStream_t)stream);
+}

@@ -1,0 +1,596 @@
+// vq_post.cu — post chain kernels for sm_100a: Tonemapper (K6), separable Gaussian blur (K5),
+// FidelityFX CAS (K7), FSR1 EASU (K8) / RCAS (K9), SPD (K10).
+//
+// All are streaming kernels over RGBA32F rows: float4 (LDG.128/STG.128) coalesced accesses, inputs
+// that are read once bypass L1 allocation, stencil inputs are staged in shared memory (blur) or
+// served by L1 (3x3 / 12-tap stencils). Math follows the HLSL the engine ships (file:line cited per
+// kernel); parity against oracle/ is tested in tests/test_post_gpu.py.
+#include "vq_common.cuh"
+
+using namespace vq;
+
+// =============================================================================================
+// K6 Tonemapper — Shaders/Tonemapper.hlsl:110-151, Shaders/HDR.hlsl:76-119
+// =============================================================================================
+__device__ __forceinline__ float linear_to_srgb(float c) {          // HDR.hlsl:76-80
+    return c < 0.0031308f ? 12.92f * c : fmaf(1.055f, powf(fabsf(c), 1.0f / 2.4f), -0.055f);
+}
+__device__ __forceinline__ float linear_to_st2084(float c) {        // HDR.hlsl:110-119
+    const float m1 = 2610.0f / 4096.0f / 4, m2 = 2523.0f / 4096.0f * 128;
+    const float c1 = 3424.0f / 4096.0f, c2 = 2413.0f / 4096.0f * 32, c3 = 2392.0f / 4096.0f * 32;
+    const float cp = powf(fabsf(c), m1);
+    return powf(fmaf(c2, cp, c1) / fmaf(c3, cp, 1.0f), m2);
+}
+
+template <int CURVE, bool GAMMA, bool TO2020>
+__device__ __forceinline__ float4 tonemap_px(float4 in, float hdrScalar) {
+    float3 o;
+    if (CURVE == VQ_DISPLAY_CURVE_SRGB) {
+        // Tonemap_Reinhard (Tonemapper.hlsl:24-27): c / (c + 1), IEEE division
+        o = f3(in.x / (in.x + 1.0f), in.y / (in.y + 1.0f), in.z / (in.z + 1.0f));
+        if (GAMMA) o = f3(linear_to_srgb(o.x), linear_to_srgb(o.y), linear_to_srgb(o.z));
+    } else if (CURVE == VQ_DISPLAY_CURVE_ST2084) {
+        o = xyz(in);
+        if (TO2020) {   // Rec709ToRec2020, HDR.hlsl:88-97 (rows dot colour)
+            const float3 c = o;
+            o.x = 0.627402f * c.x + 0.329292f * c.y + 0.043306f * c.z;
+            o.y = 0.069095f * c.x + 0.919544f * c.y + 0.011360f * c.z;
+            o.z = 0.016394f * c.x + 0.088028f * c.y + 0.895578f * c.z;
+        }
+        o = f3(linear_to_st2084(o.x * hdrScalar), linear_to_st2084(o.y * hdrScalar), linear_to_st2084(o.z * hdrScalar));
+    } else if (CURVE == VQ_DISPLAY_CURVE_LINEAR) {
+        o = xyz(in);
+    } else {
+        o = f3(1.0f, 1.0f, 0.0f);
+    }
+    return make_float4(o.x, o.y, o.z, in.w);
+}
+
+constexpr int TM_THREADS = 256;
+constexpr int TM_PX = 4;   // pixels per thread, loads issued back to back for memory-level parallelism
+
+template <int CURVE, bool GAMMA, bool TO2020>
+__global__ void __launch_bounds__(TM_THREADS) tonemap_kernel(ImgV in, ImgV out, float hdrScalar) {
+    const int y = blockIdx.y;
+    const int x0 = blockIdx.x * (TM_THREADS * TM_PX) + threadIdx.x;
+    const float4* __restrict__ src = in.row(y);
+    float4* __restrict__ dst = out.row(y);
+    float4 v[TM_PX];
+#pragma unroll
+    for (int i = 0; i < TM_PX; ++i) {
+        const int x = x0 + i * TM_THREADS;
+        if (x < in.w) v[i] = ld_stream(src + x);
+    }
+#pragma unroll
+    for (int i = 0; i < TM_PX; ++i) {
+        const int x = x0 + i * TM_THREADS;
+        if (x < in.w) st_stream(dst + x, tonemap_px<CURVE, GAMMA, TO2020>(v[i], hdrScalar));
+    }
+}
+
+extern "C" int vq_tonemap(VqContext* ctx, const VqTonemapperParams* p, VqImage in, VqImage out, void* stream) {
+    int rc = vq_enter(ctx); if (rc) return rc;
+    VQ_REQUIRE(p, "params is null");
+    VQ_REQUIRE(vq_image_ok(in) && vq_image_ok(out), "bad image descriptor");
+    VQ_REQUIRE(in.width == out.width && in.height == out.height, "tonemap: in/out size mismatch");
+    const dim3 grid((in.width + TM_THREADS * TM_PX - 1) / (TM_THREADS * TM_PX), in.height);
+    const ImgV vi = make_view(in), vo = make_view(out);
+    cudaStream_t s = (cudaStream_t)stream;
+    const float hdrScalar = p->DisplayReferenceBrightnessLevel / 10000.0f;   // ST2084_MAX, HDR.hlsl:43
+    switch (p->OutputDisplayCurve) {
+        case VQ_DISPLAY_CURVE_SRGB:
+            if (p->ToggleGammaCorrection) tonemap_kernel<VQ_DISPLAY_CURVE_SRGB, true, false><<<grid, TM_THREADS, 0, s>>>(vi, vo, hdrScalar);
+            else                          tonemap_kernel<VQ_DISPLAY_CURVE_SRGB, false, false><<<grid, TM_THREADS, 0, s>>>(vi, vo, hdrScalar);
+            break;
+        case VQ_DISPLAY_CURVE_ST2084:
+            if (p->ContentColorSpace == VQ_COLOR_SPACE_REC_709) tonemap_kernel<VQ_DISPLAY_CURVE_ST2084, false, true><<<grid, TM_THREADS, 0, s>>>(vi, vo, hdrScalar);
+            else                                                 tonemap_kernel<VQ_DISPLAY_CURVE_ST2084, false, false><<<grid, TM_THREADS, 0, s>>>(vi, vo, hdrScalar);
+            break;
+        case VQ_DISPLAY_CURVE_LINEAR:
+            tonemap_kernel<VQ_DISPLAY_CURVE_LINEAR, false, false><<<grid, TM_THREADS, 0, s>>>(vi, vo, hdrScalar);
+            break;
+        default:   // Tonemapper.hlsl:143-145: unknown curve paints yellow
+            tonemap_kernel<3, false, false><<<grid, TM_THREADS, 0, s>>>(vi, vo, hdrScalar);
+            break;
+    }
+    return vq_check_launch("tonemap");
+}
+
+// =============================================================================================
+// K5 Gaussian blur — Shaders/GaussianBlur.hlsl:74-186, KERNEL_DIMENSION 21, clamp-to-edge, alpha = 1
+// =============================================================================================
+__constant__ float c_gauss[11] = {0.224716f, 0.191756f, 0.119146f, 0.053897f, 0.017746f, 0.004252f,
+                                  0.000741f, 0.000094f, 0.000009f, 0.000001f, 0.0f};   // GaussianBlur.hlsl:110
+
+// X pass: a block stages BX_W+24 pixels of BX_ROWS rows into PLANAR shared memory (R,G,B planes) so
+// that each thread reads its 28-value window with conflict-free LDS.128 and produces 4 adjacent
+// pixels from registers (sliding window: 7 LDS.128 per channel per 4 pixels).
+constexpr int BX_T = 128;            // threads along x
+constexpr int BX_ROWS = 2;           // rows per block
+constexpr int BX_W = BX_T * 4;       // output pixels per row per block
+constexpr int BX_SM = BX_W + 24;     // staged: [-12, BX_W+12)
+
+__global__ void __launch_bounds__(BX_T * BX_ROWS) blur_x_kernel(ImgV in, ImgV out, int sizeX, int sizeY) {
+    __shared__ __align__(16) float sm[BX_ROWS][3][BX_SM];
+    const int ty = threadIdx.y;
+    const int y = blockIdx.y * BX_ROWS + ty;
+    const int xBase = blockIdx.x * BX_W;
+    if (y < sizeY) {
+        const float4* __restrict__ src = in.row(y);
+        for (int i = threadIdx.x; i < BX_SM; i += BX_T) {
+            int sx = xBase - 12 + i;
+            sx = min(max(sx, 0), sizeX - 1);              // sampleCoord clamp, GaussianBlur.hlsl:144
+            const float4 v = __ldg(src + sx);
+            sm[ty][0][i] = v.x; sm[ty][1][i] = v.y; sm[ty][2][i] = v.z;
+        }
+    }
+    __syncthreads();
+    if (y >= sizeY) return;
+    const int x = xBase + threadIdx.x * 4;
+    if (x >= sizeX) return;
+    float acc[3][4];
+#pragma unroll
+    for (int c = 0; c < 3; ++c) {
+        float win[28];                                     // staged positions 4t .. 4t+27  == image x-12 .. x+15
+        const float4* p = reinterpret_cast<const float4*>(&sm[ty][c][threadIdx.x * 4]);
+#pragma unroll
+        for (int q = 0; q < 7; ++q) { const float4 v = p[q]; win[4 * q] = v.x; win[4 * q + 1] = v.y; win[4 * q + 2] = v.z; win[4 * q + 3] = v.w; }
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            float a = 0.0f;
+#pragma unroll
+            for (int k = 0; k < 21; ++k) {                 // kernelIt order 0..20 as in the HLSL loop
+                const int ki = k < 10 ? 10 - k : k - 10;
+                a = fmaf(win[j + 2 + k], c_gauss[ki], a);  // tap at x+j-10+k -> window index j+2+k
+            }
+            acc[c][j] = a;
+        }
+    }
+    float4* __restrict__ dst = out.row(y);
+#pragma unroll
+    for (int j = 0; j < 4; ++j)
+        if (x + j < sizeX) dst[x + j] = make_float4(acc[0][j], acc[1][j], acc[2][j], 1.0f);
+}
+
+// Y pass: a block stages a (BY_H+20) x BY_W tile of float4 and each thread produces BY_PER consecutive
+// rows of one column from a register sliding window (lanes are adjacent columns: conflict-free LDS.128).
+constexpr int BY_W = 32;
+constexpr int BY_TY = 8;
+constexpr int BY_PER = 8;
+constexpr int BY_H = BY_TY * BY_PER;   // 64 output rows per block
+
+__global__ void __launch_bounds__(BY_W * BY_TY) blur_y_kernel(ImgV in, ImgV out, int sizeX, int sizeY) {
+    __shared__ float4 sm[BY_H + 20][BY_W];
+    const int x = blockIdx.x * BY_W + threadIdx.x;
+    const int yBase = blockIdx.y * BY_H;
+    const int xc = min(x, sizeX - 1);
+    for (int r = threadIdx.y; r < BY_H + 20; r += BY_TY) {
+        int sy = yBase - 10 + r;
+        sy = min(max(sy, 0), sizeY - 1);                   // GaussianBlur.hlsl:180
+        sm[r][threadIdx.x] = __ldg(in.row(sy) + xc);
+    }
+    __syncthreads();
+    if (x >= sizeX) return;
+    const int r0 = threadIdx.y * BY_PER;                   // first output row (tile-relative)
+    float3 acc[BY_PER];
+#pragma unroll
+    for (int j = 0; j < BY_PER; ++j) acc[j] = f3(0.0f);
+#pragma unroll
+    for (int t = 0; t < BY_PER + 20; ++t) {                // tap row r0+t (tile) == image row yBase+r0+t-10
+        const float4 v = sm[r0 + t][threadIdx.x];
+#pragma unroll
+        for (int j = 0; j < BY_PER; ++j) {
+            const int k = t - j;                           // kernelIt for output j
+            if (k >= 0 && k < 21) {
+                const float w = c_gauss[k < 10 ? 10 - k : k - 10];
+                acc[j].x = fmaf(v.x, w, acc[j].x); acc[j].y = fmaf(v.y, w, acc[j].y); acc[j].z = fmaf(v.z, w, acc[j].z);
+            }
+        }
+    }
+#pragma unroll
+    for (int j = 0; j < BY_PER; ++j) {
+        const int y = yBase + r0 + j;
+        if (y < sizeY) out.row(y)[x] = make_float4(acc[j].x, acc[j].y, acc[j].z, 1.0f);
+    }
+}
+
+static int blur_common(VqContext* ctx, const VqBlurParams* p, VqImage in, VqImage out, void* stream, bool vertical) {
+    int rc = vq_enter(ctx); if (rc) return rc;
+    VQ_REQUIRE(p, "params is null");
+    VQ_REQUIRE(vq_image_ok(in) && vq_image_ok(out), "bad image descriptor");
+    VQ_REQUIRE(p->iImageSizeX > 0 && p->iImageSizeY > 0, "blur: image size must be positive");
+    VQ_REQUIRE(p->iImageSizeX <= in.width && p->iImageSizeY <= in.height &&
+               p->iImageSizeX <= out.width && p->iImageSizeY <= out.height, "blur: iImageSize exceeds the images");
+    VQ_REQUIRE(in.ptr != out.ptr, "blur: in-place is not supported (the engine ping-pongs too)");
+    const ImgV vi = make_view(in), vo = make_view(out);
+    cudaStream_t s = (cudaStream_t)stream;
+    if (!vertical) {
+        const dim3 grid((p->iImageSizeX + BX_W - 1) / BX_W, (p->iImageSizeY + BX_ROWS - 1) / BX_ROWS);
+        blur_x_kernel<<<grid, dim3(BX_T, BX_ROWS), 0, s>>>(vi, vo, p->iImageSizeX, p->iImageSizeY);
+    } else {
+        const dim3 grid((p->iImageSizeX + BY_W - 1) / BY_W, (p->iImageSizeY + BY_H - 1) / BY_H);
+        blur_y_kernel<<<grid, dim3(BY_W, BY_TY), 0, s>>>(vi, vo, p->iImageSizeX, p->iImageSizeY);
+    }
+    return vq_check_launch(vertical ? "gaussian_blur_y" : "gaussian_blur_x");
+}
+extern "C" int vq_gaussian_blur_x(VqContext* ctx, const VqBlurParams* p, VqImage in, VqImage out, void* stream) { return blur_common(ctx, p, in, out, stream, false); }
+extern "C" int vq_gaussian_blur_y(VqContext* ctx, const VqBlurParams* p, VqImage in, VqImage out, void* stream) { return blur_common(ctx, p, in, out, stream, true); }
+
+// =============================================================================================
+// FidelityFX scalar helpers — FSR1.0/ffx_a.h:1842-1845 (integer bit tricks: reproduced exactly)
+// =============================================================================================
+__device__ __forceinline__ float APrxLoSqrtF1(float a) { return __uint_as_float((__float_as_uint(a) >> 1u) + 0x1fbc4639u); }
+__device__ __forceinline__ float APrxLoRcpF1(float a)  { return __uint_as_float(0x7ef07ebbu - __float_as_uint(a)); }
+__device__ __forceinline__ float APrxMedRcpF1(float a) { const float b = __uint_as_float(0x7ef19fffu - __float_as_uint(a)); return b * fmaf(-b, a, 2.0f); }
+__device__ __forceinline__ float APrxLoRsqF1(float a)  { return __uint_as_float(0x5f347d74u - (__float_as_uint(a) >> 1u)); }
+__device__ __forceinline__ float min3f(float a, float b, float c) { return fminf(a, fminf(b, c)); }
+__device__ __forceinline__ float max3f(float a, float b, float c) { return fmaxf(a, fmaxf(b, c)); }
+
+// Texture.Load semantics: out-of-range reads return 0
+__device__ __forceinline__ float3 load_zero_border(const ImgV& im, int x, int y) {
+    if ((unsigned)x >= (unsigned)im.w || (unsigned)y >= (unsigned)im.h) return f3(0.0f);
+    return xyz(__ldg(im.row(y) + x));
+}
+
+// =============================================================================================
+// K7 CAS sharpen-only — CAS/ffx_cas.h:408-537 (noScaling), wrapper AMDFidelityFX.hlsl:122-174
+// =============================================================================================
+constexpr int ST_BX = 32, ST_BY = 8;   // 3x3 stencil kernels: 32x8 pixel blocks, rows shared through L1
+
+__global__ void __launch_bounds__(ST_BX * ST_BY) cas_kernel(ImgV in, ImgV out, float peak) {
+    const int x = blockIdx.x * ST_BX + threadIdx.x, y = blockIdx.y * ST_BY + threadIdx.y;
+    if (x >= out.w || y >= out.h) return;
+    const float3 b = load_zero_border(in, x, y - 1);
+    const float3 d = load_zero_border(in, x - 1, y);
+    const float3 e = load_zero_border(in, x, y);
+    const float3 f = load_zero_border(in, x + 1, y);
+    const float3 h = load_zero_border(in, x, y + 1);
+    // only the green channel's weight survives without CAS_SLOW (ffx_cas.h:511-519)
+    const float mnG = min3f(min3f(d.y, e.y, f.y), b.y, h.y);
+    const float mxG = max3f(max3f(d.y, e.y, f.y), b.y, h.y);
+    const float rcpMG = APrxLoRcpF1(mxG);
+    float ampG = saturate(fminf(mnG, 1.0f - mxG) * rcpMG);
+    ampG = APrxLoSqrtF1(ampG);
+    const float wG = ampG * peak;
+    const float rcpWeight = APrxMedRcpF1(fmaf(4.0f, wG, 1.0f));
+    float3 o;
+    o.x = saturate((b.x * wG + d.x * wG + f.x * wG + h.x * wG + e.x) * rcpWeight);
+    o.y = saturate((b.y * wG + d.y * wG + f.y * wG + h.y * wG + e.y) * rcpWeight);
+    o.z = saturate((b.z * wG + d.z * wG + f.z * wG + h.z * wG + e.z) * rcpWeight);
+    st_stream(out.row(y) + x, make_float4(o.x, o.y, o.z, 1.0f));
+}
+
+extern "C" int vq_cas(VqContext* ctx, const uint32_t cas_const[8], VqImage in, VqImage out, void* stream) {
+    int rc = vq_enter(ctx); if (rc) return rc;
+    VQ_REQUIRE(cas_const, "cas_const is null");
+    VQ_REQUIRE(vq_image_ok(in) && vq_image_ok(out), "bad image descriptor");
+    VQ_REQUIRE(in.width == out.width && in.height == out.height, "cas: sharpen-only path needs equal sizes (FFXCAS_NO_UPSCALING)");
+    VQ_REQUIRE(in.ptr != out.ptr, "cas: in-place is not supported");
+    float peak; memcpy(&peak, &cas_const[4], 4);     // const1.x
+    const dim3 grid((out.width + ST_BX - 1) / ST_BX, (out.height + ST_BY - 1) / ST_BY);
+    cas_kernel<<<grid, dim3(ST_BX, ST_BY), 0, (cudaStream_t)stream>>>(make_view(in), make_view(out), peak);
+    return vq_check_launch("cas");
+}
+
+// =============================================================================================
+// K9 RCAS — FSR1.0/ffx_fsr1.h:684-769, wrapper AMDFidelityFX.hlsl:335-376
+// =============================================================================================
+__global__ void __launch_bounds__(ST_BX * ST_BY) rcas_kernel(ImgV in, ImgV out, float sharp) {
+    const int x = blockIdx.x * ST_BX + threadIdx.x, y = blockIdx.y * ST_BY + threadIdx.y;
+    if (x >= out.w || y >= out.h) return;
+    const float3 b = load_zero_border(in, x, y - 1);
+    const float3 d = load_zero_border(in, x - 1, y);
+    const float3 e = load_zero_border(in, x, y);
+    const float3 f = load_zero_border(in, x + 1, y);
+    const float3 h = load_zero_border(in, x, y + 1);
+    const float3 mn4 = f3(fminf(min3f(b.x, d.x, f.x), h.x), fminf(min3f(b.y, d.y, f.y), h.y), fminf(min3f(b.z, d.z, f.z), h.z));
+    const float3 mx4 = f3(fmaxf(max3f(b.x, d.x, f.x), h.x), fmaxf(max3f(b.y, d.y, f.y), h.y), fmaxf(max3f(b.z, d.z, f.z), h.z));
+    // limiters need high-precision reciprocals (ffx_fsr1.h:749-755): IEEE division
+    const float hitMinR = mn4.x * (1.0f / (4.0f * mx4.x));
+    const float hitMinG = mn4.y * (1.0f / (4.0f * mx4.y));
+    const float hitMinB = mn4.z * (1.0f / (4.0f * mx4.z));
+    const float hitMaxR = (1.0f - mx4.x) * (1.0f / (4.0f * mn4.x + -4.0f));
+    const float hitMaxG = (1.0f - mx4.y) * (1.0f / (4.0f * mn4.y + -4.0f));
+    const float hitMaxB = (1.0f - mx4.z) * (1.0f / (4.0f * mn4.z + -4.0f));
+    const float lobeR = fmaxf(-hitMinR, hitMaxR);
+    const float lobeG = fmaxf(-hitMinG, hitMaxG);
+    const float lobeB = fmaxf(-hitMinB, hitMaxB);
+    const float FSR_RCAS_LIMIT = 0.25f - (1.0f / 16.0f);   // ffx_fsr1.h:654
+    const float lobe = fmaxf(-FSR_RCAS_LIMIT, fminf(max3f(lobeR, lobeG, lobeB), 0.0f)) * sharp;
+    const float rcpL = APrxMedRcpF1(fmaf(4.0f, lobe, 1.0f));
+    float3 o;
+    o.x = (lobe * b.x + lobe * d.x + lobe * h.x + lobe * f.x + e.x) * rcpL;
+    o.y = (lobe * b.y + lobe * d.y + lobe * h.y + lobe * f.y + e.y) * rcpL;
+    o.z = (lobe * b.z + lobe * d.z + lobe * h.z + lobe * f.z + e.z) * rcpL;
+    st_stream(out.row(y) + x, make_float4(o.x, o.y, o.z, 1.0f));
+}
+
+extern "C" int vq_fsr_rcas(VqContext* ctx, const uint32_t rcas_const[4], VqImage in, VqImage out, void* stream) {
+    int rc = vq_enter(ctx); if (rc) return rc;
+    VQ_REQUIRE(rcas_const, "rcas_const is null");
+    VQ_REQUIRE(vq_image_ok(in) && vq_image_ok(out), "bad image descriptor");
+    VQ_REQUIRE(in.width == out.width && in.height == out.height, "rcas: in/out size mismatch");
+    VQ_REQUIRE(in.ptr != out.ptr, "rcas: in-place is not supported");
+    float sharp; memcpy(&sharp, &rcas_const[0], 4);
+    const dim3 grid((out.width + ST_BX - 1) / ST_BX, (out.height + ST_BY - 1) / ST_BY);
+    rcas_kernel<<<grid, dim3(ST_BX, ST_BY), 0, (cudaStream_t)stream>>>(make_view(in), make_view(out), sharp);
+    return vq_check_launch("fsr_rcas");
+}
+
+// =============================================================================================
+// K8 EASU — FSR1.0/ffx_fsr1.h:239-437, wrapper AMDFidelityFX.hlsl:247-288.
+// FsrEasuCon puts every Gather4 coordinate on a texel corner, so the 4 gathers are 12 integer texel
+// fetches around (fx,fy) = floor(ip*con0.xy + con0.zw) under the sampler's addressing mode.
+// =============================================================================================
+template <int ADDR>
+__device__ __forceinline__ float3 load_addr(const ImgV& im, int x, int y) {
+    if (ADDR == VQ_ADDRESS_WRAP) {
+        x %= im.w; if (x < 0) x += im.w;
+        y %= im.h; if (y < 0) y += im.h;
+    } else {
+        x = min(max(x, 0), im.w - 1);
+        y = min(max(y, 0), im.h - 1);
+    }
+    return xyz(__ldg(im.row(y) + x));
+}
+
+__device__ __forceinline__ void easu_set(float2& dir, float& len, float w, float lA, float lB, float lC, float lD, float lE) {
+    // FsrEasuSetF, ffx_fsr1.h:275-313 (w = the bilinear weight selected by biS/biT/biU/biV)
+    const float dc = lD - lC, cb = lC - lB;
+    float lenX = fmaxf(fabsf(dc), fabsf(cb));
+    lenX = APrxLoRcpF1(lenX);
+    const float dirX = lD - lB;
+    dir.x = fmaf(dirX, w, dir.x);
+    lenX = saturate(fabsf(dirX) * lenX);
+    lenX *= lenX;
+    len = fmaf(lenX, w, len);
+    const float ec = lE - lC, ca = lC - lA;
+    float lenY = fmaxf(fabsf(ec), fabsf(ca));
+    lenY = APrxLoRcpF1(lenY);
+    const float dirY = lE - lA;
+    dir.y = fmaf(dirY, w, dir.y);
+    lenY = saturate(fabsf(dirY) * lenY);
+    lenY *= lenY;
+    len = fmaf(lenY, w, len);
+}
+__device__ __forceinline__ void easu_tap(float3& aC, float& aW, float offx, float offy, float2 dir, float2 len, float lob, float clp, float3 c) {
+    // FsrEasuTapF, ffx_fsr1.h:239-272
+    float vx = offx * dir.x + offy * dir.y;
+    float vy = offx * (-dir.y) + offy * dir.x;
+    vx *= len.x; vy *= len.y;
+    float d2 = vx * vx + vy * vy;
+    d2 = fminf(d2, clp);
+    float wB = fmaf(2.0f / 5.0f, d2, -1.0f);
+    float wA = fmaf(lob, d2, -1.0f);
+    wB *= wB; wA *= wA;
+    wB = fmaf(25.0f / 16.0f, wB, -(25.0f / 16.0f - 1.0f));
+    const float w = wB * wA;
+    aC.x = fmaf(c.x, w, aC.x); aC.y = fmaf(c.y, w, aC.y); aC.z = fmaf(c.z, w, aC.z);
+    aW += w;
+}
+__device__ __forceinline__ float luma2(float3 c) { return fmaf(c.z, 0.5f, fmaf(c.x, 0.5f, c.y)); }
+
+struct EasuCon { float c0x, c0y, c0z, c0w; };
+
+template <int ADDR>
+__global__ void __launch_bounds__(ST_BX * ST_BY) easu_kernel(ImgV in, ImgV out, EasuCon con) {
+    const int x = blockIdx.x * ST_BX + threadIdx.x, y = blockIdx.y * ST_BY + threadIdx.y;
+    if (x >= out.w || y >= out.h) return;
+    // position of 'f' (ffx_fsr1.h:323-326). Unfused mul+add so floor() sees the oracle's value.
+    float ppx = __fadd_rn(__fmul_rn((float)x, con.c0x), con.c0z);
+    float ppy = __fadd_rn(__fmul_rn((float)y, con.c0y), con.c0w);
+    const float fpx = floorf(ppx), fpy = floorf(ppy);
+    ppx -= fpx; ppy -= fpy;
+    const int fx = (int)fpx, fy = (int)fpy;
+    const float3 b = load_addr<ADDR>(in, fx, fy - 1), c = load_addr<ADDR>(in, fx + 1, fy - 1);
+    const float3 e = load_addr<ADDR>(in, fx - 1, fy), f = load_addr<ADDR>(in, fx, fy);
+    const float3 g = load_addr<ADDR>(in, fx + 1, fy), h = load_addr<ADDR>(in, fx + 2, fy);
+    const float3 i = load_addr<ADDR>(in, fx - 1, fy + 1), j = load_addr<ADDR>(in, fx, fy + 1);
+    const float3 k = load_addr<ADDR>(in, fx + 1, fy + 1), l = load_addr<ADDR>(in, fx + 2, fy + 1);
+    const float3 n = load_addr<ADDR>(in, fx, fy + 2), o = load_addr<ADDR>(in, fx + 1, fy + 2);
+    const float bL = luma2(b), cL = luma2(c), eL = luma2(e), fL = luma2(f), gL = luma2(g), hL = luma2(h);
+    const float iL = luma2(i), jL = luma2(j), kL = luma2(k), lL = luma2(l), nL = luma2(n), oL = luma2(o);
+    float2 dir = make_float2(0.0f, 0.0f);
+    float len = 0.0f;
+    easu_set(dir, len, (1.0f - ppx) * (1.0f - ppy), bL, eL, fL, gL, jL);
+    easu_set(dir, len, ppx * (1.0f - ppy), cL, fL, gL, hL, kL);
+    easu_set(dir, len, (1.0f - ppx) * ppy, fL, iL, jL, kL, nL);
+    easu_set(dir, len, ppx * ppy, gL, jL, kL, lL, oL);
+    float dirR = dir.x * dir.x + dir.y * dir.y;
+    const bool zro = dirR < (1.0f / 32768.0f);
+    dirR = APrxLoRsqF1(dirR);
+    dirR = zro ? 1.0f : dirR;
+    dir.x = zro ? 1.0f : dir.x;
+    dir.x *= dirR; dir.y *= dirR;
+    len = len * 0.5f;
+    len *= len;
+    const float stretch = (dir.x * dir.x + dir.y * dir.y) * APrxLoRcpF1(fmaxf(fabsf(dir.x), fabsf(dir.y)));
+    const float2 len2 = make_float2(fmaf(stretch - 1.0f, len, 1.0f), fmaf(-0.5f, len, 1.0f));
+    const float lob = fmaf((1.0f / 4.0f - 0.04f) - 0.5f, len, 0.5f);
+    const float clp = APrxLoRcpF1(lob);
+    const float3 min4 = fmin3(fmin3(f, fmin3(g, j)), k);
+    const float3 max4 = fmax3(fmax3(f, fmax3(g, j)), k);
+    float3 aC = f3(0.0f);
+    float aW = 0.0f;
+    easu_tap(aC, aW, 0.0f - ppx, -1.0f - ppy, dir, len2, lob, clp, b);
+    easu_tap(aC, aW, 1.0f - ppx, -1.0f - ppy, dir, len2, lob, clp, c);
+    easu_tap(aC, aW, -1.0f - ppx, 1.0f - ppy, dir, len2, lob, clp, i);
+    easu_tap(aC, aW, 0.0f - ppx, 1.0f - ppy, dir, len2, lob, clp, j);
+    easu_tap(aC, aW, 0.0f - ppx, 0.0f - ppy, dir, len2, lob, clp, f);
+    easu_tap(aC, aW, -1.0f - ppx, 0.0f - ppy, dir, len2, lob, clp, e);
+    easu_tap(aC, aW, 1.0f - ppx, 1.0f - ppy, dir, len2, lob, clp, k);
+    easu_tap(aC, aW, 2.0f - ppx, 1.0f - ppy, dir, len2, lob, clp, l);
+    easu_tap(aC, aW, 2.0f - ppx, 0.0f - ppy, dir, len2, lob, clp, h);
+    easu_tap(aC, aW, 1.0f - ppx, 0.0f - ppy, dir, len2, lob, clp, g);
+    easu_tap(aC, aW, 1.0f - ppx, 2.0f - ppy, dir, len2, lob, clp, o);
+    easu_tap(aC, aW, 0.0f - ppx, 2.0f - ppy, dir, len2, lob, clp, n);
+    const float rw = 1.0f / aW;   // ARcpF1, high precision
+    const float3 pix = fmin3(max4, fmax3(min4, aC * rw));
+    st_stream(out.row(y) + x, make_float4(pix.x, pix.y, pix.z, 1.0f));
+}
+
+extern "C" int vq_fsr_easu(VqContext* ctx, const uint32_t con[16], int address_mode, VqImage in, VqImage out, void* stream) {
+    int rc = vq_enter(ctx); if (rc) return rc;
+    VQ_REQUIRE(con, "easu_const is null");
+    VQ_REQUIRE(vq_image_ok(in) && vq_image_ok(out), "bad image descriptor");
+    VQ_REQUIRE(address_mode == VQ_ADDRESS_WRAP || address_mode == VQ_ADDRESS_CLAMP, "easu: unknown address mode");
+    VQ_REQUIRE(in.ptr != out.ptr, "easu: in-place is not supported");
+    EasuCon c; memcpy(&c, con, 16);
+    const dim3 grid((out.width + ST_BX - 1) / ST_BX, (out.height + ST_BY - 1) / ST_BY);
+    if (address_mode == VQ_ADDRESS_WRAP) easu_kernel<VQ_ADDRESS_WRAP><<<grid, dim3(ST_BX, ST_BY), 0, (cudaStream_t)stream>>>(make_view(in), make_view(out), c);
+    else                                 easu_kernel<VQ_ADDRESS_CLAMP><<<grid, dim3(ST_BX, ST_BY), 0, (cudaStream_t)stream>>>(make_view(in), make_view(out), c);
+    return vq_check_launch("fsr_easu");
+}
+
+// =============================================================================================
+// K10 SPD — SPD/ffx_spd.h:557-835 (LDS ordering), reduction (v0+v1+v2+v3)*0.25 (AMDFidelityFX.hlsl:463-466)
+//
+// One 256-thread block per 64x64 source tile. Thread t owns a 4x4 source patch; patches are laid out
+// in Morton order inside each warp, so levels 1-2 are pure register work and levels 3-4 are warp
+// shuffles; levels 5-6 go through 1 KB of shared memory. A global ticket (atomicAdd + __threadfence)
+// elects the last block, which reduces level 6 -> 7..12 out of shared memory.
+// Operand order per level: levels 1 and 7 sum (x,y),(x,y+1),(x+1,y),(x+1,y+1);
+// every other level sums (x,y),(x+1,y),(x,y+1),(x+1,y+1).
+// =============================================================================================
+struct SpdLevels { float4* p[12]; int w[12], h[12], pitch4[12]; };
+
+__device__ __forceinline__ float4 spd_reduce4(float4 v0, float4 v1, float4 v2, float4 v3) {
+    return make_float4(((v0.x + v1.x) + v2.x + v3.x) * 0.25f, ((v0.y + v1.y) + v2.y + v3.y) * 0.25f,
+                       ((v0.z + v1.z) + v2.z + v3.z) * 0.25f, ((v0.w + v1.w) + v2.w + v3.w) * 0.25f);
+}
+__device__ __forceinline__ float4 shfl4(float4 v, int lane) {
+    return make_float4(__shfl_sync(0xffffffffu, v.x, lane), __shfl_sync(0xffffffffu, v.y, lane),
+                       __shfl_sync(0xffffffffu, v.z, lane), __shfl_sync(0xffffffffu, v.w, lane));
+}
+__device__ __forceinline__ void spd_store(const SpdLevels& L, int lvl /*1-based*/, int mips, int x, int y, float4 v) {
+    if (lvl <= mips && x < L.w[lvl - 1] && y < L.h[lvl - 1]) L.p[lvl - 1][(size_t)y * L.pitch4[lvl - 1] + x] = v;
+}
+
+__global__ void __launch_bounds__(256) spd_kernel(ImgV src, SpdLevels L, int mips, uint32_t numWorkGroups,
+                                                  uint32_t offX, uint32_t offY, uint32_t* counter) {
+    __shared__ float4 s4[4][4];        // level-4 texels of this tile
+    __shared__ float4 s5[2][2];
+    __shared__ uint32_t sTicket;
+    __shared__ float4 sTail[32 * 32];  // level 7 and beyond, ping-pong halves handled by index ranges
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    // Morton decode of the lane (5 bits: x0 y0 x1 y1 x2) -> 8 wide x 4 high patches per warp
+    const int lx = (lane & 1) | ((lane >> 1) & 2) | ((lane >> 2) & 4);
+    const int ly = ((lane >> 1) & 1) | ((lane >> 2) & 2);
+    // warps tile the 16x16 patch grid as 2 columns x 4 rows of 8x4 patch blocks
+    const int px = (warp & 1) * 8 + lx, py = (warp >> 1) * 4 + ly;          // patch coords in the tile
+    const int tileX = blockIdx.x + offX, tileY = blockIdx.y + offY;
+    const int sx0 = tileX * 64 + px * 4, sy0 = tileY * 64 + py * 4;        // source texel of the patch
+
+    // ---- load the 4x4 patch (zeros outside the image: they only ever feed dropped texels) ----
+    float4 t[4][4];
+#pragma unroll
+    for (int j = 0; j < 4; ++j)
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+            const int sx = sx0 + i, sy = sy0 + j;
+            t[j][i] = (sx < src.w && sy < src.h) ? ld_stream(src.row(sy) + sx) : make_float4(0, 0, 0, 0);
+        }
+    // ---- level 1: 2x2 per thread, column-major operand order (ffx_spd.h:468-476) ----
+    float4 l1[2][2];
+#pragma unroll
+    for (int j = 0; j < 2; ++j)
+#pragma unroll
+        for (int i = 0; i < 2; ++i) {
+            l1[j][i] = spd_reduce4(t[2 * j][2 * i], t[2 * j + 1][2 * i], t[2 * j][2 * i + 1], t[2 * j + 1][2 * i + 1]);
+            spd_store(L, 1, mips, tileX * 32 + px * 2 + i, tileY * 32 + py * 2 + j, l1[j][i]);
+        }
+    if (mips <= 1) return;
+    // ---- level 2: 1 per thread, row-major operand order (ffx_spd.h:590-595) ----
+    const float4 l2 = spd_reduce4(l1[0][0], l1[0][1], l1[1][0], l1[1][1]);
+    spd_store(L, 2, mips, tileX * 16 + px, tileY * 16 + py, l2);
+    // ---- level 3: quad of lanes (Morton bits 0,1) ----
+    const int q = lane & ~3;
+    const float4 l3 = spd_reduce4(shfl4(l2, q), shfl4(l2, q | 1), shfl4(l2, q | 2), shfl4(l2, q | 3));
+    if (mips >= 3 && (lane & 3) == 0) spd_store(L, 3, mips, tileX * 8 + (px >> 1), tileY * 8 + (py >> 1), l3);
+    // ---- level 4: 16 lanes (Morton bits 2,3) ----
+    const int g = lane & ~15;
+    const float4 l4 = spd_reduce4(shfl4(l3, g), shfl4(l3, g | 4), shfl4(l3, g | 8), shfl4(l3, g | 12));
+    if ((lane & 15) == 0) {
+        if (mips >= 4) spd_store(L, 4, mips, tileX * 4 + (px >> 2), tileY * 4 + (py >> 2), l4);
+        s4[py >> 2][px >> 2] = l4;
+    }
+    __syncthreads();
+    // ---- level 5 and 6 through shared memory ----
+    if (tid < 4 && mips >= 5) {
+        const int x = tid & 1, y = tid >> 1;
+        const float4 v = spd_reduce4(s4[2 * y][2 * x], s4[2 * y][2 * x + 1], s4[2 * y + 1][2 * x], s4[2 * y + 1][2 * x + 1]);
+        spd_store(L, 5, mips, tileX * 2 + x, tileY * 2 + y, v);
+        s5[y][x] = v;
+    }
+    __syncthreads();
+    if (tid == 0 && mips >= 6) {
+        const float4 v = spd_reduce4(s5[0][0], s5[0][1], s5[1][0], s5[1][1]);
+        spd_store(L, 6, mips, tileX, tileY, v);
+    }
+    if (mips <= 6) return;
+
+    // ---- elect the last block (SpdExitWorkgroup, ffx_spd.h:391-400) ----
+    __threadfence();                       // publish this block's level-6 texel device-wide
+    __syncthreads();
+    if (tid == 0) sTicket = atomicAdd(counter, 1u);
+    __syncthreads();
+    if (sTicket != numWorkGroups - 1) return;
+    if (tid == 0) *counter = 0;            // SpdResetAtomicCounter: ready for the next launch
+    __threadfence();
+
+    // ---- tail: level 6 (<= 64x64, read through L2) -> 7 (column-major order), then 8..12 row-major ----
+    const int w6 = L.w[5], h6 = L.h[5];
+    const float4* p6 = L.p[5];
+    const int pitch6 = L.pitch4[5];
+    int cw = L.w[6], ch = L.h[6];          // level 7 size
+    for (int idx = tid; idx < cw * ch; idx += 256) {
+        const int x = idx % cw, y = idx / cw;
+        const float4 v0 = __ldcg(p6 + (size_t)(2 * y) * pitch6 + 2 * x);
+        const float4 v1 = __ldcg(p6 + (size_t)(2 * y + 1) * pitch6 + 2 * x);
+        const float4 v2 = __ldcg(p6 + (size_t)(2 * y) * pitch6 + 2 * x + 1);
+        const float4 v3 = __ldcg(p6 + (size_t)(2 * y + 1) * pitch6 + 2 * x + 1);
+        const float4 v = spd_reduce4(v0, v1, v2, v3);
+        spd_store(L, 7, mips, x, y, v);
+        sTail[y * 32 + x] = v;
+    }
+    (void)w6; (void)h6;
+    __syncthreads();
+    // levels 8.. : source rows live at stride 32 in sTail; results overwrite in place after a barrier
+    for (int lvl = 8; lvl <= mips; ++lvl) {
+        const int nw = L.w[lvl - 1], nh = L.h[lvl - 1];
+        float4 v = make_float4(0, 0, 0, 0);
+        const bool active = tid < nw * nh;             // nw*nh <= 16*16
+        int x = 0, y = 0;
+        if (active) {
+            x = tid % nw; y = tid / nw;
+            v = spd_reduce4(sTail[(2 * y) * 32 + 2 * x], sTail[(2 * y) * 32 + 2 * x + 1],
+                            sTail[(2 * y + 1) * 32 + 2 * x], sTail[(2 * y + 1) * 32 + 2 * x + 1]);
+            spd_store(L, lvl, mips, x, y, v);
+        }
+        __syncthreads();
+        if (active) sTail[y * 32 + x] = v;
+        __syncthreads();
+    }
+}
+
+extern "C" int vq_spd_downsample(VqContext* ctx, const VqSpdConstants* c, VqImage src, const VqImage* mips, void* stream) {
+    int rc = vq_enter(ctx); if (rc) return rc;
+    VQ_REQUIRE(c && mips, "constants/mips is null");
+    VQ_REQUIRE(vq_image_ok(src), "bad source image");
+    VQ_REQUIRE(c->mips >= 1 && c->mips <= 12, "spd: 1..12 destination mips");
+    VQ_REQUIRE(src.width <= 4096 && src.height <= 4096, "spd: source up to 4096^2 (ffx_spd.h limit)");
+    SpdLevels L; memset(&L, 0, sizeof(L));
+    for (uint32_t i = 0; i < c->mips; ++i) {
+        VQ_REQUIRE(vq_image_ok(mips[i]), "bad mip image");
+        VQ_REQUIRE(mips[i].width == (src.width >> (i + 1)) && mips[i].height == (src.height >> (i + 1)),
+                   "spd: mip i must be floor-halved (src >> (i+1))");
+        L.p[i] = (float4*)mips[i].ptr; L.w[i] = mips[i].width; L.h[i] = mips[i].height; L.pitch4[i] = (int)(mips[i].pitch_bytes / 16);
+    }
+    // group grid: same arithmetic as SpdSetup (ffx_spd.h:336-343) for a full-image rect at the given offset
+    const uint32_t gx = (uint32_t)(src.width + 63) / 64 - c->workGroupOffset[0];
+    const uint32_t gy = (uint32_t)(src.height + 63) / 64 - c->workGroupOffset[1];
+    VQ_REQUIRE(gx >= 1 && gy >= 1 && gx * gy == c->numWorkGroups, "spd: numWorkGroups does not match the image / offset (use vq_spd_setup)");
+    spd_kernel<<<dim3(gx, gy), 256, 0, (cudaStream_t)stream>>>(make_view(src), L, (int)c->mips, c->numWorkGroups,
+                                                               c->workGroupOffset[0], c->workGroupOffset[1], ctx->spd_counter);
+    return vq_check_launch("spd_downsample");
+}
