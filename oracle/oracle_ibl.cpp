@@ -9,11 +9,15 @@
 namespace orc {
 
 // DXGIUtils.cpp:289-317, bytesPerPixel == 16 branch: RGB = min of the 2x2 block, A = 1.
+// The reference loops `y < height; y += 2` and reads (x+1, y+1): for an odd width/height that reads (and,
+// through outY, writes) out of bounds. Its HDRIs are power-of-two sized so it never happens there; the
+// restatement visits only complete 2x2 blocks (destination = floor(w/2) x floor(h/2), the size the
+// reference allocates), which is identical for even sizes.
 void MipImage_MinFilter(const float* src, float* dst, int width, int height) {
     const int offsetsX[] = {0, 1, 0, 1};
     const int offsetsY[] = {0, 0, 1, 1};
-    for (int y = 0; y < height; y += 2)
-        for (int x = 0; x < width; x += 2) {
+    for (int y = 0; y + 1 < height; y += 2)
+        for (int x = 0; x + 1 < width; x += 2) {
             float rgb[4][3];
             for (int smp = 0; smp < 4; ++smp)
                 for (int ch = 0; ch < 3; ++ch)

@@ -144,10 +144,36 @@ struct Px {
     float3 albedoOverPi;
 };
 
-// BRDF(s, Wi, V) * NdotL_surface, BRDF.hlsl:163-194 with the V-only terms precomputed
-__device__ __forceinline__ float3 brdf_times_ndotl(const Px& s, float3 Wi) {
+// ---- exact re-evaluation of N.H -------------------------------------------------------------------
+// GGX's t = nh2*(a2-1)+1 cancels catastrophically near a highlight on a smooth surface (t ~ a2 ~ 1e-5),
+// so D amplifies a 1-ulp difference in N.H by up to 1e4. Where t is small the kernel therefore recomputes
+// N.H with the oracle's exact operation sequence (IEEE div/sqrt, no FMA contraction): V, Wo, N, Wi, H as
+// BRDF.hlsl:166-169 / Lighting.hlsl:312 write them. It is rare (a few % of pixel-light pairs), so the
+// fast path keeps rsqrt/FMA everywhere else.
+__device__ __forceinline__ float dot_u(float3 a, float3 b) {     // (x*x' + y*y') + z*z', two roundings per term
+    return __fadd_rn(__fadd_rn(__fmul_rn(a.x, b.x), __fmul_rn(a.y, b.y)), __fmul_rn(a.z, b.z));
+}
+__device__ __forceinline__ float3 div_u(float3 v, float d) { return f3(__fdiv_rn(v.x, d), __fdiv_rn(v.y, d), __fdiv_rn(v.z, d)); }
+__device__ __forceinline__ float3 normalize_u(float3 v) { return div_u(v, __fsqrt_rn(dot_u(v, v))); }
+
+constexpr float T_EXACT = 0.05f;
+
+__device__ __noinline__ float exact_ndoth(float3 cam, float3 P, float3 Ns, float3 wiSrc, float wiLenSq) {
+    const float3 Vv = f3(__fsub_rn(cam.x, P.x), __fsub_rn(cam.y, P.y), __fsub_rn(cam.z, P.z));
+    const float3 V = normalize_u(Vv);                 // ForwardLighting.hlsl:285
+    const float3 Wo = normalize_u(V);                 // BRDF.hlsl:166
+    const float3 N = normalize_u(Ns);                 // BRDF.hlsl:167
+    const float3 Wi = div_u(wiSrc, __fsqrt_rn(wiLenSq));
+    const float3 Hs = f3(__fadd_rn(Wo.x, Wi.x), __fadd_rn(Wo.y, Wi.y), __fadd_rn(Wo.z, Wi.z));
+    const float3 H = normalize_u(Hs);                 // BRDF.hlsl:168
+    return saturate(dot_u(N, H));
+}
+
+// BRDF(s, Wi, V) * NdotL_surface, BRDF.hlsl:163-194 with the V-only terms precomputed.
+// (wiSrc, wiLenSq): the un-normalised light vector and its exact squared length, Wi == wiSrc/sqrt(wiLenSq)
+__device__ __forceinline__ float3 brdf_times_ndotl(const Px& s, float3 Wi, float3 cam, float3 wiSrc, float wiLenSq) {
     const float3 H = normalize(s.V + Wi);
-    const float NdotH = saturate(dot(s.Nn, H));
+    float NdotH = saturate(dot(s.Nn, H));
     const float NL_raw = dot(s.Nn, Wi);
     const float NdotL = saturate(NL_raw);
     const float NL = fmaxf(0.0f, NL_raw);
@@ -155,7 +181,11 @@ __device__ __forceinline__ float3 brdf_times_ndotl(const Px& s, float3 Wi) {
     const float fc = pow5(1.0f - HV);                            // Fresnel_Schlick, BRDF.hlsl:132-136
     const float3 F = f3(fmaf(s.oneMinusF0.x, fc, s.F0.x), fmaf(s.oneMinusF0.y, fc, s.F0.y), fmaf(s.oneMinusF0.z, fc, s.F0.z));
     // D = a2 / (PI * (nh2*(a2-1)+1)^2)   (BRDF.hlsl:65-79),  G = gV * NL/((NL*(1-k)+k)+1e-4)  (:82-97,118-121)
-    const float t = fmaf(NdotH * NdotH, s.a2m1, 1.0f);
+    float t = fmaf(NdotH * NdotH, s.a2m1, 1.0f);
+    if (t < T_EXACT) {
+        NdotH = exact_ndoth(cam, s.P, s.Ns, wiSrc, wiLenSq);
+        t = __fadd_rn(__fmul_rn(__fmul_rn(NdotH, NdotH), s.a2m1), 1.0f);
+    }
     const float dDen = PI * (t * t);
     const float gDen = fmaf(NL, s.omk, s.k) + 0.0001f;
     const float sDen = fmaxf(4.0f * s.NdotV * NdotL, 0.0001f);
@@ -217,8 +247,7 @@ __global__ void __launch_bounds__(FWD_THREADS) forward_kernel(const __grid_const
     float3 dirWi = f3(0.0f), dirRadiance = f3(0.0f);
     if (dirEnabled) {                                            // Lighting.hlsl:334-345
         const float3 nd = f3(-L.directional.lightDirection.x, -L.directional.lightDirection.y, -L.directional.lightDirection.z);
-        const float dl = sqrtf(dot(nd, nd));
-        dirWi = f3(nd.x / dl, nd.y / dl, nd.z / dl);
+        dirWi = normalize_u(nd);                                 // exact: it also feeds exact_ndoth
         dirRadiance = f3(L.directional.color.x, L.directional.color.y, L.directional.color.z) * L.directional.brightness;
     }
 
@@ -239,7 +268,7 @@ __global__ void __launch_bounds__(FWD_THREADS) forward_kernel(const __grid_const
         s.F0 = lerp(f3(0.04f), s.albedo, s.metalness);           // BRDF.hlsl:177
         s.oneMinusF0 = f3(1.0f) - s.F0;
         const float a = s.roughness * s.roughness;
-        s.a2 = a * a; s.a2m1 = s.a2 - 1.0f;
+        s.a2 = __fmul_rn(a, a); s.a2m1 = __fsub_rn(s.a2, 1.0f);     // no contraction: feeds the exact t
         const float rp1 = s.roughness + 1.0f;
         s.k = (rp1 * rp1) * 0.125f; s.omk = 1.0f - s.k;
         const float nv = dot(s.Nn, s.V);
@@ -288,14 +317,14 @@ __global__ void __launch_bounds__(FWD_THREADS) forward_kernel(const __grid_const
                 const float invD = rsqrtf(d2);
                 const float3 Wi = Lv * invD;
                 const float3 radiance = l.color * ((invD * invD) * l.brightness);   // AttenuationBRDF = 1/D^2
-                I += brdf_times_ndotl(s, Wi) * radiance;
+                I += brdf_times_ndotl(s, Wi, P.cam, Lv, d2) * radiance;
             }
         }
         // ---- spot lights, then unshadowed spot casters (Lighting.hlsl:57-73,323-333) ----
         for (int i = 0; i < numSpot; ++i) {
             const SSpot l = sSpot[i];
             const float3 Lv = l.pos - s.P;
-            const float d2 = dot(Lv, Lv);
+            const float d2 = dot_u(Lv, Lv);
             const float invD = rsqrtf(d2);
             const float3 Wi = Lv * invD;
             const float theta = acosf(dot(-Wi, l.dir));          // pixelDirection = normalize(P - l.position)
@@ -304,10 +333,10 @@ __global__ void __launch_bounds__(FWD_THREADS) forward_kernel(const __grid_const
             else if (theta <= l.inner) inten = 1.0f;
             else inten = 1.0f - (theta - l.inner) / l.invCone;
             const float3 radiance = l.color * (inten * l.brightness * (invD * invD));
-            I += brdf_times_ndotl(s, Wi) * radiance;
+            I += brdf_times_ndotl(s, Wi, P.cam, Lv, d2) * radiance;
         }
         // ---- directional (PSMain :360-377 with ShadowingFactor = 1) ----
-        if (dirEnabled) I += brdf_times_ndotl(s, dirWi) * dirRadiance;
+        if (dirEnabled) I += brdf_times_ndotl(s, dirWi, P.cam, dirWi, 1.0f) * dirRadiance;
 
         st_stream(P.out.row(y) + x, make_float4(I.x, I.y, I.z, s.roughness));   // :380
     }

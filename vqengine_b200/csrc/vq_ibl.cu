@@ -87,7 +87,8 @@ __device__ __forceinline__ float3 sample_equirect_level(const PyrV& t, float u, 
 // DirectionToEquirectUV, ShadingMath.hlsl:70-80
 __device__ __forceinline__ void dir_to_equirect(float3 d, float& u, float& v) {
     u = atan2f(d.z, d.x) / (-TWO_PI) + 0.5f;
-    v = asinf(-d.y) / PI + 0.5f;
+    // |d.y| <= 1 holds for the oracle's exact normalize; rsqrt-normalised vectors can overshoot by an ulp
+    v = asinf(fminf(fmaxf(-d.y, -1.0f), 1.0f)) / PI + 0.5f;
 }
 
 // A35: look direction of a cube texel (CubemapUtility.cpp:40-48 + 90-degree projection)
