@@ -100,8 +100,10 @@ float4 ForwardLighting_PSMain(const VqPerFrameData& cbPerFrame, const VqPerViewL
 void   MipImage_MinFilter(const float* src, float* dst, int width, int height);       // DXGIUtils.cpp:289-317
 // phi/theta sequences of PSMain_DiffuseIrradiance's loops (CubemapConvolution.hlsl:129-135)
 void   DiffuseIrradianceAngles(float step, int n_phi, int n_theta, std::vector<float>& phis, std::vector<float>& thetas);
+// f64Accum = false: the HLSL's sequential fp32 running sum. true: diagnostic variant that adds the SAME fp32 terms in
+// double, to separate the reference's own summation error (O(n*eps) for 99k terms) from kernel error.
 float4 DiffuseIrradiance_PSMain(const Pyramid& hdri, float3 lookDir, const std::vector<float>& phis,
-                                const std::vector<float>& thetas, int srcMip);        // :112-163
+                                const std::vector<float>& thetas, int srcMip, bool f64Accum = false);   // :112-163
 float4 SpecularIrradiance_PSMain(const Pyramid& hdri, float3 lookDir, float Roughness,
                                  float2 TextureDimensionsLOD0, uint32_t numSamples);  // :168-223
 

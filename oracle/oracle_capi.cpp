@@ -76,7 +76,7 @@ int orc_diffuse_angle_counts(float step, int n_phi, int n_theta, int* out_phi, i
 }
 void orc_diffuse_irradiance(const float* pyramid, int w, int h, int levels,
                             float step, int n_phi, int n_theta, int src_mip,
-                            float* out_cube, int res, int row_begin, int row_end, int threads) {
+                            float* out_cube, int res, int row_begin, int row_end, int threads, int f64_accum) {
     const Pyramid p{pyramid, w, h, levels};
     std::vector<float> phis, thetas;
     DiffuseIrradianceAngles(step, n_phi, n_theta, phis, thetas);
@@ -85,7 +85,7 @@ void orc_diffuse_irradiance(const float* pyramid, int w, int h, int levels,
         for (int px = 0; px < res; ++px) {
             const float3 dir = CubeTexelDirection(face, px, py, res);
             st(out_cube + 4 * ((size_t)face * res * res + (size_t)py * res + px),
-               DiffuseIrradiance_PSMain(p, dir, phis, thetas, src_mip));
+               DiffuseIrradiance_PSMain(p, dir, phis, thetas, src_mip, f64_accum != 0));
         }
     });
 }

@@ -51,13 +51,14 @@ void DiffuseIrradianceAngles(float step, int n_phi, int n_theta, std::vector<flo
 
 // CubemapConvolution.hlsl:112-163
 float4 DiffuseIrradiance_PSMain(const Pyramid& hdri, float3 lookDir, const std::vector<float>& phis,
-                                const std::vector<float>& thetas, int srcMip) {
+                                const std::vector<float>& thetas, int srcMip, bool f64Accum) {
     const float3 N = normalize(lookDir);
     float3 up = make3(0, 1, 0);
     const float3 right = normalize(cross(up, N));
     up = normalize(cross(N, right));
 
     float3 irradiance = splat3(0.0f);
+    double acc64[3] = {0.0, 0.0, 0.0};   // diagnostic only (f64Accum): the same fp32 terms summed without fp32 rounding
     float numSamples = 0.0f;
     for (float phi : phis) {
         for (float theta : thetas) {
@@ -70,10 +71,13 @@ float4 DiffuseIrradiance_PSMain(const Pyramid& hdri, float3 lookDir, const std::
             sampleVec = normalize(sampleVec);
             const float mipLevel = (float)srcMip;
             const float3 L = xyz(SampleEquirectLevel(hdri, DirectionToEquirectUV(sampleVec), mipLevel));
-            irradiance += L * cosTheta * sinTheta;
+            const float3 term = L * cosTheta * sinTheta;
+            irradiance += term;
+            acc64[0] += term.x; acc64[1] += term.y; acc64[2] += term.z;
             numSamples += 1.0f;
         }
     }
+    if (f64Accum) irradiance = make3((float)acc64[0], (float)acc64[1], (float)acc64[2]);
     irradiance = irradiance * PI / numSamples;
     return make4(irradiance, 1.0f);
 }

@@ -11,6 +11,9 @@ for p in (ROOT, os.path.join(ROOT, "tests")):
 
 def pytest_configure(config):
     config.addinivalue_line("markers", "gpu: needs a CUDA device (run on the B200 box with -m gpu)")
+    # keep the in-tree libraries in step with the sources (no-op when they are up to date)
+    import __graft_entry__
+    __graft_entry__.build()
 
 
 @pytest.fixture(scope="session")

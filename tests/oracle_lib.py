@@ -91,10 +91,10 @@ def hdri_build_mips(level0: np.ndarray, levels: int) -> np.ndarray:
 
 
 def diffuse_irradiance(pyr, w, h, levels, res, step=0.0, n_phi=64, n_theta=16, src_mip=3,
-                       row_begin=0, row_end=None, threads=None) -> np.ndarray:
+                       row_begin=0, row_end=None, threads=None, f64_accum=False) -> np.ndarray:
     out = np.zeros((6 * res * res, 4), np.float32)
     lib().orc_diffuse_irradiance(_p(_f(pyr)), w, h, levels, f32(step), n_phi, n_theta, src_mip, _p(out), res,
-                                 row_begin, 6 * res if row_end is None else row_end, threads or cpu_threads())
+                                 row_begin, 6 * res if row_end is None else row_end, threads or cpu_threads(), int(f64_accum))
     return out
 
 

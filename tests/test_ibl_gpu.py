@@ -49,8 +49,14 @@ def test_diffuse_irradiance_reference_step_constant(ctx, vq, orc):
     o = host(out)
     assert np.allclose(o[:, 0] / 2.0, 0.99415, atol=2e-4) and np.allclose(o[:, 2] / 0.5, 0.99415, atol=2e-4)
     assert (o[:, 3] == 1.0).all()
-    ref = orc.diffuse_irradiance(host(d), w, h, levels, res, step=0.01, src_mip=3)
-    assert_abs("diffuse_ref_step", o, ref)
+    # 99 382 terms: the HLSL's sequential fp32 running sum carries its own O(n*eps) error, so the kernel (pairwise,
+    # i.e. more accurate) is held to 1e-4 against the same terms summed in double, and must be no further from the
+    # fp32-sequential oracle than that oracle is from the double sum (+ 2e-5).
+    ref32 = orc.diffuse_irradiance(host(d), w, h, levels, res, step=0.01, src_mip=3)
+    ref64 = orc.diffuse_irradiance(host(d), w, h, levels, res, step=0.01, src_mip=3, f64_accum=True)
+    print(assert_abs("diffuse_ref_step_vs_f64sum", o, ref64, tol=2e-5))
+    own = np.abs(ref32 - ref64).max()
+    assert np.abs(o - ref32).max() <= own + 2e-5, (np.abs(o - ref32).max(), own)
 
 
 def test_diffuse_row_ranges(ctx, vq, orc):

@@ -5,7 +5,7 @@ import numpy as np
 import pytest
 import torch
 
-from gpu_util import dev, host, assert_abs, assert_scaled
+from gpu_util import dev, host, assert_abs, assert_scaled, report
 
 pytestmark = pytest.mark.gpu
 
@@ -107,27 +107,38 @@ def test_spd(ctx, vq, orc, w, h):
 
 
 def test_post_chain_config4_small(ctx, vq, orc):
-    """BASELINE config 4 order at a small size: SPD -> BlurX,Y -> Tonemap -> CAS -> EASU 2x -> RCAS."""
+    """BASELINE config 4 order at a small size: SPD -> BlurX,Y -> Tonemap -> CAS -> EASU 2x -> RCAS.
+    Every stage is checked against the oracle applied to the SAME input (the kernel's previous-stage output):
+    CAS/EASU/RCAS contain sqrt-like and min/max non-smooth steps that amplify 1e-7 input differences, so an
+    end-to-end comparison of two independently rounded chains is reported, not asserted at 1e-4."""
     from vqengine_b200 import synth
     w, h = 480, 270
     img = synth.hdr_image(w, h, seed=4)
     d = dev(img)
     a, b, t, c = (torch.empty_like(d) for _ in range(4))
-    ctx.gaussian_blur(d, a, False)
-    ctx.gaussian_blur(a, b, True)
     tm = synth.default_tonemapper()
-    ctx.tonemap(tm, b, t)
-    ctx.cas(vq.cas_setup(0.8, w, h, w, h), t, c)
     e = torch.empty((2 * h, 2 * w, 4), dtype=torch.float32, device="cuda")
     r = torch.empty_like(e)
+    ctx.gaussian_blur(d, a, False)
+    assert_abs("chain.blur_x", host(a), orc.gaussian_blur(img, False), tol=1e-5)
+    ctx.gaussian_blur(a, b, True)
+    assert_abs("chain.blur_y", host(b), orc.gaussian_blur(host(a), True), tol=1e-5)
+    ctx.tonemap(tm, b, t)
+    assert_abs("chain.tonemap", host(t), orc.tonemap(tm, host(b)), tol=1e-5)
+    ctx.cas(vq.cas_setup(0.8, w, h, w, h), t, c)
+    assert_abs("chain.cas", host(c), orc.cas(orc.cas_setup(0.8, w, h, w, h), host(t)), tol=1e-5)
     ctx.fsr_easu(vq.fsr_easu_con(w, h, w, h, 2 * w, 2 * h), c, e)
+    assert_abs("chain.easu", host(e), orc.fsr_easu(orc.fsr_easu_con(w, h, w, h, 2 * w, 2 * h), host(c), 2 * w, 2 * h, 0), tol=2e-5)
     ctx.fsr_rcas(vq.fsr_rcas_con(0.2), e, r)
+    assert_abs("chain.rcas", host(r), orc.fsr_rcas(orc.fsr_rcas_con(0.2), host(e)), tol=1e-5)
     o = orc.gaussian_blur(orc.gaussian_blur(img, False), True)
     o = orc.tonemap(tm, o)
     o = orc.cas(orc.cas_setup(0.8, w, h, w, h), o)
     o = orc.fsr_easu(orc.fsr_easu_con(w, h, w, h, 2 * w, 2 * h), o, 2 * w, 2 * h, 0)
     o = orc.fsr_rcas(orc.fsr_rcas_con(0.2), o)
-    assert_abs("chain", host(r), o)
+    rep = report("chain_end_to_end", host(r), o)
+    print(rep)
+    assert rep["frac_abs_le_tol"] > 0.999 and rep["max_abs"] < 2e-2
 
 
 def test_bad_arguments(ctx, vq):

@@ -46,13 +46,13 @@ struct SSpot { float3 pos; float outer; float3 color; float brightness; float3 d
 __device__ __forceinline__ void dir_to_face(float3 d, int& face, float& sx, float& sy) {
     const float ax = fabsf(d.x), ay = fabsf(d.y), az = fabsf(d.z);
     if (ax >= ay && ax >= az) {
-        const float r = 1.0f / ax;     // IEEE division, as the oracle
+        const float r = rcp_fast(ax);
         if (d.x > 0) { face = 0; sx = -d.z * r; sy = d.y * r; } else { face = 1; sx = d.z * r; sy = d.y * r; }
     } else if (ay >= az) {
-        const float r = 1.0f / ay;
+        const float r = rcp_fast(ay);
         if (d.y > 0) { face = 2; sx = d.x * r; sy = -d.z * r; } else { face = 3; sx = d.x * r; sy = d.z * r; }
     } else {
-        const float r = 1.0f / az;
+        const float r = rcp_fast(az);
         if (d.z > 0) { face = 4; sx = d.x * r; sy = d.y * r; } else { face = 5; sx = -d.x * r; sy = d.y * r; }
     }
 }
@@ -138,80 +138,92 @@ __device__ __forceinline__ float2 sample_lut(const LutV& l, float u, float v) { 
 // per-pixel shading state with everything that does not depend on the light hoisted
 // ---------------------------------------------------------------------------------------------
 struct Px {
-    float3 P, Ns, Nn, V, albedo, F0, oneMinusF0;
-    float roughness, metalness;
-    float a2, a2m1, k, omk, NdotV, gV, diffScale;   // diffScale = (1-metal)/PI applied to (1-F)*albedo
-    float3 albedoOverPi;
+    float3 P, Ns, Nn, V;          // position, G-buffer normal, normalize(Ns), normalize(cam - P)
+    float3 F0, omF0, K1;          // F0, 1-F0, (1-F0)*albedo*(1-metal)/PI
+    float nsLen;                  // |Ns|: dot(Ns,Wi) = nsLen * dot(Nn,Wi)  (Lighting.hlsl:316 uses the raw s.N)
+    float nv, NdotV, gV;          // dot(Nn,V), saturate, Smith-G1 of V (BRDF.hlsl:82-97)
+    float a2, a2m1, k, omk;
 };
 
 // ---- exact re-evaluation of N.H -------------------------------------------------------------------
 // GGX's t = nh2*(a2-1)+1 cancels catastrophically near a highlight on a smooth surface (t ~ a2 ~ 1e-5),
 // so D amplifies a 1-ulp difference in N.H by up to 1e4. Where t is small the kernel therefore recomputes
-// N.H with the oracle's exact operation sequence (IEEE div/sqrt, no FMA contraction): V, Wo, N, Wi, H as
-// BRDF.hlsl:166-169 / Lighting.hlsl:312 write them. It is rare (a few % of pixel-light pairs), so the
-// fast path keeps rsqrt/FMA everywhere else.
-__device__ __forceinline__ float dot_u(float3 a, float3 b) {     // (x*x' + y*y') + z*z', two roundings per term
+// N.H with the oracle's exact operation sequence (correctly rounded div/sqrt, no FMA contraction): V, Wo,
+// N, Wi, H as BRDF.hlsl:166-169 / Lighting.hlsl:312 write them. T_EXACT = 0.02 bounds the fast path's
+// relative error in D by 2*dt/t <= 2*5e-7/0.02 = 5e-5; the slow path runs for < 1 % of pixel-light pairs.
+constexpr float T_EXACT = 0.02f;
+
+__device__ __forceinline__ float dot_u(float3 a, float3 b) {     // (x*x' + y*y') + z*z', every op rounded
     return __fadd_rn(__fadd_rn(__fmul_rn(a.x, b.x), __fmul_rn(a.y, b.y)), __fmul_rn(a.z, b.z));
 }
-__device__ __forceinline__ float3 div_u(float3 v, float d) { return f3(__fdiv_rn(v.x, d), __fdiv_rn(v.y, d), __fdiv_rn(v.z, d)); }
-__device__ __forceinline__ float3 normalize_u(float3 v) { return div_u(v, __fsqrt_rn(dot_u(v, v))); }
-
-constexpr float T_EXACT = 0.05f;
+// v / sqrt(dot(v,v)) with correctly rounded sqrt and divisions (== the oracle's normalize)
+__device__ __forceinline__ float3 normalize_u(float3 v) {
+    const float l = __fsqrt_rn(dot_u(v, v));
+    return f3(__fdiv_rn(v.x, l), __fdiv_rn(v.y, l), __fdiv_rn(v.z, l));
+}
 
 __device__ __noinline__ float exact_ndoth(float3 cam, float3 P, float3 Ns, float3 wiSrc, float wiLenSq) {
     const float3 Vv = f3(__fsub_rn(cam.x, P.x), __fsub_rn(cam.y, P.y), __fsub_rn(cam.z, P.z));
     const float3 V = normalize_u(Vv);                 // ForwardLighting.hlsl:285
     const float3 Wo = normalize_u(V);                 // BRDF.hlsl:166
     const float3 N = normalize_u(Ns);                 // BRDF.hlsl:167
-    const float3 Wi = div_u(wiSrc, __fsqrt_rn(wiLenSq));
+    const float wl = __fsqrt_rn(wiLenSq);
+    const float3 Wi = f3(__fdiv_rn(wiSrc.x, wl), __fdiv_rn(wiSrc.y, wl), __fdiv_rn(wiSrc.z, wl));
     const float3 Hs = f3(__fadd_rn(Wo.x, Wi.x), __fadd_rn(Wo.y, Wi.y), __fadd_rn(Wo.z, Wi.z));
     const float3 H = normalize_u(Hs);                 // BRDF.hlsl:168
     return saturate(dot_u(N, H));
 }
 
-// BRDF(s, Wi, V) * NdotL_surface, BRDF.hlsl:163-194 with the V-only terms precomputed.
-// (wiSrc, wiLenSq): the un-normalised light vector and its exact squared length, Wi == wiSrc/sqrt(wiLenSq)
-__device__ __forceinline__ float3 brdf_times_ndotl(const Px& s, float3 Wi, float3 cam, float3 wiSrc, float wiLenSq) {
-    const float3 H = normalize(s.V + Wi);
-    float NdotH = saturate(dot(s.Nn, H));
-    const float NL_raw = dot(s.Nn, Wi);
-    const float NdotL = saturate(NL_raw);
-    const float NL = fmaxf(0.0f, NL_raw);
-    const float HV = fmaxf(0.0f, dot(H, s.V));
-    const float fc = pow5(1.0f - HV);                            // Fresnel_Schlick, BRDF.hlsl:132-136
-    const float3 F = f3(fmaf(s.oneMinusF0.x, fc, s.F0.x), fmaf(s.oneMinusF0.y, fc, s.F0.y), fmaf(s.oneMinusF0.z, fc, s.F0.z));
-    // D = a2 / (PI * (nh2*(a2-1)+1)^2)   (BRDF.hlsl:65-79),  G = gV * NL/((NL*(1-k)+k)+1e-4)  (:82-97,118-121)
-    float t = fmaf(NdotH * NdotH, s.a2m1, 1.0f);
+struct Acc { float3 a, b, c; };   // sum over lights of w*col * {(1-fc), fc*spec, spec}
+
+// One light: accumulates BRDF(s, Wi, V) * radiance * NdotL (BRDF.hlsl:163-194, Lighting.hlsl:308-345) in the
+// factored form  r = K1*(1-fc) + omF0*(fc*spec) + F0*spec  with  F = F0 + (1-F0)*fc.
+//   Lv, d2 : un-normalised light vector and its squared length (Wi = Lv/sqrt(d2)),  invD = 1/sqrt(d2)
+//   scale  : attenuation * brightness * spot intensity;  col : light colour
+// H = normalize(V+Wi) is never formed: |V+Wi|^2 = 2+2c with c = V.Wi, so N.H = (N.V+N.Wi)*rh and
+// H.V = (1+c)*rh with rh = rsqrt(2+2c).
+__device__ __forceinline__ void shade_light(const Px& s, Acc& acc, float3 cam, float3 Lv, float d2, float invD,
+                                            float scale, float3 col) {
+    const float nl = dot(s.Nn, Lv) * invD;
+    if (nl <= 0.0f) return;                            // N.L = 0 -> the light contributes exactly 0
+    const float c = dot(s.V, Lv) * invD;
+    const float sq = fmaxf(fmaf(2.0f, c, 2.0f), 1e-20f);
+    const float rh = rsqrtf(sq);
+    float NdotH = saturate((s.nv + nl) * rh);
+    const float HV = fmaxf(0.0f, (1.0f + c) * rh);
+    const float fc = pow5(1.0f - HV);                  // Fresnel_Schlick (BRDF.hlsl:132-136)
+    float t = fmaf(NdotH * NdotH, s.a2m1, 1.0f);       // NormalDistributionGGX (BRDF.hlsl:65-79)
     if (t < T_EXACT) {
-        NdotH = exact_ndoth(cam, s.P, s.Ns, wiSrc, wiLenSq);
+        NdotH = exact_ndoth(cam, s.P, s.Ns, Lv, d2);
         t = __fadd_rn(__fmul_rn(__fmul_rn(NdotH, NdotH), s.a2m1), 1.0f);
     }
+    const float NL = fminf(nl, 1.0f);                  // saturate(N.L) == max(0,N.L) for unit vectors
     const float dDen = PI * (t * t);
-    const float gDen = fmaf(NL, s.omk, s.k) + 0.0001f;
-    const float sDen = fmaxf(4.0f * s.NdotV * NdotL, 0.0001f);
-    // D*G/denom with ONE reciprocal; `denom < EPSILON -> D = 1` (BRDF.hlsl:77) kept as a select
-    const bool tiny = dDen < 0.000000000001f;
+    const float gDen = fmaf(NL, s.omk, s.k) + 0.0001f; // Geometry_Smiths_SchlickGGX of L (BRDF.hlsl:82-97)
+    const float sDen = fmaxf(4.0f * s.NdotV * NL, 0.0001f);
+    const bool tiny = dDen < 0.000000000001f;          // `denom < EPSILON -> D = 1` (BRDF.hlsl:77)
     const float num = (tiny ? 1.0f : s.a2) * s.gV * NL;
     const float den = (tiny ? 1.0f : dDen) * gDen * sDen;
-    const float spec = __fdividef(num, den);
-    const float NdotLs = saturate(dot(s.Ns, Wi));                // Lighting.hlsl:316: un-normalised s.N
-    // Id = (1-F)*(1-metal)*albedo/PI
-    float3 r;
-    r.x = fmaf(1.0f - F.x, s.albedoOverPi.x, F.x * spec);
-    r.y = fmaf(1.0f - F.y, s.albedoOverPi.y, F.y * spec);
-    r.z = fmaf(1.0f - F.z, s.albedoOverPi.z, F.z * spec);
-    return r * NdotLs;
+    const float spec = __fdividef(num, den);           // D*G/denom with ONE reciprocal
+    const float w = saturate(s.nsLen * nl) * scale;    // NdotL of the raw s.N (Lighting.hlsl:316) * radiance scale
+    const float wa = (1.0f - fc) * w, wc = spec * w, wb = fc * wc;
+    const float3 cw = col;
+    acc.a.x = fmaf(wa, cw.x, acc.a.x); acc.a.y = fmaf(wa, cw.y, acc.a.y); acc.a.z = fmaf(wa, cw.z, acc.a.z);
+    acc.b.x = fmaf(wb, cw.x, acc.b.x); acc.b.y = fmaf(wb, cw.y, acc.b.y); acc.b.z = fmaf(wb, cw.z, acc.b.z);
+    acc.c.x = fmaf(wc, cw.x, acc.c.x); acc.c.y = fmaf(wc, cw.y, acc.c.y); acc.c.z = fmaf(wc, cw.z, acc.c.z);
 }
 
-__global__ void __launch_bounds__(FWD_THREADS) forward_kernel(const __grid_constant__ FwdParams P) {
+constexpr int FWD_BX = 64, FWD_BY = 4;   // 256 threads: 64 x 4 pixel tile; grid.x covers the row, grid.y strides rows
+
+__global__ void __launch_bounds__(FWD_THREADS, 3) forward_kernel(const __grid_constant__ FwdParams P) {
     __shared__ SPoint sPoint[MAX_POINT];
     __shared__ SSpot sSpot[MAX_SPOT];
-    __shared__ int sCounts[2];
 
     // ---- stage the light arrays (Scene::GatherLightData layout) into shared memory, once per block ----
     const VqSceneLighting& L = P.lights;
     const int nP = L.numPointLights, nPC = L.numPointCasters, nS = L.numSpotLights, nSC = L.numSpotCasters;
-    for (int i = threadIdx.x; i < nP + nPC; i += FWD_THREADS) {
+    const int tid = threadIdx.y * FWD_BX + threadIdx.x;
+    for (int i = tid; i < nP + nPC; i += FWD_THREADS) {
         const VqPointLight& l = i < nP ? L.point_lights[i] : L.point_casters[i - nP];
         SPoint s;
         s.pos = f3(l.position.x, l.position.y, l.position.z);
@@ -227,57 +239,54 @@ __global__ void __launch_bounds__(FWD_THREADS) forward_kernel(const __grid_const
         s.d2Limit = lim;
         sPoint[i] = s;
     }
-    for (int i = threadIdx.x; i < nS + nSC; i += FWD_THREADS) {
+    for (int i = tid; i < nS + nSC; i += FWD_THREADS) {
         const VqSpotLight& l = i < nS ? L.spot_lights[i] : L.spot_casters[i - nS];
         SSpot s;
         s.pos = f3(l.position.x, l.position.y, l.position.z);
         s.color = f3(l.color.x, l.color.y, l.color.z);
         s.brightness = l.brightness;
-        const float3 d = f3(l.spotDir.x, l.spotDir.y, l.spotDir.z);
-        const float dl = sqrtf(dot(d, d));
-        s.dir = f3(d.x / dl, d.y / dl, d.z / dl);               // normalize(l.spotDir), Lighting.hlsl:60
+        s.dir = normalize_u(f3(l.spotDir.x, l.spotDir.y, l.spotDir.z));   // normalize(l.spotDir), Lighting.hlsl:60
         s.outer = l.outerConeAngle; s.inner = l.innerConeAngle;
-        s.invCone = l.outerConeAngle - l.innerConeAngle;        // divisor kept as-is (IEEE division below)
+        s.invCone = 1.0f / (l.outerConeAngle - l.innerConeAngle);
         sSpot[i] = s;
     }
-    if (threadIdx.x == 0) { sCounts[0] = nP + nPC; sCounts[1] = nS + nSC; }
     __syncthreads();
-    const int numPoint = sCounts[0], numSpot = sCounts[1];
+    const int numPoint = nP + nPC, numSpot = nS + nSC;
     const bool dirEnabled = L.directional.enabled != 0;
     float3 dirWi = f3(0.0f), dirRadiance = f3(0.0f);
     if (dirEnabled) {                                            // Lighting.hlsl:334-345
-        const float3 nd = f3(-L.directional.lightDirection.x, -L.directional.lightDirection.y, -L.directional.lightDirection.z);
-        dirWi = normalize_u(nd);                                 // exact: it also feeds exact_ndoth
+        dirWi = normalize_u(f3(-L.directional.lightDirection.x, -L.directional.lightDirection.y, -L.directional.lightDirection.z));
         dirRadiance = f3(L.directional.color.x, L.directional.color.y, L.directional.color.z) * L.directional.brightness;
     }
 
-    const long long total = (long long)P.rows * P.width;
-    for (long long idx = (long long)blockIdx.x * FWD_THREADS + threadIdx.x; idx < total; idx += (long long)gridDim.x * FWD_THREADS) {
-        const int y = P.rowBegin + (int)(idx / P.width);
-        const int x = (int)(idx % P.width);
+    const int x = blockIdx.x * FWD_BX + threadIdx.x;
+    if (x >= P.width) return;
+    for (int ry = blockIdx.y * FWD_BY + threadIdx.y; ry < P.rows; ry += gridDim.y * FWD_BY) {
+        const int y = P.rowBegin + ry;
         const float4 pa = ld_stream(P.pos.row(y) + x);
         const float4 nr = ld_stream(P.nrm.row(y) + x);
         const float4 am = ld_stream(P.alb.row(y) + x);
 
         Px s;
-        s.P = xyz(pa); s.Ns = xyz(nr); s.albedo = xyz(am);
-        s.roughness = nr.w; s.metalness = am.w;
-        const float ao = pa.w;
+        s.P = xyz(pa); s.Ns = xyz(nr);
+        const float3 albedo = xyz(am);
+        const float roughness = nr.w, metalness = am.w, ao = pa.w;
         s.V = normalize(P.cam - s.P);                            // ForwardLighting.hlsl:285
-        s.Nn = normalize(s.Ns);                                  // BRDF.hlsl:167
-        s.F0 = lerp(f3(0.04f), s.albedo, s.metalness);           // BRDF.hlsl:177
-        s.oneMinusF0 = f3(1.0f) - s.F0;
-        const float a = s.roughness * s.roughness;
-        s.a2 = __fmul_rn(a, a); s.a2m1 = __fsub_rn(s.a2, 1.0f);     // no contraction: feeds the exact t
-        const float rp1 = s.roughness + 1.0f;
+        const float n2 = dot(s.Ns, s.Ns), rn = rsqrtf(n2);
+        s.Nn = s.Ns * rn;                                        // BRDF.hlsl:167
+        s.nsLen = n2 * rn;
+        s.F0 = lerp(f3(0.04f), albedo, metalness);               // BRDF.hlsl:177
+        s.omF0 = f3(1.0f) - s.F0;
+        s.K1 = s.omF0 * albedo * ((1.0f - metalness) * (1.0f / PI));   // (1-F0)*kD-part*albedo/PI (BRDF.hlsl:189-191)
+        const float a = roughness * roughness;
+        s.a2 = __fmul_rn(a, a); s.a2m1 = __fsub_rn(s.a2, 1.0f);  // no contraction: feeds the exact t
+        const float rp1 = roughness + 1.0f;
         s.k = (rp1 * rp1) * 0.125f; s.omk = 1.0f - s.k;
-        const float nv = dot(s.Nn, s.V);
-        s.NdotV = saturate(nv);
-        const float NV = fmaxf(0.0f, nv);
-        s.gV = NV / (fmaf(NV, s.omk, s.k) + 0.0001f);
-        s.albedoOverPi = s.albedo * ((1.0f - s.metalness) * (1.0f / PI));
+        s.nv = dot(s.Nn, s.V);
+        s.NdotV = saturate(s.nv);
+        s.gV = __fdividef(s.NdotV, fmaf(s.NdotV, s.omk, s.k) + 0.0001f);
 
-        float3 I = s.albedo * ao;                                // ForwardLighting.hlsl:290-293
+        float3 I = albedo * ao;                                  // ForwardLighting.hlsl:290-293
         if (P.hasEmissive) {
             const float4 em = ld_stream(P.emi.row(y) + x);
             I += xyz(em) * em.w;
@@ -285,39 +294,37 @@ __global__ void __launch_bounds__(FWD_THREADS) forward_kernel(const __grid_const
 
         // ---- environment map (Lighting.hlsl:360-395, BRDF.hlsl:196-207) ----
         {
-            const float NdotVs = saturate(dot(s.Ns, s.V));
+            const float NdotVs = saturate(s.nsLen * s.nv);       // saturate(dot(s.N, V))
             const float3 Nr = f3(s.Ns.x * P.cosB - s.Ns.z * P.sinB, s.Ns.y, s.Ns.x * P.sinB + s.Ns.z * P.cosB);
             const float3 diffIrr = sample_cube(P.diff, Nr, 0);
             float3 specCol = f3(0.0f); float2 sb = make_float2(0.0f, 0.0f);
             if (!P.diffuseOnly) {
                 const float3 R0 = reflect(-s.V, s.Ns);
                 const float3 R = f3(R0.x * P.cosB - R0.z * P.sinB, R0.y, R0.x * P.sinB + R0.z * P.cosB);
-                const int mip = (int)(s.roughness * (float)P.maxLod);
+                const int mip = (int)(roughness * (float)P.maxLod);
                 specCol = sample_cube(P.spec, R, mip);
-                sb = sample_lut(P.lut, NdotVs, s.roughness);
+                sb = sample_lut(P.lut, NdotVs, roughness);
             }
             const float fr = pow5(1.0f - NdotVs);                // FresnelWithRoughness, BRDF.hlsl:152-156
-            const float omr = 1.0f - s.roughness;
+            const float omr = 1.0f - roughness;
             const float3 Ks = f3(fmaf(fmaxf(omr, s.F0.x) - s.F0.x, fr, s.F0.x),
                                  fmaf(fmaxf(omr, s.F0.y) - s.F0.y, fr, s.F0.y),
                                  fmaf(fmaxf(omr, s.F0.z) - s.F0.z, fr, s.F0.z));
-            const float om = 1.0f - s.metalness;
-            I.x += (1.0f - Ks.x) * om * (diffIrr.x * s.albedo.x) + specCol.x * fmaf(Ks.x, sb.x, sb.y);
-            I.y += (1.0f - Ks.y) * om * (diffIrr.y * s.albedo.y) + specCol.y * fmaf(Ks.y, sb.x, sb.y);
-            I.z += (1.0f - Ks.z) * om * (diffIrr.z * s.albedo.z) + specCol.z * fmaf(Ks.z, sb.x, sb.y);
+            const float om = 1.0f - metalness;
+            I.x += (1.0f - Ks.x) * om * (diffIrr.x * albedo.x) + specCol.x * fmaf(Ks.x, sb.x, sb.y);
+            I.y += (1.0f - Ks.y) * om * (diffIrr.y * albedo.y) + specCol.y * fmaf(Ks.y, sb.x, sb.y);
+            I.z += (1.0f - Ks.z) * om * (diffIrr.z * albedo.z) + specCol.z * fmaf(Ks.z, sb.x, sb.y);
         }
 
+        Acc acc; acc.a = f3(0.0f); acc.b = f3(0.0f); acc.c = f3(0.0f);
         // ---- point lights, then unshadowed point casters (Lighting.hlsl:308-322; PSMain :310-313,321-340) ----
         for (int i = 0; i < numPoint; ++i) {
             const SPoint l = sPoint[i];
             const float3 Lv = l.pos - s.P;
-            // |L-P|^2 exactly as the oracle's dot(): (x*x + y*y) + z*z, no contraction
-            const float d2 = __fadd_rn(__fadd_rn(__fmul_rn(Lv.x, Lv.x), __fmul_rn(Lv.y, Lv.y)), __fmul_rn(Lv.z, Lv.z));
-            if (d2 < l.d2Limit) {
+            const float d2 = dot_u(Lv, Lv);                      // |L-P|^2 exactly as the oracle's dot()
+            if (d2 < l.d2Limit) {                                // == (length(Lw-P) < l.range), Lighting.hlsl:318
                 const float invD = rsqrtf(d2);
-                const float3 Wi = Lv * invD;
-                const float3 radiance = l.color * ((invD * invD) * l.brightness);   // AttenuationBRDF = 1/D^2
-                I += brdf_times_ndotl(s, Wi, P.cam, Lv, d2) * radiance;
+                shade_light(s, acc, P.cam, Lv, d2, invD, (invD * invD) * l.brightness, l.color);   // AttenuationBRDF = 1/D^2
             }
         }
         // ---- spot lights, then unshadowed spot casters (Lighting.hlsl:57-73,323-333) ----
@@ -326,19 +333,18 @@ __global__ void __launch_bounds__(FWD_THREADS) forward_kernel(const __grid_const
             const float3 Lv = l.pos - s.P;
             const float d2 = dot_u(Lv, Lv);
             const float invD = rsqrtf(d2);
-            const float3 Wi = Lv * invD;
-            const float theta = acosf(dot(-Wi, l.dir));          // pixelDirection = normalize(P - l.position)
-            float inten;
-            if (theta > l.outer) inten = 0.0f;
-            else if (theta <= l.inner) inten = 1.0f;
-            else inten = 1.0f - (theta - l.inner) / l.invCone;
-            const float3 radiance = l.color * (inten * l.brightness * (invD * invD));
-            I += brdf_times_ndotl(s, Wi, P.cam, Lv, d2) * radiance;
+            const float theta = acosf(fminf(fmaxf(-dot(Lv, l.dir) * invD, -1.0f), 1.0f));   // pixel direction = -Wi
+            float inten = 1.0f - (theta - l.inner) * l.invCone;
+            inten = theta > l.outer ? 0.0f : (theta <= l.inner ? 1.0f : inten);
+            shade_light(s, acc, P.cam, Lv, d2, invD, inten * l.brightness * (invD * invD), l.color);
         }
         // ---- directional (PSMain :360-377 with ShadowingFactor = 1) ----
-        if (dirEnabled) I += brdf_times_ndotl(s, dirWi, P.cam, dirWi, 1.0f) * dirRadiance;
+        if (dirEnabled) shade_light(s, acc, P.cam, dirWi, 1.0f, 1.0f, 1.0f, dirRadiance);
 
-        st_stream(P.out.row(y) + x, make_float4(I.x, I.y, I.z, s.roughness));   // :380
+        I.x += fmaf(s.K1.x, acc.a.x, fmaf(s.omF0.x, acc.b.x, s.F0.x * acc.c.x));
+        I.y += fmaf(s.K1.y, acc.a.y, fmaf(s.omF0.y, acc.b.y, s.F0.y * acc.c.y));
+        I.z += fmaf(s.K1.z, acc.a.z, fmaf(s.omF0.z, acc.b.z, s.F0.z * acc.c.z));
+        st_stream(P.out.row(y) + x, make_float4(I.x, I.y, I.z, roughness));   // :380
     }
 }
 
@@ -396,16 +402,13 @@ int vq_forward_launch(VqContext* ctx, const VqPerFrameData* pf, const VqPerViewL
     }
     P.rowBegin = row_begin; P.rows = row_end - row_begin; P.width = W;
 
-    static int blocksPerSM = 0;
-    if (!blocksPerSM) {
-        VQ_CUDA_OK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&blocksPerSM, forward_kernel, FWD_THREADS, 0));
-        if (blocksPerSM < 1) blocksPerSM = 1;
-    }
-    const long long total = (long long)P.rows * W;
-    long long blocks = (total + FWD_THREADS - 1) / FWD_THREADS;
-    const long long persistent = (long long)ctx->sm_count * blocksPerSM;   // one wave of resident CTAs
-    if (blocks > persistent) blocks = persistent;
-    forward_kernel<<<(unsigned)blocks, FWD_THREADS, 0, stream>>>(P);
+    // grid.x covers a row in 64-pixel tiles; grid.y strides 4-row groups: about 3 resident CTAs per SM, several waves
+    const unsigned gx = (unsigned)((W + FWD_BX - 1) / FWD_BX);
+    unsigned gy = (unsigned)((P.rows + FWD_BY - 1) / FWD_BY);
+    const unsigned targetBlocks = (unsigned)ctx->sm_count * 3u * 4u;
+    const unsigned gyCap = (targetBlocks + gx - 1) / gx;
+    if (gy > gyCap) gy = gyCap < 1 ? 1 : gyCap;
+    forward_kernel<<<dim3(gx, gy), dim3(FWD_BX, FWD_BY), 0, stream>>>(P);
     return vq_check_launch("forward_lighting");
 }
 

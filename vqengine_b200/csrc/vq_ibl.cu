@@ -186,6 +186,33 @@ struct SpecArgs {
     float roughness; float dimX, dimY; int numSamples;
 };
 
+// Roughness 0 (mip 0): every sample is the same direction (H = N, L = N, source mip 0), so the texel is the
+// weighted mean of numSamples IDENTICAL terms. One THREAD per texel samples the HDRI once and then replays the
+// HLSL's running sums sequentially (4 independent FADD chains), so their fp32 rounding is reproduced exactly.
+__global__ void __launch_bounds__(IBL_THREADS) specular_mip0_kernel(const __grid_constant__ SpecArgs A) {
+    const int tx = blockIdx.x * IBL_THREADS + threadIdx.x;
+    if (tx >= A.texels) return;
+    const int fr = A.rowBegin + tx / A.n, px = tx % A.n;
+    const int face = fr / A.n, py = fr % A.n;
+    const float3 N = normalize_exact(cube_texel_dir(face, px, py, A.n));
+    const float3 H = normalize_exact(N);                       // ImportanceSampleGGX with sinTheta = 0
+    const float3 Lv = H * (2.0f * dot(N, H)) - N;              // reflect(-V, H), V = N
+    const float NdotL = saturate(dot(N, Lv));
+    float4 o = make_float4(0.0f, 0.0f, 0.0f, 1.0f);
+    if (NdotL > 0.0f) {
+        float u, v; dir_to_equirect(Lv, u, v);
+        const float3 c = sample_equirect_level(A.hdri, u, v, 0.0f);
+        const float t0 = c.x * NdotL, t1 = c.y * NdotL, t2 = c.z * NdotL;
+        float a0 = 0.0f, a1 = 0.0f, a2 = 0.0f, aw = 0.0f;
+        for (int i = 0; i < A.numSamples; ++i) {
+            a0 = __fadd_rn(a0, t0); a1 = __fadd_rn(a1, t1); a2 = __fadd_rn(a2, t2); aw = __fadd_rn(aw, NdotL);
+        }
+        const float d = fmaxf(aw, 0.0001f);
+        o = make_float4(a0 / d, a1 / d, a2 / d, 1.0f);
+    }
+    A.out[(size_t)fr * A.n + px] = o;
+}
+
 __global__ void __launch_bounds__(IBL_THREADS) specular_prefilter_kernel(const __grid_constant__ SpecArgs A) {
     extern __shared__ float4 sH[];       // tangent-space half vectors: (cos(phi)*sinT, sin(phi)*sinT, cosT, -)
     // ImportanceSampleGGX (BRDF.hlsl:217-229): the part that depends only on (i, roughness)
@@ -211,21 +238,6 @@ __global__ void __launch_bounds__(IBL_THREADS) specular_prefilter_kernel(const _
         const int fr = A.rowBegin + tx / A.n, px = tx % A.n;
         const int face = fr / A.n, py = fr % A.n;
         const float3 N = normalize_exact(cube_texel_dir(face, px, py, A.n));   // N = R = V
-        if (A.roughness == 0.0f) {
-            // all samples are the same direction (H = N, L = N, mip 0): the weighted mean of identical
-            // terms; one sample gives the same value (see DESIGN.md "mip 0 of the specular prefilter")
-            if (lane == 0) {
-                const float3 H = normalize(N);
-                const float3 Lv = H * (2.0f * dot(N, H)) - N;
-                const float NdotL = saturate(dot(N, Lv));
-                float u, v; dir_to_equirect(Lv, u, v);
-                const float3 c = sample_equirect_level(A.hdri, u, v, 0.0f);
-                const float wsum = NdotL * fN, inv = 1.0f / fmaxf(wsum, 0.0001f);
-                A.out[(size_t)fr * A.n + px] = NdotL > 0.0f ? make_float4(c.x * wsum * inv, c.y * wsum * inv, c.z * wsum * inv, 1.0f)
-                                                             : make_float4(0, 0, 0, 1.0f);
-            }
-            continue;
-        }
         // tangent frame (BRDF.hlsl:231-234)
         const float3 upv = fabsf(N.z) < 0.999f ? f3(0, 0, 1) : f3(1, 0, 0);
         const float3 T = normalize_exact(cross(upv, N));
@@ -390,10 +402,14 @@ extern "C" int vq_specular_prefilter(VqContext* ctx, VqPyramid hd, VqCubemap out
             A.numSamples = num_samples;
             const size_t smem = (size_t)num_samples * sizeof(float4);
             if (smem > 48 * 1024) VQ_CUDA_OK(cudaFuncSetAttribute(specular_prefilter_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-            int blocks = (A.texels + IBL_WARPS - 1) / IBL_WARPS;
-            const int cap = ctx->sm_count * 8;
-            if (blocks > cap) blocks = cap;
-            specular_prefilter_kernel<<<blocks, IBL_THREADS, smem, (cudaStream_t)stream>>>(A);
+            if (A.roughness == 0.0f) {
+                specular_mip0_kernel<<<(A.texels + IBL_THREADS - 1) / IBL_THREADS, IBL_THREADS, 0, (cudaStream_t)stream>>>(A);
+            } else {
+                int blocks = (A.texels + IBL_WARPS - 1) / IBL_WARPS;
+                const int cap = ctx->sm_count * 8;
+                if (blocks > cap) blocks = cap;
+                specular_prefilter_kernel<<<blocks, IBL_THREADS, smem, (cudaStream_t)stream>>>(A);
+            }
             rc = vq_check_launch("specular_prefilter"); if (rc) return rc;
         }
         mipRow0 += rows;
