@@ -115,6 +115,9 @@ def build_env_maps_gpu(ctx, vq, torch, hdri_w=2048, hdri_h=1024, diff_res=64, sp
                 diff_res=diff_res, spec_res=spec_res, spec_mips=spec_mips, levels=levels, hdri_w=hdri_w, hdri_h=hdri_h)
     keep["env"] = vq.EnvironmentMaps(vq.cubemap_of(keep["diff"], diff_res, 1), vq.cubemap_of(spec, spec_res, spec_mips),
                                      vq.image_of(lut_t, 2))
+    # the RENDER_TARGET -> SHADER_RESOURCE transition after prefiltering: bordered sampling copies, built once
+    ctx.environment_prepare(keep["env"])
+    torch.cuda.synchronize()
     return keep
 
 
@@ -204,11 +207,16 @@ def cpu_reference_forward(planes, rows_target_s=12.0, env=None, threads=None):
     orc.forward_lighting(pf, pv, planes, *args, 0, probe_rows, threads)
     rate = probe_rows * W4K / (time.perf_counter() - t0)
     rows = int(min(planes[0].shape[0], max(probe_rows, rows_target_s * rate / W4K)))
-    t0 = time.perf_counter()
-    orc.forward_lighting(pf, pv, planes, *args, 0, rows, threads)
-    dt = time.perf_counter() - t0
-    return {"value": round(rows * W4K / dt / 1e6, 4), "unit": UNIT, "cores": threads, "kind": "port",
-            "sample": f"{rows} of {H4K} rows x {W4K} px of the same 4K G-buffer ({rows * W4K} px in {dt:.1f} s), scalar C++ oracle, std::thread row split"}
+    # repeat the (bounded) sample until about rows_target_s of CPU work has been timed
+    t0 = time.perf_counter(); reps = 0
+    while True:
+        orc.forward_lighting(pf, pv, planes, *args, 0, rows, threads)
+        reps += 1
+        dt = time.perf_counter() - t0
+        if dt >= rows_target_s or reps >= 200:
+            break
+    return {"value": round(reps * rows * W4K / dt / 1e6, 4), "unit": UNIT, "cores": threads, "kind": "port",
+            "sample": f"{reps} x ({rows} of {H4K} rows x {W4K} px of the same 4K G-buffer) = {reps * rows * W4K} px in {dt:.1f} s, scalar C++ oracle, std::thread row split"}
 
 
 def cpu_env():

@@ -121,6 +121,15 @@ VQ_API int vq_forward_lighting(VqContext* ctx,
                                int row_begin, int row_end,
                                void* stream);
 
+/* The forward pass samples the IBL cubemaps from bordered copies (each face carries a 1-texel border of its
+ * neighbours, so seamless bilinear taps never leave the face). vq_environment_prepare builds those copies once and
+ * registers them in the context — the analogue of the RENDER_TARGET -> PIXEL_SHADER_RESOURCE barrier the engine
+ * records after prefiltering (EnvironmentMapRendering.cpp:466-472). Call it again whenever the maps' contents
+ * change, or vq_environment_invalidate to drop the registration. Without it vq_forward_lighting re-pads the cubes
+ * into context scratch on every call (always correct; serialise such calls per context). */
+VQ_API int vq_environment_prepare(VqContext* ctx, const VqEnvironmentMaps* env, void* stream);
+VQ_API int vq_environment_invalidate(VqContext* ctx);
+
 /* ------------------------------------------------------------------------------------------
  * K11 HDRI mip pyramid, 2x2 MIN filter, alpha = 1.  Replaces VQ_DXGI_UTILS::MipImage
  *     (DXGIUtils.cpp:289-317) called from TextureManager.cpp:714-727. Level 0 must be filled.

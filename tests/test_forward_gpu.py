@@ -42,6 +42,32 @@ def test_forward_config3_shape(ctx, vq, orc, w, h):
     print(r)
 
 
+def test_forward_prepared_environment_equals_per_call_padding(ctx, vq, orc):
+    """vq_environment_prepare (bordered cube copies built once) must not change a single bit of the result,
+    and a stale registration must not be used for different maps."""
+    from vqengine_b200 import synth
+    env = small_env()
+    w, h = 96, 54
+    planes = synth.gbuffer(w, h, seed=5)
+    pf, pv = synth.scene_constants(w, h, env["spec_mips"], seed=5)
+    dplanes = [dev(p) for p in planes]
+    gb = vq.GBuffer(vq.image_of(dplanes[0]), vq.image_of(dplanes[1]), vq.image_of(dplanes[2]), vq.null_image())
+    dd, ds, dl = dev(env["diff"]), dev(env["spec"]), dev(env["lut"])
+    em = vq.EnvironmentMaps(vq.cubemap_of(dd, env["diff_res"], 1), vq.cubemap_of(ds, env["spec_res"], env["spec_mips"]), vq.image_of(dl, 2))
+    a, b, c = (torch.zeros((h, w, 4), dtype=torch.float32, device="cuda") for _ in range(3))
+    ctx.environment_invalidate()
+    ctx.forward_lighting(pf, pv, gb, em, a)
+    ctx.environment_prepare(em)
+    ctx.forward_lighting(pf, pv, gb, em, b)
+    assert np.array_equal(host(a), host(b))
+    # different maps at different addresses: the registration does not match -> padded per call -> different result
+    ds2 = dev(env["spec"] * 0.5)
+    em2 = vq.EnvironmentMaps(vq.cubemap_of(dd, env["diff_res"], 1), vq.cubemap_of(ds2, env["spec_res"], env["spec_mips"]), vq.image_of(dl, 2))
+    ctx.forward_lighting(pf, pv, gb, em2, c)
+    assert not np.array_equal(host(c), host(b))
+    ctx.environment_invalidate()
+
+
 def test_forward_all_light_types(ctx, vq, orc):
     got, ref = _run(ctx, vq, orc, 160, 90, n_point=7, n_spot=3, emissive=True, offset=0.7, casters=True)
     assert_scaled("forward_all", got, ref)

@@ -137,7 +137,8 @@ ABI_SYMBOLS = [
     "vq_brdf_integration_lut", "vq_gaussian_blur_x", "vq_gaussian_blur_y", "vq_tonemap", "vq_cas",
     "vq_fsr_easu", "vq_fsr_rcas", "vq_spd_downsample", "vq_fsr_easu_con", "vq_fsr_rcas_con", "vq_cas_setup",
     "vq_spd_setup", "vq_mip_level_count", "vq_cubemap_texel_count", "vq_cubemap_offset", "vq_cubemap_row_count",
-    "vq_pyramid_texel_count", "vq_pyramid_offset", "vq_forward_lighting_host",
+    "vq_pyramid_texel_count", "vq_pyramid_offset", "vq_forward_lighting_host", "vq_environment_prepare",
+    "vq_environment_invalidate",
 ]
 
 
@@ -165,6 +166,8 @@ def _load() -> C.CDLL:
                                         Image, C.c_int, C.c_int, vp]
     lib.vq_forward_lighting_host.argtypes = [vp, P(PerFrameData), P(PerViewLightingData), P(GBuffer),
                                              P(EnvironmentMaps), Image]
+    lib.vq_environment_prepare.argtypes = [vp, P(EnvironmentMaps), vp]
+    lib.vq_environment_invalidate.argtypes = [vp]
     lib.vq_hdri_build_mips.argtypes = [vp, Pyramid, vp]
     lib.vq_diffuse_irradiance.argtypes = [vp, P(DiffuseIrradianceParams), Pyramid, Cubemap, C.c_int, C.c_int, vp]
     lib.vq_specular_prefilter.argtypes = [vp, Pyramid, Cubemap, C.c_int, C.c_int, C.c_int, vp]
@@ -317,6 +320,12 @@ class Context:
     def forward_lighting_host(self, per_frame, per_view, host_gbuffer: GBuffer, env: EnvironmentMaps, host_out):
         _check(lib.vq_forward_lighting_host(self._h, C.byref(per_frame), C.byref(per_view), C.byref(host_gbuffer),
                                             C.byref(env), image_of(host_out)))
+
+    def environment_prepare(self, env: EnvironmentMaps, stream=None):
+        _check(lib.vq_environment_prepare(self._h, C.byref(env), _stream_ptr(stream)))
+
+    def environment_invalidate(self):
+        _check(lib.vq_environment_invalidate(self._h))
 
     # K11 / K2 / K3 / K4
     def hdri_build_mips(self, pyr: Pyramid, stream=None):

@@ -21,6 +21,9 @@ constexpr int FWD_THREADS = 256;
 constexpr int MAX_POINT = VQ_NUM_LIGHTS_POINT + VQ_NUM_SHADOWING_LIGHTS_POINT;   // casters appended (shadow factor 1)
 constexpr int MAX_SPOT = VQ_NUM_LIGHTS_SPOT + VQ_NUM_SHADOWING_LIGHTS_SPOT;
 
+// Bordered sampling copy of a cubemap: every face of every mip is stored as (N+2)x(N+2) texels, the 1-texel
+// border holding the neighbouring faces' edge texels (corners: the mean of the three texels that meet there), so
+// that the seamless bilinear footprint never leaves the face. mipOffset[] are texel offsets of face 0 per mip.
 struct CubeV { const float4* p; int res, mips; uint32_t mipOffset[16]; };
 struct LutV { const float2* p; int w, h, pitch2; };
 
@@ -57,8 +60,9 @@ __device__ __forceinline__ void dir_to_face(float3 d, int& face, float& sx, floa
     }
 }
 
-// integer-only neighbour lookup for a tap one texel outside the face (see DESIGN.md "cube edges")
-__device__ __noinline__ void cube_resolve_edge(int N, int face, int i, int j, int& of, int& oi, int& oj) {
+// integer-only neighbour lookup for a tap one texel outside the face (see DESIGN.md "cube edges"); used only by
+// the border-padding kernel, never per pixel
+__device__ void cube_resolve_edge(int N, int face, int i, int j, int& of, int& oi, int& oj) {
     const int A = 2 * i + 1 - N, B = N - 1 - 2 * j, C = N;
     int dx, dy, dz;
     switch (face) {
@@ -81,45 +85,53 @@ __device__ __noinline__ void cube_resolve_edge(int N, int face, int i, int j, in
     oj = min(max(((M - nsy) * N) / (2 * M), 0), N - 1);
 }
 
+// packed cube (mip-major / face-minor, N x N faces) -> bordered sampling copy ((N+2) x (N+2) faces)
+__global__ void __launch_bounds__(256) cube_pad_kernel(const float4* __restrict__ src, float4* __restrict__ dst,
+                                                        int res, int mips, uint32_t totalPadded) {
+    for (uint32_t idx = blockIdx.x * 256u + threadIdx.x; idx < totalPadded; idx += gridDim.x * 256u) {
+        // locate (mip, face, pj, pi) of this padded texel
+        uint32_t rem = idx, srcOff = 0; int m = 0, N = res;
+        for (; m < mips; ++m) {
+            N = res >> m;
+            const uint32_t sz = 6u * (uint32_t)(N + 2) * (uint32_t)(N + 2);
+            if (rem < sz) break;
+            rem -= sz; srcOff += 6u * (uint32_t)N * (uint32_t)N;
+        }
+        const int P = N + 2;
+        const int face = (int)(rem / (uint32_t)(P * P));
+        const int r2 = (int)(rem % (uint32_t)(P * P));
+        const int i = r2 % P - 1, j = r2 / P - 1;           // face-relative texel, -1..N
+        const float4* sm = src + srcOff;
+        auto fetch = [&](int f, int x, int y) { return __ldg(sm + (size_t)f * N * N + (size_t)y * N + x); };
+        auto edge = [&](int x, int y) { int f2, i2, j2; cube_resolve_edge(N, face, x, y, f2, i2, j2); return fetch(f2, i2, j2); };
+        const bool oi = (i < 0 || i >= N), oj = (j < 0 || j >= N);
+        float4 v;
+        if (!oi && !oj) v = fetch(face, i, j);
+        else if (oi != oj) v = edge(i, j);
+        else {   // cube corner: mean of the three texels meeting there (own corner + the two edge neighbours)
+            const int ci = i < 0 ? 0 : N - 1, cj = j < 0 ? 0 : N - 1;
+            const float4 a = fetch(face, ci, cj), b = edge(i, cj), c = edge(ci, j);
+            v = make_float4((a.x + b.x + c.x) * (1.0f / 3.0f), (a.y + b.y + c.y) * (1.0f / 3.0f),
+                            (a.z + b.z + c.z) * (1.0f / 3.0f), (a.w + b.w + c.w) * (1.0f / 3.0f));
+        }
+        dst[idx] = v;
+    }
+}
+
 __device__ __forceinline__ float3 sample_cube(const CubeV& c, float3 dir, int mip) {
     mip = min(max(mip, 0), c.mips - 1);
-    const int N = c.res >> mip;
+    const int N = c.res >> mip, P = N + 2;
     int face; float sx, sy;
     dir_to_face(dir, face, sx, sy);
     const float x = fmaf(fmaf(sx, 0.5f, 0.5f), (float)N, -0.5f);
     const float y = fmaf(fmaf(-sy, 0.5f, 0.5f), (float)N, -0.5f);
-    const int i0 = min(max((int)floorf(x), -1), N - 1);
-    const int j0 = min(max((int)floorf(y), -1), N - 1);
-    const float fx = x - (float)i0, fy = y - (float)j0;
-    const float4* base = c.p + c.mipOffset[mip];
-    const size_t faceSz = (size_t)N * N;
-    float4 t[4];
-    if (i0 >= 0 && j0 >= 0 && i0 + 1 < N && j0 + 1 < N) {     // interior: the common case
-        const float4* p = base + face * faceSz + (size_t)j0 * N + i0;
-        t[0] = __ldg(p); t[1] = __ldg(p + 1); t[2] = __ldg(p + N); t[3] = __ldg(p + N + 1);
-    } else {
-        bool corner[4]; bool any = false;
-#pragma unroll
-        for (int k = 0; k < 4; ++k) {
-            const int i = i0 + (k & 1), j = j0 + (k >> 1);
-            const bool oi = (i < 0 || i >= N), oj = (j < 0 || j >= N);
-            corner[k] = oi && oj;
-            if (corner[k]) { any = true; t[k] = make_float4(0, 0, 0, 0); continue; }
-            int f2 = face, i2 = i, j2 = j;
-            if (oi || oj) cube_resolve_edge(N, face, i, j, f2, i2, j2);
-            t[k] = __ldg(base + f2 * faceSz + (size_t)j2 * N + i2);
-        }
-        if (any) {
-            float4 s = make_float4(0, 0, 0, 0);
-#pragma unroll
-            for (int k = 0; k < 4; ++k) if (!corner[k]) s = s + t[k];
-            s = s * (1.0f / 3.0f);
-#pragma unroll
-            for (int k = 0; k < 4; ++k) if (corner[k]) t[k] = s;
-        }
-    }
-    const float4 top = lerp(t[0], t[1], fx), bot = lerp(t[2], t[3], fx);
-    return xyz(lerp(top, bot, fy));
+    const float xf = fminf(fmaxf(floorf(x), -1.0f), (float)(N - 1)), yf = fminf(fmaxf(floorf(y), -1.0f), (float)(N - 1));
+    const float fx = x - xf, fy = y - yf;
+    const int i0 = (int)xf + 1, j0 = (int)yf + 1;            // bordered coordinates: 0..N
+    const float4* p = c.p + c.mipOffset[mip] + (size_t)face * (P * P) + j0 * P + i0;
+    const float4 t00 = __ldg(p), t10 = __ldg(p + 1), t01 = __ldg(p + P), t11 = __ldg(p + P + 1);
+    const float3 top = lerp(xyz(t00), xyz(t10), fx), bot = lerp(xyz(t01), xyz(t11), fx);
+    return lerp(top, bot, fy);
 }
 
 __device__ __forceinline__ float2 sample_lut(const LutV& l, float u, float v) {   // bilinear, CLAMP
@@ -348,13 +360,39 @@ __global__ void __launch_bounds__(FWD_THREADS, 3) forward_kernel(const __grid_co
     }
 }
 
-int fill_cube(const VqCubemap& c, CubeV& v, const char* what) {
-    if (!c.ptr || c.res < 1 || c.mips < 1 || c.mips > 16 || (c.res >> (c.mips - 1)) < 1) {
-        vq_set_error("invalid argument: bad cubemap descriptor (%s)", what);
-        return VQ_ERR_INVALID_ARG;
+uint64_t padded_texels(int res, int mips) {
+    uint64_t n = 0;
+    for (int m = 0; m < mips; ++m) { const uint64_t p = (uint64_t)(res >> m) + 2; n += 6 * p * p; }
+    return n;
+}
+bool cube_desc_ok(const VqCubemap& c) {
+    return c.ptr && c.res >= 1 && c.mips >= 1 && c.mips <= 16 && (c.res >> (c.mips - 1)) >= 1 &&
+           padded_texels(c.res, c.mips) < (1ull << 31);
+}
+// builds the bordered sampling copy of `c` into `dst` (padded_texels() float4s) on `stream`
+int pad_cube(const VqCubemap& c, float4* dst, cudaStream_t stream) {
+    const uint32_t total = (uint32_t)padded_texels(c.res, c.mips);
+    unsigned blocks = (total + 255u) / 256u;
+    if (blocks > 148u * 16u) blocks = 148u * 16u;
+    cube_pad_kernel<<<blocks, 256, 0, stream>>>((const float4*)c.ptr, dst, c.res, c.mips, total);
+    return vq_check_launch("cube_pad");
+}
+void fill_cube_view(const VqCubemap& c, const float4* padded, CubeV& v) {
+    v.p = padded; v.res = c.res; v.mips = c.mips;
+    uint32_t off = 0;
+    for (int m = 0; m < 16; ++m) {
+        v.mipOffset[m] = m < c.mips ? off : 0u;
+        if (m < c.mips) { const uint32_t p = (uint32_t)(c.res >> m) + 2u; off += 6u * p * p; }
     }
-    v.p = (const float4*)c.ptr; v.res = c.res; v.mips = c.mips;
-    for (int m = 0; m < 16; ++m) v.mipOffset[m] = m < c.mips ? (uint32_t)vq_cubemap_offset(c.res, m, 0) : 0u;
+}
+bool same_cube(const VqCubemap& a, const VqCubemap& b) { return a.ptr == b.ptr && a.res == b.res && a.mips == b.mips; }
+
+int ensure_bytes(void** ptr, size_t* have, size_t need) {
+    if (*have >= need && *ptr) return VQ_OK;
+    if (*ptr) cudaFree(*ptr);
+    *ptr = nullptr; *have = 0;
+    if (cudaMalloc(ptr, need) != cudaSuccess) { cudaGetLastError(); vq_set_error("cudaMalloc(%zu) failed", need); return VQ_ERR_OUT_OF_MEMORY; }
+    *have = need;
     return VQ_OK;
 }
 
@@ -393,12 +431,29 @@ int vq_forward_launch(VqContext* ctx, const VqPerFrameData* pf, const VqPerViewL
         VQ_REQUIRE(vq_image_ok(gb->emissive) && gb->emissive.width == W && gb->emissive.height == H, "bad emissive plane");
         P.emi = make_view(gb->emissive);
     }
-    int rc = fill_cube(env->irradiance_diffuse, P.diff, "irradiance_diffuse"); if (rc) return rc;
+    VQ_REQUIRE(cube_desc_ok(env->irradiance_diffuse), "bad cubemap descriptor (irradiance_diffuse)");
     if (!P.diffuseOnly) {
-        rc = fill_cube(env->irradiance_specular, P.spec, "irradiance_specular"); if (rc) return rc;
+        VQ_REQUIRE(cube_desc_ok(env->irradiance_specular), "bad cubemap descriptor (irradiance_specular)");
         VQ_REQUIRE(vq_image_ok(env->brdf_lut, 8), "bad BRDF LUT descriptor");
         P.lut.p = (const float2*)env->brdf_lut.ptr; P.lut.w = env->brdf_lut.width; P.lut.h = env->brdf_lut.height;
         P.lut.pitch2 = (int)(env->brdf_lut.pitch_bytes / 8);
+    }
+    // bordered sampling copies: from the prepared environment when it matches, else padded now on this stream
+    int rc;
+    const bool prepared = ctx->env_valid && same_cube(ctx->env_key.irradiance_diffuse, env->irradiance_diffuse) &&
+                          (P.diffuseOnly || same_cube(ctx->env_key.irradiance_specular, env->irradiance_specular));
+    if (prepared) {
+        fill_cube_view(env->irradiance_diffuse, (const float4*)ctx->env_diff, P.diff);
+        if (!P.diffuseOnly) fill_cube_view(env->irradiance_specular, (const float4*)ctx->env_spec, P.spec);
+    } else {
+        rc = ensure_bytes(&ctx->tmp_diff, &ctx->tmp_diff_bytes, padded_texels(env->irradiance_diffuse.res, env->irradiance_diffuse.mips) * 16); if (rc) return rc;
+        rc = pad_cube(env->irradiance_diffuse, (float4*)ctx->tmp_diff, stream); if (rc) return rc;
+        fill_cube_view(env->irradiance_diffuse, (const float4*)ctx->tmp_diff, P.diff);
+        if (!P.diffuseOnly) {
+            rc = ensure_bytes(&ctx->tmp_spec, &ctx->tmp_spec_bytes, padded_texels(env->irradiance_specular.res, env->irradiance_specular.mips) * 16); if (rc) return rc;
+            rc = pad_cube(env->irradiance_specular, (float4*)ctx->tmp_spec, stream); if (rc) return rc;
+            fill_cube_view(env->irradiance_specular, (const float4*)ctx->tmp_spec, P.spec);
+        }
     }
     P.rowBegin = row_begin; P.rows = row_end - row_begin; P.width = W;
 
@@ -417,4 +472,30 @@ extern "C" int vq_forward_lighting(VqContext* ctx, const VqPerFrameData* pf, con
                                    int row_begin, int row_end, void* stream) {
     int rc = vq_enter(ctx); if (rc) return rc;
     return vq_forward_launch(ctx, pf, pv, gb, env, out, row_begin, row_end, (cudaStream_t)stream);
+}
+
+// The IBL cubemaps are sampled from bordered copies (see CubeV). vq_environment_prepare builds them once and
+// registers them in the context: the analogue of the RENDER_TARGET -> PIXEL_SHADER_RESOURCE transition the engine
+// records after prefiltering (EnvironmentMapRendering.cpp:466-472). Call it again whenever the maps' contents change.
+// Without it vq_forward_lighting re-pads the cubes on every call (always correct, ~15 us slower at 512^2 x 9 mips).
+extern "C" int vq_environment_prepare(VqContext* ctx, const VqEnvironmentMaps* env, void* stream) {
+    int rc = vq_enter(ctx); if (rc) return rc;
+    VQ_REQUIRE(env, "env is null");
+    VQ_REQUIRE(cube_desc_ok(env->irradiance_diffuse), "bad cubemap descriptor (irradiance_diffuse)");
+    ctx->env_valid = 0;
+    rc = ensure_bytes(&ctx->env_diff, &ctx->env_diff_bytes, padded_texels(env->irradiance_diffuse.res, env->irradiance_diffuse.mips) * 16); if (rc) return rc;
+    rc = pad_cube(env->irradiance_diffuse, (float4*)ctx->env_diff, (cudaStream_t)stream); if (rc) return rc;
+    ctx->env_key = *env;
+    if (env->irradiance_specular.ptr) {
+        VQ_REQUIRE(cube_desc_ok(env->irradiance_specular), "bad cubemap descriptor (irradiance_specular)");
+        rc = ensure_bytes(&ctx->env_spec, &ctx->env_spec_bytes, padded_texels(env->irradiance_specular.res, env->irradiance_specular.mips) * 16); if (rc) return rc;
+        rc = pad_cube(env->irradiance_specular, (float4*)ctx->env_spec, (cudaStream_t)stream); if (rc) return rc;
+    }
+    ctx->env_valid = 1;
+    return VQ_OK;
+}
+extern "C" int vq_environment_invalidate(VqContext* ctx) {
+    if (!ctx) { vq_set_error("null context"); return VQ_ERR_INVALID_ARG; }
+    ctx->env_valid = 0;
+    return VQ_OK;
 }
