@@ -12,22 +12,25 @@ using namespace vq;
 // =============================================================================================
 // K6 Tonemapper — Shaders/Tonemapper.hlsl:110-151, Shaders/HDR.hlsl:76-119
 // =============================================================================================
+// pow(x, e) for x >= 0 as ex2(e * lg2(x)) on the SFU (MUFU.LG2 + MUFU.EX2): |rel err| <~ 3e-7 * max(1, e), far inside the
+// 1e-4 budget even for the PQ exponent 78.84; powf() costs ~40 instructions per call and made the pass ALU-bound.
+__device__ __forceinline__ float pow_sfu(float x, float e) { return exp2f(e * __log2f(x)); }
 __device__ __forceinline__ float linear_to_srgb(float c) {          // HDR.hlsl:76-80
-    return c < 0.0031308f ? 12.92f * c : fmaf(1.055f, powf(fabsf(c), 1.0f / 2.4f), -0.055f);
+    return c < 0.0031308f ? 12.92f * c : fmaf(1.055f, pow_sfu(fabsf(c), 1.0f / 2.4f), -0.055f);
 }
 __device__ __forceinline__ float linear_to_st2084(float c) {        // HDR.hlsl:110-119
     const float m1 = 2610.0f / 4096.0f / 4, m2 = 2523.0f / 4096.0f * 128;
     const float c1 = 3424.0f / 4096.0f, c2 = 2413.0f / 4096.0f * 32, c3 = 2392.0f / 4096.0f * 32;
-    const float cp = powf(fabsf(c), m1);
-    return powf(fmaf(c2, cp, c1) / fmaf(c3, cp, 1.0f), m2);
+    const float cp = pow_sfu(fabsf(c), m1);
+    return pow_sfu(__fdividef(fmaf(c2, cp, c1), fmaf(c3, cp, 1.0f)), m2);
 }
 
 template <int CURVE, bool GAMMA, bool TO2020>
 __device__ __forceinline__ float4 tonemap_px(float4 in, float hdrScalar) {
     float3 o;
     if (CURVE == VQ_DISPLAY_CURVE_SRGB) {
-        // Tonemap_Reinhard (Tonemapper.hlsl:24-27): c / (c + 1), IEEE division
-        o = f3(in.x / (in.x + 1.0f), in.y / (in.y + 1.0f), in.z / (in.z + 1.0f));
+        // Tonemap_Reinhard (Tonemapper.hlsl:24-27): c / (c + 1)
+        o = f3(__fdividef(in.x, in.x + 1.0f), __fdividef(in.y, in.y + 1.0f), __fdividef(in.z, in.z + 1.0f));
         if (GAMMA) o = f3(linear_to_srgb(o.x), linear_to_srgb(o.y), linear_to_srgb(o.z));
     } else if (CURVE == VQ_DISPLAY_CURVE_ST2084) {
         o = xyz(in);
@@ -112,6 +115,7 @@ constexpr int BX_SM = BX_W + 24;     // staged: [-12, BX_W+12)
 
 __global__ void __launch_bounds__(BX_T * BX_ROWS) blur_x_kernel(ImgV in, ImgV out, int sizeX, int sizeY) {
     __shared__ __align__(16) float sm[BX_ROWS][3][BX_SM];
+    __shared__ float4 so[BX_ROWS][BX_W];                  // results, so that the global stores are coalesced
     const int ty = threadIdx.y;
     const int y = blockIdx.y * BX_ROWS + ty;
     const int xBase = blockIdx.x * BX_W;
@@ -125,31 +129,36 @@ __global__ void __launch_bounds__(BX_T * BX_ROWS) blur_x_kernel(ImgV in, ImgV ou
         }
     }
     __syncthreads();
-    if (y >= sizeY) return;
-    const int x = xBase + threadIdx.x * 4;
-    if (x >= sizeX) return;
-    float acc[3][4];
+    if (y < sizeY && xBase + threadIdx.x * 4 < sizeX) {
+        float acc[3][4];
 #pragma unroll
-    for (int c = 0; c < 3; ++c) {
-        float win[28];                                     // staged positions 4t .. 4t+27  == image x-12 .. x+15
-        const float4* p = reinterpret_cast<const float4*>(&sm[ty][c][threadIdx.x * 4]);
+        for (int c = 0; c < 3; ++c) {
+            float win[28];                                 // staged positions 4t .. 4t+27  == image x-12 .. x+15
+            const float4* p = reinterpret_cast<const float4*>(&sm[ty][c][threadIdx.x * 4]);
 #pragma unroll
-        for (int q = 0; q < 7; ++q) { const float4 v = p[q]; win[4 * q] = v.x; win[4 * q + 1] = v.y; win[4 * q + 2] = v.z; win[4 * q + 3] = v.w; }
+            for (int q = 0; q < 7; ++q) { const float4 v = p[q]; win[4 * q] = v.x; win[4 * q + 1] = v.y; win[4 * q + 2] = v.z; win[4 * q + 3] = v.w; }
 #pragma unroll
-        for (int j = 0; j < 4; ++j) {
-            float a = 0.0f;
+            for (int j = 0; j < 4; ++j) {
+                float a = 0.0f;
 #pragma unroll
-            for (int k = 0; k < 21; ++k) {                 // kernelIt order 0..20 as in the HLSL loop
-                const int ki = k < 10 ? 10 - k : k - 10;
-                a = fmaf(win[j + 2 + k], c_gauss[ki], a);  // tap at x+j-10+k -> window index j+2+k
+                for (int k = 0; k < 21; ++k) {             // kernelIt order 0..20 as in the HLSL loop
+                    const int ki = k < 10 ? 10 - k : k - 10;
+                    a = fmaf(win[j + 2 + k], c_gauss[ki], a);   // tap at x+j-10+k -> window index j+2+k
+                }
+                acc[c][j] = a;
             }
-            acc[c][j] = a;
         }
+#pragma unroll
+        for (int j = 0; j < 4; ++j) so[ty][threadIdx.x * 4 + j] = make_float4(acc[0][j], acc[1][j], acc[2][j], 1.0f);
     }
+    __syncthreads();
+    if (y >= sizeY) return;
     float4* __restrict__ dst = out.row(y);
 #pragma unroll
-    for (int j = 0; j < 4; ++j)
-        if (x + j < sizeX) dst[x + j] = make_float4(acc[0][j], acc[1][j], acc[2][j], 1.0f);
+    for (int k = 0; k < 4; ++k) {
+        const int lx = threadIdx.x + k * BX_T;
+        if (xBase + lx < sizeX) st_stream(dst + xBase + lx, so[ty][lx]);
+    }
 }
 
 // Y pass: a block stages a (BY_H+20) x BY_W tile of float4 and each thread produces BY_PER consecutive
@@ -285,13 +294,13 @@ __global__ void __launch_bounds__(ST_BX * ST_BY) rcas_kernel(ImgV in, ImgV out, 
     const float3 h = load_zero_border(in, x, y + 1);
     const float3 mn4 = f3(fminf(min3f(b.x, d.x, f.x), h.x), fminf(min3f(b.y, d.y, f.y), h.y), fminf(min3f(b.z, d.z, f.z), h.z));
     const float3 mx4 = f3(fmaxf(max3f(b.x, d.x, f.x), h.x), fmaxf(max3f(b.y, d.y, f.y), h.y), fmaxf(max3f(b.z, d.z, f.z), h.z));
-    // limiters need high-precision reciprocals (ffx_fsr1.h:749-755): IEEE division
-    const float hitMinR = mn4.x * (1.0f / (4.0f * mx4.x));
-    const float hitMinG = mn4.y * (1.0f / (4.0f * mx4.y));
-    const float hitMinB = mn4.z * (1.0f / (4.0f * mx4.z));
-    const float hitMaxR = (1.0f - mx4.x) * (1.0f / (4.0f * mn4.x + -4.0f));
-    const float hitMaxG = (1.0f - mx4.y) * (1.0f / (4.0f * mn4.y + -4.0f));
-    const float hitMaxB = (1.0f - mx4.z) * (1.0f / (4.0f * mn4.z + -4.0f));
+    // limiters use the full-precision rcp of the HLSL (ffx_fsr1.h:749-755), i.e. the hardware reciprocal (1 ulp)
+    const float hitMinR = mn4.x * rcp_fast(4.0f * mx4.x);
+    const float hitMinG = mn4.y * rcp_fast(4.0f * mx4.y);
+    const float hitMinB = mn4.z * rcp_fast(4.0f * mx4.z);
+    const float hitMaxR = (1.0f - mx4.x) * rcp_fast(fmaf(4.0f, mn4.x, -4.0f));
+    const float hitMaxG = (1.0f - mx4.y) * rcp_fast(fmaf(4.0f, mn4.y, -4.0f));
+    const float hitMaxB = (1.0f - mx4.z) * rcp_fast(fmaf(4.0f, mn4.z, -4.0f));
     const float lobeR = fmaxf(-hitMinR, hitMaxR);
     const float lobeG = fmaxf(-hitMinG, hitMaxG);
     const float lobeB = fmaxf(-hitMinB, hitMaxB);
@@ -325,8 +334,9 @@ extern "C" int vq_fsr_rcas(VqContext* ctx, const uint32_t rcas_const[4], VqImage
 template <int ADDR>
 __device__ __forceinline__ float3 load_addr(const ImgV& im, int x, int y) {
     if (ADDR == VQ_ADDRESS_WRAP) {
-        x %= im.w; if (x < 0) x += im.w;
-        y %= im.h; if (y < 0) y += im.h;
+        // taps lie within [-2, size+2]: one conditional add/sub wraps them (the general % only for images < 3 wide)
+        if (im.w >= 3) { x = x < 0 ? x + im.w : (x >= im.w ? x - im.w : x); } else { x %= im.w; if (x < 0) x += im.w; }
+        if (im.h >= 3) { y = y < 0 ? y + im.h : (y >= im.h ? y - im.h : y); } else { y %= im.h; if (y < 0) y += im.h; }
     } else {
         x = min(max(x, 0), im.w - 1);
         y = min(max(y, 0), im.h - 1);
@@ -424,7 +434,7 @@ __global__ void __launch_bounds__(ST_BX * ST_BY) easu_kernel(ImgV in, ImgV out, 
     easu_tap(aC, aW, 1.0f - ppx, 0.0f - ppy, dir, len2, lob, clp, g);
     easu_tap(aC, aW, 1.0f - ppx, 2.0f - ppy, dir, len2, lob, clp, o);
     easu_tap(aC, aW, 0.0f - ppx, 2.0f - ppy, dir, len2, lob, clp, n);
-    const float rw = 1.0f / aW;   // ARcpF1, high precision
+    const float rw = rcp_fast(aW);   // ARcpF1 = rcp() in the HLSL
     const float3 pix = fmin3(max4, fmax3(min4, aC * rw));
     st_stream(out.row(y) + x, make_float4(pix.x, pix.y, pix.z, 1.0f));
 }
