@@ -15,7 +15,7 @@ import ctypes as C
 import os
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libvqcuda.so")
+LIB_PATH = os.environ.get("VQCUDA_LIB") or os.path.join(_HERE, "libvqcuda.so")   # override only for A/B kernel experiments
 
 VQ_OK = 0
 VQ_ERR_INVALID_ARG = -1

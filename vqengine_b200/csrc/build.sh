@@ -2,7 +2,7 @@
 # Builds libvqcuda.so for sm_100a IN-TREE (vqengine_b200/libvqcuda.so). No GPU needed (cross-compile).
 set -euo pipefail
 here="$(cd "$(dirname "$0")" && pwd)"
-out="$here/../libvqcuda.so"
+out="${VQ_OUT:-$here/../libvqcuda.so}"
 NVCC="${NVCC:-/usr/local/cuda/bin/nvcc}"
 FLAGS=(-gencode arch=compute_100a,code=sm_100a -lineinfo -O3 -std=c++17 --shared -Xcompiler -fPIC,-fvisibility=hidden
        -Xptxas -v --expt-relaxed-constexpr)

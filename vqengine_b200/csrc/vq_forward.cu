@@ -46,18 +46,21 @@ struct SSpot { float3 pos; float outer; float3 color; float brightness; float3 d
 // ---------------------------------------------------------------------------------------------
 // cubemap sampling: bilinear, seamless (identical rule in oracle/oracle_shading.cpp)
 // ---------------------------------------------------------------------------------------------
+// D3D face selection (largest |component|; ties X > Y > Z as in the oracle) written with selects so that a warp never
+// diverges on it:  face, and the face-plane coordinates sx (right), sy (up) in [-1,1]
 __device__ __forceinline__ void dir_to_face(float3 d, int& face, float& sx, float& sy) {
     const float ax = fabsf(d.x), ay = fabsf(d.y), az = fabsf(d.z);
-    if (ax >= ay && ax >= az) {
-        const float r = rcp_fast(ax);
-        if (d.x > 0) { face = 0; sx = -d.z * r; sy = d.y * r; } else { face = 1; sx = d.z * r; sy = d.y * r; }
-    } else if (ay >= az) {
-        const float r = rcp_fast(ay);
-        if (d.y > 0) { face = 2; sx = d.x * r; sy = -d.z * r; } else { face = 3; sx = d.x * r; sy = d.z * r; }
-    } else {
-        const float r = rcp_fast(az);
-        if (d.z > 0) { face = 4; sx = d.x * r; sy = d.y * r; } else { face = 5; sx = -d.x * r; sy = d.y * r; }
-    }
+    const bool isX = ax >= ay && ax >= az;
+    const bool isY = !isX && ay >= az;
+    const float ma = isX ? ax : (isY ? ay : az);
+    const float mv = isX ? d.x : (isY ? d.y : d.z);          // signed major component
+    const bool pos = mv > 0.0f;
+    const float r = rcp_fast(ma);
+    // +X: (-z, y)  -X: (z, y)  +Y: (x, -z)  -Y: (x, z)  +Z: (x, y)  -Z: (-x, y)
+    const float u = isX ? (pos ? -d.z : d.z) : (isY ? d.x : (pos ? d.x : -d.x));
+    const float v = isY ? (pos ? -d.z : d.z) : d.y;
+    sx = u * r; sy = v * r;
+    face = (isX ? 0 : (isY ? 2 : 4)) + (pos ? 0 : 1);
 }
 
 // integer-only neighbour lookup for a tap one texel outside the face (see DESIGN.md "cube edges"); used only by
@@ -128,7 +131,7 @@ __device__ __forceinline__ float3 sample_cube(const CubeV& c, float3 dir, int mi
     const float xf = fminf(fmaxf(floorf(x), -1.0f), (float)(N - 1)), yf = fminf(fmaxf(floorf(y), -1.0f), (float)(N - 1));
     const float fx = x - xf, fy = y - yf;
     const int i0 = (int)xf + 1, j0 = (int)yf + 1;            // bordered coordinates: 0..N
-    const float4* p = c.p + c.mipOffset[mip] + (size_t)face * (P * P) + j0 * P + i0;
+    const float4* p = c.p + (c.mipOffset[mip] + (uint32_t)(face * (P * P) + j0 * P + i0));
     const float4 t00 = __ldg(p), t10 = __ldg(p + 1), t01 = __ldg(p + P), t11 = __ldg(p + P + 1);
     const float3 top = lerp(xyz(t00), xyz(t10), fx), bot = lerp(xyz(t01), xyz(t11), fx);
     return lerp(top, bot, fy);
@@ -140,8 +143,9 @@ __device__ __forceinline__ float2 sample_lut(const LutV& l, float u, float v) { 
     const float fx = x - x0, fy = y - y0;
     const int ix0 = min(max((int)x0, 0), l.w - 1), ix1 = min(max((int)x0 + 1, 0), l.w - 1);
     const int iy0 = min(max((int)y0, 0), l.h - 1), iy1 = min(max((int)y0 + 1, 0), l.h - 1);
-    const float2 p00 = __ldg(l.p + (size_t)iy0 * l.pitch2 + ix0), p10 = __ldg(l.p + (size_t)iy0 * l.pitch2 + ix1);
-    const float2 p01 = __ldg(l.p + (size_t)iy1 * l.pitch2 + ix0), p11 = __ldg(l.p + (size_t)iy1 * l.pitch2 + ix1);
+    const uint32_t r0 = (uint32_t)(iy0 * l.pitch2), r1 = (uint32_t)(iy1 * l.pitch2);
+    const float2 p00 = __ldg(l.p + (r0 + ix0)), p10 = __ldg(l.p + (r0 + ix1));
+    const float2 p01 = __ldg(l.p + (r1 + ix0)), p11 = __ldg(l.p + (r1 + ix1));
     return make_float2(lerp(lerp(p00.x, p10.x, fx), lerp(p01.x, p11.x, fx), fy),
                        lerp(lerp(p00.y, p10.y, fx), lerp(p01.y, p11.y, fx), fy));
 }
@@ -149,12 +153,13 @@ __device__ __forceinline__ float2 sample_lut(const LutV& l, float u, float v) { 
 // ---------------------------------------------------------------------------------------------
 // per-pixel shading state with everything that does not depend on the light hoisted
 // ---------------------------------------------------------------------------------------------
+// Only what the light loop reads stays live across it (register diet: 64-80 registers decide the occupancy).
 struct Px {
-    float3 P, Ns, Nn, V;          // position, G-buffer normal, normalize(Ns), normalize(cam - P)
-    float3 F0, omF0, K1;          // F0, 1-F0, (1-F0)*albedo*(1-metal)/PI
+    float3 P, Nn, V;              // position, normalize(Ns), normalize(cam - P)
     float nsLen;                  // |Ns|: dot(Ns,Wi) = nsLen * dot(Nn,Wi)  (Lighting.hlsl:316 uses the raw s.N)
     float nv, NdotV, gV;          // dot(Nn,V), saturate, Smith-G1 of V (BRDF.hlsl:82-97)
     float a2, a2m1, k, omk;
+    const float4* nrmTexel;       // where the raw normal lives: re-read by the exact slow path only
 };
 
 // ---- exact re-evaluation of N.H -------------------------------------------------------------------
@@ -174,7 +179,9 @@ __device__ __forceinline__ float3 normalize_u(float3 v) {
     return f3(__fdiv_rn(v.x, l), __fdiv_rn(v.y, l), __fdiv_rn(v.z, l));
 }
 
-__device__ __noinline__ float exact_ndoth(float3 cam, float3 P, float3 Ns, float3 wiSrc, float wiLenSq) {
+__device__ __noinline__ float exact_ndoth(float3 cam, float3 P, const float4* nrmTexel, float3 wiSrc, float wiLenSq) {
+    const float4 nr = __ldg(nrmTexel);
+    const float3 Ns = f3(nr.x, nr.y, nr.z);
     const float3 Vv = f3(__fsub_rn(cam.x, P.x), __fsub_rn(cam.y, P.y), __fsub_rn(cam.z, P.z));
     const float3 V = normalize_u(Vv);                 // ForwardLighting.hlsl:285
     const float3 Wo = normalize_u(V);                 // BRDF.hlsl:166
@@ -191,43 +198,65 @@ struct Acc { float3 a, b, c; };   // sum over lights of w*col * {(1-fc), fc*spec
 // One light: accumulates BRDF(s, Wi, V) * radiance * NdotL (BRDF.hlsl:163-194, Lighting.hlsl:308-345) in the
 // factored form  r = K1*(1-fc) + omF0*(fc*spec) + F0*spec  with  F = F0 + (1-F0)*fc.
 //   Lv, d2 : un-normalised light vector and its squared length (Wi = Lv/sqrt(d2)),  invD = 1/sqrt(d2)
-//   scale  : attenuation * brightness * spot intensity;  col : light colour
+//   scale  : attenuation * brightness * spot intensity (0 when the light is out of range);  col : light colour
 // H = normalize(V+Wi) is never formed: |V+Wi|^2 = 2+2c with c = V.Wi, so N.H = (N.V+N.Wi)*rh and
 // H.V = (1+c)*rh with rh = rsqrt(2+2c).
+// The body is branch-free (a light that does not contribute gets weight 0) so that two lights can be interleaved
+// by the scheduler; only the rare exact-N.H slow path branches.
 __device__ __forceinline__ void shade_light(const Px& s, Acc& acc, float3 cam, float3 Lv, float d2, float invD,
                                             float scale, float3 col) {
     const float nl = dot(s.Nn, Lv) * invD;
-    if (nl <= 0.0f) return;                            // N.L = 0 -> the light contributes exactly 0
     const float c = dot(s.V, Lv) * invD;
-    const float sq = fmaxf(fmaf(2.0f, c, 2.0f), 1e-20f);
-    const float rh = rsqrtf(sq);
+    const float sq = fmaxf(fmaf(2.0f, c, 2.0f), 1e-12f);
+    const float rh = rsqrt_fast(sq);
     float NdotH = saturate((s.nv + nl) * rh);
     const float HV = fmaxf(0.0f, (1.0f + c) * rh);
     const float fc = pow5(1.0f - HV);                  // Fresnel_Schlick (BRDF.hlsl:132-136)
     float t = fmaf(NdotH * NdotH, s.a2m1, 1.0f);       // NormalDistributionGGX (BRDF.hlsl:65-79)
-    if (t < T_EXACT) {
-        NdotH = exact_ndoth(cam, s.P, s.Ns, Lv, d2);
+    const float NL = fminf(fmaxf(nl, 0.0f), 1.0f);     // saturate(N.L) == max(0,N.L) for unit vectors
+    const float w = saturate(s.nsLen * nl) * scale;    // NdotL of the raw s.N (Lighting.hlsl:316) * radiance scale
+    if (t < T_EXACT && w > 0.0f) {
+        NdotH = exact_ndoth(cam, s.P, s.nrmTexel, Lv, d2);
         t = __fadd_rn(__fmul_rn(__fmul_rn(NdotH, NdotH), s.a2m1), 1.0f);
     }
-    const float NL = fminf(nl, 1.0f);                  // saturate(N.L) == max(0,N.L) for unit vectors
     const float dDen = PI * (t * t);
     const float gDen = fmaf(NL, s.omk, s.k) + 0.0001f; // Geometry_Smiths_SchlickGGX of L (BRDF.hlsl:82-97)
     const float sDen = fmaxf(4.0f * s.NdotV * NL, 0.0001f);
     const bool tiny = dDen < 0.000000000001f;          // `denom < EPSILON -> D = 1` (BRDF.hlsl:77)
     const float num = (tiny ? 1.0f : s.a2) * s.gV * NL;
     const float den = (tiny ? 1.0f : dDen) * gDen * sDen;
-    const float spec = __fdividef(num, den);           // D*G/denom with ONE reciprocal
-    const float w = saturate(s.nsLen * nl) * scale;    // NdotL of the raw s.N (Lighting.hlsl:316) * radiance scale
+    const float spec = num * rcp_fast(den);            // D*G/denom with ONE reciprocal (den >= 1e-20)
     const float wa = (1.0f - fc) * w, wc = spec * w, wb = fc * wc;
-    const float3 cw = col;
-    acc.a.x = fmaf(wa, cw.x, acc.a.x); acc.a.y = fmaf(wa, cw.y, acc.a.y); acc.a.z = fmaf(wa, cw.z, acc.a.z);
-    acc.b.x = fmaf(wb, cw.x, acc.b.x); acc.b.y = fmaf(wb, cw.y, acc.b.y); acc.b.z = fmaf(wb, cw.z, acc.b.z);
-    acc.c.x = fmaf(wc, cw.x, acc.c.x); acc.c.y = fmaf(wc, cw.y, acc.c.y); acc.c.z = fmaf(wc, cw.z, acc.c.z);
+    acc.a.x = fmaf(wa, col.x, acc.a.x); acc.a.y = fmaf(wa, col.y, acc.a.y); acc.a.z = fmaf(wa, col.z, acc.a.z);
+    acc.b.x = fmaf(wb, col.x, acc.b.x); acc.b.y = fmaf(wb, col.y, acc.b.y); acc.b.z = fmaf(wb, col.z, acc.b.z);
+    acc.c.x = fmaf(wc, col.x, acc.c.x); acc.c.y = fmaf(wc, col.y, acc.c.y); acc.c.z = fmaf(wc, col.z, acc.c.z);
+}
+
+// point light i (Lighting.hlsl:308-322): in range <=> d2 < d2Limit (== length(Lw-P) < l.range, exactly)
+__device__ __forceinline__ void shade_point(const Px& s, Acc& acc, float3 cam, const SPoint& l) {
+    const float3 Lv = l.pos - s.P;
+    const float d2 = dot_u(Lv, Lv);                    // |L-P|^2 exactly as the oracle's dot()
+    const float invD = rsqrt_fast(fmaxf(d2, 1e-30f));
+    const float scale = d2 < l.d2Limit ? (invD * invD) * l.brightness : 0.0f;   // AttenuationBRDF = 1/D^2
+    shade_light(s, acc, cam, Lv, d2, invD, scale, l.color);
 }
 
 constexpr int FWD_BX = 64, FWD_BY = 4;   // 256 threads: 64 x 4 pixel tile; grid.x covers the row, grid.y strides rows
 
-__global__ void __launch_bounds__(FWD_THREADS, 3) forward_kernel(const __grid_constant__ FwdParams P) {
+// Tuning knobs, A/B-measured on B200 at 4K (gpurun_out/perf_variants2.log, us per frame):
+//   blocks/SM 4, no prefetch, no pairing: 344   | 4,no,pair: 379 | 3,no,pair: 364 | 3,prefetch,pair: 381
+//   2,prefetch,pair (116 regs, no spills): 358  | 4,prefetch,pair (heavy spills): 425
+// Occupancy (8 warps/scheduler at 64 registers) beats the extra ILP of prefetching / pairing at this register budget.
+#ifndef FWD_MIN_BLOCKS
+#define FWD_MIN_BLOCKS 4
+#endif
+#ifndef FWD_PREFETCH
+#define FWD_PREFETCH 0
+#endif
+#ifndef FWD_PAIR
+#define FWD_PAIR 0
+#endif
+__global__ void __launch_bounds__(FWD_THREADS, FWD_MIN_BLOCKS) forward_kernel(const __grid_constant__ FwdParams P) {
     __shared__ SPoint sPoint[MAX_POINT];
     __shared__ SSpot sSpot[MAX_SPOT];
 
@@ -273,30 +302,41 @@ __global__ void __launch_bounds__(FWD_THREADS, 3) forward_kernel(const __grid_co
 
     const int x = blockIdx.x * FWD_BX + threadIdx.x;
     if (x >= P.width) return;
-    for (int ry = blockIdx.y * FWD_BY + threadIdx.y; ry < P.rows; ry += gridDim.y * FWD_BY) {
+    const int rowStep = gridDim.y * FWD_BY;
+    int ry = blockIdx.y * FWD_BY + threadIdx.y;
+    if (ry >= P.rows) return;
+    // software prefetch: the next row's G-buffer texels are requested before the current pixel is shaded
+    float4 pa = ld_stream(P.pos.row(P.rowBegin + ry) + x);
+    float4 nr = ld_stream(P.nrm.row(P.rowBegin + ry) + x);
+    float4 am = ld_stream(P.alb.row(P.rowBegin + ry) + x);
+    for (; ry < P.rows; ry += rowStep) {
         const int y = P.rowBegin + ry;
-        const float4 pa = ld_stream(P.pos.row(y) + x);
-        const float4 nr = ld_stream(P.nrm.row(y) + x);
-        const float4 am = ld_stream(P.alb.row(y) + x);
+        const int ryn = ry + rowStep;
+        const bool more = ryn < P.rows;
+        float4 paN = pa, nrN = nr, amN = am;
+        if (FWD_PREFETCH && more) {
+            paN = ld_stream(P.pos.row(P.rowBegin + ryn) + x);
+            nrN = ld_stream(P.nrm.row(P.rowBegin + ryn) + x);
+            amN = ld_stream(P.alb.row(P.rowBegin + ryn) + x);
+        }
 
         Px s;
-        s.P = xyz(pa); s.Ns = xyz(nr);
-        const float3 albedo = xyz(am);
+        s.P = xyz(pa);
+        s.nrmTexel = P.nrm.row(y) + x;
+        const float3 Ns = xyz(nr), albedo = xyz(am);
         const float roughness = nr.w, metalness = am.w, ao = pa.w;
-        s.V = normalize(P.cam - s.P);                            // ForwardLighting.hlsl:285
-        const float n2 = dot(s.Ns, s.Ns), rn = rsqrtf(n2);
-        s.Nn = s.Ns * rn;                                        // BRDF.hlsl:167
+        const float3 Vv = P.cam - s.P;
+        s.V = Vv * rsqrt_fast(dot(Vv, Vv));                      // ForwardLighting.hlsl:285
+        const float n2 = dot(Ns, Ns), rn = rsqrt_fast(n2);
+        s.Nn = Ns * rn;                                          // BRDF.hlsl:167
         s.nsLen = n2 * rn;
-        s.F0 = lerp(f3(0.04f), albedo, metalness);               // BRDF.hlsl:177
-        s.omF0 = f3(1.0f) - s.F0;
-        s.K1 = s.omF0 * albedo * ((1.0f - metalness) * (1.0f / PI));   // (1-F0)*kD-part*albedo/PI (BRDF.hlsl:189-191)
         const float a = roughness * roughness;
         s.a2 = __fmul_rn(a, a); s.a2m1 = __fsub_rn(s.a2, 1.0f);  // no contraction: feeds the exact t
         const float rp1 = roughness + 1.0f;
         s.k = (rp1 * rp1) * 0.125f; s.omk = 1.0f - s.k;
         s.nv = dot(s.Nn, s.V);
         s.NdotV = saturate(s.nv);
-        s.gV = __fdividef(s.NdotV, fmaf(s.NdotV, s.omk, s.k) + 0.0001f);
+        s.gV = s.NdotV * rcp_fast(fmaf(s.NdotV, s.omk, s.k) + 0.0001f);
 
         float3 I = albedo * ao;                                  // ForwardLighting.hlsl:290-293
         if (P.hasEmissive) {
@@ -306,12 +346,13 @@ __global__ void __launch_bounds__(FWD_THREADS, 3) forward_kernel(const __grid_co
 
         // ---- environment map (Lighting.hlsl:360-395, BRDF.hlsl:196-207) ----
         {
+            const float3 F0 = lerp(f3(0.04f), albedo, metalness);
             const float NdotVs = saturate(s.nsLen * s.nv);       // saturate(dot(s.N, V))
-            const float3 Nr = f3(s.Ns.x * P.cosB - s.Ns.z * P.sinB, s.Ns.y, s.Ns.x * P.sinB + s.Ns.z * P.cosB);
+            const float3 Nr = f3(Ns.x * P.cosB - Ns.z * P.sinB, Ns.y, Ns.x * P.sinB + Ns.z * P.cosB);
             const float3 diffIrr = sample_cube(P.diff, Nr, 0);
             float3 specCol = f3(0.0f); float2 sb = make_float2(0.0f, 0.0f);
             if (!P.diffuseOnly) {
-                const float3 R0 = reflect(-s.V, s.Ns);
+                const float3 R0 = reflect(-s.V, Ns);
                 const float3 R = f3(R0.x * P.cosB - R0.z * P.sinB, R0.y, R0.x * P.sinB + R0.z * P.cosB);
                 const int mip = (int)(roughness * (float)P.maxLod);
                 specCol = sample_cube(P.spec, R, mip);
@@ -319,9 +360,9 @@ __global__ void __launch_bounds__(FWD_THREADS, 3) forward_kernel(const __grid_co
             }
             const float fr = pow5(1.0f - NdotVs);                // FresnelWithRoughness, BRDF.hlsl:152-156
             const float omr = 1.0f - roughness;
-            const float3 Ks = f3(fmaf(fmaxf(omr, s.F0.x) - s.F0.x, fr, s.F0.x),
-                                 fmaf(fmaxf(omr, s.F0.y) - s.F0.y, fr, s.F0.y),
-                                 fmaf(fmaxf(omr, s.F0.z) - s.F0.z, fr, s.F0.z));
+            const float3 Ks = f3(fmaf(fmaxf(omr, F0.x) - F0.x, fr, F0.x),
+                                 fmaf(fmaxf(omr, F0.y) - F0.y, fr, F0.y),
+                                 fmaf(fmaxf(omr, F0.z) - F0.z, fr, F0.z));
             const float om = 1.0f - metalness;
             I.x += (1.0f - Ks.x) * om * (diffIrr.x * albedo.x) + specCol.x * fmaf(Ks.x, sb.x, sb.y);
             I.y += (1.0f - Ks.y) * om * (diffIrr.y * albedo.y) + specCol.y * fmaf(Ks.y, sb.x, sb.y);
@@ -330,21 +371,20 @@ __global__ void __launch_bounds__(FWD_THREADS, 3) forward_kernel(const __grid_co
 
         Acc acc; acc.a = f3(0.0f); acc.b = f3(0.0f); acc.c = f3(0.0f);
         // ---- point lights, then unshadowed point casters (Lighting.hlsl:308-322; PSMain :310-313,321-340) ----
-        for (int i = 0; i < numPoint; ++i) {
-            const SPoint l = sPoint[i];
-            const float3 Lv = l.pos - s.P;
-            const float d2 = dot_u(Lv, Lv);                      // |L-P|^2 exactly as the oracle's dot()
-            if (d2 < l.d2Limit) {                                // == (length(Lw-P) < l.range), Lighting.hlsl:318
-                const float invD = rsqrtf(d2);
-                shade_light(s, acc, P.cam, Lv, d2, invD, (invD * invD) * l.brightness, l.color);   // AttenuationBRDF = 1/D^2
-            }
+        // two at a time: the two bodies are independent, so their dependency chains interleave
+        int i = 0;
+        for (; FWD_PAIR && i + 1 < numPoint; i += 2) {
+            const SPoint l0 = sPoint[i], l1 = sPoint[i + 1];
+            shade_point(s, acc, P.cam, l0);
+            shade_point(s, acc, P.cam, l1);
         }
+        for (; i < numPoint; ++i) shade_point(s, acc, P.cam, sPoint[i]);
         // ---- spot lights, then unshadowed spot casters (Lighting.hlsl:57-73,323-333) ----
-        for (int i = 0; i < numSpot; ++i) {
-            const SSpot l = sSpot[i];
+        for (int k = 0; k < numSpot; ++k) {
+            const SSpot l = sSpot[k];
             const float3 Lv = l.pos - s.P;
             const float d2 = dot_u(Lv, Lv);
-            const float invD = rsqrtf(d2);
+            const float invD = rsqrt_fast(fmaxf(d2, 1e-30f));
             const float theta = acosf(fminf(fmaxf(-dot(Lv, l.dir) * invD, -1.0f), 1.0f));   // pixel direction = -Wi
             float inten = 1.0f - (theta - l.inner) * l.invCone;
             inten = theta > l.outer ? 0.0f : (theta <= l.inner ? 1.0f : inten);
@@ -353,10 +393,21 @@ __global__ void __launch_bounds__(FWD_THREADS, 3) forward_kernel(const __grid_co
         // ---- directional (PSMain :360-377 with ShadowingFactor = 1) ----
         if (dirEnabled) shade_light(s, acc, P.cam, dirWi, 1.0f, 1.0f, 1.0f, dirRadiance);
 
-        I.x += fmaf(s.K1.x, acc.a.x, fmaf(s.omF0.x, acc.b.x, s.F0.x * acc.c.x));
-        I.y += fmaf(s.K1.y, acc.a.y, fmaf(s.omF0.y, acc.b.y, s.F0.y * acc.c.y));
-        I.z += fmaf(s.K1.z, acc.a.z, fmaf(s.omF0.z, acc.b.z, s.F0.z * acc.c.z));
+        {   // F0 = lerp(0.04, albedo, metal) (BRDF.hlsl:177); K1 = (1-F0)*(1-metal)*albedo/PI (BRDF.hlsl:189-191)
+            const float3 F0 = lerp(f3(0.04f), albedo, metalness);
+            const float3 omF0 = f3(1.0f) - F0;
+            const float3 K1 = omF0 * albedo * ((1.0f - metalness) * (1.0f / PI));
+            I.x += fmaf(K1.x, acc.a.x, fmaf(omF0.x, acc.b.x, F0.x * acc.c.x));
+            I.y += fmaf(K1.y, acc.a.y, fmaf(omF0.y, acc.b.y, F0.y * acc.c.y));
+            I.z += fmaf(K1.z, acc.a.z, fmaf(omF0.z, acc.b.z, F0.z * acc.c.z));
+        }
         st_stream(P.out.row(y) + x, make_float4(I.x, I.y, I.z, roughness));   // :380
+        if (FWD_PREFETCH) { pa = paN; nr = nrN; am = amN; }
+        else if (more) {
+            pa = ld_stream(P.pos.row(P.rowBegin + ryn) + x);
+            nr = ld_stream(P.nrm.row(P.rowBegin + ryn) + x);
+            am = ld_stream(P.alb.row(P.rowBegin + ryn) + x);
+        }
     }
 }
 
@@ -460,7 +511,7 @@ int vq_forward_launch(VqContext* ctx, const VqPerFrameData* pf, const VqPerViewL
     // grid.x covers a row in 64-pixel tiles; grid.y strides 4-row groups: about 3 resident CTAs per SM, several waves
     const unsigned gx = (unsigned)((W + FWD_BX - 1) / FWD_BX);
     unsigned gy = (unsigned)((P.rows + FWD_BY - 1) / FWD_BY);
-    const unsigned targetBlocks = (unsigned)ctx->sm_count * 3u * 4u;
+    const unsigned targetBlocks = (unsigned)ctx->sm_count * (unsigned)FWD_MIN_BLOCKS * 4u;
     const unsigned gyCap = (targetBlocks + gx - 1) / gx;
     if (gy > gyCap) gy = gyCap < 1 ? 1 : gyCap;
     forward_kernel<<<dim3(gx, gy), dim3(FWD_BX, FWD_BY), 0, stream>>>(P);

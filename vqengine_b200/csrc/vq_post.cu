@@ -382,22 +382,16 @@ __device__ __forceinline__ float luma2(float3 c) { return fmaf(c.z, 0.5f, fmaf(c
 
 struct EasuCon { float c0x, c0y, c0z, c0w; };
 
-template <int ADDR>
-__global__ void __launch_bounds__(ST_BX * ST_BY) easu_kernel(ImgV in, ImgV out, EasuCon con) {
-    const int x = blockIdx.x * ST_BX + threadIdx.x, y = blockIdx.y * ST_BY + threadIdx.y;
-    if (x >= out.w || y >= out.h) return;
-    // position of 'f' (ffx_fsr1.h:323-326). Unfused mul+add so floor() sees the oracle's value.
-    float ppx = __fadd_rn(__fmul_rn((float)x, con.c0x), con.c0z);
-    float ppy = __fadd_rn(__fmul_rn((float)y, con.c0y), con.c0w);
-    const float fpx = floorf(ppx), fpy = floorf(ppy);
-    ppx -= fpx; ppy -= fpy;
-    const int fx = (int)fpx, fy = (int)fpy;
-    const float3 b = load_addr<ADDR>(in, fx, fy - 1), c = load_addr<ADDR>(in, fx + 1, fy - 1);
-    const float3 e = load_addr<ADDR>(in, fx - 1, fy), f = load_addr<ADDR>(in, fx, fy);
-    const float3 g = load_addr<ADDR>(in, fx + 1, fy), h = load_addr<ADDR>(in, fx + 2, fy);
-    const float3 i = load_addr<ADDR>(in, fx - 1, fy + 1), j = load_addr<ADDR>(in, fx, fy + 1);
-    const float3 k = load_addr<ADDR>(in, fx + 1, fy + 1), l = load_addr<ADDR>(in, fx + 2, fy + 1);
-    const float3 n = load_addr<ADDR>(in, fx, fy + 2), o = load_addr<ADDR>(in, fx + 1, fy + 2);
+// position of 'f' for output coordinate o (ffx_fsr1.h:323-326). Unfused mul+add so floor() sees the oracle's value.
+__device__ __forceinline__ float easu_pos(int o, float scale, float bias) { return __fadd_rn(__fmul_rn((float)o, scale), bias); }
+
+// The 12-tap kernel + analysis for one output pixel; tap(dx,dy) returns the texel at (fx+dx, fy+dy).
+template <class Tap>
+__device__ __forceinline__ float3 easu_filter(float ppx, float ppy, Tap tap) {
+    const float3 b = tap(0, -1), c = tap(1, -1);
+    const float3 e = tap(-1, 0), f = tap(0, 0), g = tap(1, 0), h = tap(2, 0);
+    const float3 i = tap(-1, 1), j = tap(0, 1), k = tap(1, 1), l = tap(2, 1);
+    const float3 n = tap(0, 2), o = tap(1, 2);
     const float bL = luma2(b), cL = luma2(c), eL = luma2(e), fL = luma2(f), gL = luma2(g), hL = luma2(h);
     const float iL = luma2(i), jL = luma2(j), kL = luma2(k), lL = luma2(l), nL = luma2(n), oL = luma2(o);
     float2 dir = make_float2(0.0f, 0.0f);
@@ -435,7 +429,49 @@ __global__ void __launch_bounds__(ST_BX * ST_BY) easu_kernel(ImgV in, ImgV out, 
     easu_tap(aC, aW, 1.0f - ppx, 2.0f - ppy, dir, len2, lob, clp, o);
     easu_tap(aC, aW, 0.0f - ppx, 2.0f - ppy, dir, len2, lob, clp, n);
     const float rw = rcp_fast(aW);   // ARcpF1 = rcp() in the HLSL
-    const float3 pix = fmin3(max4, fmax3(min4, aC * rw));
+    return fmin3(max4, fmax3(min4, aC * rw));
+}
+
+// Generic path (any scale): taps fetched straight from global memory through L1.
+template <int ADDR>
+__global__ void __launch_bounds__(ST_BX * ST_BY) easu_kernel(ImgV in, ImgV out, EasuCon con) {
+    const int x = blockIdx.x * ST_BX + threadIdx.x, y = blockIdx.y * ST_BY + threadIdx.y;
+    if (x >= out.w || y >= out.h) return;
+    float ppx = easu_pos(x, con.c0x, con.c0z), ppy = easu_pos(y, con.c0y, con.c0w);
+    const float fpx = floorf(ppx), fpy = floorf(ppy);
+    ppx -= fpx; ppy -= fpy;
+    const int fx = (int)fpx, fy = (int)fpy;
+    const float3 pix = easu_filter(ppx, ppy, [&](int dx, int dy) { return load_addr<ADDR>(in, fx + dx, fy + dy); });
+    st_stream(out.row(y) + x, make_float4(pix.x, pix.y, pix.z, 1.0f));
+}
+
+// Upscaling path (input/output ratio <= 1, the FSR use case): the CTA's input footprint — at most
+// (EU_BX+4) x (EU_BY+4) texels — is staged once into shared memory with the sampler's addressing applied, so the
+// 12 taps per pixel are LDS.128 at constant offsets from one base index instead of 12 address computations.
+constexpr int EU_BX = 32, EU_BY = 16;
+constexpr int EU_TW = EU_BX + 4, EU_TH = EU_BY + 4;
+
+template <int ADDR>
+__global__ void __launch_bounds__(EU_BX * EU_BY) easu_up_kernel(ImgV in, ImgV out, EasuCon con) {
+    __shared__ float4 tile[EU_TH][EU_TW];
+    const int ox0 = blockIdx.x * EU_BX, oy0 = blockIdx.y * EU_BY;
+    // footprint origin: fp of the first output of the tile, minus the 1-texel left/top reach of the kernel
+    const int tx0 = (int)floorf(easu_pos(ox0, con.c0x, con.c0z)) - 1;
+    const int ty0 = (int)floorf(easu_pos(oy0, con.c0y, con.c0w)) - 1;
+    const int tid = threadIdx.y * EU_BX + threadIdx.x;
+    for (int i = tid; i < EU_TW * EU_TH; i += EU_BX * EU_BY) {
+        const int lx = i % EU_TW, ly = i / EU_TW;
+        const float3 v = load_addr<ADDR>(in, tx0 + lx, ty0 + ly);
+        tile[ly][lx] = make_float4(v.x, v.y, v.z, 0.0f);
+    }
+    __syncthreads();
+    const int x = ox0 + threadIdx.x, y = oy0 + threadIdx.y;
+    if (x >= out.w || y >= out.h) return;
+    float ppx = easu_pos(x, con.c0x, con.c0z), ppy = easu_pos(y, con.c0y, con.c0w);
+    const float fpx = floorf(ppx), fpy = floorf(ppy);
+    ppx -= fpx; ppy -= fpy;
+    const float4* base = &tile[(int)fpy - ty0][(int)fpx - tx0];
+    const float3 pix = easu_filter(ppx, ppy, [&](int dx, int dy) { const float4 t = base[dy * EU_TW + dx]; return f3(t.x, t.y, t.z); });
     st_stream(out.row(y) + x, make_float4(pix.x, pix.y, pix.z, 1.0f));
 }
 
@@ -446,9 +482,18 @@ extern "C" int vq_fsr_easu(VqContext* ctx, const uint32_t con[16], int address_m
     VQ_REQUIRE(address_mode == VQ_ADDRESS_WRAP || address_mode == VQ_ADDRESS_CLAMP, "easu: unknown address mode");
     VQ_REQUIRE(in.ptr != out.ptr, "easu: in-place is not supported");
     EasuCon c; memcpy(&c, con, 16);
-    const dim3 grid((out.width + ST_BX - 1) / ST_BX, (out.height + ST_BY - 1) / ST_BY);
-    if (address_mode == VQ_ADDRESS_WRAP) easu_kernel<VQ_ADDRESS_WRAP><<<grid, dim3(ST_BX, ST_BY), 0, (cudaStream_t)stream>>>(make_view(in), make_view(out), c);
-    else                                 easu_kernel<VQ_ADDRESS_CLAMP><<<grid, dim3(ST_BX, ST_BY), 0, (cudaStream_t)stream>>>(make_view(in), make_view(out), c);
+    cudaStream_t st = (cudaStream_t)stream;
+    // ratio <= 1 (upscale or 1:1) and the footprint of a 32x16 output tile fits the staged tile: shared-memory path
+    const bool up = c.c0x > 0.0f && c.c0y > 0.0f && c.c0x <= 1.0f && c.c0y <= 1.0f;
+    if (up) {
+        const dim3 grid((out.width + EU_BX - 1) / EU_BX, (out.height + EU_BY - 1) / EU_BY);
+        if (address_mode == VQ_ADDRESS_WRAP) easu_up_kernel<VQ_ADDRESS_WRAP><<<grid, dim3(EU_BX, EU_BY), 0, st>>>(make_view(in), make_view(out), c);
+        else                                 easu_up_kernel<VQ_ADDRESS_CLAMP><<<grid, dim3(EU_BX, EU_BY), 0, st>>>(make_view(in), make_view(out), c);
+    } else {
+        const dim3 grid((out.width + ST_BX - 1) / ST_BX, (out.height + ST_BY - 1) / ST_BY);
+        if (address_mode == VQ_ADDRESS_WRAP) easu_kernel<VQ_ADDRESS_WRAP><<<grid, dim3(ST_BX, ST_BY), 0, st>>>(make_view(in), make_view(out), c);
+        else                                 easu_kernel<VQ_ADDRESS_CLAMP><<<grid, dim3(ST_BX, ST_BY), 0, st>>>(make_view(in), make_view(out), c);
+    }
     return vq_check_launch("fsr_easu");
 }
 
