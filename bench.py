@@ -121,12 +121,21 @@ def build_env_maps_gpu(ctx, vq, torch, hdri_w=2048, hdri_h=1024, diff_res=64, sp
     return keep
 
 
-def time_gpu(torch, fn, iters, warmup=3):
-    """median-free simple timing: warmup, then `iters` launches between two CUDA events on the current stream."""
-    for _ in range(warmup):
-        fn()
-    torch.cuda.synchronize()
+def time_gpu(torch, fn, iters, warmup=3, min_warm_ms=30.0, min_timed_ms=20.0):
+    """CUDA-event timing on the current stream. Warm-up runs at least `warmup` launches AND `min_warm_ms` of GPU work (the
+    SM clock needs a few ms of load to leave its idle state after host-side input generation); the timed region is at
+    least `iters` launches and about `min_timed_ms` long."""
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record(); n = 0
+    while True:
+        fn(); n += 1
+        if n >= warmup:
+            e1.record(); torch.cuda.synchronize()
+            if e0.elapsed_time(e1) >= min_warm_ms or n >= 2000:
+                break
+    per = max(e0.elapsed_time(e1) / n, 1e-3)
+    iters = max(iters, min(int(min_timed_ms / per), 2000))
+    torch.cuda.synchronize()
     e0.record()
     for _ in range(iters):
         fn()
@@ -192,6 +201,47 @@ def extra_passes(ctx, vq, torch, envk, peak):
     nb = envk["hdri_w"] * envk["hdri_h"] * (16 * 4 / 3 + 16 / 3)
     out["hdri_min_pyramid"] = {"ms": round(ms, 4), "algorithmic_GBps": round(nb / ms / 1e6, 1)}
     return out
+
+
+def ibl_specular_strong_scaling(ctx, vq, torch, dist, rank, world, hdri_w=4096, hdri_h=2048, res=512, mips=9, iters=3):
+    """BASELINE config 5 (IBL half): 4096x2048 HDRI -> 512^2 x6 x9-mip specular prefilter, STRONG scaling: the flattened
+    (mip, face, row) space is cut into `world` cost-balanced contiguous ranges, every rank prefilters its range from a
+    replicated HDRI pyramid, then ONE all-gather assembles the packed cubemap on every rank (inside the timed region)."""
+    from vqengine_b200 import synth, distributed as vd
+    levels = vq.mip_level_count(hdri_w, hdri_h)
+    pyr_t = torch.zeros((vq.pyramid_texel_count(hdri_w, hdri_h, levels), 4), dtype=torch.float32, device="cuda")
+    pyr_t[: hdri_w * hdri_h] = torch.from_numpy(synth.hdri(hdri_w, hdri_h)).cuda().reshape(-1, 4)
+    pyr = vq.pyramid_of(pyr_t, hdri_w, hdri_h, levels)
+    ctx.hdri_build_mips(pyr)
+    cube_t = torch.zeros((vq.cubemap_texel_count(res, mips), 4), dtype=torch.float32, device="cuda")
+    cube = vq.cubemap_of(cube_t, res, mips)
+    rows, texels = vd.specular_tiles(res, mips, world)
+    rb, re = rows[rank]
+
+    def step():
+        ctx.specular_prefilter(pyr, cube, 512, rb, re)
+        if dist is not None and world > 1:
+            vd.allgather_ranges(cube_t, texels)
+
+    step(); torch.cuda.synchronize()
+    if dist: dist.barrier()
+    e0, e1, e2 = (torch.cuda.Event(enable_timing=True) for _ in range(3))
+    e0.record()
+    for _ in range(iters):
+        step()
+    e1.record()
+    for _ in range(iters):
+        ctx.specular_prefilter(pyr, cube, 512, rb, re)
+    e2.record()
+    torch.cuda.synchronize()
+    t = torch.tensor([e0.elapsed_time(e1) / iters, e1.elapsed_time(e2) / iters], dtype=torch.float64, device="cuda")
+    if dist: dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    ms, ms_compute = float(t[0]), float(t[1])
+    n_tex = vq.cubemap_texel_count(res, mips)
+    del pyr_t, cube_t
+    return {"config": f"{hdri_w}x{hdri_h} HDRI -> {res}^2 x6 x{mips} mips, 512 samples; strong scaling over {world} GPU(s), cost-balanced row ranges + 1 all-gather (33.5 MB)",
+            "ms": round(ms, 3), "texels_per_s": round(n_tex / ms * 1e3), "ms_compute_only": round(ms_compute, 3),
+            "rows_per_rank": [b - a for a, b in rows]}
 
 
 # ------------------------------------------------------------------------------------------------
@@ -391,10 +441,17 @@ def main():
                         "api": "vq_forward_lighting_host (pinned host buffers, 16 row chunks pipelined over 3 streams)"},
                 "gpu_launches": int(timed_launches), "clocks": clocks}
         if gather: line["allgather"] = gather
-    if world == 1 and rank == 0:
+    ibl_strong = None
+    if not args.no_extra:
         del hpl, hout
+        hpl = hout = None
+        ibl_strong = ibl_specular_strong_scaling(ctx, vq, torch, dist, rank, world)
+    if rank == 0 and ibl_strong is not None:
+        line["ibl_specular_prefilter_strong"] = ibl_strong
+    if world == 1 and rank == 0:
         if not args.no_extra:
             line["extra"] = extra_passes(ctx, vq, torch, envk, peak)
+            line["extra"]["note"] = "per-kernel figures for the other SURVEY.md section-8 rows; not part of `value`"
         if not args.no_cpu:
             line["cpu_baseline"] = cpu_reference_forward(planes, env=cpu_env())
     if rank == 0:

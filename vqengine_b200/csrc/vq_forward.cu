@@ -348,12 +348,13 @@ __global__ void __launch_bounds__(FWD_THREADS, FWD_MIN_BLOCKS) forward_kernel(co
         {
             const float3 F0 = lerp(f3(0.04f), albedo, metalness);
             const float NdotVs = saturate(s.nsLen * s.nv);       // saturate(dot(s.N, V))
-            const float3 Nr = f3(Ns.x * P.cosB - Ns.z * P.sinB, Ns.y, Ns.x * P.sinB + Ns.z * P.cosB);
+            const bool rot = P.sinB != 0.0f || P.cosB != 1.0f;       // uniform: yaw offset 0 is the common case
+            const float3 Nr = rot ? f3(Ns.x * P.cosB - Ns.z * P.sinB, Ns.y, Ns.x * P.sinB + Ns.z * P.cosB) : Ns;
             const float3 diffIrr = sample_cube(P.diff, Nr, 0);
             float3 specCol = f3(0.0f); float2 sb = make_float2(0.0f, 0.0f);
             if (!P.diffuseOnly) {
                 const float3 R0 = reflect(-s.V, Ns);
-                const float3 R = f3(R0.x * P.cosB - R0.z * P.sinB, R0.y, R0.x * P.sinB + R0.z * P.cosB);
+                const float3 R = rot ? f3(R0.x * P.cosB - R0.z * P.sinB, R0.y, R0.x * P.sinB + R0.z * P.cosB) : R0;
                 const int mip = (int)(roughness * (float)P.maxLod);
                 specCol = sample_cube(P.spec, R, mip);
                 sb = sample_lut(P.lut, NdotVs, roughness);
