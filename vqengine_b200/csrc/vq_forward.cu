@@ -243,18 +243,22 @@ __device__ __forceinline__ void shade_point(const Px& s, Acc& acc, float3 cam, c
 
 constexpr int FWD_BX = 64, FWD_BY = 4;   // 256 threads: 64 x 4 pixel tile; grid.x covers the row, grid.y strides rows
 
-// Tuning knobs, A/B-measured on B200 at 4K (gpurun_out/perf_variants2.log, us per frame):
-//   blocks/SM 4, no prefetch, no pairing: 344   | 4,no,pair: 379 | 3,no,pair: 364 | 3,prefetch,pair: 381
-//   2,prefetch,pair (116 regs, no spills): 358  | 4,prefetch,pair (heavy spills): 425
-// Occupancy (8 warps/scheduler at 64 registers) beats the extra ILP of prefetching / pairing at this register budget.
+// Tuning knobs, A/B-measured on B200 at 4K (profiles/r01_forward_variants.txt, us per frame):
+//   blocks/SM, prefetch, pair, IBL-last:  3,0,0,1 -> 328 (80 regs, no spills)  | 4,0,0,1 -> 334 | 4,0,0,0 -> 344
+//   3,0,1,1 -> 349 | 2,1,1,0 (116 regs) -> 358 | 3,0,1,0 -> 364 | 4,0,1,x -> 376-379 | 3,1,1,0 -> 381 | 5,0,0,1 -> 437
+// Shading the lights first and the environment map last keeps the 8 gathered texels out of the light loop's live
+// range; neither register prefetching nor interleaving two lights pays at this register budget.
 #ifndef FWD_MIN_BLOCKS
-#define FWD_MIN_BLOCKS 4
+#define FWD_MIN_BLOCKS 3
 #endif
 #ifndef FWD_PREFETCH
 #define FWD_PREFETCH 0
 #endif
 #ifndef FWD_PAIR
 #define FWD_PAIR 0
+#endif
+#ifndef FWD_IBL_LAST
+#define FWD_IBL_LAST 1
 #endif
 __global__ void __launch_bounds__(FWD_THREADS, FWD_MIN_BLOCKS) forward_kernel(const __grid_constant__ FwdParams P) {
     __shared__ SPoint sPoint[MAX_POINT];
@@ -344,6 +348,7 @@ __global__ void __launch_bounds__(FWD_THREADS, FWD_MIN_BLOCKS) forward_kernel(co
             I += xyz(em) * em.w;
         }
 
+#if !FWD_IBL_LAST
         // ---- environment map (Lighting.hlsl:360-395, BRDF.hlsl:196-207) ----
         {
             const float3 F0 = lerp(f3(0.04f), albedo, metalness);
@@ -370,6 +375,7 @@ __global__ void __launch_bounds__(FWD_THREADS, FWD_MIN_BLOCKS) forward_kernel(co
             I.z += (1.0f - Ks.z) * om * (diffIrr.z * albedo.z) + specCol.z * fmaf(Ks.z, sb.x, sb.y);
         }
 
+#endif
         Acc acc; acc.a = f3(0.0f); acc.b = f3(0.0f); acc.c = f3(0.0f);
         // ---- point lights, then unshadowed point casters (Lighting.hlsl:308-322; PSMain :310-313,321-340) ----
         // two at a time: the two bodies are independent, so their dependency chains interleave
@@ -402,6 +408,34 @@ __global__ void __launch_bounds__(FWD_THREADS, FWD_MIN_BLOCKS) forward_kernel(co
             I.y += fmaf(K1.y, acc.a.y, fmaf(omF0.y, acc.b.y, F0.y * acc.c.y));
             I.z += fmaf(K1.z, acc.a.z, fmaf(omF0.z, acc.b.z, F0.z * acc.c.z));
         }
+#if FWD_IBL_LAST
+        // ---- environment map (Lighting.hlsl:360-395, BRDF.hlsl:196-207) ----
+        {
+            const float3 F0 = lerp(f3(0.04f), albedo, metalness);
+            const float NdotVs = saturate(s.nsLen * s.nv);       // saturate(dot(s.N, V))
+            const bool rot = P.sinB != 0.0f || P.cosB != 1.0f;       // uniform: yaw offset 0 is the common case
+            const float3 Nr = rot ? f3(Ns.x * P.cosB - Ns.z * P.sinB, Ns.y, Ns.x * P.sinB + Ns.z * P.cosB) : Ns;
+            const float3 diffIrr = sample_cube(P.diff, Nr, 0);
+            float3 specCol = f3(0.0f); float2 sb = make_float2(0.0f, 0.0f);
+            if (!P.diffuseOnly) {
+                const float3 R0 = reflect(-s.V, Ns);
+                const float3 R = rot ? f3(R0.x * P.cosB - R0.z * P.sinB, R0.y, R0.x * P.sinB + R0.z * P.cosB) : R0;
+                const int mip = (int)(roughness * (float)P.maxLod);
+                specCol = sample_cube(P.spec, R, mip);
+                sb = sample_lut(P.lut, NdotVs, roughness);
+            }
+            const float fr = pow5(1.0f - NdotVs);                // FresnelWithRoughness, BRDF.hlsl:152-156
+            const float omr = 1.0f - roughness;
+            const float3 Ks = f3(fmaf(fmaxf(omr, F0.x) - F0.x, fr, F0.x),
+                                 fmaf(fmaxf(omr, F0.y) - F0.y, fr, F0.y),
+                                 fmaf(fmaxf(omr, F0.z) - F0.z, fr, F0.z));
+            const float om = 1.0f - metalness;
+            I.x += (1.0f - Ks.x) * om * (diffIrr.x * albedo.x) + specCol.x * fmaf(Ks.x, sb.x, sb.y);
+            I.y += (1.0f - Ks.y) * om * (diffIrr.y * albedo.y) + specCol.y * fmaf(Ks.y, sb.x, sb.y);
+            I.z += (1.0f - Ks.z) * om * (diffIrr.z * albedo.z) + specCol.z * fmaf(Ks.z, sb.x, sb.y);
+        }
+
+#endif
         st_stream(P.out.row(y) + x, make_float4(I.x, I.y, I.z, roughness));   // :380
         if (FWD_PREFETCH) { pa = paN; nr = nrN; am = amN; }
         else if (more) {
