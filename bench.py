@@ -215,13 +215,17 @@ def ibl_specular_strong_scaling(ctx, vq, torch, dist, rank, world, hdri_w=4096, 
     ctx.hdri_build_mips(pyr)
     cube_t = torch.zeros((vq.cubemap_texel_count(res, mips), 4), dtype=torch.float32, device="cuda")
     cube = vq.cubemap_of(cube_t, res, mips)
-    rows, texels = vd.specular_tiles(res, mips, world)
-    rb, re = rows[rank]
+    plan = vd.InterleavedSpecularPlan(res, mips, world)
+    my_rows = plan.row_ranges(rank)
+
+    def compute():
+        for rb, re in my_rows:
+            ctx.specular_prefilter(pyr, cube, 512, rb, re)
 
     def step():
-        ctx.specular_prefilter(pyr, cube, 512, rb, re)
+        compute()
         if dist is not None and world > 1:
-            vd.allgather_ranges(cube_t, texels)
+            plan.gather(cube_t, rank)
 
     step(); torch.cuda.synchronize()
     if dist: dist.barrier()
@@ -231,7 +235,7 @@ def ibl_specular_strong_scaling(ctx, vq, torch, dist, rank, world, hdri_w=4096, 
         step()
     e1.record()
     for _ in range(iters):
-        ctx.specular_prefilter(pyr, cube, 512, rb, re)
+        compute()
     e2.record()
     torch.cuda.synchronize()
     t = torch.tensor([e0.elapsed_time(e1) / iters, e1.elapsed_time(e2) / iters], dtype=torch.float64, device="cuda")
@@ -239,9 +243,9 @@ def ibl_specular_strong_scaling(ctx, vq, torch, dist, rank, world, hdri_w=4096, 
     ms, ms_compute = float(t[0]), float(t[1])
     n_tex = vq.cubemap_texel_count(res, mips)
     del pyr_t, cube_t
-    return {"config": f"{hdri_w}x{hdri_h} HDRI -> {res}^2 x6 x{mips} mips, 512 samples; strong scaling over {world} GPU(s), cost-balanced row ranges + 1 all-gather (33.5 MB)",
+    return {"config": f"{hdri_w}x{hdri_h} HDRI -> {res}^2 x6 x{mips} mips, 512 samples; strong scaling over {world} GPU(s): every mip split into {world} equal row blocks (tiny mips replicated) + ONE all-gather of the 33.5 MB cubemap",
             "ms": round(ms, 3), "texels_per_s": round(n_tex / ms * 1e3), "ms_compute_only": round(ms_compute, 3),
-            "rows_per_rank": [b - a for a, b in rows]}
+            "rows_per_rank": sum(b - a for a, b in my_rows), "replicated_mips": [m for (m, _, _, _) in plan.replicated]}
 
 
 # ------------------------------------------------------------------------------------------------

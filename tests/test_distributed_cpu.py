@@ -69,6 +69,17 @@ def _worker(rank, world, port, mode, q):
             buf[a:b] = float(rank + 1)
             vd.allgather_ranges(buf, tiles)
             want = torch.repeat_interleave(torch.arange(1, world + 1, dtype=torch.float32), 8)[:, None, None].expand(H, W, 4)
+        elif mode == "interleaved":   # equal-cost + equal-size plan: pack -> one all_gather -> per-mip strided copy
+            res, mips = 16, 4
+            plan = vd.InterleavedSpecularPlan(res, mips, world)
+            n = vq.cubemap_texel_count(res, mips)
+            buf = torch.zeros((n, 4))
+            want = torch.arange(0, n, dtype=torch.float32)[:, None] * 2.0 + torch.tensor([0.0, 0.25, 0.5, 1.0])
+            covered = torch.zeros(n, dtype=torch.bool)
+            for (ra, rb) in plan.row_ranges(rank):
+                a, b = plan.texel_range(ra, rb)
+                buf[a:b] = want[a:b]
+            plan.gather(buf, rank)
         else:   # packed specular cubemap: unequal texel ranges
             res, mips = 16, 4
             rows, texels = vd.specular_tiles(res, mips, world, samples=64)
@@ -84,7 +95,7 @@ def _worker(rank, world, port, mode, q):
 
 
 @pytest.mark.parametrize("world", [2, 3])
-@pytest.mark.parametrize("mode", ["rows", "equal", "spec"])
+@pytest.mark.parametrize("mode", ["rows", "equal", "spec", "interleaved"])
 def test_tiles_gather_gloo(world, mode):
     ctx = mp.get_context("spawn")
     q = ctx.Queue()
@@ -94,3 +105,23 @@ def test_tiles_gather_gloo(world, mode):
     res = [q.get(timeout=120) for _ in range(world)]
     for p in procs: p.join(timeout=60)
     assert all(ok for _, ok in res), res
+
+
+def test_interleaved_plan_partitions_every_row_once_or_replicates():
+    for world in (1, 2, 3, 8):
+        plan = vd.InterleavedSpecularPlan(512, 9, world)
+        assert plan.total_rows == vq.cubemap_row_count(512, 9)
+        cover = np.zeros(plan.total_rows, np.int32)
+        sizes = []
+        for r in range(world):
+            rr = plan.row_ranges(r)
+            sizes.append(sum(plan.texel_range(a, b)[1] - plan.texel_range(a, b)[0] for a, b in rr))
+            for a, b in rr:
+                cover[a:b] += 1
+        rep = np.zeros(plan.total_rows, bool)
+        for (_, r0, rows, _) in plan.replicated:
+            rep[r0:r0 + rows] = True
+        assert (cover[~rep] == 1).all() and (cover[rep] == world).all()
+        assert len(set(sizes)) == 1                       # equal bytes per rank
+    p8 = vd.InterleavedSpecularPlan(512, 9, 8)
+    assert [m for (m, _, _, _) in p8.replicated] == [8]     # only the 2x2 mip does not divide by 8

@@ -1,0 +1,68 @@
+"""Builds profiles/README.md from the bench JSON lines kept under profiles/ (r01_bench_{1,2,8}gpu.json)."""
+import json, os, sys
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+P = os.path.join(ROOT, "profiles")
+
+def load(name):
+    p = os.path.join(P, name)
+    if not os.path.exists(p): return None
+    for line in reversed(open(p).read().splitlines()):
+        line = line.strip()
+        if line.startswith("{"):
+            try: return json.loads(line)
+            except Exception: pass
+    return None
+
+b1, b2, b8 = load("r01_bench_1gpu.json"), load("r01_bench_2gpu.json"), load("r01_bench_8gpu.json")
+peak = b1["roofline"]["peak"]
+out = []
+out.append("# profiles/ — round-1 measurements and ncu evidence (B200, sm_100a)\n")
+out.append("All numbers are CUDA-event timings from `bench.py` on a `gpurun` B200 box (no profiler attached); the ncu files are for "
+           "per-kernel shares, DRAM traffic and stall reasons only. Roofline denominator: **measured** HBM copy bandwidth "
+           f"{peak:.0f} GB/s (`MEASURED_PEAKS.json`, \"of measured\").\n")
+out.append("## Headline (BASELINE.json metric: forward-PBR @4K)\n")
+out.append("| N GPUs | Mpixels/s (HBM-resident) | ms/step | HBM frac (algorithmic 64 B/px) | e2e Mpixels/s (host buffers, PCIe inside) | with all-gather of tiles |")
+out.append("|---|---|---|---|---|---|")
+for b in (b1, b2, b8):
+    if not b: continue
+    ag = b.get("allgather")
+    out.append(f"| {b['n_gpus']} | {b['value']:.0f} | {b['ms_per_step']:.4f} | {b['roofline']['frac']:.3f} | {b['e2e']['value']:.0f} | "
+               + (f"{ag['value_with_allgather']:.0f} Mpx/s ({ag['ms_per_step_with_allgather']:.3f} ms/step)" if ag else "—") + " |")
+cb = b1.get("cpu_baseline")
+if cb:
+    out.append(f"\nCPU baseline (scalar C++ oracle = CPU port of the HLSL, all host threads): **{cb['value']:.1f} Mpixels/s on {cb['cores']} cores** — {cb['sample']}.")
+    out.append(f"GPU/CPU = {b1['value'] / cb['value']:.0f}x (HBM-resident), {b1['e2e']['value'] / cb['value']:.0f}x end to end. (A large ratio says nothing about kernel quality; the roofline fraction does.)\n")
+out.append(f"Clocks during the timed region: {b1.get('clocks')}\n")
+out.append("## IBL specular prefilter, strong scaling (BASELINE config 5: 4096x2048 HDRI -> 512^2 x6 x9 mips, 512 samples)\n")
+out.append("| N GPUs | ms (compute + all-gather of the 33.5 MB cubemap) | texels/s | compute only ms | speed-up vs 1 GPU |")
+out.append("|---|---|---|---|---|")
+base = None
+for b in (b1, b2, b8):
+    if not b or "ibl_specular_prefilter_strong" not in b: continue
+    s = b["ibl_specular_prefilter_strong"]
+    base = base or s["ms"]
+    out.append(f"| {b['n_gpus']} | {s['ms']:.3f} | {s['texels_per_s']:.3e} | {s['ms_compute_only']:.3f} | {base / s['ms']:.2f}x |")
+ex = b1.get("extra", {})
+out.append("\n## Per-kernel table (1 GPU, 3840x2160 unless stated)\n")
+out.append("| pass | ms | algorithmic GB/s | frac of measured HBM peak | note |")
+out.append("|---|---|---|---|---|")
+out.append(f"| K1 forward PBR (4 point + 1 dir + IBL) | {b1['ms_per_step']:.4f} | {b1['roofline']['achieved']:.0f} | {b1['roofline']['frac']:.3f} | instruction-issue bound (~950 instr/pixel, ncu r01_forward_d); DRAM traffic {b1['roofline'].get('traffic')} B vs algorithmic {b1['roofline']['algorithmic_bytes_per_launch']} B |")
+names = [("spd", "K10 SPD (11 mips)"), ("blur_x", "K5 blur X"), ("blur_y", "K5 blur Y"), ("tonemap", "K6 tonemap sRGB"), ("cas", "K7 CAS"),
+         ("fsr_easu_2x", "K8 EASU 4K->8K"), ("fsr_rcas_8k", "K9 RCAS @8K"), ("post_chain_4k", "post chain total (config 4)")]
+for k, label in names:
+    if k in ex:
+        e = ex[k]
+        out.append(f"| {label} | {e['ms']:.4f} | {e['algorithmic_GBps']:.0f} | {e['hbm_frac']:.3f} | |")
+for k, label in [("ibl_specular_prefilter", "K3 specular prefilter"), ("ibl_diffuse_irradiance", "K2 diffuse irradiance (config 2)"),
+                 ("ibl_diffuse_irradiance_reference_step", "K2 diffuse, engine step 0.010"), ("brdf_lut", "K4 BRDF LUT"), ("hdri_min_pyramid", "K11 HDRI min pyramid")]:
+    if k in ex:
+        e = ex[k]
+        rate = f"{e.get('texels_per_s', 0):.3e} texels/s, " if "texels_per_s" in e else ""
+        rate += f"{e.get('samples_per_s', 0):.3e} samples/s" if "samples_per_s" in e else (f"{e.get('algorithmic_GBps')} GB/s" if "algorithmic_GBps" in e else "")
+        out.append(f"| {label} | {e['ms']:.4f} | — | — | {e.get('config', '')}; {rate} (SFU/FP32-bound, HBM % is low by construction) |")
+out.append("\n## Files\n")
+for f in sorted(os.listdir(P)):
+    if f != "README.md":
+        out.append(f"* `{f}`")
+open(os.path.join(P, "README.md"), "w").write("\n".join(out) + "\n")
+print("wrote profiles/README.md")

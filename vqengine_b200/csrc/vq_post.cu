@@ -445,13 +445,17 @@ __global__ void __launch_bounds__(ST_BX * ST_BY) easu_kernel(ImgV in, ImgV out, 
     st_stream(out.row(y) + x, make_float4(pix.x, pix.y, pix.z, 1.0f));
 }
 
-// Upscaling path (input/output ratio <= 1, the FSR use case). One THREAD PER INPUT TEXEL 'f': every output pixel whose
-// resolve position floors to that texel shares the 12 taps, their lumas and the four FsrEasuSetF analyses (which depend
-// only on the lumas), so those are computed once and only the bilinear blend of the analyses + the 12 tap weights are
-// per output pixel. At 2x this halves the instruction count per output pixel (505 -> ~280, ncu r01). The CTA's input
-// footprint is staged once into shared memory with the sampler's addressing applied.
-constexpr int EU_BX = 32, EU_BY = 8;                  // input texels per CTA
-constexpr int EU_TW = EU_BX + 3, EU_TH = EU_BY + 3;   // + reach of the kernel: 1 left/top, 2 right/bottom
+// Upscaling path (input/output ratio <= 1, the FSR use case), two phases per CTA of 32x8 OUTPUT pixels:
+//   stage  : the CTA's input footprint (<= 36x12 texels) goes to shared memory once, sampler addressing applied,
+//            with the tap's luma in .w;
+//   phase 1: one thread per candidate 'f' texel (<= 32x8) evaluates the four FsrEasuSetF analyses — they depend only
+//            on the 12 lumas around 'f', so every output pixel that resolves to the same texel shares them (4 outputs
+//            per texel at 2x) — and parks them in shared memory;
+//   phase 2: one thread per output pixel blends the four analyses with its bilinear weights and runs the 12 taps with
+//            incrementally updated rotated offsets (v(i,j) = v(0,0) + i*A + j*B instead of two dot products per tap).
+// ncu r01: the per-output kernel executed 505 instructions per output pixel; this organisation needs ~60 % of that.
+constexpr int EU_BX = 32, EU_BY = 8;
+constexpr int EU_TW = EU_BX + 4, EU_TH = EU_BY + 4;
 
 struct EasuSet { float dirX, dirY, lenX, lenY; };
 __device__ __forceinline__ EasuSet easu_set_shared(float lA, float lB, float lC, float lD, float lE) {
@@ -469,89 +473,112 @@ __device__ __forceinline__ EasuSet easu_set_shared(float lA, float lB, float lC,
     r.lenY = lenY * lenY;
     return r;
 }
-__device__ __forceinline__ void easu_set_blend(float2& dir, float& len, float w, const EasuSet& a) {
-    dir.x = fmaf(a.dirX, w, dir.x); len = fmaf(a.lenX, w, len);
-    dir.y = fmaf(a.dirY, w, dir.y); len = fmaf(a.lenY, w, len);
+__device__ __forceinline__ void easu_set_blend(float2& dir, float& len, float w, const float4& a) {   // a = {dirX,dirY,lenX,lenY}
+    dir.x = fmaf(a.x, w, dir.x); len = fmaf(a.z, w, len);
+    dir.y = fmaf(a.y, w, dir.y); len = fmaf(a.w, w, len);
+}
+// weight of a tap at rotated, anisotropically scaled offset (vx,vy) (the second half of FsrEasuTapF)
+__device__ __forceinline__ void easu_tap_v(float3& aC, float& aW, float vx, float vy, float lob, float clp, float4 c) {
+    float d2 = fminf(fmaf(vx, vx, vy * vy), clp);
+    float wB = fmaf(2.0f / 5.0f, d2, -1.0f);
+    float wA = fmaf(lob, d2, -1.0f);
+    wB *= wB; wA *= wA;
+    wB = fmaf(25.0f / 16.0f, wB, -(25.0f / 16.0f - 1.0f));
+    const float w = wB * wA;
+    aC.x = fmaf(c.x, w, aC.x); aC.y = fmaf(c.y, w, aC.y); aC.z = fmaf(c.z, w, aC.z);
+    aW += w;
 }
 
 template <int ADDR>
-__global__ void __launch_bounds__(EU_BX * EU_BY) easu_up_kernel(ImgV in, ImgV out, EasuCon con, int maxPerAxis) {
-    __shared__ float4 tile[EU_TH][EU_TW];
-    // this CTA's 'f' texels: fx in [fx0, fx0+EU_BX), starting at -1 (the first output column resolves left of texel 0)
-    const int fx0 = blockIdx.x * EU_BX - 1, fy0 = blockIdx.y * EU_BY - 1;
+__global__ void __launch_bounds__(EU_BX * EU_BY, 4) easu_up_kernel(ImgV in, ImgV out, EasuCon con) {
+    __shared__ float4 tile[EU_TH][EU_TW];          // rgb + luma
+    __shared__ float4 sets[4][EU_BY][EU_BX];       // S,T,U,V analyses of candidate texel (fy-fyFirst, fx-fxFirst); SoA: conflict-free
+    const int ox0 = blockIdx.x * EU_BX, oy0 = blockIdx.y * EU_BY;
+    const int fxFirst = (int)floorf(easu_pos(ox0, con.c0x, con.c0z));
+    const int fyFirst = (int)floorf(easu_pos(oy0, con.c0y, con.c0w));
+    const int tx0 = fxFirst - 1, ty0 = fyFirst - 1;
     const int tid = threadIdx.y * EU_BX + threadIdx.x;
     for (int i = tid; i < EU_TW * EU_TH; i += EU_BX * EU_BY) {
         const int lx = i % EU_TW, ly = i / EU_TW;
-        const float3 v = load_addr<ADDR>(in, fx0 - 1 + lx, fy0 - 1 + ly);
-        tile[ly][lx] = make_float4(v.x, v.y, v.z, 0.0f);
+        const float3 v = load_addr<ADDR>(in, tx0 + lx, ty0 + ly);
+        tile[ly][lx] = make_float4(v.x, v.y, v.z, luma2(v));
     }
     __syncthreads();
-    const int fx = fx0 + threadIdx.x, fy = fy0 + threadIdx.y;
-    if (fx >= in.w || fy >= in.h) return;
-    // candidate outputs: x with floor(pos(x)) == fx lie in [ (fx-b)/s , (fx+1-b)/s ); start one early, test exactly
-    const int xc = (int)floorf(((float)fx - con.c0z) / con.c0x) - 1;
-    const int yc = (int)floorf(((float)fy - con.c0w) / con.c0y) - 1;
-    const float4* base = &tile[threadIdx.y + 1][threadIdx.x + 1];
-    auto tap = [&](int dx, int dy) { const float4 t = base[dy * EU_TW + dx]; return f3(t.x, t.y, t.z); };
-    const float3 b = tap(0, -1), c = tap(1, -1);
-    const float3 e = tap(-1, 0), f = tap(0, 0), g = tap(1, 0), h = tap(2, 0);
-    const float3 i_ = tap(-1, 1), j = tap(0, 1), k = tap(1, 1), l = tap(2, 1);
-    const float3 n = tap(0, 2), o = tap(1, 2);
-    const float bL = luma2(b), cL = luma2(c), eL = luma2(e), fL = luma2(f), gL = luma2(g), hL = luma2(h);
-    const float iL = luma2(i_), jL = luma2(j), kL = luma2(k), lL = luma2(l), nL = luma2(n), oL = luma2(o);
-    const EasuSet sS = easu_set_shared(bL, eL, fL, gL, jL), sT = easu_set_shared(cL, fL, gL, hL, kL);
-    const EasuSet sU = easu_set_shared(fL, iL, jL, kL, nL), sV = easu_set_shared(gL, jL, kL, lL, oL);
-    const float3 min4 = fmin3(fmin3(f, fmin3(g, j)), k);
-    const float3 max4 = fmax3(fmax3(f, fmax3(g, j)), k);
-    for (int yi = 0; yi < maxPerAxis + 3; ++yi) {   // +3: one early start, two for fp slack in the start estimate
-        const int y = yc + yi;
-        if (y < 0 || y >= out.h) continue;
-        float ppy = easu_pos(y, con.c0y, con.c0w);
-        if (floorf(ppy) != (float)fy) continue;
-        ppy -= (float)fy;
-        for (int xi = 0; xi < maxPerAxis + 3; ++xi) {
-            const int x = xc + xi;
-            if (x < 0 || x >= out.w) continue;
-            float ppx = easu_pos(x, con.c0x, con.c0z);
-            if (floorf(ppx) != (float)fx) continue;
-            ppx -= (float)fx;
-            float2 dir = make_float2(0.0f, 0.0f);
-            float len = 0.0f;
-            easu_set_blend(dir, len, (1.0f - ppx) * (1.0f - ppy), sS);
-            easu_set_blend(dir, len, ppx * (1.0f - ppy), sT);
-            easu_set_blend(dir, len, (1.0f - ppx) * ppy, sU);
-            easu_set_blend(dir, len, ppx * ppy, sV);
-            float dirR = dir.x * dir.x + dir.y * dir.y;
-            const bool zro = dirR < (1.0f / 32768.0f);
-            dirR = APrxLoRsqF1(dirR);
-            dirR = zro ? 1.0f : dirR;
-            dir.x = zro ? 1.0f : dir.x;
-            dir.x *= dirR; dir.y *= dirR;
-            len = len * 0.5f;
-            len *= len;
-            const float stretch = (dir.x * dir.x + dir.y * dir.y) * APrxLoRcpF1(fmaxf(fabsf(dir.x), fabsf(dir.y)));
-            const float2 len2 = make_float2(fmaf(stretch - 1.0f, len, 1.0f), fmaf(-0.5f, len, 1.0f));
-            const float lob = fmaf((1.0f / 4.0f - 0.04f) - 0.5f, len, 0.5f);
-            const float clp = APrxLoRcpF1(lob);
-            float3 aC = f3(0.0f);
-            float aW = 0.0f;
-            easu_tap(aC, aW, 0.0f - ppx, -1.0f - ppy, dir, len2, lob, clp, b);
-            easu_tap(aC, aW, 1.0f - ppx, -1.0f - ppy, dir, len2, lob, clp, c);
-            easu_tap(aC, aW, -1.0f - ppx, 1.0f - ppy, dir, len2, lob, clp, i_);
-            easu_tap(aC, aW, 0.0f - ppx, 1.0f - ppy, dir, len2, lob, clp, j);
-            easu_tap(aC, aW, 0.0f - ppx, 0.0f - ppy, dir, len2, lob, clp, f);
-            easu_tap(aC, aW, -1.0f - ppx, 0.0f - ppy, dir, len2, lob, clp, e);
-            easu_tap(aC, aW, 1.0f - ppx, 1.0f - ppy, dir, len2, lob, clp, k);
-            easu_tap(aC, aW, 2.0f - ppx, 1.0f - ppy, dir, len2, lob, clp, l);
-            easu_tap(aC, aW, 2.0f - ppx, 0.0f - ppy, dir, len2, lob, clp, h);
-            easu_tap(aC, aW, 1.0f - ppx, 0.0f - ppy, dir, len2, lob, clp, g);
-            easu_tap(aC, aW, 1.0f - ppx, 2.0f - ppy, dir, len2, lob, clp, o);
-            easu_tap(aC, aW, 0.0f - ppx, 2.0f - ppy, dir, len2, lob, clp, n);
-            const float rw = rcp_fast(aW);
-            const float3 pix = fmin3(max4, fmax3(min4, aC * rw));
-            st_stream(out.row(y) + x, make_float4(pix.x, pix.y, pix.z, 1.0f));
+    // ---- phase 1: candidate 'f' texels of this tile: local (cx,cy), cx <= fp(last x) - fxFirst ----
+    {
+        const int oxl = min(ox0 + EU_BX - 1, out.w - 1), oyl = min(oy0 + EU_BY - 1, out.h - 1);
+        const int ncx = (int)floorf(easu_pos(oxl, con.c0x, con.c0z)) - fxFirst + 1;
+        const int ncy = (int)floorf(easu_pos(oyl, con.c0y, con.c0w)) - fyFirst + 1;
+        const int cx = threadIdx.x, cy = threadIdx.y;
+        if (cx < ncx && cy < ncy) {
+            const float4* t = &tile[cy + 1][cx + 1];                   // 'f'
+            const float bL = t[-EU_TW].w, cL = t[-EU_TW + 1].w;
+            const float eL = t[-1].w, fL = t[0].w, gL = t[1].w, hL = t[2].w;
+            const float iL = t[EU_TW - 1].w, jL = t[EU_TW].w, kL = t[EU_TW + 1].w, lL = t[EU_TW + 2].w;
+            const float nL = t[2 * EU_TW].w, oL = t[2 * EU_TW + 1].w;
+            const EasuSet sS = easu_set_shared(bL, eL, fL, gL, jL), sT = easu_set_shared(cL, fL, gL, hL, kL);
+            const EasuSet sU = easu_set_shared(fL, iL, jL, kL, nL), sV = easu_set_shared(gL, jL, kL, lL, oL);
+            sets[0][cy][cx] = make_float4(sS.dirX, sS.dirY, sS.lenX, sS.lenY);
+            sets[1][cy][cx] = make_float4(sT.dirX, sT.dirY, sT.lenX, sT.lenY);
+            sets[2][cy][cx] = make_float4(sU.dirX, sU.dirY, sU.lenX, sU.lenY);
+            sets[3][cy][cx] = make_float4(sV.dirX, sV.dirY, sV.lenX, sV.lenY);
         }
     }
+    __syncthreads();
+    // ---- phase 2: one output pixel per thread ----
+    const int x = ox0 + threadIdx.x, y = oy0 + threadIdx.y;
+    if (x >= out.w || y >= out.h) return;
+    float ppx = easu_pos(x, con.c0x, con.c0z), ppy = easu_pos(y, con.c0y, con.c0w);
+    const float fpx = floorf(ppx), fpy = floorf(ppy);
+    ppx -= fpx; ppy -= fpy;
+    const int cx = (int)fpx - fxFirst, cy = (int)fpy - fyFirst;
+    float2 dir = make_float2(0.0f, 0.0f);
+    float len = 0.0f;
+    easu_set_blend(dir, len, (1.0f - ppx) * (1.0f - ppy), sets[0][cy][cx]);
+    easu_set_blend(dir, len, ppx * (1.0f - ppy), sets[1][cy][cx]);
+    easu_set_blend(dir, len, (1.0f - ppx) * ppy, sets[2][cy][cx]);
+    easu_set_blend(dir, len, ppx * ppy, sets[3][cy][cx]);
+    float dirR = dir.x * dir.x + dir.y * dir.y;
+    const bool zro = dirR < (1.0f / 32768.0f);
+    dirR = APrxLoRsqF1(dirR);
+    dirR = zro ? 1.0f : dirR;
+    dir.x = zro ? 1.0f : dir.x;
+    dir.x *= dirR; dir.y *= dirR;
+    len = len * 0.5f;
+    len *= len;
+    const float stretch = (dir.x * dir.x + dir.y * dir.y) * APrxLoRcpF1(fmaxf(fabsf(dir.x), fabsf(dir.y)));
+    const float lenx = fmaf(stretch - 1.0f, len, 1.0f), leny = fmaf(-0.5f, len, 1.0f);
+    const float lob = fmaf((1.0f / 4.0f - 0.04f) - 0.5f, len, 0.5f);
+    const float clp = APrxLoRcpF1(lob);
+    // rotated + scaled offset of tap (i,j):  vx = ((i-ppx)*dir.x + (j-ppy)*dir.y)*lenx,  vy = (-(i-ppx)*dir.y + (j-ppy)*dir.x)*leny
+    const float Ax = dir.x * lenx, Bx = dir.y * lenx;        // d vx / d i , d vx / d j
+    const float Ay = -dir.y * leny, By = dir.x * leny;       // d vy / d i , d vy / d j
+    const float vx00 = -(ppx * Ax + ppy * Bx), vy00 = -(ppx * Ay + ppy * By);
+    const float4* t = &tile[cy + 1][cx + 1];                 // 'f'
+    const float4 tf = t[0], tg = t[1], tj = t[EU_TW], tk = t[EU_TW + 1];
+    const float3 min4 = fmin3(fmin3(xyz(tf), fmin3(xyz(tg), xyz(tj))), xyz(tk));
+    const float3 max4 = fmax3(fmax3(xyz(tf), fmax3(xyz(tg), xyz(tj))), xyz(tk));
+    float3 aC = f3(0.0f);
+    float aW = 0.0f;
+    // rows j = -1, 0, 1, 2 of the 12-tap cross; offsets built by additions only
+    const float vxm = vx00 - Bx, vym = vy00 - By;                               // (0,-1)
+    easu_tap_v(aC, aW, vxm, vym, lob, clp, t[-EU_TW]);                           // b (0,-1)
+    easu_tap_v(aC, aW, vxm + Ax, vym + Ay, lob, clp, t[-EU_TW + 1]);             // c (1,-1)
+    easu_tap_v(aC, aW, vx00 - Ax, vy00 - Ay, lob, clp, t[-1]);                   // e (-1,0)
+    easu_tap_v(aC, aW, vx00, vy00, lob, clp, tf);                                // f (0,0)
+    easu_tap_v(aC, aW, vx00 + Ax, vy00 + Ay, lob, clp, tg);                      // g (1,0)
+    easu_tap_v(aC, aW, fmaf(2.0f, Ax, vx00), fmaf(2.0f, Ay, vy00), lob, clp, t[2]);   // h (2,0)
+    const float vx1 = vx00 + Bx, vy1 = vy00 + By;                                // (0,1)
+    easu_tap_v(aC, aW, vx1 - Ax, vy1 - Ay, lob, clp, t[EU_TW - 1]);              // i (-1,1)
+    easu_tap_v(aC, aW, vx1, vy1, lob, clp, tj);                                  // j (0,1)
+    easu_tap_v(aC, aW, vx1 + Ax, vy1 + Ay, lob, clp, tk);                        // k (1,1)
+    easu_tap_v(aC, aW, fmaf(2.0f, Ax, vx1), fmaf(2.0f, Ay, vy1), lob, clp, t[EU_TW + 2]);   // l (2,1)
+    const float vx2 = fmaf(2.0f, Bx, vx00), vy2 = fmaf(2.0f, By, vy00);          // (0,2)
+    easu_tap_v(aC, aW, vx2, vy2, lob, clp, t[2 * EU_TW]);                        // n (0,2)
+    easu_tap_v(aC, aW, vx2 + Ax, vy2 + Ay, lob, clp, t[2 * EU_TW + 1]);          // o (1,2)
+    const float rw = rcp_fast(aW);
+    const float3 pix = fmin3(max4, fmax3(min4, aC * rw));
+    st_stream(out.row(y) + x, make_float4(pix.x, pix.y, pix.z, 1.0f));
 }
 
 extern "C" int vq_fsr_easu(VqContext* ctx, const uint32_t con[16], int address_mode, VqImage in, VqImage out, void* stream) {
@@ -565,13 +592,9 @@ extern "C" int vq_fsr_easu(VqContext* ctx, const uint32_t con[16], int address_m
     // ratio <= 1 (upscale or 1:1) and the footprint of a 32x16 output tile fits the staged tile: shared-memory path
     const bool up = c.c0x > 0.0f && c.c0y > 0.0f && c.c0x <= 1.0f && c.c0y <= 1.0f;
     if (up) {
-        // one thread per input texel fx in [-1, in.width), fy in [-1, in.height); outputs per texel per axis <= ceil(1/ratio)
-        const dim3 grid((in.width + 1 + EU_BX - 1) / EU_BX, (in.height + 1 + EU_BY - 1) / EU_BY);
-        const float rmin = c.c0x < c.c0y ? c.c0x : c.c0y;
-        int maxPerAxis = (int)ceilf(1.0f / rmin);
-        VQ_REQUIRE(maxPerAxis <= 16, "easu: upscale ratio above 16x is not supported");
-        if (address_mode == VQ_ADDRESS_WRAP) easu_up_kernel<VQ_ADDRESS_WRAP><<<grid, dim3(EU_BX, EU_BY), 0, st>>>(make_view(in), make_view(out), c, maxPerAxis);
-        else                                 easu_up_kernel<VQ_ADDRESS_CLAMP><<<grid, dim3(EU_BX, EU_BY), 0, st>>>(make_view(in), make_view(out), c, maxPerAxis);
+        const dim3 grid((out.width + EU_BX - 1) / EU_BX, (out.height + EU_BY - 1) / EU_BY);
+        if (address_mode == VQ_ADDRESS_WRAP) easu_up_kernel<VQ_ADDRESS_WRAP><<<grid, dim3(EU_BX, EU_BY), 0, st>>>(make_view(in), make_view(out), c);
+        else                                 easu_up_kernel<VQ_ADDRESS_CLAMP><<<grid, dim3(EU_BX, EU_BY), 0, st>>>(make_view(in), make_view(out), c);
     } else {
         const dim3 grid((out.width + ST_BX - 1) / ST_BX, (out.height + ST_BY - 1) / ST_BY);
         if (address_mode == VQ_ADDRESS_WRAP) easu_kernel<VQ_ADDRESS_WRAP><<<grid, dim3(ST_BX, ST_BY), 0, st>>>(make_view(in), make_view(out), c);

@@ -95,3 +95,60 @@ def allgather_ranges(buf, ranges: Sequence[Tuple[int, int]], group=None):
     for w in works:
         w.wait()
     return buf
+
+
+class InterleavedSpecularPlan:
+    """Equal-cost AND equal-size partition of the specular prefilter for one all-gather.
+
+    Cost-balanced contiguous ranges differ 50x in size (mip 0 is 75 % of the texels and 1 % of the cost), which forces
+    either padding or one broadcast per owner (8 collectives ~ 0.3 ms of launch latency at 8 GPUs, measured). Instead
+    every mip whose 6*n rows divide by `world` is split into `world` equal row blocks (rank r takes block r of EVERY such
+    mip: equal cost and equal bytes by construction); the few tiny mips that do not divide are simply computed by every
+    rank (a few dozen texels). The gather is then: pack my blocks -> ONE all_gather_into_tensor -> one strided copy per
+    split mip back into the packed cubemap.
+    """
+
+    def __init__(self, res: int, mips: int, world: int):
+        self.res, self.mips, self.world = res, mips, world
+        self.split, self.replicated = [], []      # (mip, row0 (flattened), rows_per_rank, n) / (mip, row0, rows, n)
+        row0 = 0
+        for m in range(mips):
+            n = res >> m
+            rows = 6 * n
+            if rows % world == 0 and world > 1:
+                self.split.append((m, row0, rows // world, n))
+            else:
+                self.replicated.append((m, row0, rows, n))
+            row0 += rows
+        self.total_rows = row0
+        self.chunk_texels = sum(k * n for (_, _, k, n) in self.split)
+
+    def row_ranges(self, rank: int):
+        """flattened (mip, face, row) ranges this rank computes"""
+        out = [(r0 + rank * k, r0 + (rank + 1) * k) for (_, r0, k, _) in self.split]
+        out += [(r0, r0 + rows) for (_, r0, rows, _) in self.replicated]
+        return [(a, b) for a, b in out if b > a]
+
+    def texel_range(self, row_a: int, row_b: int):
+        return specular_row_to_texel(self.res, self.mips, row_a), specular_row_to_texel(self.res, self.mips, row_b)
+
+    def gather(self, cube_t, rank: int, group=None):
+        """cube_t: [texels, 4] packed cubemap; on entry this rank's row_ranges are filled; on exit all are."""
+        import torch
+        import torch.distributed as dist
+        if self.world == 1 or not self.split:
+            return cube_t
+        parts = []
+        for (_, r0, k, _) in self.split:
+            a, b = self.texel_range(r0 + rank * k, r0 + (rank + 1) * k)
+            parts.append(cube_t[a:b])
+        send = torch.cat(parts, dim=0)
+        recv = torch.empty((self.world * self.chunk_texels,) + tuple(cube_t.shape[1:]), dtype=cube_t.dtype, device=cube_t.device)
+        dist.all_gather_into_tensor(recv, send, group=group)
+        recv = recv.view(self.world, self.chunk_texels, *cube_t.shape[1:])
+        off = 0
+        for (_, r0, k, n) in self.split:
+            a, b = self.texel_range(r0, r0 + self.world * k)          # the whole mip: rank blocks are contiguous, in rank order
+            cube_t[a:b].view(self.world, k * n, *cube_t.shape[1:]).copy_(recv[:, off:off + k * n])
+            off += k * n
+        return cube_t
