@@ -105,101 +105,131 @@ extern "C" int vq_tonemap(VqContext* ctx, const VqTonemapperParams* p, VqImage i
 __constant__ float c_gauss[11] = {0.224716f, 0.191756f, 0.119146f, 0.053897f, 0.017746f, 0.004252f,
                                   0.000741f, 0.000094f, 0.000009f, 0.000001f, 0.0f};   // GaussianBlur.hlsl:110
 
-// X pass: a block stages BX_W+24 pixels of BX_ROWS rows into PLANAR shared memory (R,G,B planes) so
-// that each thread reads its 28-value window with conflict-free LDS.128 and produces 4 adjacent
-// pixels from registers (sliding window: 7 LDS.128 per channel per 4 pixels).
-constexpr int BX_T = 128;            // threads along x
-constexpr int BX_ROWS = 2;           // rows per block
-constexpr int BX_W = BX_T * 4;       // output pixels per row per block
-constexpr int BX_SM = BX_W + 24;     // staged: [-12, BX_W+12)
+// X pass: a CTA owns a 512-pixel column strip and walks BX_XR consecutive rows. Each row's BX_W+24 pixels are staged into
+// PLANAR shared memory (R,G,B planes) so that each thread reads its 28-value window with conflict-free LDS.128 and
+// produces 4 adjacent pixels from registers (sliding window: 7 LDS.128 per channel per 4 pixels). The next row's global
+// loads are issued into registers before the current row is filtered (software pipelining), results leave through a
+// shared-memory transpose so that the stores are coalesced.
+constexpr int BX_T = 128;            // threads per CTA (4 autonomous warps)
+#ifndef BX_XR_D
+#define BX_XR_D 4
+#endif
+constexpr int BX_XR = BX_XR_D;       // consecutive rows per CTA (software-pipelined)
+constexpr int BX_WW = 128;           // output pixels per warp per row (4 per lane)
+constexpr int BX_W = BX_WW * (BX_T / 32);   // per CTA
+constexpr int BX_SM = BX_WW + 24;    // staged per warp: [-12, BX_WW+12)
+constexpr int BX_LD = (BX_SM + 31) / 32;    // float4 loads per lane per row (5)
 
-__global__ void __launch_bounds__(BX_T * BX_ROWS) blur_x_kernel(ImgV in, ImgV out, int sizeX, int sizeY) {
-    __shared__ __align__(16) float sm[BX_ROWS][3][BX_SM];
-    __shared__ float4 so[BX_ROWS][BX_W];                  // results, so that the global stores are coalesced
-    const int ty = threadIdx.y;
-    const int y = blockIdx.y * BX_ROWS + ty;
-    const int xBase = blockIdx.x * BX_W;
-    if (y < sizeY) {
+__global__ void __launch_bounds__(BX_T) blur_x_kernel(ImgV in, ImgV out, int sizeX, int sizeY) {
+    // every warp owns its sub-strip end to end (private staging + private output tile): only __syncwarp(), so warps
+    // drift apart and overlap each other's load / filter / store phases instead of meeting at CTA barriers
+    __shared__ __align__(16) float sm[BX_T / 32][3][BX_SM];
+    __shared__ float4 so[BX_T / 32][BX_WW];
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int xBase = blockIdx.x * BX_W + warp * BX_WW;
+    const int row0 = blockIdx.y * BX_XR;
+    if (xBase >= sizeX) return;
+    float4 pre[BX_LD];
+    auto load_row = [&](int y) {
         const float4* __restrict__ src = in.row(y);
-        for (int i = threadIdx.x; i < BX_SM; i += BX_T) {
-            int sx = xBase - 12 + i;
-            sx = min(max(sx, 0), sizeX - 1);              // sampleCoord clamp, GaussianBlur.hlsl:144
-            const float4 v = __ldg(src + sx);
-            sm[ty][0][i] = v.x; sm[ty][1][i] = v.y; sm[ty][2][i] = v.z;
+#pragma unroll
+        for (int q = 0; q < BX_LD; ++q) {
+            const int i = lane + q * 32;
+            const int sx = min(max(xBase - 12 + i, 0), sizeX - 1);       // sampleCoord clamp, GaussianBlur.hlsl:144
+            if (i < BX_SM) pre[q] = __ldg(src + sx);
         }
-    }
-    __syncthreads();
-    if (y < sizeY && xBase + threadIdx.x * 4 < sizeX) {
+    };
+    if (row0 < sizeY) load_row(row0);
+    float (*buf)[BX_SM] = sm[warp];
+    for (int r = 0; r < BX_XR; ++r) {
+        const int y = row0 + r;
+        if (y >= sizeY) break;
+#pragma unroll
+        for (int q = 0; q < BX_LD; ++q) {
+            const int i = lane + q * 32;
+            if (i < BX_SM) { buf[0][i] = pre[q].x; buf[1][i] = pre[q].y; buf[2][i] = pre[q].z; }
+        }
+        __syncwarp();
+        if (r + 1 < BX_XR && y + 1 < sizeY) load_row(y + 1);             // in flight while this row is filtered
         float acc[3][4];
 #pragma unroll
         for (int c = 0; c < 3; ++c) {
-            float win[28];                                 // staged positions 4t .. 4t+27  == image x-12 .. x+15
-            const float4* p = reinterpret_cast<const float4*>(&sm[ty][c][threadIdx.x * 4]);
+            float win[28];                                               // staged positions 4l .. 4l+27 == image x-12 .. x+15
+            const float4* p = reinterpret_cast<const float4*>(&buf[c][lane * 4]);
 #pragma unroll
             for (int q = 0; q < 7; ++q) { const float4 v = p[q]; win[4 * q] = v.x; win[4 * q + 1] = v.y; win[4 * q + 2] = v.z; win[4 * q + 3] = v.w; }
 #pragma unroll
             for (int j = 0; j < 4; ++j) {
                 float a = 0.0f;
 #pragma unroll
-                for (int k = 0; k < 21; ++k) {             // kernelIt order 0..20 as in the HLSL loop
+                for (int k = 0; k < 21; ++k) {                           // kernelIt order 0..20 as in the HLSL loop
                     const int ki = k < 10 ? 10 - k : k - 10;
-                    a = fmaf(win[j + 2 + k], c_gauss[ki], a);   // tap at x+j-10+k -> window index j+2+k
+                    a = fmaf(win[j + 2 + k], c_gauss[ki], a);            // tap at x+j-10+k -> window index j+2+k
                 }
                 acc[c][j] = a;
             }
         }
 #pragma unroll
-        for (int j = 0; j < 4; ++j) so[ty][threadIdx.x * 4 + j] = make_float4(acc[0][j], acc[1][j], acc[2][j], 1.0f);
-    }
-    __syncthreads();
-    if (y >= sizeY) return;
-    float4* __restrict__ dst = out.row(y);
+        for (int j = 0; j < 4; ++j) so[warp][lane * 4 + j] = make_float4(acc[0][j], acc[1][j], acc[2][j], 1.0f);
+        __syncwarp();
+        float4* __restrict__ dst = out.row(y);
 #pragma unroll
-    for (int k = 0; k < 4; ++k) {
-        const int lx = threadIdx.x + k * BX_T;
-        if (xBase + lx < sizeX) st_stream(dst + xBase + lx, so[ty][lx]);
+        for (int k = 0; k < 4; ++k) {
+            const int lx = lane + k * 32;
+            if (xBase + lx < sizeX) st_stream(dst + xBase + lx, so[warp][lx]);
+        }
+        __syncwarp();                                                    // so[] and buf[] free for the next row
     }
 }
 
-// Y pass: a block stages a (BY_H+20) x BY_W tile of float4 and each thread produces BY_PER consecutive
-// rows of one column from a register sliding window (lanes are adjacent columns: conflict-free LDS.128).
-constexpr int BY_W = 32;
-constexpr int BY_TY = 8;
-constexpr int BY_PER = 8;
-constexpr int BY_H = BY_TY * BY_PER;   // 64 output rows per block
+// Y pass: no shared memory. A thread owns one column and marches down BYM_ROWS output rows keeping the last 21 input
+// rows of its column in a REGISTER ring (the loop is unrolled by 21 so that every ring index is a compile-time constant):
+// one coalesced LDG.128 and one STG.128 per output pixel, 63 FMAs, no barriers. Lanes are adjacent columns, so every
+// warp instruction moves 512 contiguous bytes. Segments overlap by 20 rows (re-read through L2).
+constexpr int BYM_T = 128;          // threads per CTA = columns per CTA
+// A/B on B200 at 4K (us): rows/prefetch 21/21: 47.9 | 42/21: 49.2 | 63/21: 51.0 | 63/7: 57.2 | 126/7: 65.3 | 252/7: 62.5
+// (the shared-memory tile version it replaces: 67.5)
+#ifndef BYM_ROWS_D
+#define BYM_ROWS_D 21
+#endif
+#ifndef BYM_PRE_D
+#define BYM_PRE_D 21
+#endif
+constexpr int BYM_ROWS = BYM_ROWS_D; // output rows per thread (multiple of 21)
+constexpr int BYM_PRE = BYM_PRE_D;   // rows requested ahead of use (divides 21): memory-level parallelism per thread
 
-__global__ void __launch_bounds__(BY_W * BY_TY) blur_y_kernel(ImgV in, ImgV out, int sizeX, int sizeY) {
-    __shared__ float4 sm[BY_H + 20][BY_W];
-    const int x = blockIdx.x * BY_W + threadIdx.x;
-    const int yBase = blockIdx.y * BY_H;
-    const int xc = min(x, sizeX - 1);
-    for (int r = threadIdx.y; r < BY_H + 20; r += BY_TY) {
-        int sy = yBase - 10 + r;
-        sy = min(max(sy, 0), sizeY - 1);                   // GaussianBlur.hlsl:180
-        sm[r][threadIdx.x] = __ldg(in.row(sy) + xc);
-    }
-    __syncthreads();
+__global__ void __launch_bounds__(BYM_T) blur_y_kernel(ImgV in, ImgV out, int sizeX, int sizeY) {
+    const int x = blockIdx.x * BYM_T + threadIdx.x;
     if (x >= sizeX) return;
-    const int r0 = threadIdx.y * BY_PER;                   // first output row (tile-relative)
-    float3 acc[BY_PER];
+    const int y0 = blockIdx.y * BYM_ROWS;
+    const float4* __restrict__ src = in.p + x;
+    float4* __restrict__ dst = out.p + x;
+    const int pin = in.pitch4, pout = out.pitch4;
+    float3 ring[21], pre[BYM_PRE];
+    // rows y0-10 .. y0+9 (clamped) fill ring slots 0..19; slot k holds input row (y0 - 10 + k)
 #pragma unroll
-    for (int j = 0; j < BY_PER; ++j) acc[j] = f3(0.0f);
-#pragma unroll
-    for (int t = 0; t < BY_PER + 20; ++t) {                // tap row r0+t (tile) == image row yBase+r0+t-10
-        const float4 v = sm[r0 + t][threadIdx.x];
-#pragma unroll
-        for (int j = 0; j < BY_PER; ++j) {
-            const int k = t - j;                           // kernelIt for output j
-            if (k >= 0 && k < 21) {
-                const float w = c_gauss[k < 10 ? 10 - k : k - 10];
-                acc[j].x = fmaf(v.x, w, acc[j].x); acc[j].y = fmaf(v.y, w, acc[j].y); acc[j].z = fmaf(v.z, w, acc[j].z);
-            }
-        }
+    for (int k = 0; k < 20; ++k) {
+        const int sy = min(max(y0 - 10 + k, 0), sizeY - 1);          // GaussianBlur.hlsl:180
+        ring[k] = xyz(__ldg(src + (size_t)sy * pin));
     }
 #pragma unroll
-    for (int j = 0; j < BY_PER; ++j) {
-        const int y = yBase + r0 + j;
-        if (y < sizeY) out.row(y)[x] = make_float4(acc[j].x, acc[j].y, acc[j].z, 1.0f);
+    for (int k = 0; k < BYM_PRE; ++k) pre[k] = xyz(__ldg(src + (size_t)min(y0 + 10 + k, sizeY - 1) * pin));
+    for (int base = 0; base < BYM_ROWS && y0 + base < sizeY; base += 21) {
+#pragma unroll
+        for (int u = 0; u < 21; ++u) {
+            const int y = y0 + base + u;              // no early exit inside the unrolled body: loads stay hoistable
+            // newest row y+10 (requested BYM_PRE iterations ago) goes to slot (20+u)%21; request row y+10+BYM_PRE
+            ring[(20 + u) % 21] = pre[u % BYM_PRE];
+            pre[u % BYM_PRE] = xyz(__ldg(src + (size_t)min(y + 10 + BYM_PRE, sizeY - 1) * pin));
+            float3 a = f3(0.0f);
+#pragma unroll
+            for (int k = 0; k < 21; ++k) {                           // kernelIt order 0..20 as in the HLSL loop
+                const float w = c_gauss[k < 10 ? 10 - k : k - 10];
+                const float3 v = ring[(u + k) % 21];
+                a.x = fmaf(v.x, w, a.x); a.y = fmaf(v.y, w, a.y); a.z = fmaf(v.z, w, a.z);
+            }
+            if (y < sizeY) st_stream(dst + (size_t)y * pout, make_float4(a.x, a.y, a.z, 1.0f));
+        }
     }
 }
 
@@ -214,11 +244,11 @@ static int blur_common(VqContext* ctx, const VqBlurParams* p, VqImage in, VqImag
     const ImgV vi = make_view(in), vo = make_view(out);
     cudaStream_t s = (cudaStream_t)stream;
     if (!vertical) {
-        const dim3 grid((p->iImageSizeX + BX_W - 1) / BX_W, (p->iImageSizeY + BX_ROWS - 1) / BX_ROWS);
-        blur_x_kernel<<<grid, dim3(BX_T, BX_ROWS), 0, s>>>(vi, vo, p->iImageSizeX, p->iImageSizeY);
+        const dim3 grid((p->iImageSizeX + BX_W - 1) / BX_W, (p->iImageSizeY + BX_XR - 1) / BX_XR);
+        blur_x_kernel<<<grid, BX_T, 0, s>>>(vi, vo, p->iImageSizeX, p->iImageSizeY);
     } else {
-        const dim3 grid((p->iImageSizeX + BY_W - 1) / BY_W, (p->iImageSizeY + BY_H - 1) / BY_H);
-        blur_y_kernel<<<grid, dim3(BY_W, BY_TY), 0, s>>>(vi, vo, p->iImageSizeX, p->iImageSizeY);
+        const dim3 grid((p->iImageSizeX + BYM_T - 1) / BYM_T, (p->iImageSizeY + BYM_ROWS - 1) / BYM_ROWS);
+        blur_y_kernel<<<grid, BYM_T, 0, s>>>(vi, vo, p->iImageSizeX, p->iImageSizeY);
     }
     return vq_check_launch(vertical ? "gaussian_blur_y" : "gaussian_blur_x");
 }
@@ -649,7 +679,7 @@ __global__ void __launch_bounds__(256) spd_kernel(ImgV src, SpdLevels L, int mip
 #pragma unroll
         for (int i = 0; i < 4; ++i) {
             const int sx = sx0 + i, sy = sy0 + j;
-            t[j][i] = (sx < src.w && sy < src.h) ? ld_stream(src.row(sy) + sx) : make_float4(0, 0, 0, 0);
+            t[j][i] = (sx < src.w && sy < src.h) ? ld_stream(src.row(sy) + sx) : make_float4(0, 0, 0, 0);   // (A/B: through L1 is 8 % slower)
         }
     // ---- level 1: 2x2 per thread, column-major operand order (ffx_spd.h:468-476) ----
     float4 l1[2][2];
