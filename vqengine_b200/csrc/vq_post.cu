@@ -484,7 +484,10 @@ __global__ void __launch_bounds__(ST_BX * ST_BY) easu_kernel(ImgV in, ImgV out, 
 //   phase 2: one thread per output pixel blends the four analyses with its bilinear weights and runs the 12 taps with
 //            incrementally updated rotated offsets (v(i,j) = v(0,0) + i*A + j*B instead of two dot products per tap).
 // ncu r01: the per-output kernel executed 505 instructions per output pixel; this organisation needs ~60 % of that.
-constexpr int EU_BX = 32, EU_BY = 8;
+#ifndef EU_BY_D
+#define EU_BY_D 8
+#endif
+constexpr int EU_BX = 32, EU_BY = EU_BY_D;
 constexpr int EU_TW = EU_BX + 4, EU_TH = EU_BY + 4;
 
 struct EasuSet { float dirX, dirY, lenX, lenY; };
@@ -520,25 +523,32 @@ __device__ __forceinline__ void easu_tap_v(float3& aC, float& aW, float vx, floa
 }
 
 template <int ADDR>
-__global__ void __launch_bounds__(EU_BX * EU_BY, 4) easu_up_kernel(ImgV in, ImgV out, EasuCon con) {
+__global__ void __launch_bounds__(EU_BX * EU_BY, EU_BY <= 8 ? 4 : 2) easu_up_kernel(ImgV in, ImgV out, EasuCon con) {
     __shared__ float4 tile[EU_TH][EU_TW];          // rgb + luma
     __shared__ float4 sets[4][EU_BY][EU_BX];       // S,T,U,V analyses of candidate texel (fy-fyFirst, fx-fxFirst); SoA: conflict-free
     const int ox0 = blockIdx.x * EU_BX, oy0 = blockIdx.y * EU_BY;
     const int fxFirst = (int)floorf(easu_pos(ox0, con.c0x, con.c0z));
     const int fyFirst = (int)floorf(easu_pos(oy0, con.c0y, con.c0w));
     const int tx0 = fxFirst - 1, ty0 = fyFirst - 1;
-    const int tid = threadIdx.y * EU_BX + threadIdx.x;
-    for (int i = tid; i < EU_TW * EU_TH; i += EU_BX * EU_BY) {
-        const int lx = i % EU_TW, ly = i / EU_TW;
-        const float3 v = load_addr<ADDR>(in, tx0 + lx, ty0 + ly);
-        tile[ly][lx] = make_float4(v.x, v.y, v.z, luma2(v));
+    // candidate 'f' texels of this tile: local (cx,cy) in [0,ncx) x [0,ncy); the staged footprint is (ncx+3) x (ncy+3)
+    const int oxl = min(ox0 + EU_BX - 1, out.w - 1), oyl = min(oy0 + EU_BY - 1, out.h - 1);
+    const int ncx = (int)floorf(easu_pos(oxl, con.c0x, con.c0z)) - fxFirst + 1;
+    const int ncy = (int)floorf(easu_pos(oyl, con.c0y, con.c0w)) - fyFirst + 1;
+    if (threadIdx.x < ncx + 3) {                               // only the footprint this ratio needs (20x8 texels at 2x, not 36x12)
+        for (int ly = threadIdx.y; ly < ncy + 3; ly += EU_BY) {
+            const float3 v = load_addr<ADDR>(in, tx0 + (int)threadIdx.x, ty0 + ly);
+            tile[ly][threadIdx.x] = make_float4(v.x, v.y, v.z, luma2(v));
+        }
+    }
+    if (threadIdx.x < 4 && (int)threadIdx.x + EU_BX < ncx + 3) {   // columns 32..35 of the footprint (ratio close to 1)
+        for (int ly = threadIdx.y; ly < ncy + 3; ly += EU_BY) {
+            const float3 v = load_addr<ADDR>(in, tx0 + (int)threadIdx.x + EU_BX, ty0 + ly);
+            tile[ly][threadIdx.x + EU_BX] = make_float4(v.x, v.y, v.z, luma2(v));
+        }
     }
     __syncthreads();
-    // ---- phase 1: candidate 'f' texels of this tile: local (cx,cy), cx <= fp(last x) - fxFirst ----
+    // ---- phase 1 ----
     {
-        const int oxl = min(ox0 + EU_BX - 1, out.w - 1), oyl = min(oy0 + EU_BY - 1, out.h - 1);
-        const int ncx = (int)floorf(easu_pos(oxl, con.c0x, con.c0z)) - fxFirst + 1;
-        const int ncy = (int)floorf(easu_pos(oyl, con.c0y, con.c0w)) - fyFirst + 1;
         const int cx = threadIdx.x, cy = threadIdx.y;
         if (cx < ncx && cy < ncy) {
             const float4* t = &tile[cy + 1][cx + 1];                   // 'f'
