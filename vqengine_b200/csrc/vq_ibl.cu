@@ -369,6 +369,10 @@ __global__ void __launch_bounds__(256) brdf_lut_kernel(const __grid_constant__ L
 extern "C" int vq_hdri_build_mips(VqContext* ctx, VqPyramid hd, void* stream) {
     int rc = vq_enter(ctx); if (rc) return rc;
     VQ_REQUIRE(pyr_ok(hd), "bad HDRI pyramid descriptor");
+    if (hd.levels == 1) return VQ_OK;
+    // one launch for the whole chain when the image fits the SPD kernel (<= 4096^2, <= 12 destination levels)
+    if (hd.width <= 4096 && hd.height <= 4096 && hd.levels - 1 <= 12)
+        return vq_spd_min_pyramid(ctx, hd, (cudaStream_t)stream);
     float4* base = (float4*)hd.ptr;
     for (int l = 1; l < hd.levels; ++l) {
         const int sw = hd.width >> (l - 1), dw = hd.width >> l, dh = hd.height >> l;

@@ -655,9 +655,17 @@ extern "C" int vq_fsr_easu(VqContext* ctx, const uint32_t con[16], int address_m
 // =============================================================================================
 struct SpdLevels { float4* p[12]; int w[12], h[12], pitch4[12]; };
 
+// SpdReduce4 is the callback the integration supplies: the engine's colour wrapper averages (AMDFidelityFX.hlsl:463-466),
+// its live depth-pyramid use takes a MIN (DownsampleDepth.hlsl:72) and the CPU HDRI mip filter this backend also routes
+// through the same kernel is min(rgb), alpha = 1 (DXGIUtils.cpp:305-311).
+enum { SPD_AVG = 0, SPD_MIN_RGB_A1 = 1 };
+template <int OP>
 __device__ __forceinline__ float4 spd_reduce4(float4 v0, float4 v1, float4 v2, float4 v3) {
-    return make_float4(((v0.x + v1.x) + v2.x + v3.x) * 0.25f, ((v0.y + v1.y) + v2.y + v3.y) * 0.25f,
-                       ((v0.z + v1.z) + v2.z + v3.z) * 0.25f, ((v0.w + v1.w) + v2.w + v3.w) * 0.25f);
+    if (OP == SPD_AVG)
+        return make_float4(((v0.x + v1.x) + v2.x + v3.x) * 0.25f, ((v0.y + v1.y) + v2.y + v3.y) * 0.25f,
+                           ((v0.z + v1.z) + v2.z + v3.z) * 0.25f, ((v0.w + v1.w) + v2.w + v3.w) * 0.25f);
+    return make_float4(fminf(v0.x, fminf(v1.x, fminf(v2.x, v3.x))), fminf(v0.y, fminf(v1.y, fminf(v2.y, v3.y))),
+                       fminf(v0.z, fminf(v1.z, fminf(v2.z, v3.z))), 1.0f);
 }
 __device__ __forceinline__ float4 shfl4(float4 v, int lane) {
     return make_float4(__shfl_sync(0xffffffffu, v.x, lane), __shfl_sync(0xffffffffu, v.y, lane),
@@ -667,6 +675,7 @@ __device__ __forceinline__ void spd_store(const SpdLevels& L, int lvl /*1-based*
     if (lvl <= mips && x < L.w[lvl - 1] && y < L.h[lvl - 1]) L.p[lvl - 1][(size_t)y * L.pitch4[lvl - 1] + x] = v;
 }
 
+template <int OP>
 __global__ void __launch_bounds__(256) spd_kernel(ImgV src, SpdLevels L, int mips, uint32_t numWorkGroups,
                                                   uint32_t offX, uint32_t offY, uint32_t* counter) {
     __shared__ float4 s4[4][4];        // level-4 texels of this tile
@@ -697,20 +706,20 @@ __global__ void __launch_bounds__(256) spd_kernel(ImgV src, SpdLevels L, int mip
     for (int j = 0; j < 2; ++j)
 #pragma unroll
         for (int i = 0; i < 2; ++i) {
-            l1[j][i] = spd_reduce4(t[2 * j][2 * i], t[2 * j + 1][2 * i], t[2 * j][2 * i + 1], t[2 * j + 1][2 * i + 1]);
+            l1[j][i] = spd_reduce4<OP>(t[2 * j][2 * i], t[2 * j + 1][2 * i], t[2 * j][2 * i + 1], t[2 * j + 1][2 * i + 1]);
             spd_store(L, 1, mips, tileX * 32 + px * 2 + i, tileY * 32 + py * 2 + j, l1[j][i]);
         }
     if (mips <= 1) return;
     // ---- level 2: 1 per thread, row-major operand order (ffx_spd.h:590-595) ----
-    const float4 l2 = spd_reduce4(l1[0][0], l1[0][1], l1[1][0], l1[1][1]);
+    const float4 l2 = spd_reduce4<OP>(l1[0][0], l1[0][1], l1[1][0], l1[1][1]);
     spd_store(L, 2, mips, tileX * 16 + px, tileY * 16 + py, l2);
     // ---- level 3: quad of lanes (Morton bits 0,1) ----
     const int q = lane & ~3;
-    const float4 l3 = spd_reduce4(shfl4(l2, q), shfl4(l2, q | 1), shfl4(l2, q | 2), shfl4(l2, q | 3));
+    const float4 l3 = spd_reduce4<OP>(shfl4(l2, q), shfl4(l2, q | 1), shfl4(l2, q | 2), shfl4(l2, q | 3));
     if (mips >= 3 && (lane & 3) == 0) spd_store(L, 3, mips, tileX * 8 + (px >> 1), tileY * 8 + (py >> 1), l3);
     // ---- level 4: 16 lanes (Morton bits 2,3) ----
     const int g = lane & ~15;
-    const float4 l4 = spd_reduce4(shfl4(l3, g), shfl4(l3, g | 4), shfl4(l3, g | 8), shfl4(l3, g | 12));
+    const float4 l4 = spd_reduce4<OP>(shfl4(l3, g), shfl4(l3, g | 4), shfl4(l3, g | 8), shfl4(l3, g | 12));
     if ((lane & 15) == 0) {
         if (mips >= 4) spd_store(L, 4, mips, tileX * 4 + (px >> 2), tileY * 4 + (py >> 2), l4);
         s4[py >> 2][px >> 2] = l4;
@@ -719,13 +728,13 @@ __global__ void __launch_bounds__(256) spd_kernel(ImgV src, SpdLevels L, int mip
     // ---- level 5 and 6 through shared memory ----
     if (tid < 4 && mips >= 5) {
         const int x = tid & 1, y = tid >> 1;
-        const float4 v = spd_reduce4(s4[2 * y][2 * x], s4[2 * y][2 * x + 1], s4[2 * y + 1][2 * x], s4[2 * y + 1][2 * x + 1]);
+        const float4 v = spd_reduce4<OP>(s4[2 * y][2 * x], s4[2 * y][2 * x + 1], s4[2 * y + 1][2 * x], s4[2 * y + 1][2 * x + 1]);
         spd_store(L, 5, mips, tileX * 2 + x, tileY * 2 + y, v);
         s5[y][x] = v;
     }
     __syncthreads();
     if (tid == 0 && mips >= 6) {
-        const float4 v = spd_reduce4(s5[0][0], s5[0][1], s5[1][0], s5[1][1]);
+        const float4 v = spd_reduce4<OP>(s5[0][0], s5[0][1], s5[1][0], s5[1][1]);
         spd_store(L, 6, mips, tileX, tileY, v);
     }
     if (mips <= 6) return;
@@ -750,7 +759,7 @@ __global__ void __launch_bounds__(256) spd_kernel(ImgV src, SpdLevels L, int mip
         const float4 v1 = __ldcg(p6 + (size_t)(2 * y + 1) * pitch6 + 2 * x);
         const float4 v2 = __ldcg(p6 + (size_t)(2 * y) * pitch6 + 2 * x + 1);
         const float4 v3 = __ldcg(p6 + (size_t)(2 * y + 1) * pitch6 + 2 * x + 1);
-        const float4 v = spd_reduce4(v0, v1, v2, v3);
+        const float4 v = spd_reduce4<OP>(v0, v1, v2, v3);
         spd_store(L, 7, mips, x, y, v);
         sTail[y * 32 + x] = v;
     }
@@ -764,7 +773,7 @@ __global__ void __launch_bounds__(256) spd_kernel(ImgV src, SpdLevels L, int mip
         int x = 0, y = 0;
         if (active) {
             x = tid % nw; y = tid / nw;
-            v = spd_reduce4(sTail[(2 * y) * 32 + 2 * x], sTail[(2 * y) * 32 + 2 * x + 1],
+            v = spd_reduce4<OP>(sTail[(2 * y) * 32 + 2 * x], sTail[(2 * y) * 32 + 2 * x + 1],
                             sTail[(2 * y + 1) * 32 + 2 * x], sTail[(2 * y + 1) * 32 + 2 * x + 1]);
             spd_store(L, lvl, mips, x, y, v);
         }
@@ -791,7 +800,22 @@ extern "C" int vq_spd_downsample(VqContext* ctx, const VqSpdConstants* c, VqImag
     const uint32_t gx = (uint32_t)(src.width + 63) / 64 - c->workGroupOffset[0];
     const uint32_t gy = (uint32_t)(src.height + 63) / 64 - c->workGroupOffset[1];
     VQ_REQUIRE(gx >= 1 && gy >= 1 && gx * gy == c->numWorkGroups, "spd: numWorkGroups does not match the image / offset (use vq_spd_setup)");
-    spd_kernel<<<dim3(gx, gy), 256, 0, (cudaStream_t)stream>>>(make_view(src), L, (int)c->mips, c->numWorkGroups,
+    spd_kernel<SPD_AVG><<<dim3(gx, gy), 256, 0, (cudaStream_t)stream>>>(make_view(src), L, (int)c->mips, c->numWorkGroups,
                                                                c->workGroupOffset[0], c->workGroupOffset[1], ctx->spd_counter);
     return vq_check_launch("spd_downsample");
+}
+
+// K11 through the SPD kernel: the whole HDRI min-pyramid in ONE launch (levels 1..levels-1 of the packed pyramid).
+int vq_spd_min_pyramid(VqContext* ctx, VqPyramid hd, cudaStream_t stream) {
+    SpdLevels L; memset(&L, 0, sizeof(L));
+    const int mips = hd.levels - 1;
+    float4* base = (float4*)hd.ptr;
+    for (int i = 0; i < mips; ++i) {
+        L.p[i] = base + vq_pyramid_offset(hd.width, hd.height, i + 1);
+        L.w[i] = hd.width >> (i + 1); L.h[i] = hd.height >> (i + 1); L.pitch4[i] = L.w[i];
+    }
+    ImgV src; src.p = base; src.w = hd.width; src.h = hd.height; src.pitch4 = hd.width;
+    const unsigned gx = (unsigned)(hd.width + 63) / 64, gy = (unsigned)(hd.height + 63) / 64;
+    spd_kernel<SPD_MIN_RGB_A1><<<dim3(gx, gy), 256, 0, stream>>>(src, L, mips, gx * gy, 0u, 0u, ctx->spd_counter + 1);
+    return vq_check_launch("hdri_build_mips(spd)");
 }
