@@ -423,6 +423,36 @@ def main():
         gather = {"ms_per_step_with_allgather": round(float(tg.item()), 4),
                   "value_with_allgather": round(px_all / float(tg.item()) / 1e3, 1),
                   "allgather_bytes_per_rank_in": (world - 1) * H4K * W4K * 16}
+        # reference result of the NCCL path for the fused check below
+        step(); dist.all_gather_into_tensor(full, out); torch.cuda.synchronize()
+        # ---- fused compute + gather: the forward kernel stores every pixel straight into all ranks' frames over NVLink
+        #      (peer pointers from torch symmetric memory), so the transfer overlaps the shading ----
+        try:
+            import torch.distributed._symmetric_memory as symm
+            frame = symm.empty((world * H4K, W4K, 4), dtype=torch.float32, device=torch.device("cuda", local))
+            hdl = symm.rendezvous(frame, dist.group.WORLD)
+            frame.zero_(); torch.cuda.synchronize(); dist.barrier()
+            # local frame first, then peers in a rotated order so that the ranks do not all write to the same peer at once
+            imgs = [vq.Image(int(hdl.buffer_ptrs[(rank + k) % world]), W4K, world * H4K, W4K * 16) for k in range(world)]
+            fused = lambda: ctx.forward_lighting_multi(pf, pv, gb, envk["env"], imgs, rank * H4K)
+            for _ in range(2):
+                fused(); hdl.barrier()
+            torch.cuda.synchronize(); dist.barrier(); torch.cuda.synchronize()
+            f0, f1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            f0.record()
+            for _ in range(5):
+                fused(); hdl.barrier()
+            f1.record(); torch.cuda.synchronize()
+            tf = torch.tensor([f0.elapsed_time(f1) / 5], dtype=torch.float64, device="cuda")
+            dist.all_reduce(tf, op=dist.ReduceOp.MAX)
+            same = torch.tensor([1.0 if torch.equal(frame, full) else 0.0], device="cuda")
+            dist.all_reduce(same, op=dist.ReduceOp.MIN)
+            gather["fused_p2p"] = {"ms_per_step": round(float(tf.item()), 4), "value": round(px_all / float(tf.item()) / 1e3, 1),
+                                   "equals_nccl_allgather": bool(same.item() == 1.0),
+                                   "how": "vq_forward_lighting_multi: one kernel shades the local tile and stores it into every rank's frame (symmetric-memory peer pointers, NVLink P2P), then one device-side barrier"}
+            del frame
+        except Exception as ex:   # symmetric memory unavailable on this box: keep the NCCL numbers
+            gather["fused_p2p"] = {"error": repr(ex)[:300]}
         del full
 
     line = None

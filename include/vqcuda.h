@@ -121,6 +121,20 @@ VQ_API int vq_forward_lighting(VqContext* ctx,
                                int row_begin, int row_end,
                                void* stream);
 
+/* K1 fused with the gather of tiles (multi-GPU): shades rows [row_begin,row_end) of the local G-buffer tile and stores every
+ * pixel to row (dst_row_offset + y) of EACH of the n_outs (<= 8) destination frames. Destinations other than the local
+ * frame are peer-GPU buffers mapped into this process (CUDA IPC / torch symmetric memory): the stores travel over NVLink
+ * while the SMs keep shading, so the all-gather of tiles overlaps the math instead of following it. The caller provides
+ * the cross-rank barrier after the kernel (e.g. symmetric-memory barrier or a 1-element all-reduce). */
+VQ_API int vq_forward_lighting_multi(VqContext* ctx,
+                                     const VqPerFrameData* per_frame,
+                                     const VqPerViewLightingData* per_view,
+                                     const VqGBuffer* gbuffer,
+                                     const VqEnvironmentMaps* env,
+                                     const VqImage* out_frames, int n_outs, int dst_row_offset,
+                                     int row_begin, int row_end,
+                                     void* stream);
+
 /* The forward pass samples the IBL cubemaps from bordered copies (each face carries a 1-texel border of its
  * neighbours, so seamless bilinear taps never leave the face). vq_environment_prepare builds those copies once and
  * registers them in the context — the analogue of the RENDER_TARGET -> PIXEL_SHADER_RESOURCE barrier the engine

@@ -184,3 +184,26 @@ def test_forward_rejects_bad_arguments(ctx, vq):
     pf.Lights.numPointLights = 0
     with pytest.raises(vq.VqError):
         ctx.forward_lighting(pf, pv, gb, em, torch.zeros((5, 4, 4), device="cuda"))     # size mismatch
+
+
+def test_forward_multi_destination_store(ctx, vq, orc):
+    """vq_forward_lighting_multi: the tile is written to row dst_row_offset+y of EVERY destination frame (on the GPU box
+    the extra destinations are peer-GPU frames over NVLink; here two local frames stand in for them)."""
+    from vqengine_b200 import synth
+    env = small_env()
+    w, h = 80, 24
+    planes = synth.gbuffer(w, h, seed=21)
+    pf, pv = synth.scene_constants(w, h, env["spec_mips"], seed=21)
+    dplanes = [dev(p) for p in planes]
+    gb = vq.GBuffer(vq.image_of(dplanes[0]), vq.image_of(dplanes[1]), vq.image_of(dplanes[2]), vq.null_image())
+    dd, ds, dl = dev(env["diff"]), dev(env["spec"]), dev(env["lut"])
+    em = vq.EnvironmentMaps(vq.cubemap_of(dd, env["diff_res"], 1), vq.cubemap_of(ds, env["spec_res"], env["spec_mips"]), vq.image_of(dl, 2))
+    single = torch.zeros((h, w, 4), dtype=torch.float32, device="cuda")
+    ctx.forward_lighting(pf, pv, gb, em, single)
+    frames = [torch.zeros((3 * h, w, 4), dtype=torch.float32, device="cuda") for _ in range(3)]
+    ctx.forward_lighting_multi(pf, pv, gb, em, [vq.image_of(f) for f in frames], dst_row_offset=h)
+    for f in frames:
+        got = host(f)
+        assert np.array_equal(got[h:2 * h], host(single)) and (got[:h] == 0).all() and (got[2 * h:] == 0).all()
+    with pytest.raises(vq.VqError):      # destination too small for offset + tile
+        ctx.forward_lighting_multi(pf, pv, gb, em, [vq.image_of(frames[0])], dst_row_offset=2 * h + 1)

@@ -138,7 +138,7 @@ ABI_SYMBOLS = [
     "vq_fsr_easu", "vq_fsr_rcas", "vq_spd_downsample", "vq_fsr_easu_con", "vq_fsr_rcas_con", "vq_cas_setup",
     "vq_spd_setup", "vq_mip_level_count", "vq_cubemap_texel_count", "vq_cubemap_offset", "vq_cubemap_row_count",
     "vq_pyramid_texel_count", "vq_pyramid_offset", "vq_forward_lighting_host", "vq_environment_prepare",
-    "vq_environment_invalidate",
+    "vq_environment_invalidate", "vq_forward_lighting_multi",
 ]
 
 
@@ -164,6 +164,8 @@ def _load() -> C.CDLL:
     lib.vq_launch_count.restype = C.c_uint64
     lib.vq_forward_lighting.argtypes = [vp, P(PerFrameData), P(PerViewLightingData), P(GBuffer), P(EnvironmentMaps),
                                         Image, C.c_int, C.c_int, vp]
+    lib.vq_forward_lighting_multi.argtypes = [vp, P(PerFrameData), P(PerViewLightingData), P(GBuffer), P(EnvironmentMaps),
+                                              P(Image), C.c_int, C.c_int, C.c_int, C.c_int, vp]
     lib.vq_forward_lighting_host.argtypes = [vp, P(PerFrameData), P(PerViewLightingData), P(GBuffer),
                                              P(EnvironmentMaps), Image]
     lib.vq_environment_prepare.argtypes = [vp, P(EnvironmentMaps), vp]
@@ -316,6 +318,15 @@ class Context:
         o = image_of(out)
         _check(lib.vq_forward_lighting(self._h, C.byref(per_frame), C.byref(per_view), C.byref(gbuffer), C.byref(env), o,
                                        row_begin, o.height if row_end is None else row_end, _stream_ptr(stream)))
+
+    def forward_lighting_multi(self, per_frame, per_view, gbuffer: GBuffer, env: EnvironmentMaps, out_images, dst_row_offset,
+                               row_begin=0, row_end=None, stream=None):
+        """out_images: list of Image descriptors (local frame first, then the peers' mapped frames)"""
+        arr = (Image * len(out_images))(*out_images)
+        h = gbuffer.position_ao.height
+        _check(lib.vq_forward_lighting_multi(self._h, C.byref(per_frame), C.byref(per_view), C.byref(gbuffer), C.byref(env), arr,
+                                             len(out_images), dst_row_offset, row_begin, h if row_end is None else row_end,
+                                             _stream_ptr(stream)))
 
     def forward_lighting_host(self, per_frame, per_view, host_gbuffer: GBuffer, env: EnvironmentMaps, host_out):
         _check(lib.vq_forward_lighting_host(self._h, C.byref(per_frame), C.byref(per_view), C.byref(host_gbuffer),

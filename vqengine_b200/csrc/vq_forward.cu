@@ -34,7 +34,9 @@ struct FwdParams {
     int maxLod;                        // int(MaxEnvMapLODLevels)
     int diffuseOnly;
     int hasEmissive;
-    ImgV pos, nrm, alb, emi, out;
+    ImgV pos, nrm, alb, emi;
+    ImgV outs[8];                      // destinations: the local frame and, for the fused gather, the peers' frames (NVLink P2P)
+    int nOut, dstRowOffset;            // every shaded pixel goes to row dstRowOffset+y of every destination
     CubeV diff, spec;
     LutV lut;
     int rowBegin, rows, width;
@@ -436,7 +438,10 @@ __global__ void __launch_bounds__(FWD_THREADS, FWD_MIN_BLOCKS) forward_kernel(co
         }
 
 #endif
-        st_stream(P.out.row(y) + x, make_float4(I.x, I.y, I.z, roughness));   // :380
+        {   // :380 — one STG.128 per destination; peer destinations are mapped NVLink addresses (fused compute + gather)
+            const float4 o = make_float4(I.x, I.y, I.z, roughness);
+            for (int k = 0; k < P.nOut; ++k) st_stream(P.outs[k].row(P.dstRowOffset + y) + x, o);
+        }
         if (FWD_PREFETCH) { pa = paN; nr = nrN; am = amN; }
         else if (more) {
             pa = ld_stream(P.pos.row(P.rowBegin + ryn) + x);
@@ -484,16 +489,19 @@ int ensure_bytes(void** ptr, size_t* have, size_t need) {
 
 }  // namespace
 
-int vq_forward_launch(VqContext* ctx, const VqPerFrameData* pf, const VqPerViewLightingData* pv,
-                      const VqGBuffer* gb, const VqEnvironmentMaps* env, VqImage out,
-                      int row_begin, int row_end, cudaStream_t stream) {
-    VQ_REQUIRE(pf && pv && gb && env, "null parameter block");
-    VQ_REQUIRE(vq_image_ok(gb->position_ao) && vq_image_ok(gb->normal_roughness) && vq_image_ok(gb->albedo_metalness) && vq_image_ok(out),
-               "bad image descriptor");
-    const int W = out.width, H = out.height;
-    VQ_REQUIRE(gb->position_ao.width == W && gb->normal_roughness.width == W && gb->albedo_metalness.width == W &&
-               gb->position_ao.height == H && gb->normal_roughness.height == H && gb->albedo_metalness.height == H,
-               "G-buffer planes and output must have the same size");
+int vq_forward_launch_multi(VqContext* ctx, const VqPerFrameData* pf, const VqPerViewLightingData* pv,
+                            const VqGBuffer* gb, const VqEnvironmentMaps* env, const VqImage* outs, int n_outs,
+                            int dst_row_offset, int row_begin, int row_end, cudaStream_t stream) {
+    VQ_REQUIRE(pf && pv && gb && env && outs, "null parameter block");
+    VQ_REQUIRE(n_outs >= 1 && n_outs <= 8, "1..8 destinations");
+    VQ_REQUIRE(vq_image_ok(gb->position_ao) && vq_image_ok(gb->normal_roughness) && vq_image_ok(gb->albedo_metalness), "bad image descriptor");
+    const int W = gb->position_ao.width, H = gb->position_ao.height;
+    VQ_REQUIRE(gb->normal_roughness.width == W && gb->albedo_metalness.width == W &&
+               gb->normal_roughness.height == H && gb->albedo_metalness.height == H, "G-buffer planes must have the same size");
+    VQ_REQUIRE(dst_row_offset >= 0, "negative destination row offset");
+    for (int k = 0; k < n_outs; ++k)
+        VQ_REQUIRE(vq_image_ok(outs[k]) && outs[k].width == W && outs[k].height >= dst_row_offset + H,
+                   "every destination must be as wide as the G-buffer and hold dst_row_offset + height rows");
     VQ_REQUIRE(row_begin >= 0 && row_end <= H && row_begin <= row_end, "row range out of bounds");
     const VqSceneLighting& L = pf->Lights;
     VQ_REQUIRE(L.numPointLights >= 0 && L.numPointLights <= VQ_NUM_LIGHTS_POINT &&
@@ -511,7 +519,8 @@ int vq_forward_launch(VqContext* ctx, const VqPerFrameData* pf, const VqPerViewL
     P.maxLod = (int)pv->MaxEnvMapLODLevels;
     P.diffuseOnly = pv->EnvironmentMapDiffuseOnlyIllumination != 0;
     P.pos = make_view(gb->position_ao); P.nrm = make_view(gb->normal_roughness); P.alb = make_view(gb->albedo_metalness);
-    P.out = make_view(out);
+    for (int k = 0; k < n_outs; ++k) P.outs[k] = make_view(outs[k]);
+    P.nOut = n_outs; P.dstRowOffset = dst_row_offset;
     P.hasEmissive = gb->emissive.ptr != nullptr;
     if (P.hasEmissive) {
         VQ_REQUIRE(vq_image_ok(gb->emissive) && gb->emissive.width == W && gb->emissive.height == H, "bad emissive plane");
@@ -553,11 +562,25 @@ int vq_forward_launch(VqContext* ctx, const VqPerFrameData* pf, const VqPerViewL
     return vq_check_launch("forward_lighting");
 }
 
+int vq_forward_launch(VqContext* ctx, const VqPerFrameData* pf, const VqPerViewLightingData* pv,
+                      const VqGBuffer* gb, const VqEnvironmentMaps* env, VqImage out,
+                      int row_begin, int row_end, cudaStream_t stream) {
+    VQ_REQUIRE(gb && vq_image_ok(out) && out.height == gb->position_ao.height, "G-buffer planes and output must have the same size");
+    return vq_forward_launch_multi(ctx, pf, pv, gb, env, &out, 1, 0, row_begin, row_end, stream);
+}
+
 extern "C" int vq_forward_lighting(VqContext* ctx, const VqPerFrameData* pf, const VqPerViewLightingData* pv,
                                    const VqGBuffer* gb, const VqEnvironmentMaps* env, VqImage out,
                                    int row_begin, int row_end, void* stream) {
     int rc = vq_enter(ctx); if (rc) return rc;
     return vq_forward_launch(ctx, pf, pv, gb, env, out, row_begin, row_end, (cudaStream_t)stream);
+}
+
+extern "C" int vq_forward_lighting_multi(VqContext* ctx, const VqPerFrameData* pf, const VqPerViewLightingData* pv,
+                                         const VqGBuffer* gb, const VqEnvironmentMaps* env, const VqImage* outs, int n_outs,
+                                         int dst_row_offset, int row_begin, int row_end, void* stream) {
+    int rc = vq_enter(ctx); if (rc) return rc;
+    return vq_forward_launch_multi(ctx, pf, pv, gb, env, outs, n_outs, dst_row_offset, row_begin, row_end, (cudaStream_t)stream);
 }
 
 // The IBL cubemaps are sampled from bordered copies (see CubeV). vq_environment_prepare builds them once and
