@@ -200,6 +200,58 @@ def extra_passes(ctx, vq, torch, envk, peak):
     ms = time_gpu(torch, lambda: ctx.hdri_build_mips(pyr), 5, warmup=1)
     nb = envk["hdri_w"] * envk["hdri_h"] * (16 * 4 / 3 + 16 / 3)
     out["hdri_min_pyramid"] = {"ms": round(ms, 4), "algorithmic_GBps": round(nb / ms / 1e6, 1)}
+    out.update(surface_producer_pass(ctx, vq, torch, peak))
+    return out
+
+
+def surface_scene_gpu(ctx, vq, torch, w, h, n_materials=4, tex_res=1024):
+    """SURVEY 8(f).1 workload: n materials x up to 6 RGBA8 maps of tex_res^2 (mip chains built on the GPU by
+    vq_texture_build_mips) + the three interpolant planes and the SSAO plane of a w x h frame"""
+    from vqengine_b200 import synth
+    mats, texs = synth.materials(n_materials, tex_res, uniform=True)
+    keep, mts, tex_bytes = [], [], 0
+    for t in texs:
+        mt = vq.MaterialTextures()
+        for slot, lvl0 in t.items():
+            if lvl0 is None:
+                continue
+            th, tw = lvl0.shape[:2]
+            levels = vq.mip_level_count(tw, th)
+            buf = torch.zeros(vq.pyramid_texel_count(tw, th, levels) * 4, dtype=torch.uint8, device="cuda")
+            buf[: tw * th * 4] = torch.from_numpy(lvl0.reshape(-1)).cuda()
+            desc = vq.texture_of(buf, tw, th, levels)
+            ctx.texture_build_mips(desc)
+            setattr(mt, slot, desc)
+            keep.append(buf); tex_bytes += buf.numel()
+        mts.append(mt)
+    table = ctx.material_table(mats, mts)
+    planes = [torch.from_numpy(p).cuda() for p in synth.surface_inputs(w, h, n_materials)]
+    si = vq.SurfaceInputs(vq.image_of(planes[0]), vq.image_of(planes[1]), vq.image_of(planes[2]), vq.image_of(planes[3], 1))
+    return {"table": table, "inputs": si, "keep": keep + planes, "texture_bytes": tex_bytes, "n_materials": n_materials,
+            "tex_res": tex_res}
+
+
+def surface_producer_pass(ctx, vq, torch, peak):
+    w, h = W4K, H4K
+    sc = surface_scene_gpu(ctx, vq, torch, w, h)
+    g = [torch.empty((h, w, 4), dtype=torch.float32, device="cuda") for _ in range(4)]
+    gb = vq.GBuffer(*(vq.image_of(t) for t in g))
+    ms = time_gpu(torch, lambda: ctx.gbuffer_from_materials(sc["inputs"], sc["table"], 0.3, gb), 10)
+    nbytes = w * h * (48 + 4 + 64)          # 3 float4 interpolant planes + SSAO in, 4 float4 G-buffer planes out
+    out = {"surface_producer_4k": {
+        "config": f"{sc['n_materials']} materials (separate maps / ORM / constants / tiled non-pow2), {sc['tex_res']}^2 RGBA8 "
+                  f"maps = {sc['texture_bytes'] / 1e6:.1f} MB (L2-resident side data), SSAO + emissive planes",
+        "ms": round(ms, 4), "Mpixels_per_s": round(w * h / ms / 1e3, 1), "algorithmic_bytes_per_px": 116,
+        "algorithmic_GBps": round(nbytes / ms / 1e6, 1), "hbm_frac": round(nbytes / ms / 1e6 / peak, 3)}}
+    tw = 4096
+    levels = vq.mip_level_count(tw, tw)
+    buf = torch.randint(0, 256, (vq.pyramid_texel_count(tw, tw, levels) * 4,), dtype=torch.uint8, device="cuda")
+    desc = vq.texture_of(buf, tw, tw, levels)
+    ms = time_gpu(torch, lambda: ctx.texture_build_mips(desc), 10)
+    nb = tw * tw * 4 * (4 / 3 + 1 / 3)      # every level read once (except the last), every level but 0 written once
+    out["texture_box_mips_4096"] = {"ms": round(ms, 4), "algorithmic_GBps": round(nb / ms / 1e6, 1),
+                                    "hbm_frac": round(nb / ms / 1e6 / peak, 3), "launches": (levels - 1 + 5) // 6}
+    sc["table"].close()
     return out
 
 

@@ -125,8 +125,30 @@ typedef struct VqSpdConstants {
     uint32_t workGroupOffset[2];
 } VqSpdConstants;
 
+/* reference: LightingConstantBufferData.h:126-143 (MaterialData, 80 B; textureConfig is the Has*Map bitfield
+ * of Material::GetTextureConfig (Material.cpp:23-36) converted to float, Material.h:126) */
+typedef struct VqMaterialData {
+    VqFloat3 diffuse;       float alpha;
+    VqFloat3 emissiveColor; float emissiveIntensity;
+    VqFloat3 specular;      float normalMapMipBias;
+    VqFloat4 uvScaleOffset;
+    float roughness, metalness, displacement, textureConfig;
+} VqMaterialData;
+
+/* reference: LightingConstantBufferData.h:116-124 (Has*Map bits) */
+#define VQ_TEXCFG_DIFFUSE    (1 << 0)
+#define VQ_TEXCFG_NORMAL     (1 << 1)
+#define VQ_TEXCFG_AO         (1 << 2)
+#define VQ_TEXCFG_ALPHA_MASK (1 << 3)
+#define VQ_TEXCFG_ROUGHNESS  (1 << 4)
+#define VQ_TEXCFG_METALLIC   (1 << 5)
+#define VQ_TEXCFG_HEIGHT     (1 << 6)
+#define VQ_TEXCFG_EMISSIVE   (1 << 7)
+#define VQ_TEXCFG_ORM        (1 << 8)
+
 #ifdef __cplusplus
 } /* extern "C" */
+static_assert(sizeof(VqMaterialData) == 80, "MaterialData layout");
 static_assert(sizeof(VqPointLight) == 48, "PointLight layout");
 static_assert(sizeof(VqSpotLight) == 64, "SpotLight layout");
 static_assert(sizeof(VqDirectionalLight) == 40, "DirectionalLight layout");

@@ -261,6 +261,57 @@ VQ_API uint64_t vq_pyramid_texel_count(int width, int height, int levels);
 VQ_API uint64_t vq_pyramid_offset(int width, int height, int level);   /* texel offset of a level */
 
 /* ------------------------------------------------------------------------------------------
+ * SURVEY §8(f).1  Surface producer: the part of PSMain BEFORE lighting (ForwardLighting.hlsl:226-283) —
+ *     material-texture sampling, sRGB->linear, normal mapping, Has*Map selection — turned into a kernel
+ *     that fills the G-buffer K1 consumes from what a rasteriser interpolates per covered pixel.
+ * ------------------------------------------------------------------------------------------ */
+
+/* Material texture: RGBA8 UNORM (what Image::LoadFromFile + TextureManager upload, 4 B/texel), with the CPU-built
+ * box-filter mip chain (TextureManager.cpp:714-727 -> DXGIUtils.cpp:250-287), tightly packed levels, level l is
+ * (width>>l) x (height>>l), levels <= vq_mip_level_count(); texel offsets as vq_pyramid_offset().
+ * ptr == NULL is the engine's null SRV (Renderer_Resources.cpp:383-387): every read returns 0. */
+typedef struct VqTexture2D {
+    void*   ptr;
+    int32_t width, height;
+    int32_t levels;
+} VqTexture2D;
+
+/* the descriptor table of one material, in the order PSMain samples them (ForwardLighting.hlsl:87-94,229-235; texAlphaMask t3 is bound but never sampled) */
+typedef struct VqMaterialTextures {
+    VqTexture2D diffuse, normals, emissive, metalness, roughness, occl_rough_metal, local_ao;
+} VqMaterialTextures;
+
+/* PSInput as a rasteriser would deliver it (ForwardLighting.hlsl:42-53), one record per pixel in three float4 planes:
+ *   position_u = { WorldSpacePosition.xyz, uv.x }
+ *   normal_v   = { WorldSpaceNormal.xyz  (interpolated, not normalised), uv.y }
+ *   tangent_m  = { WorldSpaceTangent.xyz (interpolated, not normalised), material index as an exact small float }
+ *   ssao       = optional R32F plane, the texScreenSpaceAO the shader point-samples (NULL -> 1) */
+typedef struct VqSurfaceInputs {
+    VqImage position_u, normal_v, tangent_m;
+    VqImage ssao;
+} VqSurfaceInputs;
+
+typedef struct VqMaterialTable VqMaterialTable;   /* device-resident copy of the scene's materials */
+
+/* RGBA8 mip chain, per-channel (a+b+c+d)/4 truncating: VQ_DXGI_UTILS::MipImage, 4-byte branch (DXGIUtils.cpp:250-287).
+ * Level 0 must be filled. Bit-exact. */
+VQ_API int vq_texture_build_mips(VqContext* ctx, VqTexture2D tex, void* stream);
+
+/* Uploads `count` materials (constants + texture descriptors, both HOST arrays; the texel pointers inside are DEVICE
+ * pointers that must outlive the table). Material::GetCBufferData + the SRV table built at AssetLoader.cpp:406-420. */
+VQ_API int vq_material_table_create(VqContext* ctx, const VqMaterialData* materials,
+                                    const VqMaterialTextures* textures, int count, VqMaterialTable** out_table);
+VQ_API int vq_material_table_destroy(VqContext* ctx, VqMaterialTable* table);
+
+/* Fills rows [row_begin,row_end) of the G-buffer (emissive plane optional). `ambient_factor` = PerFrameData
+ * fAmbientLightingFactor (ForwardLighting.hlsl:245). alpha_mask != 0 compiles in the ENABLE_ALPHA_MASK discard
+ * (ForwardLighting.hlsl:237-240): such pixels are left untouched in the G-buffer. Texture LOD comes from the 2x2-quad
+ * finite differences of uv, as the implicit-derivative Sample() of a pixel shader does. */
+VQ_API int vq_gbuffer_from_materials(VqContext* ctx, const VqSurfaceInputs* in, const VqMaterialTable* table,
+                                     float ambient_factor, int alpha_mask, const VqGBuffer* out,
+                                     int row_begin, int row_end, void* stream);
+
+/* ------------------------------------------------------------------------------------------
  * Blocking host-buffer entry points: the same passes called with HOST pointers (what an engine
  * integration that keeps its frame data in system memory would call). Each call uploads the
  * inputs, runs the kernel(s), downloads the result and returns when the result is in `out`.

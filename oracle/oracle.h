@@ -44,6 +44,25 @@ size_t cubemap_texel_count(int res, int mips);
 int    cubemap_row_count(int res, int mips);
 size_t pyramid_texel_count(int w, int h, int levels);
 
+// ---- §8(f).1 surface producer (oracle_surface.cpp) -----------------------------------------------
+struct Texture8 {         // RGBA8 UNORM, packed levels (width>>l) x (height>>l); data == nullptr -> null SRV (reads 0)
+    const uint8_t* data; int width, height, levels;
+    size_t offset(int level) const;           // in texels
+    int w(int l) const { return width >> l; }
+    int h(int l) const { return height >> l; }
+};
+struct MaterialTextures8 { Texture8 diffuse, normals, emissive, metalness, roughness, occl_rough_metal, local_ao; };
+struct SurfaceIn  { float3 WorldSpacePosition, WorldSpaceNormal, WorldSpaceTangent; float2 uv; };   // ForwardLighting.hlsl:42-53
+struct SurfaceOut { float3 P; float ao; float3 N; float roughness; float3 diffuseColor; float metalness;
+                    float3 emissiveColor; float emissiveIntensity; };
+void   MipImage_Box8(const uint8_t* src, uint8_t* dst, int width, int height);                       // DXGIUtils.cpp:263-287
+float  TextureLod(const Texture8& tex, float2 ddx, float2 ddy, float bias);
+float4 SampleTexture8(const Texture8& tex, float2 uv, float2 ddx, float2 ddy, float bias);
+float3 UnpackNormal(float3 SampledNormal, float3 worldNormal, float3 worldTangent);                  // ShadingMath.hlsl:44-52
+bool   Surface_PSMain(const SurfaceIn& In, float2 uv_ddx_raw, float2 uv_ddy_raw, const VqMaterialData& mat,
+                      const MaterialTextures8& tex, float fAmbientLightingFactor, float ssao, bool alphaMask,
+                      SurfaceOut* o);                                                                 // ForwardLighting.hlsl:226-283
+
 // ---- BRDF.hlsl ---------------------------------------------------------------------------------
 struct BRDF_Surface {     // BRDF.hlsl:50-58
     float3 N; float roughness; float3 diffuseColor; float metalness;

@@ -60,6 +60,69 @@ void orc_forward_lighting(const VqPerFrameData* pf, const VqPerViewLightingData*
     });
 }
 
+// ---- §8(f).1 surface producer -----------------------------------------------------------------
+void orc_texture_build_mips(uint8_t* tex, int w, int h, int levels) {
+    const Texture8 t{tex, w, h, levels};
+    for (int l = 1; l < levels; ++l)
+        MipImage_Box8(tex + 4 * t.offset(l - 1), tex + 4 * t.offset(l), w >> (l - 1), h >> (l - 1));
+}
+
+void orc_sample_texture8(const uint8_t* tex, int w, int h, int levels, float u, float v,
+                         float dudx, float dvdx, float dudy, float dvdy, float bias, float* out4, float* out_lod) {
+    const Texture8 t{tex, w, h, levels};
+    st(out4, SampleTexture8(t, make2(u, v), make2(dudx, dvdx), make2(dudy, dvdy), bias));
+    if (out_lod) *out_lod = tex ? TextureLod(t, make2(dudx, dvdx), make2(dudy, dvdy), bias) : 0.0f;
+}
+void orc_unpack_normal(const float* sampled, const float* n, const float* t, float* out3) {
+    const float3 r = UnpackNormal(make3(sampled[0], sampled[1], sampled[2]), make3(n[0], n[1], n[2]), make3(t[0], t[1], t[2]));
+    out3[0] = r.x; out3[1] = r.y; out3[2] = r.z;
+}
+
+// host-side mirror of VqTexture2D / VqMaterialTextures with HOST pointers
+struct OrcTexture2D { const uint8_t* ptr; int32_t width, height, levels; };
+struct OrcMaterialTextures { OrcTexture2D t[7]; };
+
+void orc_gbuffer_from_materials(const float* position_u, const float* normal_v, const float* tangent_m, const float* ssao,
+                                int width, int height, const VqMaterialData* materials, const OrcMaterialTextures* textures,
+                                int n_materials, float ambient_factor, int alpha_mask,
+                                float* position_ao, float* normal_roughness, float* albedo_metalness, float* emissive,
+                                int row_begin, int row_end, int threads) {
+    auto tex8 = [](const OrcTexture2D& t) { return Texture8{t.ptr, t.width, t.height, t.levels}; };
+    auto rawuv = [&](int x, int y) {
+        const size_t o = ((size_t)y * width + x) * 4;
+        return make2(position_u[o + 3], normal_v[o + 3]);
+    };
+    par_rows(row_end - row_begin, threads, [&](int r) {
+        const int y = row_begin + r;
+        for (int x = 0; x < width; ++x) {
+            const size_t o = ((size_t)y * width + x) * 4;
+            SurfaceIn in;
+            in.WorldSpacePosition = make3(position_u[o], position_u[o + 1], position_u[o + 2]);
+            in.WorldSpaceNormal = make3(normal_v[o], normal_v[o + 1], normal_v[o + 2]);
+            in.WorldSpaceTangent = make3(tangent_m[o], tangent_m[o + 1], tangent_m[o + 2]);
+            in.uv = rawuv(x, y);
+            int mi = (int)tangent_m[o + 3];
+            mi = mi < 0 ? 0 : (mi >= n_materials ? n_materials - 1 : mi);
+            // fine derivatives inside the aligned 2x2 quad, partner clamped to the image
+            const int qx = x & ~1, qy = y & ~1;
+            const int qx1 = qx + 1 < width ? qx + 1 : qx, qy1 = qy + 1 < height ? qy + 1 : qy;
+            const float2 a = rawuv(qx, y), b = rawuv(qx1, y), c = rawuv(x, qy), d = rawuv(x, qy1);
+            const float2 ddx = make2(b.x - a.x, b.y - a.y), ddy = make2(d.x - c.x, d.y - c.y);
+            const OrcMaterialTextures& mt = textures[mi];
+            const MaterialTextures8 t8{tex8(mt.t[0]), tex8(mt.t[1]), tex8(mt.t[2]), tex8(mt.t[3]), tex8(mt.t[4]),
+                                       tex8(mt.t[5]), tex8(mt.t[6])};
+            float ao_ss = 1.0f;
+            if (ssao) ao_ss = ssao[(size_t)((y + 1) % height) * width + (x + 1) % width];
+            SurfaceOut so;
+            if (!Surface_PSMain(in, ddx, ddy, materials[mi], t8, ambient_factor, ao_ss, alpha_mask != 0, &so)) continue;
+            st(position_ao + o, make4(so.P, so.ao));
+            st(normal_roughness + o, make4(so.N, so.roughness));
+            st(albedo_metalness + o, make4(so.diffuseColor, so.metalness));
+            if (emissive) st(emissive + o, make4(so.emissiveColor, so.emissiveIntensity));
+        }
+    });
+}
+
 // ---- K11 --------------------------------------------------------------------------------------
 void orc_hdri_build_mips(float* pyramid, int w, int h, int levels) {
     Pyramid p{pyramid, w, h, levels};

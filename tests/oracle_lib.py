@@ -191,3 +191,67 @@ def spd_setup(rect, mips=-1, which="oracle"):
     fn = lib().orc_spd_setup if which == "oracle" else ref().ref_spd_setup
     fn(d, o, n, r, mips)
     return list(d), list(o), list(n)
+
+
+# ---- SURVEY §8(f).1 surface producer ---------------------------------------------------------------
+class _OrcTexture2D(C.Structure):
+    _fields_ = [("ptr", C.c_void_p), ("width", C.c_int32), ("height", C.c_int32), ("levels", C.c_int32)]
+
+
+class _OrcMaterialTextures(C.Structure):
+    _fields_ = [("t", _OrcTexture2D * 7)]
+
+
+def texture_mip_chain(level0: np.ndarray, levels: int = None) -> np.ndarray:
+    """[H,W,4] uint8 -> packed RGBA8 mip chain (flat uint8), DXGIUtils.cpp:263-287 box filter"""
+    h, w = level0.shape[:2]
+    import vqengine_b200 as vq
+    levels = vq.mip_level_count(w, h) if levels is None else levels
+    n = vq.pyramid_texel_count(w, h, levels)
+    buf = np.zeros(n * 4, np.uint8)
+    buf[: w * h * 4] = np.ascontiguousarray(level0).reshape(-1)
+    lib().orc_texture_build_mips(buf.ctypes.data_as(C.c_void_p), w, h, levels)
+    return buf
+
+
+def gbuffer_from_materials(planes, materials, chains, ambient_factor: float, alpha_mask: bool = False, emissive: bool = True,
+                           init=None, row_begin=0, row_end=None, threads=None):
+    """planes = [position_u, normal_v, tangent_m(, ssao)]; chains = list of dict slot -> (packed uint8 chain, w, h, levels) or None.
+    Returns [position_ao, normal_roughness, albedo_metalness(, emissive)]; `init` pre-fills the outputs (alpha-mask discard)."""
+    import vqengine_b200 as vq
+    h, w = planes[0].shape[:2]
+    n = len(materials)
+    mats = (vq.MaterialData * n)(*materials)
+    tex = (_OrcMaterialTextures * n)()
+    for i, d in enumerate(chains):
+        for k, slot in enumerate(vq.MATERIAL_TEXTURE_SLOTS):
+            e = d.get(slot)
+            if e is not None:
+                buf, tw, th, tl = e
+                tex[i].t[k] = _OrcTexture2D(buf.ctypes.data, tw, th, tl)
+    outs = [np.zeros((h, w, 4), np.float32) if init is None else np.array(init[i], np.float32, copy=True)
+            for i in range(4 if emissive else 3)]
+    ssao = planes[3] if len(planes) > 3 and planes[3] is not None else None
+    fp = lambda a: a.ctypes.data_as(C.c_void_p) if a is not None else None
+    p0, p1, p2 = _f(planes[0]), _f(planes[1]), _f(planes[2])
+    ssao = _f(ssao) if ssao is not None else None
+    lib().orc_gbuffer_from_materials(fp(p0), fp(p1), fp(p2), fp(ssao), w, h,
+                                     mats, tex, n, C.c_float(ambient_factor), 1 if alpha_mask else 0,
+                                     fp(outs[0]), fp(outs[1]), fp(outs[2]), fp(outs[3]) if emissive else None,
+                                     row_begin, h if row_end is None else row_end, threads or cpu_threads())
+    return outs
+
+
+def sample_texture8(chain, w, h, levels, u, v, ddx=(0.0, 0.0), ddy=(0.0, 0.0), bias=0.0):
+    out = np.zeros(4, np.float32)
+    lod = C.c_float(0)
+    ptr = chain.ctypes.data_as(C.c_void_p) if chain is not None else None
+    lib().orc_sample_texture8(ptr, w, h, levels, f32(u), f32(v), f32(ddx[0]), f32(ddx[1]), f32(ddy[0]), f32(ddy[1]),
+                              f32(bias), _p(out), C.byref(lod))
+    return out, lod.value
+
+
+def unpack_normal(sampled, n, t):
+    out = np.zeros(3, np.float32)
+    lib().orc_unpack_normal(_p(_f(sampled)), _p(_f(n)), _p(_f(t)), _p(out))
+    return out

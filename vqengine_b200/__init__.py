@@ -130,6 +130,31 @@ class EnvironmentMaps(C.Structure):
     _fields_ = [("irradiance_diffuse", Cubemap), ("irradiance_specular", Cubemap), ("brdf_lut", Image)]
 
 
+class MaterialData(C.Structure):          # include/vq_shader_data.h VqMaterialData (LightingConstantBufferData.h:126-143)
+    _fields_ = [("diffuse", Float3), ("alpha", f32), ("emissiveColor", Float3), ("emissiveIntensity", f32),
+                ("specular", Float3), ("normalMapMipBias", f32), ("uvScaleOffset", Float4),
+                ("roughness", f32), ("metalness", f32), ("displacement", f32), ("textureConfig", f32)]
+
+
+assert C.sizeof(MaterialData) == 80
+
+TEXCFG_DIFFUSE, TEXCFG_NORMAL, TEXCFG_AO, TEXCFG_ALPHA_MASK, TEXCFG_ROUGHNESS, TEXCFG_METALLIC, TEXCFG_HEIGHT, \
+    TEXCFG_EMISSIVE, TEXCFG_ORM = (1 << b for b in range(9))
+MATERIAL_TEXTURE_SLOTS = ("diffuse", "normals", "emissive", "metalness", "roughness", "occl_rough_metal", "local_ao")
+
+
+class Texture2D(C.Structure):
+    _fields_ = [("ptr", C.c_void_p), ("width", i32), ("height", i32), ("levels", i32)]
+
+
+class MaterialTextures(C.Structure):
+    _fields_ = [(k, Texture2D) for k in MATERIAL_TEXTURE_SLOTS]
+
+
+class SurfaceInputs(C.Structure):
+    _fields_ = [("position_u", Image), ("normal_v", Image), ("tangent_m", Image), ("ssao", Image)]
+
+
 # every symbol include/vqcuda.h declares (tests/test_abi.py checks the library exports all of them)
 ABI_SYMBOLS = [
     "vq_ctx_create", "vq_ctx_destroy", "vq_ctx_resize", "vq_last_error", "vq_version", "vq_launch_count",
@@ -139,6 +164,7 @@ ABI_SYMBOLS = [
     "vq_spd_setup", "vq_mip_level_count", "vq_cubemap_texel_count", "vq_cubemap_offset", "vq_cubemap_row_count",
     "vq_pyramid_texel_count", "vq_pyramid_offset", "vq_forward_lighting_host", "vq_environment_prepare",
     "vq_environment_invalidate", "vq_forward_lighting_multi",
+    "vq_texture_build_mips", "vq_material_table_create", "vq_material_table_destroy", "vq_gbuffer_from_materials",
 ]
 
 
@@ -199,6 +225,10 @@ def _load() -> C.CDLL:
     lib.vq_pyramid_texel_count.restype = C.c_uint64
     lib.vq_pyramid_offset.argtypes = [C.c_int, C.c_int, C.c_int]
     lib.vq_pyramid_offset.restype = C.c_uint64
+    lib.vq_texture_build_mips.argtypes = [vp, Texture2D, vp]
+    lib.vq_material_table_create.argtypes = [vp, P(MaterialData), P(MaterialTextures), C.c_int, P(vp)]
+    lib.vq_material_table_destroy.argtypes = [vp, vp]
+    lib.vq_gbuffer_from_materials.argtypes = [vp, P(SurfaceInputs), vp, f32, C.c_int, P(GBuffer), C.c_int, C.c_int, vp]
     return lib
 
 
@@ -283,6 +313,14 @@ def pyramid_of(t, w: int, h: int, levels: int) -> Pyramid:
     return Pyramid(t.data_ptr(), w, h, levels)
 
 
+def texture_of(t, w: int, h: int, levels: int) -> Texture2D:
+    """uint8 tensor holding the packed RGBA8 mip chain of a w x h texture; None -> null SRV"""
+    if t is None:
+        return Texture2D(None, 0, 0, 0)
+    assert t.is_contiguous() and t.element_size() == 1 and t.numel() == pyramid_texel_count(w, h, levels) * 4
+    return Texture2D(t.data_ptr(), w, h, levels)
+
+
 def _stream_ptr(stream) -> C.c_void_p:
     if stream is None:
         import torch
@@ -338,6 +376,20 @@ class Context:
     def environment_invalidate(self):
         _check(lib.vq_environment_invalidate(self._h))
 
+    # material textures -> G-buffer
+    def texture_build_mips(self, tex: Texture2D, stream=None):
+        _check(lib.vq_texture_build_mips(self._h, tex, _stream_ptr(stream)))
+
+    def material_table(self, materials, textures) -> "MaterialTable":
+        return MaterialTable(self, materials, textures)
+
+    def gbuffer_from_materials(self, inputs: SurfaceInputs, table: "MaterialTable", ambient_factor: float, gbuffer: GBuffer,
+                               alpha_mask: bool = False, row_begin=0, row_end=None, stream=None):
+        h = inputs.position_u.height
+        _check(lib.vq_gbuffer_from_materials(self._h, C.byref(inputs), table._h, ambient_factor, 1 if alpha_mask else 0,
+                                             C.byref(gbuffer), row_begin, h if row_end is None else row_end,
+                                             _stream_ptr(stream)))
+
     # K11 / K2 / K3 / K4
     def hdri_build_mips(self, pyr: Pyramid, stream=None):
         _check(lib.vq_hdri_build_mips(self._h, pyr, _stream_ptr(stream)))
@@ -379,6 +431,30 @@ class Context:
     def spd_downsample(self, constants: SpdConstants, src, mips, stream=None):
         arr = (Image * len(mips))(*[image_of(m) for m in mips])
         _check(lib.vq_spd_downsample(self._h, C.byref(constants), image_of(src), arr, _stream_ptr(stream)))
+
+
+class MaterialTable:
+    """device-resident materials (vq_material_table_create); keeps the texel tensors' descriptors alive by reference"""
+
+    def __init__(self, ctx: Context, materials, textures):
+        n = len(materials)
+        assert n == len(textures) and n >= 1
+        self._ctx = ctx
+        self._mats = (MaterialData * n)(*materials)
+        self._tex = (MaterialTextures * n)(*textures)
+        self._h = C.c_void_p()
+        _check(lib.vq_material_table_create(ctx._h, self._mats, self._tex, n, C.byref(self._h)))
+
+    def close(self):
+        if self._h:
+            lib.vq_material_table_destroy(self._ctx._h, self._h)
+            self._h = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
 
 
 def launch_count() -> int:

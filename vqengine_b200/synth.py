@@ -165,3 +165,127 @@ def hdr_image(width: int, height: int, seed: int = SEED_BASE + 4, max_value: flo
 def default_tonemapper() -> TonemapperParams:
     """PostProcess.h:84-91 defaults: REC_709 content, sRGB curve, 200 nits, gamma on."""
     return TonemapperParams(COLOR_SPACE_REC_709, DISPLAY_CURVE_SRGB, 200.0, 1, 1.0)
+
+
+# ---- SURVEY §8(f).1: material textures + rasteriser interpolants ---------------------------------
+def _value_noise(rng, res_w: int, res_h: int, cells: int, channels: int) -> np.ndarray:
+    """smooth tileable value noise in [0,1], [res_h,res_w,channels] (bilinear upsample of a cells x cells lattice)"""
+    lat = rng.uniform(0.0, 1.0, (cells, cells, channels)).astype(np.float32)
+    ys = (np.arange(res_h, dtype=np.float32) + 0.5) * cells / res_h
+    xs = (np.arange(res_w, dtype=np.float32) + 0.5) * cells / res_w
+    y0, x0 = np.floor(ys).astype(int), np.floor(xs).astype(int)
+    fy, fx = (ys - y0)[:, None, None], (xs - x0)[None, :, None]
+    y1, x1 = (y0 + 1) % cells, (x0 + 1) % cells
+    y0 %= cells; x0 %= cells
+    top = lat[y0][:, x0] * (1 - fx) + lat[y0][:, x1] * fx
+    bot = lat[y1][:, x0] * (1 - fx) + lat[y1][:, x1] * fx
+    return top * (1 - fy) + bot * fy
+
+
+def material_texture(kind: str, width: int, height: int, seed: int) -> np.ndarray:
+    """level 0 of a synthetic RGBA8 material map, [H,W,4] uint8. kinds: albedo (alpha has cut-outs), normal (tangent-space,
+    z-dominant), emissive (sparse), scalar (R = smooth noise + grain), orm"""
+    rng = np.random.default_rng(seed)
+    grain = rng.uniform(-0.06, 0.06, (height, width, 4)).astype(np.float32)
+    if kind == "albedo":
+        img = np.empty((height, width, 4), np.float32)
+        img[..., :3] = 0.15 + 0.8 * _value_noise(rng, width, height, 8, 3)
+        img[..., 3] = np.where(_value_noise(rng, width, height, 6, 1)[..., 0] < 0.28, 0.0, 1.0)
+        img[..., :3] += grain[..., :3]
+    elif kind == "normal":
+        bump = _value_noise(rng, width, height, 16, 2) - 0.5
+        n = np.stack([bump[..., 0] * 1.2, bump[..., 1] * 1.2, np.ones((height, width), np.float32)], -1)
+        n /= np.sqrt((n * n).sum(-1, keepdims=True))
+        img = np.concatenate([n * 0.5 + 0.5, np.ones((height, width, 1), np.float32)], -1)
+    elif kind == "emissive":
+        img = np.zeros((height, width, 4), np.float32)
+        mask = _value_noise(rng, width, height, 10, 1)[..., 0] > 0.7
+        img[..., :3] = np.where(mask[..., None], 0.3 + 0.7 * _value_noise(rng, width, height, 4, 3), 0.0)
+        img[..., 3] = 1.0
+    elif kind in ("scalar", "orm"):
+        img = 0.1 + 0.85 * _value_noise(rng, width, height, 12, 4) + grain
+    else:
+        raise ValueError(kind)
+    return np.ascontiguousarray(np.clip(np.rint(img * 255.0), 0, 255).astype(np.uint8))
+
+
+def materials(n: int = 4, tex_res: int = 256, seed: int = SEED_BASE + 11, uniform: bool = False):
+    """n materials cycling through the texture configurations the engine's material sets use (Data/Materials/*.xml):
+    0 fully textured (separate roughness/metal/AO maps, emissive), 1 glTF style (albedo+normal+ORM),
+    2 constants only (all SRVs null), 3 albedo+normal with uv tiling and a non-square, non-pow2 albedo.
+    uniform=True gives every map of material 0 the same tex_res^2 size (how shipped material sets look); the default mixes
+    sizes and aspect ratios to exercise the sampler. Returns (list[MaterialData], list[dict slot -> level-0 uint8 array or None])."""
+    from . import MaterialData, TEXCFG_DIFFUSE, TEXCFG_NORMAL, TEXCFG_AO, TEXCFG_ROUGHNESS, TEXCFG_METALLIC, \
+        TEXCFG_EMISSIVE, TEXCFG_ORM, MATERIAL_TEXTURE_SLOTS
+    rng = np.random.default_rng(seed)
+    mats, texs = [], []
+    for i in range(n):
+        m = MaterialData()
+        C.memset(C.byref(m), 0, C.sizeof(m))
+        m.diffuse.x, m.diffuse.y, m.diffuse.z = rng.uniform(0.5, 1.0, 3)
+        m.alpha = 1.0
+        m.emissiveColor.x, m.emissiveColor.y, m.emissiveColor.z = rng.uniform(0.2, 1.0, 3)
+        m.specular.x = m.specular.y = m.specular.z = 1.0
+        m.uvScaleOffset.x, m.uvScaleOffset.y, m.uvScaleOffset.z, m.uvScaleOffset.w = 1.0, 1.0, 0.0, 0.0
+        m.roughness, m.metalness = rng.uniform(0.3, 1.0), rng.uniform(0.0, 1.0)
+        t = {k: None for k in MATERIAL_TEXTURE_SLOTS}
+        s = seed * 131 + i * 17
+        kind = i % 4
+        if kind == 0:
+            t["diffuse"] = material_texture("albedo", tex_res, tex_res, s + 1)
+            t["normals"] = material_texture("normal", tex_res, tex_res, s + 2)
+            hr = tex_res if uniform else tex_res // 2
+            t["emissive"] = material_texture("emissive", hr, hr, s + 3)
+            t["metalness"] = material_texture("scalar", hr, hr, s + 4)
+            t["roughness"] = material_texture("scalar", tex_res, hr, s + 5)
+            t["local_ao"] = material_texture("scalar", hr, tex_res, s + 6)
+            cfg = TEXCFG_DIFFUSE | TEXCFG_NORMAL | TEXCFG_EMISSIVE | TEXCFG_METALLIC | TEXCFG_ROUGHNESS | TEXCFG_AO
+            m.emissiveIntensity = 2.5
+            m.normalMapMipBias = 0.0 if uniform else -0.5
+        elif kind == 1:
+            t["diffuse"] = material_texture("albedo", tex_res, tex_res, s + 1)
+            t["normals"] = material_texture("normal", tex_res, tex_res, s + 2)
+            t["occl_rough_metal"] = material_texture("orm", tex_res, tex_res, s + 3)
+            cfg = TEXCFG_DIFFUSE | TEXCFG_NORMAL | TEXCFG_ORM
+            m.uvScaleOffset.x, m.uvScaleOffset.y, m.uvScaleOffset.z, m.uvScaleOffset.w = 3.0, 2.0, 0.25, 0.4
+        elif kind == 2:
+            cfg = 0
+            m.emissiveIntensity = 0.4
+        else:
+            w3 = max(12, (tex_res * 3) // 4 - 4)            # neither square nor a power of two
+            t["diffuse"] = material_texture("albedo", w3, tex_res // 2 + 6, s + 1)
+            t["normals"] = material_texture("normal", tex_res, tex_res, s + 2)
+            cfg = TEXCFG_DIFFUSE | TEXCFG_NORMAL
+            m.uvScaleOffset.x, m.uvScaleOffset.y, m.uvScaleOffset.z, m.uvScaleOffset.w = 7.5, 7.5, -0.3, 0.1
+            m.normalMapMipBias = 0.75
+        m.textureConfig = float(cfg)
+        mats.append(m)
+        texs.append(t)
+    return mats, texs
+
+
+def surface_inputs(width: int, height: int, n_materials: int, seed: int = SEED_BASE + 12, ssao: bool = True,
+                   uv_scale: float = 0.1):
+    """PSInput planes of a height field seen from above: position_u, normal_v, tangent_m [H,W,4] (+ssao [H,W,1]).
+    uv = world xz * uv_scale (so texel footprints grow with the pixel pitch: every mip level is exercised between 96x54 and 4K),
+    materials in 64-pixel screen blocks with ragged borders, interpolated (non-unit) normals/tangents."""
+    rng = np.random.default_rng(seed)
+    g = gbuffer(width, height, seed)
+    P, N = g[0][..., :3], g[1][..., :3]
+    pos_u = np.empty((height, width, 4), np.float32)
+    nrm_v = np.empty((height, width, 4), np.float32)
+    tan_m = np.empty((height, width, 4), np.float32)
+    pos_u[..., :3] = P
+    pos_u[..., 3] = P[..., 0] * np.float32(uv_scale)
+    nrm_v[..., :3] = N * rng.uniform(0.6, 1.0, (height, width, 1)).astype(np.float32)
+    nrm_v[..., 3] = P[..., 2] * np.float32(uv_scale)
+    T = np.stack([np.ones((height, width), np.float32), 0.3 * N[..., 0], 0.1 * np.ones((height, width), np.float32)], -1)
+    tan_m[..., :3] = T * rng.uniform(0.7, 1.3, (height, width, 1)).astype(np.float32)
+    by, bx = np.meshgrid(np.arange(height) // 64, np.arange(width) // 64, indexing="ij")
+    jitter = rng.integers(0, 40, (height, width)) == 0
+    mid = (by * 3 + bx + jitter) % n_materials
+    tan_m[..., 3] = mid.astype(np.float32)
+    planes = [np.ascontiguousarray(pos_u), np.ascontiguousarray(nrm_v), np.ascontiguousarray(tan_m)]
+    if ssao:
+        planes.append(np.ascontiguousarray(rng.uniform(0.2, 1.0, (height, width, 1)).astype(np.float32)))
+    return planes
