@@ -22,6 +22,8 @@ import sys
 import threading
 import time
 
+import numpy as np
+
 ROOT = os.path.dirname(os.path.abspath(__file__))
 for _p in (ROOT, os.path.join(ROOT, "tests")):
     if _p not in sys.path:
@@ -201,6 +203,47 @@ def extra_passes(ctx, vq, torch, envk, peak):
     nb = envk["hdri_w"] * envk["hdri_h"] * (16 * 4 / 3 + 16 / 3)
     out["hdri_min_pyramid"] = {"ms": round(ms, 4), "algorithmic_GBps": round(nb / ms / 1e6, 1)}
     out.update(surface_producer_pass(ctx, vq, torch, peak))
+    out.update(frame_format_passes(ctx, vq, torch, envk, peak))
+    return out
+
+
+def frame_format_passes(ctx, vq, torch, envk, peak):
+    """.hdr decode / encode at BASELINE config 5's HDRI size, skydome + ApplyReflections at 4K"""
+    import time
+    from vqengine_b200 import synth
+    out = {}
+    hw, hh = 4096, 2048
+    src = torch.from_numpy(synth.hdri(hw, hh)).cuda()
+    t0 = time.perf_counter(); data = ctx.hdr_save_host(src); t_save = time.perf_counter() - t0
+    info, offs = vq.hdr_parse(data)
+    n = len(data)
+    dfile = torch.zeros(((n + 15) // 16 * 16 + 16,), dtype=torch.uint8, device="cuda")
+    dfile[:n] = torch.frombuffer(bytearray(data), dtype=torch.uint8).cuda()
+    doffs = torch.from_numpy(offs.view(np.int64)).cuda()
+    img = torch.empty((hh, hw, 4), dtype=torch.float32, device="cuda")
+    lum = torch.zeros((1,), dtype=torch.float32, device="cuda")
+    ms = time_gpu(torch, lambda: vq._check(vq.lib.vq_hdr_decode(ctx._h, dfile.data_ptr(), n, C.byref(info), doffs.data_ptr(),
+                                                                vq.image_of(img), lum.data_ptr(), vq._stream_ptr(None))), 10)
+    nb = n + hw * hh * 16
+    out["hdr_decode_4096x2048"] = {"config": f".hdr file {n / 1e6:.1f} MB (RLE, {n / hw / hh:.2f} B/texel) -> RGBA32F + max luminance, bit-exact vs stbi_loadf",
+                                   "ms": round(ms, 4), "Mtexels_per_s": round(hw * hh / ms / 1e3, 1),
+                                   "algorithmic_GBps": round(nb / ms / 1e6, 1), "hbm_frac": round(nb / ms / 1e6 / peak, 3)}
+    t0 = time.perf_counter(); ctx.hdr_load_host(data, img); t_load = time.perf_counter() - t0
+    out["hdr_decode_4096x2048"]["e2e_host_file_to_device_image_ms"] = round(t_load * 1e3, 2)
+    ms = time_gpu(torch, lambda: ctx.hdr_encode_rgbe(src), 10)
+    nb = hw * hh * 20
+    out["hdr_encode_rgbe_4096x2048"] = {"ms": round(ms, 4), "algorithmic_GBps": round(nb / ms / 1e6, 1), "hbm_frac": round(nb / ms / 1e6 / peak, 3),
+                                        "e2e_device_image_to_host_file_ms": round(t_save * 1e3, 2)}
+    w, h = W4K, H4K
+    _, inv = synth.sky_view_proj(0.7, 0.1, 1.0, w / h)
+    scene = torch.zeros((h, w, 4), dtype=torch.float32, device="cuda")
+    ms = time_gpu(torch, lambda: ctx.skydome(inv.astype(np.float32).reshape(16), envk["pyr"], scene), 10)
+    out["skydome_4k"] = {"config": "every pixel background (no mask), 2048x1024 HDRI level 0", "ms": round(ms, 4),
+                         "algorithmic_GBps": round(w * h * 16 / ms / 1e6, 1), "hbm_frac": round(w * h * 16 / ms / 1e6 / peak, 3)}
+    refl = torch.rand((h, w, 4), dtype=torch.float32, device="cuda")
+    ms = time_gpu(torch, lambda: ctx.apply_reflections(scene, refl), 10)
+    out["apply_reflections_4k"] = {"ms": round(ms, 4), "algorithmic_GBps": round(w * h * 48 / ms / 1e6, 1),
+                                   "hbm_frac": round(w * h * 48 / ms / 1e6 / peak, 3)}
     return out
 
 

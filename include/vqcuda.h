@@ -312,6 +312,56 @@ VQ_API int vq_gbuffer_from_materials(VqContext* ctx, const VqSurfaceInputs* in, 
                                      int row_begin, int row_end, void* stream);
 
 /* ------------------------------------------------------------------------------------------
+ * SURVEY §8(f).2  On-disk format at either end of the path: Radiance .hdr (RGBE).
+ *     Load  = Image::LoadFromFile -> stbi_loadf(path, &x, &y, &n, 4) (Libs/VQUtils/Source/Image.cpp:119-121) with
+ *             Image::CalculateMaxLuminance (Image.cpp:43-86) fused into the same pass; results are bit-identical to stb's.
+ *     Save  = Image::SaveToDisk -> stbi_write_hdr(path, x, y, 4, data) (Image.cpp:210-213); files are byte-identical.
+ *     The byte-serial work (header text, locating / emitting run lists) is host code; the per-texel work is kernels,
+ *     so host<->device traffic is the file image (<= ~4 B/texel), not the fp32 image (16 B/texel).
+ * ------------------------------------------------------------------------------------------ */
+typedef struct VqHdrInfo {
+    int32_t  width, height;
+    uint64_t data_offset;   /* first byte after the resolution line (or where flat data starts) */
+    int32_t  flat;          /* 1: 4 bytes per texel from data_offset on, no run-length encoding */
+    int32_t  reserved;
+} VqHdrInfo;
+/* HOST. Parses the header of a .hdr file image. channel_offsets == NULL: header only (dims for allocation).
+ * Otherwise (run-length encoded files: info->flat == 0 after the first call) it must hold 4*height+1 entries and
+ * receives the file offset of every scanline's R,G,B,E run list (+ the end offset); the run headers are validated
+ * (stb's "corrupt HDR" conditions -> VQ_ERR_INVALID_ARG; a stream that ends inside a scanline is an error, where stb
+ * would spin on zero bytes). A file whose scanlines turn out not to be run-length encoded flips info->flat to 1. */
+VQ_API int vq_hdr_parse(const void* file, uint64_t size, VqHdrInfo* info, uint64_t* channel_offsets);
+/* DEVICE. Expands the file image into `out` (width x height RGBA32F, alpha 1). dev_file: 16-byte aligned, allocation
+ * padded to a multiple of 16 bytes. dev_channel_offsets: device copy of the index (NULL for flat files).
+ * dev_max_luminance (optional): receives max over texels of 0.2126 r + 0.7152 g + 0.0722 b (Image::MaxLuminance). */
+VQ_API int vq_hdr_decode(VqContext* ctx, const void* dev_file, uint64_t size, const VqHdrInfo* info,
+                         const uint64_t* dev_channel_offsets, VqImage out, float* dev_max_luminance, void* stream);
+/* Blocking: host file image -> device fp32 image (parse + upload + decode). */
+VQ_API int vq_hdr_load_host(VqContext* ctx, const void* host_file, uint64_t size, VqImage out, float* max_luminance);
+/* DEVICE. RGBA32F -> RGBE texels (4 bytes each, tightly packed rows), stbiw__linear_to_rgbe. Inputs are radiance (>= 0). */
+VQ_API int vq_hdr_encode_rgbe(VqContext* ctx, VqImage in, void* dev_rgbe, void* stream);
+/* HOST. RGBE texels -> the .hdr file image (text header + per-scanline run lists). file == NULL: size query. */
+VQ_API int vq_hdr_pack_file(const void* host_rgbe, int width, int height, void* file, uint64_t capacity, uint64_t* size);
+/* Blocking: device fp32 image -> host file image (encode + download + pack). */
+VQ_API int vq_hdr_save_host(VqContext* ctx, VqImage in, void* host_file, uint64_t capacity, uint64_t* size);
+
+/* ------------------------------------------------------------------------------------------
+ * SURVEY §8(f).3  The two streaming passes that complete a headless frame.
+ *   Skydome: replaces the environment-map draw at SceneRendering.cpp:1821-1850 + PSMain (Skydome.hlsl:35-56).
+ *     inv_view_proj = inverse of the matViewProj the engine uploads (SceneView.EnvironmentMapViewProj = skyCam.View *
+ *     skyCam.Proj, Scene.cpp:573-584; row-vector convention), computed by the caller. The pass writes {rgb, 1} to
+ *     rows [row_begin,row_end) of scene_color where no surface was shaded: pixels whose normal_mask texel has
+ *     xyz == 0 (the G-buffer normal plane; the engine gets the same effect from the depth test), or every pixel when
+ *     normal_mask is NULL.
+ *   ApplyReflections: replaces CSMain (ApplyReflections.hlsl:31-57): scene.rgb += reflection.rgb, alpha kept;
+ *     with a bounding_volumes layer (COMPOSITE_BOUNDING_VOLUMES) the sum is blended under it. In place.
+ * ------------------------------------------------------------------------------------------ */
+VQ_API int vq_skydome(VqContext* ctx, const VqMatrix* inv_view_proj, VqPyramid hdri, const VqImage* normal_mask,
+                      VqImage scene_color, int row_begin, int row_end, void* stream);
+VQ_API int vq_apply_reflections(VqContext* ctx, VqImage scene_color, VqImage reflection_radiance,
+                                const VqImage* bounding_volumes, void* stream);
+
+/* ------------------------------------------------------------------------------------------
  * Blocking host-buffer entry points: the same passes called with HOST pointers (what an engine
  * integration that keeps its frame data in system memory would call). Each call uploads the
  * inputs, runs the kernel(s), downloads the result and returns when the result is in `out`.

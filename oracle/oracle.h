@@ -153,6 +153,16 @@ float3 FsrRcasF(const Image& in, int x, int y, const uint32_t con[4]);          
 // SPD: dst level L+1 from level L with the reduction order of the LDS path (SURVEY.md §9 "SPD")
 void   SpdDownsampleLevel(const Image& src, const MutImage& dst, int dstLevel /*1-based*/);
 
+// ---- §8(f).2/(f).3 on-disk formats and frame composition (oracle_frame.cpp) -------------------------
+float4 HdrConvert(const uint8_t rgbe[4]);                                            // stb_image.h stbi__hdr_convert, req_comp 4
+int    HdrDecode(const uint8_t* file, size_t n, int* w, int* h, std::vector<float>* rgba);   // stbi__hdr_load (Image.cpp:119-121)
+float  CalculateMaxLuminance(const float* rgba, int width, int height);              // Image.cpp:43-86
+void   LinearToRgbe(uint8_t rgbe[4], const float linear[3]);                         // stb_image_write.h stbiw__linear_to_rgbe
+void   HdrEncode(const float* rgba, int width, int height, std::vector<uint8_t>* file);      // stbi_write_hdr_core (Image.cpp:210-213)
+float4 Skydome_PSMain(const Pyramid& texEquirectEnvironmentMap, const VqMatrix& invViewProj,
+                      int px, int py, int width, int height);                        // Skydome.hlsl:35-56
+float4 ApplyReflections_CSMain(float4 SceneRadianceAndRoughness, float4 ReflectionRadiance, const float4* bv); // ApplyReflections.hlsl:31-57
+
 // run f(row) for rows [0,n) on `threads` std::threads (contiguous row blocks)
 void   ParallelRows(int n, int threads, void (*f)(int row, void* user), void* user);
 

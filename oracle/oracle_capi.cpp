@@ -317,4 +317,49 @@ float orc_aprx(int which, float a) {
     switch (which) { case 0: return APrxLoSqrtF1(a); case 1: return APrxLoRcpF1(a); case 2: return APrxMedRcpF1(a); default: return APrxLoRsqF1(a); }
 }
 
+
+// ---- §8(f).2 Radiance .hdr codec, §8(f).3 skydome / ApplyReflections -----------------------------------------
+// decode: call with rgba == nullptr to get the size, then again with a buffer of w*h*4 floats. Returns the stb error class.
+int orc_hdr_decode(const uint8_t* file, uint64_t n, int* w, int* h, float* rgba, float* max_luminance) {
+    std::vector<float> px;
+    const int rc = HdrDecode(file, (size_t)n, w, h, &px);
+    if (rc) return rc;
+    if (rgba) std::memcpy(rgba, px.data(), px.size() * sizeof(float));
+    if (max_luminance) *max_luminance = CalculateMaxLuminance(px.data(), *w, *h);
+    return 0;
+}
+// encode: returns the file size; writes at most `capacity` bytes
+uint64_t orc_hdr_encode(const float* rgba, int w, int h, uint8_t* file, uint64_t capacity) {
+    std::vector<uint8_t> f;
+    HdrEncode(rgba, w, h, &f);
+    if (file) std::memcpy(file, f.data(), std::min<uint64_t>(capacity, f.size()));
+    return f.size();
+}
+void orc_linear_to_rgbe(const float* rgba, int n, uint8_t* rgbe) {
+    for (int i = 0; i < n; ++i) LinearToRgbe(rgbe + 4 * (size_t)i, rgba + 4 * (size_t)i);
+}
+void orc_skydome(const float* hdri, int hw, int hh, int levels, const VqMatrix* inv_view_proj,
+                 const float* normal_mask /* may be null */, float* scene, int width, int height,
+                 int row_begin, int row_end, int threads) {
+    const Pyramid py{hdri, hw, hh, levels};
+    par_rows(row_end - row_begin, threads, [&](int r) {
+        const int y = row_begin + r;
+        for (int x = 0; x < width; ++x) {
+            const size_t o = ((size_t)y * width + x) * 4;
+            if (normal_mask && !(normal_mask[o] == 0.0f && normal_mask[o + 1] == 0.0f && normal_mask[o + 2] == 0.0f)) continue;
+            st(scene + o, Skydome_PSMain(py, *inv_view_proj, x, y, width, height));
+        }
+    });
+}
+void orc_apply_reflections(float* scene, const float* reflection, const float* bounding_volumes /* may be null */,
+                           int width, int height, int threads) {
+    par_rows(height, threads, [&](int y) {
+        for (int x = 0; x < width; ++x) {
+            const size_t o = ((size_t)y * width + x) * 4;
+            float4 bv;
+            if (bounding_volumes) bv = ld(bounding_volumes + o);
+            st(scene + o, ApplyReflections_CSMain(ld(scene + o), ld(reflection + o), bounding_volumes ? &bv : nullptr));
+        }
+    });
+}
 }  // extern "C"

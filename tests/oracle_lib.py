@@ -255,3 +255,86 @@ def unpack_normal(sampled, n, t):
     out = np.zeros(3, np.float32)
     lib().orc_unpack_normal(_p(_f(sampled)), _p(_f(n)), _p(_f(t)), _p(out))
     return out
+
+
+# ---- §8(f).2 Radiance .hdr codec / §8(f).3 skydome + ApplyReflections (oracle_frame.cpp) ---------------------------
+STB_REF_LIB = os.path.join(ORACLE_DIR, "_ref", "libstbref.so")
+_stb = None
+
+
+def stb_ref():
+    """The reference's own vendored stb_image / stb_image_write .hdr codec (oracle/_ref/libstbref.so), or None."""
+    global _stb
+    if _stb is None and os.path.exists(STB_REF_LIB):
+        _stb = C.CDLL(STB_REF_LIB)
+        _stb.stbref_write_hdr.restype = C.c_uint64
+    return _stb
+
+
+def _bytes_ptr(b: np.ndarray):
+    return b.ctypes.data_as(C.POINTER(C.c_uint8))
+
+
+def hdr_decode(file_bytes, which: str = "oracle"):
+    """-> (rc, rgba float32 [h,w,4] or None, max_luminance). rc: 0 ok, else the stb failure class (oracle) / 1 (ref)."""
+    buf = np.frombuffer(bytes(file_bytes), dtype=np.uint8).copy()
+    w, h = C.c_int(0), C.c_int(0)
+    if which == "ref":
+        r = stb_ref()
+        if not r.stbref_loadf(_bytes_ptr(buf), C.c_int(buf.size), C.byref(w), C.byref(h), None):
+            return 1, None, None
+        out = np.empty((h.value, w.value, 4), dtype=np.float32)
+        r.stbref_loadf(_bytes_ptr(buf), C.c_int(buf.size), C.byref(w), C.byref(h), _p(out))
+        return 0, out, None
+    L = lib()
+    rc = L.orc_hdr_decode(_bytes_ptr(buf), C.c_uint64(buf.size), C.byref(w), C.byref(h), None, None)
+    if rc:
+        return rc, None, None
+    out = np.empty((h.value, w.value, 4), dtype=np.float32)
+    lum = f32(0)
+    L.orc_hdr_decode(_bytes_ptr(buf), C.c_uint64(buf.size), C.byref(w), C.byref(h), _p(out), C.byref(lum))
+    return 0, out, lum.value
+
+
+def hdr_encode(rgba, which: str = "oracle") -> bytes:
+    a = _f(rgba)
+    h, w = a.shape[:2]
+    cap = 256 + w * h * 6 + h * 8
+    out = np.empty(cap, dtype=np.uint8)
+    if which == "ref":
+        n = stb_ref().stbref_write_hdr(_p(a), C.c_int(w), C.c_int(h), _bytes_ptr(out), C.c_uint64(cap))
+    else:
+        L = lib()
+        L.orc_hdr_encode.restype = C.c_uint64
+        n = L.orc_hdr_encode(_p(a), C.c_int(w), C.c_int(h), _bytes_ptr(out), C.c_uint64(cap))
+    assert n <= cap
+    return out[:n].tobytes()
+
+
+def linear_to_rgbe(rgba) -> np.ndarray:
+    a = _f(rgba).reshape(-1, 4)
+    out = np.empty((a.shape[0], 4), dtype=np.uint8)
+    lib().orc_linear_to_rgbe(_p(a), C.c_int(a.shape[0]), _bytes_ptr(out))
+    return out.reshape(np.asarray(rgba).shape[:-1] + (4,))
+
+
+def skydome(hdri_pyramid, hw, hh, levels, inv_view_proj, scene, normal_mask=None, rows=None, threads=0):
+    """scene [h,w,4] is updated in place where normal_mask.xyz == 0 (everywhere if normal_mask is None)."""
+    import vqengine_b200 as vq  # struct definitions only (VqMatrix)
+    h, w = scene.shape[:2]
+    m = vq.Matrix((f32 * 16)(*[float(x) for x in np.asarray(inv_view_proj, dtype=np.float32).reshape(16)]))
+    rb, re = rows if rows else (0, h)
+    py = _f(hdri_pyramid)
+    nm = _f(normal_mask) if normal_mask is not None else None
+    lib().orc_skydome(_p(py), C.c_int(hw), C.c_int(hh), C.c_int(levels), C.byref(m), _p(nm) if nm is not None else None,
+                      _p(scene), C.c_int(w), C.c_int(h), C.c_int(rb), C.c_int(re), C.c_int(threads or (os.cpu_count() or 1)))
+    return scene
+
+
+def apply_reflections(scene, reflection, bounding_volumes=None, threads=0):
+    h, w = scene.shape[:2]
+    refl = _f(reflection)
+    bv = _f(bounding_volumes) if bounding_volumes is not None else None
+    lib().orc_apply_reflections(_p(scene), _p(refl), _p(bv) if bv is not None else None, C.c_int(w), C.c_int(h),
+                                C.c_int(threads or (os.cpu_count() or 1)))
+    return scene

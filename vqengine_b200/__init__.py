@@ -151,6 +151,11 @@ class MaterialTextures(C.Structure):
     _fields_ = [(k, Texture2D) for k in MATERIAL_TEXTURE_SLOTS]
 
 
+class HdrInfo(C.Structure):
+    _fields_ = [("width", C.c_int32), ("height", C.c_int32), ("data_offset", C.c_uint64), ("flat", C.c_int32),
+                ("reserved", C.c_int32)]
+
+
 class SurfaceInputs(C.Structure):
     _fields_ = [("position_u", Image), ("normal_v", Image), ("tangent_m", Image), ("ssao", Image)]
 
@@ -165,6 +170,8 @@ ABI_SYMBOLS = [
     "vq_pyramid_texel_count", "vq_pyramid_offset", "vq_forward_lighting_host", "vq_environment_prepare",
     "vq_environment_invalidate", "vq_forward_lighting_multi",
     "vq_texture_build_mips", "vq_material_table_create", "vq_material_table_destroy", "vq_gbuffer_from_materials",
+    "vq_hdr_parse", "vq_hdr_decode", "vq_hdr_load_host", "vq_hdr_encode_rgbe", "vq_hdr_pack_file", "vq_hdr_save_host",
+    "vq_skydome", "vq_apply_reflections",
 ]
 
 
@@ -229,6 +236,15 @@ def _load() -> C.CDLL:
     lib.vq_material_table_create.argtypes = [vp, P(MaterialData), P(MaterialTextures), C.c_int, P(vp)]
     lib.vq_material_table_destroy.argtypes = [vp, vp]
     lib.vq_gbuffer_from_materials.argtypes = [vp, P(SurfaceInputs), vp, f32, C.c_int, P(GBuffer), C.c_int, C.c_int, vp]
+    u64 = C.c_uint64
+    lib.vq_hdr_parse.argtypes = [vp, u64, P(HdrInfo), P(u64)]
+    lib.vq_hdr_decode.argtypes = [vp, vp, u64, P(HdrInfo), vp, Image, vp, vp]
+    lib.vq_hdr_load_host.argtypes = [vp, vp, u64, Image, P(f32)]
+    lib.vq_hdr_encode_rgbe.argtypes = [vp, Image, vp, vp]
+    lib.vq_hdr_pack_file.argtypes = [vp, C.c_int, C.c_int, vp, u64, P(u64)]
+    lib.vq_hdr_save_host.argtypes = [vp, Image, vp, u64, P(u64)]
+    lib.vq_skydome.argtypes = [vp, P(Matrix), Pyramid, P(Image), Image, C.c_int, C.c_int, vp]
+    lib.vq_apply_reflections.argtypes = [vp, Image, Image, P(Image), vp]
     return lib
 
 
@@ -289,6 +305,32 @@ def pyramid_texel_count(w: int, h: int, levels: int) -> int:
 
 def pyramid_offset(w: int, h: int, level: int) -> int:
     return lib.vq_pyramid_offset(w, h, level)
+
+
+# ---- Radiance .hdr, host side (no GPU needed) ----------------------------------------------------
+def hdr_parse(file_bytes: bytes):
+    """-> (HdrInfo, channel_offsets numpy uint64 [4*height+1] or None for flat files). Raises VqError on a bad file."""
+    import numpy as np
+    buf = (C.c_uint8 * len(file_bytes)).from_buffer_copy(file_bytes)
+    info = HdrInfo()
+    _check(lib.vq_hdr_parse(buf, len(file_bytes), C.byref(info), None))
+    if info.flat:
+        return info, None
+    offs = np.zeros(4 * info.height + 1, dtype=np.uint64)
+    _check(lib.vq_hdr_parse(buf, len(file_bytes), C.byref(info), offs.ctypes.data_as(C.POINTER(C.c_uint64))))
+    return info, (None if info.flat else offs)
+
+
+def hdr_pack_file(rgbe) -> bytes:
+    """[H, W, 4] uint8 RGBE texels -> the .hdr file image (host side of Image::SaveToDisk)."""
+    import numpy as np
+    a = np.ascontiguousarray(rgbe, dtype=np.uint8)
+    h, w = a.shape[:2]
+    n = C.c_uint64(0)
+    _check(lib.vq_hdr_pack_file(a.ctypes.data, w, h, None, 0, C.byref(n)))
+    out = np.empty(n.value, dtype=np.uint8)
+    _check(lib.vq_hdr_pack_file(a.ctypes.data, w, h, out.ctypes.data, n.value, C.byref(n)))
+    return out.tobytes()
 
 
 # ---- descriptors from torch tensors ------------------------------------------------------------
@@ -389,6 +431,60 @@ class Context:
         _check(lib.vq_gbuffer_from_materials(self._h, C.byref(inputs), table._h, ambient_factor, 1 if alpha_mask else 0,
                                              C.byref(gbuffer), row_begin, h if row_end is None else row_end,
                                              _stream_ptr(stream)))
+
+    # Radiance .hdr
+    def hdr_decode(self, file_bytes: bytes, stream=None):
+        """file image (host bytes) -> ([H, W, 4] float32 CUDA tensor, 1-element max-luminance tensor); asynchronous."""
+        import numpy as np
+        import torch
+        info, offs = hdr_parse(file_bytes)
+        n = len(file_bytes)
+        dfile = torch.zeros(((n + 15) // 16 * 16 + 16,), dtype=torch.uint8, device=f"cuda:{self.device}")
+        dfile[:n] = torch.frombuffer(bytearray(file_bytes), dtype=torch.uint8).to(dfile.device)
+        doffs = torch.from_numpy(offs.view(np.int64)).to(dfile.device) if offs is not None else None
+        out = torch.empty((info.height, info.width, 4), dtype=torch.float32, device=dfile.device)
+        lum = torch.zeros((1,), dtype=torch.float32, device=dfile.device)
+        _check(lib.vq_hdr_decode(self._h, dfile.data_ptr(), n, C.byref(info), doffs.data_ptr() if doffs is not None else None,
+                                 image_of(out), lum.data_ptr(), _stream_ptr(stream)))
+        out._vq_keepalive = (dfile, doffs)
+        return out, lum
+
+    def hdr_load_host(self, file_bytes: bytes, out):
+        """blocking vq_hdr_load_host; returns Image::MaxLuminance"""
+        buf = (C.c_uint8 * len(file_bytes)).from_buffer_copy(file_bytes)
+        lum = f32(0)
+        _check(lib.vq_hdr_load_host(self._h, buf, len(file_bytes), image_of(out), C.byref(lum)))
+        return lum.value
+
+    def hdr_encode_rgbe(self, src, stream=None):
+        """[H, W, 4] float32 CUDA tensor -> [H, W, 4] uint8 RGBE CUDA tensor"""
+        import torch
+        out = torch.empty(src.shape, dtype=torch.uint8, device=src.device)
+        _check(lib.vq_hdr_encode_rgbe(self._h, image_of(src), out.data_ptr(), _stream_ptr(stream)))
+        return out
+
+    def hdr_save_host(self, src) -> bytes:
+        """blocking vq_hdr_save_host: device image -> .hdr file image"""
+        import numpy as np
+        h, w = src.shape[:2]
+        cap = 256 + w * h * 6 + h * 8
+        out = np.empty(cap, dtype=np.uint8)
+        n = C.c_uint64(0)
+        _check(lib.vq_hdr_save_host(self._h, image_of(src), out.ctypes.data, cap, C.byref(n)))
+        return out[:n.value].tobytes()
+
+    # SURVEY 8(f).3: skydome + reflection composite
+    def skydome(self, inv_view_proj, pyr: Pyramid, scene, normal_mask=None, row_begin=0, row_end=None, stream=None):
+        m = Matrix((f32 * 16)(*[float(x) for x in inv_view_proj]))
+        o = image_of(scene)
+        mask = image_of(normal_mask) if normal_mask is not None else None
+        _check(lib.vq_skydome(self._h, C.byref(m), pyr, C.byref(mask) if mask is not None else None, o, row_begin,
+                              o.height if row_end is None else row_end, _stream_ptr(stream)))
+
+    def apply_reflections(self, scene, reflection, bounding_volumes=None, stream=None):
+        bv = image_of(bounding_volumes) if bounding_volumes is not None else None
+        _check(lib.vq_apply_reflections(self._h, image_of(scene), image_of(reflection),
+                                        C.byref(bv) if bv is not None else None, _stream_ptr(stream)))
 
     # K11 / K2 / K3 / K4
     def hdri_build_mips(self, pyr: Pyramid, stream=None):

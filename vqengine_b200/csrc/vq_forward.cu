@@ -17,15 +17,19 @@ using namespace vq;
 
 namespace {
 
-constexpr int FWD_THREADS = 256;
-constexpr int MAX_POINT = VQ_NUM_LIGHTS_POINT + VQ_NUM_SHADOWING_LIGHTS_POINT;   // casters appended (shadow factor 1)
-constexpr int MAX_SPOT = VQ_NUM_LIGHTS_SPOT + VQ_NUM_SHADOWING_LIGHTS_SPOT;
 
-// Bordered sampling copy of a cubemap: every face of every mip is stored as (N+2)x(N+2) texels, the 1-texel
+// Sampling copy of a cubemap. Every face of every mip is a (N+2)x(N+2) grid of bordered texel positions, the 1-texel
 // border holding the neighbouring faces' edge texels (corners: the mean of the three texels that meet there), so
-// that the seamless bilinear footprint never leaves the face. mipOffset[] are texel offsets of face 0 per mip.
+// that the seamless bilinear footprint never leaves the face. Each position (i,j) stores the PAIR {t(i,j), t(i+1,j)}
+// as one 32-byte record: a bilinear footprint is two 256-bit loads (LDG.E.256, sm_100) instead of four 128-bit ones.
+// K1 is bound by the L1 data pipe (one wavefront per distinct 128-byte line a warp-wide load touches, ~20-30 for a
+// gather whose lanes go to unrelated texels), so the number of gather INSTRUCTIONS per pixel is what the layout
+// minimises: 12 -> 5. mipOffset[] are record offsets of face 0 per mip.
 struct CubeV { const float4* p; int res, mips; uint32_t mipOffset[16]; };
-struct LutV { const float2* p; int w, h, pitch2; };
+// Footprint copy of the BRDF LUT: record (cx,cy), cx = clamp(x0+1, 0, W), holds the CLAMP-addressed 2x2 footprint
+// {p(x0,y0), p(x0+1,y0), p(x0,y0+1), p(x0+1,y0+1)} as 4 x float2 = 32 bytes: one 256-bit load per pixel.
+struct LutV { const float4* q; int w, h; };
+struct F8 { float4 a, b; };
 
 struct FwdParams {
     VqSceneLighting lights;            // 7088 B, read once per block into shared memory
@@ -43,6 +47,7 @@ struct FwdParams {
 };
 
 struct SPoint { float3 pos; float d2Limit; float3 color; float brightness; };
+struct SDir { float3 wi; float pad0; float3 radiance; float pad1; };
 struct SSpot { float3 pos; float outer; float3 color; float brightness; float3 dir; float inner; float invCone; float pad[3]; };
 
 // ---------------------------------------------------------------------------------------------
@@ -90,66 +95,63 @@ __device__ void cube_resolve_edge(int N, int face, int i, int j, int& of, int& o
     oj = min(max(((M - nsy) * N) / (2 * M), 0), N - 1);
 }
 
-// packed cube (mip-major / face-minor, N x N faces) -> bordered sampling copy ((N+2) x (N+2) faces)
+// value of bordered position `idx` (flattened over mips, faces, (N+2)^2 positions) of a packed cube
+__device__ float4 bordered_texel(const float4* __restrict__ src, int res, int mips, uint32_t idx) {
+    uint32_t rem = idx, srcOff = 0; int m = 0, N = res;
+    for (; m < mips; ++m) {
+        N = res >> m;
+        const uint32_t sz = 6u * (uint32_t)(N + 2) * (uint32_t)(N + 2);
+        if (rem < sz) break;
+        rem -= sz; srcOff += 6u * (uint32_t)N * (uint32_t)N;
+    }
+    const int P = N + 2;
+    const int face = (int)(rem / (uint32_t)(P * P));
+    const int r2 = (int)(rem % (uint32_t)(P * P));
+    const int i = r2 % P - 1, j = r2 / P - 1;           // face-relative texel, -1..N
+    const float4* sm = src + srcOff;
+    auto fetch = [&](int f, int x, int y) { return __ldg(sm + (size_t)f * N * N + (size_t)y * N + x); };
+    auto edge = [&](int x, int y) { int f2, i2, j2; cube_resolve_edge(N, face, x, y, f2, i2, j2); return fetch(f2, i2, j2); };
+    const bool oi = (i < 0 || i >= N), oj = (j < 0 || j >= N);
+    if (!oi && !oj) return fetch(face, i, j);
+    if (oi != oj) return edge(i, j);
+    // cube corner: mean of the three texels meeting there (own corner + the two edge neighbours)
+    const int ci = i < 0 ? 0 : N - 1, cj = j < 0 ? 0 : N - 1;
+    const float4 a = fetch(face, ci, cj), b = edge(i, cj), c = edge(ci, j);
+    return make_float4((a.x + b.x + c.x) * (1.0f / 3.0f), (a.y + b.y + c.y) * (1.0f / 3.0f),
+                       (a.z + b.z + c.z) * (1.0f / 3.0f), (a.w + b.w + c.w) * (1.0f / 3.0f));
+}
+// packed cube (mip-major / face-minor, N x N faces) -> sampling copy: one {t(i,j), t(i+1,j)} record per bordered position
+// (the last position of a row repeats itself; it is never the left tap of a footprint)
 __global__ void __launch_bounds__(256) cube_pad_kernel(const float4* __restrict__ src, float4* __restrict__ dst,
                                                         int res, int mips, uint32_t totalPadded) {
     for (uint32_t idx = blockIdx.x * 256u + threadIdx.x; idx < totalPadded; idx += gridDim.x * 256u) {
-        // locate (mip, face, pj, pi) of this padded texel
-        uint32_t rem = idx, srcOff = 0; int m = 0, N = res;
-        for (; m < mips; ++m) {
-            N = res >> m;
-            const uint32_t sz = 6u * (uint32_t)(N + 2) * (uint32_t)(N + 2);
+        // is idx the last position of its row?  rows are (N+2) long and faces/mips are whole rows, so walk the mips
+        uint32_t rem = idx; int P = res + 2;
+        for (int m = 0; m < mips; ++m) {
+            P = (res >> m) + 2;
+            const uint32_t sz = 6u * (uint32_t)P * (uint32_t)P;
             if (rem < sz) break;
-            rem -= sz; srcOff += 6u * (uint32_t)N * (uint32_t)N;
+            rem -= sz;
         }
-        const int P = N + 2;
-        const int face = (int)(rem / (uint32_t)(P * P));
-        const int r2 = (int)(rem % (uint32_t)(P * P));
-        const int i = r2 % P - 1, j = r2 / P - 1;           // face-relative texel, -1..N
-        const float4* sm = src + srcOff;
-        auto fetch = [&](int f, int x, int y) { return __ldg(sm + (size_t)f * N * N + (size_t)y * N + x); };
-        auto edge = [&](int x, int y) { int f2, i2, j2; cube_resolve_edge(N, face, x, y, f2, i2, j2); return fetch(f2, i2, j2); };
-        const bool oi = (i < 0 || i >= N), oj = (j < 0 || j >= N);
-        float4 v;
-        if (!oi && !oj) v = fetch(face, i, j);
-        else if (oi != oj) v = edge(i, j);
-        else {   // cube corner: mean of the three texels meeting there (own corner + the two edge neighbours)
-            const int ci = i < 0 ? 0 : N - 1, cj = j < 0 ? 0 : N - 1;
-            const float4 a = fetch(face, ci, cj), b = edge(i, cj), c = edge(ci, j);
-            v = make_float4((a.x + b.x + c.x) * (1.0f / 3.0f), (a.y + b.y + c.y) * (1.0f / 3.0f),
-                            (a.z + b.z + c.z) * (1.0f / 3.0f), (a.w + b.w + c.w) * (1.0f / 3.0f));
-        }
-        dst[idx] = v;
+        const bool last = (rem % (uint32_t)P) == (uint32_t)(P - 1);
+        const float4 v0 = bordered_texel(src, res, mips, idx);
+        const float4 v1 = last ? v0 : bordered_texel(src, res, mips, idx + 1u);
+        dst[2 * (size_t)idx] = v0;
+        dst[2 * (size_t)idx + 1] = v1;
     }
 }
 
-__device__ __forceinline__ float3 sample_cube(const CubeV& c, float3 dir, int mip) {
-    mip = min(max(mip, 0), c.mips - 1);
-    const int N = c.res >> mip, P = N + 2;
-    int face; float sx, sy;
-    dir_to_face(dir, face, sx, sy);
-    const float x = fmaf(fmaf(sx, 0.5f, 0.5f), (float)N, -0.5f);
-    const float y = fmaf(fmaf(-sy, 0.5f, 0.5f), (float)N, -0.5f);
-    const float xf = fminf(fmaxf(floorf(x), -1.0f), (float)(N - 1)), yf = fminf(fmaxf(floorf(y), -1.0f), (float)(N - 1));
-    const float fx = x - xf, fy = y - yf;
-    const int i0 = (int)xf + 1, j0 = (int)yf + 1;            // bordered coordinates: 0..N
-    const float4* p = c.p + (c.mipOffset[mip] + (uint32_t)(face * (P * P) + j0 * P + i0));
-    const float4 t00 = __ldg(p), t10 = __ldg(p + 1), t01 = __ldg(p + P), t11 = __ldg(p + P + 1);
-    const float3 top = lerp(xyz(t00), xyz(t10), fx), bot = lerp(xyz(t01), xyz(t11), fx);
-    return lerp(top, bot, fy);
-}
-
-__device__ __forceinline__ float2 sample_lut(const LutV& l, float u, float v) {   // bilinear, CLAMP
-    const float x = fmaf(u, (float)l.w, -0.5f), y = fmaf(v, (float)l.h, -0.5f);
-    const float x0 = floorf(x), y0 = floorf(y);
-    const float fx = x - x0, fy = y - y0;
-    const int ix0 = min(max((int)x0, 0), l.w - 1), ix1 = min(max((int)x0 + 1, 0), l.w - 1);
-    const int iy0 = min(max((int)y0, 0), l.h - 1), iy1 = min(max((int)y0 + 1, 0), l.h - 1);
-    const uint32_t r0 = (uint32_t)(iy0 * l.pitch2), r1 = (uint32_t)(iy1 * l.pitch2);
-    const float2 p00 = __ldg(l.p + (r0 + ix0)), p10 = __ldg(l.p + (r0 + ix1));
-    const float2 p01 = __ldg(l.p + (r1 + ix0)), p11 = __ldg(l.p + (r1 + ix1));
-    return make_float2(lerp(lerp(p00.x, p10.x, fx), lerp(p01.x, p11.x, fx), fy),
-                       lerp(lerp(p00.y, p10.y, fx), lerp(p01.y, p11.y, fx), fy));
+// BRDF LUT (float2, pitched) -> footprint records (see LutV): (W+1) x (H+1) records of 32 bytes
+__global__ void __launch_bounds__(256) lut_footprint_kernel(const float2* __restrict__ src, int pitch2, int W, int H, float4* __restrict__ dst) {
+    const uint32_t total = (uint32_t)(W + 1) * (uint32_t)(H + 1);
+    for (uint32_t idx = blockIdx.x * 256u + threadIdx.x; idx < total; idx += gridDim.x * 256u) {
+        const int cx = (int)(idx % (uint32_t)(W + 1)), cy = (int)(idx / (uint32_t)(W + 1));
+        const int x0 = max(cx - 1, 0), x1 = min(cx, W - 1), y0 = max(cy - 1, 0), y1 = min(cy, H - 1);
+        const float2 p00 = __ldg(src + (size_t)y0 * pitch2 + x0), p10 = __ldg(src + (size_t)y0 * pitch2 + x1);
+        const float2 p01 = __ldg(src + (size_t)y1 * pitch2 + x0), p11 = __ldg(src + (size_t)y1 * pitch2 + x1);
+        dst[2 * (size_t)idx] = make_float4(p00.x, p00.y, p10.x, p10.y);
+        dst[2 * (size_t)idx + 1] = make_float4(p01.x, p01.y, p11.x, p11.y);
+    }
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -161,7 +163,7 @@ struct Px {
     float nsLen;                  // |Ns|: dot(Ns,Wi) = nsLen * dot(Nn,Wi)  (Lighting.hlsl:316 uses the raw s.N)
     float nv, NdotV, gV;          // dot(Nn,V), saturate, Smith-G1 of V (BRDF.hlsl:82-97)
     float a2, a2m1, k, omk;
-    const float4* nrmTexel;       // where the raw normal lives: re-read by the exact slow path only
+    uint32_t nrmTexel;            // shared-memory address of the raw normal texel: re-read by the exact slow path only
 };
 
 // ---- exact re-evaluation of N.H -------------------------------------------------------------------
@@ -170,26 +172,65 @@ struct Px {
 // N.H with the oracle's exact operation sequence (correctly rounded div/sqrt, no FMA contraction): V, Wo,
 // N, Wi, H as BRDF.hlsl:166-169 / Lighting.hlsl:312 write them. T_EXACT = 0.02 bounds the fast path's
 // relative error in D by 2*dt/t <= 2*5e-7/0.02 = 5e-5; the slow path runs for < 1 % of pixel-light pairs.
-constexpr float T_EXACT = 0.02f;
+#ifndef FWD_T_EXACT
+#define FWD_T_EXACT 0.02f
+#endif
+constexpr float T_EXACT = FWD_T_EXACT;
 
 __device__ __forceinline__ float dot_u(float3 a, float3 b) {     // (x*x' + y*y') + z*z', every op rounded
     return __fadd_rn(__fadd_rn(__fmul_rn(a.x, b.x), __fmul_rn(a.y, b.y)), __fmul_rn(a.z, b.z));
 }
+// Correctly rounded sqrt and division WITHOUT the range check + slow-path call that __fsqrt_rn / __fdiv_rn carry
+// (FCHK, BSSY/BSYNC and a CALL per operation: ~3x the instructions). These are the same MUFU-seeded FMA
+// sequences the CUDA intrinsics execute for in-range operands, so they return the same bits; callers guarantee
+// the range (the divisor is a vector length checked against [1e-18, 1e18]; a numerator so small that the quotient
+// is denormal can be off by one denormal ulp, 1e-45, which no consumer of a unit vector can see).
+__device__ __forceinline__ float sqrt_rn_inrange(float x) {
+    const float r = rsqrt_fast(x);
+    const float s = __fmul_rn(x, r), h = __fmul_rn(r, 0.5f);
+    return __fmaf_rn(__fmaf_rn(-s, s, x), h, s);
+}
+struct RcpRn { float r, nb; };                               // refined reciprocal of b and -b
+__device__ __forceinline__ RcpRn rcp_rn_prepare(float b) {
+    const float r0 = rcp_fast(b);
+    RcpRn q; q.nb = -b; q.r = __fmaf_rn(r0, __fmaf_rn(r0, q.nb, 1.0f), r0);
+    return q;
+}
+__device__ __forceinline__ float div_rn_inrange(float a, RcpRn d) {
+    const float q = __fmul_rn(a, d.r);
+    return __fmaf_rn(d.r, __fmaf_rn(q, d.nb, a), q);
+}
+__device__ __forceinline__ bool len2_inrange(float d) { return d > 1e-30f && d < 1e30f; }   // squared length
 // v / sqrt(dot(v,v)) with correctly rounded sqrt and divisions (== the oracle's normalize)
-__device__ __forceinline__ float3 normalize_u(float3 v) {
+__device__ __noinline__ float3 normalize_u_generic(float3 v) {
     const float l = __fsqrt_rn(dot_u(v, v));
     return f3(__fdiv_rn(v.x, l), __fdiv_rn(v.y, l), __fdiv_rn(v.z, l));
 }
+__device__ __forceinline__ float3 normalize_u(float3 v) {
+    const float d = dot_u(v, v);
+    if (!len2_inrange(d)) return normalize_u_generic(v);                          // never taken for sane geometry
+    const RcpRn r = rcp_rn_prepare(sqrt_rn_inrange(d));
+    return f3(div_rn_inrange(v.x, r), div_rn_inrange(v.y, r), div_rn_inrange(v.z, r));
+}
 
-__device__ __noinline__ float exact_ndoth(float3 cam, float3 P, const float4* nrmTexel, float3 wiSrc, float wiLenSq) {
-    const float4 nr = __ldg(nrmTexel);
+// nrmTexel: the pixel's raw {N.xyz, roughness} texel in the shared-memory stage (still valid: the stage is released
+// after the pixel is finished)
+__device__ __noinline__ float exact_ndoth(float3 cam, float3 P, uint32_t nrmTexel, float3 wiSrc, float wiLenSq) {
+    float4 nr;
+    asm volatile("ld.shared.v4.f32 {%0,%1,%2,%3}, [%4];" : "=f"(nr.x), "=f"(nr.y), "=f"(nr.z), "=f"(nr.w) : "r"(nrmTexel));
     const float3 Ns = f3(nr.x, nr.y, nr.z);
     const float3 Vv = f3(__fsub_rn(cam.x, P.x), __fsub_rn(cam.y, P.y), __fsub_rn(cam.z, P.z));
     const float3 V = normalize_u(Vv);                 // ForwardLighting.hlsl:285
     const float3 Wo = normalize_u(V);                 // BRDF.hlsl:166
     const float3 N = normalize_u(Ns);                 // BRDF.hlsl:167
-    const float wl = __fsqrt_rn(wiLenSq);
-    const float3 Wi = f3(__fdiv_rn(wiSrc.x, wl), __fdiv_rn(wiSrc.y, wl), __fdiv_rn(wiSrc.z, wl));
+    float3 Wi;                                        // Lighting.hlsl:312: Lv / length(Lv)
+    if (len2_inrange(wiLenSq)) {
+        const RcpRn r = rcp_rn_prepare(sqrt_rn_inrange(wiLenSq));
+        Wi = f3(div_rn_inrange(wiSrc.x, r), div_rn_inrange(wiSrc.y, r), div_rn_inrange(wiSrc.z, r));
+    } else {
+        const float w2 = __fsqrt_rn(wiLenSq);
+        Wi = f3(__fdiv_rn(wiSrc.x, w2), __fdiv_rn(wiSrc.y, w2), __fdiv_rn(wiSrc.z, w2));
+    }
     const float3 Hs = f3(__fadd_rn(Wo.x, Wi.x), __fadd_rn(Wo.y, Wi.y), __fadd_rn(Wo.z, Wi.z));
     const float3 H = normalize_u(Hs);                 // BRDF.hlsl:168
     return saturate(dot_u(N, H));
@@ -243,34 +284,184 @@ __device__ __forceinline__ void shade_point(const Px& s, Acc& acc, float3 cam, c
     shade_light(s, acc, cam, Lv, d2, invD, scale, l.color);
 }
 
-constexpr int FWD_BX = 64, FWD_BY = 4;   // 256 threads: 64 x 4 pixel tile; grid.x covers the row, grid.y strides rows
+// ---------------------------------------------------------------------------------------------
+// TMA (bulk async copy) + mbarrier plumbing, raw PTX for sm_100a
+// ---------------------------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" :: "r"(bar), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" :: "r"(bar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint32_t bar) {
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" :: "r"(bar) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
+    uint32_t done;
+    do {
+        asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}"
+                     : "=r"(done) : "r"(bar), "r"(parity) : "memory");
+    } while (!done);
+}
+__device__ __forceinline__ void mbar_wait_backoff(uint32_t bar, uint32_t parity) {   // single-thread waits: do not steal issue slots
+    uint32_t done;
+    for (;;) {
+        asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}"
+                     : "=r"(done) : "r"(bar), "r"(parity) : "memory");
+        if (done) break;
+        __nanosleep(128);
+    }
+}
+__device__ __forceinline__ uint64_t l2_evict_first_policy() {
+    uint64_t pol; asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(pol)); return pol;
+}
+// one contiguous row segment global -> shared through the TMA unit; completion is counted in bytes on `bar`
+__device__ __forceinline__ void tma_load_row(uint32_t dst, const void* src, uint32_t bytes, uint32_t bar, uint64_t pol) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes.L2::cache_hint [%0], [%1], %2, [%3], %4;"
+                 :: "r"(dst), "l"(src), "r"(bytes), "r"(bar), "l"(pol) : "memory");
+}
+__device__ __forceinline__ float4 lds128(uint32_t addr) {       // volatile: the load stays where it is written (register diet)
+    float4 r;
+    asm volatile("ld.shared.v4.f32 {%0,%1,%2,%3}, [%4];" : "=f"(r.x), "=f"(r.y), "=f"(r.z), "=f"(r.w) : "r"(addr) : "memory");
+    return r;
+}
+__device__ __forceinline__ float lds32(uint32_t addr) {
+    float r; asm volatile("ld.shared.f32 %0, [%1];" : "=f"(r) : "r"(addr) : "memory"); return r;
+}
+__device__ __forceinline__ void st_stream_hint(float4* p, float4 v, uint64_t pol) {
+    asm volatile("st.global.L1::no_allocate.L2::cache_hint.v4.f32 [%0], {%1,%2,%3,%4}, %5;"
+                 :: "l"(p), "f"(v.x), "f"(v.y), "f"(v.z), "f"(v.w), "l"(pol) : "memory");
+}
 
-// Tuning knobs, A/B-measured on B200 at 4K (profiles/r01_forward_variants.txt, us per frame):
-//   blocks/SM, prefetch, pair, IBL-last:  3,0,0,1 -> 328 (80 regs, no spills)  | 4,0,0,1 -> 334 | 4,0,0,0 -> 344
-//   3,0,1,1 -> 349 | 2,1,1,0 (116 regs) -> 358 | 3,0,1,0 -> 364 | 4,0,1,x -> 376-379 | 3,1,1,0 -> 381 | 5,0,0,1 -> 437
-// Shading the lights first and the environment map last keeps the 8 gathered texels out of the light loop's live
-// range; neither register prefetching nor interleaving two lights pays at this register budget.
-#ifndef FWD_MIN_BLOCKS
-#define FWD_MIN_BLOCKS 3
+// K1 is a persistent kernel: FWD_CTAS_PER_SM CTAs of 128 threads per SM, each walking the tile list
+// (tile = 128 consecutive pixels of one row = one 2 KB row segment per G-buffer plane) with stride gridDim.x.
+// The G-buffer arrives through a FWD_STAGES-deep TMA pipeline in shared memory: thread 0 issues one bulk copy
+// per plane for the tile FWD_AHEAD iterations ahead (full[] mbarriers count the bytes), every thread reads
+// ITS texels back with LDS when it needs them and releases the stage (empty[] mbarriers) when its pixel is
+// stored. Nothing of the G-buffer is live in registers across the light loop: albedo/metalness/ao, the raw
+// normal and the emissive texel are (re-)read from the stage after it, which is what lets the kernel run at
+// <= 80 registers with the HBM latency fully hidden behind the previous tiles' shading.
+// A/B on B200 at 4K: profiles/r01_forward_variants.txt.
+constexpr int FWD_TILE = 128;
+#ifndef FWD_STAGES
+#define FWD_STAGES 4           // shared-memory stages
 #endif
-#ifndef FWD_PREFETCH
-#define FWD_PREFETCH 0
+#ifndef FWD_AHEAD
+#define FWD_AHEAD 2            // tiles requested ahead of the one being shaded (< FWD_STAGES): the stage a request
+#endif                         // reuses was released FWD_STAGES-FWD_AHEAD iterations ago, so thread 0 rarely waits
+#ifndef FWD_IBL_EARLY
+#define FWD_IBL_EARLY 0        // 0: gather the environment taps after the light loop; 1: specular cube + LUT before it
+#endif                         // (24 registers in flight, latency hidden by the lights); 2: the diffuse cube as well
+#ifndef FWD_CTAS_PER_SM
+#define FWD_CTAS_PER_SM 5
 #endif
-#ifndef FWD_PAIR
-#define FWD_PAIR 0
-#endif
-#ifndef FWD_IBL_LAST
-#define FWD_IBL_LAST 1
-#endif
-__global__ void __launch_bounds__(FWD_THREADS, FWD_MIN_BLOCKS) forward_kernel(const __grid_constant__ FwdParams P) {
-    __shared__ SPoint sPoint[MAX_POINT];
-    __shared__ SSpot sSpot[MAX_SPOT];
 
-    // ---- stage the light arrays (Scene::GatherLightData layout) into shared memory, once per block ----
+static_assert(FWD_AHEAD >= 1 && FWD_AHEAD < FWD_STAGES, "the lookahead must leave at least one stage for the tile being shaded");
+
+struct CubeTap { uint32_t off; int P; float fx, fy; };
+__device__ __forceinline__ CubeTap cube_tap(const CubeV& c, float3 dir, int mip) {
+    mip = min(max(mip, 0), c.mips - 1);
+    const int N = c.res >> mip, P = N + 2;
+    int face; float sx, sy;
+    dir_to_face(dir, face, sx, sy);
+    const float x = fmaf(fmaf(sx, 0.5f, 0.5f), (float)N, -0.5f);
+    const float y = fmaf(fmaf(-sy, 0.5f, 0.5f), (float)N, -0.5f);
+    const float xf = fminf(fmaxf(floorf(x), -1.0f), (float)(N - 1)), yf = fminf(fmaxf(floorf(y), -1.0f), (float)(N - 1));
+    CubeTap t;
+    t.fx = x - xf; t.fy = y - yf; t.P = P;
+    const int i0 = (int)xf + 1, j0 = (int)yf + 1;            // bordered coordinates: 0..N
+    t.off = c.mipOffset[mip] + (uint32_t)(face * (P * P) + j0 * P + i0);
+    return t;
+}
+// A gather is split into "issue" (address + the 256-bit loads, kept where they are written: volatile) and "finish"
+// (the lerps), so that the loads can be put in flight before the light loop and consumed after it.
+template <bool PINNED>
+__device__ __forceinline__ F8 ldg256_issue(const float4* p) {
+    F8 r;
+    if (PINNED)
+        asm volatile("ld.global.nc.v8.f32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
+                     : "=f"(r.a.x), "=f"(r.a.y), "=f"(r.a.z), "=f"(r.a.w), "=f"(r.b.x), "=f"(r.b.y), "=f"(r.b.z), "=f"(r.b.w) : "l"(p));
+    else   // the compiler may schedule it (gathers issued after the light loop: nothing to pin them to)
+        asm("ld.global.nc.v8.f32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
+            : "=f"(r.a.x), "=f"(r.a.y), "=f"(r.a.z), "=f"(r.a.w), "=f"(r.b.x), "=f"(r.b.y), "=f"(r.b.z), "=f"(r.b.w) : "l"(p));
+    return r;
+}
+struct CubeLoad { F8 r0, r1; float fx, fy; };                     // rows j0 and j0+1: {t(i0), t(i0+1)} each
+template <bool PINNED>
+__device__ __forceinline__ CubeLoad cube_issue(const CubeV& c, float3 dir, int mip) {
+    const CubeTap t = cube_tap(c, dir, mip);
+    const float4* p = c.p + 2u * t.off;
+    CubeLoad L;
+    L.r0 = ldg256_issue<PINNED>(p); L.r1 = ldg256_issue<PINNED>(p + 2 * t.P);
+    L.fx = t.fx; L.fy = t.fy;
+    return L;
+}
+__device__ __forceinline__ float3 cube_finish(const CubeLoad& L) {
+    const float3 top = lerp(xyz(L.r0.a), xyz(L.r0.b), L.fx), bot = lerp(xyz(L.r1.a), xyz(L.r1.b), L.fx);
+    return lerp(top, bot, L.fy);
+}
+struct LutLoad { F8 q; float fx, fy; };
+template <bool PINNED>
+__device__ __forceinline__ LutLoad lut_issue(const LutV& l, float u, float v) {   // bilinear, CLAMP
+    const float x = fmaf(u, (float)l.w, -0.5f), y = fmaf(v, (float)l.h, -0.5f);
+    const float x0 = floorf(x), y0 = floorf(y);
+    LutLoad L;
+    L.fx = x - x0; L.fy = y - y0;
+    const int cx = min(max((int)x0 + 1, 0), l.w), cy = min(max((int)y0 + 1, 0), l.h);
+    L.q = ldg256_issue<PINNED>(l.q + 2u * (uint32_t)(cy * (l.w + 1) + cx));
+    return L;
+}
+__device__ __forceinline__ float2 lut_finish(const LutLoad& L) {
+    return make_float2(lerp(lerp(L.q.a.x, L.q.a.z, L.fx), lerp(L.q.b.x, L.q.b.z, L.fx), L.fy),
+                       lerp(lerp(L.q.a.y, L.q.a.w, L.fx), lerp(L.q.b.y, L.q.b.w, L.fx), L.fy));
+}
+
+template <bool MULTI>
+__global__ void __launch_bounds__(FWD_TILE, FWD_CTAS_PER_SM) forward_kernel(const __grid_constant__ FwdParams P) {
+    extern __shared__ __align__(128) unsigned char smemRaw[];
     const VqSceneLighting& L = P.lights;
     const int nP = L.numPointLights, nPC = L.numPointCasters, nS = L.numSpotLights, nSC = L.numSpotCasters;
-    const int tid = threadIdx.y * FWD_BX + threadIdx.x;
-    for (int i = tid; i < nP + nPC; i += FWD_THREADS) {
+    const int numPoint = nP + nPC, numSpot = nS + nSC;
+    const int nPl = P.hasEmissive ? 4 : 3;
+    const int tid = threadIdx.x;
+    // shared-memory layout: [FWD_STAGES][nPl][FWD_TILE] float4 | full[S], empty[S] mbarriers | SDir | SPoint[] | SSpot[]
+    const uint32_t stageBytes = (uint32_t)nPl * FWD_TILE * 16u;
+    uint64_t* bars = (uint64_t*)(smemRaw + FWD_STAGES * stageBytes);
+    SDir* sDir = (SDir*)(bars + 2 * FWD_STAGES);
+    SPoint* sPoint = (SPoint*)(sDir + 1);
+    SSpot* sSpot = (SSpot*)(sPoint + numPoint);
+    const uint32_t stage0 = smem_u32(smemRaw), bar0 = smem_u32(bars);
+    auto fullBar = [&](int st) { return bar0 + 8u * (uint32_t)st; };
+    auto emptyBar = [&](int st) { return bar0 + 8u * (uint32_t)(FWD_STAGES + st); };
+
+    // ---- tile schedule: the grid is (tiles per row) x (row groups); a CTA keeps its column and strides rows, so the
+    //      only loop state is the row, the stage index and the stage's use count ----
+    const int x0 = (int)blockIdx.x * FWD_TILE;
+    const int rowStep = (int)gridDim.y;
+    const uint32_t tileBytes = (uint32_t)min(FWD_TILE, P.width - x0) * 16u;
+    // thread 0: request the tile of row `r` into stage `sIdx`, which has been used `useCount` times before
+    auto request = [&](int r, int sIdx, uint32_t useCount) {
+        if (r >= P.rows) return;
+        if (useCount > 0) mbar_wait_backoff(emptyBar(sIdx), (useCount - 1u) & 1u);   // every thread is done with the previous use
+        const uint64_t pol = l2_evict_first_policy();                 // the G-buffer is touched once: first out of L2
+        const uint32_t dst = stage0 + (uint32_t)sIdx * stageBytes, bar = fullBar(sIdx);
+        const size_t y = (size_t)(P.rowBegin + r);
+        mbar_expect_tx(bar, tileBytes * (uint32_t)nPl);
+        tma_load_row(dst, P.pos.p + y * P.pos.pitch4 + x0, tileBytes, bar, pol);
+        tma_load_row(dst + FWD_TILE * 16u, P.nrm.p + y * P.nrm.pitch4 + x0, tileBytes, bar, pol);
+        tma_load_row(dst + 2u * FWD_TILE * 16u, P.alb.p + y * P.alb.pitch4 + x0, tileBytes, bar, pol);
+        if (nPl == 4) tma_load_row(dst + 3u * FWD_TILE * 16u, P.emi.p + y * P.emi.pitch4 + x0, tileBytes, bar, pol);
+    };
+    if (tid == 0) {
+        for (int s = 0; s < FWD_STAGES; ++s) { mbar_init(fullBar(s), 1u); mbar_init(emptyBar(s), (uint32_t)FWD_TILE); }
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+        for (int s = 0; s < FWD_AHEAD; ++s) request((int)blockIdx.y + s * rowStep, s, 0u);   // prologue: FWD_AHEAD tiles in flight
+    }
+
+    // ---- stage the light arrays (Scene::GatherLightData layout) into shared memory, once per CTA ----
+    for (int i = tid; i < numPoint; i += FWD_TILE) {
         const VqPointLight& l = i < nP ? L.point_lights[i] : L.point_casters[i - nP];
         SPoint s;
         s.pos = f3(l.position.x, l.position.y, l.position.z);
@@ -286,168 +477,143 @@ __global__ void __launch_bounds__(FWD_THREADS, FWD_MIN_BLOCKS) forward_kernel(co
         s.d2Limit = lim;
         sPoint[i] = s;
     }
-    for (int i = tid; i < nS + nSC; i += FWD_THREADS) {
+    for (int i = tid; i < numSpot; i += FWD_TILE) {
         const VqSpotLight& l = i < nS ? L.spot_lights[i] : L.spot_casters[i - nS];
         SSpot s;
         s.pos = f3(l.position.x, l.position.y, l.position.z);
         s.color = f3(l.color.x, l.color.y, l.color.z);
         s.brightness = l.brightness;
-        s.dir = normalize_u(f3(l.spotDir.x, l.spotDir.y, l.spotDir.z));   // normalize(l.spotDir), Lighting.hlsl:60
+        s.dir = normalize_u_generic(f3(l.spotDir.x, l.spotDir.y, l.spotDir.z));   // normalize(l.spotDir), Lighting.hlsl:60
         s.outer = l.outerConeAngle; s.inner = l.innerConeAngle;
         s.invCone = 1.0f / (l.outerConeAngle - l.innerConeAngle);
         sSpot[i] = s;
     }
-    __syncthreads();
-    const int numPoint = nP + nPC, numSpot = nS + nSC;
     const bool dirEnabled = L.directional.enabled != 0;
-    float3 dirWi = f3(0.0f), dirRadiance = f3(0.0f);
-    if (dirEnabled) {                                            // Lighting.hlsl:334-345
-        dirWi = normalize_u(f3(-L.directional.lightDirection.x, -L.directional.lightDirection.y, -L.directional.lightDirection.z));
-        dirRadiance = f3(L.directional.color.x, L.directional.color.y, L.directional.color.z) * L.directional.brightness;
+    if (dirEnabled && tid == FWD_TILE - 1) {                       // Lighting.hlsl:334-345: Wi = normalize(-dir), radiance = color * brightness
+        SDir d;
+        d.wi = normalize_u_generic(f3(-L.directional.lightDirection.x, -L.directional.lightDirection.y, -L.directional.lightDirection.z));
+        d.radiance = f3(L.directional.color.x, L.directional.color.y, L.directional.color.z) * L.directional.brightness;
+        d.pad0 = d.pad1 = 0.0f;
+        *sDir = d;
     }
+    __syncthreads();                                              // lights staged, mbarriers initialised
+    const bool rot = P.sinB != 0.0f || P.cosB != 1.0f;           // uniform: yaw offset 0 is the common case
 
-    const int x = blockIdx.x * FWD_BX + threadIdx.x;
-    if (x >= P.width) return;
-    const int rowStep = gridDim.y * FWD_BY;
-    int ry = blockIdx.y * FWD_BY + threadIdx.y;
-    if (ry >= P.rows) return;
-    // software prefetch: the next row's G-buffer texels are requested before the current pixel is shaded
-    float4 pa = ld_stream(P.pos.row(P.rowBegin + ry) + x);
-    float4 nr = ld_stream(P.nrm.row(P.rowBegin + ry) + x);
-    float4 am = ld_stream(P.alb.row(P.rowBegin + ry) + x);
-    for (; ry < P.rows; ry += rowStep) {
-        const int y = P.rowBegin + ry;
-        const int ryn = ry + rowStep;
-        const bool more = ryn < P.rows;
-        float4 paN = pa, nrN = nr, amN = am;
-        if (FWD_PREFETCH && more) {
-            paN = ld_stream(P.pos.row(P.rowBegin + ryn) + x);
-            nrN = ld_stream(P.nrm.row(P.rowBegin + ryn) + x);
-            amN = ld_stream(P.alb.row(P.rowBegin + ryn) + x);
+    int st = 0; uint32_t use = 0;                                 // stage of the current tile, completed uses of that stage
+    const int x = x0 + tid;
+    for (int row = (int)blockIdx.y; row < P.rows; row += rowStep) {
+        if (tid == 0) {                                           // request the tile FWD_AHEAD iterations ahead
+            const int ps = st + FWD_AHEAD;
+            if (ps < FWD_STAGES) request(row + FWD_AHEAD * rowStep, ps, use);
+            else request(row + FWD_AHEAD * rowStep, ps - FWD_STAGES, use + 1u);
         }
+        mbar_wait(fullBar(st), use & 1u);                         // this tile has landed
+        const int y = P.rowBegin + row;
+        const uint32_t texel = stage0 + (uint32_t)st * stageBytes + (uint32_t)tid * 16u;
+        if (x < P.width) {
+            Px s;
+            float roughness;
+            {
+                const float4 pa = lds128(texel), nr = lds128(texel + FWD_TILE * 16u);
+                s.P = xyz(pa);
+                s.nrmTexel = texel + FWD_TILE * 16u;
+                const float3 Ns = xyz(nr);
+                roughness = nr.w;
+                const float3 Vv = P.cam - s.P;
+                s.V = Vv * rsqrt_fast(dot(Vv, Vv));                  // ForwardLighting.hlsl:285
+                const float n2 = dot(Ns, Ns), rn = rsqrt_fast(n2);
+                s.Nn = Ns * rn;                                      // BRDF.hlsl:167
+                s.nsLen = n2 * rn;
+            }
+            const float a = roughness * roughness;
+            s.a2 = __fmul_rn(a, a); s.a2m1 = __fsub_rn(s.a2, 1.0f);  // no contraction: feeds the exact t
+            const float rp1 = roughness + 1.0f;
+            s.k = (rp1 * rp1) * 0.125f; s.omk = 1.0f - s.k;
+            s.nv = dot(s.Nn, s.V);
+            s.NdotV = saturate(s.nv);
+            s.gV = s.NdotV * rcp_fast(fmaf(s.NdotV, s.omk, s.k) + 0.0001f);
 
-        Px s;
-        s.P = xyz(pa);
-        s.nrmTexel = P.nrm.row(y) + x;
-        const float3 Ns = xyz(nr), albedo = xyz(am);
-        const float roughness = nr.w, metalness = am.w, ao = pa.w;
-        const float3 Vv = P.cam - s.P;
-        s.V = Vv * rsqrt_fast(dot(Vv, Vv));                      // ForwardLighting.hlsl:285
-        const float n2 = dot(Ns, Ns), rn = rsqrt_fast(n2);
-        s.Nn = Ns * rn;                                          // BRDF.hlsl:167
-        s.nsLen = n2 * rn;
-        const float a = roughness * roughness;
-        s.a2 = __fmul_rn(a, a); s.a2m1 = __fsub_rn(s.a2, 1.0f);  // no contraction: feeds the exact t
-        const float rp1 = roughness + 1.0f;
-        s.k = (rp1 * rp1) * 0.125f; s.omk = 1.0f - s.k;
-        s.nv = dot(s.Nn, s.V);
-        s.NdotV = saturate(s.nv);
-        s.gV = s.NdotV * rcp_fast(fmaf(s.NdotV, s.omk, s.k) + 0.0001f);
-
-        float3 I = albedo * ao;                                  // ForwardLighting.hlsl:290-293
-        if (P.hasEmissive) {
-            const float4 em = ld_stream(P.emi.row(y) + x);
-            I += xyz(em) * em.w;
-        }
-
-#if !FWD_IBL_LAST
-        // ---- environment map (Lighting.hlsl:360-395, BRDF.hlsl:196-207) ----
-        {
-            const float3 F0 = lerp(f3(0.04f), albedo, metalness);
-            const float NdotVs = saturate(s.nsLen * s.nv);       // saturate(dot(s.N, V))
-            const bool rot = P.sinB != 0.0f || P.cosB != 1.0f;       // uniform: yaw offset 0 is the common case
-            const float3 Nr = rot ? f3(Ns.x * P.cosB - Ns.z * P.sinB, Ns.y, Ns.x * P.sinB + Ns.z * P.cosB) : Ns;
-            const float3 diffIrr = sample_cube(P.diff, Nr, 0);
-            float3 specCol = f3(0.0f); float2 sb = make_float2(0.0f, 0.0f);
-            if (!P.diffuseOnly) {
+            // ---- environment taps (Lighting.hlsl:360-395): addresses + loads; where they are issued is FWD_IBL_EARLY ----
+            CubeLoad ldD, ldS; LutLoad ldL;
+            auto issue_spec = [&](float3 Ns) {
                 const float3 R0 = reflect(-s.V, Ns);
                 const float3 R = rot ? f3(R0.x * P.cosB - R0.z * P.sinB, R0.y, R0.x * P.sinB + R0.z * P.cosB) : R0;
-                const int mip = (int)(roughness * (float)P.maxLod);
-                specCol = sample_cube(P.spec, R, mip);
-                sb = sample_lut(P.lut, NdotVs, roughness);
+                ldS = cube_issue<(FWD_IBL_EARLY >= 1)>(P.spec, R, (int)(roughness * (float)P.maxLod));
+                ldL = lut_issue<(FWD_IBL_EARLY >= 1)>(P.lut, saturate(s.nsLen * s.nv), roughness);   // (saturate(dot(s.N, V)), roughness)
+            };
+            auto issue_diff = [&](float3 Ns) {
+                const float3 Nr = rot ? f3(Ns.x * P.cosB - Ns.z * P.sinB, Ns.y, Ns.x * P.sinB + Ns.z * P.cosB) : Ns;
+                ldD = cube_issue<(FWD_IBL_EARLY >= 2)>(P.diff, Nr, 0);
+            };
+            if (FWD_IBL_EARLY >= 1) {
+                const float3 Ns = xyz(lds128(texel + FWD_TILE * 16u));
+                if (!P.diffuseOnly) issue_spec(Ns);
+                if (FWD_IBL_EARLY >= 2) issue_diff(Ns);
             }
-            const float fr = pow5(1.0f - NdotVs);                // FresnelWithRoughness, BRDF.hlsl:152-156
-            const float omr = 1.0f - roughness;
-            const float3 Ks = f3(fmaf(fmaxf(omr, F0.x) - F0.x, fr, F0.x),
-                                 fmaf(fmaxf(omr, F0.y) - F0.y, fr, F0.y),
-                                 fmaf(fmaxf(omr, F0.z) - F0.z, fr, F0.z));
-            const float om = 1.0f - metalness;
-            I.x += (1.0f - Ks.x) * om * (diffIrr.x * albedo.x) + specCol.x * fmaf(Ks.x, sb.x, sb.y);
-            I.y += (1.0f - Ks.y) * om * (diffIrr.y * albedo.y) + specCol.y * fmaf(Ks.y, sb.x, sb.y);
-            I.z += (1.0f - Ks.z) * om * (diffIrr.z * albedo.z) + specCol.z * fmaf(Ks.z, sb.x, sb.y);
-        }
 
-#endif
-        Acc acc; acc.a = f3(0.0f); acc.b = f3(0.0f); acc.c = f3(0.0f);
-        // ---- point lights, then unshadowed point casters (Lighting.hlsl:308-322; PSMain :310-313,321-340) ----
-        // two at a time: the two bodies are independent, so their dependency chains interleave
-        int i = 0;
-        for (; FWD_PAIR && i + 1 < numPoint; i += 2) {
-            const SPoint l0 = sPoint[i], l1 = sPoint[i + 1];
-            shade_point(s, acc, P.cam, l0);
-            shade_point(s, acc, P.cam, l1);
-        }
-        for (; i < numPoint; ++i) shade_point(s, acc, P.cam, sPoint[i]);
-        // ---- spot lights, then unshadowed spot casters (Lighting.hlsl:57-73,323-333) ----
-        for (int k = 0; k < numSpot; ++k) {
-            const SSpot l = sSpot[k];
-            const float3 Lv = l.pos - s.P;
-            const float d2 = dot_u(Lv, Lv);
-            const float invD = rsqrt_fast(fmaxf(d2, 1e-30f));
-            const float theta = acosf(fminf(fmaxf(-dot(Lv, l.dir) * invD, -1.0f), 1.0f));   // pixel direction = -Wi
-            float inten = 1.0f - (theta - l.inner) * l.invCone;
-            inten = theta > l.outer ? 0.0f : (theta <= l.inner ? 1.0f : inten);
-            shade_light(s, acc, P.cam, Lv, d2, invD, inten * l.brightness * (invD * invD), l.color);
-        }
-        // ---- directional (PSMain :360-377 with ShadowingFactor = 1) ----
-        if (dirEnabled) shade_light(s, acc, P.cam, dirWi, 1.0f, 1.0f, 1.0f, dirRadiance);
-
-        {   // F0 = lerp(0.04, albedo, metal) (BRDF.hlsl:177); K1 = (1-F0)*(1-metal)*albedo/PI (BRDF.hlsl:189-191)
-            const float3 F0 = lerp(f3(0.04f), albedo, metalness);
-            const float3 omF0 = f3(1.0f) - F0;
-            const float3 K1 = omF0 * albedo * ((1.0f - metalness) * (1.0f / PI));
-            I.x += fmaf(K1.x, acc.a.x, fmaf(omF0.x, acc.b.x, F0.x * acc.c.x));
-            I.y += fmaf(K1.y, acc.a.y, fmaf(omF0.y, acc.b.y, F0.y * acc.c.y));
-            I.z += fmaf(K1.z, acc.a.z, fmaf(omF0.z, acc.b.z, F0.z * acc.c.z));
-        }
-#if FWD_IBL_LAST
-        // ---- environment map (Lighting.hlsl:360-395, BRDF.hlsl:196-207) ----
-        {
-            const float3 F0 = lerp(f3(0.04f), albedo, metalness);
-            const float NdotVs = saturate(s.nsLen * s.nv);       // saturate(dot(s.N, V))
-            const bool rot = P.sinB != 0.0f || P.cosB != 1.0f;       // uniform: yaw offset 0 is the common case
-            const float3 Nr = rot ? f3(Ns.x * P.cosB - Ns.z * P.sinB, Ns.y, Ns.x * P.sinB + Ns.z * P.cosB) : Ns;
-            const float3 diffIrr = sample_cube(P.diff, Nr, 0);
-            float3 specCol = f3(0.0f); float2 sb = make_float2(0.0f, 0.0f);
-            if (!P.diffuseOnly) {
-                const float3 R0 = reflect(-s.V, Ns);
-                const float3 R = rot ? f3(R0.x * P.cosB - R0.z * P.sinB, R0.y, R0.x * P.sinB + R0.z * P.cosB) : R0;
-                const int mip = (int)(roughness * (float)P.maxLod);
-                specCol = sample_cube(P.spec, R, mip);
-                sb = sample_lut(P.lut, NdotVs, roughness);
+            Acc acc; acc.a = f3(0.0f); acc.b = f3(0.0f); acc.c = f3(0.0f);
+            // ---- point lights, then unshadowed point casters (Lighting.hlsl:308-322; PSMain :310-313,321-340) ----
+            for (int i = 0; i < numPoint; ++i) shade_point(s, acc, P.cam, sPoint[i]);
+            // ---- spot lights, then unshadowed spot casters (Lighting.hlsl:57-73,323-333) ----
+            for (int k = 0; k < numSpot; ++k) {
+                const SSpot l = sSpot[k];
+                const float3 Lv = l.pos - s.P;
+                const float d2 = dot_u(Lv, Lv);
+                const float invD = rsqrt_fast(fmaxf(d2, 1e-30f));
+                const float theta = acosf(fminf(fmaxf(-dot(Lv, l.dir) * invD, -1.0f), 1.0f));   // pixel direction = -Wi
+                float inten = 1.0f - (theta - l.inner) * l.invCone;
+                inten = theta > l.outer ? 0.0f : (theta <= l.inner ? 1.0f : inten);
+                shade_light(s, acc, P.cam, Lv, d2, invD, inten * l.brightness * (invD * invD), l.color);
             }
-            const float fr = pow5(1.0f - NdotVs);                // FresnelWithRoughness, BRDF.hlsl:152-156
-            const float omr = 1.0f - roughness;
-            const float3 Ks = f3(fmaf(fmaxf(omr, F0.x) - F0.x, fr, F0.x),
-                                 fmaf(fmaxf(omr, F0.y) - F0.y, fr, F0.y),
-                                 fmaf(fmaxf(omr, F0.z) - F0.z, fr, F0.z));
-            const float om = 1.0f - metalness;
-            I.x += (1.0f - Ks.x) * om * (diffIrr.x * albedo.x) + specCol.x * fmaf(Ks.x, sb.x, sb.y);
-            I.y += (1.0f - Ks.y) * om * (diffIrr.y * albedo.y) + specCol.y * fmaf(Ks.y, sb.x, sb.y);
-            I.z += (1.0f - Ks.z) * om * (diffIrr.z * albedo.z) + specCol.z * fmaf(Ks.z, sb.x, sb.y);
-        }
+            // ---- directional (PSMain :360-377 with ShadowingFactor = 1) ----
+            if (dirEnabled) { const SDir d = *sDir; shade_light(s, acc, P.cam, d.wi, 1.0f, 1.0f, 1.0f, d.radiance); }
 
-#endif
-        {   // :380 — one STG.128 per destination; peer destinations are mapped NVLink addresses (fused compute + gather)
-            const float4 o = make_float4(I.x, I.y, I.z, roughness);
-            for (int k = 0; k < P.nOut; ++k) st_stream(P.outs[k].row(P.dstRowOffset + y) + x, o);
+            if (FWD_IBL_EARLY < 2) {
+                const float3 Ns = xyz(lds128(texel + FWD_TILE * 16u));
+                if (FWD_IBL_EARLY < 1 && !P.diffuseOnly) issue_spec(Ns);
+                issue_diff(Ns);
+            }
+
+            // ---- the rest of the G-buffer texel comes out of the stage only now ----
+            const float4 am = lds128(texel + 2u * FWD_TILE * 16u);
+            const float3 albedo = xyz(am);
+            const float metalness = am.w;
+            const float ao = lds32(texel + 12u);                     // the ambient factor rides in position.w
+            float3 I = albedo * ao;                                  // ForwardLighting.hlsl:290-293
+            if (P.hasEmissive) {
+                const float4 em = lds128(texel + 3u * FWD_TILE * 16u);
+                I += xyz(em) * em.w;
+            }
+            const float3 F0 = lerp(f3(0.04f), albedo, metalness);    // BRDF.hlsl:177
+            {   // K1 = (1-F0)*(1-metal)*albedo/PI (BRDF.hlsl:189-191)
+                const float3 omF0 = f3(1.0f) - F0;
+                const float3 K1 = omF0 * albedo * ((1.0f - metalness) * (1.0f / PI));
+                I.x += fmaf(K1.x, acc.a.x, fmaf(omF0.x, acc.b.x, F0.x * acc.c.x));
+                I.y += fmaf(K1.y, acc.a.y, fmaf(omF0.y, acc.b.y, F0.y * acc.c.y));
+                I.z += fmaf(K1.z, acc.a.z, fmaf(omF0.z, acc.b.z, F0.z * acc.c.z));
+            }
+            {   // ---- EnvironmentBRDF (BRDF.hlsl:196-207) on the gathered taps ----
+                float3 specCol = f3(0.0f); float2 sb = make_float2(0.0f, 0.0f);
+                if (!P.diffuseOnly) { specCol = cube_finish(ldS); sb = lut_finish(ldL); }
+                const float3 diffIrr = cube_finish(ldD);
+                const float fr = pow5(1.0f - saturate(s.nsLen * s.nv));   // FresnelWithRoughness(saturate(dot(s.N, V))), BRDF.hlsl:152-156
+                const float omr = 1.0f - roughness;
+                const float3 Ks = f3(fmaf(fmaxf(omr, F0.x) - F0.x, fr, F0.x),
+                                     fmaf(fmaxf(omr, F0.y) - F0.y, fr, F0.y),
+                                     fmaf(fmaxf(omr, F0.z) - F0.z, fr, F0.z));
+                const float om = 1.0f - metalness;
+                I.x += (1.0f - Ks.x) * om * (diffIrr.x * albedo.x) + specCol.x * fmaf(Ks.x, sb.x, sb.y);
+                I.y += (1.0f - Ks.y) * om * (diffIrr.y * albedo.y) + specCol.y * fmaf(Ks.y, sb.x, sb.y);
+                I.z += (1.0f - Ks.z) * om * (diffIrr.z * albedo.z) + specCol.z * fmaf(Ks.z, sb.x, sb.y);
+            }
+            {   // :380 — one STG.128 per destination; peer destinations are mapped NVLink addresses (fused compute + gather)
+                const float4 o = make_float4(I.x, I.y, I.z, roughness);
+                if (MULTI) { for (int k = 0; k < P.nOut; ++k) st_stream(P.outs[k].row(P.dstRowOffset + y) + x, o); }
+                else st_stream_hint(P.outs[0].row(P.dstRowOffset + y) + x, o, l2_evict_first_policy());
+            }
         }
-        if (FWD_PREFETCH) { pa = paN; nr = nrN; am = amN; }
-        else if (more) {
-            pa = ld_stream(P.pos.row(P.rowBegin + ryn) + x);
-            nr = ld_stream(P.nrm.row(P.rowBegin + ryn) + x);
-            am = ld_stream(P.alb.row(P.rowBegin + ryn) + x);
-        }
+        mbar_arrive(emptyBar(st));                               // this thread is done with the stage
+        if (++st == FWD_STAGES) { st = 0; ++use; }
     }
 }
 
@@ -458,9 +624,9 @@ uint64_t padded_texels(int res, int mips) {
 }
 bool cube_desc_ok(const VqCubemap& c) {
     return c.ptr && c.res >= 1 && c.mips >= 1 && c.mips <= 16 && (c.res >> (c.mips - 1)) >= 1 &&
-           padded_texels(c.res, c.mips) < (1ull << 31);
+           padded_texels(c.res, c.mips) < (1ull << 30);
 }
-// builds the bordered sampling copy of `c` into `dst` (padded_texels() float4s) on `stream`
+// builds the sampling copy of `c` into `dst` (padded_texels() records of 32 bytes) on `stream`
 int pad_cube(const VqCubemap& c, float4* dst, cudaStream_t stream) {
     const uint32_t total = (uint32_t)padded_texels(c.res, c.mips);
     unsigned blocks = (total + 255u) / 256u;
@@ -477,6 +643,16 @@ void fill_cube_view(const VqCubemap& c, const float4* padded, CubeV& v) {
     }
 }
 bool same_cube(const VqCubemap& a, const VqCubemap& b) { return a.ptr == b.ptr && a.res == b.res && a.mips == b.mips; }
+bool same_image(const VqImage& a, const VqImage& b) { return a.ptr == b.ptr && a.width == b.width && a.height == b.height && a.pitch_bytes == b.pitch_bytes; }
+size_t lut_footprint_bytes(const VqImage& lut) { return (size_t)(lut.width + 1) * (size_t)(lut.height + 1) * 32; }
+// builds the footprint copy of the BRDF LUT into `dst` on `stream`
+int footprint_lut(const VqImage& lut, float4* dst, cudaStream_t stream) {
+    const uint32_t total = (uint32_t)(lut.width + 1) * (uint32_t)(lut.height + 1);
+    unsigned blocks = (total + 255u) / 256u;
+    if (blocks > 148u * 16u) blocks = 148u * 16u;
+    lut_footprint_kernel<<<blocks, 256, 0, stream>>>((const float2*)lut.ptr, (int)(lut.pitch_bytes / 8), lut.width, lut.height, dst);
+    return vq_check_launch("lut_footprint");
+}
 
 int ensure_bytes(void** ptr, size_t* have, size_t need) {
     if (*have >= need && *ptr) return VQ_OK;
@@ -530,35 +706,48 @@ int vq_forward_launch_multi(VqContext* ctx, const VqPerFrameData* pf, const VqPe
     if (!P.diffuseOnly) {
         VQ_REQUIRE(cube_desc_ok(env->irradiance_specular), "bad cubemap descriptor (irradiance_specular)");
         VQ_REQUIRE(vq_image_ok(env->brdf_lut, 8), "bad BRDF LUT descriptor");
-        P.lut.p = (const float2*)env->brdf_lut.ptr; P.lut.w = env->brdf_lut.width; P.lut.h = env->brdf_lut.height;
-        P.lut.pitch2 = (int)(env->brdf_lut.pitch_bytes / 8);
+        VQ_REQUIRE(env->brdf_lut.width <= 8192 && env->brdf_lut.height <= 8192, "BRDF LUT larger than 8192^2");
+        P.lut.w = env->brdf_lut.width; P.lut.h = env->brdf_lut.height;
     }
     // bordered sampling copies: from the prepared environment when it matches, else padded now on this stream
     int rc;
     const bool prepared = ctx->env_valid && same_cube(ctx->env_key.irradiance_diffuse, env->irradiance_diffuse) &&
-                          (P.diffuseOnly || same_cube(ctx->env_key.irradiance_specular, env->irradiance_specular));
+                          (P.diffuseOnly || (same_cube(ctx->env_key.irradiance_specular, env->irradiance_specular) &&
+                                             same_image(ctx->env_key.brdf_lut, env->brdf_lut) && ctx->env_lut));
     if (prepared) {
         fill_cube_view(env->irradiance_diffuse, (const float4*)ctx->env_diff, P.diff);
-        if (!P.diffuseOnly) fill_cube_view(env->irradiance_specular, (const float4*)ctx->env_spec, P.spec);
+        if (!P.diffuseOnly) {
+            fill_cube_view(env->irradiance_specular, (const float4*)ctx->env_spec, P.spec);
+            P.lut.q = (const float4*)ctx->env_lut;
+        }
     } else {
-        rc = ensure_bytes(&ctx->tmp_diff, &ctx->tmp_diff_bytes, padded_texels(env->irradiance_diffuse.res, env->irradiance_diffuse.mips) * 16); if (rc) return rc;
+        rc = ensure_bytes(&ctx->tmp_diff, &ctx->tmp_diff_bytes, padded_texels(env->irradiance_diffuse.res, env->irradiance_diffuse.mips) * 32); if (rc) return rc;
         rc = pad_cube(env->irradiance_diffuse, (float4*)ctx->tmp_diff, stream); if (rc) return rc;
         fill_cube_view(env->irradiance_diffuse, (const float4*)ctx->tmp_diff, P.diff);
         if (!P.diffuseOnly) {
-            rc = ensure_bytes(&ctx->tmp_spec, &ctx->tmp_spec_bytes, padded_texels(env->irradiance_specular.res, env->irradiance_specular.mips) * 16); if (rc) return rc;
+            rc = ensure_bytes(&ctx->tmp_spec, &ctx->tmp_spec_bytes, padded_texels(env->irradiance_specular.res, env->irradiance_specular.mips) * 32); if (rc) return rc;
             rc = pad_cube(env->irradiance_specular, (float4*)ctx->tmp_spec, stream); if (rc) return rc;
             fill_cube_view(env->irradiance_specular, (const float4*)ctx->tmp_spec, P.spec);
+            rc = ensure_bytes(&ctx->tmp_lut, &ctx->tmp_lut_bytes, lut_footprint_bytes(env->brdf_lut)); if (rc) return rc;
+            rc = footprint_lut(env->brdf_lut, (float4*)ctx->tmp_lut, stream); if (rc) return rc;
+            P.lut.q = (const float4*)ctx->tmp_lut;
         }
     }
     P.rowBegin = row_begin; P.rows = row_end - row_begin; P.width = W;
 
-    // grid.x covers a row in 64-pixel tiles; grid.y strides 4-row groups: about 3 resident CTAs per SM, several waves
-    const unsigned gx = (unsigned)((W + FWD_BX - 1) / FWD_BX);
-    unsigned gy = (unsigned)((P.rows + FWD_BY - 1) / FWD_BY);
-    const unsigned targetBlocks = (unsigned)ctx->sm_count * (unsigned)FWD_MIN_BLOCKS * 4u;
-    const unsigned gyCap = (targetBlocks + gx - 1) / gx;
-    if (gy > gyCap) gy = gyCap < 1 ? 1 : gyCap;
-    forward_kernel<<<dim3(gx, gy), dim3(FWD_BX, FWD_BY), 0, stream>>>(P);
+    // persistent grid: x = the row's 128-pixel tiles, y = row groups striding the rows; about FWD_CTAS_PER_SM CTAs per SM
+    const unsigned gx = (unsigned)((W + FWD_TILE - 1) / FWD_TILE);
+    unsigned gy = (unsigned)(ctx->sm_count * FWD_CTAS_PER_SM) / gx;
+    if (gy < 1) gy = 1;
+    if (gy > (unsigned)P.rows) gy = (unsigned)P.rows;
+    VQ_REQUIRE(gy <= 65535u, "frame too tall for the launch grid");
+    const int nPl = P.hasEmissive ? 4 : 3;
+    const size_t smem = (size_t)FWD_STAGES * nPl * FWD_TILE * 16 + 2 * FWD_STAGES * sizeof(uint64_t) +
+                       sizeof(SDir) + (size_t)(L.numPointLights + L.numPointCasters) * sizeof(SPoint) +
+                       (size_t)(L.numSpotLights + L.numSpotCasters) * sizeof(SSpot);
+    static_assert(sizeof(SPoint) == 32 && sizeof(SSpot) == 64 && sizeof(SDir) == 32, "shared light records are 16-byte multiples");
+    if (n_outs > 1) forward_kernel<true><<<dim3(gx, gy), FWD_TILE, smem, stream>>>(P);
+    else forward_kernel<false><<<dim3(gx, gy), FWD_TILE, smem, stream>>>(P);
     return vq_check_launch("forward_lighting");
 }
 
@@ -583,22 +772,27 @@ extern "C" int vq_forward_lighting_multi(VqContext* ctx, const VqPerFrameData* p
     return vq_forward_launch_multi(ctx, pf, pv, gb, env, outs, n_outs, dst_row_offset, row_begin, row_end, (cudaStream_t)stream);
 }
 
-// The IBL cubemaps are sampled from bordered copies (see CubeV). vq_environment_prepare builds them once and
-// registers them in the context: the analogue of the RENDER_TARGET -> PIXEL_SHADER_RESOURCE transition the engine
+// The IBL cubemaps and the BRDF LUT are sampled from footprint-friendly copies (see CubeV, LutV).
+// vq_environment_prepare builds them once and registers them in the context: the analogue of the RENDER_TARGET -> PIXEL_SHADER_RESOURCE transition the engine
 // records after prefiltering (EnvironmentMapRendering.cpp:466-472). Call it again whenever the maps' contents change.
-// Without it vq_forward_lighting re-pads the cubes on every call (always correct, ~15 us slower at 512^2 x 9 mips).
+// Without it vq_forward_lighting rebuilds the copies on every call (always correct, slower: see tools/perf_forward.py).
 extern "C" int vq_environment_prepare(VqContext* ctx, const VqEnvironmentMaps* env, void* stream) {
     int rc = vq_enter(ctx); if (rc) return rc;
     VQ_REQUIRE(env, "env is null");
     VQ_REQUIRE(cube_desc_ok(env->irradiance_diffuse), "bad cubemap descriptor (irradiance_diffuse)");
     ctx->env_valid = 0;
-    rc = ensure_bytes(&ctx->env_diff, &ctx->env_diff_bytes, padded_texels(env->irradiance_diffuse.res, env->irradiance_diffuse.mips) * 16); if (rc) return rc;
+    rc = ensure_bytes(&ctx->env_diff, &ctx->env_diff_bytes, padded_texels(env->irradiance_diffuse.res, env->irradiance_diffuse.mips) * 32); if (rc) return rc;
     rc = pad_cube(env->irradiance_diffuse, (float4*)ctx->env_diff, (cudaStream_t)stream); if (rc) return rc;
     ctx->env_key = *env;
     if (env->irradiance_specular.ptr) {
         VQ_REQUIRE(cube_desc_ok(env->irradiance_specular), "bad cubemap descriptor (irradiance_specular)");
-        rc = ensure_bytes(&ctx->env_spec, &ctx->env_spec_bytes, padded_texels(env->irradiance_specular.res, env->irradiance_specular.mips) * 16); if (rc) return rc;
+        rc = ensure_bytes(&ctx->env_spec, &ctx->env_spec_bytes, padded_texels(env->irradiance_specular.res, env->irradiance_specular.mips) * 32); if (rc) return rc;
         rc = pad_cube(env->irradiance_specular, (float4*)ctx->env_spec, (cudaStream_t)stream); if (rc) return rc;
+    }
+    if (env->brdf_lut.ptr) {
+        VQ_REQUIRE(vq_image_ok(env->brdf_lut, 8) && env->brdf_lut.width <= 8192 && env->brdf_lut.height <= 8192, "bad BRDF LUT descriptor");
+        rc = ensure_bytes(&ctx->env_lut, &ctx->env_lut_bytes, lut_footprint_bytes(env->brdf_lut)); if (rc) return rc;
+        rc = footprint_lut(env->brdf_lut, (float4*)ctx->env_lut, (cudaStream_t)stream); if (rc) return rc;
     }
     ctx->env_valid = 1;
     return VQ_OK;

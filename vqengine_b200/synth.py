@@ -289,3 +289,36 @@ def surface_inputs(width: int, height: int, n_materials: int, seed: int = SEED_B
     if ssao:
         planes.append(np.ascontiguousarray(rng.uniform(0.2, 1.0, (height, width, 1)).astype(np.float32)))
     return planes
+
+
+def sky_view_proj(yaw: float, pitch: float, fov_y: float, aspect: float, near: float = 0.1, far: float = 1000.0):
+    """SceneView.EnvironmentMapViewProj (Scene.cpp:573-584): a camera at the origin rotated by yaw (about +Y) and pitch
+    (about +X), times a left-handed D3D perspective projection (XMMatrixPerspectiveFovLH), row-vector convention
+    (v' = v * M). Returns (view_proj, inverse) as float64 4x4 row-major arrays; the caller rounds to fp32."""
+    cy, sy, cp, sp = np.cos(yaw), np.sin(yaw), np.cos(pitch), np.sin(pitch)
+    rot_y = np.array([[cy, 0, -sy, 0], [0, 1, 0, 0], [sy, 0, cy, 0], [0, 0, 0, 1]], dtype=np.float64)
+    rot_x = np.array([[1, 0, 0, 0], [0, cp, sp, 0], [0, -sp, cp, 0], [0, 0, 0, 1]], dtype=np.float64)
+    world = rot_x @ rot_y                      # camera orientation (row vectors: pitch first, then yaw)
+    view = np.linalg.inv(world)
+    h = 1.0 / np.tan(0.5 * fov_y)
+    w = h / aspect
+    q = far / (far - near)
+    proj = np.array([[w, 0, 0, 0], [0, h, 0, 0], [0, 0, q, 1], [0, 0, -near * q, 0]], dtype=np.float64)
+    vp = view @ proj
+    return vp, np.linalg.inv(vp)
+
+
+def smooth_hdri(width: int, height: int, seed: int = SEED_BASE + 6, peak: float = 4.0) -> np.ndarray:
+    """Band-limited equirect radiance (no per-texel noise): sums of low-order sinusoids in (phi, theta), >= 0, alpha 1.
+    Used where a single bilinear sample is compared at 1e-4: texel-to-texel contrast stays ~1e-2."""
+    rng = np.random.default_rng(seed)
+    v, u = np.meshgrid((np.arange(height) + 0.5) / height, (np.arange(width) + 0.5) / width, indexing="ij")
+    img = np.zeros((height, width, 4), dtype=np.float64)
+    for c in range(3):
+        acc = np.full((height, width), 1.0)
+        for _ in range(4):
+            ku, kv = rng.integers(1, 4), rng.integers(1, 3)
+            acc += 0.2 * np.sin(2 * np.pi * ku * u + rng.uniform(0, 6.28)) * np.cos(np.pi * kv * v + rng.uniform(0, 6.28))
+        img[..., c] = acc * (peak / 2.0)
+    img[..., 3] = 1.0
+    return np.ascontiguousarray(np.clip(img, 0.0, None).astype(np.float32))
