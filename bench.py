@@ -214,6 +214,7 @@ def frame_format_passes(ctx, vq, torch, envk, peak):
     out = {}
     hw, hh = 4096, 2048
     src = torch.from_numpy(synth.hdri(hw, hh)).cuda()
+    data = ctx.hdr_save_host(src)                               # warm-up (allocations, worker threads, lazy module load)
     t0 = time.perf_counter(); data = ctx.hdr_save_host(src); t_save = time.perf_counter() - t0
     info, offs = vq.hdr_parse(data)
     n = len(data)
@@ -228,12 +229,18 @@ def frame_format_passes(ctx, vq, torch, envk, peak):
     out["hdr_decode_4096x2048"] = {"config": f".hdr file {n / 1e6:.1f} MB (RLE, {n / hw / hh:.2f} B/texel) -> RGBA32F + max luminance, bit-exact vs stbi_loadf",
                                    "ms": round(ms, 4), "Mtexels_per_s": round(hw * hh / ms / 1e3, 1),
                                    "algorithmic_GBps": round(nb / ms / 1e6, 1), "hbm_frac": round(nb / ms / 1e6 / peak, 3)}
+    ctx.hdr_load_host(data, img)                                # warm-up
     t0 = time.perf_counter(); ctx.hdr_load_host(data, img); t_load = time.perf_counter() - t0
     out["hdr_decode_4096x2048"]["e2e_host_file_to_device_image_ms"] = round(t_load * 1e3, 2)
     ms = time_gpu(torch, lambda: ctx.hdr_encode_rgbe(src), 10)
     nb = hw * hh * 20
     out["hdr_encode_rgbe_4096x2048"] = {"ms": round(ms, 4), "algorithmic_GBps": round(nb / ms / 1e6, 1), "hbm_frac": round(nb / ms / 1e6 / peak, 3),
                                         "e2e_device_image_to_host_file_ms": round(t_save * 1e3, 2)}
+    half = torch.empty((hh // 2, hw // 2, 4), dtype=torch.float32, device="cuda")
+    ms = time_gpu(torch, lambda: ctx.image_resize(src, half), 10)
+    nb = hw * hh * 16 + (hw // 2) * hh * 32 + (hw // 2) * (hh // 2) * 16      # read in, write + read the intermediate, write out
+    out["image_resize_4096x2048_to_2048x1024"] = {"config": "stbir_resize_float (Mitchell, separable, edge clamp), bit-exact; includes the host-side table build + upload",
+                                                   "ms": round(ms, 4), "algorithmic_GBps": round(nb / ms / 1e6, 1), "hbm_frac": round(nb / ms / 1e6 / peak, 3)}
     w, h = W4K, H4K
     _, inv = synth.sky_view_proj(0.7, 0.1, 1.0, w / h)
     scene = torch.zeros((h, w, 4), dtype=torch.float32, device="cuda")
@@ -337,10 +344,46 @@ def ibl_specular_strong_scaling(ctx, vq, torch, dist, rank, world, hdri_w=4096, 
     if dist: dist.all_reduce(t, op=dist.ReduceOp.MAX)
     ms, ms_compute = float(t[0]), float(t[1])
     n_tex = vq.cubemap_texel_count(res, mips)
+    # ---- fused compute + gather: the prefilter kernels store every texel straight into all ranks' cubemaps over NVLink
+    #      (peer pointers from torch symmetric memory); one device-side barrier ends the step ----
+    fused = None
+    if dist is not None and world > 1:
+        try:
+            import torch.distributed._symmetric_memory as symm
+            sym_t = symm.empty((n_tex, 4), dtype=torch.float32, device=torch.device("cuda", torch.cuda.current_device()))
+            hdl = symm.rendezvous(sym_t, dist.group.WORLD)
+            peers = [hdl.get_buffer(r, (n_tex, 4), torch.float32) for r in range(world)]
+            order = [rank] + [r for r in range(world) if r != rank]
+            cubes = [vq.cubemap_of(peers[r], res, mips) for r in order]
+            split_rows = [(r0 + rank * k, r0 + (rank + 1) * k) for (_, r0, k, _) in plan.split]
+            repl_rows = [(r0, r0 + rows) for (_, r0, rows, _) in plan.replicated]
+
+            def fused_step():
+                for rb, re in split_rows:
+                    ctx.specular_prefilter_multi(pyr, cubes, 512, rb, re)       # my block of every split mip -> all ranks
+                for rb, re in repl_rows:
+                    ctx.specular_prefilter(pyr, cubes[0], 512, rb, re)          # tiny mips: every rank computes its own copy
+                hdl.barrier()
+
+            fused_step(); torch.cuda.synchronize(); dist.barrier()
+            same = bool(torch.equal(sym_t, cube_t))
+            f0, f1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            f0.record()
+            for _ in range(iters):
+                fused_step()
+            f1.record(); torch.cuda.synchronize()
+            tf = torch.tensor([f0.elapsed_time(f1) / iters], dtype=torch.float64, device="cuda")
+            dist.all_reduce(tf, op=dist.ReduceOp.MAX)
+            fused = {"ms": round(float(tf[0]), 3), "texels_per_s": round(n_tex / float(tf[0]) * 1e3), "equals_nccl_allgather": same,
+                     "how": "vq_specular_prefilter_multi: every prefiltered texel is stored into all ranks' cubemaps (symmetric-memory peer pointers, NVLink P2P) while the SMs integrate; one device-side barrier"}
+            del sym_t, peers
+        except Exception as ex:   # symmetric memory unavailable on this box: keep the NCCL numbers
+            fused = {"error": repr(ex)[:300]}
     del pyr_t, cube_t
     return {"config": f"{hdri_w}x{hdri_h} HDRI -> {res}^2 x6 x{mips} mips, 512 samples; strong scaling over {world} GPU(s): every mip split into {world} equal row blocks (tiny mips replicated) + ONE all-gather of the 33.5 MB cubemap",
             "ms": round(ms, 3), "texels_per_s": round(n_tex / ms * 1e3), "ms_compute_only": round(ms_compute, 3),
-            "rows_per_rank": sum(b - a for a, b in my_rows), "replicated_mips": [m for (m, _, _, _) in plan.replicated]}
+            "rows_per_rank": sum(b - a for a, b in my_rows), "replicated_mips": [m for (m, _, _, _) in plan.replicated],
+            "fused_p2p": fused}
 
 
 # ------------------------------------------------------------------------------------------------

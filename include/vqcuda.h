@@ -179,6 +179,12 @@ VQ_API int vq_diffuse_irradiance(VqContext* ctx, const VqDiffuseIrradianceParams
  * ------------------------------------------------------------------------------------------ */
 VQ_API int vq_specular_prefilter(VqContext* ctx, VqPyramid hdri, VqCubemap out,
                                  int num_samples, int row_begin, int row_end, void* stream);
+/* K3 fused with the gather of row blocks (multi-GPU strong scaling): every texel of rows [row_begin,row_end) is stored into
+ * each of the n_outs (<= 8) cubemaps of identical shape — the local one first, then the other ranks' buffers mapped into
+ * this process (CUDA IPC / torch symmetric memory). The stores travel over NVLink while the SMs keep integrating; the caller
+ * provides the cross-rank barrier after the kernel(s). */
+VQ_API int vq_specular_prefilter_multi(VqContext* ctx, VqPyramid hdri, const VqCubemap* outs, int n_outs,
+                                       int num_samples, int row_begin, int row_end, void* stream);
 
 /* ------------------------------------------------------------------------------------------
  * K4  BRDF integration LUT (split-sum scale,bias).  Replaces ComputeBRDFIntegrationLUT
@@ -344,6 +350,16 @@ VQ_API int vq_hdr_encode_rgbe(VqContext* ctx, VqImage in, void* dev_rgbe, void* 
 VQ_API int vq_hdr_pack_file(const void* host_rgbe, int width, int height, void* file, uint64_t capacity, uint64_t* size);
 /* Blocking: device fp32 image -> host file image (encode + download + pack). */
 VQ_API int vq_hdr_save_host(VqContext* ctx, VqImage in, void* host_file, uint64_t capacity, uint64_t* size);
+
+/* Image::CreateResizedImage (Image.cpp:148-190) -> stbir_resize_float(in, w, h, 0, out, W, H, 0, 4): the downsize the engine
+ * applies to a hi-res HDRI before saving the smaller .hdr (EnvironmentMap.cpp:142-209; 8k -> 4k/2k/1k). Separable
+ * Mitchell-Netravali, edge clamp, weights normalised per output sample; bit-identical to the vendored stb_image_resize
+ * v0.96. out.width <= in.width and out.height <= in.height (otherwise VQ_ERR_UNSUPPORTED). Scratch is stream-ordered. */
+VQ_API int vq_image_resize(VqContext* ctx, VqImage in, VqImage out, void* stream);
+/* HOST. The per-axis gather table vq_image_resize builds (first tap, tap count, normalised weights per output sample):
+ * out[i] = sum_{t<count[i]} weights[i*capacity_taps + t] * in[clamp(start[i]+t, 0, in_size-1)], taps in increasing order.
+ * start == NULL: only *max_taps is written. */
+VQ_API int vq_resize_axis_table(int in_size, int out_size, int* start, int* count, float* weights, int capacity_taps, int* max_taps);
 
 /* ------------------------------------------------------------------------------------------
  * SURVEY §8(f).3  The two streaming passes that complete a headless frame.

@@ -335,6 +335,7 @@ uint64_t orc_hdr_encode(const float* rgba, int w, int h, uint8_t* file, uint64_t
     if (file) std::memcpy(file, f.data(), std::min<uint64_t>(capacity, f.size()));
     return f.size();
 }
+int orc_resize_downsample(const float* in, int w, int h, float* out, int ow, int oh) { return ResizeFloat4_Downsample(in, w, h, out, ow, oh); }
 void orc_linear_to_rgbe(const float* rgba, int n, uint8_t* rgbe) {
     for (int i = 0; i < n; ++i) LinearToRgbe(rgbe + 4 * (size_t)i, rgba + 4 * (size_t)i);
 }

@@ -12,6 +12,8 @@
 #define STB_IMAGE_WRITE_IMPLEMENTATION
 #define STBI_WRITE_NO_STDIO
 #include "stb/stb_image_write.h"
+#define STB_IMAGE_RESIZE_IMPLEMENTATION
+#include "stb/stb_image_resize.h"
 #include <cstdint>
 #include <cstring>
 #include <vector>
@@ -38,6 +40,11 @@ uint64_t stbref_write_hdr(const float* rgba, int w, int h, uint8_t* file, uint64
     if (!stbi_write_hdr_to_func(sink, &v, w, h, 4, rgba)) return 0;
     if (file) std::memcpy(file, v.data(), v.size() < capacity ? v.size() : capacity);
     return v.size();
+}
+
+// Image::CreateResizedImage (Image.cpp:148-190): stbir_resize_float(in, w, h, 0, out, ow, oh, 0, 4); returns stb's rc (1 = ok)
+int stbref_resize_float(const float* in, int w, int h, float* out, int ow, int oh) {
+    return stbir_resize_float(in, w, h, 0, out, ow, oh, 0, 4);
 }
 
 }  // extern "C"

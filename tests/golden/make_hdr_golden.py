@@ -37,3 +37,15 @@ for name, (w, h) in {"rle_48x6": (48, 6), "rle_200x3": (200, 3), "flat_5x4": (5,
     np.save(os.path.join(HERE, f"hdr_{name}_src.npy"), src)
 json.dump(meta, open(os.path.join(HERE, "hdr_golden.json"), "w"), indent=1)
 print("wrote", list(meta))
+
+# ---- stbir_resize_float golden (Image::CreateResizedImage): input regenerated from the seed, output bits from the reference ----
+rz = {}
+rng2 = np.random.default_rng(0x5EED0000 + 22)
+for name, (w, h, ow, oh) in {"64x32_to_32x16": (64, 32, 32, 16), "100x37_to_41x13": (100, 37, 41, 13), "96x48_to_12x6": (96, 48, 12, 6)}.items():
+    src = (rng2.random((h, w, 4), dtype=np.float32) ** 2 * 9.0).astype(np.float32)
+    ref = orc.resize_downsample(src, ow, oh, "ref")               # the reference's stbir_resize_float
+    rz[name] = {"w": w, "h": h, "ow": ow, "oh": oh, "source_f32_sha256": hashlib.sha256(src.tobytes()).hexdigest(),
+                "resized_f32_sha256": hashlib.sha256(ref.tobytes()).hexdigest(),
+                "resized_first_texels_hex": [f"{x:08x}" for x in ref.reshape(-1).view(np.uint32)[:12]]}
+json.dump(rz, open(os.path.join(HERE, "resize_golden.json"), "w"), indent=1)
+print("wrote", list(rz))

@@ -338,3 +338,17 @@ def apply_reflections(scene, reflection, bounding_volumes=None, threads=0):
     lib().orc_apply_reflections(_p(scene), _p(refl), _p(bv) if bv is not None else None, C.c_int(w), C.c_int(h),
                                 C.c_int(threads or (os.cpu_count() or 1)))
     return scene
+
+
+def resize_downsample(img, ow: int, oh: int, which: str = "oracle"):
+    """Image::CreateResizedImage (stbir_resize_float, 4 channels) for ow <= w, oh <= h -> [oh, ow, 4] float32"""
+    a = _f(img)
+    h, w = a.shape[:2]
+    out = np.zeros((oh, ow, 4), dtype=np.float32)
+    if which == "ref":
+        rc = stb_ref().stbref_resize_float(_p(a), C.c_int(w), C.c_int(h), _p(out), C.c_int(ow), C.c_int(oh))
+        assert rc == 1
+    else:
+        rc = lib().orc_resize_downsample(_p(a), C.c_int(w), C.c_int(h), _p(out), C.c_int(ow), C.c_int(oh))
+        assert rc == 0
+    return out

@@ -193,3 +193,41 @@ def test_frame_passes_on_pitched_images(ctx, vq, orc):
     big = torch.zeros((h, wp, 4), dtype=torch.float32, device="cuda")
     big[:, :w] = dev(a)
     assert ctx.hdr_save_host(big[:, :w]) == orc.hdr_encode(a)
+
+
+# ---- Image::CreateResizedImage (stbir_resize_float) ------------------------------------------------------------------
+@pytest.mark.parametrize("w,h,ow,oh", [(64, 32, 32, 16), (100, 37, 41, 13), (33, 17, 33, 9), (16, 16, 16, 16), (128, 64, 16, 8),
+                                       (50, 50, 49, 1), (257, 3, 100, 3), (9, 9, 1, 1), (1024, 512, 256, 128)])
+def test_image_resize_bit_exact(ctx, orc, w, h, ow, oh):
+    rng = np.random.default_rng(w * 5 + h)
+    a = (rng.random((h, w, 4), dtype=np.float32) * 5).astype(np.float32)
+    out = torch.zeros((oh, ow, 4), dtype=torch.float32, device="cuda")
+    ctx.image_resize(dev(a), out)
+    assert np.array_equal(_bits(host(out)), _bits(orc.resize_downsample(a, ow, oh)))
+
+
+def test_image_resize_engine_sizes_and_errors(ctx, vq, orc):
+    """the engine's case (EnvironmentMap.cpp:159-166): 2:1 equirect down by 2x / 4x; size-independent properties at
+    4096x2048 -> 2048x1024 plus a bit-exact band against the oracle; upsizing is rejected"""
+    from vqengine_b200 import synth
+    w, h = 4096, 2048
+    src = synth.hdri(w, h)
+    d = dev(src)
+    half = torch.zeros((h // 2, w // 2, 4), dtype=torch.float32, device="cuda")
+    ctx.image_resize(d, half)
+    quarter = torch.zeros((h // 4, w // 4, 4), dtype=torch.float32, device="cuda")
+    ctx.image_resize(d, quarter)
+    torch.cuda.synchronize()
+    assert bool(torch.isfinite(half).all()) and bool((half[..., 3] - 1.0).abs().max() <= 2e-6)     # alpha = 1 stays 1 (weights sum to 1)
+    assert abs(float(half.mean()) - float(d.mean())) <= 1e-3 * float(d.mean())
+    assert abs(float(quarter.mean()) - float(d.mean())) <= 1e-3 * float(d.mean())
+    ref = orc.resize_downsample(src, w // 2, h // 2)
+    assert np.array_equal(_bits(host(half)), _bits(ref))
+    with pytest.raises(vq.VqError):
+        ctx.image_resize(half, torch.zeros((h, w, 4), dtype=torch.float32, device="cuda"))
+    # pitched source and destination
+    big = torch.zeros((40, 96, 4), dtype=torch.float32, device="cuda"); a = _rand_image(80, 40, seed=4); big[:, :80] = dev(a)
+    outb = torch.full((20, 64, 4), -3.0, dtype=torch.float32, device="cuda")
+    ctx.image_resize(big[:, :80], outb[:, :40])
+    got = host(outb)
+    assert np.array_equal(_bits(got[:, :40]), _bits(orc.resize_downsample(a, 40, 20))) and (got[:, 40:] == -3.0).all()

@@ -15,7 +15,7 @@ def test_headless_smoke_run():
     r = subprocess.run([EXE, "-Test", "-TestFrames=20", "-W=320", "-H=180"], capture_output=True, text=True, timeout=300)
     print(r.stdout, r.stderr)
     assert r.returncode == 0, (r.returncode, r.stderr)
-    assert "20 frames OK" in r.stdout
+    assert "20 frames OK" in r.stdout and ".hdr file image" in r.stdout
 
 
 def test_host_layer_exports_reference_shaped_api():
@@ -25,5 +25,7 @@ def test_host_layer_exports_reference_shaped_api():
     syms = subprocess.run(["nm", "-DC", so], capture_output=True, text=True).stdout
     for name in ["vq::VQRenderer::RenderSceneColor", "vq::VQRenderer::RenderPostProcess", "vq::VQRenderer::PreFilterEnvironmentMap",
                  "vq::VQRenderer::LoadDefaultResources", "vq::FEnvironmentMapRenderingResources::CreateRenderingResources",
-                 "vq::FPostProcessParameters::FFSR1_EASU::UpdateEASUConstantBlock", "vq::GaussianBlurPass::RecordCommands"]:
+                 "vq::FPostProcessParameters::FFSR1_EASU::UpdateEASUConstantBlock", "vq::GaussianBlurPass::RecordCommands",
+                 "vq::FEnvironmentMapRenderingResources::CreateRenderingResourcesFromHDRFile", "vq::VQRenderer::RenderEnvironmentMap",
+                 "vq::VQRenderer::ApplyReflections", "vq::VQRenderer::SaveToHDRFileImage"]:
         assert name in syms, name

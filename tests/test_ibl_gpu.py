@@ -115,6 +115,30 @@ def test_specular_row_ranges(ctx, vq, orc):
     assert np.array_equal(host(full), host(parts))
 
 
+def test_specular_multi_destination_store(ctx, vq, orc):
+    """vq_specular_prefilter_multi: every texel of the row range lands in EVERY destination cubemap (on the GPU box the
+    extra destinations are the other ranks' buffers over NVLink; here three local buffers), bit-identical to the
+    single-destination call; rows outside the range stay untouched in all of them."""
+    w, h, res, mips = 128, 64, 16, 4
+    _, levels, d, p = _pyr(ctx, vq, orc, w, h)
+    n = vq.cubemap_texel_count(res, mips)
+    single = torch.zeros((n, 4), device="cuda")
+    ctx.specular_prefilter(p, vq.cubemap_of(single, res, mips), 128, 5, 120)
+    outs = [torch.full((n, 4), -7.0, device="cuda") for _ in range(3)]
+    ctx.specular_prefilter_multi(p, [vq.cubemap_of(o, res, mips) for o in outs], 128, 5, 120)
+    s = host(single)
+    a, b = 5 * res, None
+    written = np.zeros(n, dtype=bool)
+    from vqengine_b200 import distributed as vd
+    ta, tb = vd.specular_row_to_texel(res, mips, 5), vd.specular_row_to_texel(res, mips, 120)
+    written[ta:tb] = True
+    for o in outs:
+        ho = host(o)
+        assert np.array_equal(ho[written], s[written]) and (ho[~written] == -7.0).all()
+    with pytest.raises(vq.VqError):
+        ctx.specular_prefilter_multi(p, [vq.cubemap_of(outs[0], res, mips), vq.cubemap_of(outs[1][: vq.cubemap_texel_count(8, 3)], 8, 3)], 128)
+
+
 @pytest.mark.parametrize("w,h,samples", [(64, 64, 2048), (33, 17, 256)])
 def test_brdf_lut(ctx, vq, orc, w, h, samples):
     out = torch.zeros((h, w, 2), dtype=torch.float32, device="cuda")

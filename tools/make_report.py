@@ -46,7 +46,7 @@ ex = b1.get("extra", {})
 out.append("\n## Per-kernel table (1 GPU, 3840x2160 unless stated)\n")
 out.append("| pass | ms | algorithmic GB/s | frac of measured HBM peak | note |")
 out.append("|---|---|---|---|---|")
-out.append(f"| K1 forward PBR (4 point + 1 dir + IBL) | {b1['ms_per_step']:.4f} | {b1['roofline']['achieved']:.0f} | {b1['roofline']['frac']:.3f} | instruction-issue bound (~950 instr/pixel, ncu r01_forward_d); DRAM traffic {b1['roofline'].get('traffic')} B vs algorithmic {b1['roofline']['algorithmic_bytes_per_launch']} B |")
+out.append(f"| K1 forward PBR (4 point + 1 dir + IBL) | {b1['ms_per_step']:.4f} | {b1['roofline']['achieved']:.0f} | {b1['roofline']['frac']:.3f} | bound by the L1 data pipe (gather wavefronts, 64 %) and instruction issue (70 % active, ~880 instr/pixel): r01_forward_g_summary.txt, r01_forward_f_l1bound.txt; DRAM traffic {b1['roofline'].get('traffic')} B vs algorithmic {b1['roofline']['algorithmic_bytes_per_launch']} B |")
 names = [("spd", "K10 SPD (11 mips)"), ("blur_x", "K5 blur X"), ("blur_y", "K5 blur Y"), ("tonemap", "K6 tonemap sRGB"), ("cas", "K7 CAS"),
          ("fsr_easu_2x", "K8 EASU 4K->8K"), ("fsr_rcas_8k", "K9 RCAS @8K"), ("post_chain_4k", "post chain total (config 4)")]
 for k, label in names:
@@ -60,6 +60,24 @@ for k, label in [("ibl_specular_prefilter", "K3 specular prefilter"), ("ibl_diff
         rate = f"{e.get('texels_per_s', 0):.3e} texels/s, " if "texels_per_s" in e else ""
         rate += f"{e.get('samples_per_s', 0):.3e} samples/s" if "samples_per_s" in e else (f"{e.get('algorithmic_GBps')} GB/s" if "algorithmic_GBps" in e else "")
         out.append(f"| {label} | {e['ms']:.4f} | — | — | {e.get('config', '')}; {rate} (SFU/FP32-bound, HBM % is low by construction) |")
+out.append("\n## SURVEY 8(f) rows (1 GPU)\n")
+out.append("| pass | ms | algorithmic GB/s | frac of measured HBM peak | note |")
+out.append("|---|---|---|---|---|")
+for k, label in [("surface_producer_4k", "(f).1 surface producer 4K"), ("texture_box_mips_4096", "(f).1 RGBA8 box mips 4096^2"),
+                 ("hdr_decode_4096x2048", "(f).2 .hdr decode 4096x2048"), ("hdr_encode_rgbe_4096x2048", "(f).2 RGBE encode 4096x2048"),
+                 ("image_resize_4096x2048_to_2048x1024", "(f).2 Mitchell downsize 4096x2048 -> 2048x1024"),
+                 ("skydome_4k", "(f).3 skydome 4K"), ("apply_reflections_4k", "(f).3 ApplyReflections 4K")]:
+    if k in ex:
+        e = ex[k]
+        note = e.get("config", "")
+        for kk in ("e2e_host_file_to_device_image_ms", "e2e_device_image_to_host_file_ms"):
+            if kk in e: note += f"; {kk} = {e[kk]}"
+        out.append(f"| {label} | {e['ms']:.4f} | {e['algorithmic_GBps']:.0f} | {e['hbm_frac']:.3f} | {note} |")
+fp = [(b['n_gpus'], b["ibl_specular_prefilter_strong"].get("fused_p2p")) for b in (b2, b8) if b and "ibl_specular_prefilter_strong" in b]
+fp = [(n, f) for n, f in fp if f and "ms" in f]
+if fp:
+    out.append("\nFused compute + gather for the specular prefilter (`vq_specular_prefilter_multi`, peer stores over NVLink): "
+               + ", ".join(f"{n} GPUs {f['ms']:.3f} ms ({base / f['ms']:.2f}x vs 1 GPU, equals NCCL result: {f.get('equals_nccl_allgather')})" for n, f in fp) + ".")
 out.append("\n## Files\n")
 for f in sorted(os.listdir(P)):
     if f != "README.md":

@@ -1,5 +1,5 @@
 """GPU-box helper for profiling: builds the 4K inputs and runs the chosen pass a few times.
-usage: python tools/run_pass.py forward|post|ibl [iters]"""
+usage: python tools/run_pass.py forward|post|ibl|frame [iters]"""
 import os, sys
 import numpy as np, torch
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
@@ -39,6 +39,19 @@ elif which == "post":
         ctx.cas(vq.cas_setup(0.8, W, H, W, H), t, c)
         ctx.fsr_easu(vq.fsr_easu_con(W, H, W, H, 2 * W, 2 * H), c, e)
         ctx.fsr_rcas(vq.fsr_rcas_con(0.2), e, r)
+    torch.cuda.synchronize()
+elif which == "frame":
+    envk = bench.build_env_maps_gpu(ctx, vq, torch)
+    src = torch.from_numpy(synth.hdri(4096, 2048)).cuda()
+    data = ctx.hdr_save_host(src)
+    scene = torch.zeros((H, W, 4), dtype=torch.float32, device="cuda")
+    refl = torch.rand((H, W, 4), dtype=torch.float32, device="cuda")
+    _, inv = synth.sky_view_proj(0.7, 0.1, 1.0, W / H)
+    for _ in range(iters):
+        img, lum = ctx.hdr_decode(data)
+        ctx.hdr_encode_rgbe(src)
+        ctx.skydome(inv.astype(np.float32).reshape(16), envk["pyr"], scene)
+        ctx.apply_reflections(scene, refl)
     torch.cuda.synchronize()
 else:
     for _ in range(iters):

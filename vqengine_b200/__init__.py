@@ -171,7 +171,7 @@ ABI_SYMBOLS = [
     "vq_environment_invalidate", "vq_forward_lighting_multi",
     "vq_texture_build_mips", "vq_material_table_create", "vq_material_table_destroy", "vq_gbuffer_from_materials",
     "vq_hdr_parse", "vq_hdr_decode", "vq_hdr_load_host", "vq_hdr_encode_rgbe", "vq_hdr_pack_file", "vq_hdr_save_host",
-    "vq_skydome", "vq_apply_reflections",
+    "vq_skydome", "vq_apply_reflections", "vq_specular_prefilter_multi", "vq_image_resize", "vq_resize_axis_table",
 ]
 
 
@@ -206,6 +206,7 @@ def _load() -> C.CDLL:
     lib.vq_hdri_build_mips.argtypes = [vp, Pyramid, vp]
     lib.vq_diffuse_irradiance.argtypes = [vp, P(DiffuseIrradianceParams), Pyramid, Cubemap, C.c_int, C.c_int, vp]
     lib.vq_specular_prefilter.argtypes = [vp, Pyramid, Cubemap, C.c_int, C.c_int, C.c_int, vp]
+    lib.vq_specular_prefilter_multi.argtypes = [vp, Pyramid, P(Cubemap), C.c_int, C.c_int, C.c_int, C.c_int, vp]
     lib.vq_brdf_integration_lut.argtypes = [vp, Image, C.c_int, C.c_int, C.c_int, vp]
     lib.vq_gaussian_blur_x.argtypes = [vp, P(BlurParams), Image, Image, vp]
     lib.vq_gaussian_blur_y.argtypes = [vp, P(BlurParams), Image, Image, vp]
@@ -243,6 +244,8 @@ def _load() -> C.CDLL:
     lib.vq_hdr_encode_rgbe.argtypes = [vp, Image, vp, vp]
     lib.vq_hdr_pack_file.argtypes = [vp, C.c_int, C.c_int, vp, u64, P(u64)]
     lib.vq_hdr_save_host.argtypes = [vp, Image, vp, u64, P(u64)]
+    lib.vq_image_resize.argtypes = [vp, Image, Image, vp]
+    lib.vq_resize_axis_table.argtypes = [C.c_int, C.c_int, P(C.c_int), P(C.c_int), P(f32), C.c_int, P(C.c_int)]
     lib.vq_skydome.argtypes = [vp, P(Matrix), Pyramid, P(Image), Image, C.c_int, C.c_int, vp]
     lib.vq_apply_reflections.argtypes = [vp, Image, Image, P(Image), vp]
     return lib
@@ -331,6 +334,18 @@ def hdr_pack_file(rgbe) -> bytes:
     out = np.empty(n.value, dtype=np.uint8)
     _check(lib.vq_hdr_pack_file(a.ctypes.data, w, h, out.ctypes.data, n.value, C.byref(n)))
     return out.tobytes()
+
+
+def resize_axis_table(in_size: int, out_size: int):
+    """-> (start int32 [out], count int32 [out], weights float32 [out, max_taps]) of one axis of vq_image_resize"""
+    import numpy as np
+    mt = C.c_int(0)
+    _check(lib.vq_resize_axis_table(in_size, out_size, None, None, None, 0, C.byref(mt)))
+    start = np.zeros(out_size, dtype=np.int32); count = np.zeros(out_size, dtype=np.int32)
+    w = np.zeros((out_size, mt.value), dtype=np.float32)
+    _check(lib.vq_resize_axis_table(in_size, out_size, start.ctypes.data_as(C.POINTER(C.c_int)), count.ctypes.data_as(C.POINTER(C.c_int)),
+                                    w.ctypes.data_as(C.POINTER(f32)), mt.value, C.byref(mt)))
+    return start, count, w
 
 
 # ---- descriptors from torch tensors ------------------------------------------------------------
@@ -473,6 +488,10 @@ class Context:
         _check(lib.vq_hdr_save_host(self._h, image_of(src), out.ctypes.data, cap, C.byref(n)))
         return out[:n.value].tobytes()
 
+    def image_resize(self, src, dst, stream=None):
+        """Image::CreateResizedImage (stbir_resize_float): dst is [H', W', 4] with H' <= H, W' <= W"""
+        _check(lib.vq_image_resize(self._h, image_of(src), image_of(dst), _stream_ptr(stream)))
+
     # SURVEY 8(f).3: skydome + reflection composite
     def skydome(self, inv_view_proj, pyr: Pyramid, scene, normal_mask=None, row_begin=0, row_end=None, stream=None):
         m = Matrix((f32 * 16)(*[float(x) for x in inv_view_proj]))
@@ -500,6 +519,13 @@ class Context:
         _check(lib.vq_specular_prefilter(self._h, pyr, cube, num_samples, row_begin,
                                          cubemap_row_count(cube.res, cube.mips) if row_end is None else row_end,
                                          _stream_ptr(stream)))
+
+    def specular_prefilter_multi(self, pyr: Pyramid, cubes, num_samples=512, row_begin=0, row_end=None, stream=None):
+        """cubes: list of Cubemap descriptors of identical shape (local first, then the peers' mapped buffers)"""
+        arr = (Cubemap * len(cubes))(*cubes)
+        _check(lib.vq_specular_prefilter_multi(self._h, pyr, arr, len(cubes), num_samples, row_begin,
+                                               cubemap_row_count(cubes[0].res, cubes[0].mips) if row_end is None else row_end,
+                                               _stream_ptr(stream)))
 
     def brdf_integration_lut(self, out, num_samples=2048, row_begin=0, row_end=None, stream=None):
         o = image_of(out, 2)

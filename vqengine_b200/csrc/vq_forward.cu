@@ -15,6 +15,10 @@
 
 using namespace vq;
 
+#ifndef FWD_BACKOFF
+#define FWD_BACKOFF 128        // ns the producer thread sleeps between polls of an empty[] barrier (0: spin)
+#endif
+
 namespace {
 
 
@@ -310,7 +314,9 @@ __device__ __forceinline__ void mbar_wait_backoff(uint32_t bar, uint32_t parity)
         asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}"
                      : "=r"(done) : "r"(bar), "r"(parity) : "memory");
         if (done) break;
-        __nanosleep(128);
+#if FWD_BACKOFF
+        __nanosleep(FWD_BACKOFF);
+#endif
     }
 }
 __device__ __forceinline__ uint64_t l2_evict_first_policy() {
@@ -343,18 +349,18 @@ __device__ __forceinline__ void st_stream_hint(float4* p, float4 v, uint64_t pol
 // normal and the emissive texel are (re-)read from the stage after it, which is what lets the kernel run at
 // <= 80 registers with the HBM latency fully hidden behind the previous tiles' shading.
 // A/B on B200 at 4K: profiles/r01_forward_variants.txt.
-constexpr int FWD_TILE = 128;
+#ifndef FWD_TILE_PX
+#define FWD_TILE_PX 128
+#endif
+constexpr int FWD_TILE = FWD_TILE_PX;
 #ifndef FWD_STAGES
 #define FWD_STAGES 4           // shared-memory stages
 #endif
 #ifndef FWD_AHEAD
 #define FWD_AHEAD 2            // tiles requested ahead of the one being shaded (< FWD_STAGES): the stage a request
 #endif                         // reuses was released FWD_STAGES-FWD_AHEAD iterations ago, so thread 0 rarely waits
-#ifndef FWD_IBL_EARLY
-#define FWD_IBL_EARLY 0        // 0: gather the environment taps after the light loop; 1: specular cube + LUT before it
-#endif                         // (24 registers in flight, latency hidden by the lights); 2: the diffuse cube as well
 #ifndef FWD_CTAS_PER_SM
-#define FWD_CTAS_PER_SM 5
+#define FWD_CTAS_PER_SM 6
 #endif
 
 static_assert(FWD_AHEAD >= 1 && FWD_AHEAD < FWD_STAGES, "the lookahead must leave at least one stage for the tile being shaded");
@@ -374,26 +380,29 @@ __device__ __forceinline__ CubeTap cube_tap(const CubeV& c, float3 dir, int mip)
     t.off = c.mipOffset[mip] + (uint32_t)(face * (P * P) + j0 * P + i0);
     return t;
 }
-// A gather is split into "issue" (address + the 256-bit loads, kept where they are written: volatile) and "finish"
-// (the lerps), so that the loads can be put in flight before the light loop and consumed after it.
-template <bool PINNED>
-__device__ __forceinline__ F8 ldg256_issue(const float4* p) {
+// A gather is split into "issue" (address + the 256-bit loads) and "finish" (the lerps) so that the loads of several
+// gathers can be put in flight before the first one is consumed.
+#ifndef FWD_L2_KEEP
+#define FWD_L2_KEEP 0          // 1: gathers carry an L2 evict_last hint (side data should outlive the streaming G-buffer)
+#endif
+__device__ __forceinline__ F8 ldg256_issue(const float4* p) {      // 32-byte aligned, read-only path (LDG.E.256)
     F8 r;
-    if (PINNED)
-        asm volatile("ld.global.nc.v8.f32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
-                     : "=f"(r.a.x), "=f"(r.a.y), "=f"(r.a.z), "=f"(r.a.w), "=f"(r.b.x), "=f"(r.b.y), "=f"(r.b.z), "=f"(r.b.w) : "l"(p));
-    else   // the compiler may schedule it (gathers issued after the light loop: nothing to pin them to)
-        asm("ld.global.nc.v8.f32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
-            : "=f"(r.a.x), "=f"(r.a.y), "=f"(r.a.z), "=f"(r.a.w), "=f"(r.b.x), "=f"(r.b.y), "=f"(r.b.z), "=f"(r.b.w) : "l"(p));
+#if FWD_L2_KEEP
+    uint64_t pol; asm("createpolicy.fractional.L2::evict_last.b64 %0, 1.0;" : "=l"(pol));
+    asm("ld.global.nc.L2::cache_hint.v8.f32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8], %9;"
+        : "=f"(r.a.x), "=f"(r.a.y), "=f"(r.a.z), "=f"(r.a.w), "=f"(r.b.x), "=f"(r.b.y), "=f"(r.b.z), "=f"(r.b.w) : "l"(p), "l"(pol));
+#else
+    asm("ld.global.nc.v8.f32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
+        : "=f"(r.a.x), "=f"(r.a.y), "=f"(r.a.z), "=f"(r.a.w), "=f"(r.b.x), "=f"(r.b.y), "=f"(r.b.z), "=f"(r.b.w) : "l"(p));
+#endif
     return r;
 }
 struct CubeLoad { F8 r0, r1; float fx, fy; };                     // rows j0 and j0+1: {t(i0), t(i0+1)} each
-template <bool PINNED>
 __device__ __forceinline__ CubeLoad cube_issue(const CubeV& c, float3 dir, int mip) {
     const CubeTap t = cube_tap(c, dir, mip);
     const float4* p = c.p + 2u * t.off;
     CubeLoad L;
-    L.r0 = ldg256_issue<PINNED>(p); L.r1 = ldg256_issue<PINNED>(p + 2 * t.P);
+    L.r0 = ldg256_issue(p); L.r1 = ldg256_issue(p + 2 * t.P);
     L.fx = t.fx; L.fy = t.fy;
     return L;
 }
@@ -402,14 +411,13 @@ __device__ __forceinline__ float3 cube_finish(const CubeLoad& L) {
     return lerp(top, bot, L.fy);
 }
 struct LutLoad { F8 q; float fx, fy; };
-template <bool PINNED>
 __device__ __forceinline__ LutLoad lut_issue(const LutV& l, float u, float v) {   // bilinear, CLAMP
     const float x = fmaf(u, (float)l.w, -0.5f), y = fmaf(v, (float)l.h, -0.5f);
     const float x0 = floorf(x), y0 = floorf(y);
     LutLoad L;
     L.fx = x - x0; L.fy = y - y0;
     const int cx = min(max((int)x0 + 1, 0), l.w), cy = min(max((int)y0 + 1, 0), l.h);
-    L.q = ldg256_issue<PINNED>(l.q + 2u * (uint32_t)(cy * (l.w + 1) + cx));
+    L.q = ldg256_issue(l.q + 2u * (uint32_t)(cy * (l.w + 1) + cx));
     return L;
 }
 __device__ __forceinline__ float2 lut_finish(const LutLoad& L) {
@@ -533,24 +541,6 @@ __global__ void __launch_bounds__(FWD_TILE, FWD_CTAS_PER_SM) forward_kernel(cons
             s.NdotV = saturate(s.nv);
             s.gV = s.NdotV * rcp_fast(fmaf(s.NdotV, s.omk, s.k) + 0.0001f);
 
-            // ---- environment taps (Lighting.hlsl:360-395): addresses + loads; where they are issued is FWD_IBL_EARLY ----
-            CubeLoad ldD, ldS; LutLoad ldL;
-            auto issue_spec = [&](float3 Ns) {
-                const float3 R0 = reflect(-s.V, Ns);
-                const float3 R = rot ? f3(R0.x * P.cosB - R0.z * P.sinB, R0.y, R0.x * P.sinB + R0.z * P.cosB) : R0;
-                ldS = cube_issue<(FWD_IBL_EARLY >= 1)>(P.spec, R, (int)(roughness * (float)P.maxLod));
-                ldL = lut_issue<(FWD_IBL_EARLY >= 1)>(P.lut, saturate(s.nsLen * s.nv), roughness);   // (saturate(dot(s.N, V)), roughness)
-            };
-            auto issue_diff = [&](float3 Ns) {
-                const float3 Nr = rot ? f3(Ns.x * P.cosB - Ns.z * P.sinB, Ns.y, Ns.x * P.sinB + Ns.z * P.cosB) : Ns;
-                ldD = cube_issue<(FWD_IBL_EARLY >= 2)>(P.diff, Nr, 0);
-            };
-            if (FWD_IBL_EARLY >= 1) {
-                const float3 Ns = xyz(lds128(texel + FWD_TILE * 16u));
-                if (!P.diffuseOnly) issue_spec(Ns);
-                if (FWD_IBL_EARLY >= 2) issue_diff(Ns);
-            }
-
             Acc acc; acc.a = f3(0.0f); acc.b = f3(0.0f); acc.c = f3(0.0f);
             // ---- point lights, then unshadowed point casters (Lighting.hlsl:308-322; PSMain :310-313,321-340) ----
             for (int i = 0; i < numPoint; ++i) shade_point(s, acc, P.cam, sPoint[i]);
@@ -568,10 +558,23 @@ __global__ void __launch_bounds__(FWD_TILE, FWD_CTAS_PER_SM) forward_kernel(cons
             // ---- directional (PSMain :360-377 with ShadowingFactor = 1) ----
             if (dirEnabled) { const SDir d = *sDir; shade_light(s, acc, P.cam, d.wi, 1.0f, 1.0f, 1.0f, d.radiance); }
 
-            if (FWD_IBL_EARLY < 2) {
+            // ---- environment taps (Lighting.hlsl:360-395). Order tuned on B200 (profiles/r01_forward_variants.txt): the two
+            //      diffuse-cube loads go out first and fly while the specular address math runs; then the specular cube
+            //      and the LUT. Issuing all five before the light loop (40 registers in flight) or all five together
+            //      after it costs occupancy / spills and measured slower. ----
+            float3 specCol = f3(0.0f), diffIrr; float2 sb = make_float2(0.0f, 0.0f);
+            {
                 const float3 Ns = xyz(lds128(texel + FWD_TILE * 16u));
-                if (FWD_IBL_EARLY < 1 && !P.diffuseOnly) issue_spec(Ns);
-                issue_diff(Ns);
+                const float3 Nr = rot ? f3(Ns.x * P.cosB - Ns.z * P.sinB, Ns.y, Ns.x * P.sinB + Ns.z * P.cosB) : Ns;
+                const CubeLoad ldD = cube_issue(P.diff, Nr, 0);
+                if (!P.diffuseOnly) {
+                    const float3 R0 = reflect(-s.V, Ns);
+                    const float3 R = rot ? f3(R0.x * P.cosB - R0.z * P.sinB, R0.y, R0.x * P.sinB + R0.z * P.cosB) : R0;
+                    const CubeLoad ldS = cube_issue(P.spec, R, (int)(roughness * (float)P.maxLod));
+                    const LutLoad ldL = lut_issue(P.lut, saturate(s.nsLen * s.nv), roughness);   // (saturate(dot(s.N, V)), roughness)
+                    specCol = cube_finish(ldS); sb = lut_finish(ldL);
+                }
+                diffIrr = cube_finish(ldD);
             }
 
             // ---- the rest of the G-buffer texel comes out of the stage only now ----
@@ -593,9 +596,6 @@ __global__ void __launch_bounds__(FWD_TILE, FWD_CTAS_PER_SM) forward_kernel(cons
                 I.z += fmaf(K1.z, acc.a.z, fmaf(omF0.z, acc.b.z, F0.z * acc.c.z));
             }
             {   // ---- EnvironmentBRDF (BRDF.hlsl:196-207) on the gathered taps ----
-                float3 specCol = f3(0.0f); float2 sb = make_float2(0.0f, 0.0f);
-                if (!P.diffuseOnly) { specCol = cube_finish(ldS); sb = lut_finish(ldL); }
-                const float3 diffIrr = cube_finish(ldD);
                 const float fr = pow5(1.0f - saturate(s.nsLen * s.nv));   // FresnelWithRoughness(saturate(dot(s.N, V))), BRDF.hlsl:152-156
                 const float omr = 1.0f - roughness;
                 const float3 Ks = f3(fmaf(fmaxf(omr, F0.x) - F0.x, fr, F0.x),

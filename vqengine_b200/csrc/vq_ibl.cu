@@ -129,6 +129,7 @@ __device__ __forceinline__ float radical_inverse_vdc(uint32_t bits) {      // Sh
 
 struct SpecArgs {
     PyrV hdri; float4* out;      // out already offset to this mip's face 0
+    float4* peers[7]; int nPeers; // further destinations (the other ranks' cubemaps, NVLink-mapped), same offset: fused gather
     int n;                       // face edge of this mip
     int rowBegin, texels;        // rows are flattened face*n + row inside this mip
     float roughness; float dimX, dimY; int numSamples;
@@ -159,6 +160,7 @@ __global__ void __launch_bounds__(IBL_THREADS) specular_mip0_kernel(const __grid
         o = make_float4(a0 / d, a1 / d, a2 / d, 1.0f);
     }
     A.out[(size_t)fr * A.n + px] = o;
+    for (int k = 0; k < A.nPeers; ++k) A.peers[k][(size_t)fr * A.n + px] = o;
 }
 
 __global__ void __launch_bounds__(IBL_THREADS) specular_prefilter_kernel(const __grid_constant__ SpecArgs A) {
@@ -218,7 +220,9 @@ __global__ void __launch_bounds__(IBL_THREADS) specular_prefilter_kernel(const _
         acc.x = warp_sum(acc.x); acc.y = warp_sum(acc.y); acc.z = warp_sum(acc.z); wsum = warp_sum(wsum);
         if (lane == 0) {
             const float d = fmaxf(wsum, 0.0001f);
-            A.out[(size_t)fr * A.n + px] = make_float4(acc.x / d, acc.y / d, acc.z / d, 1.0f);
+            const float4 o = make_float4(acc.x / d, acc.y / d, acc.z / d, 1.0f);
+            A.out[(size_t)fr * A.n + px] = o;
+            for (int k = 0; k < A.nPeers; ++k) A.peers[k][(size_t)fr * A.n + px] = o;
         }
     }
 }
@@ -330,12 +334,15 @@ extern "C" int vq_diffuse_irradiance(VqContext* ctx, const VqDiffuseIrradiancePa
     return vq_check_launch("diffuse_irradiance");
 }
 
-extern "C" int vq_specular_prefilter(VqContext* ctx, VqPyramid hd, VqCubemap out, int num_samples,
-                                     int row_begin, int row_end, void* stream) {
-    int rc = vq_enter(ctx); if (rc) return rc;
+static int specular_launch(VqContext* ctx, VqPyramid hd, const VqCubemap* outs, int n_outs, int num_samples,
+                           int row_begin, int row_end, cudaStream_t stream) {
+    VQ_REQUIRE(outs && n_outs >= 1 && n_outs <= 8, "1..8 destination cubemaps");
+    const VqCubemap out = outs[0];
     VQ_REQUIRE(pyr_ok(hd), "bad HDRI pyramid descriptor");
     VQ_REQUIRE(out.ptr && out.res >= 2 && out.mips >= 2 && out.mips <= 16 && (out.res >> (out.mips - 1)) >= 1, "bad specular cubemap descriptor");
     VQ_REQUIRE((out.res >> (out.mips - 1)) % 2 == 0 || (out.res >> (out.mips - 1)) == 1, "every mip needs an even edge (pole texel)");
+    for (int k = 1; k < n_outs; ++k)
+        VQ_REQUIRE(outs[k].ptr && outs[k].res == out.res && outs[k].mips == out.mips, "every destination cubemap must have the same shape");
     VQ_REQUIRE(num_samples >= 1 && num_samples <= 8192, "num_samples out of range");
     const int totalRows = vq_cubemap_row_count(out.res, out.mips);
     VQ_REQUIRE(row_begin >= 0 && row_end <= totalRows && row_begin <= row_end, "row range out of bounds");
@@ -347,7 +354,10 @@ extern "C" int vq_specular_prefilter(VqContext* ctx, VqPyramid hd, VqCubemap out
         if (b < e) {
             SpecArgs A;
             A.hdri = make_pyr(hd);
-            A.out = (float4*)out.ptr + vq_cubemap_offset(out.res, m, 0);
+            const uint64_t mipOff = vq_cubemap_offset(out.res, m, 0);
+            A.out = (float4*)out.ptr + mipOff;
+            A.nPeers = n_outs - 1;
+            for (int k = 0; k < 7; ++k) A.peers[k] = k + 1 < n_outs ? (float4*)outs[k + 1].ptr + mipOff : nullptr;
             A.n = n; A.rowBegin = b - mipRow0; A.texels = (e - b) * n;
             A.roughness = (float)m / (float)(out.mips - 1);          // EnvironmentMapRendering.cpp:432
             A.dimX = (float)hd.width; A.dimY = (float)hd.height;     // EnvironmentMapRendering.cpp:433-434
@@ -355,18 +365,33 @@ extern "C" int vq_specular_prefilter(VqContext* ctx, VqPyramid hd, VqCubemap out
             const size_t smem = (size_t)num_samples * sizeof(float4);
             if (smem > 48 * 1024) VQ_CUDA_OK(cudaFuncSetAttribute(specular_prefilter_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
             if (A.roughness == 0.0f) {
-                specular_mip0_kernel<<<(A.texels + IBL_THREADS - 1) / IBL_THREADS, IBL_THREADS, 0, (cudaStream_t)stream>>>(A);
+                specular_mip0_kernel<<<(A.texels + IBL_THREADS - 1) / IBL_THREADS, IBL_THREADS, 0, stream>>>(A);
             } else {
                 int blocks = (A.texels + IBL_WARPS - 1) / IBL_WARPS;
                 const int cap = ctx->sm_count * 8;
                 if (blocks > cap) blocks = cap;
-                specular_prefilter_kernel<<<blocks, IBL_THREADS, smem, (cudaStream_t)stream>>>(A);
+                specular_prefilter_kernel<<<blocks, IBL_THREADS, smem, stream>>>(A);
             }
-            rc = vq_check_launch("specular_prefilter"); if (rc) return rc;
+            int rc = vq_check_launch("specular_prefilter"); if (rc) return rc;
         }
         mipRow0 += rows;
     }
     return VQ_OK;
+}
+
+extern "C" int vq_specular_prefilter(VqContext* ctx, VqPyramid hd, VqCubemap out, int num_samples,
+                                     int row_begin, int row_end, void* stream) {
+    int rc = vq_enter(ctx); if (rc) return rc;
+    return specular_launch(ctx, hd, &out, 1, num_samples, row_begin, row_end, (cudaStream_t)stream);
+}
+
+// K3 fused with the gather of the row blocks (multi-GPU): every prefiltered texel is stored into ALL n_outs cubemaps —
+// the local one first, then the other ranks' buffers mapped into this process (NVLink P2P) — while the SMs keep
+// integrating (16 bytes of stores per 512-sample texel: the transfer hides completely behind the math).
+extern "C" int vq_specular_prefilter_multi(VqContext* ctx, VqPyramid hd, const VqCubemap* outs, int n_outs, int num_samples,
+                                           int row_begin, int row_end, void* stream) {
+    int rc = vq_enter(ctx); if (rc) return rc;
+    return specular_launch(ctx, hd, outs, n_outs, num_samples, row_begin, row_end, (cudaStream_t)stream);
 }
 
 extern "C" int vq_brdf_integration_lut(VqContext* ctx, VqImage out, int num_samples, int row_begin, int row_end, void* stream) {

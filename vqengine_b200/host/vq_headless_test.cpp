@@ -36,10 +36,23 @@ int main(int argc, char** argv) {
             t[0] = 0.1f + 1.2f * (1 - v) + sun; t[1] = 0.15f + 1.5f * (1 - v) + sun * 0.9f; t[2] = 0.3f + 1.9f * (1 - v) + sun * 0.7f; t[3] = 1.0f;
             t[0] *= 1.0f + 0.05f * (frand(seed) - 0.5f);
         }
+    // The engine loads its environment maps from Radiance .hdr files (Data/Textures/EnvironmentMaps via EnvironmentMaps.ini):
+    // write the synthetic panorama out as a .hdr file image through the backend (Image::SaveToDisk route) and load the
+    // environment from THAT (Image::LoadFromFile route), so the smoke run covers both ends of the on-disk format.
     vq::FEnvironmentMapRenderingResources env;
-    vq::FEnvironmentMapDescriptor desc{hdri.data(), EW, EH, 1000.0f};
     vq::FGraphicsSettings gfx; gfx.EnvironmentMapResolution = 128;
-    if (!env.CreateRenderingResources(renderer, desc, 64, gfx.EnvironmentMapResolution)) return 4;
+    {
+        vq::FTexture2D staging;
+        if (!staging.Create(EW, EH)) return 4;
+        cudaMemcpy(staging.mem.ptr, hdri.data(), hdri.size() * 4, cudaMemcpyHostToDevice);
+        const std::vector<unsigned char> file = renderer.SaveToHDRFileImage(staging.View());
+        if (file.empty()) { std::fprintf(stderr, "SaveToHDRFileImage: %s\n", vq::LastError()); return 4; }
+        if (!env.CreateRenderingResourcesFromHDRFile(renderer, file.data(), file.size(), 64, gfx.EnvironmentMapResolution)) {
+            std::fprintf(stderr, "CreateRenderingResourcesFromHDRFile: %s\n", vq::LastError()); return 4;
+        }
+        std::printf("environment map: %dx%d .hdr file image of %zu bytes, MaxContentLightLevel %d\n", env.HDRIWidth, env.HDRIHeight,
+                    file.size(), env.MaxContentLightLevel);
+    }
     if (!renderer.PreFilterEnvironmentMap(env, 0.05f)) return 5;
 
     // synthetic G-buffer
@@ -54,6 +67,7 @@ int main(int argc, char** argv) {
             nrm[o] = n[0] / l; nrm[o + 1] = n[1] / l; nrm[o + 2] = n[2] / l; nrm[o + 3] = 0.04f + 0.9f * frand(seed);
             alb[o] = 0.1f + 0.8f * frand(seed); alb[o + 1] = 0.1f + 0.8f * frand(seed); alb[o + 2] = 0.1f + 0.8f * frand(seed);
             alb[o + 3] = frand(seed) < 0.2f ? 1.0f : 0.0f;
+            if (y < H / 6) { nrm[o] = nrm[o + 1] = nrm[o + 2] = 0.0f; }       // the top band is sky: no surface, filled by the skydome pass
         }
     vq::FTexture2D gp, gn, ga;
     if (!gp.Create(W, H) || !gn.Create(W, H) || !ga.Create(W, H)) return 6;
@@ -85,6 +99,15 @@ int main(int argc, char** argv) {
     for (int f = 0; f < frames; ++f) {
         view.HDRIYawOffset = 0.01f * f;                         // the unit-test scene orbits; here the sky turns
         if (!renderer.RenderSceneColor(pCmd, view, pp, gb, env, gfx, false)) return 8;
+        {   // skyCam at the origin, yaw following the HDRI offset (Scene.cpp:573-584): view = rotY(-yaw), LH perspective 60 degrees
+            const float yaw = view.HDRIYawOffset, c = std::cos(yaw), s = std::sin(yaw);
+            const float h = 1.0f / std::tan(0.5f * 1.0472f), w = h * (float)H / (float)W, q = 1000.0f / (1000.0f - 0.1f);
+            const float viewM[16] = {c, 0, s, 0,  0, 1, 0, 0,  -s, 0, c, 0,  0, 0, 0, 1};
+            const float proj[16] = {w, 0, 0, 0,  0, h, 0, 0,  0, 0, q, 1,  0, 0, -0.1f * q, 0};
+            float vp[16];
+            for (int r = 0; r < 4; ++r) for (int k = 0; k < 4; ++k) { float a = 0; for (int j = 0; j < 4; ++j) a += viewM[4 * r + j] * proj[4 * j + k]; vp[4 * r + k] = a; }
+            if (!renderer.RenderEnvironmentMap(pCmd, vp, gb, env)) return 8;
+        }
         const VqImage* out = renderer.RenderPostProcess(pCmd, pp, false);
         if (!out) return 9;
         if (f == frames - 1 || f == 0) {

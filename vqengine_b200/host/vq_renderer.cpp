@@ -64,6 +64,25 @@ bool FEnvironmentMapRenderingResources::CreateRenderingResources(VQRenderer& Ren
            Tex_BlurTemp.Alloc((size_t)DiffuseRes * DiffuseRes * 16) &&
            Tex_IrradianceSpec.Alloc(vq_cubemap_texel_count(SpecRes, SpecMips) * 16);
 }
+bool FEnvironmentMapRenderingResources::CreateRenderingResourcesFromHDRFile(VQRenderer& Renderer, const void* pFileBytes, size_t NumBytes,
+                                                                            int DiffuseRes_, int SpecRes_) {
+    VqHdrInfo info;
+    VQ_TRY(vq_hdr_parse(pFileBytes, NumBytes, &info, nullptr), "vq_hdr_parse");          // "Error loading file" in the engine
+    HDRIWidth = info.width; HDRIHeight = info.height;
+    HDRIMips = vq_mip_level_count((uint64_t)info.width, (uint64_t)info.height);
+    DiffuseRes = DiffuseRes_; SpecRes = SpecRes_;
+    SpecMips = vq_mip_level_count((uint64_t)SpecRes_, (uint64_t)SpecRes_) - 1;           // EnvironmentMapRendering.cpp:63
+    if (!Tex_HDREnvironment.Alloc(vq_pyramid_texel_count(HDRIWidth, HDRIHeight, HDRIMips) * 16)) return false;
+    float MaxLuminance = 0.0f;
+    const VqImage level0{Tex_HDREnvironment.ptr, HDRIWidth, HDRIHeight, (size_t)HDRIWidth * 16};
+    VQ_TRY(vq_hdr_load_host(Renderer.Context(), pFileBytes, NumBytes, level0, &MaxLuminance), "vq_hdr_load_host");
+    MaxContentLightLevel = (int)MaxLuminance;
+    VQ_TRY(vq_hdri_build_mips(Renderer.Context(), HDRI(), nullptr), "vq_hdri_build_mips");
+    const size_t diffBytes = vq_cubemap_texel_count(DiffuseRes, 1) * 16;
+    return Tex_IrradianceDiff.Alloc(diffBytes) && Tex_IrradianceDiffBlurred.Alloc(diffBytes) &&
+           Tex_BlurTemp.Alloc((size_t)DiffuseRes * DiffuseRes * 16) &&
+           Tex_IrradianceSpec.Alloc(vq_cubemap_texel_count(SpecRes, SpecMips) * 16);
+}
 void FEnvironmentMapRenderingResources::DestroyRenderingResources() {
     Tex_HDREnvironment.Free(); Tex_IrradianceDiff.Free(); Tex_IrradianceDiffBlurred.Free(); Tex_BlurTemp.Free(); Tex_IrradianceSpec.Free();
 }
@@ -136,6 +155,47 @@ bool VQRenderer::RenderSceneColor(cudaStream_t pCmd, const FSceneView& SceneView
     VQ_TRY(vq_forward_lighting(mCtx, &PerFrame, &PerView, &GBuffer, &maps, mSceneColor.View(), 0, mSceneColor.height, pCmd),
            "vq_forward_lighting");
     return true;
+}
+
+// 4x4 inverse in double (row-major; the convention does not matter for an inverse), rounded to fp32 at the end
+static bool Invert4x4(const float m[16], float out[16]) {
+    double a[4][8];
+    for (int r = 0; r < 4; ++r)
+        for (int c = 0; c < 4; ++c) { a[r][c] = m[4 * r + c]; a[r][4 + c] = r == c ? 1.0 : 0.0; }
+    for (int c = 0; c < 4; ++c) {
+        int piv = c;
+        for (int r = c + 1; r < 4; ++r) if (std::fabs(a[r][c]) > std::fabs(a[piv][c])) piv = r;
+        if (std::fabs(a[piv][c]) < 1e-300) return false;
+        if (piv != c) for (int k = 0; k < 8; ++k) std::swap(a[piv][k], a[c][k]);
+        const double d = 1.0 / a[c][c];
+        for (int k = 0; k < 8; ++k) a[c][k] *= d;
+        for (int r = 0; r < 4; ++r)
+            if (r != c) { const double f = a[r][c]; if (f != 0.0) for (int k = 0; k < 8; ++k) a[r][k] -= f * a[c][k]; }
+    }
+    for (int r = 0; r < 4; ++r) for (int c = 0; c < 4; ++c) out[4 * r + c] = (float)a[r][4 + c];
+    return true;
+}
+
+bool VQRenderer::RenderEnvironmentMap(cudaStream_t pCmd, const float EnvironmentMapViewProj[16], const VqGBuffer& GBuffer,
+                                      const FEnvironmentMapRenderingResources& env) {
+    VqMatrix inv;
+    if (!Invert4x4(EnvironmentMapViewProj, inv.m)) { g_err = "EnvironmentMapViewProj is singular"; return false; }
+    const VqPyramid level0{env.Tex_HDREnvironment.ptr, env.HDRIWidth, env.HDRIHeight, 1};   // Skydome.hlsl samples mip 0 only
+    VQ_TRY(vq_skydome(mCtx, &inv, level0, &GBuffer.normal_roughness, mSceneColor.View(), 0, mSceneColor.height, pCmd), "vq_skydome");
+    return true;
+}
+
+bool VQRenderer::ApplyReflections(cudaStream_t pCmd, const VqImage& ReflectionRadiance, const VqImage* BoundingVolumes) {
+    VQ_TRY(vq_apply_reflections(mCtx, mSceneColor.View(), ReflectionRadiance, BoundingVolumes, pCmd), "vq_apply_reflections");
+    return true;
+}
+
+std::vector<unsigned char> VQRenderer::SaveToHDRFileImage(const VqImage& Image) {
+    std::vector<unsigned char> file((size_t)256 + (size_t)Image.width * Image.height * 6 + (size_t)Image.height * 8);
+    uint64_t n = 0;
+    if (vq_hdr_save_host(mCtx, Image, file.data(), file.size(), &n) != VQ_OK) { Fail("vq_hdr_save_host"); return {}; }
+    file.resize((size_t)n);
+    return file;
 }
 
 const VqImage* VQRenderer::RenderPostProcess(cudaStream_t pCmd, const FPostProcessParameters& PPParams, bool /*bHDR*/) {

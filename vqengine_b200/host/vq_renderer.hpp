@@ -119,6 +119,11 @@ struct FEnvironmentMapRenderingResources {
     int MaxContentLightLevel = 0;
     bool CreateRenderingResources(VQRenderer& Renderer, const FEnvironmentMapDescriptor& desc,
                                   int DiffuseIrradianceCubemapResolution, int SpecularMapMip0Resolution);
+    // the engine's own route: a Radiance .hdr file image (Image::LoadFromFile, Libs/VQUtils/Source/Image.cpp:88-140, then
+    // TextureManager upload). The file is decoded ON THE DEVICE straight into level 0 of the pyramid (vq_hdr_load_host);
+    // MaxContentLightLevel = Image::MaxLuminance as the engine computes it.
+    bool CreateRenderingResourcesFromHDRFile(VQRenderer& Renderer, const void* pFileBytes, size_t NumBytes,
+                                             int DiffuseIrradianceCubemapResolution, int SpecularMapMip0Resolution);
     void DestroyRenderingResources();
     int GetNumSpecularIrradianceCubemapLODLevels() const { return SpecMips; }
     VqPyramid HDRI() const { return VqPyramid{Tex_HDREnvironment.ptr, HDRIWidth, HDRIHeight, HDRIMips}; }
@@ -192,6 +197,15 @@ public:
                           const VqGBuffer& GBuffer, const FEnvironmentMapRenderingResources& env,
                           const FGraphicsSettings& GFXSettings, bool bHDR);
     const VqImage* RenderPostProcess(cudaStream_t pCmd, const FPostProcessParameters& PPParams, bool bHDR);
+    // "Draw Environment Map" (SceneRendering.cpp:1821-1850, Skydome.hlsl): fills the pixels of SceneColor that no surface
+    // covered (normal plane == 0) with the equirect HDRI seen through EnvironmentMapViewProj (row-major, row-vector
+    // convention as XMMATRIX; SceneView.EnvironmentMapViewProj, Scene.cpp:573-584). Call after RenderSceneColor.
+    bool RenderEnvironmentMap(cudaStream_t pCmd, const float EnvironmentMapViewProj[16], const VqGBuffer& GBuffer,
+                              const FEnvironmentMapRenderingResources& env);
+    // ApplyReflectionsPass::RecordCommands (ApplyReflections.hlsl:31-57): SceneColor.rgb += ReflectionRadiance.rgb
+    bool ApplyReflections(cudaStream_t pCmd, const VqImage& ReflectionRadiance, const VqImage* BoundingVolumes = nullptr);
+    // Image::SaveToDisk for .hdr (Image.cpp:192-220): returns the file image (empty on failure)
+    std::vector<unsigned char> SaveToHDRFileImage(const VqImage& Image);
 
     VqContext* Context() const { return mCtx; }
     const FTexture2D& SceneColor() const { return mSceneColor; }
