@@ -354,7 +354,8 @@ VQ_API int vq_hdr_save_host(VqContext* ctx, VqImage in, void* host_file, uint64_
 /* Image::CreateResizedImage (Image.cpp:148-190) -> stbir_resize_float(in, w, h, 0, out, W, H, 0, 4): the downsize the engine
  * applies to a hi-res HDRI before saving the smaller .hdr (EnvironmentMap.cpp:142-209; 8k -> 4k/2k/1k). Separable
  * Mitchell-Netravali, edge clamp, weights normalised per output sample; bit-identical to the vendored stb_image_resize
- * v0.96. out.width <= in.width and out.height <= in.height (otherwise VQ_ERR_UNSUPPORTED). Scratch is stream-ordered. */
+ * v0.96. out.width <= in.width and out.height <= in.height (otherwise VQ_ERR_UNSUPPORTED). The intermediate image and the gather
+ * tables live in the context (grow-only; tables are rebuilt when the size pair changes): serialise calls per context. */
 VQ_API int vq_image_resize(VqContext* ctx, VqImage in, VqImage out, void* stream);
 /* HOST. The per-axis gather table vq_image_resize builds (first tap, tap count, normalised weights per output sample):
  * out[i] = sum_{t<count[i]} weights[i*capacity_taps + t] * in[clamp(start[i]+t, 0, in_size-1)], taps in increasing order.

@@ -44,12 +44,14 @@ elif which == "frame":
     envk = bench.build_env_maps_gpu(ctx, vq, torch)
     src = torch.from_numpy(synth.hdri(4096, 2048)).cuda()
     data = ctx.hdr_save_host(src)
+    half = torch.empty((1024, 2048, 4), dtype=torch.float32, device="cuda")
     scene = torch.zeros((H, W, 4), dtype=torch.float32, device="cuda")
     refl = torch.rand((H, W, 4), dtype=torch.float32, device="cuda")
     _, inv = synth.sky_view_proj(0.7, 0.1, 1.0, W / H)
     for _ in range(iters):
         img, lum = ctx.hdr_decode(data)
         ctx.hdr_encode_rgbe(src)
+        ctx.image_resize(src, half)
         ctx.skydome(inv.astype(np.float32).reshape(16), envk["pyr"], scene)
         ctx.apply_reflections(scene, refl)
     torch.cuda.synchronize()

@@ -36,5 +36,28 @@ em = vq.EnvironmentMaps(vq.cubemap_of(diff, 8, 1), vq.cubemap_of(spec, 16, 4), v
 out = torch.zeros((40, 64, 4), device="cuda")
 ctx.forward_lighting(pf, pv, gb, em, out)
 ctx.environment_prepare(em); ctx.forward_lighting(pf, pv, gb, em, out)
+# wider frame: several column tiles + ragged last tile + more rows than the persistent grid has row groups
+planes2 = [dev(p) for p in synth.gbuffer(300, 9)]
+pf2, pv2 = synth.scene_constants(300, 9, 4)
+out2 = torch.zeros((9, 300, 4), device="cuda")
+ctx.forward_lighting(pf2, pv2, vq.GBuffer(vq.image_of(planes2[0]), vq.image_of(planes2[1]), vq.image_of(planes2[2]), vq.null_image()), em, out2)
+ctx.forward_lighting_multi(pf, pv, gb, em, [vq.image_of(out), vq.image_of(torch.zeros_like(out))], 0)
+ctx.specular_prefilter_multi(pyr, [vq.cubemap_of(spec, 16, 4), vq.cubemap_of(torch.zeros_like(spec), 16, 4)], 64)
+# SURVEY 8(f).1 (bench.surface_scene_gpu builds the mip chains with vq_texture_build_mips and a material table)
+import bench
+sc = bench.surface_scene_gpu(ctx, vq, torch, 64, 38, n_materials=3, tex_res=64)
+g4 = [torch.empty((38, 64, 4), device="cuda") for _ in range(4)]
+ctx.gbuffer_from_materials(sc["inputs"], sc["table"], 0.3, vq.GBuffer(*(vq.image_of(t) for t in g4)))
+# SURVEY 8(f).2 / (f).3
+src = dev(synth.hdri(96, 20)); src8 = dev(synth.hdri(6, 5))
+for im in (src, src8):
+    data = ctx.hdr_save_host(im)
+    dec, lum = ctx.hdr_decode(data)
+    ctx.hdr_load_host(data, torch.zeros_like(im))
+small = torch.zeros((7, 41, 4), device="cuda"); ctx.image_resize(src, small)
+_, inv = synth.sky_view_proj(0.3, 0.1, 1.0, 64 / 40)
+ctx.skydome(inv.astype(np.float32).reshape(16), pyr, out, normal_mask=planes[1])
+ctx.skydome(inv.astype(np.float32).reshape(16), pyr, out)
+ctx.apply_reflections(out, torch.rand_like(out)); ctx.apply_reflections(out, torch.rand_like(out), torch.rand_like(out))
 torch.cuda.synchronize()
 print("sanitize_small: all kernels launched, finite:", bool(torch.isfinite(out).all()))
