@@ -207,3 +207,34 @@ def test_forward_multi_destination_store(ctx, vq, orc):
         assert np.array_equal(got[h:2 * h], host(single)) and (got[:h] == 0).all() and (got[2 * h:] == 0).all()
     with pytest.raises(vq.VqError):      # destination too small for offset + tile
         ctx.forward_lighting_multi(pf, pv, gb, em, [vq.image_of(frames[0])], dst_row_offset=2 * h + 1)
+
+
+def test_forward_full_size_4k_properties(ctx, vq, orc):
+    """BASELINE full size (3840x2160, 4 point + 1 directional + IBL at 64^2 / 512^2 x9 / 1024^2): size-independent
+    properties — row tiling is bit-invariant (the multi-GPU partition), alpha passes roughness through, everything is
+    finite — plus parity against the oracle on two 12-row bands (prepared sampling copies, persistent grid with all
+    30 x 29 CTAs in play)."""
+    import bench
+    from vqengine_b200 import synth
+    envk = bench.build_env_maps_gpu(ctx, vq, torch)
+    w, h = 3840, 2160
+    planes = synth.gbuffer(w, h)
+    pf, pv = synth.scene_constants(w, h, envk["spec_mips"])
+    dpl = [dev(p) for p in planes]
+    gb = vq.GBuffer(vq.image_of(dpl[0]), vq.image_of(dpl[1]), vq.image_of(dpl[2]), vq.null_image())
+    whole = torch.zeros((h, w, 4), dtype=torch.float32, device="cuda")
+    ctx.forward_lighting(pf, pv, gb, envk["env"], whole)
+    tiled = torch.zeros_like(whole)
+    for rb, re in ((0, 541), (541, 1080), (1080, 1081), (1081, 2160)):
+        ctx.forward_lighting(pf, pv, gb, envk["env"], tiled, rb, re)
+    torch.cuda.synchronize()
+    assert torch.equal(whole, tiled)
+    assert bool(torch.isfinite(whole).all())
+    assert torch.equal(whole[..., 3], dpl[1][..., 3])
+    got = host(whole)
+    env_np = {k: host(envk[k]) for k in ("diff", "spec", "lut")}
+    for r0 in (7, 1500):
+        ref = orc.forward_lighting(pf, pv, planes, env_np["diff"], envk["diff_res"], env_np["spec"], envk["spec_res"],
+                                   envk["spec_mips"], env_np["lut"], r0, r0 + 12)
+        assert_scaled(f"forward4k rows {r0}", got[r0:r0 + 12], ref[r0:r0 + 12])
+    ctx.environment_invalidate()

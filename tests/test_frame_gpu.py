@@ -231,3 +231,15 @@ def test_image_resize_engine_sizes_and_errors(ctx, vq, orc):
     ctx.image_resize(big[:, :80], outb[:, :40])
     got = host(outb)
     assert np.array_equal(_bits(got[:, :40]), _bits(orc.resize_downsample(a, 40, 20))) and (got[:, 40:] == -3.0).all()
+
+
+def test_decode_very_wide_scanlines(ctx, orc):
+    """the widest scanlines the format can run-length encode (width < 32768): 120 KB of expanded planes per block, the
+    compressed bytes no longer fit next to them and are read from global memory (STAGED = false instantiation)"""
+    _decode_both(ctx, orc, orc.hdr_encode(_rand_image(30000, 2, seed=12)))
+    _decode_both(ctx, orc, orc.hdr_encode(_rand_image(32767, 1, seed=13)))
+    a = _rand_image(32768, 1, seed=14)                 # one texel wider: stb writes (and reads) it flat
+    data = orc.hdr_encode(a)
+    assert len(data) > 32768 * 4
+    _decode_both(ctx, orc, data)
+    assert ctx.hdr_save_host(dev(a)) == data

@@ -349,10 +349,7 @@ __device__ __forceinline__ void st_stream_hint(float4* p, float4 v, uint64_t pol
 // normal and the emissive texel are (re-)read from the stage after it, which is what lets the kernel run at
 // <= 80 registers with the HBM latency fully hidden behind the previous tiles' shading.
 // A/B on B200 at 4K: profiles/r01_forward_variants.txt.
-#ifndef FWD_TILE_PX
-#define FWD_TILE_PX 128
-#endif
-constexpr int FWD_TILE = FWD_TILE_PX;
+constexpr int FWD_TILE = 128;     // 64-pixel tiles measured 3 % slower (profiles/r01_forward_variants.txt)
 #ifndef FWD_STAGES
 #define FWD_STAGES 4           // shared-memory stages
 #endif
@@ -382,19 +379,10 @@ __device__ __forceinline__ CubeTap cube_tap(const CubeV& c, float3 dir, int mip)
 }
 // A gather is split into "issue" (address + the 256-bit loads) and "finish" (the lerps) so that the loads of several
 // gathers can be put in flight before the first one is consumed.
-#ifndef FWD_L2_KEEP
-#define FWD_L2_KEEP 0          // 1: gathers carry an L2 evict_last hint (side data should outlive the streaming G-buffer)
-#endif
 __device__ __forceinline__ F8 ldg256_issue(const float4* p) {      // 32-byte aligned, read-only path (LDG.E.256)
     F8 r;
-#if FWD_L2_KEEP
-    uint64_t pol; asm("createpolicy.fractional.L2::evict_last.b64 %0, 1.0;" : "=l"(pol));
-    asm("ld.global.nc.L2::cache_hint.v8.f32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8], %9;"
-        : "=f"(r.a.x), "=f"(r.a.y), "=f"(r.a.z), "=f"(r.a.w), "=f"(r.b.x), "=f"(r.b.y), "=f"(r.b.z), "=f"(r.b.w) : "l"(p), "l"(pol));
-#else
     asm("ld.global.nc.v8.f32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
         : "=f"(r.a.x), "=f"(r.a.y), "=f"(r.a.z), "=f"(r.a.w), "=f"(r.b.x), "=f"(r.b.y), "=f"(r.b.z), "=f"(r.b.w) : "l"(p));
-#endif
     return r;
 }
 struct CubeLoad { F8 r0, r1; float fx, fy; };                     // rows j0 and j0+1: {t(i0), t(i0+1)} each
