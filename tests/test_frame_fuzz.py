@@ -1,0 +1,110 @@
+"""CPU (-m "not gpu"): randomised agreement between the product's HOST codec half (vq_hdr_parse index builder,
+vq_hdr_pack_file run-list packer — no GPU involved) and the oracle (pinned to the reference's stb): arbitrary byte strings
+after a valid header, mutated valid files, arbitrary RGBE planes."""
+import numpy as np
+import pytest
+from hypothesis import given, settings, strategies as st, HealthCheck
+
+HEADER = b"#?RADIANCE\nFORMAT=32-bit_rle_rgbe\n\n"
+SET = dict(deadline=None, max_examples=150, suppress_health_check=[HealthCheck.function_scoped_fixture, HealthCheck.too_slow])
+
+
+def _expand_with_index(data: bytes, info, offs):
+    """what the device decoder does with the index, restated in numpy/python: -> RGBE [h, w, 4] uint8"""
+    w, h = info.width, info.height
+    buf = np.frombuffer(data, dtype=np.uint8)
+    at = lambda p: int(buf[p]) if p < buf.size else 0                      # bytes past the end read as 0
+    if info.flat:
+        out = np.zeros((h * w, 4), np.uint8)
+        for t in range(h * w):
+            out[t] = [at(info.data_offset + 4 * t + k) for k in range(4)]
+        return out.reshape(h, w, 4)
+    out = np.zeros((h, w, 4), np.uint8)
+    for j in range(h):
+        for k in range(4):
+            pos, i = int(offs[4 * j + k]), 0
+            while i < w:
+                c = at(pos)
+                if c > 128:
+                    out[j, i:i + c - 128, k] = at(pos + 1); pos += 2; i += c - 128
+                else:
+                    for z in range(c):
+                        out[j, i + z, k] = at(pos + 1 + z)
+                    pos += 1 + c; i += c
+    return out
+
+
+def _rgbe_to_float(rgbe):
+    e = rgbe[..., 3].astype(np.int32)
+    f = np.ldexp(np.float32(1.0), e - 136).astype(np.float32)
+    out = np.ones(rgbe.shape[:-1] + (4,), dtype=np.float32)
+    out[..., :3] = np.where(e[..., None] != 0, rgbe[..., :3].astype(np.float32) * f[..., None], np.float32(0.0))
+    return out
+
+
+@settings(**SET)
+@given(w=st.integers(1, 40), h=st.integers(1, 5), body=st.binary(min_size=0, max_size=700))
+def test_parse_agrees_with_oracle_on_arbitrary_bodies(vq, orc, w, h, body):
+    """any bytes after a valid header: the host index builder accepts exactly what the oracle decodes, and expanding the
+    file through the index gives the oracle's texels (flat, run-length encoded, truncated, corrupt alike)"""
+    data = HEADER + f"-Y {h} +X {w}\n".encode() + body
+    rc, ref, _ = orc.hdr_decode(data)
+    try:
+        info, offs = vq.hdr_parse(data)
+    except vq.VqError:
+        assert rc != 0
+        return
+    assert rc == 0 and (info.width, info.height) == (w, h)
+    got = _rgbe_to_float(_expand_with_index(data, info, offs))
+    assert np.array_equal(got.view(np.uint32), ref.view(np.uint32))
+
+
+@settings(**SET)
+@given(w=st.integers(8, 48), h=st.integers(1, 4), seed=st.integers(0, 2**31 - 1), nmut=st.integers(0, 4), data=st.data())
+def test_parse_agrees_with_oracle_on_mutated_files(vq, orc, w, h, seed, nmut, data):
+    """valid run-length encoded files with a few bytes flipped / the tail cut: same verdict, same texels"""
+    rng = np.random.default_rng(seed)
+    img = (rng.random((h, w, 4), dtype=np.float32) * 3).astype(np.float32)
+    img[:, : w // 2, :3] = np.float32(0.5)
+    f = bytearray(orc.hdr_encode(img))
+    for _ in range(nmut):
+        i = data.draw(st.integers(len(HEADER), len(f) - 1))
+        f[i] = data.draw(st.integers(0, 255))
+    cut = data.draw(st.integers(0, 6))
+    f = bytes(f[: len(f) - cut])
+    rc, ref, _ = orc.hdr_decode(f)
+    try:
+        info, offs = vq.hdr_parse(f)
+    except vq.VqError:
+        assert rc != 0
+        return
+    assert rc == 0
+    if (info.width, info.height) == ref.shape[1::-1] and info.width * info.height <= 4096:
+        got = _rgbe_to_float(_expand_with_index(f, info, offs))
+        assert np.array_equal(got.view(np.uint32), ref.view(np.uint32))
+
+
+@settings(**SET)
+@given(w=st.integers(1, 300), h=st.integers(1, 3), seed=st.integers(0, 2**31 - 1), mode=st.sampled_from(["noise", "runs", "mixed"]))
+def test_pack_file_equals_oracle_on_arbitrary_rgbe(vq, orc, w, h, seed, mode):
+    """the host run-list packer on arbitrary RGBE planes == the oracle's encoder fed with the decoded floats, and the
+    packed file decodes back to the same RGBE bytes"""
+    rng = np.random.default_rng(seed)
+    if mode == "noise":
+        rgbe = rng.integers(0, 256, (h, w, 4), dtype=np.uint8)
+    elif mode == "runs":
+        rgbe = np.repeat(rng.integers(0, 256, (h, (w + 6) // 7, 4), dtype=np.uint8), 7, axis=1)[:, :w]
+    else:
+        rgbe = rng.integers(0, 256, (h, w, 4), dtype=np.uint8)
+        rgbe[:, w // 3: 2 * w // 3] = rgbe[:, w // 3: w // 3 + 1]
+    # keep the texels canonical (what stbiw__linear_to_rgbe can emit), so that float -> RGBE -> float is the identity
+    rgbe = np.ascontiguousarray(rgbe)
+    mant = rgbe[..., :3].max(axis=-1)
+    rgbe[mant < 128] = 0                                      # a normalised mantissa has its top bit set; everything else -> black
+    rgbe[(rgbe[..., 3] < 30) | (rgbe[..., 3] > 240)] = 0      # keep exponents away from the 1e-32 cut-off (e = 22) and float overflow
+    file_bytes = vq.hdr_pack_file(rgbe)
+    as_float = _rgbe_to_float(rgbe)
+    assert np.array_equal(orc.linear_to_rgbe(as_float), rgbe)
+    assert file_bytes == orc.hdr_encode(as_float)
+    rc, dec, _ = orc.hdr_decode(file_bytes)
+    assert rc == 0 and np.array_equal(dec.view(np.uint32), as_float.view(np.uint32))

@@ -2,9 +2,11 @@
 //
 // Replaces VQRenderer::RenderSceneColor (SceneRendering.cpp:1619-1851) + PSMain
 // (ForwardLighting.hlsl:285-380) over a G-buffer of three float4 planes (+ optional emissive):
-//   64 B/pixel of HBM traffic (3 x LDG.128 + 1 x STG.128, all coalesced, streaming);
-//   the light array is staged once per block into shared memory; the IBL cubemaps and the BRDF LUT
-//   are read through L1/L2 (they are L2-resident side data: <= 42 MB at the reference sizes).
+//   64 B/pixel of HBM traffic: the three planes arrive as 2 KB row segments through a TMA (cp.async.bulk) /
+//   mbarrier ring in shared memory, the result leaves as one STG.128 per pixel; the light array is staged once per
+//   CTA into shared memory; the IBL cubemaps and the BRDF LUT are gathered from L2-resident sampling copies
+//   (pair / footprint records, 102 MB at the reference sizes) with five 256-bit loads per pixel, because the
+//   L1 data pipe — one wavefront per distinct line of a divergent gather — is what bounds this kernel.
 // The math is PSMain's with per-pixel invariants hoisted out of the light loops (N, V, N.V, the
 // Smith-G term of V, F0, kD factors). Discontinuities are evaluated exactly as the oracle does:
 //   * `D < l.range` uses an unfused |L-P|^2 and a per-light threshold on the squared distance that is
