@@ -27,5 +27,5 @@ def test_host_layer_exports_reference_shaped_api():
                  "vq::VQRenderer::LoadDefaultResources", "vq::FEnvironmentMapRenderingResources::CreateRenderingResources",
                  "vq::FPostProcessParameters::FFSR1_EASU::UpdateEASUConstantBlock", "vq::GaussianBlurPass::RecordCommands",
                  "vq::FEnvironmentMapRenderingResources::CreateRenderingResourcesFromHDRFile", "vq::VQRenderer::RenderEnvironmentMap",
-                 "vq::VQRenderer::ApplyReflections", "vq::VQRenderer::SaveToHDRFileImage"]:
+                 "vq::VQRenderer::ApplyReflections", "vq::VQRenderer::SaveToHDRFileImage", "vq::ApplyReflectionsPass::RecordCommands"]:
         assert name in syms, name

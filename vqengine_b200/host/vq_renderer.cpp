@@ -190,6 +190,18 @@ bool VQRenderer::ApplyReflections(cudaStream_t pCmd, const VqImage& ReflectionRa
     return true;
 }
 
+void ApplyReflectionsPass::RecordCommands(const IRenderPassDrawParameters* pDrawParameters) {
+    const FDrawParameters* pParams = static_cast<const FDrawParameters*>(pDrawParameters);
+    if (!pParams || !pParams->UAVSceneRadiance.ptr || !pParams->SRVReflectionRadiance.ptr) { g_err = "ApplyReflectionsPass: missing draw parameters"; return; }
+    if (pParams->UAVSceneRadiance.width != pParams->iSceneRTWidth || pParams->UAVSceneRadiance.height != pParams->iSceneRTHeight) {
+        g_err = "ApplyReflectionsPass: iSceneRTWidth/Height do not match the scene radiance target"; return;
+    }
+    const bool bCompositeColor2 = pParams->SRVBoundingVolumes.ptr != nullptr;                       // ApplyReflections.cpp:52
+    if (vq_apply_reflections(mRenderer.Context(), pParams->UAVSceneRadiance, pParams->SRVReflectionRadiance,
+                             bCompositeColor2 ? &pParams->SRVBoundingVolumes : nullptr, pParams->pCmd) != VQ_OK)
+        g_err = std::string("vq_apply_reflections: ") + vq_last_error();
+}
+
 std::vector<unsigned char> VQRenderer::SaveToHDRFileImage(const VqImage& Image) {
     std::vector<unsigned char> file((size_t)256 + (size_t)Image.width * Image.height * 6 + (size_t)Image.height * 8);
     uint64_t n = 0;

@@ -180,6 +180,28 @@ private:
     std::vector<std::unique_ptr<FTexture2D>> mMips; VqSpdConstants mConstants{};
 };
 
+// ApplyReflectionsPass (Source/Renderer/Rendering/RenderPass/ApplyReflections.h:27-57): the one dispatch of the hot path that the
+// reference itself wraps in an IRenderPass. FDrawParameters keeps its field names; SRV/UAV ids become image descriptors, the
+// command list becomes a stream, pCBufferHeap disappears. SRVBoundingVolumes.ptr == nullptr == INVALID_ID selects the variant
+// without COMPOSITE_BOUNDING_VOLUMES (ApplyReflections.cpp:52,62).
+class ApplyReflectionsPass : public RenderPassBase {
+public:
+    struct FResourceCollection : IRenderPassResourceCollection {};
+    struct FDrawParameters : IRenderPassDrawParameters {
+        cudaStream_t pCmd = nullptr;
+        VqImage SRVReflectionRadiance{};
+        VqImage SRVBoundingVolumes{};
+        VqImage UAVSceneRadiance{};
+        int iSceneRTWidth = 0, iSceneRTHeight = 0;
+    };
+    explicit ApplyReflectionsPass(VQRenderer& r) : RenderPassBase(r) {}
+    bool Initialize() override { return true; }
+    void Destroy() override {}
+    void OnCreateWindowSizeDependentResources(unsigned, unsigned, const IRenderPassResourceCollection* = nullptr) override {}
+    void OnDestroyWindowSizeDependentResources() override {}
+    void RecordCommands(const IRenderPassDrawParameters* pDrawParameters = nullptr) override;
+};
+
 // ---- the renderer front end ----
 class VQRenderer {
 public:
