@@ -112,3 +112,25 @@ def test_product_does_not_touch_oracle():
     assert "oracle" not in subprocess.run(["ldd", so], capture_output=True, text=True).stdout
     strings = subprocess.run(["strings", so], capture_output=True, text=True).stdout
     assert "liboracle" not in strings and "orc_" not in strings
+
+
+def test_header_is_plain_c_and_c_client_links(tmp_path):
+    """include/vqcuda.h must be consumable from C (the drop-in boundary carries no C++ or torch types): the example client
+    compiles as C99 with -Wall -Wextra -Werror and links against nothing but libvqcuda.so and the CUDA runtime."""
+    import os
+    import shutil
+    import subprocess
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    cuda = os.environ.get("CUDA_HOME", "/usr/local/cuda")
+    if not shutil.which("gcc") or not os.path.exists(os.path.join(cuda, "include", "cuda_runtime_api.h")):
+        pytest.skip("gcc / CUDA headers not available")
+    obj, exe = str(tmp_path / "c_client.o"), str(tmp_path / "c_client")
+    subprocess.check_call(["gcc", "-std=c99", "-Wall", "-Wextra", "-Werror", "-c", os.path.join(root, "examples", "c_client.c"),
+                           "-I", os.path.join(root, "include"), "-I", os.path.join(cuda, "include"), "-o", obj])
+    subprocess.check_call(["gcc", obj, "-L", os.path.join(root, "vqengine_b200"), "-lvqcuda", "-L", os.path.join(cuda, "lib64"),
+                           "-lcudart", "-lm", "-o", exe])
+    # and a translation unit that only includes the headers, as strict C89-style C
+    src = tmp_path / "hdr_only.c"
+    src.write_text('#include "vqcuda.h"\nint main(void) { return (int)sizeof(VqPerFrameData) == 0; }\n')
+    subprocess.check_call(["gcc", "-std=c99", "-pedantic", "-Wall", "-Werror", "-c", str(src), "-I", os.path.join(root, "include"),
+                           "-o", str(tmp_path / "hdr_only.o")])
