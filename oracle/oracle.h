@@ -115,6 +115,23 @@ float4 ForwardLighting_PSMain(const VqPerFrameData& cbPerFrame, const VqPerViewL
                               const float4* emissive,   // may be null
                               const Cubemap& texEnvMapDiff, const Cubemap& texEnvMapSpec, const Image& lut);
 
+// ---- shadow tests (oracle_shadow.cpp; SURVEY A25 / §8(f).4 groundwork — the product still uses shadow factor 1) ----
+struct ShadowTestPCFData { float4 lightSpacePos; float depthBias, NdotL, viewDistanceOfPixel; };     // Lighting.hlsl:79-87
+struct ShadowMaps {       // linear R32F; any pointer may be null (= that light type is lit unshadowed)
+    const float* pointCubes; int pointRes;        // [caster][face][y][x], value = distance / light range (Lighting.hlsl:156-158)
+    const float* spotMaps; int spotW, spotH;      // [caster][y][x], value = light-space depth
+    const float* dirMap; int dirW, dirH;          // [y][x]
+};
+float  SamplePoint2D(const float* map, int w, int h, float u, float v);                // POINT filter, WRAP (RootSignatures.cpp:148)
+float  SamplePointCube(const float* cube, int res, float3 dir);
+float  OmnidirectionalShadowTestPCF(const ShadowTestPCFData& pcf, const float* cube, int res, float3 lightVectorWorldSpace, float fFarPlane); // :113-165
+float  ShadowTestPCF(const ShadowTestPCFData& pcf, const float* map, int w, int h, float2 shadowMapDimensions);             // :168-211
+float  ShadowTestPCF_Directional(const ShadowTestPCFData& pcf, const float* map, int w, int h, float2 shadowMapDimensions); // :215-263
+float4 ForwardLighting_PSMain_Shadowed(const VqPerFrameData& cbPerFrame, const VqPerViewLightingData& cbPerView,
+                                       float4 position_ao, float4 normal_roughness, float4 albedo_metalness, const float4* emissive,
+                                       const Cubemap& texEnvMapDiff, const Cubemap& texEnvMapSpec, const Image& lut,
+                                       const ShadowMaps& sm);                                                                // ForwardLighting.hlsl:285-380
+
 // ---- CubemapConvolution.hlsl / IBL -------------------------------------------------------------
 void   MipImage_MinFilter(const float* src, float* dst, int width, int height);       // DXGIUtils.cpp:289-317
 // phi/theta sequences of PSMain_DiffuseIrradiance's loops (CubemapConvolution.hlsl:129-135)

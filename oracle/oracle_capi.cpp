@@ -318,6 +318,36 @@ float orc_aprx(int which, float a) {
 }
 
 
+// ---- A25 / §8(f).4 groundwork: PSMain with shadow maps bound (any map pointer may be null) --------------------------------
+void orc_forward_lighting_shadowed(const VqPerFrameData* pf, const VqPerViewLightingData* pv,
+                                   const float* position_ao, const float* normal_roughness, const float* albedo_metalness,
+                                   int width, int height, const float* diff_cube, int diff_res,
+                                   const float* spec_cube, int spec_res, int spec_mips, const float* lut, int lut_w, int lut_h,
+                                   const float* point_cubes, int point_res, const float* spot_maps, int spot_w, int spot_h,
+                                   const float* dir_map, int dir_w, int dir_h, float* out, int threads) {
+    const Cubemap cd{diff_cube, diff_res, 1};
+    const Cubemap cs{spec_cube, spec_res, spec_mips};
+    const Image lutImg{lut, lut_w, lut_h, (size_t)lut_w * 2, 2};
+    const ShadowMaps sm{point_cubes, point_res, spot_maps, spot_w, spot_h, dir_map, dir_w, dir_h};
+    par_rows(height, threads, [&](int y) {
+        for (int x = 0; x < width; ++x) {
+            const size_t o = ((size_t)y * width + x) * 4;
+            st(out + o, ForwardLighting_PSMain_Shadowed(*pf, *pv, ld(position_ao + o), ld(normal_roughness + o), ld(albedo_metalness + o),
+                                                        nullptr, cd, cs, lutImg, sm));
+        }
+    });
+}
+float orc_shadow_test_pcf(const float lightSpacePos[4], float depthBias, float NdotL, const float* map, int w, int h, int directional) {
+    ShadowTestPCFData pcf{}; pcf.lightSpacePos = {lightSpacePos[0], lightSpacePos[1], lightSpacePos[2], lightSpacePos[3]};
+    pcf.depthBias = depthBias; pcf.NdotL = NdotL;
+    const float2 dims = {(float)w, (float)h};
+    return directional ? ShadowTestPCF_Directional(pcf, map, w, h, dims) : ShadowTestPCF(pcf, map, w, h, dims);
+}
+float orc_shadow_test_omni(const float Lw[3], float depthBias, float viewDistance, float farPlane, const float* cube, int res) {
+    ShadowTestPCFData pcf{}; pcf.depthBias = depthBias; pcf.viewDistanceOfPixel = viewDistance;
+    return OmnidirectionalShadowTestPCF(pcf, cube, res, make3(Lw[0], Lw[1], Lw[2]), farPlane);
+}
+
 // ---- §8(f).2 Radiance .hdr codec, §8(f).3 skydome / ApplyReflections -----------------------------------------
 // decode: call with rgba == nullptr to get the size, then again with a buffer of w*h*4 floats. Returns the stb error class.
 int orc_hdr_decode(const uint8_t* file, uint64_t n, int* w, int* h, float* rgba, float* max_luminance) {

@@ -352,3 +352,38 @@ def resize_downsample(img, ow: int, oh: int, which: str = "oracle"):
         rc = lib().orc_resize_downsample(_p(a), C.c_int(w), C.c_int(h), _p(out), C.c_int(ow), C.c_int(oh))
         assert rc == 0
     return out
+
+
+# ---- A25 / §8(f).4 groundwork: shadow tests (oracle_shadow.cpp) ------------------------------------------------------------
+def forward_lighting_shadowed(pf, pv, planes, diff_cube, diff_res, spec_cube, spec_res, spec_mips, lut,
+                              point_cubes=None, point_res=0, spot_maps=None, dir_map=None, threads=None) -> np.ndarray:
+    pos, nrm, alb = (_f(p) for p in planes[:3])
+    h, w = pos.shape[:2]
+    out = np.zeros((h, w, 4), np.float32)
+    lutc = _f(lut)
+    pc = _f(point_cubes) if point_cubes is not None else None
+    sm = _f(spot_maps) if spot_maps is not None else None
+    dm = _f(dir_map) if dir_map is not None else None
+    lib().orc_forward_lighting_shadowed(
+        C.byref(pf), C.byref(pv), _p(pos), _p(nrm), _p(alb), C.c_int(w), C.c_int(h),
+        _p(_f(diff_cube)), C.c_int(diff_res), _p(_f(spec_cube)), C.c_int(spec_res), C.c_int(spec_mips),
+        _p(lutc), C.c_int(lutc.shape[1]), C.c_int(lutc.shape[0]),
+        _p(pc) if pc is not None else None, C.c_int(point_res),
+        _p(sm) if sm is not None else None, C.c_int(sm.shape[2] if sm is not None else 0), C.c_int(sm.shape[1] if sm is not None else 0),
+        _p(dm) if dm is not None else None, C.c_int(dm.shape[1] if dm is not None else 0), C.c_int(dm.shape[0] if dm is not None else 0),
+        _p(out), C.c_int(threads or cpu_threads()))
+    return out
+
+
+def shadow_test_pcf(light_space_pos, depth_bias, ndotl, shadow_map, directional=False) -> float:
+    m = _f(shadow_map)
+    lib().orc_shadow_test_pcf.restype = f32
+    return float(lib().orc_shadow_test_pcf((f32 * 4)(*[float(x) for x in light_space_pos]), f32(depth_bias), f32(ndotl), _p(m),
+                                           C.c_int(m.shape[1]), C.c_int(m.shape[0]), C.c_int(int(directional))))
+
+
+def shadow_test_omni(lw, depth_bias, view_distance, far_plane, cube) -> float:
+    c = _f(cube)
+    lib().orc_shadow_test_omni.restype = f32
+    return float(lib().orc_shadow_test_omni((f32 * 3)(*[float(x) for x in lw]), f32(depth_bias), f32(view_distance), f32(far_plane),
+                                            _p(c), C.c_int(c.shape[1])))
