@@ -78,6 +78,18 @@ fp = [(n, f) for n, f in fp if f and "ms" in f]
 if fp:
     out.append("\nFused compute + gather for the specular prefilter (`vq_specular_prefilter_multi`, peer stores over NVLink): "
                + ", ".join(f"{n} GPUs {f['ms']:.3f} ms ({base / f['ms']:.2f}x vs 1 GPU, equals NCCL result: {f.get('equals_nccl_allgather')})" for n, f in fp) + ".")
+out.append("\n## How these were produced\n")
+out.append("All on `gpurun` B200 boxes from this tree (scripts under `tools/`):\n")
+out.append("* `bash tools/gpu_full.sh` — `pytest -m gpu` (-> `r01_gpu_tests.txt`), `python bench.py` (-> `r01_bench_1gpu.json`), "
+           "`ncu --set full --clock-control none --import-source on -k regex:forward_kernel -s 8 -c 1` over `tools/perf_forward.py` "
+           "(-> `r01_forward_g_summary.txt` via `tools/ncu_summary.py`), the same over `tools/run_pass.py frame` (-> `r01_frame_a_summary.txt`), "
+           "`ncu --metrics gpu__time_duration.sum --clock-control none -c 700 --csv` over `bench.py --steps 2 --warmup 1` (-> `r01_launches_bench.csv`; "
+           "cold, serialised per-launch times: shares only), `compute-sanitizer --tool memcheck python tools/sanitize_small.py` "
+           "(-> `r01_sanitize_memcheck.txt`), `vq_headless_test -TestFrames=100` (-> `r01_headless_100frames.txt`).")
+out.append("* `bash tools/gpu_2gpu.sh` under `gpurun --gpus 2` — the driver's torchrun command for `bench.py --gpus 2` (-> `r01_bench_2gpu.json`).")
+out.append("* `bash tools/gpu_variants.sh <names>` — A/B timings of K1 builds in `variants/` + the decomposition run (-> `r01_forward_variants.txt`).")
+out.append("* `r01_bench_8gpu.json`, `r01_topo_8gpu.txt`, `r01_forward_d/e_summary.txt`, `r01_post_b_summary.txt`, `r01_ibl_a_summary.txt`, "
+           "`r01_surface_*`: earlier in round 1 (K1 has changed since: its 8-GPU line is from the previous kernel build).")
 out.append("\n## Files\n")
 for f in sorted(os.listdir(P)):
     if f != "README.md":
