@@ -5,6 +5,7 @@
 #include <cuda_runtime_api.h>
 #include <cmath>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 
 namespace vq {
@@ -85,6 +86,54 @@ bool FEnvironmentMapRenderingResources::CreateRenderingResourcesFromHDRFile(VQRe
 }
 void FEnvironmentMapRenderingResources::DestroyRenderingResources() {
     Tex_HDREnvironment.Free(); Tex_IrradianceDiff.Free(); Tex_IrradianceDiffBlurred.Free(); Tex_BlurTemp.Free(); Tex_IrradianceSpec.Free();
+}
+
+// ---- Data/EnvironmentMaps.ini ----------------------------------------------------------------------
+std::vector<FEnvironmentMapFileDescriptor> ParseEnvironmentMapsINI(const std::string& text) {
+    std::vector<FEnvironmentMapFileDescriptor> out;
+    FEnvironmentMapFileDescriptor desc;
+    bool sawEmptyLine = false, readingEnvMap = false;
+    size_t pos = 0;
+    while (pos <= text.size()) {
+        size_t eol = text.find('\n', pos);
+        if (eol == std::string::npos) eol = text.size();
+        std::string line = text.substr(pos, eol - pos);
+        pos = eol + 1;
+        if (!line.empty() && line.back() == '\r') line.pop_back();
+        if (!line.empty() && line[0] == ';') continue;                       // comment
+        if (line.empty()) { sawEmptyLine = true; if (pos > text.size()) break; continue; }
+        if (line.front() == '[') {                                          // section header: "[Name]"
+            const size_t close = line.find(']');
+            readingEnvMap = true;
+            if (sawEmptyLine) { out.push_back(desc); desc = {}; sawEmptyLine = false; }
+            desc.Name = line.substr(1, close == std::string::npos ? std::string::npos : close - 1);
+            continue;
+        }
+        const size_t eq = line.find('=');
+        if (eq != std::string::npos) {
+            const std::string key = line.substr(0, eq), value = line.substr(eq + 1);
+            if (key == "Path") desc.FilePath = value;
+            if (key == "MaxCLL") desc.MaxContentLightLevel = std::strtof(value.c_str(), nullptr);
+        }
+        sawEmptyLine = false;
+    }
+    if (readingEnvMap) out.push_back(desc);
+    return out;
+}
+
+std::vector<unsigned char> CreateEnvironmentMapFileImageFromHiRes(VQRenderer& Renderer, const void* pHiResFileBytes, size_t NumBytes,
+                                                                  int TargetWidth, int TargetHeight) {
+    VqHdrInfo info;
+    if (vq_hdr_parse(pHiResFileBytes, NumBytes, &info, nullptr) != VQ_OK) { Fail("vq_hdr_parse"); return {}; }
+    if (TargetWidth <= 0 || TargetHeight <= 0 || TargetWidth > info.width || TargetHeight > info.height) {
+        g_err = "CreateEnvironmentMapFileImageFromHiRes: the target must not be larger than the source"; return {};
+    }
+    FTexture2D hi, lo;
+    if (!hi.Create(info.width, info.height) || !lo.Create(TargetWidth, TargetHeight)) return {};
+    float maxLuminance = 0.0f;
+    if (vq_hdr_load_host(Renderer.Context(), pHiResFileBytes, NumBytes, hi.View(), &maxLuminance) != VQ_OK) { Fail("vq_hdr_load_host"); return {}; }
+    if (vq_image_resize(Renderer.Context(), hi.View(), lo.View(), nullptr) != VQ_OK) { Fail("vq_image_resize"); return {}; }
+    return Renderer.SaveToHDRFileImage(lo.View());                          // vq_hdr_save_host synchronises
 }
 
 // ---- renderer ------------------------------------------------------------------------------------

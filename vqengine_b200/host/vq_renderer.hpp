@@ -131,6 +131,20 @@ struct FEnvironmentMapRenderingResources {
     VqCubemap Specular() const { return VqCubemap{Tex_IrradianceSpec.ptr, SpecRes, SpecMips}; }
 };
 
+// ---- Data/EnvironmentMaps.ini (FileParser::ParseEnvironmentMapsFile, Source/Engine/Core/FileParser.cpp:264-321) ----
+// "[Name]" sections with "Path=" and "MaxCLL=" keys, ';' comment lines. Host-only text parsing; the engine's quirk that a new
+// section only closes the previous one after an empty line is kept.
+struct FEnvironmentMapFileDescriptor {      // Source/Engine/EnvironmentMap.h:23-28
+    std::string Name, FilePath; float MaxContentLightLevel = 0.0f;
+};
+std::vector<FEnvironmentMapFileDescriptor> ParseEnvironmentMapsINI(const std::string& FileContents);
+
+// CreateEnvironmentMapTextureFromHiResAndSaveToDisk (Source/Engine/EnvironmentMap.cpp:142-209) on file images: decode the
+// hi-res .hdr, Image::CreateResizedImage to TargetWidth x TargetHeight (the engine's table: 8k 8192x4096, 4k 4096x2048,
+// 2k 2048x1024, 1k 1024x512), Image::SaveToDisk — all three steps on the device. Returns the smaller file image (empty on failure).
+std::vector<unsigned char> CreateEnvironmentMapFileImageFromHiRes(VQRenderer& Renderer, const void* pHiResFileBytes, size_t NumBytes,
+                                                                  int TargetWidth, int TargetHeight);
+
 // ---- IRenderPass (RenderPass.h:25-59) ----
 struct IRenderPassResourceCollection {};
 struct IRenderPassDrawParameters {};
