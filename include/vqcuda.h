@@ -335,7 +335,8 @@ typedef struct VqHdrInfo {
  * Otherwise (run-length encoded files: info->flat == 0 after the first call) it must hold 4*height+1 entries and
  * receives the file offset of every scanline's R,G,B,E run list (+ the end offset); the run headers are validated
  * (stb's "corrupt HDR" conditions -> VQ_ERR_INVALID_ARG; a stream that ends inside a scanline is an error, where stb
- * would spin on zero bytes). A file whose scanlines turn out not to be run-length encoded flips info->flat to 1. */
+ * would spin on zero bytes; a resolution line with a zero dimension is rejected, where stb returns an image without texels).
+ * A file whose scanlines turn out not to be run-length encoded flips info->flat to 1. */
 VQ_API int vq_hdr_parse(const void* file, uint64_t size, VqHdrInfo* info, uint64_t* channel_offsets);
 /* DEVICE. Expands the file image into `out` (width x height RGBA32F, alpha 1). dev_file: 16-byte aligned, allocation
  * padded to a multiple of 16 bytes. dev_channel_offsets: device copy of the index (NULL for flat files).

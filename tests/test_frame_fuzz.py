@@ -6,7 +6,7 @@ import pytest
 from hypothesis import given, settings, strategies as st, HealthCheck
 
 HEADER = b"#?RADIANCE\nFORMAT=32-bit_rle_rgbe\n\n"
-SET = dict(deadline=None, max_examples=150, suppress_health_check=[HealthCheck.function_scoped_fixture, HealthCheck.too_slow])
+SET = dict(deadline=None, max_examples=150, derandomize=True, database=None, suppress_health_check=[HealthCheck.function_scoped_fixture, HealthCheck.too_slow])
 
 
 def _expand_with_index(data: bytes, info, offs):
@@ -76,7 +76,9 @@ def test_parse_agrees_with_oracle_on_mutated_files(vq, orc, w, h, seed, nmut, da
     try:
         info, offs = vq.hdr_parse(f)
     except vq.VqError:
-        assert rc != 0
+        # a mutated resolution line can make a dimension parse as 0: stb (and the oracle) then "succeed" with an image
+        # without texels; the product rejects it (documented in vqcuda.h) — every other rejection must be the oracle's too
+        assert rc != 0 or ref.size == 0
         return
     assert rc == 0
     if (info.width, info.height) == ref.shape[1::-1] and info.width * info.height <= 4096:
