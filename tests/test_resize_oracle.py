@@ -88,3 +88,17 @@ def test_constant_image_and_mean(orc):
     a = _img(128, 64, 5)
     o = orc.resize_downsample(a, 64, 32)
     assert abs(float(o.mean()) - float(a.mean())) <= 2e-2
+
+
+def test_random_size_pairs(vq, orc):
+    """40 random (w, h) -> (ow <= w, oh <= h) pairs, ratios from 1:1 to 300:1: host tables replayed == oracle bit for bit,
+    and oracle == the reference's stbir where it is built. (A 400-pair sweep of the same generator found no difference.)"""
+    rng = np.random.default_rng(5)
+    for _ in range(40):
+        w, h = int(rng.integers(1, 300)), int(rng.integers(1, 40))
+        ow, oh = int(rng.integers(1, w + 1)), int(rng.integers(1, h + 1))
+        a = (rng.random((h, w, 4), dtype=np.float32) * 8).astype(np.float32)
+        o = orc.resize_downsample(a, ow, oh)
+        assert np.array_equal(replay_gather_tables(vq, a, ow, oh).view(np.uint32), o.view(np.uint32)), (w, h, ow, oh)
+        if orc.stb_ref() is not None:
+            assert np.array_equal(o.view(np.uint32), orc.resize_downsample(a, ow, oh, "ref").view(np.uint32)), (w, h, ow, oh)
