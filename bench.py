@@ -411,6 +411,33 @@ def cpu_reference_forward(planes, rows_target_s=12.0, env=None, threads=None):
             "sample": f"{reps} x ({rows} of {H4K} rows x {W4K} px of the same 4K G-buffer) = {reps * rows * W4K} px in {dt:.1f} s, scalar C++ oracle, std::thread row split"}
 
 
+def cpu_reference_image_class(hw=4096, hh=2048):
+    """cpu_baseline for the SURVEY 8(f).2 rows, kind "reference": the engine's OWN Image class (Libs/VQUtils/Source/Image.cpp
+    compiled unmodified into oracle/_ref/libvqimageref.so) timed on this box's host cores, single-threaded as in the engine —
+    Image::LoadFromFile (stbi_loadf + CalculateMaxLuminance), Image::CreateResizedImage (stbir_resize_float), Image::SaveToDisk
+    (stbi_write_hdr) on the same 4096x2048 HDRI the GPU rows are measured on. Returns None when the library is not present."""
+    import tempfile
+    import oracle_lib as orc
+    from vqengine_b200 import synth
+    if orc.image_ref() is None:
+        return None
+    src = synth.hdri(hw, hh)
+    with tempfile.TemporaryDirectory() as td:
+        path_in, path_out = os.path.join(td, "in.hdr"), os.path.join(td, "out.hdr")
+        open(path_in, "wb").write(orc.hdr_encode(src))
+        t0 = time.perf_counter(); texels, lum = orc.ref_image_load(path_in); t_load = time.perf_counter() - t0
+        if texels is None:
+            return None
+        t0 = time.perf_counter(); half = orc.ref_image_resize(texels, hw // 2, hh // 2); t_resize = time.perf_counter() - t0
+        t0 = time.perf_counter(); ok = orc.ref_image_save(path_out, texels); t_save = time.perf_counter() - t0
+        if not ok:
+            return None
+    return {"kind": "reference", "cores": 1, "unit": "ms",
+            "sample": f"one {hw}x{hh} equirect HDRI through the reference's Image class (oracle/_ref/libvqimageref.so), file on tmpfs/disk cache",
+            "image_load_from_file_ms": round(t_load * 1e3, 1), "image_create_resized_half_ms": round(t_resize * 1e3, 1),
+            "image_save_to_disk_ms": round(t_save * 1e3, 1)}
+
+
 def cpu_env():
     """IBL maps for the CPU arm, built by the ORACLE at reduced sizes (the full-size maps would cost the scalar CPU
     code minutes; map size does not change the per-pixel work of the forward pass)."""
@@ -626,6 +653,12 @@ def main():
             line["extra"]["note"] = "per-kernel figures for the other SURVEY.md section-8 rows; not part of `value`"
         if not args.no_cpu:
             line["cpu_baseline"] = cpu_reference_forward(planes, env=cpu_env())
+            try:                     # the (f).2 rows have a compilable reference: time it beside the kernels
+                ref_img = cpu_reference_image_class()
+                if ref_img is not None:
+                    line["cpu_baseline_image_class"] = ref_img
+            except Exception as ex:  # never let the side measurement cost the bench line
+                line["cpu_baseline_image_class"] = {"error": repr(ex)[:200]}
     if rank == 0:
         print(json.dumps(line))
     if dist:

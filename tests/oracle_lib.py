@@ -387,3 +387,42 @@ def shadow_test_omni(lw, depth_bias, view_distance, far_plane, cube) -> float:
     lib().orc_shadow_test_omni.restype = f32
     return float(lib().orc_shadow_test_omni((f32 * 3)(*[float(x) for x in lw]), f32(depth_bias), f32(view_distance), f32(far_plane),
                                             _p(c), C.c_int(c.shape[1])))
+
+
+# ---- the reference's OWN Image class (Libs/VQUtils/Source/Image.cpp compiled unmodified: oracle/_ref/libvqimageref.so) ----
+IMG_REF_LIB = os.path.join(ORACLE_DIR, "_ref", "libvqimageref.so")
+_img = None
+
+
+def image_ref():
+    global _img
+    if _img is None and os.path.exists(IMG_REF_LIB):
+        _img = C.CDLL(IMG_REF_LIB)
+    return _img
+
+
+def ref_image_load(path: str):
+    """Image::LoadFromFile(path) -> (rgba float32 [h,w,4], Image::MaxLuminance) or (None, None)"""
+    r = image_ref()
+    w, h, lum = C.c_int(0), C.c_int(0), f32(0)
+    if r.vqimg_load(path.encode(), C.byref(w), C.byref(h), C.byref(lum), None) != 2:
+        return None, None
+    out = np.empty((h.value, w.value, 4), dtype=np.float32)
+    r.vqimg_load(path.encode(), C.byref(w), C.byref(h), C.byref(lum), _p(out))
+    return out, lum.value
+
+
+def ref_image_resize(img, ow: int, oh: int):
+    a = _f(img)
+    out = np.zeros((oh, ow, 4), dtype=np.float32)
+    assert image_ref().vqimg_resize(_p(a), C.c_int(a.shape[1]), C.c_int(a.shape[0]), _p(out), C.c_int(ow), C.c_int(oh)) == 1
+    return out
+
+
+def ref_image_save(path: str, img) -> bool:
+    a = _f(img)
+    return image_ref().vqimg_save(path.encode(), _p(a), C.c_int(a.shape[1]), C.c_int(a.shape[0])) == 1
+
+
+def ref_mip_level_count(w: int, h: int) -> int:
+    return int(image_ref().vqimg_mip_level_count(C.c_ulonglong(w), C.c_ulonglong(h)))

@@ -73,6 +73,11 @@ for k, label in [("surface_producer_4k", "(f).1 surface producer 4K"), ("texture
         for kk in ("e2e_host_file_to_device_image_ms", "e2e_device_image_to_host_file_ms"):
             if kk in e: note += f"; {kk} = {e[kk]}"
         out.append(f"| {label} | {e['ms']:.4f} | {e['algorithmic_GBps']:.0f} | {e['hbm_frac']:.3f} | {note} |")
+ric = b1.get("cpu_baseline_image_class")
+if ric and "error" not in ric:
+    out.append(f"\nReference CPU path for the (f).2 rows (the engine's own `Image` class compiled unmodified, 1 host core, same 4096x2048 HDRI): "
+               f"`Image::LoadFromFile` {ric['image_load_from_file_ms']} ms, `Image::CreateResizedImage` to half size {ric['image_create_resized_half_ms']} ms, "
+               f"`Image::SaveToDisk` {ric['image_save_to_disk_ms']} ms.")
 fp = [(b['n_gpus'], b["ibl_specular_prefilter_strong"].get("fused_p2p")) for b in (b2, b8) if b and "ibl_specular_prefilter_strong" in b]
 fp = [(n, f) for n, f in fp if f and "ms" in f]
 if fp:
