@@ -426,3 +426,40 @@ def ref_image_save(path: str, img) -> bool:
 
 def ref_mip_level_count(w: int, h: int) -> int:
     return int(image_ref().vqimg_mip_level_count(C.c_ulonglong(w), C.c_ulonglong(h)))
+
+
+# ---- the reference's OWN VQ_DXGI_UTILS::MipImage (DXGIUtils.cpp compiled unmodified: oracle/_ref/libvqmipref.so) --------
+MIP_REF_LIB = os.path.join(ORACLE_DIR, "_ref", "libvqmipref.so")
+_mip = None
+
+
+def mip_ref():
+    global _mip
+    if _mip is None and os.path.exists(MIP_REF_LIB):
+        _mip = C.CDLL(MIP_REF_LIB)
+    return _mip
+
+
+def ref_mip_image(level: np.ndarray) -> np.ndarray:
+    """one MipImage step on an even-sized level: [H,W,4] float32 (RGB MIN, A = 1) or uint8 (box, truncating) -> [H/2,W/2,4]"""
+    a = np.ascontiguousarray(level)
+    h, w = a.shape[:2]
+    assert w % 2 == 0 and h % 2 == 0, "the reference indexes (x+1, y+1) unconditionally"
+    out = np.zeros((h // 2, w // 2, 4), dtype=a.dtype)
+    mip_ref().vqmip_image(a.ctypes.data_as(C.c_void_p), out.ctypes.data_as(C.c_void_p), C.c_uint(w), C.c_uint(h),
+                          C.c_uint(16 if a.dtype == np.float32 else 4))
+    return out
+
+
+# ---- the reference's OWN FPostProcessParameters wrappers (PostProcess.cpp compiled unmodified: oracle/_ref/libvqppref.so) ----
+PP_REF_LIB = os.path.join(ORACLE_DIR, "_ref", "libvqppref.so")
+_pp = None
+
+
+def pp_ref():
+    global _pp
+    if _pp is None and os.path.exists(PP_REF_LIB):
+        _pp = C.CDLL(PP_REF_LIB)
+        _pp.vqpp_rcas_linear_from_stops.restype = f32
+        _pp.vqpp_rcas_stops_from_linear.restype = f32
+    return _pp
