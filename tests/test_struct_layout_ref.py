@@ -43,10 +43,10 @@ def test_layouts_match_the_reference_header(tmp_path):
     for ours, fn in [("VQ_TEXCFG_DIFFUSE", "HasDiffuseMap"), ("VQ_TEXCFG_NORMAL", "HasNormalMap"), ("VQ_TEXCFG_AO", "HasAmbientOcclusionMap"),
                      ("VQ_TEXCFG_ALPHA_MASK", "HasAlphaMask"), ("VQ_TEXCFG_ROUGHNESS", "HasRoughnessMap"), ("VQ_TEXCFG_METALLIC", "HasMetallicMap"),
                      ("VQ_TEXCFG_HEIGHT", "HasHeightMap"), ("VQ_TEXCFG_EMISSIVE", "HasEmissiveMap"), ("VQ_TEXCFG_ORM", "HasOcclusionRoughnessMetalnessMap")]:
-        lines.append(f'  if (VQ_SHADER_DATA::{fn}({ours}) != 1 || VQ_SHADER_DATA::{fn}(0x1ff & ~{ours}) != 0) {{ std::printf("{ours} vs {fn}\n"); ++bad; }}')
+        lines.append(f'  if (VQ_SHADER_DATA::{fn}({ours}) != 1 || VQ_SHADER_DATA::{fn}(0x1ff & ~{ours}) != 0) {{ std::printf("{ours} vs {fn}\\n"); ++bad; }}')
     for ours, theirs in [("VQ_NUM_LIGHTS_POINT", "NUM_LIGHTS__POINT"), ("VQ_NUM_LIGHTS_SPOT", "NUM_LIGHTS__SPOT"),
                          ("VQ_NUM_SHADOWING_LIGHTS_POINT", "NUM_SHADOWING_LIGHTS__POINT"), ("VQ_NUM_SHADOWING_LIGHTS_SPOT", "NUM_SHADOWING_LIGHTS__SPOT")]:
-        lines.append(f'  if ({ours} != {theirs}) {{ std::printf("{ours} != {theirs}\n"); ++bad; }}')
+        lines.append(f'  if ({ours} != {theirs}) {{ std::printf("{ours} != {theirs}\\n"); ++bad; }}')
     lines += ['  std::printf("checked, %d mismatches, sizeof PerFrameData %zu\\n", bad, sizeof(VQ_SHADER_DATA::PerFrameData));', '  return bad; }']
     src = tmp_path / "layout.cpp"
     src.write_text("\n".join(lines))
