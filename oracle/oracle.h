@@ -177,6 +177,7 @@ float  CalculateMaxLuminance(const float* rgba, int width, int height);         
 void   LinearToRgbe(uint8_t rgbe[4], const float linear[3]);                         // stb_image_write.h stbiw__linear_to_rgbe
 void   HdrEncode(const float* rgba, int width, int height, std::vector<uint8_t>* file);      // stbi_write_hdr_core (Image.cpp:210-213)
 int    ResizeFloat4_Downsample(const float* in, int w, int h, float* out, int ow, int oh);  // stbir_resize_float (Image.cpp:148-190)
+float3 SkydomeLookDirection(const VqMatrix& invViewProj, int px, int py, int width, int height);
 float4 Skydome_PSMain(const Pyramid& texEquirectEnvironmentMap, const VqMatrix& invViewProj,
                       int px, int py, int width, int height);                        // Skydome.hlsl:35-56
 float4 ApplyReflections_CSMain(float4 SceneRadianceAndRoughness, float4 ReflectionRadiance, const float4* bv); // ApplyReflections.hlsl:31-57

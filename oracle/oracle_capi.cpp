@@ -393,4 +393,60 @@ void orc_apply_reflections(float* scene, const float* reflection, const float* b
         }
     });
 }
+
+// ---- probes used by the compiled-shader pin (tests/test_hlsl_ref.py; oracle/ref_shim/hlsl_ref_shim.cpp) ------------
+void orc_sample_lut(const float* lut, int w, int h, float u, float v, float out[2]) {
+    const float2 r = SampleLUT(Image{lut, w, h, (size_t)w * 2, 2}, u, v); out[0] = r.x; out[1] = r.y;
+}
+float orc_sample_point2d(const float* map, int w, int h, float u, float v) { return SamplePoint2D(map, w, h, u, v); }
+float orc_sample_point_cube(const float* cube, int res, const float d[3]) { return SamplePointCube(cube, res, make3(d[0], d[1], d[2])); }
+void orc_diffuse_irradiance_texel(const float* pyramid, int w, int h, int levels, const float dir[3],
+                                  float step, int n_phi, int n_theta, int src_mip, float out[4]) {
+    std::vector<float> phis, thetas;
+    DiffuseIrradianceAngles(step, n_phi, n_theta, phis, thetas);
+    st(out, DiffuseIrradiance_PSMain(Pyramid{pyramid, w, h, levels}, make3(dir[0], dir[1], dir[2]), phis, thetas, src_mip, false));
+}
+void orc_specular_irradiance_texel(const float* pyramid, int w, int h, int levels, const float dir[3],
+                                   float roughness, float dim_x, float dim_y, int num_samples, float out[4]) {
+    st(out, SpecularIrradiance_PSMain(Pyramid{pyramid, w, h, levels}, make3(dir[0], dir[1], dir[2]), roughness,
+                                      make2(dim_x, dim_y), (uint32_t)num_samples));
+}
+void orc_skydome_look_direction(const VqMatrix* inv_view_proj, int px, int py, int width, int height, float out[3]) {
+    const float3 d = SkydomeLookDirection(*inv_view_proj, px, py, width, height); out[0] = d.x; out[1] = d.y; out[2] = d.z;
+}
+void orc_environment_brdf(float NdotV, float roughness, float metallic, const float diffuseColor[3], const float diffuseIrradiance[3],
+                          const float preFilteredSpecular[3], const float F0ScaleBias[2], float out[3]) {
+    const float3 r = EnvironmentBRDF(NdotV, roughness, metallic, make3(diffuseColor[0], diffuseColor[1], diffuseColor[2]),
+                                     make3(diffuseIrradiance[0], diffuseIrradiance[1], diffuseIrradiance[2]),
+                                     make3(preFilteredSpecular[0], preFilteredSpecular[1], preFilteredSpecular[2]),
+                                     make2(F0ScaleBias[0], F0ScaleBias[1]));
+    out[0] = r.x; out[1] = r.y; out[2] = r.z;
+}
+void orc_hdr_curves(const float c[3], float lin_to_srgb[3], float srgb_to_lin[3], float r709_to_2020[3], float r2020_to_709[3], float st2084[3]) {
+    const float3 v = make3(c[0], c[1], c[2]);
+    auto o3 = [](float* o, float3 r) { o[0] = r.x; o[1] = r.y; o[2] = r.z; };
+    o3(lin_to_srgb, LinearToSRGB(v)); o3(srgb_to_lin, SRGBToLinear(v)); o3(r709_to_2020, Rec709ToRec2020(v));
+    o3(r2020_to_709, Rec2020ToRec709(v)); o3(st2084, LinearToST2084(v));
+}
+// the shadowed pass with the emissive plane (orc_forward_lighting_shadowed predates it and passes none)
+void orc_forward_lighting_shadowed_e(const VqPerFrameData* pf, const VqPerViewLightingData* pv,
+                                     const float* position_ao, const float* normal_roughness, const float* albedo_metalness,
+                                     const float* emissive, int width, int height, const float* diff_cube, int diff_res,
+                                     const float* spec_cube, int spec_res, int spec_mips, const float* lut, int lut_w, int lut_h,
+                                     const float* point_cubes, int point_res, const float* spot_maps, int spot_w, int spot_h,
+                                     const float* dir_map, int dir_w, int dir_h, float* out, int threads) {
+    const Cubemap cd{diff_cube, diff_res, 1};
+    const Cubemap cs{spec_cube, spec_res, spec_mips};
+    const Image lutImg{lut, lut_w, lut_h, (size_t)lut_w * 2, 2};
+    const ShadowMaps sm{point_cubes, point_res, spot_maps, spot_w, spot_h, dir_map, dir_w, dir_h};
+    par_rows(height, threads, [&](int y) {
+        for (int x = 0; x < width; ++x) {
+            const size_t o = ((size_t)y * width + x) * 4;
+            float4 em;
+            if (emissive) em = ld(emissive + o);
+            st(out + o, ForwardLighting_PSMain_Shadowed(*pf, *pv, ld(position_ao + o), ld(normal_roughness + o), ld(albedo_metalness + o),
+                                                        emissive ? &em : nullptr, cd, cs, lutImg, sm));
+        }
+    });
+}
 }  // extern "C"

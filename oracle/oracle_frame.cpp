@@ -213,7 +213,7 @@ void HdrEncode(const float* rgba, int width, int height, std::vector<uint8_t>* f
 // CubemapLookDirection is proportional to the cube-surface point under the pixel, i.e. to the view ray, so per pixel:
 //   ndc = pixel centre; ray = mul(float4(ndc, 1, 1), inverse(matViewProj)); dir = normalize(ray.xyz / ray.w)
 // (row-vector convention, XMMATRIX). `invViewProj` is that inverse, computed by the caller in double and rounded.
-float4 Skydome_PSMain(const Pyramid& texEquirectEnvironmentMap, const VqMatrix& invViewProj, int px, int py, int width, int height) {
+float3 SkydomeLookDirection(const VqMatrix& invViewProj, int px, int py, int width, int height) {
     const float nx = ((float)px + 0.5f) / (float)width * 2.0f - 1.0f;
     const float ny = 1.0f - ((float)py + 0.5f) / (float)height * 2.0f;
     const float* m = invViewProj.m;                       // row-major: v' = v * M
@@ -222,7 +222,10 @@ float4 Skydome_PSMain(const Pyramid& texEquirectEnvironmentMap, const VqMatrix& 
     const float z = nx * m[2] + ny * m[6] + m[10] + m[14];
     const float w = nx * m[3] + ny * m[7] + m[11] + m[15];
     const float3 ray = {x / w, y / w, z / w};
-    const float3 dir = normalize(normalize(ray));         // VSMain normalizes, PSMain normalizes again (:47,:53)
+    return normalize(ray);                                // VSMain: CubemapLookDirection = normalize(position.xyz) (:47)
+}
+float4 Skydome_PSMain(const Pyramid& texEquirectEnvironmentMap, const VqMatrix& invViewProj, int px, int py, int width, int height) {
+    const float3 dir = normalize(SkydomeLookDirection(invViewProj, px, py, width, height));   // PSMain normalizes again (:53)
     const float2 uv = DirectionToEquirectUV(dir);
     const float4 c = SampleEquirectLevel(texEquirectEnvironmentMap, uv, 0.0f);
     return {c.x, c.y, c.z, 1.0f};

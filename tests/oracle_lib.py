@@ -463,3 +463,75 @@ def pp_ref():
         _pp.vqpp_rcas_linear_from_stops.restype = f32
         _pp.vqpp_rcas_stops_from_linear.restype = f32
     return _pp
+
+
+# ---- the reference's SHADER TEXT compiled as C++ (oracle/_ref/libhlslref.so; ref_shim/hlsl_ref_shim.cpp) -----------------------
+HLSL_REF_LIB = os.path.join(ORACLE_DIR, "_ref", "libhlslref.so")
+_hlsl = None
+
+
+def hlsl_ref():
+    """Shaders/*.hlsl of the reference compiled with g++ on top of ref_shim/hlsl_compat.h, or None if oracle/_ref was not built."""
+    global _hlsl
+    if _hlsl is None and os.path.exists(HLSL_REF_LIB):
+        lib()                                   # liboracle.so first: libhlslref.so resolves its samplers from it
+        _hlsl = C.CDLL(HLSL_REF_LIB)
+        for n in ("hlslref_ndf_ggx", "hlslref_geometry_smith", "hlslref_spotlight_intensity"):
+            getattr(_hlsl, n).restype = f32
+    return _hlsl
+
+
+def hlsl_forward_image(pf, pv, planes, materials, chains, env, alpha_mask=False, point_cubes=None, point_res=0, spot_maps=None,
+                       dir_map=None):
+    """ForwardLighting.hlsl PSMain (compiled reference text) over the interpolated-attribute planes of the surface producer.
+    Returns (color [H,W,4], discarded [H,W] bool)."""
+    import vqengine_b200 as vq
+    h, w = planes[0].shape[:2]
+    n = len(materials)
+    mats = (vq.MaterialData * n)(*materials)
+    tex = (_OrcMaterialTextures * n)()
+    for i, d in enumerate(chains):
+        for k, slot in enumerate(vq.MATERIAL_TEXTURE_SLOTS):
+            e = d.get(slot)
+            if e is not None:
+                buf, tw, th, tl = e
+                tex[i].t[k] = _OrcTexture2D(buf.ctypes.data, tw, th, tl)
+    p0, p1, p2 = _f(planes[0]), _f(planes[1]), _f(planes[2])
+    ssao = _f(planes[3]) if len(planes) > 3 and planes[3] is not None else None
+    out = np.zeros((h, w, 4), np.float32)
+    disc = np.zeros((h, w), np.uint8)
+    lutc = _f(env["lut"])
+    pc = _f(point_cubes) if point_cubes is not None else None
+    sm = _f(spot_maps) if spot_maps is not None else None
+    dm = _f(dir_map) if dir_map is not None else None
+    q = lambda a: _p(a) if a is not None else None
+    hlsl_ref().hlslref_forward_image(
+        C.byref(pf), C.byref(pv), _p(p0), _p(p1), _p(p2), q(ssao), C.c_int(w), C.c_int(h), mats, tex, C.c_int(n), C.c_int(int(alpha_mask)),
+        _p(_f(env["diff"])), C.c_int(env["diff_res"]), _p(_f(env["spec"])), C.c_int(env["spec_res"]), C.c_int(env["spec_mips"]),
+        _p(lutc), C.c_int(lutc.shape[1]), C.c_int(lutc.shape[0]),
+        q(pc), C.c_int(point_res), q(sm), C.c_int(sm.shape[2] if sm is not None else 0), C.c_int(sm.shape[1] if sm is not None else 0),
+        q(dm), C.c_int(dm.shape[1] if dm is not None else 0), C.c_int(dm.shape[0] if dm is not None else 0),
+        _p(out), disc.ctypes.data_as(C.c_void_p))
+    return out, disc.astype(bool)
+
+
+def forward_lighting_shadowed_e(pf, pv, planes, diff_cube, diff_res, spec_cube, spec_res, spec_mips, lut,
+                                point_cubes=None, point_res=0, spot_maps=None, dir_map=None, threads=None) -> np.ndarray:
+    """orc_forward_lighting_shadowed with the emissive plane (planes[3]) passed through."""
+    pos, nrm, alb = (_f(p) for p in planes[:3])
+    em = _f(planes[3]) if len(planes) > 3 and planes[3] is not None else None
+    h, w = pos.shape[:2]
+    out = np.zeros((h, w, 4), np.float32)
+    lutc = _f(lut)
+    pc = _f(point_cubes) if point_cubes is not None else None
+    sm = _f(spot_maps) if spot_maps is not None else None
+    dm = _f(dir_map) if dir_map is not None else None
+    q = lambda a: _p(a) if a is not None else None
+    lib().orc_forward_lighting_shadowed_e(
+        C.byref(pf), C.byref(pv), _p(pos), _p(nrm), _p(alb), q(em), C.c_int(w), C.c_int(h),
+        _p(_f(diff_cube)), C.c_int(diff_res), _p(_f(spec_cube)), C.c_int(spec_res), C.c_int(spec_mips),
+        _p(lutc), C.c_int(lutc.shape[1]), C.c_int(lutc.shape[0]),
+        q(pc), C.c_int(point_res), q(sm), C.c_int(sm.shape[2] if sm is not None else 0), C.c_int(sm.shape[1] if sm is not None else 0),
+        q(dm), C.c_int(dm.shape[1] if dm is not None else 0), C.c_int(dm.shape[0] if dm is not None else 0),
+        _p(out), C.c_int(threads or cpu_threads()))
+    return out
