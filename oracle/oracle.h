@@ -5,8 +5,14 @@
 // golden vectors or numeric tests for this path — the restatement is pinned by
 //   (1) the FidelityFX A_CPU setup functions compiled from the reference's own headers
 //       (oracle/_ref/libffxref.so, built by oracle/Makefile; tests/test_oracle_pins.py), and
-//   (2) the analytic known-answer values derived in SURVEY.md §8(c) (tests/golden/kat.json).
-// Everything else is "parity unpinned" by the reference itself and says so in DESIGN.md.
+//   (2) the analytic known-answer values derived in SURVEY.md §8(c) (tests/golden/kat.json),
+//   (3) the reference's own code where it compiles here: stb codec / resizer, Image.cpp, DXGIUtils.cpp MipImage,
+//       PostProcess.cpp, LightingConstantBufferData.h (oracle/_ref/lib*.so, tests/test_*_ref.py), and
+//   (4) the reference's SHADER TEXT compiled as C++ (oracle/_ref/libhlslref.so = Shaders/*.hlsl through
+//       ref_shim/hlsl_to_cpp.py + ref_shim/hlsl_compat/hlsl_compat.h): tests/test_hlsl_ref.py requires this oracle to
+//       equal it bit for bit (whole PSMain incl. shadowed casters, tonemapper, blur, IBL integrals, skydome, reflection
+//       composite, CAS / EASU / RCAS). What stays a decision is D3D's unspecified intrinsic and filter rounding
+//       (hlsl_math.h, the samplers below) — see DESIGN.md §5.
 #pragma once
 #include "hlsl_math.h"
 #include "../include/vq_shader_data.h"

@@ -4,8 +4,9 @@
 // (Shaders/Lighting.hlsl:79-272, Shaders/ForwardLighting.hlsl:321-377), restated as scalar C++ over linear R32F shadow
 // maps. GROUNDWORK for the (f).4 row: the product path still lights casters with shadow factor 1 (no depth producer
 // headless); this file fixes the semantics the CUDA path will have to reproduce once shadow maps are an input.
-// PARITY UNPINNED: the reference ships no vectors for it and its HLSL cannot run here. Decisions (D3D behaviour that is
-// not in the source), to be kept identical in the kernel:
+// PARITY: the reference ships no vectors for it; pinned bit for bit against the reference's own Lighting.hlsl /
+// ForwardLighting.hlsl text compiled as C++ (oracle/_ref/libhlslref.so, tests/test_hlsl_ref.py::test_forward_psmain_shadowed_bit_exact).
+// Decisions (D3D behaviour that is not in the source), to be kept identical in the kernel:
 //   * `PointSampler` is POINT filtering with WRAP addressing (RootSignatures.cpp:148: EDefaultSampler::POINT_WRAP at s1):
 //     a 2-D tap reads texel (floor(u*W) mod W, floor(v*H) mod H); the mip is always 0 (shadow maps have one);
 //   * a cube tap selects the face as D3D does (largest |component|, ties X > Y > Z: DirectionToCubeFace) and reads

@@ -1,6 +1,7 @@
 """CPU: the §8(f).1 oracle (oracle/oracle_surface.cpp) against independent restatements and known answers.
 The reference holds no golden vectors for this path: parity unpinned by the reference itself; the pins
-here are (1) an independent numpy restatement of DXGIUtils.cpp:263-287 and (2) analytic known answers."""
+here are (1) an independent numpy restatement of DXGIUtils.cpp:263-287 and (2) analytic known answers. (The restatement of
+PSMain's surface half is additionally pinned against the reference's shader text compiled as C++: tests/test_hlsl_ref.py.)"""
 import ctypes as C
 
 import numpy as np
