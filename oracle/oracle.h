@@ -133,6 +133,7 @@ float  SamplePointCube(const float* cube, int res, float3 dir);
 float  OmnidirectionalShadowTestPCF(const ShadowTestPCFData& pcf, const float* cube, int res, float3 lightVectorWorldSpace, float fFarPlane); // :113-165
 float  ShadowTestPCF(const ShadowTestPCFData& pcf, const float* map, int w, int h, float2 shadowMapDimensions);             // :168-211
 float  ShadowTestPCF_Directional(const ShadowTestPCFData& pcf, const float* map, int w, int h, float2 shadowMapDimensions); // :215-263
+int    DepthMinPyramid(const float* depth, int w, int h, float* levels, int max_levels);       // DownsampleDepth.hlsl:50-119
 float4 ForwardLighting_PSMain_Shadowed(const VqPerFrameData& cbPerFrame, const VqPerViewLightingData& cbPerView,
                                        float4 position_ao, float4 normal_roughness, float4 albedo_metalness, const float4* emissive,
                                        const Cubemap& texEnvMapDiff, const Cubemap& texEnvMapSpec, const Image& lut,

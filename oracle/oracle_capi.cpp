@@ -428,6 +428,7 @@ void orc_hdr_curves(const float c[3], float lin_to_srgb[3], float srgb_to_lin[3]
     o3(lin_to_srgb, LinearToSRGB(v)); o3(srgb_to_lin, SRGBToLinear(v)); o3(r709_to_2020, Rec709ToRec2020(v));
     o3(r2020_to_709, Rec2020ToRec709(v)); o3(st2084, LinearToST2084(v));
 }
+int orc_depth_min_pyramid(const float* depth, int w, int h, float* levels, int max_levels) { return DepthMinPyramid(depth, w, h, levels, max_levels); }
 // the shadowed pass with the emissive plane (orc_forward_lighting_shadowed predates it and passes none)
 void orc_forward_lighting_shadowed_e(const VqPerFrameData* pf, const VqPerViewLightingData* pv,
                                      const float* position_ao, const float* normal_roughness, const float* albedo_metalness,

@@ -163,4 +163,39 @@ float4 ForwardLighting_PSMain_Shadowed(const VqPerFrameData& cbPerFrame, const V
     return make4(I_total, Surface.roughness);
 }
 
+// ------------------------------------------------------------------------------------------------
+// the hierarchical MIN depth pyramid, DownsampleDepth.hlsl:50-119 = FidelityFX SPD with
+// SpdReduce4 = min(min(v0,v1),min(v2,v3)) (:72) over a D3D mip chain. Level 0 is a copy of the depth buffer (:92-103);
+// level l is max(1, w>>l) x max(1, h>>l); the shader asks for 1 + floor(log2(max(w,h))) mips (:79-82,:108), i.e. levels up to
+// the 1x1 one. SPD works on the 64x64-tile padded domain: source texels outside the image load as 0 (D3D out-of-range Load)
+// and stores outside a level are dropped, so level l+1 = 2x2 MIN of the zero-padded level l. With floor-halved sizes no
+// padded texel is ever read — except once a dimension has been clamped to 1, where the second row / column of the block
+// lies outside and contributes the padded domain's value (0 for the usual depth >= 0: the thin tail of a non-square
+// pyramid collapses to 0; kept as is). Pinned against the shader text compiled as C++ (tests/test_hlsl_ref.py).
+// `levels` is packed level after level; returns the number of levels written (<= max_levels).
+// ------------------------------------------------------------------------------------------------
+int DepthMinPyramid(const float* depth, int w, int h, float* levels, int max_levels) {
+    int n = 1;
+    for (int m = std::max(w, h); m > 1; m >>= 1) ++n;          // 1 + floor(log2(max(w,h)))
+    n = std::min(std::min(n, max_levels), 13);                 // SPD: at most 12 mips below level 0
+    std::vector<float> cur(depth, depth + (size_t)w * h), next;
+    int pw = w, ph = h;                                        // padded-domain size of the current level (ceil-halved)
+    float* out = levels;
+    for (int l = 0; l < n; ++l) {
+        const int lw = std::max(1, w >> l), lh = std::max(1, h >> l);
+        for (int y = 0; y < lh; ++y)
+            for (int x = 0; x < lw; ++x) out[(size_t)y * lw + x] = (x < pw && y < ph) ? cur[(size_t)y * pw + x] : 0.0f;
+        out += (size_t)lw * lh;
+        const int nw = (pw + 1) / 2, nh = (ph + 1) / 2;
+        next.assign((size_t)nw * nh, 0.0f);
+        auto at = [&](int x, int y) { return (x < pw && y < ph) ? cur[(size_t)y * pw + x] : 0.0f; };
+        for (int y = 0; y < nh; ++y)
+            for (int x = 0; x < nw; ++x)
+                next[(size_t)y * nw + x] = std::fmin(std::fmin(at(2 * x, 2 * y), at(2 * x + 1, 2 * y)),
+                                                     std::fmin(at(2 * x, 2 * y + 1), at(2 * x + 1, 2 * y + 1)));
+        cur.swap(next); pw = nw; ph = nh;
+    }
+    return n;
+}
+
 }  // namespace orc

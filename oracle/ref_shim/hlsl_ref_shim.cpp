@@ -12,6 +12,8 @@
 // requires oracle == compiled shader text, bit for bit.
 #include "hlsl_compat.h"
 #include "../../include/vq_shader_data.h"
+#include <pthread.h>
+#include <thread>
 #include <vector>
 
 extern "C" {   // liboracle.so (oracle_capi.cpp)
@@ -60,11 +62,18 @@ namespace easu {     // AMDFidelityFX.hlsl, FSR_EASU_CS=1 (fp32)
 namespace rcas {     // AMDFidelityFX.hlsl, FSR_RCAS_CS=1 (fp32)
 #include "ffx_rcas.inc"
 }
+void (*g_group_barrier)() = nullptr;
+namespace spd {      // AMDFidelityFX.hlsl, FFXSPD_CS=1, SPD_NO_WAVE_OPERATIONS (LDS path). The engine's PSO for it is commented
+#include "ffx_spd.inc"   // out and the section lacks its own #include of SPD/ffx_a.h: the build passes it with --pre-include.
+}
+namespace depth {    // DownsampleDepth.hlsl (the engine's live SPD user: MIN depth pyramid), SPD_NO_WAVE_OPERATIONS
+#include "depth.inc"
+}
 }  // namespace hl
 
 namespace {
 
-enum Kind { K_NULL = 0, K_TEX8, K_EQUIRECT, K_CUBE, K_LUT, K_PLANE1_POINT, K_R32_2D_ARRAY, K_R32_CUBE_ARRAY, K_IMAGE4, K_IMAGE2, K_IMAGE3IN4, K_CONST };
+enum Kind { K_NULL = 0, K_TEX8, K_EQUIRECT, K_CUBE, K_LUT, K_PLANE1_POINT, K_R32_2D_ARRAY, K_R32_CUBE_ARRAY, K_IMAGE4, K_IMAGE2, K_IMAGE3IN4, K_IMAGE1, K_CONST };
 struct Binding { int kind; const void* ptr; void* wptr; int w, h, levels; float constant; };
 Binding g_bind[64];
 float g_ddx[2], g_ddy[2];   // implicit derivatives of the scaled uv for the pixel being shaded (see forward_image)
@@ -100,12 +109,19 @@ void fetch(void*, int tid, int /*sid*/, int kind, const float c[4], float lod, f
             if (x < 0 || y < 0 || x >= b.w || y >= b.h) return;                  // out-of-range Load reads 0
             const float* p = img + ((size_t)y * b.w + x) * 4; out[0] = p[0]; out[1] = p[1]; out[2] = p[2]; out[3] = p[3]; return;
         }
+        case K_IMAGE1: {                                                        // R32F plane: Load (0 outside), size query
+            if (kind == 7) { out[0] = (float)b.w; out[1] = (float)b.h; return; }
+            const int x = (int)c[0], y = (int)c[1];
+            if (x < 0 || y < 0 || x >= b.w || y >= b.h) return;
+            out[0] = ((const float*)b.ptr)[(size_t)y * b.w + x]; return;
+        }
         case K_IMAGE2: { const float* p = (const float*)b.ptr + ((size_t)(int)c[1] * b.w + (int)c[0]) * 2; out[0] = p[0]; out[1] = p[1]; return; }
     }
 }
 void store(void*, int tid, int x, int y, const float v[4]) {
     const Binding& b = g_bind[tid];
     if (x < 0 || y < 0 || x >= b.w || y >= b.h) return;                          // out-of-range UAV writes are dropped
+    if (b.kind == K_IMAGE1) { ((float*)b.wptr)[(size_t)y * b.w + x] = v[0]; return; }
     const int n = b.kind == K_IMAGE2 ? 2 : (b.kind == K_IMAGE3IN4 ? 3 : 4);       // K_IMAGE3IN4: float3 UAV over an RGBA plane
     float* p = (float*)b.wptr + ((size_t)y * b.w + x) * (b.kind == K_IMAGE2 ? 2 : 4);
     for (int i = 0; i < n; ++i) p[i] = v[i];
@@ -219,6 +235,20 @@ void forward_image_impl(PSMainFn psmain, CBO& cbPerObject,
                 out_discarded[(size_t)y * width + x] = 1;
             }
         }
+}
+
+// One workgroup of a shader that uses groupshared memory and barriers: one OS thread per lane, GroupMemoryBarrierWithGroupSync
+// = a pthread barrier over all lanes. Workgroups run one after the other (any order is legal for a dispatch).
+pthread_barrier_t g_bar;
+void bar_wait() { pthread_barrier_wait(&g_bar); }
+template <class F> void run_workgroup(int lanes, F lane) {
+    pthread_barrier_init(&g_bar, nullptr, (unsigned)lanes);
+    hl::g_group_barrier = bar_wait;
+    std::vector<std::thread> th;
+    th.reserve((size_t)lanes);
+    for (int i = 0; i < lanes; ++i) th.emplace_back(lane, i);
+    for (auto& t : th) t.join();
+    pthread_barrier_destroy(&g_bar);
 }
 
 template <class F> static void dispatch16(int w, int h, F csmain) {
@@ -404,6 +434,57 @@ void hlslref_fsr_rcas(const uint32_t c[4], const float* in, float* out, int w, i
     hl::rcas::RCASInputTexture.id = T_IN; hl::rcas::RCASOutputTexture.id = T_OUT;
     bind(T_IN, K_IMAGE4, in, w, h, 1); bind(T_OUT, K_IMAGE3IN4, nullptr, w, h, 1, 0.0f, out);
     dispatch16(w, h, hl::rcas::FSR_RCAS_CSMain);
+}
+
+
+// ---- FidelityFX SPD through the engine's two wrappers ----------------------------------------------------------------
+// levels: packed float4 mip chain, level 0 = the source (w x h), level l = max(1, w>>l) x max(1, h>>l); the shader writes
+// levels 1..mips. Constants as SpdSetup computes them for the full rectangle (oracle / libffxref).
+void hlslref_spd_downsample(float* levels, int w, int h, int n_levels, uint32_t mips, uint32_t num_work_groups,
+                            uint32_t wg_off_x, uint32_t wg_off_y, uint32_t dispatch_x, uint32_t dispatch_y) {
+    install();
+    hl::spd::mips = mips; hl::spd::numWorkGroups = num_work_groups; hl::spd::workGroupOffset = hl::uint2(wg_off_x, wg_off_y);
+    static hl::spd::SpdGlobalAtomicBuffer counter; counter = hl::spd::SpdGlobalAtomicBuffer{};
+    hl::spd::spdGlobalAtomic.data = &counter;
+    size_t off = 0;
+    for (int l = 0; l < 13; ++l) {
+        const int id = 32 + l;
+        hl::spd::imgDst[l].id = id;
+        if (l < n_levels) {
+            const int lw = (w >> l) > 0 ? (w >> l) : 1, lh = (h >> l) > 0 ? (h >> l) : 1;
+            bind(id, K_IMAGE4, levels + off * 4, lw, lh, 1, 0.0f, levels + off * 4);
+            off += (size_t)lw * lh;
+        } else g_bind[id] = Binding{};
+    }
+    hl::spd::imgDst6.id = 32 + 6;
+    for (uint32_t gy = 0; gy < dispatch_y; ++gy)
+        for (uint32_t gx = 0; gx < dispatch_x; ++gx)
+            run_workgroup(256, [&](int lane) { hl::spd::SPD_CSMain(hl::uint3(gx, gy, 0u), (uint32_t)lane); });
+}
+// DownsampleDepth.hlsl CSMain: level 0 = copy of the depth buffer, levels 1.. = MIN pyramid. One 32x8 group per 64x64 texels.
+void hlslref_depth_pyramid(const float* depth, int w, int h, float* levels, int n_levels) {
+    install();
+    hl::depth::uImageDimensionsXY = hl::int2(w, h);
+    static uint32_t counter; counter = 0;
+    hl::depth::g_global_atomic.data = &counter;
+    hl::depth::g_depth_buffer.id = T_IN; bind(T_IN, K_IMAGE1, depth, w, h, 1);
+    size_t off = 0;
+    for (int l = 0; l < 13; ++l) {
+        const int id = 32 + l;
+        hl::depth::g_downsampled_depth_buffer[l].id = id;
+        if (l < n_levels) {
+            const int lw = (w >> l) > 0 ? (w >> l) : 1, lh = (h >> l) > 0 ? (h >> l) : 1;
+            bind(id, K_IMAGE1, levels + off, lw, lh, 1, 0.0f, levels + off);
+            off += (size_t)lw * lh;
+        } else g_bind[id] = Binding{};
+    }
+    const uint32_t gxn = (uint32_t)((w + 63) / 64), gyn = (uint32_t)((h + 63) / 64);
+    for (uint32_t gy = 0; gy < gyn; ++gy)
+        for (uint32_t gx = 0; gx < gxn; ++gx)
+            run_workgroup(256, [&](int lane) {
+                const uint32_t tx = (uint32_t)lane & 31u, ty = (uint32_t)lane >> 5;
+                hl::depth::CSMain(hl::uint3(gx * 32u + tx, gy * 8u + ty, 0u), hl::uint3(gx, gy, 0u), (uint32_t)lane);
+            });
 }
 
 }  // extern "C"

@@ -535,3 +535,23 @@ def forward_lighting_shadowed_e(pf, pv, planes, diff_cube, diff_res, spec_cube, 
         q(dm), C.c_int(dm.shape[1] if dm is not None else 0), C.c_int(dm.shape[0] if dm is not None else 0),
         _p(out), C.c_int(threads or cpu_threads()))
     return out
+
+
+def depth_min_pyramid(depth):
+    """[H,W] float32 depth -> list of levels (level 0 = copy, then 2x2 MIN, D3D mip-chain sizes), oracle_shadow.cpp DepthMinPyramid"""
+    d = _f(depth)
+    h, w = d.shape
+    dims = []
+    l = 0
+    while True:
+        dims.append((max(1, w >> l), max(1, h >> l)))
+        if dims[-1] == (1, 1) or l == 12:
+            break
+        l += 1
+    buf = np.zeros(sum(a * b for a, b in dims), np.float32)
+    n = lib().orc_depth_min_pyramid(_p(d), C.c_int(w), C.c_int(h), _p(buf), C.c_int(len(dims)))
+    out, o = [], 0
+    for (lw, lh) in dims[:n]:
+        out.append(buf[o:o + lw * lh].reshape(lh, lw))
+        o += lw * lh
+    return out

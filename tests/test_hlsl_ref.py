@@ -371,3 +371,60 @@ def test_fsr_rcas_csmain_bit_exact(w, h, stops):
     got = np.zeros_like(img); got[..., 3] = 1.0
     orc.hlsl_ref().hlslref_fsr_rcas(con, orc._p(img), orc._p(got), C.c_int(w), C.c_int(h))
     assert _same(orc.fsr_rcas(con, img), got)
+
+
+# ---- FidelityFX SPD (ffx_spd.h, LDS path) through AMDFidelityFX.hlsl's callbacks: one OS thread per lane, real barriers ------
+def _mip_dims(w, h, n):
+    return [(max(1, w >> l), max(1, h >> l)) for l in range(n)]
+
+
+@pytest.mark.parametrize("w,h", [(128, 128), (256, 64), (64, 64), (192, 128), (512, 256), (100, 60), (70, 130), (33, 17)])
+def test_spd_downsample_bit_exact(w, h):
+    """every mip the 256-lane workgroups produce (LDS reductions, the last-workgroup tail from mip 6 on) == the oracle's
+    level-by-level restatement, including its claim about which levels reduce column-major"""
+    rng = np.random.default_rng(150 + w)
+    src = (rng.uniform(0, 1, (h, w, 4)) ** 2 * 3).astype(np.float32)
+    (dx, dy), (ox, oy), (nwg, mips) = orc.spd_setup((0, 0, w, h))
+    want = orc.spd_downsample(src, mips)
+    # the product (and the oracle) stop where a dimension would drop below 1 (DESIGN.md K10): the D3D mip chain goes on with
+    # max(1, .) sizes and SPD fills those levels from out-of-range (zero) texels; they are left unbound here (stores dropped)
+    n_levels = len(want) + 1
+    dims = _mip_dims(w, h, n_levels)
+    levels = np.zeros((sum(a * b for a, b in dims), 4), np.float32)
+    levels[: w * h] = src.reshape(-1, 4)
+    orc.hlsl_ref().hlslref_spd_downsample(orc._p(levels), C.c_int(w), C.c_int(h), C.c_int(n_levels), C.c_uint32(mips), C.c_uint32(nwg),
+                                          C.c_uint32(ox), C.c_uint32(oy), C.c_uint32(dx), C.c_uint32(dy))
+    o = w * h
+    assert 1 <= len(want) <= mips
+    for l, lvl in enumerate(want, start=1):
+        lw, lh = dims[l]
+        got = levels[o: o + lw * lh].reshape(lh, lw, 4)
+        o += lw * lh
+        assert lvl.shape[:2] == (lh, lw)
+        assert _same(lvl, got), (l, np.argwhere(_bits(lvl) != _bits(got))[:4])
+
+
+@pytest.mark.parametrize("w,h", [(128, 128), (64, 64), (200, 120), (65, 33), (31, 70), (256, 16), (5, 3), (1, 1)])
+def test_depth_min_pyramid_bit_exact(w, h):
+    """DownsampleDepth.hlsl CSMain (level 0 copy + SPD with the MIN reduction, D3D mip-chain sizes, zero padding) == oracle"""
+    rng = np.random.default_rng(160 + w)
+    depth = rng.uniform(0.05, 1.0, (h, w)).astype(np.float32)
+    want = orc.depth_min_pyramid(depth)
+    dims = [lv.shape[::-1] for lv in want]
+    assert dims[0] == (w, h) and dims[-1] == (1, 1) and len(want) == 1 + int(np.floor(np.log2(max(w, h))))
+    levels = np.full(sum(a * b for a, b in dims), -1.0, np.float32)
+    orc.hlsl_ref().hlslref_depth_pyramid(orc._p(depth), C.c_int(w), C.c_int(h), orc._p(levels), C.c_int(len(dims)))
+    o = 0
+    for l, lv in enumerate(want):
+        lw, lh = dims[l]
+        got = levels[o:o + lw * lh].reshape(lh, lw)
+        o += lw * lh
+        assert _same(lv, got), (l, lv, got)
+    # closed form where no dimension has been clamped yet: plain 2x2 MIN of the level above
+    for l in range(1, len(want)):
+        if (w >> l) >= 1 and (h >> l) >= 1:
+            up = want[l - 1]
+            lh, lw = want[l].shape
+            ref = np.minimum(np.minimum(up[0:2 * lh:2, 0:2 * lw:2], up[0:2 * lh:2, 1:2 * lw:2]),
+                             np.minimum(up[1:2 * lh:2, 0:2 * lw:2], up[1:2 * lh:2, 1:2 * lw:2]))
+            assert np.array_equal(ref, want[l])
