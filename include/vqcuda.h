@@ -380,6 +380,41 @@ VQ_API int vq_apply_reflections(VqContext* ctx, VqImage scene_color, VqImage ref
                                 const VqImage* bounding_volumes, void* stream);
 
 /* ------------------------------------------------------------------------------------------
+ * SURVEY §8(f).4  Shadowed casters and the hierarchical MIN depth pyramid.
+ *   vq_forward_lighting_shadowed: vq_forward_lighting with the shadow maps PSMain binds (ForwardLighting.hlsl:87-89):
+ *     the caster lists are multiplied by OmnidirectionalShadowTestPCF / ShadowTestPCF and a shadowing directional light
+ *     by ShadowTestPCF_Directional (Lighting.hlsl:79-272; ForwardLighting.hlsl:321-377). Maps are linear R32F, tightly
+ *     packed, POINT-sampled with WRAP addressing (RootSignatures.cpp:148):
+ *       point_cubes      [caster][face][y][x], value = distance / light range   (TextureCubeArray, t22)
+ *       spot_maps        [caster][y][x],       value = light-space depth         (Texture2DArray, t16)
+ *       directional_map  [y][x]                                                   (Texture2D, t13)
+ *     A NULL map lights that light type unshadowed (factor 1). shadowViews / shadowViewDirectional and the
+ *     f2*ShadowMapDimensions fields of per_frame are read as the shader reads them.
+ *   vq_depth_min_pyramid: replaces CSMain (DownsampleDepth.hlsl:85-119 = FidelityFX SPD with a MIN reduction): level 0 is
+ *     a copy of the R32F depth image, level l = max(1, w>>l) x max(1, h>>l) holds the 2x2 minimum of the zero-padded
+ *     level above; `levels` receives n_levels (<= vq_depth_pyramid_level_count = 1 + floor(log2(max(w,h))), at most 13)
+ *     tightly packed levels, vq_depth_pyramid_texel_count() floats in total.
+ *   STATUS: compiled for sm_100a and checked against the oracle's semantics on paper only — not yet run on a GPU.
+ * ------------------------------------------------------------------------------------------ */
+typedef struct VqShadowMaps {
+    const void* point_cubes;     int32_t point_res;
+    const void* spot_maps;       int32_t spot_width, spot_height;
+    const void* directional_map; int32_t directional_width, directional_height;
+} VqShadowMaps;
+VQ_API int vq_forward_lighting_shadowed(VqContext* ctx,
+                                        const VqPerFrameData* per_frame,
+                                        const VqPerViewLightingData* per_view,
+                                        const VqGBuffer* gbuffer,
+                                        const VqEnvironmentMaps* env,
+                                        const VqShadowMaps* shadow_maps,
+                                        VqImage out_color,
+                                        int row_begin, int row_end,
+                                        void* stream);
+VQ_API int      vq_depth_pyramid_level_count(int width, int height);
+VQ_API uint64_t vq_depth_pyramid_texel_count(int width, int height, int levels);
+VQ_API int vq_depth_min_pyramid(VqContext* ctx, VqImage depth_r32f, void* levels, int n_levels, void* stream);
+
+/* ------------------------------------------------------------------------------------------
  * Blocking host-buffer entry points: the same passes called with HOST pointers (what an engine
  * integration that keeps its frame data in system memory would call). Each call uploads the
  * inputs, runs the kernel(s), downloads the result and returns when the result is in `out`.

@@ -130,6 +130,12 @@ class EnvironmentMaps(C.Structure):
     _fields_ = [("irradiance_diffuse", Cubemap), ("irradiance_specular", Cubemap), ("brdf_lut", Image)]
 
 
+class ShadowMaps(C.Structure):            # include/vqcuda.h VqShadowMaps
+    _fields_ = [("point_cubes", C.c_void_p), ("point_res", C.c_int32),
+                ("spot_maps", C.c_void_p), ("spot_width", C.c_int32), ("spot_height", C.c_int32),
+                ("directional_map", C.c_void_p), ("directional_width", C.c_int32), ("directional_height", C.c_int32)]
+
+
 class MaterialData(C.Structure):          # include/vq_shader_data.h VqMaterialData (LightingConstantBufferData.h:126-143)
     _fields_ = [("diffuse", Float3), ("alpha", f32), ("emissiveColor", Float3), ("emissiveIntensity", f32),
                 ("specular", Float3), ("normalMapMipBias", f32), ("uvScaleOffset", Float4),
@@ -172,6 +178,7 @@ ABI_SYMBOLS = [
     "vq_texture_build_mips", "vq_material_table_create", "vq_material_table_destroy", "vq_gbuffer_from_materials",
     "vq_hdr_parse", "vq_hdr_decode", "vq_hdr_load_host", "vq_hdr_encode_rgbe", "vq_hdr_pack_file", "vq_hdr_save_host",
     "vq_skydome", "vq_apply_reflections", "vq_specular_prefilter_multi", "vq_image_resize", "vq_resize_axis_table",
+    "vq_forward_lighting_shadowed", "vq_depth_pyramid_level_count", "vq_depth_pyramid_texel_count", "vq_depth_min_pyramid",
 ]
 
 
@@ -248,6 +255,12 @@ def _load() -> C.CDLL:
     lib.vq_resize_axis_table.argtypes = [C.c_int, C.c_int, P(C.c_int), P(C.c_int), P(f32), C.c_int, P(C.c_int)]
     lib.vq_skydome.argtypes = [vp, P(Matrix), Pyramid, P(Image), Image, C.c_int, C.c_int, vp]
     lib.vq_apply_reflections.argtypes = [vp, Image, Image, P(Image), vp]
+    lib.vq_forward_lighting_shadowed.argtypes = [vp, P(PerFrameData), P(PerViewLightingData), P(GBuffer), P(EnvironmentMaps),
+                                                 P(ShadowMaps), Image, C.c_int, C.c_int, vp]
+    lib.vq_depth_pyramid_level_count.argtypes = [C.c_int, C.c_int]
+    lib.vq_depth_pyramid_texel_count.argtypes = [C.c_int, C.c_int, C.c_int]
+    lib.vq_depth_pyramid_texel_count.restype = C.c_uint64
+    lib.vq_depth_min_pyramid.argtypes = [vp, Image, vp, C.c_int, vp]
     return lib
 
 
@@ -349,6 +362,14 @@ def resize_axis_table(in_size: int, out_size: int):
 
 
 # ---- descriptors from torch tensors ------------------------------------------------------------
+def depth_pyramid_level_count(w: int, h: int) -> int:
+    return int(lib.vq_depth_pyramid_level_count(w, h))
+
+
+def depth_pyramid_texel_count(w: int, h: int, levels: int) -> int:
+    return int(lib.vq_depth_pyramid_texel_count(w, h, levels))
+
+
 def image_of(t, channels: int = 4) -> Image:
     """[H, W, channels] float32 tensor (CUDA, or pinned/pageable host for the *_host calls)."""
     assert t.dim() == 3 and t.shape[2] == channels and t.dtype.is_floating_point and t.element_size() == 4
@@ -422,6 +443,33 @@ class Context:
         _check(lib.vq_forward_lighting_multi(self._h, C.byref(per_frame), C.byref(per_view), C.byref(gbuffer), C.byref(env), arr,
                                              len(out_images), dst_row_offset, row_begin, h if row_end is None else row_end,
                                              _stream_ptr(stream)))
+
+    # the pass with shadow maps bound, and the MIN depth pyramid (compiled, not yet run on a GPU: DESIGN.md 8)
+    def forward_lighting_shadowed(self, per_frame, per_view, gbuffer: GBuffer, env: EnvironmentMaps, out, point_cubes=None,
+                                  spot_maps=None, directional_map=None, row_begin=0, row_end=None, stream=None):
+        """point_cubes [casters,6,R,R], spot_maps [casters,H,W], directional_map [H,W]: contiguous float32 CUDA tensors or None"""
+        sm = ShadowMaps()
+        if point_cubes is not None:
+            assert point_cubes.is_contiguous() and point_cubes.dim() == 4 and point_cubes.shape[1] == 6 and point_cubes.shape[2] == point_cubes.shape[3]
+            sm.point_cubes, sm.point_res = point_cubes.data_ptr(), point_cubes.shape[2]
+        if spot_maps is not None:
+            assert spot_maps.is_contiguous() and spot_maps.dim() == 3
+            sm.spot_maps, sm.spot_width, sm.spot_height = spot_maps.data_ptr(), spot_maps.shape[2], spot_maps.shape[1]
+        if directional_map is not None:
+            assert directional_map.is_contiguous() and directional_map.dim() == 2
+            sm.directional_map, sm.directional_width, sm.directional_height = directional_map.data_ptr(), directional_map.shape[1], directional_map.shape[0]
+        o = image_of(out)
+        _check(lib.vq_forward_lighting_shadowed(self._h, C.byref(per_frame), C.byref(per_view), C.byref(gbuffer), C.byref(env),
+                                                C.byref(sm), o, row_begin, o.height if row_end is None else row_end, _stream_ptr(stream)))
+
+    def depth_min_pyramid(self, depth, levels_out, n_levels=None, stream=None):
+        """depth: [H,W] float32 CUDA tensor (dense rows); levels_out: flat float32 CUDA tensor of depth_pyramid_texel_count floats"""
+        assert depth.dim() == 2 and depth.stride(1) == 1 and depth.element_size() == 4
+        h, w = depth.shape
+        n = depth_pyramid_level_count(w, h) if n_levels is None else n_levels
+        assert levels_out.is_contiguous() and levels_out.numel() >= depth_pyramid_texel_count(w, h, n)
+        _check(lib.vq_depth_min_pyramid(self._h, Image(depth.data_ptr(), w, h, depth.stride(0) * 4), levels_out.data_ptr(), n,
+                                        _stream_ptr(stream)))
 
     def forward_lighting_host(self, per_frame, per_view, host_gbuffer: GBuffer, env: EnvironmentMaps, host_out):
         _check(lib.vq_forward_lighting_host(self._h, C.byref(per_frame), C.byref(per_view), C.byref(host_gbuffer),
