@@ -9,7 +9,8 @@ A "step" is ONE forward-PBR lighting pass (K1) over a 3840x2160 synthetic G-buff
   roofline   = algorithmic 64 B/pixel / kernel time, against the measured HBM copy peak
   cpu_baseline = the scalar oracle (CPU port of the HLSL) on this box's host cores, bounded row sample
   extra      = per-kernel timings for the other SURVEY.md §8 rows (post chain @4K, IBL integrals)
-`--impl reference` times the CPU oracle instead (the reference's D3D12/HLSL path cannot run here).
+`--impl reference` times the reference's shader text compiled for the CPU (oracle/_ref/libhlslref.so), or the CPU oracle when that
+library is absent (the reference's D3D12/HLSL path itself cannot run here).
 """
 from __future__ import annotations
 
@@ -388,6 +389,24 @@ def ibl_specular_strong_scaling(ctx, vq, torch, dist, rank, world, hdri_w=4096, 
 
 # ------------------------------------------------------------------------------------------------
 def cpu_reference_forward(planes, rows_target_s=12.0, env=None, threads=None):
+    """cpu_baseline of the GPU arm: the scalar oracle over a bounded row sample of the 4K workload. Preferred form: one process per
+    host core, run in a FRESH interpreter (`bench.py --impl cpu-port`: no fork of this process, which holds a CUDA context) —
+    on the pool's boxes processes scale where the threads of one process do not. Fallback: std::thread row split in this process."""
+    try:
+        env_ = {k: v for k, v in os.environ.items() if k not in ("RANK", "LOCAL_RANK", "WORLD_SIZE")}
+        r = subprocess.run([sys.executable, os.path.abspath(__file__), "--impl", "cpu-port", "--steps", "4", "--warmup", "1"],
+                           capture_output=True, text=True, timeout=420, env=env_)
+        j = json.loads([l for l in r.stdout.splitlines() if l.startswith("{")][-1])
+        px = j["rows"] * W4K
+        return {"value": round(j["value"], 4), "unit": UNIT, "cores": j["procs"], "kind": "port",
+                "sample": f"4 x ({j['rows']} of {H4K} rows x {W4K} px of the same 4K G-buffer) = {4 * px} px at {j['ms']:.1f} ms per pass, scalar C++ "
+                          f"oracle, one forked process per host core ({j['one_process_mpx_s']} Mpixels/s per process)"}
+    except Exception as ex:
+        print(f"# multi-process cpu_baseline unavailable ({ex!r}); using threads", file=sys.stderr)
+    return _cpu_reference_forward_threads(planes, rows_target_s, env, threads)
+
+
+def _cpu_reference_forward_threads(planes, rows_target_s=12.0, env=None, threads=None):
     """The scalar oracle on `threads` host threads over a bounded row sample of the 4K workload."""
     import oracle_lib as orc
     from vqengine_b200 import synth
@@ -445,35 +464,120 @@ def cpu_env():
     return small_env(hdri_w=256, hdri_h=128, diff_res=16, spec_res=64, spec_mips=6, lut=64, seed=77)
 
 
+_REF_JOB = {}
+
+
+def _cpu_rows_worker(rng):
+    """forked worker: rows [rb,re) of the band through the reference's shader text compiled as C++ ('text') or the scalar port ('port')"""
+    import oracle_lib as orc
+    j = _REF_JOB
+    rb, re = rng
+    if j["kind"] == "text":
+        orc.hlsl_forward_gbuffer(j["pf"], j["pv"], j["planes"], *j["env"], row_begin=rb, row_end=re, out=j["out"])
+        return float(j["out"][rb:re, :, :3].sum())
+    return float(orc.forward_lighting(j["pf"], j["pv"], j["planes"], *j["env"], rb, re, 1)[rb:re, :, :3].sum())
+
+
+def _cpu_arm(kind, steps, warmup, planes, pf, pv, a, budget_s=60.0):
+    """`kind` over a bounded band of the 4K G-buffer, one FORKED PROCESS per host core (the compiled shader's cbuffers are process
+    globals; and processes were measured to scale where threads of one process did not on the pool's boxes).
+    Returns dict(value Mpx/s, ms, rows, procs, one_process_mpx_s)."""
+    import multiprocessing as mp
+    import numpy as np
+    import oracle_lib as orc
+    procs = orc.cpu_threads()
+    band = planes[0].shape[0]
+    _REF_JOB.update(kind=kind, pf=pf, pv=pv, planes=planes, env=a, out=np.zeros((band, W4K, 4), np.float32))
+    t0 = time.perf_counter()
+    _cpu_rows_worker((0, 4))
+    one = 4 * W4K / (time.perf_counter() - t0)                           # px/s of one process
+    with mp.get_context("fork").Pool(procs) as pool:
+        def step(rows):
+            n = min(procs, rows)
+            return sum(pool.map(_cpu_rows_worker, [(rows * i // n, rows * (i + 1) // n) for i in range(n)], chunksize=1))
+        t0 = time.perf_counter(); step(min(band, procs)); dt = time.perf_counter() - t0
+        rate = min(band, procs) * W4K / dt                                # measured parallel rate (a box may grant fewer CPUs than it lists)
+        rows = int(min(band, max(procs, budget_s * rate / W4K / (steps + warmup))))
+        for _ in range(warmup):
+            step(rows)
+        t0 = time.perf_counter()
+        work = 0.0
+        for _ in range(steps):
+            work += step(rows)
+        dt = (time.perf_counter() - t0) / steps
+    assert work != 0.0
+    return {"value": rows * W4K / dt / 1e6, "ms": dt * 1e3, "rows": rows, "procs": procs, "one_process_mpx_s": round(one / 1e6, 3)}
+
+
+def _cpu_workload():
+    from vqengine_b200 import synth
+    env = cpu_env()
+    planes = synth.gbuffer(W4K, 512, seed=synth.SEED_BASE + 3)   # a 512-row band of the 4K G-buffer
+    pf, pv = synth.scene_constants(W4K, H4K, env["spec_mips"])
+    a = (env["diff"], env["diff_res"], env["spec"], env["spec_res"], env["spec_mips"], env["lut"])
+    return planes, pf, pv, a
+
+
+def run_cpu_port(args):
+    """hidden helper (`--impl cpu-port`): the scalar port, one process per core, as one JSON line. The GPU arm runs this in a fresh
+    interpreter for its cpu_baseline leg (no fork of a process that holds a CUDA context)."""
+    planes, pf, pv, a = _cpu_workload()
+    r = _cpu_arm("port", args.steps, args.warmup, planes, pf, pv, a, budget_s=15.0)
+    print(json.dumps({"impl": "cpu-port", **{k: (round(v, 4) if isinstance(v, float) else v) for k, v in r.items()}}))
+
+
 def run_reference(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
+    import numpy as np
     import oracle_lib as orc
-    from vqengine_b200 import synth
-    env = cpu_env()
-    threads = orc.cpu_threads()
-    planes = synth.gbuffer(W4K, 512, seed=synth.SEED_BASE + 3)   # a 512-row band of the 4K G-buffer
-    pf, pv = synth.scene_constants(W4K, H4K, env["spec_mips"])
-    a = (env["diff"], env["diff_res"], env["spec"], env["spec_res"], env["spec_mips"], env["lut"])
-    # bounded sample: size the per-step row count so that warmup+steps take about a minute in total
-    t0 = time.perf_counter()
-    orc.forward_lighting(pf, pv, planes, *a, 0, 16, threads)
-    rate = 16 * W4K / (time.perf_counter() - t0)
-    rows = int(min(512, max(16, 60.0 * rate / W4K / (args.steps + args.warmup))))
-    for _ in range(args.warmup):
-        orc.forward_lighting(pf, pv, planes, *a, 0, rows, threads)
-    t0 = time.perf_counter()
-    for _ in range(args.steps):
-        orc.forward_lighting(pf, pv, planes, *a, 0, rows, threads)
-    dt = (time.perf_counter() - t0) / args.steps
-    v = rows * W4K / dt / 1e6
-    sample = f"each step = {rows} rows x {W4K} px of the 4K G-buffer through the scalar C++ oracle on {threads} host threads"
+    planes, pf, pv, a = _cpu_workload()
+    port = text = None
+    try:
+        port = _cpu_arm("port", max(2, args.steps // 4), 1, planes, pf, pv, a, budget_s=10.0)
+    except Exception as ex:
+        print(f"# multi-process port unavailable ({ex!r})", file=sys.stderr)
+    try:
+        if orc.hlsl_ref() is not None:
+            # agreement with the port on a few rows (PSMain renormalises the interpolated normal; the G-buffer pass takes it as is)
+            chk = orc.hlsl_forward_gbuffer(pf, pv, planes, *a, row_begin=0, row_end=2)[:2]
+            want = orc.forward_lighting(pf, pv, planes, *a, 0, 2, 1)[:2]
+            rel = float(np.max(np.abs(chk - want) / np.maximum(1.0, np.abs(want))))
+            text = _cpu_arm("text", args.steps, args.warmup, planes, pf, pv, a)
+            text["max_scaled_delta_vs_port"] = rel
+    except Exception as ex:                                        # library missing / fork unavailable: time the port instead
+        print(f"# reference shader text arm unavailable ({ex!r}); timing the CPU port", file=sys.stderr)
+    port_note = (f"the scalar C++ port of the same math on the same box: {port['value']:.2f} Mpixels/s ({port['procs']} processes, "
+                 f"{port['one_process_mpx_s']} per process)") if port else "scalar port not timed"
+    if text is not None:
+        v, ms, kind, cores = text["value"], text["ms"], "reference", text["procs"]
+        sample = (f"each step = {text['rows']} rows x {W4K} px of the 4K G-buffer through the reference's own ForwardLighting.hlsl PSMain "
+                  f"(+ Lighting/BRDF/ShadingMath.hlsl) compiled as C++ (oracle/_ref/libhlslref.so), {cores} forked processes "
+                  f"({text['one_process_mpx_s']} Mpixels/s per process); texture fetches served by the oracle's samplers; max scaled "
+                  f"|delta| vs the port {text['max_scaled_delta_vs_port']:.1e}; {port_note}")
+        note = "the reference's D3D12/HLSL path needs Windows; this arm runs its shader text compiled for the CPU"
+    else:
+        threads = orc.cpu_threads()
+        if port is None:                                           # last resort: threads of this process
+            t0 = time.perf_counter(); orc.forward_lighting(pf, pv, planes, *a, 0, 16, threads)
+            rate = 16 * W4K / (time.perf_counter() - t0)
+            rows = int(min(512, max(16, 60.0 * rate / W4K / (args.steps + args.warmup))))
+            for _ in range(args.warmup):
+                orc.forward_lighting(pf, pv, planes, *a, 0, rows, threads)
+            t0 = time.perf_counter()
+            for _ in range(args.steps):
+                orc.forward_lighting(pf, pv, planes, *a, 0, rows, threads)
+            dt = (time.perf_counter() - t0) / args.steps
+            port = {"value": rows * W4K / dt / 1e6, "ms": dt * 1e3, "rows": rows, "procs": threads}
+        v, ms, kind, cores = port["value"], port["ms"], "port", port["procs"]
+        sample = f"each step = {port['rows']} rows x {W4K} px of the 4K G-buffer through the scalar C++ oracle on {cores} host cores"
+        note = "the reference's D3D12/HLSL path needs Windows; this arm is the CPU port (oracle) of the identical math"
     print(json.dumps({"impl": "reference", "metric": METRIC, "value": round(v, 4), "unit": UNIT, "n_gpus": args.gpus,
-                      "steps": args.steps, "warmup": args.warmup, "ms_per_step": round(dt * 1e3, 3),
+                      "steps": args.steps, "warmup": args.warmup, "ms_per_step": round(ms, 3),
                       "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-                      "config": {"workload": WORKLOAD, "note": "the reference's D3D12/HLSL path needs Windows; this arm is the CPU port (oracle) of the identical math"},
-                      "cpu_baseline": {"value": round(v, 4), "unit": UNIT, "cores": threads, "kind": "port", "sample": sample},
+                      "config": {"workload": WORKLOAD, "note": note},
+                      "cpu_baseline": {"value": round(v, 4), "unit": UNIT, "cores": cores, "kind": kind, "sample": sample},
                       "e2e": {"value": round(v, 4), "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
                       "gpu_launches": 0}))
 
@@ -484,13 +588,15 @@ def main():
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=50)
     ap.add_argument("--warmup", type=int, default=5)
-    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference", "cpu-port"])
     ap.add_argument("--no-extra", action="store_true", help="skip the per-kernel extra section")
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3)
     if args.impl == "reference":
         return run_reference(args)
+    if args.impl == "cpu-port":
+        return run_cpu_port(args)
 
     import numpy as np
     import torch

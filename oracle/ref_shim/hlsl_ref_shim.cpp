@@ -294,6 +294,47 @@ void hlslref_forward_image(const VqPerFrameData* pf, const VqPerViewLightingData
     }
 }
 
+// ForwardLighting.hlsl PSMain driven from a G-buffer (the K1 workload): per pixel the material constants are set to the
+// G-buffer texel (diffuse = albedo, roughness, metalness, emissive; textureConfig = 0, every material map a null SRV, SSAO = 1,
+// fAmbientLightingFactor = the texel's ao), so the UNMODIFIED PSMain text shades exactly what K1 shades. Used by
+// bench.py --impl reference as the reference's own implementation of the path on the CPU (one process per core: the
+// shader's cbuffer globals are per process).
+void hlslref_forward_gbuffer_rows(const VqPerFrameData* pf, const VqPerViewLightingData* pv,
+                                  const float* position_ao, const float* normal_roughness, const float* albedo_metalness,
+                                  const float* emissive /* may be null */, int width, int row_begin, int row_end,
+                                  const float* diff_cube, int diff_res, const float* spec_cube, int spec_res, int spec_mips,
+                                  const float* lut, int lut_w, int lut_h, float* out_color) {
+    install();
+    for (auto& b : g_bind) b = Binding{};
+    bind(T_SSAO, K_CONST, nullptr, 0, 0, 0, 1.0f);
+    bind(T_ENVDIFF, K_CUBE, diff_cube, diff_res, diff_res, 1);
+    bind(T_ENVSPEC, K_CUBE, spec_cube, spec_res, spec_res, spec_mips);
+    bind(T_BRDFLUT, K_LUT, lut, lut_w, lut_h, 1);
+    BIND_FORWARD_RESOURCES(fwd)
+    load_per_frame(hl::fwd::cbPerFrame, *pf); load_per_view(hl::fwd::cbPerView, *pv);
+    VqMaterialData mat{};
+    mat.uvScaleOffset.x = 1.0f; mat.uvScaleOffset.y = 1.0f; mat.alpha = 1.0f;
+    g_ddx[0] = g_ddx[1] = g_ddy[0] = g_ddy[1] = 0.0f;
+    for (int y = row_begin; y < row_end; ++y)
+        for (int x = 0; x < width; ++x) {
+            const size_t o = ((size_t)y * width + x) * 4;
+            mat.diffuse = VqFloat3{albedo_metalness[o], albedo_metalness[o + 1], albedo_metalness[o + 2]};
+            mat.metalness = albedo_metalness[o + 3];
+            mat.roughness = normal_roughness[o + 3];
+            if (emissive) { mat.emissiveColor = VqFloat3{emissive[o], emissive[o + 1], emissive[o + 2]}; mat.emissiveIntensity = emissive[o + 3]; }
+            load_material(hl::fwd::cbPerObject.materialData, mat);
+            hl::fwd::cbPerFrame.fAmbientLightingFactor = position_ao[o + 3];
+            hl::fwd::PSInput In;
+            In.position = hl::float4((float)x + 0.5f, (float)y + 0.5f, 0.0f, 1.0f);
+            In.WorldSpacePosition = hl::float3(position_ao[o], position_ao[o + 1], position_ao[o + 2]);
+            In.WorldSpaceNormal = hl::float3(normal_roughness[o], normal_roughness[o + 1], normal_roughness[o + 2]);
+            In.WorldSpaceTangent = hl::float3(1.0f, 0.0f, 0.0f);
+            In.uv = hl::float2(0.0f, 0.0f);
+            const auto r = hl::fwd::PSMain(In);
+            out_color[o] = r.color.x; out_color[o + 1] = r.color.y; out_color[o + 2] = r.color.z; out_color[o + 3] = r.color.w;
+        }
+}
+
 // ---- scalar probes into BRDF.hlsl / ShadingMath.hlsl / Lighting.hlsl (compiled inside ForwardLighting.hlsl) ---------
 static hl::float3 v3(const float* p) { return hl::float3(p[0], p[1], p[2]); }
 static void o3(float* o, const hl::float3& v) { o[0] = v.x; o[1] = v.y; o[2] = v.z; }

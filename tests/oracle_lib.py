@@ -555,3 +555,17 @@ def depth_min_pyramid(depth):
         out.append(buf[o:o + lw * lh].reshape(lh, lw))
         o += lw * lh
     return out
+
+
+def hlsl_forward_gbuffer(pf, pv, planes, diff_cube, diff_res, spec_cube, spec_res, spec_mips, lut, row_begin=0, row_end=None, out=None):
+    """ForwardLighting.hlsl PSMain (compiled reference text) driven from a G-buffer: rows [row_begin,row_end) -> out [H,W,4]"""
+    pos, nrm, alb = (_f(p) for p in planes[:3])
+    em = _f(planes[3]) if len(planes) > 3 and planes[3] is not None else None
+    h, w = pos.shape[:2]
+    out = np.zeros((h, w, 4), np.float32) if out is None else out
+    lutc = _f(lut)
+    hlsl_ref().hlslref_forward_gbuffer_rows(C.byref(pf), C.byref(pv), _p(pos), _p(nrm), _p(alb), _p(em) if em is not None else None,
+                                            C.c_int(w), C.c_int(row_begin), C.c_int(h if row_end is None else row_end),
+                                            _p(_f(diff_cube)), C.c_int(diff_res), _p(_f(spec_cube)), C.c_int(spec_res), C.c_int(spec_mips),
+                                            _p(lutc), C.c_int(lutc.shape[1]), C.c_int(lutc.shape[0]), _p(out))
+    return out

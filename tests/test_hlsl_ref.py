@@ -428,3 +428,22 @@ def test_depth_min_pyramid_bit_exact(w, h):
             ref = np.minimum(np.minimum(up[0:2 * lh:2, 0:2 * lw:2], up[0:2 * lh:2, 1:2 * lw:2]),
                              np.minimum(up[1:2 * lh:2, 0:2 * lw:2], up[1:2 * lh:2, 1:2 * lw:2]))
             assert np.array_equal(ref, want[l])
+
+
+def test_psmain_driven_from_a_gbuffer_equals_the_forward_oracle():
+    """the K1 workload through the unmodified PSMain text (material constants = G-buffer texel): what bench.py --impl reference
+    times. PSMain renormalises the interpolated normal, the G-buffer path takes it as is: equal up to that rounding."""
+    from vqengine_b200 import synth
+    env = small_env()
+    w, h = 96, 40
+    for emissive in (False, True):
+        planes = synth.gbuffer(w, h, seed=8, emissive=emissive)
+        pf, pv = synth.scene_constants(w, h, env["spec_mips"], seed=8, n_point=4, n_spot=2, casters=False)
+        pf.Lights.directional.shadowing = 0
+        args = (env["diff"], env["diff_res"], env["spec"], env["spec_res"], env["spec_mips"], env["lut"])
+        want = orc.forward_lighting(pf, pv, planes, *args)
+        got = orc.hlsl_forward_gbuffer(pf, pv, planes, *args)
+        assert np.allclose(got, want, rtol=2e-5, atol=2e-6), np.abs(got - want).max()
+        assert (got[..., 3] == want[..., 3]).all()
+        part = orc.hlsl_forward_gbuffer(pf, pv, planes, *args, row_begin=7, row_end=19)
+        assert np.array_equal(part[7:19], got[7:19]) and not part[:7].any() and not part[19:].any()

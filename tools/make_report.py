@@ -86,7 +86,10 @@ if fp:
 out.append("\nIs the CPU baseline (`\"kind\": \"port\"`, the scalar oracle) a fair stand-in for the reference's own code? Measured in the build container "
            "(one core, 256x128 px, 4 textured materials, 3 point + 2 spot + directional lights + IBL; `tests/test_hlsl_ref.py` scene): the oracle "
            "(surface producer + forward pass) takes 653 ns/pixel, the reference's `ForwardLighting.hlsl` `PSMain` compiled as C++ "
-           "(`oracle/_ref/libhlslref.so`) takes 718 ns/pixel for the identical, bit-identical work: the port is not slower than the reference text.")
+           "(`oracle/_ref/libhlslref.so`) takes 718 ns/pixel for the identical, bit-identical work: the port is not slower than the reference text. "
+           "`bench.py --impl reference` now times that compiled shader text itself (one process per core), and both CPU arms use processes instead of "
+           "threads: in the build container 8 threads of one process ran at 1.0x of one thread, 8 forked processes at 5x (10.8 Mpixels/s shader text, "
+           "10-12 Mpixels/s port), so the 25.4 Mpixels/s recorded above on the GPU box (threaded form, 128 listed cores) understates what its CPUs can do.")
 out.append("\n## How these were produced\n")
 out.append("All on `gpurun` B200 boxes from this tree (scripts under `tools/`):\n")
 out.append("* `bash tools/gpu_full.sh` — `pytest -m gpu` (-> `r01_gpu_tests.txt`), `python bench.py` (-> `r01_bench_1gpu.json`), "
