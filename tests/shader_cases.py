@@ -72,7 +72,8 @@ def cases():
     # ---- whole PSMain -------------------------------------------------------------------------------------------------
     def psmain(kind):
         def build():
-            env, mats, chains, planes, pf, pv = _pixel_scene(48, 24, 5, casters=(kind == "shadowed"))
+            w, h, seed = (96, 48, 7) if kind == "alpha_mask" else (48, 24, 5)         # the larger scene has pixels the mask discards
+            env, mats, chains, planes, pf, pv = _pixel_scene(w, h, seed, casters=(kind == "shadowed"))
             kw = {}
             if kind == "shadowed":
                 kw = _shadow_setup(pf, 110)
