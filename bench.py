@@ -397,9 +397,9 @@ def cpu_reference_forward(planes, rows_target_s=12.0, env=None, threads=None):
         r = subprocess.run([sys.executable, os.path.abspath(__file__), "--impl", "cpu-port", "--steps", "4", "--warmup", "1"],
                            capture_output=True, text=True, timeout=420, env=env_)
         j = json.loads([l for l in r.stdout.splitlines() if l.startswith("{")][-1])
-        px = j["rows"] * W4K
+        px = j["rows"] * j["reps"] * W4K
         return {"value": round(j["value"], 4), "unit": UNIT, "cores": j["procs"], "kind": "port",
-                "sample": f"4 x ({j['rows']} of {H4K} rows x {W4K} px of the same 4K G-buffer) = {4 * px} px at {j['ms']:.1f} ms per pass, scalar C++ "
+                "sample": f"4 x {j['reps']} x ({j['rows']} of {H4K} rows x {W4K} px of the same 4K G-buffer) = {4 * px} px at {j['ms']:.1f} ms per pass, scalar C++ "
                           f"oracle, one forked process per host core ({j['one_process_mpx_s']} Mpixels/s per process)"}
     except Exception as ex:
         print(f"# multi-process cpu_baseline unavailable ({ex!r}); using threads", file=sys.stderr)
@@ -467,46 +467,55 @@ def cpu_env():
 _REF_JOB = {}
 
 
-def _cpu_rows_worker(rng):
-    """forked worker: rows [rb,re) of the band through the reference's shader text compiled as C++ ('text') or the scalar port ('port')"""
+def _cpu_rows_worker(job):
+    """forked worker: rows [rb,re) of the band, `reps` times over, through the reference's shader text compiled as C++ ('text') or the
+    scalar port ('port')"""
     import oracle_lib as orc
     j = _REF_JOB
-    rb, re = rng
-    if j["kind"] == "text":
-        orc.hlsl_forward_gbuffer(j["pf"], j["pv"], j["planes"], *j["env"], row_begin=rb, row_end=re, out=j["out"])
-        return float(j["out"][rb:re, :, :3].sum())
-    return float(orc.forward_lighting(j["pf"], j["pv"], j["planes"], *j["env"], rb, re, 1)[rb:re, :, :3].sum())
+    rb, re, reps = job
+    acc = 0.0
+    for _ in range(reps):
+        if j["kind"] == "text":
+            orc.hlsl_forward_gbuffer(j["pf"], j["pv"], j["planes"], *j["env"], row_begin=rb, row_end=re, out=j["out"])
+            acc += float(j["out"][rb:re, :, :3].sum())
+        else:
+            acc += float(orc.forward_lighting(j["pf"], j["pv"], j["planes"], *j["env"], rb, re, 1)[rb:re, :, :3].sum())
+    return acc
 
 
 def _cpu_arm(kind, steps, warmup, planes, pf, pv, a, budget_s=60.0):
     """`kind` over a bounded band of the 4K G-buffer, one FORKED PROCESS per host core (the compiled shader's cbuffers are process
-    globals; and processes were measured to scale where threads of one process did not on the pool's boxes).
-    Returns dict(value Mpx/s, ms, rows, procs, one_process_mpx_s)."""
+    globals; and processes were measured to scale where threads of one process did not). A step = the whole band `reps` times,
+    every process shading its own rows, `reps` sized from a probe so that a step lasts about budget_s / (steps + warmup) seconds
+    (long enough for the task hand-off not to matter). Returns dict(value Mpx/s, ms, rows, reps, procs, one_process_mpx_s)."""
     import multiprocessing as mp
     import numpy as np
     import oracle_lib as orc
     procs = orc.cpu_threads()
     band = planes[0].shape[0]
+    budget_s = float(os.environ.get("VQ_CPU_ARM_BUDGET_S", budget_s))     # tests shorten it
     _REF_JOB.update(kind=kind, pf=pf, pv=pv, planes=planes, env=a, out=np.zeros((band, W4K, 4), np.float32))
     t0 = time.perf_counter()
-    _cpu_rows_worker((0, 4))
+    _cpu_rows_worker((0, 4, 1))
     one = 4 * W4K / (time.perf_counter() - t0)                           # px/s of one process
+    n = min(procs, band)
+    cuts = [(band * i // n, band * (i + 1) // n) for i in range(n)]
     with mp.get_context("fork").Pool(procs) as pool:
-        def step(rows):
-            n = min(procs, rows)
-            return sum(pool.map(_cpu_rows_worker, [(rows * i // n, rows * (i + 1) // n) for i in range(n)], chunksize=1))
-        t0 = time.perf_counter(); step(min(band, procs)); dt = time.perf_counter() - t0
-        rate = min(band, procs) * W4K / dt                                # measured parallel rate (a box may grant fewer CPUs than it lists)
-        rows = int(min(band, max(procs, budget_s * rate / W4K / (steps + warmup))))
+        def step(reps):
+            return sum(pool.map(_cpu_rows_worker, [(rb, re, reps) for rb, re in cuts], chunksize=1))
+        t0 = time.perf_counter(); step(1); dt = time.perf_counter() - t0
+        rate = band * W4K / dt                                            # measured parallel rate (a box may grant fewer CPUs than it lists)
+        reps = int(max(1, round(budget_s / (steps + warmup) * rate / (band * W4K))))
         for _ in range(warmup):
-            step(rows)
+            step(reps)
         t0 = time.perf_counter()
         work = 0.0
         for _ in range(steps):
-            work += step(rows)
+            work += step(reps)
         dt = (time.perf_counter() - t0) / steps
     assert work != 0.0
-    return {"value": rows * W4K / dt / 1e6, "ms": dt * 1e3, "rows": rows, "procs": procs, "one_process_mpx_s": round(one / 1e6, 3)}
+    return {"value": band * reps * W4K / dt / 1e6, "ms": dt * 1e3, "rows": band, "reps": reps, "procs": procs,
+            "one_process_mpx_s": round(one / 1e6, 3)}
 
 
 def _cpu_workload():
@@ -552,7 +561,7 @@ def run_reference(args):
                  f"{port['one_process_mpx_s']} per process)") if port else "scalar port not timed"
     if text is not None:
         v, ms, kind, cores = text["value"], text["ms"], "reference", text["procs"]
-        sample = (f"each step = {text['rows']} rows x {W4K} px of the 4K G-buffer through the reference's own ForwardLighting.hlsl PSMain "
+        sample = (f"each step = {text['reps']} x ({text['rows']} rows x {W4K} px of the 4K G-buffer) through the reference's own ForwardLighting.hlsl PSMain "
                   f"(+ Lighting/BRDF/ShadingMath.hlsl) compiled as C++ (oracle/_ref/libhlslref.so), {cores} forked processes "
                   f"({text['one_process_mpx_s']} Mpixels/s per process); texture fetches served by the oracle's samplers; max scaled "
                   f"|delta| vs the port {text['max_scaled_delta_vs_port']:.1e}; {port_note}")
@@ -571,7 +580,7 @@ def run_reference(args):
             dt = (time.perf_counter() - t0) / args.steps
             port = {"value": rows * W4K / dt / 1e6, "ms": dt * 1e3, "rows": rows, "procs": threads}
         v, ms, kind, cores = port["value"], port["ms"], "port", port["procs"]
-        sample = f"each step = {port['rows']} rows x {W4K} px of the 4K G-buffer through the scalar C++ oracle on {cores} host cores"
+        sample = f"each step = {port.get('reps', 1)} x ({port['rows']} rows x {W4K} px of the 4K G-buffer) through the scalar C++ oracle on {cores} host cores"
         note = "the reference's D3D12/HLSL path needs Windows; this arm is the CPU port (oracle) of the identical math"
     print(json.dumps({"impl": "reference", "metric": METRIC, "value": round(v, 4), "unit": UNIT, "n_gpus": args.gpus,
                       "steps": args.steps, "warmup": args.warmup, "ms_per_step": round(ms, 3),

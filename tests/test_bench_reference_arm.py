@@ -10,7 +10,7 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 
 def test_reference_arm_line():
     r = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--impl", "reference", "--steps", "2", "--warmup", "1"],
-                       capture_output=True, text=True, timeout=900, cwd=ROOT)
+                       capture_output=True, text=True, timeout=900, cwd=ROOT, env=dict(os.environ, VQ_CPU_ARM_BUDGET_S="3"))
     assert r.returncode == 0, r.stderr[-2000:]
     lines = [l for l in r.stdout.splitlines() if l.startswith("{")]
     assert len(lines) == 1
