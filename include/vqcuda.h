@@ -393,7 +393,8 @@ VQ_API int vq_apply_reflections(VqContext* ctx, VqImage scene_color, VqImage ref
  *   vq_depth_min_pyramid: replaces CSMain (DownsampleDepth.hlsl:85-119 = FidelityFX SPD with a MIN reduction): level 0 is
  *     a copy of the R32F depth image, level l = max(1, w>>l) x max(1, h>>l) holds the 2x2 minimum of the zero-padded
  *     level above; `levels` receives n_levels (<= vq_depth_pyramid_level_count = 1 + floor(log2(max(w,h))), at most 13)
- *     tightly packed levels, vq_depth_pyramid_texel_count() floats in total.
+ *     tightly packed levels, vq_depth_pyramid_texel_count() floats in total. The padded-domain levels ping-pong through scratch
+ *     owned by the context (like vq_image_resize): calls on ONE context must be issued on one stream at a time.
  *   STATUS: compiled for sm_100a and checked against the oracle's semantics on paper only — not yet run on a GPU.
  * ------------------------------------------------------------------------------------------ */
 typedef struct VqShadowMaps {
