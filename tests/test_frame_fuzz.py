@@ -137,3 +137,59 @@ def test_oracle_agrees_with_reference_stb_on_mutated_files(orc):
         assert (rc == 0) == (rc2 == 0), trial
         if rc == 0:
             assert a.shape == b.shape and np.array_equal(a.view(np.uint32), b.view(np.uint32)), trial
+
+
+def _pack_reference(rgbe):
+    """plain restatement of stbiw__write_hdr_scanline's run lists (stb_image_write.h): per channel, literals up to the first position
+    where three equal bytes start (<= 128 per record), then the run (<= 127 per record)"""
+    h, w = rgbe.shape[:2]
+    out = bytearray(b"#?RADIANCE\n# Written by stb_image_write.h\nFORMAT=32-bit_rle_rgbe\nEXPOSURE=          1.0000000000000\n\n-Y %d +X %d\n" % (h, w))
+    for y in range(h):
+        row = rgbe[y]
+        if w < 8 or w >= 32768:
+            out += row.tobytes(); continue
+        out += bytes([2, 2, w >> 8, w & 0xff])
+        for c in range(4):
+            pl = row[:, c].tolist()
+            x = 0
+            while x < w:
+                r = x
+                while r + 2 < w and not (pl[r] == pl[r + 1] == pl[r + 2]):
+                    r += 1
+                found = r + 2 < w
+                if not found:
+                    r = w
+                while x < r:
+                    n = min(128, r - x); out.append(n); out += bytes(pl[x:x + n]); x += n
+                if found:
+                    while r < w and pl[r] == pl[x]:
+                        r += 1
+                    while x < r:
+                        n = min(127, r - x); out += bytes([128 + n, pl[x]]); x += n
+    return bytes(out)
+
+
+def test_packer_equals_the_run_list_rule_byte_for_byte(vq):
+    """the host packer's word-at-a-time triple search and raw-pointer output against the rule written out plainly: widths around the
+    8-byte probe and the 127/128 record limits, triples at every offset modulo 8, runs touching the row end, two-valued noise"""
+    rng = np.random.default_rng(77)
+    n = 0
+    for w in (8, 9, 10, 15, 16, 17, 23, 24, 25, 126, 127, 128, 129, 130, 131, 255, 256, 257, 385, 1000):
+        for mode in range(8):
+            h = 2
+            if mode == 0: a = rng.integers(0, 256, (h, w, 4), dtype=np.uint8)
+            elif mode == 1: a = rng.integers(0, 2, (h, w, 4), dtype=np.uint8)                       # many short runs
+            elif mode == 2: a = rng.integers(0, 3, (h, w, 4), dtype=np.uint8)
+            elif mode == 3: a = np.repeat(rng.integers(0, 256, (h, (w + 2) // 3, 4), dtype=np.uint8), 3, axis=1)[:, :w]   # exact triples
+            elif mode == 4: a = np.full((h, w, 4), 9, np.uint8)                                     # one run per channel
+            elif mode == 5:                                                                       # a triple at each offset, noise elsewhere
+                a = (np.arange(w, dtype=np.uint8)[None, :, None] * np.array([1, 3, 5, 7], np.uint8)).repeat(h, 0).copy()
+                for k in range(0, w - 2, 11): a[:, k:k + 3] = a[:, k:k + 1]
+            elif mode == 6:                                                                       # runs that end exactly at the row end / start
+                a = rng.integers(0, 256, (h, w, 4), dtype=np.uint8); a[:, -3:] = 200; a[:, :3] = 100
+            else:                                                                                 # pairs only: never a triple
+                a = np.repeat(np.arange((w + 1) // 2, dtype=np.uint8), 2)[:w][None, :, None].repeat(h, 0).repeat(4, 2).copy()
+            a = np.ascontiguousarray(a)
+            assert vq.hdr_pack_file(a) == _pack_reference(a), (w, mode)
+            n += 1
+    assert n == 160
