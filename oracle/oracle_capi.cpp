@@ -280,6 +280,22 @@ void orc_point_light(const VqPointLight* l, const float P[3], const float N[3], 
     const float3 r = CalculatePointLightIllumination(*l, s, make3(P[0], P[1], P[2]), make3(V[0], V[1], V[2]));
     out[0] = r.x; out[1] = r.y; out[2] = r.z;
 }
+void orc_spot_light(const VqSpotLight* l, const float P[3], const float N[3], const float V[3],
+                    const float albedo[3], float roughness, float metalness, float out[3]) {
+    BRDF_Surface s{};
+    s.N = make3(N[0], N[1], N[2]); s.roughness = roughness; s.metalness = metalness;
+    s.diffuseColor = make3(albedo[0], albedo[1], albedo[2]);
+    const float3 r = CalculateSpotLightIllumination(*l, s, make3(P[0], P[1], P[2]), make3(V[0], V[1], V[2]));
+    out[0] = r.x; out[1] = r.y; out[2] = r.z;
+}
+void orc_directional_light(const VqDirectionalLight* l, const float N[3], const float V[3],
+                           const float albedo[3], float roughness, float metalness, float out[3]) {
+    BRDF_Surface s{};
+    s.N = make3(N[0], N[1], N[2]); s.roughness = roughness; s.metalness = metalness;
+    s.diffuseColor = make3(albedo[0], albedo[1], albedo[2]);
+    const float3 r = CalculateDirectionalLightIllumination(*l, s, make3(V[0], V[1], V[2]));
+    out[0] = r.x; out[1] = r.y; out[2] = r.z;
+}
 float orc_spotlight_intensity(const VqSpotLight* l, const float P[3]) { return SpotlightIntensity(*l, make3(P[0], P[1], P[2])); }
 void orc_hammersley(uint32_t i, uint32_t n, float out[2]) { const float2 h = Hammersley(i, n); out[0] = h.x; out[1] = h.y; }
 void orc_importance_sample_ggx(const float Xi[2], const float N[3], float roughness, float out[3]) {

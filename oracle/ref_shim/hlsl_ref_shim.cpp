@@ -363,6 +363,13 @@ void hlslref_spot_light(const VqSpotLight* l, const float P[3], const float N[3]
     hl::fwd::SpotLight sl; cp(sl, *l);
     o3(out, hl::fwd::CalculateSpotLightIllumination(sl, surf(N, albedo, roughness, metalness), v3(P), v3(V)));
 }
+void hlslref_directional_light(const VqDirectionalLight* l, const float N[3], const float V[3], const float albedo[3],
+                               float roughness, float metalness, float out[3]) {
+    hl::fwd::DirectionalLight dl;
+    dl.lightDirection = f3(l->lightDirection); dl.brightness = l->brightness; dl.color = f3(l->color); dl.depthBias = l->depthBias;
+    dl.shadowing = l->shadowing; dl.enabled = l->enabled;
+    o3(out, hl::fwd::CalculateDirectionalLightIllumination(dl, surf(N, albedo, roughness, metalness), v3(V)));
+}
 float hlslref_spotlight_intensity(const VqSpotLight* l, const float P[3]) { hl::fwd::SpotLight sl; cp(sl, *l); return hl::fwd::SpotlightIntensity(sl, v3(P)); }
 void hlslref_hammersley(uint32_t i, uint32_t n, float out[2]) { const hl::float2 h = hl::fwd::Hammersley(i, n); out[0] = h.x; out[1] = h.y; }
 void hlslref_importance_sample_ggx(const float Xi[2], const float N[3], float roughness, float out[3]) {

@@ -106,10 +106,17 @@ def test_light_functions_bit_exact(vq):
         sl.innerConeAngle = float(rng.uniform(0.1, 0.6)); sl.outerConeAngle = sl.innerConeAngle + float(rng.uniform(0.05, 0.8))
         sl.brightness = float(rng.uniform(0, 500)); sl.range = float(rng.uniform(1, 30))
         assert _same(o.orc_spotlight_intensity(C.byref(sl), _v(*P)), r.hlslref_spotlight_intensity(C.byref(sl), _v(*P)))
+        o.orc_spot_light(C.byref(sl), _v(*P), _v(*N), _v(*V), _v(*alb), f32(rough), f32(metal), orc._p(a))
         r.hlslref_spot_light(C.byref(sl), _v(*P), _v(*N), _v(*V), _v(*alb), f32(rough), f32(metal), orc._p(b))
-        # the oracle exposes the spot light through the whole pass only; its intensity + the shared BRDF are covered above and
-        # the full PSMain comparison below covers CalculateSpotLightIllumination itself
-        assert np.all(np.isfinite(b))
+        assert _same(a, b), (i, a, b)
+        dl = vq.DirectionalLight()
+        d = _unit(rng) * np.float32(rng.uniform(0.5, 2))
+        dl.lightDirection.x, dl.lightDirection.y, dl.lightDirection.z = [float(x) for x in d]
+        dl.color.x, dl.color.y, dl.color.z = [float(x) for x in rng.uniform(0, 1, 3)]
+        dl.brightness = float(rng.uniform(0, 20)); dl.enabled = 1
+        o.orc_directional_light(C.byref(dl), _v(*N), _v(*V), _v(*alb), f32(rough), f32(metal), orc._p(a))
+        r.hlslref_directional_light(C.byref(dl), _v(*N), _v(*V), _v(*alb), f32(rough), f32(metal), orc._p(b))
+        assert _same(a, b), (i, a, b)
 
 
 def test_sampling_math_bit_exact():
