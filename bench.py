@@ -479,7 +479,7 @@ def _cpu_rows_worker(job):
             orc.hlsl_forward_gbuffer(j["pf"], j["pv"], j["planes"], *j["env"], row_begin=rb, row_end=re, out=j["out"])
             acc += float(j["out"][rb:re, :, :3].sum())
         else:
-            acc += float(orc.forward_lighting(j["pf"], j["pv"], j["planes"], *j["env"], rb, re, 1)[rb:re, :, :3].sum())
+            acc += float(orc.forward_lighting(j["pf"], j["pv"], j["planes"], *j["env"], rb, re, 1, out=j["out"])[rb:re, :, :3].sum())
     return acc
 
 

@@ -67,11 +67,11 @@ def cpu_threads() -> int:
 
 # ---- whole passes ------------------------------------------------------------------------------
 def forward_lighting(pf, pv, planes, diff_cube, diff_res, spec_cube, spec_res, spec_mips, lut,
-                     row_begin=0, row_end=None, threads=None) -> np.ndarray:
+                     row_begin=0, row_end=None, threads=None, out=None) -> np.ndarray:
     pos, nrm, alb = (_f(p) for p in planes[:3])
     em = _f(planes[3]) if len(planes) > 3 else None
     h, w = pos.shape[:2]
-    out = np.zeros((h, w, 4), np.float32)
+    out = np.zeros((h, w, 4), np.float32) if out is None else out
     lutc = _f(lut)
     lib().orc_forward_lighting(C.byref(pf), C.byref(pv), _p(pos), _p(nrm), _p(alb),
                                _p(em) if em is not None else None, w, h,
