@@ -503,6 +503,7 @@ def _cpu_arm(kind, steps, warmup, planes, pf, pv, a, budget_s=60.0):
     with mp.get_context("fork").Pool(procs) as pool:
         def step(reps):
             return sum(pool.map(_cpu_rows_worker, [(rb, re, reps) for rb, re in cuts], chunksize=1))
+        step(1)                                                           # first touch of every process's pages
         t0 = time.perf_counter(); step(1); dt = time.perf_counter() - t0
         rate = band * W4K / dt                                            # measured parallel rate (a box may grant fewer CPUs than it lists)
         reps = int(max(1, round(budget_s / (steps + warmup) * rate / (band * W4K))))
