@@ -19,4 +19,26 @@ struct XMFLOAT3X3 { float m[3][3]; };
 struct XMFLOAT4X3 { float m[4][3]; };
 struct XMFLOAT3X4 { float m[3][4]; };
 struct XMFLOAT4X4 { float m[4][4]; };
+
+// --- the few functions Source/Renderer/Resources/CubemapUtility.cpp calls, with DirectXMath's DOCUMENTED semantics (public API
+// of Microsoft's MIT-licensed library, which is not part of the reference tree): row-vector convention, v' = v * M.
+constexpr float XM_PI = 3.141592654f;
+constexpr float XM_PIDIV2 = 1.570796327f;
+struct XMVECTOR { float f[4]; };
+inline XMVECTOR XMLoadFloat3(const XMFLOAT3* p) { return XMVECTOR{{p->x, p->y, p->z, 0.0f}}; }
+inline XMVECTOR operator+(XMVECTOR a, XMVECTOR b) { return XMVECTOR{{a.f[0] + b.f[0], a.f[1] + b.f[1], a.f[2] + b.f[2], a.f[3] + b.f[3]}}; }
+inline XMMATRIX XMMatrixIdentity() { XMMATRIX m{}; for (int i = 0; i < 4; ++i) m.r[i][i] = 1.0f; return m; }
+// XMMatrixLookAtLH(eye, at, up): zaxis = normalize(at - eye); xaxis = normalize(cross(up, zaxis)); yaxis = cross(zaxis, xaxis);
+// columns of the rotation part are the axes, last row = (-dot(xaxis,eye), -dot(yaxis,eye), -dot(zaxis,eye), 1)
+inline XMMATRIX XMMatrixLookAtLH(XMVECTOR eye, XMVECTOR at, XMVECTOR up) {
+    auto sub = [](XMVECTOR a, XMVECTOR b) { return XMVECTOR{{a.f[0] - b.f[0], a.f[1] - b.f[1], a.f[2] - b.f[2], 0.0f}}; };
+    auto dot = [](XMVECTOR a, XMVECTOR b) { return a.f[0] * b.f[0] + a.f[1] * b.f[1] + a.f[2] * b.f[2]; };
+    auto cross = [](XMVECTOR a, XMVECTOR b) { return XMVECTOR{{a.f[1] * b.f[2] - a.f[2] * b.f[1], a.f[2] * b.f[0] - a.f[0] * b.f[2], a.f[0] * b.f[1] - a.f[1] * b.f[0], 0.0f}}; };
+    auto norm = [&](XMVECTOR a) { const float l = __builtin_sqrtf(dot(a, a)); return XMVECTOR{{a.f[0] / l, a.f[1] / l, a.f[2] / l, 0.0f}}; };
+    const XMVECTOR z = norm(sub(at, eye)), x = norm(cross(up, z)), y = cross(z, x);
+    XMMATRIX m{};
+    for (int i = 0; i < 3; ++i) { m.r[i][0] = x.f[i]; m.r[i][1] = y.f[i]; m.r[i][2] = z.f[i]; }
+    m.r[3][0] = -dot(x, eye); m.r[3][1] = -dot(y, eye); m.r[3][2] = -dot(z, eye); m.r[3][3] = 1.0f;
+    return m;
+}
 }
