@@ -11,8 +11,16 @@
  *     VqStatus; vq_last_error() gives a thread-local message;
  *   - calls only ENQUEUE work on `stream` (== recording into a command list); they are
  *     thread-safe when callers use distinct streams (== per-thread command lists,
- *     SceneRendering.cpp:197-207). Synchronisation is the caller's (cudaStreamSynchronize
- *     == fence wait), except the *_host convenience calls which block.
+ *     SceneRendering.cpp:197-207): host-side context state is guarded by a lock and every
+ *     SPD launch gets its own ticket word. EXCEPTIONS — calls whose DEVICE scratch is one
+ *     buffer per context and which therefore must not be in flight concurrently on two
+ *     streams of the same context (use one context per thread for these, or order them):
+ *       vq_forward_lighting* with an environment that is NOT registered by
+ *       vq_environment_prepare (the sampling copies are rebuilt into per-context scratch),
+ *       vq_environment_prepare itself, vq_image_resize, vq_depth_min_pyramid,
+ *       vq_forward_lighting_host.
+ *     Synchronisation is the caller's (cudaStreamSynchronize == fence wait), except the
+ *     *_host convenience calls which block.
  *   - there is NO CPU fallback: without a CUDA device every device call fails with
  *     VQ_ERR_NO_DEVICE.
  *
@@ -110,7 +118,9 @@ VQ_API uint64_t vq_launch_count(void);
  * K1  Forward PBR lighting.  Replaces VQRenderer::RenderSceneColor (SceneRendering.cpp:1619-1851)
  *     + PSMain (ForwardLighting.hlsl:222-391) over a G-buffer instead of rasterised draws.
  *     Shades rows [row_begin,row_end) of the image (row tiling for multi-GPU); out = {I.rgb, roughness}.
- *     Shadow maps do not exist headless: caster lists are lit with shadow factor 1 (no occlusion).
+ *     This entry point binds no shadow maps: caster lists and a shadowing directional light are lit with shadow
+ *     factor 1 (no occlusion) - which differs from PSMain whenever the engine has shadow maps bound; use
+ *     vq_forward_lighting_shadowed (below) for the PCF-shadowed result.
  * ------------------------------------------------------------------------------------------ */
 VQ_API int vq_forward_lighting(VqContext* ctx,
                                const VqPerFrameData* per_frame,

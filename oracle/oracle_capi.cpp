@@ -174,6 +174,23 @@ void orc_specular_prefilter(const float* pyramid, int w, int h, int levels,
     });
 }
 
+// K3 on an arbitrary texel list (flattened mip-major / face-minor / row-major indices of the packed cube): the same
+// per-texel call as orc_specular_prefilter (CubemapConvolution.hlsl:168-223, EnvironmentMapRendering.cpp:413-465), used
+// by the full-size parity test that samples 1 % of BASELINE config 5's texels at random. out = n x float4.
+void orc_specular_prefilter_texels(const float* pyramid, int w, int h, int levels, int res, int mips, int num_samples,
+                                   const int64_t* texels, int n, float* out, int threads) {
+    const Pyramid p{pyramid, w, h, levels};
+    par_rows(n, threads, [&](int k) {
+        int64_t t = texels[k]; int mip = 0;
+        for (; mip < mips; ++mip) { const int64_t sz = 6ll * (res >> mip) * (res >> mip); if (t < sz) break; t -= sz; }
+        if (mip >= mips) { st(out + 4 * (size_t)k, float4{0, 0, 0, 0}); return; }
+        const int nn = res >> mip, face = (int)(t / ((int64_t)nn * nn)), py = (int)((t % ((int64_t)nn * nn)) / nn), px = (int)(t % nn);
+        const float roughness = (float)mip / (float)(mips - 1);
+        st(out + 4 * (size_t)k, SpecularIrradiance_PSMain(p, CubeTexelDirection(face, px, py, nn), roughness,
+                                                          make2((float)w, (float)h), (uint32_t)num_samples));
+    });
+}
+
 // ---- K4 ---------------------------------------------------------------------------------------
 void orc_brdf_integration_lut(float* out_rg, int w, int h, int samples, int row_begin, int row_end, int threads) {
     par_rows(row_end - row_begin, threads, [&](int r) {

@@ -11,8 +11,6 @@ for p in (ROOT, os.path.join(ROOT, "tests")):
 
 def pytest_configure(config):
     config.addinivalue_line("markers", "gpu: needs a CUDA device (run on the B200 box with -m gpu)")
-    config.addinivalue_line("markers", "gpu_next: needs a CUDA device; parity tests of kernels that were written after the round's "
-                            "GPU budget was spent and have never run on a GPU yet (run with -m gpu_next; promoted to gpu once green)")
     # keep the in-tree libraries in step with the sources (no-op when they are up to date)
     import __graft_entry__
     __graft_entry__.build()

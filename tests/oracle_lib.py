@@ -107,6 +107,15 @@ def specular_prefilter(pyr, w, h, levels, res, mips, num_samples=512, row_begin=
     return out
 
 
+def specular_prefilter_texels(pyr, w, h, levels, res, mips, texels, num_samples=512, threads=None) -> np.ndarray:
+    """K3 on a list of flattened texel indices of the packed cube -> (n, 4)"""
+    t = np.ascontiguousarray(texels, dtype=np.int64)
+    out = np.zeros((t.size, 4), np.float32)
+    lib().orc_specular_prefilter_texels(_p(_f(pyr)), w, h, levels, res, mips, num_samples,
+                                        t.ctypes.data_as(C.POINTER(C.c_int64)), int(t.size), _p(out), threads or cpu_threads())
+    return out
+
+
 def brdf_integration_lut(w, h, samples=2048, row_begin=0, row_end=None, threads=None) -> np.ndarray:
     out = np.zeros((h, w, 2), np.float32)
     lib().orc_brdf_integration_lut(_p(out), w, h, samples, row_begin, h if row_end is None else row_end,

@@ -145,6 +145,33 @@ def test_forward_host_entry(ctx, vq, orc):
     assert np.array_equal(hout.numpy(), host(out))
 
 
+def test_forward_host_entry_rejects_mismatched_planes(ctx, vq):
+    """every host plane is copied with the OUTPUT's width/height: a smaller G-buffer plane or a bad emissive descriptor must
+    be refused before any copy is enqueued (it would read past the end of the caller's host memory)"""
+    from vqengine_b200 import synth
+    env = small_env()
+    w, h = 64, 48
+    planes = synth.gbuffer(w, h, seed=8, emissive=True)
+    pf, pv = synth.scene_constants(w, h, env["spec_mips"], seed=8)
+    hp = [torch.from_numpy(p) for p in planes]
+    small = torch.zeros((h // 2, w, 4), dtype=torch.float32)
+    narrow = torch.zeros((h, w // 2, 4), dtype=torch.float32)
+    dd, ds, dl = dev(env["diff"]), dev(env["spec"]), dev(env["lut"])
+    em = vq.EnvironmentMaps(vq.cubemap_of(dd, env["diff_res"], 1), vq.cubemap_of(ds, env["spec_res"], env["spec_mips"]), vq.image_of(dl, 2))
+    hout = torch.zeros((h, w, 4), dtype=torch.float32)
+    for bad in (vq.GBuffer(vq.image_of(hp[0]), vq.image_of(small), vq.image_of(hp[2]), vq.null_image()),
+                vq.GBuffer(vq.image_of(narrow), vq.image_of(hp[1]), vq.image_of(hp[2]), vq.null_image()),
+                vq.GBuffer(vq.image_of(hp[0]), vq.image_of(hp[1]), vq.image_of(hp[2]), vq.image_of(small))):
+        with pytest.raises(vq.VqError) as e:
+            ctx.forward_lighting_host(pf, pv, bad, em, hout)
+        assert e.value.code == vq.VQ_ERR_INVALID_ARG
+    badpitch = vq.image_of(hp[3]); badpitch.pitch_bytes = w * 16 - 16
+    with pytest.raises(vq.VqError):
+        ctx.forward_lighting_host(pf, pv, vq.GBuffer(vq.image_of(hp[0]), vq.image_of(hp[1]), vq.image_of(hp[2]), badpitch), em, hout)
+    ctx.forward_lighting_host(pf, pv, vq.GBuffer(*(vq.image_of(t) for t in hp)), em, hout)     # the good call still works
+    assert np.isfinite(hout.numpy()).all() and hout.numpy().any()
+
+
 def test_forward_pitched_planes_and_output(ctx, vq, orc):
     from vqengine_b200 import synth
     env = small_env()

@@ -106,6 +106,30 @@ def test_spd(ctx, vq, orc, w, h):
         assert np.array_equal(host(g), r), f"spd level {l} of {w}x{h}: not bit-exact, max diff {np.abs(host(g) - r).max()}"
 
 
+def test_spd_two_streams_in_flight(ctx, vq, orc):
+    """vqcuda.h: calls are thread-safe on distinct streams. Two SPD pyramids with a last-workgroup tail (mips > 6) are kept in
+    flight on two streams of ONE context, many times over: every launch owns its ticket word, so each result stays bit-exact."""
+    from vqengine_b200 import synth
+    sizes = [(1024, 512), (960, 540)]
+    imgs = [synth.hdr_image(w, h, seed=50 + i) for i, (w, h) in enumerate(sizes)]
+    streams = [torch.cuda.Stream(), torch.cuda.Stream()]
+    torch.cuda.synchronize()
+    work = []
+    for (w, h), img in zip(sizes, imgs):
+        (dx, dy), c = vq.spd_setup(w, h)
+        c.mips = min(c.mips, int(np.floor(np.log2(min(w, h)))))
+        assert c.mips > 6
+        work.append((c, dev(img), [torch.zeros((h >> l, w >> l, 4), dtype=torch.float32, device="cuda") for l in range(1, c.mips + 1)]))
+    torch.cuda.synchronize()
+    for rep in range(40):
+        for s, (c, d, dsts) in zip(streams, work):
+            ctx.spd_downsample(c, d, dsts, stream=s)
+    torch.cuda.synchronize()
+    for img, (c, d, dsts) in zip(imgs, work):
+        for l, (g, r) in enumerate(zip(dsts, orc.spd_downsample(img, c.mips)), start=1):
+            assert np.array_equal(host(g), r), f"level {l}"
+
+
 def test_post_chain_config4_small(ctx, vq, orc):
     """BASELINE config 4 order at a small size: SPD -> BlurX,Y -> Tonemap -> CAS -> EASU 2x -> RCAS.
     Every stage is checked against the oracle applied to the SAME input (the kernel's previous-stage output):

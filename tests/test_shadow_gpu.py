@@ -1,9 +1,7 @@
-"""-m gpu_next (NOT part of -m gpu): SURVEY §8(f).4 — vq_forward_lighting_shadowed and vq_depth_min_pyramid against the oracle.
+"""-m gpu: SURVEY §8(f).4 — vq_forward_lighting_shadowed and vq_depth_min_pyramid against the oracle.
 
-These kernels (vqengine_b200/csrc/vq_shadow.cu) were written after the round's GPU budget was spent: they compile for sm_100a
-and follow the oracle operation by operation, but have never run on a GPU. The tests are complete and are the first thing to run
-next round (`python -m pytest tests -m gpu_next`); once green they become `-m gpu`. The oracle side of every comparison is
-already pinned against the reference's shader text (tests/test_hlsl_ref.py: shadowed PSMain, DownsampleDepth.hlsl)."""
+First run on a B200 at the start of round 2 (all green, memcheck clean: profiles/r02_shadow_first_run.txt). The oracle side
+of every comparison is pinned against the reference's shader text (tests/test_hlsl_ref.py: shadowed PSMain, DownsampleDepth.hlsl)."""
 import numpy as np
 import pytest
 import torch
@@ -11,7 +9,7 @@ import torch
 from gpu_util import dev, host, report, TOL
 from envmaps import small_env
 
-pytestmark = pytest.mark.gpu_next
+pytestmark = pytest.mark.gpu
 
 
 def _scene(w, h, seed):

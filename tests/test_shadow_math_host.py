@@ -4,7 +4,7 @@ vqengine_b200/csrc/vq_shadow_math.cuh holds everything the CUDA kernels of vq_sh
 light functions with individually rounded operations, the three PCF tests, cube / 2-D point taps, the caster loop of PSMain,
 the MIN-pyramid texel) plus the launcher's set-up code (light block, per-frame copy without casters, level plan). The same
 header builds with g++ when VQ_HOST_CHECK is defined (tests/host_check/shadow_math_host.cpp), so the restatement is checked
-here bit for bit without a GPU; what remains for the GPU run (tests/test_zz_shadow_gpu_next.py) is the launch code."""
+here bit for bit without a GPU; what remains for the GPU run (tests/test_shadow_gpu.py) is the launch code."""
 import ctypes as C
 import os
 import subprocess

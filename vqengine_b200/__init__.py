@@ -502,13 +502,17 @@ class Context:
         import torch
         info, offs = hdr_parse(file_bytes)
         n = len(file_bytes)
-        dfile = torch.zeros(((n + 15) // 16 * 16 + 16,), dtype=torch.uint8, device=f"cuda:{self.device}")
-        dfile[:n] = torch.frombuffer(bytearray(file_bytes), dtype=torch.uint8).to(dfile.device)
-        doffs = torch.from_numpy(offs.view(np.int64)).to(dfile.device) if offs is not None else None
-        out = torch.empty((info.height, info.width, 4), dtype=torch.float32, device=dfile.device)
-        lum = torch.zeros((1,), dtype=torch.float32, device=dfile.device)
-        _check(lib.vq_hdr_decode(self._h, dfile.data_ptr(), n, C.byref(info), doffs.data_ptr() if doffs is not None else None,
-                                 image_of(out), lum.data_ptr(), _stream_ptr(stream)))
+        # uploads, the zero fill and the launch all go onto ONE stream (`stream`, default: torch's current one), so the
+        # kernel is ordered after its inputs without an event
+        s = stream if stream is not None else torch.cuda.current_stream()
+        with torch.cuda.stream(s):
+            dfile = torch.zeros(((n + 15) // 16 * 16 + 16,), dtype=torch.uint8, device=f"cuda:{self.device}")
+            dfile[:n] = torch.frombuffer(bytearray(file_bytes), dtype=torch.uint8).to(dfile.device)
+            doffs = torch.from_numpy(offs.view(np.int64)).to(dfile.device) if offs is not None else None
+            out = torch.empty((info.height, info.width, 4), dtype=torch.float32, device=dfile.device)
+            lum = torch.zeros((1,), dtype=torch.float32, device=dfile.device)
+            _check(lib.vq_hdr_decode(self._h, dfile.data_ptr(), n, C.byref(info), doffs.data_ptr() if doffs is not None else None,
+                                     image_of(out), lum.data_ptr(), _stream_ptr(s)))
         out._vq_keepalive = (dfile, doffs)
         return out, lum
 

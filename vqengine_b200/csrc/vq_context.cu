@@ -57,8 +57,10 @@ int vq_ctx_create(int device, VqContext** out_ctx) {
     c->device = device;
     c->sm_count = prop.multiProcessorCount;
     c->l2_bytes = prop.l2CacheSize;
-    if (cudaMalloc(&c->spd_counter, 8 * sizeof(uint32_t)) != cudaSuccess) { delete c; vq_set_error("cudaMalloc failed"); return VQ_ERR_OUT_OF_MEMORY; }
-    cudaMemset(c->spd_counter, 0, 8 * sizeof(uint32_t));
+    if (cudaMalloc(&c->spd_counter, VQ_SPD_SLOTS * sizeof(uint32_t)) != cudaSuccess) { delete c; vq_set_error("cudaMalloc failed"); return VQ_ERR_OUT_OF_MEMORY; }
+    cudaMemset(c->spd_counter, 0, VQ_SPD_SLOTS * sizeof(uint32_t));
+    c->spd_next = new std::atomic<uint32_t>(0u);
+    c->mu = new std::recursive_mutex();
     *out_ctx = c;
     return VQ_OK;
 }
@@ -73,12 +75,19 @@ int vq_ctx_destroy(VqContext* ctx) {
     if (ctx->stage_dev) cudaFree(ctx->stage_dev);
     for (void* p : {ctx->env_diff, ctx->env_spec, ctx->tmp_diff, ctx->tmp_spec, ctx->env_lut, ctx->tmp_lut, ctx->resize_mid, ctx->resize_tab, ctx->depth_pad}) if (p) cudaFree(p);
     if (ctx->spd_counter) cudaFree(ctx->spd_counter);
+    delete ctx->spd_next; delete ctx->mu;
     delete ctx;
     return VQ_OK;
 }
 
+static int ctx_resize_locked(VqContext* ctx, int width, int height);
 int vq_ctx_resize(VqContext* ctx, int width, int height) {
     int rc = vq_enter(ctx); if (rc) return rc;
+    VqScratchLock lock(ctx);
+    return ctx_resize_locked(ctx, width, height);
+}
+int vq_ctx_resize_locked(VqContext* ctx, int width, int height) { return ctx_resize_locked(ctx, width, height); }
+static int ctx_resize_locked(VqContext* ctx, int width, int height) {
     VQ_REQUIRE(width > 0 && height > 0, "resolution must be positive");
     const size_t need = (size_t)width * height * 16 * 4;   // 3 G-buffer planes + output
     if (ctx->stage_dev_bytes < need) {

@@ -675,6 +675,7 @@ int vq_forward_launch_multi(VqContext* ctx, const VqPerFrameData* pf, const VqPe
                L.numPointCasters >= 0 && L.numPointCasters <= VQ_NUM_SHADOWING_LIGHTS_POINT &&
                L.numSpotCasters >= 0 && L.numSpotCasters <= VQ_NUM_SHADOWING_LIGHTS_SPOT, "light counts exceed the cbuffer arrays");
     if (row_begin == row_end) return VQ_OK;
+    VqScratchLock lock(ctx);           // env_* registration and the per-call tmp_* sampling copies are the context's
 
     FwdParams P;
     memset(&P, 0, sizeof(P));
@@ -770,6 +771,7 @@ extern "C" int vq_environment_prepare(VqContext* ctx, const VqEnvironmentMaps* e
     int rc = vq_enter(ctx); if (rc) return rc;
     VQ_REQUIRE(env, "env is null");
     VQ_REQUIRE(cube_desc_ok(env->irradiance_diffuse), "bad cubemap descriptor (irradiance_diffuse)");
+    VqScratchLock lock(ctx);
     ctx->env_valid = 0;
     rc = ensure_bytes(&ctx->env_diff, &ctx->env_diff_bytes, padded_texels(env->irradiance_diffuse.res, env->irradiance_diffuse.mips) * 32); if (rc) return rc;
     rc = pad_cube(env->irradiance_diffuse, (float4*)ctx->env_diff, (cudaStream_t)stream); if (rc) return rc;
@@ -789,6 +791,7 @@ extern "C" int vq_environment_prepare(VqContext* ctx, const VqEnvironmentMaps* e
 }
 extern "C" int vq_environment_invalidate(VqContext* ctx) {
     if (!ctx) { vq_set_error("null context"); return VQ_ERR_INVALID_ARG; }
+    VqScratchLock lock(ctx);
     ctx->env_valid = 0;
     return VQ_OK;
 }

@@ -16,11 +16,19 @@ extern "C" int vq_forward_lighting_host(VqContext* ctx, const VqPerFrameData* pf
                "bad host image descriptor");
     const int W = hout.width, H = hout.height;
     const bool hasEm = hgb->emissive.ptr != nullptr;
+    // every plane is read with cudaMemcpy2D over W x H texels of ITS pitch: a smaller plane or a bad pitch would read past
+    // the end of the caller's host memory, so all of this is checked before the first copy is enqueued
+    const VqImage* checked[3] = {&hgb->position_ao, &hgb->normal_roughness, &hgb->albedo_metalness};
+    for (const VqImage* im : checked)
+        VQ_REQUIRE(im->width == W && im->height == H, "every host G-buffer plane must have the output's width and height");
+    if (hasEm) VQ_REQUIRE(vq_image_ok(hgb->emissive) && hgb->emissive.width == W && hgb->emissive.height == H,
+                          "bad host emissive plane (descriptor, pitch or size)");
     const int planes = hasEm ? 5 : 4;
     const size_t rowBytes = (size_t)W * 16, planeBytes = rowBytes * H;
+    VqScratchLock lock(ctx);           // the staging buffer, the three streams and the event ring are the context's
     if (ctx->stage_dev_bytes < planeBytes * planes || !ctx->streams_ready) {
         // (re)size staging: vq_ctx_resize sizes for 4 planes; grow here if an emissive plane is present
-        rc = vq_ctx_resize(ctx, W, H); if (rc) return rc;
+        rc = vq_ctx_resize_locked(ctx, W, H); if (rc) return rc;
         if (ctx->stage_dev_bytes < planeBytes * planes) {
             cudaFree(ctx->stage_dev); ctx->stage_dev = nullptr; ctx->stage_dev_bytes = 0;
             if (cudaMalloc(&ctx->stage_dev, planeBytes * planes) != cudaSuccess) { cudaGetLastError(); vq_set_error("staging cudaMalloc failed"); return VQ_ERR_OUT_OF_MEMORY; }

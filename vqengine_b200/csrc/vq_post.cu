@@ -801,7 +801,7 @@ extern "C" int vq_spd_downsample(VqContext* ctx, const VqSpdConstants* c, VqImag
     const uint32_t gy = (uint32_t)(src.height + 63) / 64 - c->workGroupOffset[1];
     VQ_REQUIRE(gx >= 1 && gy >= 1 && gx * gy == c->numWorkGroups, "spd: numWorkGroups does not match the image / offset (use vq_spd_setup)");
     spd_kernel<SPD_AVG><<<dim3(gx, gy), 256, 0, (cudaStream_t)stream>>>(make_view(src), L, (int)c->mips, c->numWorkGroups,
-                                                               c->workGroupOffset[0], c->workGroupOffset[1], ctx->spd_counter);
+                                                               c->workGroupOffset[0], c->workGroupOffset[1], vq_spd_ticket(ctx));
     return vq_check_launch("spd_downsample");
 }
 
@@ -816,6 +816,6 @@ int vq_spd_min_pyramid(VqContext* ctx, VqPyramid hd, cudaStream_t stream) {
     }
     ImgV src; src.p = base; src.w = hd.width; src.h = hd.height; src.pitch4 = hd.width;
     const unsigned gx = (unsigned)(hd.width + 63) / 64, gy = (unsigned)(hd.height + 63) / 64;
-    spd_kernel<SPD_MIN_RGB_A1><<<dim3(gx, gy), 256, 0, stream>>>(src, L, mips, gx * gy, 0u, 0u, ctx->spd_counter + 1);
+    spd_kernel<SPD_MIN_RGB_A1><<<dim3(gx, gy), 256, 0, stream>>>(src, L, mips, gx * gy, 0u, 0u, vq_spd_ticket(ctx));
     return vq_check_launch("hdri_build_mips(spd)");
 }

@@ -4,9 +4,8 @@
 //                                  shadowing directional light multiplied by their PCF tests (Lighting.hlsl:79-272)
 //   vq_depth_min_pyramid           DownsampleDepth.hlsl:50-119 (FidelityFX SPD with the MIN reduction over a D3D mip chain)
 //
-// STATUS: written against the oracle (oracle/oracle_shadow.cpp, itself pinned bit for bit to the reference's shader text,
-// tests/test_hlsl_ref.py), compiled for sm_100a, NOT YET RUN ON A GPU (the round's GPU budget was spent when this row was
-// reached): its parity tests carry the `gpu_next` marker instead of `gpu` (tests/test_zz_shadow_gpu_next.py).
+// Checked against the oracle (oracle/oracle_shadow.cpp, itself pinned bit for bit to the reference's shader text,
+// tests/test_hlsl_ref.py) on a B200: tests/test_shadow_gpu.py (-m gpu), memcheck clean (profiles/r02_shadow_first_run.txt).
 //
 // Structure of the shadowed pass = the oracle's: K1 (vq_forward.cu) shades everything that involves no caster — ambient,
 // emissive, IBL, the non-shadowing point and spot lights — with the caster lists emptied and the directional light off;
@@ -14,7 +13,7 @@
 // and the directional light x ShadowTestPCF_Directional onto that result. The sum order is the reference's.
 //
 // The per-pixel math lives in vq_shadow_math.cuh, which also compiles for the HOST: tests/test_shadow_math_host.py checks it
-// against the oracle bit for bit on the CPU, so what is unverified here is only the launch code around it.
+// against the oracle bit for bit on the CPU.
 #include "vq_common.cuh"
 #include "vq_shadow_math.cuh"
 #include <string.h>
@@ -119,6 +118,7 @@ extern "C" int vq_depth_min_pyramid(VqContext* ctx, VqImage depth, void* levels,
     VQ_REQUIRE(n_levels >= 1 && n_levels <= vq_depth_pyramid_level_count(W, H), "level count out of range");
     // two ping-pong buffers for the padded-domain levels (ceil-halved sizes): level 1 is at most ceil(W/2) x ceil(H/2)
     const size_t padBytes = (size_t)((W + 1) / 2) * ((H + 1) / 2) * 4;
+    VqScratchLock lock(ctx);
     rc = ensure_scratch(&ctx->depth_pad, &ctx->depth_pad_bytes, padBytes * 2 > 16 ? padBytes * 2 : 16); if (rc) return rc;
     float* padA = (float*)ctx->depth_pad;
     float* padB = padA + padBytes / 4;
