@@ -1,9 +1,12 @@
 #!/usr/bin/env python
 """bench.py — headline benchmark of the B200 shading backend (contract: task brief + BASELINE.json).
 
-A "step" is ONE forward-PBR lighting pass (K1) over a 3840x2160 synthetic G-buffer with 4 point lights,
-1 directional light and IBL (BASELINE.json metric "Mpixels/s forward-PBR @4K"), inputs resident in HBM.
-  value      = Mpixels/s over all ranks (weak scaling: every rank shades its own 3840x2160 row tile)
+A "step" is ONE forward-PBR lighting pass (K1) with 4 point lights, 1 directional light and IBL, inputs resident in HBM:
+  N = 1   the 3840x2160 synthetic G-buffer of BASELINE.json's metric "Mpixels/s forward-PBR @4K";
+  N > 1   BASELINE config 5's 7680x4320 frame, STRONG-scaled: rank r shades rows [r*4320/N, (r+1)*4320/N) and the kernel itself
+          stores every pixel into the frame of every rank over NVLink and runs the cross-rank rendezvous (ONE kernel = shade +
+          tile assembly + barrier), so `value` includes the gather the north star names; kernel-only is under "kernel_only".
+  value      = Mpixels/s of the whole job (max over ranks of the device time)
   e2e        = the same pass through the blocking host-buffer C-ABI call (pinned host G-buffer in,
                host image out; H2D/D2H inside the timed region)
   roofline   = algorithmic 64 B/pixel / kernel time, against the measured HBM copy peak
@@ -31,6 +34,7 @@ for _p in (ROOT, os.path.join(ROOT, "tests")):
         sys.path.insert(0, _p)
 
 W4K, H4K = 3840, 2160
+W8K, H8K = 7680, 4320
 BYTES_PER_PX = 64          # 3 x float4 in + 1 x float4 out
 METRIC = "forward_pbr_4k_mpixels_per_s"
 UNIT = "Mpixels/s"
@@ -45,6 +49,53 @@ def hbm_peak():
         except Exception:
             pass
     return 6650.0, "fallback (B200_PROFILING.md)"
+
+
+def _forward_source_digest():
+    import hashlib
+    h = hashlib.sha256()
+    for f in ("vq_forward.cu", "vq_common.cuh"):
+        h.update(open(os.path.join(ROOT, "vqengine_b200", "csrc", f), "rb").read())
+    return h.hexdigest()[:16]
+
+
+def forward_profile_facts():
+    """dram bytes and warp-instructions per 4K launch of K1 from the committed ncu capture (profiles/forward_traffic.json). The file
+    carries the digest of the kernel source it was captured from: a stale file (the kernel changed since) is refused, not quoted."""
+    tp = os.path.join(ROOT, "profiles", "forward_traffic.json")
+    try:
+        j = json.load(open(tp))
+    except Exception:
+        return None, None, "profiles/forward_traffic.json absent"
+    if j.get("source_digest") != _forward_source_digest():
+        return None, None, f"profiles/forward_traffic.json is stale (captured from source {j.get('source_digest')}, tree is {_forward_source_digest()})"
+    return j.get("dram_bytes_per_launch"), j.get("warp_instructions_per_launch"), j.get("capture", "profiles/")
+
+
+def pin_to_gpu_numa_node(torch, local):
+    """e2e copies cross PCIe from pinned host memory: keep this rank's threads (and so its first-touch pinned pages) on the NUMA
+    node its GPU hangs off. Returns a short description for the JSON line."""
+    try:
+        bus = torch.cuda.get_device_properties(local).pci_bus_id if hasattr(torch.cuda.get_device_properties(local), "pci_bus_id") else None
+        dom = getattr(torch.cuda.get_device_properties(local), "pci_domain_id", 0)
+        dev = getattr(torch.cuda.get_device_properties(local), "pci_device_id", 0)
+        if bus is None:
+            return "unpinned (no pci ids)"
+        path = f"/sys/bus/pci/devices/{dom:04x}:{bus:02x}:{dev:02x}.0/numa_node"
+        node = int(open(path).read().strip())
+        if node < 0:
+            return "unpinned (single node)"
+        cpus = set()
+        for part in open(f"/sys/devices/system/node/node{node}/cpulist").read().strip().split(","):
+            a, _, b = part.partition("-")
+            cpus.update(range(int(a), int(b or a) + 1))
+        cpus &= os.sched_getaffinity(0)
+        if cpus:
+            os.sched_setaffinity(0, cpus)
+            return f"numa node {node} ({len(cpus)} cpus)"
+        return f"unpinned (node {node} has no allowed cpus)"
+    except Exception as ex:
+        return f"unpinned ({type(ex).__name__})"
 
 
 class ClockSampler:
@@ -306,85 +357,98 @@ def surface_producer_pass(ctx, vq, torch, peak):
     return out
 
 
-def ibl_specular_strong_scaling(ctx, vq, torch, dist, rank, world, hdri_w=4096, hdri_h=2048, res=512, mips=9, iters=3):
-    """BASELINE config 5 (IBL half): 4096x2048 HDRI -> 512^2 x6 x9-mip specular prefilter, STRONG scaling: the flattened
-    (mip, face, row) space is cut into `world` cost-balanced contiguous ranges, every rank prefilters its range from a
-    replicated HDRI pyramid, then ONE all-gather assembles the packed cubemap on every rank (inside the timed region)."""
+class PeerFlags:
+    """world 32-bit flag words per rank in symmetric memory + the VqPeerSignal that points at them: the rendezvous a fused
+    compute+gather kernel runs in its last CTA (include/vqcuda.h). `next()` advances the epoch for one more step."""
+
+    def __init__(self, vq, torch, dist, rank, world):
+        import torch.distributed._symmetric_memory as symm
+        self.t = symm.empty((world,), dtype=torch.int32, device=torch.device("cuda", torch.cuda.current_device()))
+        self.hdl = symm.rendezvous(self.t, dist.group.WORLD)
+        self.t.zero_(); torch.cuda.synchronize(); dist.barrier()
+        self.sig = vq.PeerSignal()
+        order = [rank] + [(rank + k) % world for k in range(1, world)]
+        for i, r in enumerate(order):
+            self.sig.flags[i] = int(self.hdl.buffer_ptrs[r])
+        self.sig.n_ranks, self.sig.my_index, self.sig.epoch = world, rank, 0
+        self.order = order
+
+    def next(self):
+        self.sig.epoch += 1
+        return self.sig
+
+
+def ibl_specular_strong_scaling(ctx, vq, torch, dist, rank, world, hdri_w=4096, hdri_h=2048, res=512, mips=9, iters=20):
+    """BASELINE config 5 (IBL half): 4096x2048 HDRI -> 512^2 x6 x9-mip specular prefilter, STRONG scaling. Rank r takes block r of
+    every mip whose rows divide by the world size (equal cost and equal bytes), the 2x2 mip is computed by every rank.
+      fused_p2p : ONE persistent kernel per rank and step (vq_specular_prefilter_ranges): all of the rank's blocks, every texel
+                  stored into all ranks' cubemaps over NVLink while the SMs integrate, the cross-rank rendezvous run by the
+                  kernel's last CTA — no per-mip launches, no host-issued barrier;
+      nccl      : the same single launch into the local cubemap, then pack -> ONE all_gather_into_tensor -> unpack."""
     from vqengine_b200 import synth, distributed as vd
     levels = vq.mip_level_count(hdri_w, hdri_h)
     pyr_t = torch.zeros((vq.pyramid_texel_count(hdri_w, hdri_h, levels), 4), dtype=torch.float32, device="cuda")
     pyr_t[: hdri_w * hdri_h] = torch.from_numpy(synth.hdri(hdri_w, hdri_h)).cuda().reshape(-1, 4)
     pyr = vq.pyramid_of(pyr_t, hdri_w, hdri_h, levels)
     ctx.hdri_build_mips(pyr)
-    cube_t = torch.zeros((vq.cubemap_texel_count(res, mips), 4), dtype=torch.float32, device="cuda")
+    n_tex = vq.cubemap_texel_count(res, mips)
+    cube_t = torch.zeros((n_tex, 4), dtype=torch.float32, device="cuda")
     cube = vq.cubemap_of(cube_t, res, mips)
     plan = vd.InterleavedSpecularPlan(res, mips, world)
     my_rows = plan.row_ranges(rank)
 
     def compute():
-        for rb, re in my_rows:
-            ctx.specular_prefilter(pyr, cube, 512, rb, re)
+        ctx.specular_prefilter_ranges(pyr, [cube], my_rows, 512)
 
     def step():
         compute()
         if dist is not None and world > 1:
             plan.gather(cube_t, rank)
 
-    step(); torch.cuda.synchronize()
-    if dist: dist.barrier()
-    e0, e1, e2 = (torch.cuda.Event(enable_timing=True) for _ in range(3))
-    e0.record()
-    for _ in range(iters):
-        step()
-    e1.record()
-    for _ in range(iters):
-        compute()
-    e2.record()
-    torch.cuda.synchronize()
-    t = torch.tensor([e0.elapsed_time(e1) / iters, e1.elapsed_time(e2) / iters], dtype=torch.float64, device="cuda")
-    if dist: dist.all_reduce(t, op=dist.ReduceOp.MAX)
-    ms, ms_compute = float(t[0]), float(t[1])
-    n_tex = vq.cubemap_texel_count(res, mips)
-    # ---- fused compute + gather: the prefilter kernels store every texel straight into all ranks' cubemaps over NVLink
-    #      (peer pointers from torch symmetric memory); one device-side barrier ends the step ----
+    def timed(fn):
+        for _ in range(3):
+            fn()
+        torch.cuda.synchronize()
+        if dist: dist.barrier()
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(iters):
+            fn()
+        e1.record(); torch.cuda.synchronize()
+        t = torch.tensor([e0.elapsed_time(e1) / iters], dtype=torch.float64, device="cuda")
+        if dist: dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t[0])
+
+    ms_compute = timed(compute)
+    ms = timed(step) if (dist is not None and world > 1) else ms_compute
     fused = None
     if dist is not None and world > 1:
         try:
             import torch.distributed._symmetric_memory as symm
             sym_t = symm.empty((n_tex, 4), dtype=torch.float32, device=torch.device("cuda", torch.cuda.current_device()))
             hdl = symm.rendezvous(sym_t, dist.group.WORLD)
-            peers = [hdl.get_buffer(r, (n_tex, 4), torch.float32) for r in range(world)]
-            order = [rank] + [r for r in range(world) if r != rank]
-            cubes = [vq.cubemap_of(peers[r], res, mips) for r in order]
-            split_rows = [(r0 + rank * k, r0 + (rank + 1) * k) for (_, r0, k, _) in plan.split]
-            repl_rows = [(r0, r0 + rows) for (_, r0, rows, _) in plan.replicated]
+            flags = PeerFlags(vq, torch, dist, rank, world)
+            cubes = [vq.cubemap_of(hdl.get_buffer(r, (n_tex, 4), torch.float32), res, mips) for r in flags.order]
 
             def fused_step():
-                for rb, re in split_rows:
-                    ctx.specular_prefilter_multi(pyr, cubes, 512, rb, re)       # my block of every split mip -> all ranks
-                for rb, re in repl_rows:
-                    ctx.specular_prefilter(pyr, cubes[0], 512, rb, re)          # tiny mips: every rank computes its own copy
-                hdl.barrier()
+                ctx.specular_prefilter_ranges(pyr, cubes, my_rows, 512, signal=flags.next())
 
-            fused_step(); torch.cuda.synchronize(); dist.barrier()
-            same = bool(torch.equal(sym_t, cube_t))
-            f0, f1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-            f0.record()
-            for _ in range(iters):
-                fused_step()
-            f1.record(); torch.cuda.synchronize()
-            tf = torch.tensor([f0.elapsed_time(f1) / iters], dtype=torch.float64, device="cuda")
-            dist.all_reduce(tf, op=dist.ReduceOp.MAX)
-            fused = {"ms": round(float(tf[0]), 3), "texels_per_s": round(n_tex / float(tf[0]) * 1e3), "equals_nccl_allgather": same,
-                     "how": "vq_specular_prefilter_multi: every prefiltered texel is stored into all ranks' cubemaps (symmetric-memory peer pointers, NVLink P2P) while the SMs integrate; one device-side barrier"}
-            del sym_t, peers
+            step(); fused_step(); torch.cuda.synchronize(); dist.barrier()
+            same = torch.tensor([1.0 if torch.equal(sym_t, cube_t) else 0.0], device="cuda")
+            dist.all_reduce(same, op=dist.ReduceOp.MIN)
+            ms_f = timed(fused_step)
+            fused = {"ms": round(ms_f, 4), "texels_per_s": round(n_tex / ms_f * 1e3), "equals_nccl_allgather": bool(same.item() == 1.0),
+                     "launches_per_step": 1,
+                     "how": "vq_specular_prefilter_ranges: one persistent kernel per rank (device work list over the rank's blocks of every mip), every texel stored into all ranks' cubemaps (symmetric-memory peer pointers, NVLink P2P), rendezvous through peer flag words in the kernel's last CTA"}
+            del sym_t
         except Exception as ex:   # symmetric memory unavailable on this box: keep the NCCL numbers
             fused = {"error": repr(ex)[:300]}
     del pyr_t, cube_t
-    return {"config": f"{hdri_w}x{hdri_h} HDRI -> {res}^2 x6 x{mips} mips, 512 samples; strong scaling over {world} GPU(s): every mip split into {world} equal row blocks (tiny mips replicated) + ONE all-gather of the 33.5 MB cubemap",
-            "ms": round(ms, 3), "texels_per_s": round(n_tex / ms * 1e3), "ms_compute_only": round(ms_compute, 3),
+    return {"config": f"{hdri_w}x{hdri_h} HDRI -> {res}^2 x6 x{mips} mips, 512 samples; strong scaling over {world} GPU(s): every mip split into {world} equal row blocks (tiny mips replicated); {iters} timed iterations",
+            "ms": round(ms, 4), "texels_per_s": round(n_tex / ms * 1e3), "ms_compute_only": round(ms_compute, 4),
             "rows_per_rank": sum(b - a for a, b in my_rows), "replicated_mips": [m for (m, _, _, _) in plan.replicated],
-            "fused_p2p": fused}
+            "launches_per_step_compute": 1, "fused_p2p": fused}
 
 
 # ------------------------------------------------------------------------------------------------
@@ -457,11 +521,86 @@ def cpu_reference_image_class(hw=4096, hh=2048):
             "image_save_to_disk_ms": round(t_save * 1e3, 1)}
 
 
-def cpu_env():
-    """IBL maps for the CPU arm, built by the ORACLE at reduced sizes (the full-size maps would cost the scalar CPU
-    code minutes; map size does not change the per-pixel work of the forward pass)."""
-    from envmaps import small_env
-    return small_env(hdri_w=256, hdri_h=128, diff_res=16, spec_res=64, spec_mips=6, lut=64, seed=77)
+def _nolib():
+    """vqengine_b200's synthetic inputs + ctypes struct mirror WITHOUT libvqcuda.so: the CPU arms (`--impl reference`,
+    `--impl cpu-port`) must not load the product. The two plain-data modules are imported under an alias package whose
+    __init__ never runs."""
+    import importlib
+    import types
+    name = "vqengine_b200_nolib"
+    if name not in sys.modules:
+        pkg = types.ModuleType(name)
+        pkg.__path__ = [os.path.join(ROOT, "vqengine_b200")]
+        sys.modules[name] = pkg
+    return importlib.import_module(name + ".synth")
+
+
+_ENV_JOB = {}
+
+
+def _env_rows_worker(job):
+    import oracle_lib as orc
+    kind, a, b, n = job
+    j = _ENV_JOB
+    if kind == "spec":
+        return a, b, orc.specular_prefilter(j["pyr"], j["hw"], j["hh"], j["levels"], j["spec_res"], j["spec_mips"], n, a, b, 1)
+    return a, b, orc.brdf_integration_lut(j["lut"], j["lut"], 2048, a, b, 1)[a:b]
+
+
+def cpu_env(hdri_w=2048, hdri_h=1024, diff_res=64, spec_res=512, spec_mips=9, lut=1024):
+    """The forward pass's IBL inputs for the CPU arms at the SAME sizes as the GPU arm's (64^2 diffuse, 512^2 x 9 specular, 1024^2
+    LUT from the same seeded 2048x1024 HDRI), built by the ORACLE on the host cores (untimed set-up; one forked process per
+    core, cached in the temp dir for the other CPU arm of the same box). Mip 0 of the specular cube (roughness 0: every one of the
+    512 samples is the same direction) is built with one sample per texel — the same texels up to the rounding of the replayed
+    sums — which keeps the set-up to tens of seconds."""
+    import multiprocessing as mp
+    import tempfile
+    import numpy as np
+    import oracle_lib as orc
+    synth = _nolib()
+    cache = os.path.join(tempfile.gettempdir(), f"vq_cpu_env_{hdri_w}x{hdri_h}_{diff_res}_{spec_res}x{spec_mips}_{lut}.npz")
+    if os.path.exists(cache):
+        try:
+            z = np.load(cache)
+            return dict(diff=z["diff"], diff_res=diff_res, spec=z["spec"], spec_res=spec_res, spec_mips=spec_mips, lut=z["lut"])
+        except Exception:
+            pass
+    t0 = time.perf_counter()
+    levels = orc.lib().orc_mip_level_count(hdri_w, hdri_h)
+    pyr = orc.hdri_build_mips(synth.hdri(hdri_w, hdri_h), levels)
+    diff = orc.diffuse_irradiance(pyr, hdri_w, hdri_h, levels, diff_res, n_phi=64, n_theta=16, src_mip=3)
+    faces = diff.reshape(6, diff_res, diff_res, 4)
+    diff = np.ascontiguousarray(np.stack([orc.gaussian_blur(orc.gaussian_blur(f, False), True) for f in faces]).reshape(-1, 4))
+    _ENV_JOB.update(pyr=pyr, hw=hdri_w, hh=hdri_h, levels=levels, spec_res=spec_res, spec_mips=spec_mips, lut=lut)
+    procs = orc.cpu_threads()
+    rows0 = 6 * spec_res
+    total_rows = int(orc.lib().orc_cubemap_row_count(spec_res, spec_mips))
+    jobs = [("spec", a, min(a + 64, rows0), 1) for a in range(0, rows0, 64)]                       # mip 0, one sample
+    jobs += [("spec", a, min(a + 8, total_rows), 512) for a in range(rows0, total_rows, 8)]         # mips 1.., 512 samples
+    jobs += [("lut", a, min(a + 8, lut), 0) for a in range(0, lut, 8)]
+    spec = np.zeros((int(orc.lib().orc_cubemap_texel_count(spec_res, spec_mips)), 4), np.float32)
+    lut_img = np.zeros((lut, lut, 2), np.float32)
+    row_tex = [0]
+    for m in range(spec_mips):
+        n = spec_res >> m
+        row_tex += [row_tex[-1] + n * (k + 1) - n * k for k in range(6 * n)]
+    with mp.get_context("fork").Pool(procs) as pool:
+        for kind, a, b, r in pool.imap_unordered(_env_rows_worker_tagged, jobs, chunksize=1):
+            if kind == "spec":
+                spec[row_tex[a]:row_tex[b]] = r[row_tex[a]:row_tex[b]]
+            else:
+                lut_img[a:b] = r
+    try:
+        np.savez(cache, diff=diff, spec=spec, lut=lut_img)
+    except Exception:
+        pass
+    print(f"# cpu_env: full-size IBL maps built by the oracle in {time.perf_counter() - t0:.1f} s on {procs} processes", file=sys.stderr)
+    return dict(diff=diff, diff_res=diff_res, spec=spec, spec_res=spec_res, spec_mips=spec_mips, lut=lut_img)
+
+
+def _env_rows_worker_tagged(job):
+    a, b, r = _env_rows_worker(job)
+    return job[0], a, b, r
 
 
 _REF_JOB = {}
@@ -520,7 +659,7 @@ def _cpu_arm(kind, steps, warmup, planes, pf, pv, a, budget_s=60.0):
 
 
 def _cpu_workload():
-    from vqengine_b200 import synth
+    synth = _nolib()
     env = cpu_env()
     planes = synth.gbuffer(W4K, 512, seed=synth.SEED_BASE + 3)   # a 512-row band of the 4K G-buffer
     pf, pv = synth.scene_constants(W4K, H4K, env["spec_mips"])
@@ -623,53 +762,75 @@ def main():
         import torch.distributed as dist
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
     peak, peak_src = hbm_peak()
+    numa = pin_to_gpu_numa_node(torch, local)
     ctx = vq.Context(local)
     envk = build_env_maps_gpu(ctx, vq, torch)
 
-    # this rank's row tile of the 3840 x (2160*world) frame: weak scaling, fixed work per GPU
-    planes = synth.gbuffer(W4K, H4K, seed=synth.SEED_BASE + 3 + rank)
-    pf, pv = synth.scene_constants(W4K, H4K, envk["spec_mips"])
+    # ---- the workload: N = 1 the metric's 4K frame; N > 1 config 5's 8K frame cut into `world` row tiles (strong scaling) ----
+    FW, FH = (W4K, H4K) if world == 1 else (W8K, H8K)
+    rb, re = (FH * rank) // world, (FH * (rank + 1)) // world
+    rows = re - rb
+    planes = synth.gbuffer(FW, rows, seed=synth.SEED_BASE + 3 + rank)        # this rank's rows of the frame's G-buffer
+    pf, pv = synth.scene_constants(FW, FH, envk["spec_mips"])
     dpl = [torch.from_numpy(p).cuda() for p in planes]
     gb = vq.GBuffer(vq.image_of(dpl[0]), vq.image_of(dpl[1]), vq.image_of(dpl[2]), vq.null_image())
-    out = torch.zeros((H4K, W4K, 4), dtype=torch.float32, device="cuda")
-    step = lambda: ctx.forward_lighting(pf, pv, gb, envk["env"], out)
+    out = torch.zeros((rows, FW, 4), dtype=torch.float32, device="cuda")
+    kernel_only = lambda: ctx.forward_lighting(pf, pv, gb, envk["env"], out)
+    frame = full = flags = None
+    fused_note = None
+    if world > 1:
+        import torch.distributed._symmetric_memory as symm
+        frame = symm.empty((FH, FW, 4), dtype=torch.float32, device=torch.device("cuda", local))   # every rank holds the assembled frame
+        hdl = symm.rendezvous(frame, dist.group.WORLD)
+        frame.zero_(); torch.cuda.synchronize(); dist.barrier()
+        flags = PeerFlags(vq, torch, dist, rank, world)
+        # local frame first, then the peers in a rotated order so that the ranks do not all write to the same peer at once
+        imgs = [vq.Image(int(hdl.buffer_ptrs[r]), FW, FH, FW * 16) for r in flags.order]
+        step = lambda: ctx.forward_lighting_multi(pf, pv, gb, envk["env"], imgs, rb, signal=flags.next())
+        fused_note = ("vq_forward_lighting_multi_signal: ONE kernel per rank shades its rows, stores every pixel into every rank's frame "
+                      "(symmetric-memory peer pointers, NVLink P2P) and runs the cross-rank rendezvous in its last CTA")
+    else:
+        step = kernel_only
 
-    launches0 = vq.launch_count()
+    def timed(fn, n):
+        """n launches of fn between barriers; device time, max over ranks -> ms per launch"""
+        torch.cuda.synchronize()
+        if dist: dist.barrier()
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(n):
+            fn()
+        e1.record()
+        torch.cuda.synchronize()
+        if dist: dist.barrier()
+        torch.cuda.synchronize()
+        t = torch.tensor([e0.elapsed_time(e1)], dtype=torch.float64, device="cuda")
+        if dist: dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item()) / n
+
     for _ in range(args.warmup):
         step()
-    torch.cuda.synchronize()
-    if dist: dist.barrier()
-    torch.cuda.synchronize()
     sampler = ClockSampler(local); sampler.start()
     time.sleep(0.15)
-    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     lt0 = vq.launch_count()
-    e0.record()
-    for _ in range(args.steps):
-        step()
-    e1.record()
-    torch.cuda.synchronize()
-    if dist: dist.barrier()
-    torch.cuda.synchronize()
+    ms_step = timed(step, args.steps)
     timed_launches = vq.launch_count() - lt0
-    ms_total = e0.elapsed_time(e1)
     # keep the GPU busy a little longer so that the clock sampler sees the load even for short runs
     t_end = time.time() + 0.4
     while time.time() < t_end:
-        step()
+        kernel_only()
     torch.cuda.synchronize()
     clocks = sampler.stop()
-    t = torch.tensor([ms_total], dtype=torch.float64, device="cuda")
-    if dist: dist.all_reduce(t, op=dist.ReduceOp.MAX)
-    ms_step = float(t.item()) / args.steps
-    px_all = W4K * H4K * world
+    px_all = FW * FH
     value = px_all / ms_step / 1e3   # Mpixels/s
+    ms_kernel = timed(kernel_only, args.steps) if world > 1 else ms_step
 
-    # ---- e2e: the blocking host-buffer call, pinned host memory, H2D + D2H inside the timed region ----
+    # ---- e2e: the blocking host-buffer call on this rank's tile, pinned host memory, H2D + D2H inside the timed region ----
     hpl = [torch.from_numpy(p).pin_memory() for p in planes]
     hgb = vq.GBuffer(vq.image_of(hpl[0]), vq.image_of(hpl[1]), vq.image_of(hpl[2]), vq.null_image())
-    hout = torch.zeros((H4K, W4K, 4), dtype=torch.float32).pin_memory()
-    ctx.resize(W4K, H4K)
+    hout = torch.zeros((rows, FW, 4), dtype=torch.float32).pin_memory()
+    ctx.resize(FW, rows)
     e2e_steps = max(3, min(args.steps, 10))
     for _ in range(2):
         ctx.forward_lighting_host(pf, pv, hgb, envk["env"], hout)
@@ -683,75 +844,60 @@ def main():
     t = torch.tensor([dt], dtype=torch.float64, device="cuda")
     if dist: dist.all_reduce(t, op=dist.ReduceOp.MAX)
     e2e_val = px_all / float(t.item()) / 1e6
+    kernel_only(); torch.cuda.synchronize()
     assert torch.equal(hout.cuda(), out), "host-buffer path and device path disagree"
-    h2d, d2h = 3 * W4K * H4K * 16, W4K * H4K * 16
+    h2d, d2h = 3 * FW * rows * 16, FW * rows * 16
 
-    # ---- multi-GPU: one all-gather of the shaded tiles over NVLink (reported separately) ----
+    # ---- multi-GPU: the NCCL baseline of the same step (kernel, then one all-gather of the tiles) and the identity check ----
     gather = None
     if dist:
-        full = torch.empty((world * H4K, W4K, 4), dtype=torch.float32, device="cuda")
+        full = torch.empty((FH, FW, 4), dtype=torch.float32, device="cuda")
+        nccl_step = lambda: (kernel_only(), dist.all_gather_into_tensor(full, out))
         for _ in range(2):
-            dist.all_gather_into_tensor(full, out)
-        torch.cuda.synchronize(); dist.barrier(); torch.cuda.synchronize()
-        g0, g1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        g0.record()
-        for _ in range(5):
-            step()
-            dist.all_gather_into_tensor(full, out)
-        g1.record(); torch.cuda.synchronize()
-        tg = torch.tensor([g0.elapsed_time(g1) / 5], dtype=torch.float64, device="cuda")
-        dist.all_reduce(tg, op=dist.ReduceOp.MAX)
-        gather = {"ms_per_step_with_allgather": round(float(tg.item()), 4),
-                  "value_with_allgather": round(px_all / float(tg.item()) / 1e3, 1),
-                  "allgather_bytes_per_rank_in": (world - 1) * H4K * W4K * 16}
-        # reference result of the NCCL path for the fused check below
-        step(); dist.all_gather_into_tensor(full, out); torch.cuda.synchronize()
-        # ---- fused compute + gather: the forward kernel stores every pixel straight into all ranks' frames over NVLink
-        #      (peer pointers from torch symmetric memory), so the transfer overlaps the shading ----
-        try:
-            import torch.distributed._symmetric_memory as symm
-            frame = symm.empty((world * H4K, W4K, 4), dtype=torch.float32, device=torch.device("cuda", local))
-            hdl = symm.rendezvous(frame, dist.group.WORLD)
-            frame.zero_(); torch.cuda.synchronize(); dist.barrier()
-            # local frame first, then peers in a rotated order so that the ranks do not all write to the same peer at once
-            imgs = [vq.Image(int(hdl.buffer_ptrs[(rank + k) % world]), W4K, world * H4K, W4K * 16) for k in range(world)]
-            fused = lambda: ctx.forward_lighting_multi(pf, pv, gb, envk["env"], imgs, rank * H4K)
-            for _ in range(2):
-                fused(); hdl.barrier()
-            torch.cuda.synchronize(); dist.barrier(); torch.cuda.synchronize()
-            f0, f1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-            f0.record()
-            for _ in range(5):
-                fused(); hdl.barrier()
-            f1.record(); torch.cuda.synchronize()
-            tf = torch.tensor([f0.elapsed_time(f1) / 5], dtype=torch.float64, device="cuda")
-            dist.all_reduce(tf, op=dist.ReduceOp.MAX)
-            same = torch.tensor([1.0 if torch.equal(frame, full) else 0.0], device="cuda")
-            dist.all_reduce(same, op=dist.ReduceOp.MIN)
-            gather["fused_p2p"] = {"ms_per_step": round(float(tf.item()), 4), "value": round(px_all / float(tf.item()) / 1e3, 1),
-                                   "equals_nccl_allgather": bool(same.item() == 1.0),
-                                   "how": "vq_forward_lighting_multi: one kernel shades the local tile and stores it into every rank's frame (symmetric-memory peer pointers, NVLink P2P), then one device-side barrier"}
-            del frame
-        except Exception as ex:   # symmetric memory unavailable on this box: keep the NCCL numbers
-            gather["fused_p2p"] = {"error": repr(ex)[:300]}
-        del full
+            nccl_step()
+        ms_nccl = timed(nccl_step, max(5, args.steps // 2))
+        step(); nccl_step(); torch.cuda.synchronize(); dist.barrier()
+        same = torch.tensor([1.0 if torch.equal(frame, full) else 0.0], device="cuda")
+        dist.all_reduce(same, op=dist.ReduceOp.MIN)
+        ingress = (world - 1) * (FH // world) * FW * 16
+        gather = {"fused_p2p": {"ms_per_step": round(ms_step, 5), "value": round(value, 1), "equals_nccl_allgather": bool(same.item() == 1.0),
+                                "nvlink_ingress_bytes_per_rank": ingress, "nvlink_ingress_GBps_per_rank": round(ingress / ms_step / 1e6, 1),
+                                "nvlink_nominal_GBps_per_direction": 900, "how": fused_note},
+                  "nccl_allgather": {"ms_per_step": round(ms_nccl, 5), "value": round(px_all / ms_nccl / 1e3, 1)},
+                  "kernel_only": {"ms_per_step": round(ms_kernel, 5), "value": round(px_all / ms_kernel / 1e3, 1),
+                                  "note": "the rank's rows shaded into a local tile, no assembly: what round 1 reported as `value`"}}
+        del full, frame
+        full = frame = None
 
     line = None
     if rank == 0:
-        achieved = BYTES_PER_PX * W4K * H4K / (ms_step * 1e-3) / 1e9   # per-GPU GB/s of the dominant (only) kernel
-        traffic = None
-        tp = os.path.join(ROOT, "profiles", "forward_traffic.json")
-        if os.path.exists(tp):
-            try: traffic = json.load(open(tp)).get("dram_bytes_per_launch")
-            except Exception: pass
+        # the dominant kernel, timed alone on this rank's rows (at N = 1 that is the step itself)
+        achieved = BYTES_PER_PX * FW * rows / (ms_kernel * 1e-3) / 1e9
+        traffic, winst, cap = forward_profile_facts()
+        issue = None
+        if winst and clocks.get("sm_mhz"):
+            # issue-slot roofline: warp-instructions per 4K launch (ncu) / (SMs x 4 schedulers x SM clock under load)
+            sm_count = torch.cuda.get_device_properties(local).multi_processor_count
+            floor_ms = winst / (sm_count * 4 * clocks["sm_mhz"] * 1e6) * 1e3
+            ms_4k = ms_kernel * (W4K * H4K) / (FW * rows)
+            issue = {"warp_instructions_per_4k_launch": winst, "issue_floor_ms_4k": round(floor_ms, 4),
+                     "frac_of_issue_floor": round(floor_ms / ms_4k, 4), "note": "one instruction per scheduler and cycle; " + str(cap)}
+        if world == 1:
+            cfg = {"workload": WORKLOAD, "frame": f"{FW}x{FH}", "parallelism": "1 GPU"}
+        else:
+            cfg = {"workload": WORKLOAD.replace("3840x2160", "7680x4320"), "frame": f"{FW}x{FH}", "rows_per_gpu": rows,
+                   "parallelism": f"row-tiles x{world} (strong scaling of BASELINE config 5's frame), fused peer-store assembly + in-kernel rendezvous inside `value`",
+                   "nvlink": f"every rank receives (N-1)/N x 531 MB = {(world - 1) * (FH // world) * FW * 16 / 1e6:.0f} MB per step",
+                   "n1_line": "at N = 1 bench.py shades the metric's 3840x2160 frame (same kernel, same Mpixels/s unit)"}
+        cfg["l2_policy"] = "inputs + output per step exceed the 126 MB L2 (4K: 398 + 133 MB); no flush needed"
+        cfg["host_numa"] = numa
         line = {"metric": METRIC, "value": round(value, 1), "unit": UNIT, "n_gpus": world, "steps": args.steps,
-                "warmup": args.warmup, "ms_per_step": round(ms_step, 5), "higher_is_better": True, "scaling": "weak",
-                "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-                "config": {"workload": WORKLOAD, "tile_per_gpu": f"{W4K}x{H4K}", "frame": f"{W4K}x{H4K * world}",
-                           "parallelism": f"row-tiles x{world}", "l2_policy": "inputs (398 MB) + output (133 MB) per step exceed the 126 MB L2; no flush needed"},
+                "warmup": args.warmup, "ms_per_step": round(ms_step, 5), "higher_is_better": True,
+                "scaling": "strong" if world > 1 else "weak",
+                "vs_baseline": None, "dtype": "f32", "data": "synthetic", "config": cfg,
                 "roofline": {"bound": "hbm", "kernel": "forward_kernel", "achieved": round(achieved, 1), "peak": peak, "unit": "GB/s",
-                             "frac": round(achieved / peak, 4), "traffic": traffic, "peak_source": peak_src,
-                             "algorithmic_bytes_per_launch": BYTES_PER_PX * W4K * H4K},
+                             "frac": round(achieved / peak, 4), "traffic": traffic, "traffic_source": cap, "peak_source": peak_src,
+                             "algorithmic_bytes_per_launch": BYTES_PER_PX * FW * rows, "issue": issue},
                 "e2e": {"value": round(e2e_val, 1), "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                         "api": "vq_forward_lighting_host (pinned host buffers, 16 row chunks pipelined over 3 streams)"},
                 "gpu_launches": int(timed_launches), "clocks": clocks}

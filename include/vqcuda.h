@@ -114,6 +114,19 @@ VQ_API const char* vq_version(void);
 /* Number of kernels this library has launched in this process (all contexts). */
 VQ_API uint64_t vq_launch_count(void);
 
+/* End-of-pass rendezvous of a multi-GPU step, run by the kernel itself (its last CTA): after all of this rank's stores
+ * (local and peer) are ordered, it writes `epoch` into word `my_index` of every OTHER rank's flag array and then waits
+ * until words j != my_index of its OWN array have reached `epoch` — i.e. until every peer has finished storing into this
+ * rank's buffers. flags[0] = this rank's array, flags[1..n_ranks-1] = the peers' arrays mapped into this process
+ * (n_ranks 32-bit words each, zero-initialised, e.g. in torch symmetric memory); epoch must increase from call to call.
+ * Replaces a host-issued barrier per step: the step is ONE kernel. */
+typedef struct VqPeerSignal {
+    uint32_t* flags[8];
+    int32_t   n_ranks;
+    int32_t   my_index;
+    uint32_t  epoch;
+} VqPeerSignal;
+
 /* ------------------------------------------------------------------------------------------
  * K1  Forward PBR lighting.  Replaces VQRenderer::RenderSceneColor (SceneRendering.cpp:1619-1851)
  *     + PSMain (ForwardLighting.hlsl:222-391) over a G-buffer instead of rasterised draws.
@@ -144,6 +157,10 @@ VQ_API int vq_forward_lighting_multi(VqContext* ctx,
                                      const VqImage* out_frames, int n_outs, int dst_row_offset,
                                      int row_begin, int row_end,
                                      void* stream);
+/* ... and with the cross-rank rendezvous run by the kernel's last CTA (VqPeerSignal above): shade + gather + barrier = ONE kernel. */
+VQ_API int vq_forward_lighting_multi_signal(VqContext* ctx, const VqPerFrameData* per_frame, const VqPerViewLightingData* per_view,
+                                            const VqGBuffer* gbuffer, const VqEnvironmentMaps* env, const VqImage* outs, int n_outs,
+                                            int dst_row_offset, int row_begin, int row_end, const VqPeerSignal* signal, void* stream);
 
 /* The forward pass samples the IBL cubemaps from bordered copies (each face carries a 1-texel border of its
  * neighbours, so seamless bilinear taps never leave the face). vq_environment_prepare builds those copies once and
@@ -195,6 +212,14 @@ VQ_API int vq_specular_prefilter(VqContext* ctx, VqPyramid hdri, VqCubemap out,
  * provides the cross-rank barrier after the kernel(s). */
 VQ_API int vq_specular_prefilter_multi(VqContext* ctx, VqPyramid hdri, const VqCubemap* outs, int n_outs,
                                        int num_samples, int row_begin, int row_end, void* stream);
+
+
+/* K3 as ONE persistent launch over several row ranges (n_ranges pairs [begin,end), increasing and disjoint) of the
+ * flattened (mip, face, row) space, stored into n_outs (<= 8) cubemaps, with the optional rendezvous above (NULL: none).
+ * This is what one rank of the strong-scaled prefilter runs per step: its row block of every mip, the replicated tail
+ * mips, the fused gather over NVLink and the cross-rank barrier, in one kernel. */
+VQ_API int vq_specular_prefilter_ranges(VqContext* ctx, VqPyramid hdri, const VqCubemap* outs, int n_outs, int num_samples,
+                                        const int* row_ranges, int n_ranges, const VqPeerSignal* signal, void* stream);
 
 /* ------------------------------------------------------------------------------------------
  * K4  BRDF integration LUT (split-sum scale,bias).  Replaces ComputeBRDFIntegrationLUT

@@ -191,6 +191,37 @@ void orc_specular_prefilter_texels(const float* pyramid, int w, int h, int level
     });
 }
 
+// Conditioning probe for K3 (test infrastructure): how much does the ORACLE's own result move when the texel's (unit) look
+// direction is tilted by a few ulps (+- eps ADDED to each component: an absolute tilt of eps radians, also at the poles where a
+// relative change of the small components would vanish)? out[k] = max over the six tilts and the colour channels
+// of |result' - result|. Near the poles of the equirect map (u = atan2(z,x) is singular there) a 1e-7 change of a sample
+// direction moves the sample by whole texels, so two correct fp32 implementations cannot agree to 1e-4 on an HDRI that
+// carries per-texel detail in its pole rows; the full-size parity test widens its bound by this measured sensitivity.
+void orc_specular_prefilter_sensitivity(const float* pyramid, int w, int h, int levels, int res, int mips, int num_samples,
+                                        const int64_t* texels, int n, float rel_eps, float* out, int threads) {
+    const Pyramid p{pyramid, w, h, levels};
+    par_rows(n, threads, [&](int k) {
+        int64_t t = texels[k]; int mip = 0;
+        for (; mip < mips; ++mip) { const int64_t sz = 6ll * (res >> mip) * (res >> mip); if (t < sz) break; t -= sz; }
+        if (mip >= mips) { out[k] = 0.0f; return; }
+        const int nn = res >> mip, face = (int)(t / ((int64_t)nn * nn)), py = (int)((t % ((int64_t)nn * nn)) / nn), px = (int)(t % nn);
+        const float roughness = (float)mip / (float)(mips - 1);
+        const float3 d = normalize(CubeTexelDirection(face, px, py, nn));
+        const float2 dim = make2((float)w, (float)h);
+        const float4 base = SpecularIrradiance_PSMain(p, d, roughness, dim, (uint32_t)num_samples);
+        float s = 0.0f;
+        for (int c = 0; c < 3; ++c)
+            for (int sgn = -1; sgn <= 1; sgn += 2) {
+                float3 e = d;
+                const float f = (float)sgn * rel_eps;
+                if (c == 0) e.x += f; else if (c == 1) e.y += f; else e.z += f;
+                const float4 r = SpecularIrradiance_PSMain(p, e, roughness, dim, (uint32_t)num_samples);
+                s = std::fmax(s, std::fmax(std::fabs(r.x - base.x), std::fmax(std::fabs(r.y - base.y), std::fabs(r.z - base.z))));
+            }
+        out[k] = s;
+    });
+}
+
 // ---- K4 ---------------------------------------------------------------------------------------
 void orc_brdf_integration_lut(float* out_rg, int w, int h, int samples, int row_begin, int row_end, int threads) {
     par_rows(row_end - row_begin, threads, [&](int r) {

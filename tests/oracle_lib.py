@@ -116,6 +116,16 @@ def specular_prefilter_texels(pyr, w, h, levels, res, mips, texels, num_samples=
     return out
 
 
+def specular_prefilter_sensitivity(pyr, w, h, levels, res, mips, texels, num_samples=512, rel_eps=2.0 ** -21, threads=None) -> np.ndarray:
+    """per texel: how far the oracle's own K3 result moves under a few-ulp (rel_eps radians) tilt of the look direction -> (n,)"""
+    t = np.ascontiguousarray(texels, dtype=np.int64)
+    out = np.zeros((t.size,), np.float32)
+    lib().orc_specular_prefilter_sensitivity(_p(_f(pyr)), w, h, levels, res, mips, num_samples,
+                                             t.ctypes.data_as(C.POINTER(C.c_int64)), int(t.size), f32(rel_eps), _p(out),
+                                             threads or cpu_threads())
+    return out
+
+
 def brdf_integration_lut(w, h, samples=2048, row_begin=0, row_end=None, threads=None) -> np.ndarray:
     out = np.zeros((h, w, 2), np.float32)
     lib().orc_brdf_integration_lut(_p(out), w, h, samples, row_begin, h if row_end is None else row_end,

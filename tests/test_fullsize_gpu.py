@@ -118,23 +118,40 @@ def test_c5_specular_full_face_and_random_texels(ctx, vq, orc):
     got = host(cube)
     hp = host(pyr_t)
     assert np.isfinite(got).all() and (got[:, 3] == 1.0).all()
-    # one full face of one mip: mip 1 (256^2, roughness 1/8), face 3
-    m, f = 1, 3
-    nn = res >> m
-    a = vq.cubemap_offset(res, m, f)
-    face_ids = np.arange(a, a + nn * nn, dtype=np.int64)
-    ref = orc.specular_prefilter_texels(hp, hw, hh, levels, res, mips, face_ids)
-    print(assert_scaled("C5 specular mip1 face3 (256^2)", got[face_ids], ref))
+    def check(name, ids, max_frac_relaxed):
+        """|delta| <= 1e-4 * max(1,|ref|) + 2 * S, S = how far the ORACLE's own texel moves when its look direction is tilted by
+        4.8e-7 rad (2^-21: a few ulps; oracle_capi.cpp: orc_specular_prefilter_sensitivity). S is ~1e-6 except where an importance
+        sample lands within a texel of a POLE of the equirect map: there u = atan2(z, x) is singular and the WRAP-in-v filter blends in
+        the opposite pole's row, so the reference's own result steps by up to 2e-3 under a 1-ulp change of its input (measured:
+        profiles/r02_diag_fullsize.txt; real HDRIs are constant along their pole rows, the synthetic one carries +-5 % per-texel
+        noise there). Two correct fp32 evaluations cannot agree better than that; everywhere else the bound is the strict one, and
+        the texels that get any noticeable relaxation (S > 2e-5) must stay a small minority."""
+        ref = orc.specular_prefilter_texels(hp, hw, hh, levels, res, mips, ids)
+        sens = orc.specular_prefilter_sensitivity(hp, hw, hh, levels, res, mips, ids)
+        g = got[ids]
+        assert np.isfinite(g).all()
+        d = np.abs(g.astype(np.float64) - ref).max(axis=1)
+        scale = np.maximum(1.0, np.abs(ref).max(axis=1))
+        bound = 1e-4 * scale + 2.0 * sens
+        relaxed = sens > 2e-5
+        r = report(name, g, ref)
+        r.update(max_sensitivity=float(sens.max()), frac_relaxed=float(relaxed.mean()),
+                 max_scaled_where_strict=float((d / scale)[~relaxed].max()), frac_within_strict=float((d <= 1e-4 * scale).mean()))
+        print(r)
+        assert (d <= bound).all(), f"{name}: {int((d > bound).sum())} texels outside the bound, worst {float((d - bound).max()):.3e} ({r})"
+        assert relaxed.mean() <= max_frac_relaxed, f"{name}: the sensitivity relaxation must stay an exception ({r})"
+        assert r["frac_within_strict"] >= 0.995, r
+
+    # one full face of one mip: mip 1 (256^2, roughness 1/8); face 3 (-Y) holds a pole, face 0 does not
+    for m, f in ((1, 3), (1, 0)):
+        nn = res >> m
+        a = vq.cubemap_offset(res, m, f)
+        check(f"C5 specular mip{m} face{f} ({nn}^2)", np.arange(a, a + nn * nn, dtype=np.int64), 0.02 if f == 3 else 0.0005)
     # 1 % of all texels, uniformly at random over the packed cube (so mostly mips 0-2, like the work itself)
     rng = np.random.default_rng(0x5EED0005)
-    ids = np.sort(rng.choice(n, size=n // 100, replace=False).astype(np.int64))
-    ref = orc.specular_prefilter_texels(hp, hw, hh, levels, res, mips, ids)
-    print(assert_scaled("C5 specular 1% random texels", got[ids], ref))
+    check("C5 specular 1% random texels", np.sort(rng.choice(n, size=n // 100, replace=False).astype(np.int64)), 0.01)
     # and every texel of the small mips (3..8), where one texel integrates a wide lobe
-    a3 = vq.cubemap_offset(res, 3, 0)
-    tail = np.arange(a3, n, dtype=np.int64)
-    ref = orc.specular_prefilter_texels(hp, hw, hh, levels, res, mips, tail)
-    print(assert_scaled("C5 specular mips 3..8 complete", got[tail], ref))
+    check("C5 specular mips 3..8 complete", np.arange(vq.cubemap_offset(res, 3, 0), n, dtype=np.int64), 0.02)
 
 
 def test_c5_forward_8k_row_tiles(ctx, vq, orc, envk):

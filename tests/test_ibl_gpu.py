@@ -139,6 +139,42 @@ def test_specular_multi_destination_store(ctx, vq, orc):
         ctx.specular_prefilter_multi(p, [vq.cubemap_of(outs[0], res, mips), vq.cubemap_of(outs[1][: vq.cubemap_texel_count(8, 3)], 8, 3)], 128)
 
 
+def test_specular_ranges_one_launch(ctx, vq, orc):
+    """vq_specular_prefilter_ranges: several row ranges (a rank's blocks of every mip + the replicated tail, cut anywhere, mip 0
+    and ragged unit counts included) as ONE persistent launch into several destinations == the whole-cube call, bit for bit;
+    rows outside the ranges stay untouched; the launch count proves it is one kernel; bad range lists are refused."""
+    from vqengine_b200 import distributed as vd
+    w, h, res, mips = 128, 64, 32, 6
+    _, levels, d, p = _pyr(ctx, vq, orc, w, h)
+    n = vq.cubemap_texel_count(res, mips)
+    whole = torch.zeros((n, 4), device="cuda")
+    ctx.specular_prefilter(p, vq.cubemap_of(whole, res, mips), 128)
+    ref = host(whole)
+    plan = vd.InterleavedSpecularPlan(res, mips, 4)
+    for rank in range(4):
+        outs = [torch.full((n, 4), -7.0, device="cuda") for _ in range(3)]
+        ranges = plan.row_ranges(rank)
+        before = vq.launch_count()
+        ctx.specular_prefilter_ranges(p, [vq.cubemap_of(o, res, mips) for o in outs], ranges, 128)
+        assert vq.launch_count() - before == 1
+        written = np.zeros(n, dtype=bool)
+        for a, b in ranges:
+            written[vd.specular_row_to_texel(res, mips, a):vd.specular_row_to_texel(res, mips, b)] = True
+        for o in outs:
+            ho = host(o)
+            assert np.array_equal(ho[written], ref[written]) and (ho[~written] == -7.0).all()
+    # odd cuts through mip 0 and the middle of faces, single destination
+    parts = torch.zeros((n, 4), device="cuda")
+    total = vq.cubemap_row_count(res, mips)
+    ctx.specular_prefilter_ranges(p, [vq.cubemap_of(parts, res, mips)], [(0, 5), (5, 37), (40, 191), (191, 300), (300, total)], 128)
+    hp = host(parts)
+    a, b = vd.specular_row_to_texel(res, mips, 37), vd.specular_row_to_texel(res, mips, 40)
+    assert np.array_equal(hp[:a], ref[:a]) and np.array_equal(hp[b:], ref[b:]) and (hp[a:b] == 0).all()
+    for bad in ([(5, 3)], [(10, 20), (15, 30)], [(0, total + 1)]):
+        with pytest.raises(vq.VqError):
+            ctx.specular_prefilter_ranges(p, [vq.cubemap_of(parts, res, mips)], bad, 128)
+
+
 @pytest.mark.parametrize("w,h,samples", [(64, 64, 2048), (33, 17, 256)])
 def test_brdf_lut(ctx, vq, orc, w, h, samples):
     out = torch.zeros((h, w, 2), dtype=torch.float32, device="cuda")

@@ -17,153 +17,8 @@ import os
 _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.environ.get("VQCUDA_LIB") or os.path.join(_HERE, "libvqcuda.so")   # override only for A/B kernel experiments
 
-VQ_OK = 0
-VQ_ERR_INVALID_ARG = -1
-VQ_ERR_CUDA = -2
-VQ_ERR_UNSUPPORTED = -3
-VQ_ERR_NO_DEVICE = -4
-VQ_ERR_OUT_OF_MEMORY = -5
-
-VQ_ADDRESS_WRAP, VQ_ADDRESS_CLAMP = 0, 1
-COLOR_SPACE_REC_709, COLOR_SPACE_REC_2020 = 0, 1
-DISPLAY_CURVE_SRGB, DISPLAY_CURVE_ST2084, DISPLAY_CURVE_LINEAR = 0, 1, 2
-
-f32 = C.c_float
-i32 = C.c_int32
-u32 = C.c_uint32
-
-
-# ---- include/vq_shader_data.h ---------------------------------------------------------------
-class Float2(C.Structure):
-    _fields_ = [("x", f32), ("y", f32)]
-
-
-class Float3(C.Structure):
-    _fields_ = [("x", f32), ("y", f32), ("z", f32)]
-
-
-class Float4(C.Structure):
-    _fields_ = [("x", f32), ("y", f32), ("z", f32), ("w", f32)]
-
-
-class Matrix(C.Structure):
-    _fields_ = [("m", f32 * 16)]
-
-
-class PointLight(C.Structure):
-    _fields_ = [("position", Float3), ("range", f32), ("color", Float3), ("brightness", f32),
-                ("attenuation", Float3), ("depthBias", f32)]
-
-
-class SpotLight(C.Structure):
-    _fields_ = [("position", Float3), ("outerConeAngle", f32), ("color", Float3), ("brightness", f32),
-                ("spotDir", Float3), ("depthBias", f32), ("innerConeAngle", f32), ("range", f32),
-                ("dummy1", f32), ("dummy2", f32)]
-
-
-class DirectionalLight(C.Structure):
-    _fields_ = [("lightDirection", Float3), ("brightness", f32), ("color", Float3), ("depthBias", f32),
-                ("shadowing", i32), ("enabled", i32)]
-
-
-class SceneLighting(C.Structure):
-    _fields_ = [("numPointLights", i32), ("numSpotLights", i32), ("numPointCasters", i32), ("numSpotCasters", i32),
-                ("directional", DirectionalLight), ("_pad_matrix_align", u32 * 2),
-                ("shadowViewDirectional", Matrix),
-                ("point_lights", PointLight * 100), ("point_casters", PointLight * 5),
-                ("spot_lights", SpotLight * 20), ("spot_casters", SpotLight * 5),
-                ("shadowViews", Matrix * 5)]
-
-
-class PerFrameData(C.Structure):
-    _fields_ = [("Lights", SceneLighting),
-                ("f2PointLightShadowMapDimensions", Float2), ("f2SpotLightShadowMapDimensions", Float2),
-                ("f2DirectionalLightShadowMapDimensions", Float2),
-                ("fAmbientLightingFactor", f32), ("fHDRIOffsetInRadians", f32)]
-
-
-class PerViewLightingData(C.Structure):
-    _fields_ = [("matView", Matrix), ("matViewToWorld", Matrix), ("matProjInverse", Matrix),
-                ("WorldFrustumPlanes", Float4 * 6), ("CameraPosition", Float3), ("MaxEnvMapLODLevels", f32),
-                ("ScreenDimensions", Float2), ("EnvironmentMapDiffuseOnlyIllumination", i32), ("pad1", f32)]
-
-
-class TonemapperParams(C.Structure):
-    _fields_ = [("ContentColorSpace", i32), ("OutputDisplayCurve", i32),
-                ("DisplayReferenceBrightnessLevel", f32), ("ToggleGammaCorrection", i32), ("UIHDRBrightness", f32)]
-
-
-class BlurParams(C.Structure):
-    _fields_ = [("iImageSizeX", i32), ("iImageSizeY", i32)]
-
-
-class SpdConstants(C.Structure):
-    _fields_ = [("mips", u32), ("numWorkGroups", u32), ("workGroupOffset", u32 * 2)]
-
-
-class DiffuseIrradianceParams(C.Structure):
-    _fields_ = [("step", f32), ("n_phi", i32), ("n_theta", i32), ("src_mip", i32)]
-
-
-assert C.sizeof(PointLight) == 48 and C.sizeof(SpotLight) == 64 and C.sizeof(DirectionalLight) == 40
-assert C.sizeof(SceneLighting) == 7088 and C.sizeof(PerFrameData) == 7120 and C.sizeof(PerViewLightingData) == 320
-
-
-# ---- include/vqcuda.h -----------------------------------------------------------------------
-class Image(C.Structure):
-    _fields_ = [("ptr", C.c_void_p), ("width", i32), ("height", i32), ("pitch_bytes", C.c_size_t)]
-
-
-class Cubemap(C.Structure):
-    _fields_ = [("ptr", C.c_void_p), ("res", i32), ("mips", i32)]
-
-
-class Pyramid(C.Structure):
-    _fields_ = [("ptr", C.c_void_p), ("width", i32), ("height", i32), ("levels", i32)]
-
-
-class GBuffer(C.Structure):
-    _fields_ = [("position_ao", Image), ("normal_roughness", Image), ("albedo_metalness", Image), ("emissive", Image)]
-
-
-class EnvironmentMaps(C.Structure):
-    _fields_ = [("irradiance_diffuse", Cubemap), ("irradiance_specular", Cubemap), ("brdf_lut", Image)]
-
-
-class ShadowMaps(C.Structure):            # include/vqcuda.h VqShadowMaps
-    _fields_ = [("point_cubes", C.c_void_p), ("point_res", C.c_int32),
-                ("spot_maps", C.c_void_p), ("spot_width", C.c_int32), ("spot_height", C.c_int32),
-                ("directional_map", C.c_void_p), ("directional_width", C.c_int32), ("directional_height", C.c_int32)]
-
-
-class MaterialData(C.Structure):          # include/vq_shader_data.h VqMaterialData (LightingConstantBufferData.h:126-143)
-    _fields_ = [("diffuse", Float3), ("alpha", f32), ("emissiveColor", Float3), ("emissiveIntensity", f32),
-                ("specular", Float3), ("normalMapMipBias", f32), ("uvScaleOffset", Float4),
-                ("roughness", f32), ("metalness", f32), ("displacement", f32), ("textureConfig", f32)]
-
-
-assert C.sizeof(MaterialData) == 80
-
-TEXCFG_DIFFUSE, TEXCFG_NORMAL, TEXCFG_AO, TEXCFG_ALPHA_MASK, TEXCFG_ROUGHNESS, TEXCFG_METALLIC, TEXCFG_HEIGHT, \
-    TEXCFG_EMISSIVE, TEXCFG_ORM = (1 << b for b in range(9))
-MATERIAL_TEXTURE_SLOTS = ("diffuse", "normals", "emissive", "metalness", "roughness", "occl_rough_metal", "local_ao")
-
-
-class Texture2D(C.Structure):
-    _fields_ = [("ptr", C.c_void_p), ("width", i32), ("height", i32), ("levels", i32)]
-
-
-class MaterialTextures(C.Structure):
-    _fields_ = [(k, Texture2D) for k in MATERIAL_TEXTURE_SLOTS]
-
-
-class HdrInfo(C.Structure):
-    _fields_ = [("width", C.c_int32), ("height", C.c_int32), ("data_offset", C.c_uint64), ("flat", C.c_int32),
-                ("reserved", C.c_int32)]
-
-
-class SurfaceInputs(C.Structure):
-    _fields_ = [("position_u", Image), ("normal_v", Image), ("tangent_m", Image), ("ssao", Image)]
+from .shader_data import *          # noqa: F401,F403  (struct mirror + constants: plain data, no library)
+from .shader_data import f32, i32, u32
 
 
 # every symbol include/vqcuda.h declares (tests/test_abi.py checks the library exports all of them)
@@ -177,7 +32,7 @@ ABI_SYMBOLS = [
     "vq_environment_invalidate", "vq_forward_lighting_multi",
     "vq_texture_build_mips", "vq_material_table_create", "vq_material_table_destroy", "vq_gbuffer_from_materials",
     "vq_hdr_parse", "vq_hdr_decode", "vq_hdr_load_host", "vq_hdr_encode_rgbe", "vq_hdr_pack_file", "vq_hdr_save_host",
-    "vq_skydome", "vq_apply_reflections", "vq_specular_prefilter_multi", "vq_image_resize", "vq_resize_axis_table",
+    "vq_skydome", "vq_apply_reflections", "vq_specular_prefilter_multi", "vq_specular_prefilter_ranges", "vq_forward_lighting_multi_signal", "vq_image_resize", "vq_resize_axis_table",
     "vq_forward_lighting_shadowed", "vq_depth_pyramid_level_count", "vq_depth_pyramid_texel_count", "vq_depth_min_pyramid",
 ]
 
@@ -206,6 +61,8 @@ def _load() -> C.CDLL:
                                         Image, C.c_int, C.c_int, vp]
     lib.vq_forward_lighting_multi.argtypes = [vp, P(PerFrameData), P(PerViewLightingData), P(GBuffer), P(EnvironmentMaps),
                                               P(Image), C.c_int, C.c_int, C.c_int, C.c_int, vp]
+    lib.vq_forward_lighting_multi_signal.argtypes = [vp, P(PerFrameData), P(PerViewLightingData), P(GBuffer), P(EnvironmentMaps),
+                                                     P(Image), C.c_int, C.c_int, C.c_int, C.c_int, P(PeerSignal), vp]
     lib.vq_forward_lighting_host.argtypes = [vp, P(PerFrameData), P(PerViewLightingData), P(GBuffer),
                                              P(EnvironmentMaps), Image]
     lib.vq_environment_prepare.argtypes = [vp, P(EnvironmentMaps), vp]
@@ -214,6 +71,7 @@ def _load() -> C.CDLL:
     lib.vq_diffuse_irradiance.argtypes = [vp, P(DiffuseIrradianceParams), Pyramid, Cubemap, C.c_int, C.c_int, vp]
     lib.vq_specular_prefilter.argtypes = [vp, Pyramid, Cubemap, C.c_int, C.c_int, C.c_int, vp]
     lib.vq_specular_prefilter_multi.argtypes = [vp, Pyramid, P(Cubemap), C.c_int, C.c_int, C.c_int, C.c_int, vp]
+    lib.vq_specular_prefilter_ranges.argtypes = [vp, Pyramid, P(Cubemap), C.c_int, C.c_int, P(C.c_int), C.c_int, P(PeerSignal), vp]
     lib.vq_brdf_integration_lut.argtypes = [vp, Image, C.c_int, C.c_int, C.c_int, vp]
     lib.vq_gaussian_blur_x.argtypes = [vp, P(BlurParams), Image, Image, vp]
     lib.vq_gaussian_blur_y.argtypes = [vp, P(BlurParams), Image, Image, vp]
@@ -436,15 +294,21 @@ class Context:
                                        row_begin, o.height if row_end is None else row_end, _stream_ptr(stream)))
 
     def forward_lighting_multi(self, per_frame, per_view, gbuffer: GBuffer, env: EnvironmentMaps, out_images, dst_row_offset,
-                               row_begin=0, row_end=None, stream=None):
-        """out_images: list of Image descriptors (local frame first, then the peers' mapped frames)"""
+                               row_begin=0, row_end=None, stream=None, signal: "PeerSignal" = None):
+        """out_images: list of Image descriptors (local frame first, then the peers' mapped frames); signal: the in-kernel
+        cross-rank rendezvous (vq_forward_lighting_multi_signal)"""
         arr = (Image * len(out_images))(*out_images)
         h = gbuffer.position_ao.height
-        _check(lib.vq_forward_lighting_multi(self._h, C.byref(per_frame), C.byref(per_view), C.byref(gbuffer), C.byref(env), arr,
-                                             len(out_images), dst_row_offset, row_begin, h if row_end is None else row_end,
-                                             _stream_ptr(stream)))
+        if signal is None:
+            _check(lib.vq_forward_lighting_multi(self._h, C.byref(per_frame), C.byref(per_view), C.byref(gbuffer), C.byref(env), arr,
+                                                 len(out_images), dst_row_offset, row_begin, h if row_end is None else row_end,
+                                                 _stream_ptr(stream)))
+        else:
+            _check(lib.vq_forward_lighting_multi_signal(self._h, C.byref(per_frame), C.byref(per_view), C.byref(gbuffer), C.byref(env),
+                                                        arr, len(out_images), dst_row_offset, row_begin,
+                                                        h if row_end is None else row_end, C.byref(signal), _stream_ptr(stream)))
 
-    # SURVEY 8(f).4: the pass with shadow maps bound, and the MIN depth pyramid (compiled, not yet run on a GPU: DESIGN.md 8)
+    # SURVEY 8(f).4: the pass with shadow maps bound, and the MIN depth pyramid
     def forward_lighting_shadowed(self, per_frame, per_view, gbuffer: GBuffer, env: EnvironmentMaps, out, point_cubes=None,
                                   spot_maps=None, directional_map=None, row_begin=0, row_end=None, stream=None):
         """point_cubes [casters,6,R,R], spot_maps [casters,H,W], directional_map [H,W]: contiguous float32 CUDA tensors or None"""
@@ -578,6 +442,14 @@ class Context:
         _check(lib.vq_specular_prefilter_multi(self._h, pyr, arr, len(cubes), num_samples, row_begin,
                                                cubemap_row_count(cubes[0].res, cubes[0].mips) if row_end is None else row_end,
                                                _stream_ptr(stream)))
+
+    def specular_prefilter_ranges(self, pyr: Pyramid, cubes, row_ranges, num_samples=512, signal: "PeerSignal" = None, stream=None):
+        """ONE persistent launch over several [begin,end) row ranges into all `cubes`, with the optional in-kernel rendezvous"""
+        arr = (Cubemap * len(cubes))(*cubes)
+        flat = [int(v) for ab in row_ranges for v in ab]
+        rr = (C.c_int * len(flat))(*flat)
+        _check(lib.vq_specular_prefilter_ranges(self._h, pyr, arr, len(cubes), num_samples, rr, len(row_ranges),
+                                                C.byref(signal) if signal is not None else None, _stream_ptr(stream)))
 
     def brdf_integration_lut(self, out, num_samples=2048, row_begin=0, row_end=None, stream=None):
         o = image_of(out, 2)

@@ -27,6 +27,15 @@ int vq_check_launch(const char* what) {
     return VQ_OK;
 }
 
+int vq_fill_peer_sync(const VqPeerSignal* sig, PeerSync* out) {
+    memset(out, 0, sizeof(*out));
+    if (!sig || sig->n_ranks <= 1) return VQ_OK;
+    VQ_REQUIRE(sig->n_ranks <= 8 && sig->my_index >= 0 && sig->my_index < sig->n_ranks, "bad peer signal descriptor");
+    for (int k = 0; k < sig->n_ranks; ++k) { VQ_REQUIRE(sig->flags[k], "null flag array in the peer signal"); out->flags[k] = sig->flags[k]; }
+    out->n = sig->n_ranks; out->myIndex = sig->my_index; out->epoch = sig->epoch;
+    return VQ_OK;
+}
+
 extern "C" {
 
 const char* vq_last_error(void) { return t_err; }
@@ -57,8 +66,8 @@ int vq_ctx_create(int device, VqContext** out_ctx) {
     c->device = device;
     c->sm_count = prop.multiProcessorCount;
     c->l2_bytes = prop.l2CacheSize;
-    if (cudaMalloc(&c->spd_counter, VQ_SPD_SLOTS * sizeof(uint32_t)) != cudaSuccess) { delete c; vq_set_error("cudaMalloc failed"); return VQ_ERR_OUT_OF_MEMORY; }
-    cudaMemset(c->spd_counter, 0, VQ_SPD_SLOTS * sizeof(uint32_t));
+    if (cudaMalloc(&c->spd_counter, 2 * VQ_SPD_SLOTS * sizeof(uint32_t)) != cudaSuccess) { delete c; vq_set_error("cudaMalloc failed"); return VQ_ERR_OUT_OF_MEMORY; }
+    cudaMemset(c->spd_counter, 0, 2 * VQ_SPD_SLOTS * sizeof(uint32_t));
     c->spd_next = new std::atomic<uint32_t>(0u);
     c->mu = new std::recursive_mutex();
     *out_ctx = c;

@@ -2,8 +2,9 @@
 //
 // Replaces VQRenderer::RenderSceneColor (SceneRendering.cpp:1619-1851) + PSMain
 // (ForwardLighting.hlsl:285-380) over a G-buffer of three float4 planes (+ optional emissive):
-//   64 B/pixel of HBM traffic: the three planes arrive as 2 KB row segments through a TMA (cp.async.bulk) /
-//   mbarrier ring in shared memory, the result leaves as one STG.128 per pixel; the light array is staged once per
+//   64 B/pixel of HBM traffic: the three planes arrive as 4 KB row segments through a TMA (cp.async.bulk) /
+//   mbarrier ring in shared memory, the result leaves as one STG.128 per pixel; one thread shades TWO pixels with packed
+//   fp32x2 arithmetic (FFMA2/FMUL2/FADD2: half the issue slots of the light loop); the light array is staged once per
 //   CTA into shared memory; the IBL cubemaps and the BRDF LUT are gathered from L2-resident sampling copies
 //   (pair / footprint records, 102 MB at the reference sizes) with five 256-bit loads per pixel, because the
 //   L1 data pipe — one wavefront per distinct line of a divergent gather — is what bounds this kernel.
@@ -49,6 +50,10 @@ struct FwdParams {
     int nOut, dstRowOffset;            // every shaded pixel goes to row dstRowOffset+y of every destination
     CubeV diff, spec;
     LutV lut;
+    PeerSync sync;                     // MULTI: optional end-of-pass rendezvous run by the last CTA (n == 0: none)
+    uint32_t* ticket;                  // MULTI: retired-CTA count (zero between launches)
+    float diffHalfN;                   // res/2 of the diffuse cube
+    uint32_t diffMaxRec, specMaxRec;   // last record a footprint may start at (address clamp for non-finite directions)
     int rowBegin, rows, width;
 };
 
@@ -161,16 +166,59 @@ __global__ void __launch_bounds__(256) lut_footprint_kernel(const float2* __rest
 }
 
 // ---------------------------------------------------------------------------------------------
-// per-pixel shading state with everything that does not depend on the light hoisted
+// packed fp32x2 arithmetic (FADD2 / FMUL2 / FFMA2, new on sm_100)
 // ---------------------------------------------------------------------------------------------
-// Only what the light loop reads stays live across it (register diet: 64-80 registers decide the occupancy).
-struct Px {
-    float3 P, Nn, V;              // position, normalize(Ns), normalize(cam - P)
-    float nsLen;                  // |Ns|: dot(Ns,Wi) = nsLen * dot(Nn,Wi)  (Lighting.hlsl:316 uses the raw s.N)
-    float nv, NdotV, gV;          // dot(Nn,V), saturate, Smith-G1 of V (BRDF.hlsl:82-97)
-    float a2, a2m1, k, omk;
-    uint32_t nrmTexel;            // shared-memory address of the raw normal texel: re-read by the exact slow path only
+// K1 is bound by instruction issue (profiles/r01_forward_g_summary.txt: 904 warp-instructions per 32 pixels, more than half of
+// them FADD/FMUL/FFMA), so one thread shades TWO pixels and every quantity of the light loop is a pair {pixel A, pixel B} in
+// an aligned 64-bit register pair: one packed instruction does the work of two at one issue slot. Lane .x of every f2
+// is pixel A (column x0 + tid), lane .y pixel B (column x0 + 128 + tid). MUFU, compares, selects and min/max have no packed
+// form and stay per lane (profiles/r02_forward_*: 80 -> 42 issue slots per pixel and light).
+}  // namespace
+namespace vq {
+struct f2 { float2 v; };
+__device__ __forceinline__ f2 mk(float a, float b) { f2 r; r.v = make_float2(a, b); return r; }
+__device__ __forceinline__ f2 bc(float a) { return mk(a, a); }
+__device__ __forceinline__ f2 operator+(f2 a, f2 b) { f2 r; r.v = __fadd2_rn(a.v, b.v); return r; }
+__device__ __forceinline__ f2 operator*(f2 a, f2 b) { f2 r; r.v = __fmul2_rn(a.v, b.v); return r; }
+__device__ __forceinline__ f2 operator-(f2 a, f2 b) { f2 r; r.v = __fadd2_rn(a.v, make_float2(-b.v.x, -b.v.y)); return r; }
+__device__ __forceinline__ f2 fma2(f2 a, f2 b, f2 c) { f2 r; r.v = __ffma2_rn(a.v, b.v, c.v); return r; }
+// The intrinsics above may be contracted into FFMA2 by the compiler (wanted). Where the oracle's operation order decides a
+// DISCONTINUITY (|L-P|^2 against the light's range) or feeds a cancellation (a^2 - 1), every operation must round on its own.
+// ptxas contracts f32x2 multiply/add pairs even when both carry an explicit .rn (checked in SASS; it also sees through
+// fma(a,b,-0)), so the unfused forms keep the PRODUCTS packed (a lone FMUL2 is correctly rounded) and do the additions with
+// scalar __fadd_rn, which is never contracted.
+__device__ __forceinline__ f2 mul_rn2(f2 a, f2 b) {
+    f2 r;
+    asm("{\n\t.reg .b64 ta, tb, tc;\n\tmov.b64 ta, {%2,%3};\n\tmov.b64 tb, {%4,%5};\n\tmul.rn.f32x2 tc, ta, tb;\n\tmov.b64 {%0,%1}, tc;\n\t}"
+        : "=f"(r.v.x), "=f"(r.v.y) : "f"(a.v.x), "f"(a.v.y), "f"(b.v.x), "f"(b.v.y));
+    return r;
+}
+__device__ __forceinline__ f2 add_rn2(f2 a, f2 b) { return mk(__fadd_rn(a.v.x, b.v.x), __fadd_rn(a.v.y, b.v.y)); }
+__device__ __forceinline__ f2 rsq2(f2 a) { return mk(rsqrt_fast(a.v.x), rsqrt_fast(a.v.y)); }
+__device__ __forceinline__ f2 rcp2(f2 a) { return mk(rcp_fast(a.v.x), rcp_fast(a.v.y)); }
+__device__ __forceinline__ f2 sat2(f2 a) { return mk(saturate(a.v.x), saturate(a.v.y)); }
+__device__ __forceinline__ f2 mulsat2(f2 a, f2 b) { return mk(saturate(a.v.x * b.v.x), saturate(a.v.y * b.v.y)); }   // FMUL.SAT x2
+__device__ __forceinline__ f2 max2(f2 a, float m) { return mk(fmaxf(a.v.x, m), fmaxf(a.v.y, m)); }
+__device__ __forceinline__ f2 dot3(f2 ax, f2 ay, f2 az, f2 bx, f2 by, f2 bz) { return fma2(az, bz, fma2(ay, by, ax * bx)); }
+
+}  // namespace vq
+namespace {
+
+// ---------------------------------------------------------------------------------------------
+// per-pixel-pair shading state with everything that does not depend on the light hoisted
+// ---------------------------------------------------------------------------------------------
+struct Px2 {
+    float3 PA, PB;                // positions of the two pixels (scalar: every use is a first-touch subtraction)
+    f2 Nx, Ny, Nz;                // normalize(Ns)                                   (BRDF.hlsl:167)
+    f2 Vx, Vy, Vz;                // normalize(cam - P)                              (ForwardLighting.hlsl:285)
+    f2 nsLen;                     // |Ns|: dot(Ns,Wi) = nsLen * dot(Nn,Wi)           (Lighting.hlsl:316 uses the raw s.N)
+    f2 nv, nv4;                   // dot(Nn,V), 4*saturate(dot(Nn,V))
+    f2 a2m1;                      // roughness^4 - 1 (unfused, feeds the exact t)
+    f2 a2gV, gV;                  // a2 * G1(V), G1(V) = Smith-Schlick-GGX of the view vector (BRDF.hlsl:82-97)
+    f2 k4, omk;                   // k + 0.0001, 1 - k with k = (roughness+1)^2 / 8
+    uint32_t texA, texB;          // shared-memory addresses of the two pixels' position texels (planes follow at FWD_PLANE)
 };
+struct Acc2 { f2 ax, ay, az, bx, by, bz, cx, cy, cz; };   // sum over lights of w*col * {(1-fc), fc*spec, spec}
 
 // ---- exact re-evaluation of N.H -------------------------------------------------------------------
 // GGX's t = nh2*(a2-1)+1 cancels catastrophically near a highlight on a smooth surface (t ~ a2 ~ 1e-5),
@@ -242,52 +290,123 @@ __device__ __noinline__ float exact_ndoth(float3 cam, float3 P, uint32_t nrmTexe
     return saturate(dot_u(N, H));
 }
 
-struct Acc { float3 a, b, c; };   // sum over lights of w*col * {(1-fc), fc*spec, spec}
-
-// One light: accumulates BRDF(s, Wi, V) * radiance * NdotL (BRDF.hlsl:163-194, Lighting.hlsl:308-345) in the
-// factored form  r = K1*(1-fc) + omF0*(fc*spec) + F0*spec  with  F = F0 + (1-F0)*fc.
-//   Lv, d2 : un-normalised light vector and its squared length (Wi = Lv/sqrt(d2)),  invD = 1/sqrt(d2)
-//   scale  : attenuation * brightness * spot intensity (0 when the light is out of range);  col : light colour
-// H = normalize(V+Wi) is never formed: |V+Wi|^2 = 2+2c with c = V.Wi, so N.H = (N.V+N.Wi)*rh and
-// H.V = (1+c)*rh with rh = rsqrt(2+2c).
-// The body is branch-free (a light that does not contribute gets weight 0) so that two lights can be interleaved
-// by the scheduler; only the rare exact-N.H slow path branches.
-__device__ __forceinline__ void shade_light(const Px& s, Acc& acc, float3 cam, float3 Lv, float d2, float invD,
-                                            float scale, float3 col) {
-    const float nl = dot(s.Nn, Lv) * invD;
-    const float c = dot(s.V, Lv) * invD;
-    const float sq = fmaxf(fmaf(2.0f, c, 2.0f), 1e-12f);
-    const float rh = rsqrt_fast(sq);
-    float NdotH = saturate((s.nv + nl) * rh);
-    const float HV = fmaxf(0.0f, (1.0f + c) * rh);
-    const float fc = pow5(1.0f - HV);                  // Fresnel_Schlick (BRDF.hlsl:132-136)
-    float t = fmaf(NdotH * NdotH, s.a2m1, 1.0f);       // NormalDistributionGGX (BRDF.hlsl:65-79)
-    const float NL = fminf(fmaxf(nl, 0.0f), 1.0f);     // saturate(N.L) == max(0,N.L) for unit vectors
-    const float w = saturate(s.nsLen * nl) * scale;    // NdotL of the raw s.N (Lighting.hlsl:316) * radiance scale
-    if (t < T_EXACT && w > 0.0f) {
-        NdotH = exact_ndoth(cam, s.P, s.nrmTexel, Lv, d2);
-        t = __fadd_rn(__fmul_rn(__fmul_rn(NdotH, NdotH), s.a2m1), 1.0f);
-    }
-    const float dDen = PI * (t * t);
-    const float gDen = fmaf(NL, s.omk, s.k) + 0.0001f; // Geometry_Smiths_SchlickGGX of L (BRDF.hlsl:82-97)
-    const float sDen = fmaxf(4.0f * s.NdotV * NL, 0.0001f);
-    const bool tiny = dDen < 0.000000000001f;          // `denom < EPSILON -> D = 1` (BRDF.hlsl:77)
-    const float num = (tiny ? 1.0f : s.a2) * s.gV * NL;
-    const float den = (tiny ? 1.0f : dDen) * gDen * sDen;
-    const float spec = num * rcp_fast(den);            // D*G/denom with ONE reciprocal (den >= 1e-20)
-    const float wa = (1.0f - fc) * w, wc = spec * w, wb = fc * wc;
-    acc.a.x = fmaf(wa, col.x, acc.a.x); acc.a.y = fmaf(wa, col.y, acc.a.y); acc.a.z = fmaf(wa, col.z, acc.a.z);
-    acc.b.x = fmaf(wb, col.x, acc.b.x); acc.b.y = fmaf(wb, col.y, acc.b.y); acc.b.z = fmaf(wb, col.z, acc.b.z);
-    acc.c.x = fmaf(wc, col.x, acc.c.x); acc.c.y = fmaf(wc, col.y, acc.c.y); acc.c.z = fmaf(wc, col.z, acc.c.z);
+// ---- exact re-evaluation of N.V ---------------------------------------------------------------------
+// `denom = max(4*NdotV*NdotL, 0.0001)` (BRDF.hlsl:186): once the clamp is active the specular term is PROPORTIONAL to NdotV
+// (the G1(V) factor no longer cancels) with a gain of 1e4, and NdotV ~ 0 comes out of a cancellation: a 2e-7 difference in
+// dot(N, Wo) is a 2e-3 difference in D*G*F/denom. Found by the full-frame parity test at 1920x1080 (4 pixels in 2 M, all with
+// |N.V| < 5e-5, profiles/r02_diag_fullsize.txt). Grazing pixels therefore recompute N.V with the oracle's operation sequence.
+constexpr float NV_EXACT = 1e-3f;
+__device__ __noinline__ float exact_nv(float3 cam, float3 P, uint32_t nrmTexel) {
+    float4 nr;
+    asm volatile("ld.shared.v4.f32 {%0,%1,%2,%3}, [%4];" : "=f"(nr.x), "=f"(nr.y), "=f"(nr.z), "=f"(nr.w) : "r"(nrmTexel));
+    const float3 Vv = f3(__fsub_rn(cam.x, P.x), __fsub_rn(cam.y, P.y), __fsub_rn(cam.z, P.z));
+    const float3 Wo = normalize_u(normalize_u(Vv));                 // ForwardLighting.hlsl:285, BRDF.hlsl:166
+    const float3 N = normalize_u(f3(nr.x, nr.y, nr.z));             // BRDF.hlsl:167
+    return dot_u(N, Wo);
 }
 
-// point light i (Lighting.hlsl:308-322): in range <=> d2 < d2Limit (== length(Lw-P) < l.range, exactly)
-__device__ __forceinline__ void shade_point(const Px& s, Acc& acc, float3 cam, const SPoint& l) {
-    const float3 Lv = l.pos - s.P;
-    const float d2 = dot_u(Lv, Lv);                    // |L-P|^2 exactly as the oracle's dot()
-    const float invD = rsqrt_fast(fmaxf(d2, 1e-30f));
-    const float scale = d2 < l.d2Limit ? (invD * invD) * l.brightness : 0.0f;   // AttenuationBRDF = 1/D^2
-    shade_light(s, acc, cam, Lv, d2, invD, scale, l.color);
+constexpr int FWD_THREADS = 128;
+constexpr int FWD_TILE = 2 * FWD_THREADS;          // pixels per tile: 256 consecutive pixels of one row (4 KB per G-buffer plane)
+constexpr uint32_t FWD_PLANE = FWD_TILE * 16u;     // bytes between the planes of one stage
+
+// One light for the pixel pair: accumulates BRDF(s, Wi, V) * radiance * NdotL (BRDF.hlsl:163-194, Lighting.hlsl:308-345) in the
+// factored form  r = K1*(1-fc) + omF0*(fc*spec) + F0*spec  with  F = F0 + (1-F0)*fc.
+//   L, d2 : un-normalised light vector and its squared length (Wi = L/sqrt(d2)),  invD = 1/sqrt(d2)
+//   scale : attenuation * brightness * spot intensity (0 when the light is out of range);  col : light colour
+// H = normalize(V+Wi) is never formed: |V+Wi|^2 = 2+2c with c = V.Wi, so N.H = (N.V+N.Wi)*rh and
+// H.V = (1+c)*rh with rh = rsqrt(2+2c).
+// The body is branch-free (a light that does not contribute gets weight 0); only the rare exact-N.H slow path branches.
+// TINY: the `denom < EPSILON -> D = 1` escape of NormalDistributionGGX (BRDF.hlsl:77) can only trigger when
+// PI*(1+min(a2-1,0))^2 < 1e-12, i.e. roughness < 0.024: the caller picks the instantiation per warp, so ordinary
+// materials never pay for the selects.
+template <bool TINY>
+__device__ __forceinline__ void shade_light2(const Px2& s, Acc2& acc, float3 cam, f2 Lx, f2 Ly, f2 Lz, f2 d2, f2 invD,
+                                             f2 scale, float3 col) {
+    const f2 nl = dot3(s.Nx, s.Ny, s.Nz, Lx, Ly, Lz) * invD;
+    const f2 c = dot3(s.Vx, s.Vy, s.Vz, Lx, Ly, Lz) * invD;
+    const f2 rh = rsq2(max2(fma2(bc(2.0f), c, bc(2.0f)), 1e-12f));
+    f2 NdotH = mulsat2(s.nv + nl, rh);
+    const f2 HV = mulsat2(bc(1.0f) + c, rh);              // (1+c)*rh = cos of the half angle: in [0,1] up to rounding
+    const f2 omh = bc(1.0f) - HV;
+    const f2 omh2 = omh * omh;
+    const f2 fc = omh2 * omh2 * omh;                      // Fresnel_Schlick (BRDF.hlsl:132-136)
+    f2 t = fma2(NdotH * NdotH, s.a2m1, bc(1.0f));         // NormalDistributionGGX (BRDF.hlsl:65-79)
+    const f2 NL = sat2(nl);                               // saturate(N.L) == max(0,N.L) for unit vectors
+    const f2 w = mulsat2(s.nsLen, nl) * scale;            // NdotL of the raw s.N (Lighting.hlsl:316) * radiance scale
+    if (fminf(t.v.x, t.v.y) < T_EXACT) {                  // < 1 % of pixel-light pairs
+        if (t.v.x < T_EXACT && w.v.x > 0.0f) {
+            const float nh = exact_ndoth(cam, s.PA, s.texA + FWD_PLANE, f3(Lx.v.x, Ly.v.x, Lz.v.x), d2.v.x);
+            t.v.x = __fadd_rn(__fmul_rn(__fmul_rn(nh, nh), s.a2m1.v.x), 1.0f);
+        }
+        if (t.v.y < T_EXACT && w.v.y > 0.0f) {
+            const float nh = exact_ndoth(cam, s.PB, s.texB + FWD_PLANE, f3(Lx.v.y, Ly.v.y, Lz.v.y), d2.v.y);
+            t.v.y = __fadd_rn(__fmul_rn(__fmul_rn(nh, nh), s.a2m1.v.y), 1.0f);
+        }
+    }
+    f2 dDen = bc(PI) * (t * t);
+    const f2 gDen = fma2(NL, s.omk, s.k4);                // Geometry_Smiths_SchlickGGX of L (BRDF.hlsl:82-97)
+    const f2 sDen = max2(s.nv4 * NL, 0.0001f);            // max(4*NdotV*NdotL, 0.0001)
+    f2 num;
+    if (TINY) {                                           // `denom < EPSILON -> D = 1` (BRDF.hlsl:77)
+        const bool ta = dDen.v.x < 0.000000000001f, tb = dDen.v.y < 0.000000000001f;
+        num = mk(ta ? s.gV.v.x : s.a2gV.v.x, tb ? s.gV.v.y : s.a2gV.v.y) * NL;
+        dDen = mk(ta ? 1.0f : dDen.v.x, tb ? 1.0f : dDen.v.y);
+    } else {
+        num = s.a2gV * NL;
+    }
+    const f2 spec = num * rcp2(dDen * gDen * sDen);       // D*G/denom with ONE reciprocal (den >= 1e-20)
+    const f2 wa = (bc(1.0f) - fc) * w, wc = spec * w, wb = fc * wc;
+    const f2 cr = bc(col.x), cg = bc(col.y), cb = bc(col.z);
+    acc.ax = fma2(wa, cr, acc.ax); acc.ay = fma2(wa, cg, acc.ay); acc.az = fma2(wa, cb, acc.az);
+    acc.bx = fma2(wb, cr, acc.bx); acc.by = fma2(wb, cg, acc.by); acc.bz = fma2(wb, cb, acc.bz);
+    acc.cx = fma2(wc, cr, acc.cx); acc.cy = fma2(wc, cg, acc.cy); acc.cz = fma2(wc, cb, acc.cz);
+}
+
+// un-normalised light vector of a positional light and its squared length, |L-P|^2 exactly as the oracle's dot():
+// (x*x + y*y) + z*z with every operation rounded
+struct LightVec2 { f2 x, y, z, d2, invD; };
+__device__ __forceinline__ LightVec2 light_vector2(const Px2& s, float3 pos) {
+    LightVec2 L;
+    // two scalar subtractions write straight into a register pair: cheaper than packing P once more per light
+    L.x = mk(pos.x - s.PA.x, pos.x - s.PB.x); L.y = mk(pos.y - s.PA.y, pos.y - s.PB.y); L.z = mk(pos.z - s.PA.z, pos.z - s.PB.z);
+    L.d2 = add_rn2(add_rn2(mul_rn2(L.x, L.x), mul_rn2(L.y, L.y)), mul_rn2(L.z, L.z));
+    L.invD = rsq2(L.d2 + bc(1e-30f));                     // == rsqrt(d2) for every d2 >= 1e-22; finite at d2 = 0
+    return L;
+}
+
+// every light of the frame for one pixel pair, in PSMain's order
+template <bool TINY>
+__device__ __forceinline__ void shade_all_lights(const Px2& s, Acc2& acc, float3 cam, const SPoint* __restrict__ sPoint, int numPoint,
+                                                 const SSpot* __restrict__ sSpot, int numSpot, const SDir* __restrict__ sDir, bool dirEnabled) {
+    // ---- point lights, then unshadowed point casters (Lighting.hlsl:308-322; PSMain :310-313,321-340):
+    //      in range <=> d2 < d2Limit (== length(Lw-P) < l.range, exactly) ----
+    for (int i = 0; i < numPoint; ++i) {
+        const SPoint l = sPoint[i];
+        const LightVec2 L = light_vector2(s, l.pos);
+        const f2 att = (L.invD * L.invD) * bc(l.brightness);               // AttenuationBRDF = 1/D^2
+        const f2 scale = mk(L.d2.v.x < l.d2Limit ? att.v.x : 0.0f, L.d2.v.y < l.d2Limit ? att.v.y : 0.0f);
+        shade_light2<TINY>(s, acc, cam, L.x, L.y, L.z, L.d2, L.invD, scale, l.color);
+    }
+    // ---- spot lights, then unshadowed spot casters (Lighting.hlsl:57-73,323-333) ----
+    for (int k = 0; k < numSpot; ++k) {
+        const SSpot l = sSpot[k];
+        const LightVec2 L = light_vector2(s, l.pos);
+        const f2 cosT = dot3(L.x, L.y, L.z, bc(l.dir.x), bc(l.dir.y), bc(l.dir.z)) * L.invD;   // pixel direction = -Wi
+        float inten[2];
+#pragma unroll
+        for (int q = 0; q < 2; ++q) {
+            const float theta = acosf(fminf(fmaxf(-(q ? cosT.v.y : cosT.v.x), -1.0f), 1.0f));
+            const float lin = 1.0f - (theta - l.inner) * l.invCone;
+            inten[q] = theta > l.outer ? 0.0f : (theta <= l.inner ? 1.0f : lin);
+        }
+        const f2 scale = mk(inten[0], inten[1]) * bc(l.brightness) * (L.invD * L.invD);
+        shade_light2<TINY>(s, acc, cam, L.x, L.y, L.z, L.d2, L.invD, scale, l.color);
+    }
+    // ---- directional (PSMain :360-377 with ShadowingFactor = 1) ----
+    if (dirEnabled) {
+        const SDir d = *sDir;
+        shade_light2<TINY>(s, acc, cam, bc(d.wi.x), bc(d.wi.y), bc(d.wi.z), bc(1.0f), bc(1.0f), bc(1.0f), d.radiance);
+    }
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -343,62 +462,77 @@ __device__ __forceinline__ void st_stream_hint(float4* p, float4 v, uint64_t pol
 }
 
 // K1 is a persistent kernel: FWD_CTAS_PER_SM CTAs of 128 threads per SM, each walking the tile list
-// (tile = 128 consecutive pixels of one row = one 2 KB row segment per G-buffer plane) with stride gridDim.x.
-// The G-buffer arrives through a FWD_STAGES-deep TMA pipeline in shared memory: thread 0 issues one bulk copy
-// per plane for the tile FWD_AHEAD iterations ahead (full[] mbarriers count the bytes), every thread reads
-// ITS texels back with LDS when it needs them and releases the stage (empty[] mbarriers) when its pixel is
+// (tile = 256 consecutive pixels of one row = one 4 KB row segment per G-buffer plane; two pixels per thread) with stride
+// gridDim.y over the rows. The G-buffer arrives through a FWD_STAGES-deep TMA pipeline in shared memory: thread 0 issues one bulk
+// copy per plane for the tile FWD_AHEAD iterations ahead (full[] mbarriers count the bytes), every thread reads
+// ITS texels back with LDS when it needs them and releases the stage (empty[] mbarriers) when its pixels are
 // stored. Nothing of the G-buffer is live in registers across the light loop: albedo/metalness/ao, the raw
-// normal and the emissive texel are (re-)read from the stage after it, which is what lets the kernel run at
-// <= 80 registers with the HBM latency fully hidden behind the previous tiles' shading.
-// A/B on B200 at 4K: profiles/r01_forward_variants.txt.
-constexpr int FWD_TILE = 128;     // 64-pixel tiles measured 3 % slower (profiles/r01_forward_variants.txt)
+// normal and the emissive texel are (re-)read from the stage after it.
 #ifndef FWD_STAGES
-#define FWD_STAGES 4           // shared-memory stages
+#define FWD_STAGES 3           // shared-memory stages
 #endif
 #ifndef FWD_AHEAD
-#define FWD_AHEAD 2            // tiles requested ahead of the one being shaded (< FWD_STAGES): the stage a request
-#endif                         // reuses was released FWD_STAGES-FWD_AHEAD iterations ago, so thread 0 rarely waits
-#ifndef FWD_CTAS_PER_SM
-#define FWD_CTAS_PER_SM 6
+#define FWD_AHEAD 2            // tiles requested ahead of the one being shaded (< FWD_STAGES)
 #endif
-
+#ifndef FWD_CTAS_PER_SM
+#define FWD_CTAS_PER_SM 4
+#endif
 static_assert(FWD_AHEAD >= 1 && FWD_AHEAD < FWD_STAGES, "the lookahead must leave at least one stage for the tile being shaded");
 
-struct CubeTap { uint32_t off; int P; float fx, fy; };
-__device__ __forceinline__ CubeTap cube_tap(const CubeV& c, float3 dir, int mip) {
-    mip = min(max(mip, 0), c.mips - 1);
-    const int N = c.res >> mip, P = N + 2;
-    int face; float sx, sy;
-    dir_to_face(dir, face, sx, sy);
-    const float x = fmaf(fmaf(sx, 0.5f, 0.5f), (float)N, -0.5f);
-    const float y = fmaf(fmaf(-sy, 0.5f, 0.5f), (float)N, -0.5f);
-    const float xf = fminf(fmaxf(floorf(x), -1.0f), (float)(N - 1)), yf = fminf(fmaxf(floorf(y), -1.0f), (float)(N - 1));
-    CubeTap t;
-    t.fx = x - xf; t.fy = y - yf; t.P = P;
-    const int i0 = (int)xf + 1, j0 = (int)yf + 1;            // bordered coordinates: 0..N
-    t.off = c.mipOffset[mip] + (uint32_t)(face * (P * P) + j0 * P + i0);
-    return t;
-}
-// A gather is split into "issue" (address + the 256-bit loads) and "finish" (the lerps) so that the loads of several
-// gathers can be put in flight before the first one is consumed.
-__device__ __forceinline__ F8 ldg256_issue(const float4* p) {      // 32-byte aligned, read-only path (LDG.E.256)
+// ---- environment taps -----------------------------------------------------------------------------------
+// per (mip, face) constants of the specular sampling copy, staged once per CTA: one LDS.128 replaces the shifts, the
+// int->float conversions and the mipOffset[] constant-bank indexing of a per-pixel mip
+struct FaceRec { uint32_t base; uint32_t P; float halfN; float c0; };     // first record of the face, row stride, N/2, N/2 - 0.5
+static_assert(sizeof(FaceRec) == 16, "one LDS.128");
+
+// L1 policy of a gather (A/B on B200, profiles/r02_forward_variants.txt): 0 = allocate, 1 = L1::no_allocate, 2 = L1::evict_last
+#ifndef FWD_L1_DIFF
+#define FWD_L1_DIFF 0
+#endif
+#ifndef FWD_L1_SPEC
+#define FWD_L1_SPEC 1
+#endif
+#ifndef FWD_L1_LUT
+#define FWD_L1_LUT 1
+#endif
+template <int POLICY>
+__device__ __forceinline__ F8 ldg256(const float4* p) {             // 32-byte aligned, read-only path (LDG.E.256)
     F8 r;
-    asm("ld.global.nc.v8.f32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
-        : "=f"(r.a.x), "=f"(r.a.y), "=f"(r.a.z), "=f"(r.a.w), "=f"(r.b.x), "=f"(r.b.y), "=f"(r.b.z), "=f"(r.b.w) : "l"(p));
+    if (POLICY == 1)
+        asm("ld.global.nc.L1::no_allocate.v8.f32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
+            : "=f"(r.a.x), "=f"(r.a.y), "=f"(r.a.z), "=f"(r.a.w), "=f"(r.b.x), "=f"(r.b.y), "=f"(r.b.z), "=f"(r.b.w) : "l"(p));
+    else if (POLICY == 2)
+        asm("ld.global.nc.L1::evict_last.v8.f32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
+            : "=f"(r.a.x), "=f"(r.a.y), "=f"(r.a.z), "=f"(r.a.w), "=f"(r.b.x), "=f"(r.b.y), "=f"(r.b.z), "=f"(r.b.w) : "l"(p));
+    else
+        asm("ld.global.nc.v8.f32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
+            : "=f"(r.a.x), "=f"(r.a.y), "=f"(r.a.z), "=f"(r.a.w), "=f"(r.b.x), "=f"(r.b.y), "=f"(r.b.z), "=f"(r.b.w) : "l"(p));
     return r;
 }
 struct CubeLoad { F8 r0, r1; float fx, fy; };                     // rows j0 and j0+1: {t(i0), t(i0+1)} each
-__device__ __forceinline__ CubeLoad cube_issue(const CubeV& c, float3 dir, int mip) {
-    const CubeTap t = cube_tap(c, dir, mip);
-    const float4* p = c.p + 2u * t.off;
+// A gather is split into "issue" (address + the 256-bit loads) and "finish" (the lerps) so that the loads of several
+// gathers are in flight before the first one is consumed.
+// maxRec: last record a footprint may start at (clamps the address for NaN/inf directions: no surface => no normal)
+template <int POLICY>
+__device__ __forceinline__ CubeLoad cube_issue(const float4* __restrict__ recs, FaceRec f, uint32_t maxRec, float sx, float sy) {
+    const float x = fmaf(sx, f.halfN, f.c0), y = fmaf(-sy, f.halfN, f.c0);       // texel space: (s*0.5+0.5)*N - 0.5
+    const float xf = floorf(x), yf = floorf(y);                                  // in [-1, N-1] for every finite direction
     CubeLoad L;
-    L.r0 = ldg256_issue(p); L.r1 = ldg256_issue(p + 2 * t.P);
-    L.fx = t.fx; L.fy = t.fy;
+    L.fx = x - xf; L.fy = y - yf;
+    const uint32_t off = min(f.base + (uint32_t)((int)yf + 1) * f.P + (uint32_t)((int)xf + 1), maxRec);
+    const float4* p = recs + 2u * off;
+    L.r0 = ldg256<POLICY>(p); L.r1 = ldg256<POLICY>(p + 2u * f.P);
     return L;
 }
+// bilinear blend of the footprint as packed pairs {x,y}, {z,w} of one pixel: 12 packed operations instead of 18 scalar ones
 __device__ __forceinline__ float3 cube_finish(const CubeLoad& L) {
-    const float3 top = lerp(xyz(L.r0.a), xyz(L.r0.b), L.fx), bot = lerp(xyz(L.r1.a), xyz(L.r1.b), L.fx);
-    return lerp(top, bot, L.fy);
+    const f2 fx = bc(L.fx), fy = bc(L.fy);
+    const f2 a0 = mk(L.r0.a.x, L.r0.a.y), a1 = mk(L.r0.a.z, L.r0.a.w), b0 = mk(L.r0.b.x, L.r0.b.y), b1 = mk(L.r0.b.z, L.r0.b.w);
+    const f2 c0 = mk(L.r1.a.x, L.r1.a.y), c1 = mk(L.r1.a.z, L.r1.a.w), d0 = mk(L.r1.b.x, L.r1.b.y), d1 = mk(L.r1.b.z, L.r1.b.w);
+    const f2 t0 = fma2(fx, b0 - a0, a0), t1 = fma2(fx, b1 - a1, a1);
+    const f2 u0 = fma2(fx, d0 - c0, c0), u1 = fma2(fx, d1 - c1, c1);
+    const f2 r0 = fma2(fy, u0 - t0, t0), r1 = fma2(fy, u1 - t1, t1);
+    return f3(r0.v.x, r0.v.y, r1.v.x);
 }
 struct LutLoad { F8 q; float fx, fy; };
 __device__ __forceinline__ LutLoad lut_issue(const LutV& l, float u, float v) {   // bilinear, CLAMP
@@ -407,26 +541,87 @@ __device__ __forceinline__ LutLoad lut_issue(const LutV& l, float u, float v) { 
     LutLoad L;
     L.fx = x - x0; L.fy = y - y0;
     const int cx = min(max((int)x0 + 1, 0), l.w), cy = min(max((int)y0 + 1, 0), l.h);
-    L.q = ldg256_issue(l.q + 2u * (uint32_t)(cy * (l.w + 1) + cx));
+    L.q = ldg256<FWD_L1_LUT>(l.q + 2u * (uint32_t)(cy * (l.w + 1) + cx));
     return L;
 }
-__device__ __forceinline__ float2 lut_finish(const LutLoad& L) {
-    return make_float2(lerp(lerp(L.q.a.x, L.q.a.z, L.fx), lerp(L.q.b.x, L.q.b.z, L.fx), L.fy),
-                       lerp(lerp(L.q.a.y, L.q.a.w, L.fx), lerp(L.q.b.y, L.q.b.w, L.fx), L.fy));
+__device__ __forceinline__ float2 lut_finish(const LutLoad& L) {    // record = {p00, p10 | p01, p11} as float2 each
+    const f2 fx = bc(L.fx), fy = bc(L.fy);
+    const f2 p00 = mk(L.q.a.x, L.q.a.y), p10 = mk(L.q.a.z, L.q.a.w), p01 = mk(L.q.b.x, L.q.b.y), p11 = mk(L.q.b.z, L.q.b.w);
+    const f2 t = fma2(fx, p10 - p00, p00), u = fma2(fx, p11 - p01, p01);
+    return fma2(fy, u - t, t).v;
 }
 
-template <bool MULTI>
-__global__ void __launch_bounds__(FWD_TILE, FWD_CTAS_PER_SM) forward_kernel(const __grid_constant__ FwdParams P) {
+// the environment lookups and the final composition of ONE pixel (PSMain :290-293, Lighting.hlsl:360-395, BRDF.hlsl:177-207)
+//   texel : shared-memory address of the pixel's position texel,  V/nsnv : normalize(cam-P), saturate(dot(s.N, V))
+//   la/lb/lc : the light sums  sum w*col*{(1-fc), fc*spec, spec}
+//   Ns : the surface normal as normalize(Ns)*|Ns| (within an ulp of the raw texel; it only steers the two cube lookups)
+template <bool ROT>
+__device__ __forceinline__ float4 finish_pixel(const FwdParams& P, const FaceRec* __restrict__ sFace, uint32_t texel, float3 V, float nsnv,
+                                               float3 Ns, float roughness, float ao, float3 la, float3 lb, float3 lc) {
+    // ---- environment taps. Order tuned on B200 (profiles/r01_forward_variants.txt): the two diffuse-cube loads go out first
+    //      and fly while the specular address math runs; then the specular cube and the LUT. ----
+    float3 specCol = f3(0.0f), diffIrr; float2 sb = make_float2(0.0f, 0.0f);
+    {
+        const float3 Nr = ROT ? f3(Ns.x * P.cosB - Ns.z * P.sinB, Ns.y, Ns.x * P.sinB + Ns.z * P.cosB) : Ns;
+        int face; float sx, sy;
+        dir_to_face(Nr, face, sx, sy);
+        FaceRec fd; fd.P = (uint32_t)P.diff.res + 2u; fd.base = (uint32_t)face * fd.P * fd.P; fd.halfN = P.diffHalfN; fd.c0 = P.diffHalfN - 0.5f;
+        const CubeLoad ldD = cube_issue<FWD_L1_DIFF>(P.diff.p, fd, P.diffMaxRec, sx, sy);
+        if (!P.diffuseOnly) {
+            const float3 R0 = reflect(-V, Ns);
+            const float3 R = ROT ? f3(R0.x * P.cosB - R0.z * P.sinB, R0.y, R0.x * P.sinB + R0.z * P.cosB) : R0;
+            dir_to_face(R, face, sx, sy);
+            const int mip = min(max((int)(roughness * (float)P.maxLod), 0), P.spec.mips - 1);
+            const CubeLoad ldS = cube_issue<FWD_L1_SPEC>(P.spec.p, sFace[face * 16 + mip], P.specMaxRec, sx, sy);
+            const LutLoad ldL = lut_issue(P.lut, nsnv, roughness);               // (saturate(dot(s.N, V)), roughness)
+            specCol = cube_finish(ldS); sb = lut_finish(ldL);
+        }
+        diffIrr = cube_finish(ldD);
+    }
+    // ---- the rest of the G-buffer texel comes out of the stage only now ----
+    const float4 am = lds128(texel + 2u * FWD_PLANE);
+    const float3 albedo = xyz(am);
+    const float metalness = am.w;
+    float3 I = albedo * ao;                                  // the ambient factor rides in position.w                                  // ForwardLighting.hlsl:290-293
+    if (P.hasEmissive) {
+        const float4 em = lds128(texel + 3u * FWD_PLANE);
+        I += xyz(em) * em.w;
+    }
+    const float3 F0 = lerp(f3(0.04f), albedo, metalness);    // BRDF.hlsl:177
+    {   // K1 = (1-F0)*(1-metal)*albedo/PI (BRDF.hlsl:189-191)
+        const float3 omF0 = f3(1.0f) - F0;
+        const float3 K1 = omF0 * albedo * ((1.0f - metalness) * (1.0f / PI));
+        I.x += fmaf(K1.x, la.x, fmaf(omF0.x, lb.x, F0.x * lc.x));
+        I.y += fmaf(K1.y, la.y, fmaf(omF0.y, lb.y, F0.y * lc.y));
+        I.z += fmaf(K1.z, la.z, fmaf(omF0.z, lb.z, F0.z * lc.z));
+    }
+    {   // ---- EnvironmentBRDF (BRDF.hlsl:196-207) on the gathered taps ----
+        const float fr = pow5(1.0f - nsnv);                      // FresnelWithRoughness(saturate(dot(s.N, V))), BRDF.hlsl:152-156
+        const float omr = 1.0f - roughness;
+        const float3 Ks = f3(fmaf(fmaxf(omr, F0.x) - F0.x, fr, F0.x),
+                             fmaf(fmaxf(omr, F0.y) - F0.y, fr, F0.y),
+                             fmaf(fmaxf(omr, F0.z) - F0.z, fr, F0.z));
+        const float om = 1.0f - metalness;
+        I.x += (1.0f - Ks.x) * om * (diffIrr.x * albedo.x) + specCol.x * fmaf(Ks.x, sb.x, sb.y);
+        I.y += (1.0f - Ks.y) * om * (diffIrr.y * albedo.y) + specCol.y * fmaf(Ks.y, sb.x, sb.y);
+        I.z += (1.0f - Ks.z) * om * (diffIrr.z * albedo.z) + specCol.z * fmaf(Ks.z, sb.x, sb.y);
+    }
+    return make_float4(I.x, I.y, I.z, roughness);                // :380
+}
+
+template <bool MULTI, bool ROT>
+__global__ void __launch_bounds__(FWD_THREADS, FWD_CTAS_PER_SM) forward_kernel(const __grid_constant__ FwdParams P) {
     extern __shared__ __align__(128) unsigned char smemRaw[];
     const VqSceneLighting& L = P.lights;
     const int nP = L.numPointLights, nPC = L.numPointCasters, nS = L.numSpotLights, nSC = L.numSpotCasters;
     const int numPoint = nP + nPC, numSpot = nS + nSC;
     const int nPl = P.hasEmissive ? 4 : 3;
     const int tid = threadIdx.x;
-    // shared-memory layout: [FWD_STAGES][nPl][FWD_TILE] float4 | full[S], empty[S] mbarriers | SDir | SPoint[] | SSpot[]
-    const uint32_t stageBytes = (uint32_t)nPl * FWD_TILE * 16u;
+    // shared-memory layout: [FWD_STAGES][nPl][FWD_TILE] float4 | full[S], empty[S] mbarriers | FaceRec[8*16] | SDir | SPoint[] | SSpot[]
+    const uint32_t stageBytes = (uint32_t)nPl * FWD_PLANE;
     uint64_t* bars = (uint64_t*)(smemRaw + FWD_STAGES * stageBytes);
-    SDir* sDir = (SDir*)(bars + 2 * FWD_STAGES);
+    FaceRec* sFace = (FaceRec*)(bars + 2 * FWD_STAGES);
+    SDir* sDir = (SDir*)(sFace + 16 * 8);
     SPoint* sPoint = (SPoint*)(sDir + 1);
     SSpot* sSpot = (SSpot*)(sPoint + numPoint);
     const uint32_t stage0 = smem_u32(smemRaw), bar0 = smem_u32(bars);
@@ -447,19 +642,19 @@ __global__ void __launch_bounds__(FWD_TILE, FWD_CTAS_PER_SM) forward_kernel(cons
         const size_t y = (size_t)(P.rowBegin + r);
         mbar_expect_tx(bar, tileBytes * (uint32_t)nPl);
         tma_load_row(dst, P.pos.p + y * P.pos.pitch4 + x0, tileBytes, bar, pol);
-        tma_load_row(dst + FWD_TILE * 16u, P.nrm.p + y * P.nrm.pitch4 + x0, tileBytes, bar, pol);
-        tma_load_row(dst + 2u * FWD_TILE * 16u, P.alb.p + y * P.alb.pitch4 + x0, tileBytes, bar, pol);
-        if (nPl == 4) tma_load_row(dst + 3u * FWD_TILE * 16u, P.emi.p + y * P.emi.pitch4 + x0, tileBytes, bar, pol);
+        tma_load_row(dst + FWD_PLANE, P.nrm.p + y * P.nrm.pitch4 + x0, tileBytes, bar, pol);
+        tma_load_row(dst + 2u * FWD_PLANE, P.alb.p + y * P.alb.pitch4 + x0, tileBytes, bar, pol);
+        if (nPl == 4) tma_load_row(dst + 3u * FWD_PLANE, P.emi.p + y * P.emi.pitch4 + x0, tileBytes, bar, pol);
     };
     if (tid == 0) {
-        for (int s = 0; s < FWD_STAGES; ++s) { mbar_init(fullBar(s), 1u); mbar_init(emptyBar(s), (uint32_t)FWD_TILE); }
+        for (int s = 0; s < FWD_STAGES; ++s) { mbar_init(fullBar(s), 1u); mbar_init(emptyBar(s), (uint32_t)FWD_THREADS); }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
         asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
         for (int s = 0; s < FWD_AHEAD; ++s) request((int)blockIdx.y + s * rowStep, s, 0u);   // prologue: FWD_AHEAD tiles in flight
     }
 
-    // ---- stage the light arrays (Scene::GatherLightData layout) into shared memory, once per CTA ----
-    for (int i = tid; i < numPoint; i += FWD_TILE) {
+    // ---- stage the light arrays (Scene::GatherLightData layout) and the specular cube's face table, once per CTA ----
+    for (int i = tid; i < numPoint; i += FWD_THREADS) {
         const VqPointLight& l = i < nP ? L.point_lights[i] : L.point_casters[i - nP];
         SPoint s;
         s.pos = f3(l.position.x, l.position.y, l.position.z);
@@ -475,7 +670,7 @@ __global__ void __launch_bounds__(FWD_TILE, FWD_CTAS_PER_SM) forward_kernel(cons
         s.d2Limit = lim;
         sPoint[i] = s;
     }
-    for (int i = tid; i < numSpot; i += FWD_TILE) {
+    for (int i = tid; i < numSpot; i += FWD_THREADS) {
         const VqSpotLight& l = i < nS ? L.spot_lights[i] : L.spot_casters[i - nS];
         SSpot s;
         s.pos = f3(l.position.x, l.position.y, l.position.z);
@@ -486,8 +681,20 @@ __global__ void __launch_bounds__(FWD_TILE, FWD_CTAS_PER_SM) forward_kernel(cons
         s.invCone = 1.0f / (l.outerConeAngle - l.innerConeAngle);
         sSpot[i] = s;
     }
+    for (int i = tid; i < 16 * 8; i += FWD_THREADS) {
+        // index = face*16 + mip: the lanes of a warp mostly share the face and differ in the mip (per-pixel roughness), so the
+        // entries they read are ADJACENT 16-byte words in different banks (mip*8+face measured 19 wavefronts per LDS.128, ideal 4)
+        const int mip = i & 15, face = i >> 4;
+        FaceRec f; f.base = 0u; f.P = 3u; f.halfN = 0.5f; f.c0 = 0.0f;
+        if (!P.diffuseOnly && mip < P.spec.mips && face < 6) {
+            const int N = P.spec.res >> mip;
+            f.P = (uint32_t)N + 2u; f.base = P.spec.mipOffset[mip] + (uint32_t)face * f.P * f.P;
+            f.halfN = 0.5f * (float)N; f.c0 = f.halfN - 0.5f;
+        }
+        sFace[i] = f;
+    }
     const bool dirEnabled = L.directional.enabled != 0;
-    if (dirEnabled && tid == FWD_TILE - 1) {                       // Lighting.hlsl:334-345: Wi = normalize(-dir), radiance = color * brightness
+    if (dirEnabled && tid == FWD_THREADS - 1) {                    // Lighting.hlsl:334-345: Wi = normalize(-dir), radiance = color * brightness
         SDir d;
         d.wi = normalize_u_generic(f3(-L.directional.lightDirection.x, -L.directional.lightDirection.y, -L.directional.lightDirection.z));
         d.radiance = f3(L.directional.color.x, L.directional.color.y, L.directional.color.z) * L.directional.brightness;
@@ -495,10 +702,10 @@ __global__ void __launch_bounds__(FWD_TILE, FWD_CTAS_PER_SM) forward_kernel(cons
         *sDir = d;
     }
     __syncthreads();                                              // lights staged, mbarriers initialised
-    const bool rot = P.sinB != 0.0f || P.cosB != 1.0f;           // uniform: yaw offset 0 is the common case
 
     int st = 0; uint32_t use = 0;                                 // stage of the current tile, completed uses of that stage
-    const int x = x0 + tid;
+    const int xA = x0 + tid, xB = xA + FWD_THREADS;
+    const bool validA = xA < P.width, validB = xB < P.width;      // a ragged last tile: B (or both) fall off the row
     for (int row = (int)blockIdx.y; row < P.rows; row += rowStep) {
         if (tid == 0) {                                           // request the tile FWD_AHEAD iterations ahead
             const int ps = st + FWD_AHEAD;
@@ -507,103 +714,82 @@ __global__ void __launch_bounds__(FWD_TILE, FWD_CTAS_PER_SM) forward_kernel(cons
         }
         mbar_wait(fullBar(st), use & 1u);                         // this tile has landed
         const int y = P.rowBegin + row;
-        const uint32_t texel = stage0 + (uint32_t)st * stageBytes + (uint32_t)tid * 16u;
-        if (x < P.width) {
-            Px s;
-            float roughness;
+        if (validA) {
+            Px2 s;
+            s.texA = stage0 + (uint32_t)st * stageBytes + (uint32_t)tid * 16u;
+            s.texB = validB ? s.texA + FWD_THREADS * 16u : s.texA;   // off the row: shade pixel A twice, store it once
+            f2 roughness, ao;
             {
-                const float4 pa = lds128(texel), nr = lds128(texel + FWD_TILE * 16u);
-                s.P = xyz(pa);
-                s.nrmTexel = texel + FWD_TILE * 16u;
-                const float3 Ns = xyz(nr);
-                roughness = nr.w;
-                const float3 Vv = P.cam - s.P;
-                s.V = Vv * rsqrt_fast(dot(Vv, Vv));                  // ForwardLighting.hlsl:285
-                const float n2 = dot(Ns, Ns), rn = rsqrt_fast(n2);
-                s.Nn = Ns * rn;                                      // BRDF.hlsl:167
+                const float4 pa = lds128(s.texA), pb = lds128(s.texB);
+                ao = mk(pa.w, pb.w);
+                const float4 na = lds128(s.texA + FWD_PLANE), nb = lds128(s.texB + FWD_PLANE);
+                s.PA = xyz(pa); s.PB = xyz(pb);
+                const f2 Nsx = mk(na.x, nb.x), Nsy = mk(na.y, nb.y), Nsz = mk(na.z, nb.z);
+                roughness = mk(na.w, nb.w);
+                const f2 Vx = mk(P.cam.x - pa.x, P.cam.x - pb.x), Vy = mk(P.cam.y - pa.y, P.cam.y - pb.y), Vz = mk(P.cam.z - pa.z, P.cam.z - pb.z);
+                const f2 rv = rsq2(dot3(Vx, Vy, Vz, Vx, Vy, Vz));
+                s.Vx = Vx * rv; s.Vy = Vy * rv; s.Vz = Vz * rv;          // ForwardLighting.hlsl:285
+                const f2 n2 = dot3(Nsx, Nsy, Nsz, Nsx, Nsy, Nsz), rn = rsq2(n2);
+                s.Nx = Nsx * rn; s.Ny = Nsy * rn; s.Nz = Nsz * rn;       // BRDF.hlsl:167
                 s.nsLen = n2 * rn;
             }
-            const float a = roughness * roughness;
-            s.a2 = __fmul_rn(a, a); s.a2m1 = __fsub_rn(s.a2, 1.0f);  // no contraction: feeds the exact t
-            const float rp1 = roughness + 1.0f;
-            s.k = (rp1 * rp1) * 0.125f; s.omk = 1.0f - s.k;
-            s.nv = dot(s.Nn, s.V);
-            s.NdotV = saturate(s.nv);
-            s.gV = s.NdotV * rcp_fast(fmaf(s.NdotV, s.omk, s.k) + 0.0001f);
+            const f2 a = roughness * roughness;
+            const f2 a2 = mul_rn2(a, a);
+            s.a2m1 = add_rn2(a2, bc(-1.0f));                             // no contraction: feeds the exact t
+            const f2 rp1 = roughness + bc(1.0f);
+            const f2 k = (rp1 * rp1) * bc(0.125f);
+            s.omk = bc(1.0f) - k; s.k4 = k + bc(0.0001f);
+            s.nv = dot3(s.Nx, s.Ny, s.Nz, s.Vx, s.Vy, s.Vz);
+            if (fminf(fabsf(s.nv.v.x), fabsf(s.nv.v.y)) < NV_EXACT) {     // grazing view: ~0.1 % of pixels
+                if (fabsf(s.nv.v.x) < NV_EXACT) s.nv.v.x = exact_nv(P.cam, s.PA, s.texA + FWD_PLANE);
+                if (fabsf(s.nv.v.y) < NV_EXACT) s.nv.v.y = exact_nv(P.cam, s.PB, s.texB + FWD_PLANE);
+            }
+            const f2 NdotV = sat2(s.nv);
+            s.gV = NdotV * rcp2(fma2(NdotV, s.omk, s.k4));
+            s.a2gV = a2 * s.gV;
+            s.nv4 = NdotV * bc(4.0f);
 
-            Acc acc; acc.a = f3(0.0f); acc.b = f3(0.0f); acc.c = f3(0.0f);
-            // ---- point lights, then unshadowed point casters (Lighting.hlsl:308-322; PSMain :310-313,321-340) ----
-            for (int i = 0; i < numPoint; ++i) shade_point(s, acc, P.cam, sPoint[i]);
-            // ---- spot lights, then unshadowed spot casters (Lighting.hlsl:57-73,323-333) ----
-            for (int k = 0; k < numSpot; ++k) {
-                const SSpot l = sSpot[k];
-                const float3 Lv = l.pos - s.P;
-                const float d2 = dot_u(Lv, Lv);
-                const float invD = rsqrt_fast(fmaxf(d2, 1e-30f));
-                const float theta = acosf(fminf(fmaxf(-dot(Lv, l.dir) * invD, -1.0f), 1.0f));   // pixel direction = -Wi
-                float inten = 1.0f - (theta - l.inner) * l.invCone;
-                inten = theta > l.outer ? 0.0f : (theta <= l.inner ? 1.0f : inten);
-                shade_light(s, acc, P.cam, Lv, d2, invD, inten * l.brightness * (invD * invD), l.color);
-            }
-            // ---- directional (PSMain :360-377 with ShadowingFactor = 1) ----
-            if (dirEnabled) { const SDir d = *sDir; shade_light(s, acc, P.cam, d.wi, 1.0f, 1.0f, 1.0f, d.radiance); }
+            Acc2 acc;
+            acc.ax = acc.ay = acc.az = acc.bx = acc.by = acc.bz = acc.cx = acc.cy = acc.cz = bc(0.0f);
+            // can `PI*t*t < 1e-12` ever hold for one of this warp's pixels?  t >= 1 + min(a2-1, 0), rounding is monotone
+            const f2 tmin = bc(1.0f) + mk(fminf(s.a2m1.v.x, 0.0f), fminf(s.a2m1.v.y, 0.0f));
+            const f2 dmin = bc(PI) * (tmin * tmin);
+            if (__any_sync(0xffffffffu, fminf(dmin.v.x, dmin.v.y) < 2e-12f))
+                shade_all_lights<true>(s, acc, P.cam, sPoint, numPoint, sSpot, numSpot, sDir, dirEnabled);
+            else
+                shade_all_lights<false>(s, acc, P.cam, sPoint, numPoint, sSpot, numSpot, sDir, dirEnabled);
 
-            // ---- environment taps (Lighting.hlsl:360-395). Order tuned on B200 (profiles/r01_forward_variants.txt): the two
-            //      diffuse-cube loads go out first and fly while the specular address math runs; then the specular cube
-            //      and the LUT. Issuing all five before the light loop (40 registers in flight) or all five together
-            //      after it costs occupancy / spills and measured slower. ----
-            float3 specCol = f3(0.0f), diffIrr; float2 sb = make_float2(0.0f, 0.0f);
-            {
-                const float3 Ns = xyz(lds128(texel + FWD_TILE * 16u));
-                const float3 Nr = rot ? f3(Ns.x * P.cosB - Ns.z * P.sinB, Ns.y, Ns.x * P.sinB + Ns.z * P.cosB) : Ns;
-                const CubeLoad ldD = cube_issue(P.diff, Nr, 0);
-                if (!P.diffuseOnly) {
-                    const float3 R0 = reflect(-s.V, Ns);
-                    const float3 R = rot ? f3(R0.x * P.cosB - R0.z * P.sinB, R0.y, R0.x * P.sinB + R0.z * P.cosB) : R0;
-                    const CubeLoad ldS = cube_issue(P.spec, R, (int)(roughness * (float)P.maxLod));
-                    const LutLoad ldL = lut_issue(P.lut, saturate(s.nsLen * s.nv), roughness);   // (saturate(dot(s.N, V)), roughness)
-                    specCol = cube_finish(ldS); sb = lut_finish(ldL);
-                }
-                diffIrr = cube_finish(ldD);
+            const f2 nsnv = mulsat2(s.nsLen, s.nv);                      // saturate(dot(s.N, V)) of the raw normal
+            const f2 Nrx = s.Nx * s.nsLen, Nry = s.Ny * s.nsLen, Nrz = s.Nz * s.nsLen;
+            const float4 oA = finish_pixel<ROT>(P, sFace, s.texA, f3(s.Vx.v.x, s.Vy.v.x, s.Vz.v.x), nsnv.v.x,
+                                                f3(Nrx.v.x, Nry.v.x, Nrz.v.x), roughness.v.x, ao.v.x, f3(acc.ax.v.x, acc.ay.v.x, acc.az.v.x), f3(acc.bx.v.x, acc.by.v.x, acc.bz.v.x),
+                                                f3(acc.cx.v.x, acc.cy.v.x, acc.cz.v.x));
+            {   // one STG.128 per destination; peer destinations are mapped NVLink addresses (fused compute + gather)
+                if (MULTI) { for (int q = 0; q < P.nOut; ++q) st_stream(P.outs[q].row(P.dstRowOffset + y) + xA, oA); }
+                else st_stream_hint(P.outs[0].row(P.dstRowOffset + y) + xA, oA, l2_evict_first_policy());
             }
-
-            // ---- the rest of the G-buffer texel comes out of the stage only now ----
-            const float4 am = lds128(texel + 2u * FWD_TILE * 16u);
-            const float3 albedo = xyz(am);
-            const float metalness = am.w;
-            const float ao = lds32(texel + 12u);                     // the ambient factor rides in position.w
-            float3 I = albedo * ao;                                  // ForwardLighting.hlsl:290-293
-            if (P.hasEmissive) {
-                const float4 em = lds128(texel + 3u * FWD_TILE * 16u);
-                I += xyz(em) * em.w;
-            }
-            const float3 F0 = lerp(f3(0.04f), albedo, metalness);    // BRDF.hlsl:177
-            {   // K1 = (1-F0)*(1-metal)*albedo/PI (BRDF.hlsl:189-191)
-                const float3 omF0 = f3(1.0f) - F0;
-                const float3 K1 = omF0 * albedo * ((1.0f - metalness) * (1.0f / PI));
-                I.x += fmaf(K1.x, acc.a.x, fmaf(omF0.x, acc.b.x, F0.x * acc.c.x));
-                I.y += fmaf(K1.y, acc.a.y, fmaf(omF0.y, acc.b.y, F0.y * acc.c.y));
-                I.z += fmaf(K1.z, acc.a.z, fmaf(omF0.z, acc.b.z, F0.z * acc.c.z));
-            }
-            {   // ---- EnvironmentBRDF (BRDF.hlsl:196-207) on the gathered taps ----
-                const float fr = pow5(1.0f - saturate(s.nsLen * s.nv));   // FresnelWithRoughness(saturate(dot(s.N, V))), BRDF.hlsl:152-156
-                const float omr = 1.0f - roughness;
-                const float3 Ks = f3(fmaf(fmaxf(omr, F0.x) - F0.x, fr, F0.x),
-                                     fmaf(fmaxf(omr, F0.y) - F0.y, fr, F0.y),
-                                     fmaf(fmaxf(omr, F0.z) - F0.z, fr, F0.z));
-                const float om = 1.0f - metalness;
-                I.x += (1.0f - Ks.x) * om * (diffIrr.x * albedo.x) + specCol.x * fmaf(Ks.x, sb.x, sb.y);
-                I.y += (1.0f - Ks.y) * om * (diffIrr.y * albedo.y) + specCol.y * fmaf(Ks.y, sb.x, sb.y);
-                I.z += (1.0f - Ks.z) * om * (diffIrr.z * albedo.z) + specCol.z * fmaf(Ks.z, sb.x, sb.y);
-            }
-            {   // :380 — one STG.128 per destination; peer destinations are mapped NVLink addresses (fused compute + gather)
-                const float4 o = make_float4(I.x, I.y, I.z, roughness);
-                if (MULTI) { for (int k = 0; k < P.nOut; ++k) st_stream(P.outs[k].row(P.dstRowOffset + y) + x, o); }
-                else st_stream_hint(P.outs[0].row(P.dstRowOffset + y) + x, o, l2_evict_first_policy());
+            if (validB) {
+                const float4 oB = finish_pixel<ROT>(P, sFace, s.texB, f3(s.Vx.v.y, s.Vy.v.y, s.Vz.v.y), nsnv.v.y,
+                                                    f3(Nrx.v.y, Nry.v.y, Nrz.v.y), roughness.v.y, ao.v.y, f3(acc.ax.v.y, acc.ay.v.y, acc.az.v.y), f3(acc.bx.v.y, acc.by.v.y, acc.bz.v.y),
+                                                    f3(acc.cx.v.y, acc.cy.v.y, acc.cz.v.y));
+                if (MULTI) { for (int q = 0; q < P.nOut; ++q) st_stream(P.outs[q].row(P.dstRowOffset + y) + xB, oB); }
+                else st_stream_hint(P.outs[0].row(P.dstRowOffset + y) + xB, oB, l2_evict_first_policy());
             }
         }
         mbar_arrive(emptyBar(st));                               // this thread is done with the stage
         if (++st == FWD_STAGES) { st = 0; ++use; }
+    }
+    if (MULTI && P.sync.n > 1) {       // fused gather: the last CTA to retire signals the peers and waits for theirs (one kernel = one step)
+        __threadfence_system();        // this CTA's peer stores are ordered before its retirement
+        __syncthreads();
+        if (tid == 0) {
+            const uint32_t done = atomicAdd(P.ticket, 1u);
+            if (done == gridDim.x * gridDim.y - 1u) {
+                *P.ticket = 0u;
+                __threadfence_system();
+                peer_rendezvous(P.sync);
+            }
+        }
     }
 }
 
@@ -612,6 +798,9 @@ uint64_t padded_texels(int res, int mips) {
     for (int m = 0; m < mips; ++m) { const uint64_t p = (uint64_t)(res >> m) + 2; n += 6 * p * p; }
     return n;
 }
+// bytes of a sampling copy: the records plus one mip-0 row of slack, so that a footprint whose first record was clamped to
+// the last record (a non-finite direction: pixels without a surface carry a zero normal) still reads inside the allocation
+size_t padded_bytes(int res, int mips) { return (size_t)(padded_texels(res, mips) + (uint64_t)res + 3u) * 32u; }
 bool cube_desc_ok(const VqCubemap& c) {
     return c.ptr && c.res >= 1 && c.mips >= 1 && c.mips <= 16 && (c.res >> (c.mips - 1)) >= 1 &&
            padded_texels(c.res, c.mips) < (1ull << 30);
@@ -657,7 +846,7 @@ int ensure_bytes(void** ptr, size_t* have, size_t need) {
 
 int vq_forward_launch_multi(VqContext* ctx, const VqPerFrameData* pf, const VqPerViewLightingData* pv,
                             const VqGBuffer* gb, const VqEnvironmentMaps* env, const VqImage* outs, int n_outs,
-                            int dst_row_offset, int row_begin, int row_end, cudaStream_t stream) {
+                            int dst_row_offset, int row_begin, int row_end, const VqPeerSignal* sig, cudaStream_t stream) {
     VQ_REQUIRE(pf && pv && gb && env && outs, "null parameter block");
     VQ_REQUIRE(n_outs >= 1 && n_outs <= 8, "1..8 destinations");
     VQ_REQUIRE(vq_image_ok(gb->position_ao) && vq_image_ok(gb->normal_roughness) && vq_image_ok(gb->albedo_metalness), "bad image descriptor");
@@ -674,6 +863,7 @@ int vq_forward_launch_multi(VqContext* ctx, const VqPerFrameData* pf, const VqPe
                L.numSpotLights >= 0 && L.numSpotLights <= VQ_NUM_LIGHTS_SPOT &&
                L.numPointCasters >= 0 && L.numPointCasters <= VQ_NUM_SHADOWING_LIGHTS_POINT &&
                L.numSpotCasters >= 0 && L.numSpotCasters <= VQ_NUM_SHADOWING_LIGHTS_SPOT, "light counts exceed the cbuffer arrays");
+    VQ_REQUIRE(row_begin < row_end || !(sig && sig->n_ranks > 1), "a rendezvous needs a non-empty row range (the kernel runs it)");
     if (row_begin == row_end) return VQ_OK;
     VqScratchLock lock(ctx);           // env_* registration and the per-call tmp_* sampling copies are the context's
 
@@ -712,11 +902,11 @@ int vq_forward_launch_multi(VqContext* ctx, const VqPerFrameData* pf, const VqPe
             P.lut.q = (const float4*)ctx->env_lut;
         }
     } else {
-        rc = ensure_bytes(&ctx->tmp_diff, &ctx->tmp_diff_bytes, padded_texels(env->irradiance_diffuse.res, env->irradiance_diffuse.mips) * 32); if (rc) return rc;
+        rc = ensure_bytes(&ctx->tmp_diff, &ctx->tmp_diff_bytes, padded_bytes(env->irradiance_diffuse.res, env->irradiance_diffuse.mips)); if (rc) return rc;
         rc = pad_cube(env->irradiance_diffuse, (float4*)ctx->tmp_diff, stream); if (rc) return rc;
         fill_cube_view(env->irradiance_diffuse, (const float4*)ctx->tmp_diff, P.diff);
         if (!P.diffuseOnly) {
-            rc = ensure_bytes(&ctx->tmp_spec, &ctx->tmp_spec_bytes, padded_texels(env->irradiance_specular.res, env->irradiance_specular.mips) * 32); if (rc) return rc;
+            rc = ensure_bytes(&ctx->tmp_spec, &ctx->tmp_spec_bytes, padded_bytes(env->irradiance_specular.res, env->irradiance_specular.mips)); if (rc) return rc;
             rc = pad_cube(env->irradiance_specular, (float4*)ctx->tmp_spec, stream); if (rc) return rc;
             fill_cube_view(env->irradiance_specular, (const float4*)ctx->tmp_spec, P.spec);
             rc = ensure_bytes(&ctx->tmp_lut, &ctx->tmp_lut_bytes, lut_footprint_bytes(env->brdf_lut)); if (rc) return rc;
@@ -726,19 +916,41 @@ int vq_forward_launch_multi(VqContext* ctx, const VqPerFrameData* pf, const VqPe
     }
     P.rowBegin = row_begin; P.rows = row_end - row_begin; P.width = W;
 
-    // persistent grid: x = the row's 128-pixel tiles, y = row groups striding the rows; about FWD_CTAS_PER_SM CTAs per SM
+    rc = vq_fill_peer_sync(sig, &P.sync); if (rc) return rc;
+    VQ_REQUIRE(P.sync.n == 0 || n_outs > 1, "a rendezvous only makes sense with peer destinations");
+    P.ticket = P.sync.n > 1 ? vq_ticket_pair(ctx) : nullptr;
+    P.diffHalfN = 0.5f * (float)env->irradiance_diffuse.res;
+    P.diffMaxRec = (uint32_t)padded_texels(env->irradiance_diffuse.res, 1) - 1u;      // K1 samples mip 0 of the diffuse cube only
+    P.specMaxRec = P.diffuseOnly ? 0u : (uint32_t)padded_texels(env->irradiance_specular.res, env->irradiance_specular.mips) - 1u;
+
+    // persistent grid: x = the row's 256-pixel tiles, y = row groups striding the rows; about FWD_CTAS_PER_SM CTAs per SM
     const unsigned gx = (unsigned)((W + FWD_TILE - 1) / FWD_TILE);
     unsigned gy = (unsigned)(ctx->sm_count * FWD_CTAS_PER_SM) / gx;
     if (gy < 1) gy = 1;
     if (gy > (unsigned)P.rows) gy = (unsigned)P.rows;
     VQ_REQUIRE(gy <= 65535u, "frame too tall for the launch grid");
     const int nPl = P.hasEmissive ? 4 : 3;
-    const size_t smem = (size_t)FWD_STAGES * nPl * FWD_TILE * 16 + 2 * FWD_STAGES * sizeof(uint64_t) +
+    const size_t smem = (size_t)FWD_STAGES * nPl * FWD_PLANE + 2 * FWD_STAGES * sizeof(uint64_t) + 16 * 8 * sizeof(FaceRec) +
                        sizeof(SDir) + (size_t)(L.numPointLights + L.numPointCasters) * sizeof(SPoint) +
                        (size_t)(L.numSpotLights + L.numSpotCasters) * sizeof(SSpot);
     static_assert(sizeof(SPoint) == 32 && sizeof(SSpot) == 64 && sizeof(SDir) == 32, "shared light records are 16-byte multiples");
-    if (n_outs > 1) forward_kernel<true><<<dim3(gx, gy), FWD_TILE, smem, stream>>>(P);
-    else forward_kernel<false><<<dim3(gx, gy), FWD_TILE, smem, stream>>>(P);
+    const bool rot = P.sinB != 0.0f || P.cosB != 1.0f;            // yaw offset 0 is the common case: compiled out
+    static std::atomic<bool> attrSet{false};                      // process-wide and idempotent: every instantiation, once
+    if (!attrSet.load(std::memory_order_acquire)) {
+        VQ_CUDA_OK(cudaFuncSetAttribute(forward_kernel<false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024));
+        VQ_CUDA_OK(cudaFuncSetAttribute(forward_kernel<false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024));
+        VQ_CUDA_OK(cudaFuncSetAttribute(forward_kernel<true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024));
+        VQ_CUDA_OK(cudaFuncSetAttribute(forward_kernel<true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024));
+        attrSet.store(true, std::memory_order_release);
+    }
+    auto launch = [&](auto kernel) -> int {
+        kernel<<<dim3(gx, gy), FWD_THREADS, smem, stream>>>(P);
+        return VQ_OK;
+    };
+    VQ_REQUIRE(smem <= 96 * 1024, "light lists too long for the shared-memory staging");
+    if (n_outs > 1) rc = rot ? launch(forward_kernel<true, true>) : launch(forward_kernel<true, false>);
+    else rc = rot ? launch(forward_kernel<false, true>) : launch(forward_kernel<false, false>);
+    if (rc) return rc;
     return vq_check_launch("forward_lighting");
 }
 
@@ -746,7 +958,7 @@ int vq_forward_launch(VqContext* ctx, const VqPerFrameData* pf, const VqPerViewL
                       const VqGBuffer* gb, const VqEnvironmentMaps* env, VqImage out,
                       int row_begin, int row_end, cudaStream_t stream) {
     VQ_REQUIRE(gb && vq_image_ok(out) && out.height == gb->position_ao.height, "G-buffer planes and output must have the same size");
-    return vq_forward_launch_multi(ctx, pf, pv, gb, env, &out, 1, 0, row_begin, row_end, stream);
+    return vq_forward_launch_multi(ctx, pf, pv, gb, env, &out, 1, 0, row_begin, row_end, nullptr, stream);
 }
 
 extern "C" int vq_forward_lighting(VqContext* ctx, const VqPerFrameData* pf, const VqPerViewLightingData* pv,
@@ -760,7 +972,15 @@ extern "C" int vq_forward_lighting_multi(VqContext* ctx, const VqPerFrameData* p
                                          const VqGBuffer* gb, const VqEnvironmentMaps* env, const VqImage* outs, int n_outs,
                                          int dst_row_offset, int row_begin, int row_end, void* stream) {
     int rc = vq_enter(ctx); if (rc) return rc;
-    return vq_forward_launch_multi(ctx, pf, pv, gb, env, outs, n_outs, dst_row_offset, row_begin, row_end, (cudaStream_t)stream);
+    return vq_forward_launch_multi(ctx, pf, pv, gb, env, outs, n_outs, dst_row_offset, row_begin, row_end, nullptr, (cudaStream_t)stream);
+}
+
+// the same, with the cross-rank rendezvous run by the kernel's last CTA (VqPeerSignal): one kernel = shade + gather + barrier
+extern "C" int vq_forward_lighting_multi_signal(VqContext* ctx, const VqPerFrameData* pf, const VqPerViewLightingData* pv,
+                                                const VqGBuffer* gb, const VqEnvironmentMaps* env, const VqImage* outs, int n_outs,
+                                                int dst_row_offset, int row_begin, int row_end, const VqPeerSignal* signal, void* stream) {
+    int rc = vq_enter(ctx); if (rc) return rc;
+    return vq_forward_launch_multi(ctx, pf, pv, gb, env, outs, n_outs, dst_row_offset, row_begin, row_end, signal, (cudaStream_t)stream);
 }
 
 // The IBL cubemaps and the BRDF LUT are sampled from footprint-friendly copies (see CubeV, LutV).
@@ -773,12 +993,12 @@ extern "C" int vq_environment_prepare(VqContext* ctx, const VqEnvironmentMaps* e
     VQ_REQUIRE(cube_desc_ok(env->irradiance_diffuse), "bad cubemap descriptor (irradiance_diffuse)");
     VqScratchLock lock(ctx);
     ctx->env_valid = 0;
-    rc = ensure_bytes(&ctx->env_diff, &ctx->env_diff_bytes, padded_texels(env->irradiance_diffuse.res, env->irradiance_diffuse.mips) * 32); if (rc) return rc;
+    rc = ensure_bytes(&ctx->env_diff, &ctx->env_diff_bytes, padded_bytes(env->irradiance_diffuse.res, env->irradiance_diffuse.mips)); if (rc) return rc;
     rc = pad_cube(env->irradiance_diffuse, (float4*)ctx->env_diff, (cudaStream_t)stream); if (rc) return rc;
     ctx->env_key = *env;
     if (env->irradiance_specular.ptr) {
         VQ_REQUIRE(cube_desc_ok(env->irradiance_specular), "bad cubemap descriptor (irradiance_specular)");
-        rc = ensure_bytes(&ctx->env_spec, &ctx->env_spec_bytes, padded_texels(env->irradiance_specular.res, env->irradiance_specular.mips) * 32); if (rc) return rc;
+        rc = ensure_bytes(&ctx->env_spec, &ctx->env_spec_bytes, padded_bytes(env->irradiance_specular.res, env->irradiance_specular.mips)); if (rc) return rc;
         rc = pad_cube(env->irradiance_specular, (float4*)ctx->env_spec, (cudaStream_t)stream); if (rc) return rc;
     }
     if (env->brdf_lut.ptr) {
@@ -792,6 +1012,5 @@ extern "C" int vq_environment_prepare(VqContext* ctx, const VqEnvironmentMaps* e
 extern "C" int vq_environment_invalidate(VqContext* ctx) {
     if (!ctx) { vq_set_error("null context"); return VQ_ERR_INVALID_ARG; }
     VqScratchLock lock(ctx);
-    ctx->env_valid = 0;
-    return VQ_OK;
+    ctx->env_valid = 0;    return VQ_OK;
 }

@@ -127,102 +127,148 @@ __device__ __forceinline__ float radical_inverse_vdc(uint32_t bits) {      // Sh
     return (float)__brev(bits) * 2.3283064365386963e-10f;
 }
 
-struct SpecArgs {
-    PyrV hdri; float4* out;      // out already offset to this mip's face 0
-    float4* peers[7]; int nPeers; // further destinations (the other ranks' cubemaps, NVLink-mapped), same offset: fused gather
-    int n;                       // face edge of this mip
-    int rowBegin, texels;        // rows are flattened face*n + row inside this mip
-    float roughness; float dimX, dimY; int numSamples;
+// One launch covers everything a caller (or a rank) has to prefilter: the flattened (mip, face, row) ranges are cut at mip
+// boundaries into SEGMENTS, segments into UNITS of about equal cost, and a persistent grid pulls units off one global ticket:
+//   roughness > 0: unit = 8 texels, one warp each, lanes stride the 512 samples          (~19 k warp-instructions)
+//   roughness = 0: unit = 256 texels, one thread each (the mip-0 replay below)          (~17 k warp-instructions)
+// so there are no per-mip launches, no launch gaps and no per-mip tails (round 1: 9 launches, 81 % efficient at 8 GPUs).
+// A CTA sees its units in increasing order, so it rebuilds the tangent-space GGX table only when the mip changes.
+// Every finished texel is stored into up to 8 destination cubemaps (the other ranks' buffers over NVLink: fused gather);
+// the LAST CTA to retire can then run the cross-rank rendezvous itself (SpecSync), so a step is ONE kernel.
+struct SpecSeg { int n, rowBegin, texels; uint32_t unitBegin, mipOff; float roughness; };
+constexpr int SPEC_MAX_SEGS = 24;
+struct SpecWork {
+    PyrV hdri;
+    float4* outs[8]; int nOuts;   // packed cubemaps (mip 0 face 0 first): the local one, then the peers'
+    SpecSeg seg[SPEC_MAX_SEGS]; int nSeg; uint32_t totalUnits;
+    float dimX, dimY; int numSamples;
+    uint32_t* ticket;             // [0] next unit, [1] retired CTAs; both zero between launches (the last CTA resets them)
+    PeerSync sync;                // optional end-of-pass rendezvous through peer-mapped flag words (n == 0: none)
 };
+constexpr int SPEC_UNIT_WARP_TEXELS = IBL_WARPS, SPEC_UNIT_THREAD_TEXELS = IBL_THREADS;
+
+__device__ __forceinline__ void spec_store(const SpecWork& W, size_t texel, float4 o) {
+    W.outs[0][texel] = o;
+    for (int k = 1; k < W.nOuts; ++k) W.outs[k][texel] = o;
+}
 
 // Roughness 0 (mip 0): every sample is the same direction (H = N, L = N, source mip 0), so the texel is the
 // weighted mean of numSamples IDENTICAL terms. One THREAD per texel samples the HDRI once and then replays the
 // HLSL's running sums sequentially (4 independent FADD chains), so their fp32 rounding is reproduced exactly.
-__global__ void __launch_bounds__(IBL_THREADS) specular_mip0_kernel(const __grid_constant__ SpecArgs A) {
-    const int tx = blockIdx.x * IBL_THREADS + threadIdx.x;
-    if (tx >= A.texels) return;
-    const int fr = A.rowBegin + tx / A.n, px = tx % A.n;
-    const int face = fr / A.n, py = fr % A.n;
-    const float3 N = normalize_exact(cube_texel_dir(face, px, py, A.n));
+__device__ __forceinline__ float4 specular_texel_mip0(const SpecWork& W, int n, int face, int px, int py) {
+    const float3 N = normalize_exact(cube_texel_dir(face, px, py, n));
     const float3 H = normalize_exact(N);                       // ImportanceSampleGGX with sinTheta = 0
     const float3 Lv = H * (2.0f * dot(N, H)) - N;              // reflect(-V, H), V = N
     const float NdotL = saturate(dot(N, Lv));
     float4 o = make_float4(0.0f, 0.0f, 0.0f, 1.0f);
     if (NdotL > 0.0f) {
         float u, v; dir_to_equirect(Lv, u, v);
-        const float3 c = sample_equirect_level(A.hdri, u, v, 0.0f);
+        const float3 c = sample_equirect_level(W.hdri, u, v, 0.0f);
         const float t0 = c.x * NdotL, t1 = c.y * NdotL, t2 = c.z * NdotL;
         float a0 = 0.0f, a1 = 0.0f, a2 = 0.0f, aw = 0.0f;
-        for (int i = 0; i < A.numSamples; ++i) {
+        for (int i = 0; i < W.numSamples; ++i) {
             a0 = __fadd_rn(a0, t0); a1 = __fadd_rn(a1, t1); a2 = __fadd_rn(a2, t2); aw = __fadd_rn(aw, NdotL);
         }
         const float d = fmaxf(aw, 0.0001f);
         o = make_float4(a0 / d, a1 / d, a2 / d, 1.0f);
     }
-    A.out[(size_t)fr * A.n + px] = o;
-    for (int k = 0; k < A.nPeers; ++k) A.peers[k][(size_t)fr * A.n + px] = o;
+    return o;
 }
 
-__global__ void __launch_bounds__(IBL_THREADS) specular_prefilter_kernel(const __grid_constant__ SpecArgs A) {
-    extern __shared__ float4 sH[];       // tangent-space half vectors: (cos(phi)*sinT, sin(phi)*sinT, cosT, -)
-    // ImportanceSampleGGX (BRDF.hlsl:217-229): the part that depends only on (i, roughness)
-    for (int i = threadIdx.x; i < A.numSamples; i += IBL_THREADS) {
-        const float xi_x = (float)i / (float)A.numSamples;        // Hammersley, ShadingMath.hlsl:119-127
-        const float xi_y = radical_inverse_vdc((uint32_t)i);
-        const float a = A.roughness * A.roughness;
-        const float phi = 2.0f * PI * xi_x;
-        const float cosTheta = sqrtf((1.0f - xi_y) / (1.0f + (a * a - 1.0f) * xi_y));
-        const float sinTheta = sqrtf(1.0f - cosTheta * cosTheta);
-        float sp, cp; sincosf(phi, &sp, &cp);
-        sH[i] = make_float4(cp * sinTheta, sp * sinTheta, cosTheta, 0.0f);
-    }
-    __syncthreads();
-
-    const int lane = threadIdx.x & 31;
-    const int warpGlobal = blockIdx.x * IBL_WARPS + (threadIdx.x >> 5);
-    const int warpCount = gridDim.x * IBL_WARPS;
+// one warp, one texel: lanes stride the importance samples (sH = tangent-space half vectors of this roughness)
+__device__ __forceinline__ float4 specular_texel_warp(const SpecWork& W, const float4* __restrict__ sH, float roughness, int lane,
+                                                      int n, int face, int px, int py) {
     // Solid angle of one texel of a 6 x W0 x H0 cube — W0,H0 are the HDRI dims: the reference's quirk
-    const float fOmegaP = 4.0f * PI / (6.0f * A.dimX * A.dimY);
-    const float fN = (float)A.numSamples;
-    for (int tx = warpGlobal; tx < A.texels; tx += warpCount) {
-        const int fr = A.rowBegin + tx / A.n, px = tx % A.n;
-        const int face = fr / A.n, py = fr % A.n;
-        const float3 N = normalize_exact(cube_texel_dir(face, px, py, A.n));   // N = R = V
-        // tangent frame (BRDF.hlsl:231-234)
-        const float3 upv = fabsf(N.z) < 0.999f ? f3(0, 0, 1) : f3(1, 0, 0);
-        const float3 T = normalize_exact(cross(upv, N));
-        const float3 B = cross(N, T);
-        float3 acc = f3(0.0f); float wsum = 0.0f;
-        for (int i = lane; i < A.numSamples; i += 32) {
-            const float4 h = sH[i];
-            float3 H = T * h.x + B * h.y + N * h.z;
-            H = normalize(H);
-            const float VdotH = dot(N, H);
-            const float3 Lv = H * (2.0f * VdotH) - N;                          // reflect(-V, H)
-            const float NdotL = saturate(dot(N, Lv));
-            if (NdotL > 0.0f) {
-                const float NdotH = saturate(VdotH);
-                const float HdotV = NdotH;
-                // NormalDistributionGGX (BRDF.hlsl:65-79)
-                const float a = A.roughness * A.roughness, a2 = a * a;
-                const float t = fmaf(NdotH * NdotH, a2 - 1.0f, 1.0f);
-                const float dDen = PI * (t * t);
-                const float D = dDen < 0.000000000001f ? 1.0f : a2 * rcp_fast(dDen);
-                const float pdf = (D * NdotH) * rcp_fast(4.0f * HdotV);
-                // 0.5*log2(omegaS/omegaP) - 1 with omegaS = 1/max(N*pdf, 1e-5): one lg2 of the product, no divisions
-                const float mip = fmaxf(fmaf(-0.5f, __log2f(fmaxf(fN * pdf, 0.00001f) * fOmegaP), -1.0f), 0.0f);
-                float u, v; dir_to_equirect(Lv, u, v);
-                const float3 c = sample_equirect_level(A.hdri, u, v, mip);
-                acc.x = fmaf(c.x, NdotL, acc.x); acc.y = fmaf(c.y, NdotL, acc.y); acc.z = fmaf(c.z, NdotL, acc.z);
-                wsum += NdotL;
+    const float fOmegaP = 4.0f * PI / (6.0f * W.dimX * W.dimY);
+    const float fN = (float)W.numSamples;
+    const float3 N = normalize_exact(cube_texel_dir(face, px, py, n));   // N = R = V
+    // tangent frame (BRDF.hlsl:231-234)
+    const float3 upv = fabsf(N.z) < 0.999f ? f3(0, 0, 1) : f3(1, 0, 0);
+    const float3 T = normalize_exact(cross(upv, N));
+    const float3 B = cross(N, T);
+    const float a = roughness * roughness, a2 = a * a;
+    float3 acc = f3(0.0f); float wsum = 0.0f;
+    for (int i = lane; i < W.numSamples; i += 32) {
+        const float4 h = sH[i];
+        float3 H = T * h.x + B * h.y + N * h.z;
+        H = normalize(H);
+        const float VdotH = dot(N, H);
+        const float3 Lv = H * (2.0f * VdotH) - N;                          // reflect(-V, H)
+        const float NdotL = saturate(dot(N, Lv));
+        if (NdotL > 0.0f) {
+            const float NdotH = saturate(VdotH);
+            const float HdotV = NdotH;
+            // NormalDistributionGGX (BRDF.hlsl:65-79)
+            const float t = fmaf(NdotH * NdotH, a2 - 1.0f, 1.0f);
+            const float dDen = PI * (t * t);
+            const float D = dDen < 0.000000000001f ? 1.0f : a2 * rcp_fast(dDen);
+            const float pdf = (D * NdotH) * rcp_fast(4.0f * HdotV);
+            // 0.5*log2(omegaS/omegaP) - 1 with omegaS = 1/max(N*pdf, 1e-5): one lg2 of the product, no divisions
+            const float mip = fmaxf(fmaf(-0.5f, __log2f(fmaxf(fN * pdf, 0.00001f) * fOmegaP), -1.0f), 0.0f);
+            float u, v; dir_to_equirect(Lv, u, v);
+            const float3 c = sample_equirect_level(W.hdri, u, v, mip);
+            acc.x = fmaf(c.x, NdotL, acc.x); acc.y = fmaf(c.y, NdotL, acc.y); acc.z = fmaf(c.z, NdotL, acc.z);
+            wsum += NdotL;
+        }
+    }
+    acc.x = warp_sum(acc.x); acc.y = warp_sum(acc.y); acc.z = warp_sum(acc.z); wsum = warp_sum(wsum);
+    const float d = fmaxf(wsum, 0.0001f);
+    return make_float4(acc.x / d, acc.y / d, acc.z / d, 1.0f);
+}
+
+__global__ void __launch_bounds__(IBL_THREADS) specular_persistent_kernel(const __grid_constant__ SpecWork W) {
+    extern __shared__ float4 sH[];       // tangent-space half vectors of the current roughness: (cos(phi)*sinT, sin(phi)*sinT, cosT, -)
+    __shared__ uint32_t sUnit[2];        // double-buffered: the fetch of unit k+1 overlaps nothing it could race with
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    float tableRoughness = -1.0f;
+    int segIdx = 0, it = 0;
+    for (;; ++it) {
+        if (threadIdx.x == 0) sUnit[it & 1] = atomicAdd(W.ticket, 1u);
+        __syncthreads();
+        const uint32_t u = sUnit[it & 1];
+        if (u >= W.totalUnits) break;
+        while (segIdx + 1 < W.nSeg && u >= W.seg[segIdx + 1].unitBegin) ++segIdx;     // units (and so segments) only move forward
+        const SpecSeg S = W.seg[segIdx];
+        const uint32_t lu = u - S.unitBegin;
+        if (S.roughness == 0.0f) {
+            const int tx = (int)lu * SPEC_UNIT_THREAD_TEXELS + (int)threadIdx.x;
+            if (tx < S.texels) {
+                const int fr = S.rowBegin + tx / S.n, px = tx % S.n;
+                spec_store(W, (size_t)S.mipOff + (size_t)fr * S.n + px, specular_texel_mip0(W, S.n, fr / S.n, px, fr % S.n));
+            }
+        } else {
+            if (S.roughness != tableRoughness) {          // ImportanceSampleGGX (BRDF.hlsl:217-229): the part that depends only on (i, roughness)
+                __syncthreads();                          // nobody still reads the previous table
+                for (int i = threadIdx.x; i < W.numSamples; i += IBL_THREADS) {
+                    const float xi_x = (float)i / (float)W.numSamples;        // Hammersley, ShadingMath.hlsl:119-127
+                    const float xi_y = radical_inverse_vdc((uint32_t)i);
+                    const float a = S.roughness * S.roughness;
+                    const float phi = 2.0f * PI * xi_x;
+                    const float cosTheta = sqrtf((1.0f - xi_y) / (1.0f + (a * a - 1.0f) * xi_y));
+                    const float sinTheta = sqrtf(1.0f - cosTheta * cosTheta);
+                    float sp, cp; sincosf(phi, &sp, &cp);
+                    sH[i] = make_float4(cp * sinTheta, sp * sinTheta, cosTheta, 0.0f);
+                }
+                tableRoughness = S.roughness;
+                __syncthreads();
+            }
+            const int tx = (int)lu * SPEC_UNIT_WARP_TEXELS + warp;
+            if (tx < S.texels) {
+                const int fr = S.rowBegin + tx / S.n, px = tx % S.n;
+                const float4 o = specular_texel_warp(W, sH, S.roughness, lane, S.n, fr / S.n, px, fr % S.n);
+                if (lane == 0) spec_store(W, (size_t)S.mipOff + (size_t)fr * S.n + px, o);
             }
         }
-        acc.x = warp_sum(acc.x); acc.y = warp_sum(acc.y); acc.z = warp_sum(acc.z); wsum = warp_sum(wsum);
-        if (lane == 0) {
-            const float d = fmaxf(wsum, 0.0001f);
-            const float4 o = make_float4(acc.x / d, acc.y / d, acc.z / d, 1.0f);
-            A.out[(size_t)fr * A.n + px] = o;
-            for (int k = 0; k < A.nPeers; ++k) A.peers[k][(size_t)fr * A.n + px] = o;
+    }
+    // ---- retire: the last CTA resets the ticket and, when asked to, runs the cross-rank rendezvous ----
+    __threadfence_system();                                // this CTA's (peer) stores are ordered before its retirement
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        const uint32_t done = atomicAdd(W.ticket + 1, 1u);
+        if (done == gridDim.x - 1) {
+            W.ticket[0] = 0u; W.ticket[1] = 0u;            // every CTA has fetched its terminating ticket by now
+            __threadfence_system();                        // every CTA's stores happen-before the signals below (cumulativity)
+            peer_rendezvous(W.sync);
         }
     }
 }
@@ -334,8 +380,9 @@ extern "C" int vq_diffuse_irradiance(VqContext* ctx, const VqDiffuseIrradiancePa
     return vq_check_launch("diffuse_irradiance");
 }
 
+// ranges: n_ranges pairs [begin,end) of the flattened (mip, face, row) space, in increasing order and disjoint
 static int specular_launch(VqContext* ctx, VqPyramid hd, const VqCubemap* outs, int n_outs, int num_samples,
-                           int row_begin, int row_end, cudaStream_t stream) {
+                           const int* ranges, int n_ranges, const VqPeerSignal* sig, cudaStream_t stream) {
     VQ_REQUIRE(outs && n_outs >= 1 && n_outs <= 8, "1..8 destination cubemaps");
     const VqCubemap out = outs[0];
     VQ_REQUIRE(pyr_ok(hd), "bad HDRI pyramid descriptor");
@@ -344,45 +391,62 @@ static int specular_launch(VqContext* ctx, VqPyramid hd, const VqCubemap* outs, 
     for (int k = 1; k < n_outs; ++k)
         VQ_REQUIRE(outs[k].ptr && outs[k].res == out.res && outs[k].mips == out.mips, "every destination cubemap must have the same shape");
     VQ_REQUIRE(num_samples >= 1 && num_samples <= 8192, "num_samples out of range");
+    VQ_REQUIRE(ranges && n_ranges >= 1, "no row ranges");
     const int totalRows = vq_cubemap_row_count(out.res, out.mips);
-    VQ_REQUIRE(row_begin >= 0 && row_end <= totalRows && row_begin <= row_end, "row range out of bounds");
-    int mipRow0 = 0;
-    for (int m = 0; m < out.mips; ++m) {
-        const int n = out.res >> m, rows = 6 * n;
-        const int b = row_begin > mipRow0 ? row_begin : mipRow0;
-        const int e = row_end < mipRow0 + rows ? row_end : mipRow0 + rows;
-        if (b < e) {
-            SpecArgs A;
-            A.hdri = make_pyr(hd);
-            const uint64_t mipOff = vq_cubemap_offset(out.res, m, 0);
-            A.out = (float4*)out.ptr + mipOff;
-            A.nPeers = n_outs - 1;
-            for (int k = 0; k < 7; ++k) A.peers[k] = k + 1 < n_outs ? (float4*)outs[k + 1].ptr + mipOff : nullptr;
-            A.n = n; A.rowBegin = b - mipRow0; A.texels = (e - b) * n;
-            A.roughness = (float)m / (float)(out.mips - 1);          // EnvironmentMapRendering.cpp:432
-            A.dimX = (float)hd.width; A.dimY = (float)hd.height;     // EnvironmentMapRendering.cpp:433-434
-            A.numSamples = num_samples;
-            const size_t smem = (size_t)num_samples * sizeof(float4);
-            if (smem > 48 * 1024) VQ_CUDA_OK(cudaFuncSetAttribute(specular_prefilter_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-            if (A.roughness == 0.0f) {
-                specular_mip0_kernel<<<(A.texels + IBL_THREADS - 1) / IBL_THREADS, IBL_THREADS, 0, stream>>>(A);
-            } else {
-                int blocks = (A.texels + IBL_WARPS - 1) / IBL_WARPS;
-                const int cap = ctx->sm_count * 8;
-                if (blocks > cap) blocks = cap;
-                specular_prefilter_kernel<<<blocks, IBL_THREADS, smem, stream>>>(A);
+    SpecWork W;
+    memset(&W, 0, sizeof(W));
+    int prevEnd = 0;
+    uint32_t units = 0;
+    for (int r = 0; r < n_ranges; ++r) {
+        const int row_begin = ranges[2 * r], row_end = ranges[2 * r + 1];
+        VQ_REQUIRE(row_begin >= prevEnd && row_end <= totalRows && row_begin <= row_end, "row ranges must be increasing, disjoint and inside the cubemap");
+        prevEnd = row_end;
+        int mipRow0 = 0;
+        for (int m = 0; m < out.mips; ++m) {
+            const int n = out.res >> m, rows = 6 * n;
+            const int b = row_begin > mipRow0 ? row_begin : mipRow0;
+            const int e = row_end < mipRow0 + rows ? row_end : mipRow0 + rows;
+            if (b < e) {
+                VQ_REQUIRE(W.nSeg < SPEC_MAX_SEGS, "too many (range, mip) segments for one launch");
+                SpecSeg& S = W.seg[W.nSeg++];
+                S.n = n; S.rowBegin = b - mipRow0; S.texels = (e - b) * n;
+                S.mipOff = (uint32_t)vq_cubemap_offset(out.res, m, 0);
+                S.roughness = (float)m / (float)(out.mips - 1);          // EnvironmentMapRendering.cpp:432
+                S.unitBegin = units;
+                const int per = S.roughness == 0.0f ? SPEC_UNIT_THREAD_TEXELS : SPEC_UNIT_WARP_TEXELS;
+                units += (uint32_t)((S.texels + per - 1) / per);
             }
-            int rc = vq_check_launch("specular_prefilter"); if (rc) return rc;
+            mipRow0 += rows;
         }
-        mipRow0 += rows;
     }
-    return VQ_OK;
+    { const int rcs = vq_fill_peer_sync(sig, &W.sync); if (rcs) return rcs; }
+    if (units == 0 && W.sync.n == 0) return VQ_OK;
+    // segments must be visited in increasing unit order with mips that only change forward per CTA: sort is implied by the
+    // increasing ranges; roughness 0 segments may sit between others, which only costs a table rebuild
+    W.hdri = make_pyr(hd);
+    for (int k = 0; k < n_outs; ++k) W.outs[k] = (float4*)outs[k].ptr;
+    W.nOuts = n_outs; W.totalUnits = units;
+    W.dimX = (float)hd.width; W.dimY = (float)hd.height;     // EnvironmentMapRendering.cpp:433-434
+    W.numSamples = num_samples;
+    W.ticket = vq_ticket_pair(ctx);
+    const size_t smem = (size_t)num_samples * sizeof(float4);
+    if (smem > 48 * 1024) VQ_CUDA_OK(cudaFuncSetAttribute(specular_persistent_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    // persistent grid: as many CTAs as fit (8 per SM at 8 KB of table), never more than there are units
+    int perSm = 0;
+    VQ_CUDA_OK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&perSm, specular_persistent_kernel, IBL_THREADS, smem));
+    if (perSm < 1) perSm = 1;
+    unsigned blocks = (unsigned)(ctx->sm_count * perSm);
+    if (blocks > units) blocks = units > 0 ? units : 1u;
+    specular_persistent_kernel<<<blocks, IBL_THREADS, smem, stream>>>(W);
+    return vq_check_launch("specular_prefilter");
 }
 
 extern "C" int vq_specular_prefilter(VqContext* ctx, VqPyramid hd, VqCubemap out, int num_samples,
                                      int row_begin, int row_end, void* stream) {
     int rc = vq_enter(ctx); if (rc) return rc;
-    return specular_launch(ctx, hd, &out, 1, num_samples, row_begin, row_end, (cudaStream_t)stream);
+    const int range[2] = {row_begin, row_end};
+    if (row_begin == row_end && row_begin >= 0) return VQ_OK;
+    return specular_launch(ctx, hd, &out, 1, num_samples, range, 1, nullptr, (cudaStream_t)stream);
 }
 
 // K3 fused with the gather of the row blocks (multi-GPU): every prefiltered texel is stored into ALL n_outs cubemaps —
@@ -391,7 +455,17 @@ extern "C" int vq_specular_prefilter(VqContext* ctx, VqPyramid hd, VqCubemap out
 extern "C" int vq_specular_prefilter_multi(VqContext* ctx, VqPyramid hd, const VqCubemap* outs, int n_outs, int num_samples,
                                            int row_begin, int row_end, void* stream) {
     int rc = vq_enter(ctx); if (rc) return rc;
-    return specular_launch(ctx, hd, outs, n_outs, num_samples, row_begin, row_end, (cudaStream_t)stream);
+    const int range[2] = {row_begin, row_end};
+    if (row_begin == row_end && row_begin >= 0) return VQ_OK;
+    return specular_launch(ctx, hd, outs, n_outs, num_samples, range, 1, nullptr, (cudaStream_t)stream);
+}
+
+// Everything one rank prefilters in a step — several row ranges, all destinations, optionally the cross-rank rendezvous —
+// as ONE persistent launch.
+extern "C" int vq_specular_prefilter_ranges(VqContext* ctx, VqPyramid hd, const VqCubemap* outs, int n_outs, int num_samples,
+                                            const int* row_ranges, int n_ranges, const VqPeerSignal* signal, void* stream) {
+    int rc = vq_enter(ctx); if (rc) return rc;
+    return specular_launch(ctx, hd, outs, n_outs, num_samples, row_ranges, n_ranges, signal, (cudaStream_t)stream);
 }
 
 extern "C" int vq_brdf_integration_lut(VqContext* ctx, VqImage out, int num_samples, int row_begin, int row_end, void* stream) {

@@ -127,7 +127,7 @@ class InterleavedSpecularPlan:
         """flattened (mip, face, row) ranges this rank computes"""
         out = [(r0 + rank * k, r0 + (rank + 1) * k) for (_, r0, k, _) in self.split]
         out += [(r0, r0 + rows) for (_, r0, rows, _) in self.replicated]
-        return [(a, b) for a, b in out if b > a]
+        return sorted((a, b) for a, b in out if b > a)     # increasing and disjoint: what vq_specular_prefilter_ranges takes
 
     def texel_range(self, row_a: int, row_b: int):
         return specular_row_to_texel(self.res, self.mips, row_a), specular_row_to_texel(self.res, self.mips, row_b)

@@ -8,7 +8,7 @@ from __future__ import annotations
 import ctypes as C
 import numpy as np
 
-from . import (PerFrameData, PerViewLightingData, TonemapperParams, COLOR_SPACE_REC_709, DISPLAY_CURVE_SRGB)
+from .shader_data import (PerFrameData, PerViewLightingData, TonemapperParams, COLOR_SPACE_REC_709, DISPLAY_CURVE_SRGB)
 
 SEED_BASE = 0x5EED0000
 
@@ -215,7 +215,7 @@ def materials(n: int = 4, tex_res: int = 256, seed: int = SEED_BASE + 11, unifor
     2 constants only (all SRVs null), 3 albedo+normal with uv tiling and a non-square, non-pow2 albedo.
     uniform=True gives every map of material 0 the same tex_res^2 size (how shipped material sets look); the default mixes
     sizes and aspect ratios to exercise the sampler. Returns (list[MaterialData], list[dict slot -> level-0 uint8 array or None])."""
-    from . import MaterialData, TEXCFG_DIFFUSE, TEXCFG_NORMAL, TEXCFG_AO, TEXCFG_ROUGHNESS, TEXCFG_METALLIC, \
+    from .shader_data import MaterialData, TEXCFG_DIFFUSE, TEXCFG_NORMAL, TEXCFG_AO, TEXCFG_ROUGHNESS, TEXCFG_METALLIC, \
         TEXCFG_EMISSIVE, TEXCFG_ORM, MATERIAL_TEXTURE_SLOTS
     rng = np.random.default_rng(seed)
     mats, texs = [], []
