@@ -430,7 +430,7 @@ VQ_API int vq_apply_reflections(VqContext* ctx, VqImage scene_color, VqImage ref
  *     level above; `levels` receives n_levels (<= vq_depth_pyramid_level_count = 1 + floor(log2(max(w,h))), at most 13)
  *     tightly packed levels, vq_depth_pyramid_texel_count() floats in total. The padded-domain levels ping-pong through scratch
  *     owned by the context (like vq_image_resize): calls on ONE context must be issued on one stream at a time.
- *   STATUS: compiled for sm_100a and checked against the oracle's semantics on paper only — not yet run on a GPU.
+ *   Parity on B200: tests/test_shadow_gpu.py (15 tests against the oracle, itself pinned to the reference's shader text).
  * ------------------------------------------------------------------------------------------ */
 typedef struct VqShadowMaps {
     const void* point_cubes;     int32_t point_res;

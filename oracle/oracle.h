@@ -148,7 +148,8 @@ void   DiffuseIrradianceAngles(float step, int n_phi, int n_theta, std::vector<f
 float4 DiffuseIrradiance_PSMain(const Pyramid& hdri, float3 lookDir, const std::vector<float>& phis,
                                 const std::vector<float>& thetas, int srcMip, bool f64Accum = false);   // :112-163
 float4 SpecularIrradiance_PSMain(const Pyramid& hdri, float3 lookDir, float Roughness,
-                                 float2 TextureDimensionsLOD0, uint32_t numSamples);  // :168-223
+                                 float2 TextureDimensionsLOD0, uint32_t numSamples,
+                                 float sampleLengthScale = 1.0f);  // :168-223
 
 // ---- post chain --------------------------------------------------------------------------------
 float3 Tonemap_Reinhard(float3 c);                                                    // Tonemapper.hlsl:24-27

@@ -193,7 +193,8 @@ void orc_specular_prefilter_texels(const float* pyramid, int w, int h, int level
 
 // Conditioning probe for K3 (test infrastructure): how much does the ORACLE's own result move when the texel's (unit) look
 // direction is tilted by a few ulps (+- eps ADDED to each component: an absolute tilt of eps radians, also at the poles where a
-// relative change of the small components would vanish)? out[k] = max over the six tilts and the colour channels
+// relative change of the small components would vanish), or when the length of its un-normalised sample vectors is off by
+// 1-4 ulps (the asin(-L.y) of the equirect map is singular at the poles)? out[k] = max over all probes and colour channels
 // of |result' - result|. Near the poles of the equirect map (u = atan2(z,x) is singular there) a 1e-7 change of a sample
 // direction moves the sample by whole texels, so two correct fp32 implementations cannot agree to 1e-4 on an HDRI that
 // carries per-texel detail in its pole rows; the full-size parity test widens its bound by this measured sensitivity.
@@ -210,14 +211,20 @@ void orc_specular_prefilter_sensitivity(const float* pyramid, int w, int h, int 
         const float2 dim = make2((float)w, (float)h);
         const float4 base = SpecularIrradiance_PSMain(p, d, roughness, dim, (uint32_t)num_samples);
         float s = 0.0f;
+        auto upd = [&](const float4& r) {
+            s = std::fmax(s, std::fmax(std::fabs(r.x - base.x), std::fmax(std::fabs(r.y - base.y), std::fabs(r.z - base.z))));
+        };
         for (int c = 0; c < 3; ++c)
             for (int sgn = -1; sgn <= 1; sgn += 2) {
                 float3 e = d;
                 const float f = (float)sgn * rel_eps;
                 if (c == 0) e.x += f; else if (c == 1) e.y += f; else e.z += f;
-                const float4 r = SpecularIrradiance_PSMain(p, e, roughness, dim, (uint32_t)num_samples);
-                s = std::fmax(s, std::fmax(std::fabs(r.x - base.x), std::fmax(std::fabs(r.y - base.y), std::fabs(r.z - base.z))));
+                upd(SpecularIrradiance_PSMain(p, e, roughness, dim, (uint32_t)num_samples));
             }
+        // the length of the un-normalised sample vectors, +-1, 2 and 4 ulps (see SpecularIrradiance_PSMain)
+        for (int k2 = 1; k2 <= 4; k2 *= 2)
+            for (int sgn = -1; sgn <= 1; sgn += 2)
+                upd(SpecularIrradiance_PSMain(p, d, roughness, dim, (uint32_t)num_samples, 1.0f + (float)(sgn * k2) * 5.9604645e-8f));
         out[k] = s;
     });
 }

@@ -83,8 +83,12 @@ float4 DiffuseIrradiance_PSMain(const Pyramid& hdri, float3 lookDir, const std::
 }
 
 // CubemapConvolution.hlsl:168-223
+// sampleLengthScale (test infrastructure, 1 = the reference): scales the UN-normalised sample vector L before it is mapped to
+// the equirect uv. The reference feeds reflect(-V, H) straight into asin(-L.y): |L| = 1 only up to rounding, and near a pole
+// (|L.y| -> 1, infinite slope of asin) one ulp of |L| moves v by a fraction of a texel row — with the WRAP-in-v sampler blending
+// in the opposite pole's row. The conditioning probe of the full-size parity test varies exactly this degree of freedom.
 float4 SpecularIrradiance_PSMain(const Pyramid& hdri, float3 lookDir, float Roughness,
-                                 float2 TextureDimensionsLOD0, uint32_t NUM_SAMPLES) {
+                                 float2 TextureDimensionsLOD0, uint32_t NUM_SAMPLES, float sampleLengthScale) {
     const float3 N = normalize(lookDir);
     const float3 R = N;
     const float3 V = R;
@@ -105,7 +109,8 @@ float4 SpecularIrradiance_PSMain(const Pyramid& hdri, float3 lookDir, float Roug
             const float fMipBias = -1.0f;
             const float fMipLevel = Roughness == 0.0f ? 0.0f
                                   : std::fmax(0.5f * std::log2(fOmegaS / fOmegaP) + fMipBias, 0.0f);
-            prefilteredColor += xyz(SampleEquirectLevel(hdri, DirectionToEquirectUV(L), fMipLevel)) * NdotL;
+            const float3 Ls = sampleLengthScale == 1.0f ? L : L * sampleLengthScale;
+            prefilteredColor += xyz(SampleEquirectLevel(hdri, DirectionToEquirectUV(Ls), fMipLevel)) * NdotL;
             totalWeight += NdotL;
         }
     }

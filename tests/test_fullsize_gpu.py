@@ -119,13 +119,15 @@ def test_c5_specular_full_face_and_random_texels(ctx, vq, orc):
     hp = host(pyr_t)
     assert np.isfinite(got).all() and (got[:, 3] == 1.0).all()
     def check(name, ids, max_frac_relaxed):
-        """|delta| <= 1e-4 * max(1,|ref|) + 2 * S, S = how far the ORACLE's own texel moves when its look direction is tilted by
-        4.8e-7 rad (2^-21: a few ulps; oracle_capi.cpp: orc_specular_prefilter_sensitivity). S is ~1e-6 except where an importance
-        sample lands within a texel of a POLE of the equirect map: there u = atan2(z, x) is singular and the WRAP-in-v filter blends in
-        the opposite pole's row, so the reference's own result steps by up to 2e-3 under a 1-ulp change of its input (measured:
-        profiles/r02_diag_fullsize.txt; real HDRIs are constant along their pole rows, the synthetic one carries +-5 % per-texel
-        noise there). Two correct fp32 evaluations cannot agree better than that; everywhere else the bound is the strict one, and
-        the texels that get any noticeable relaxation (S > 2e-5) must stay a small minority."""
+        """|delta| <= 1e-4 * max(1,|ref|) + 2 * S, S = how far the ORACLE's own texel moves when (a) its look direction is tilted by
+        4.8e-7 rad (2^-21: a few ulps) or (b) the length of its un-normalised sample vectors is off by 1-4 ulps
+        (oracle_capi.cpp: orc_specular_prefilter_sensitivity). S is ~1e-6 except where an importance sample lands within a few
+        texels of a POLE of the equirect map: the reference feeds reflect(-V, H) — unit length only up to rounding — into
+        v = asin(-L.y)/pi + 0.5, whose slope is infinite at the poles, and its WRAP-in-v sampler then blends in the OPPOSITE pole's
+        row: one ulp of |L| moves the blend weight by ~0.15 and the texel by 4e-4 (measured: profiles/r02_diag_fullsize.txt, up
+        to 2e-3 on the 5 texels around each pole of mips 1-2). Two correct fp32 evaluations cannot agree better than the
+        reference agrees with itself; everywhere else the bound is the strict one, and
+        the texels that get any noticeable relaxation (S > 2e-5 * max(1,|ref|)) must stay a small minority."""
         ref = orc.specular_prefilter_texels(hp, hw, hh, levels, res, mips, ids)
         sens = orc.specular_prefilter_sensitivity(hp, hw, hh, levels, res, mips, ids)
         g = got[ids]
@@ -133,7 +135,7 @@ def test_c5_specular_full_face_and_random_texels(ctx, vq, orc):
         d = np.abs(g.astype(np.float64) - ref).max(axis=1)
         scale = np.maximum(1.0, np.abs(ref).max(axis=1))
         bound = 1e-4 * scale + 2.0 * sens
-        relaxed = sens > 2e-5
+        relaxed = sens > 2e-5 * scale                 # a relaxation worth more than a fifth of the strict bound
         r = report(name, g, ref)
         r.update(max_sensitivity=float(sens.max()), frac_relaxed=float(relaxed.mean()),
                  max_scaled_where_strict=float((d / scale)[~relaxed].max()), frac_within_strict=float((d <= 1e-4 * scale).mean()))

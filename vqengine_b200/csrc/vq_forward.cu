@@ -173,36 +173,6 @@ __global__ void __launch_bounds__(256) lut_footprint_kernel(const float2* __rest
 // an aligned 64-bit register pair: one packed instruction does the work of two at one issue slot. Lane .x of every f2
 // is pixel A (column x0 + tid), lane .y pixel B (column x0 + 128 + tid). MUFU, compares, selects and min/max have no packed
 // form and stay per lane (profiles/r02_forward_*: 80 -> 42 issue slots per pixel and light).
-}  // namespace
-namespace vq {
-struct f2 { float2 v; };
-__device__ __forceinline__ f2 mk(float a, float b) { f2 r; r.v = make_float2(a, b); return r; }
-__device__ __forceinline__ f2 bc(float a) { return mk(a, a); }
-__device__ __forceinline__ f2 operator+(f2 a, f2 b) { f2 r; r.v = __fadd2_rn(a.v, b.v); return r; }
-__device__ __forceinline__ f2 operator*(f2 a, f2 b) { f2 r; r.v = __fmul2_rn(a.v, b.v); return r; }
-__device__ __forceinline__ f2 operator-(f2 a, f2 b) { f2 r; r.v = __fadd2_rn(a.v, make_float2(-b.v.x, -b.v.y)); return r; }
-__device__ __forceinline__ f2 fma2(f2 a, f2 b, f2 c) { f2 r; r.v = __ffma2_rn(a.v, b.v, c.v); return r; }
-// The intrinsics above may be contracted into FFMA2 by the compiler (wanted). Where the oracle's operation order decides a
-// DISCONTINUITY (|L-P|^2 against the light's range) or feeds a cancellation (a^2 - 1), every operation must round on its own.
-// ptxas contracts f32x2 multiply/add pairs even when both carry an explicit .rn (checked in SASS; it also sees through
-// fma(a,b,-0)), so the unfused forms keep the PRODUCTS packed (a lone FMUL2 is correctly rounded) and do the additions with
-// scalar __fadd_rn, which is never contracted.
-__device__ __forceinline__ f2 mul_rn2(f2 a, f2 b) {
-    f2 r;
-    asm("{\n\t.reg .b64 ta, tb, tc;\n\tmov.b64 ta, {%2,%3};\n\tmov.b64 tb, {%4,%5};\n\tmul.rn.f32x2 tc, ta, tb;\n\tmov.b64 {%0,%1}, tc;\n\t}"
-        : "=f"(r.v.x), "=f"(r.v.y) : "f"(a.v.x), "f"(a.v.y), "f"(b.v.x), "f"(b.v.y));
-    return r;
-}
-__device__ __forceinline__ f2 add_rn2(f2 a, f2 b) { return mk(__fadd_rn(a.v.x, b.v.x), __fadd_rn(a.v.y, b.v.y)); }
-__device__ __forceinline__ f2 rsq2(f2 a) { return mk(rsqrt_fast(a.v.x), rsqrt_fast(a.v.y)); }
-__device__ __forceinline__ f2 rcp2(f2 a) { return mk(rcp_fast(a.v.x), rcp_fast(a.v.y)); }
-__device__ __forceinline__ f2 sat2(f2 a) { return mk(saturate(a.v.x), saturate(a.v.y)); }
-__device__ __forceinline__ f2 mulsat2(f2 a, f2 b) { return mk(saturate(a.v.x * b.v.x), saturate(a.v.y * b.v.y)); }   // FMUL.SAT x2
-__device__ __forceinline__ f2 max2(f2 a, float m) { return mk(fmaxf(a.v.x, m), fmaxf(a.v.y, m)); }
-__device__ __forceinline__ f2 dot3(f2 ax, f2 ay, f2 az, f2 bx, f2 by, f2 bz) { return fma2(az, bz, fma2(ay, by, ax * bx)); }
-
-}  // namespace vq
-namespace {
 
 // ---------------------------------------------------------------------------------------------
 // per-pixel-pair shading state with everything that does not depend on the light hoisted
@@ -509,6 +479,11 @@ __device__ __forceinline__ F8 ldg256(const float4* p) {             // 32-byte a
             : "=f"(r.a.x), "=f"(r.a.y), "=f"(r.a.z), "=f"(r.a.w), "=f"(r.b.x), "=f"(r.b.y), "=f"(r.b.z), "=f"(r.b.w) : "l"(p));
     return r;
 }
+// A/B on B200 (profiles/r02_forward_variants_b.txt): a lane-pair variant — column-major records so that the two rows of a footprint
+// are adjacent, lanes 2q/2q+1 fetching one footprint together and swapping halves with shuffles — touches fewer 128-byte lines per
+// instruction (tools/ubench_gather.cu: 16 lines cost 20 L1 wavefronts, 32 cost 33) but measured 268 us against 258 us for this
+// form: the five shuffles per footprint and the lost line sharing between neighbouring lanes (row-major records of neighbouring
+// pixels share lines) cost more than the pairing saves.
 struct CubeLoad { F8 r0, r1; float fx, fy; };                     // rows j0 and j0+1: {t(i0), t(i0+1)} each
 // A gather is split into "issue" (address + the 256-bit loads) and "finish" (the lerps) so that the loads of several
 // gathers are in flight before the first one is consumed.
@@ -714,10 +689,12 @@ __global__ void __launch_bounds__(FWD_THREADS, FWD_CTAS_PER_SM) forward_kernel(c
         }
         mbar_wait(fullBar(st), use & 1u);                         // this tile has landed
         const int y = P.rowBegin + row;
-        if (validA) {
+        {   // every lane shades (the warp votes below need whole warps): pixels off the end of a ragged row are aliased to the
+            // row's last pixel and simply not stored
             Px2 s;
-            s.texA = stage0 + (uint32_t)st * stageBytes + (uint32_t)tid * 16u;
-            s.texB = validB ? s.texA + FWD_THREADS * 16u : s.texA;   // off the row: shade pixel A twice, store it once
+            const uint32_t stageBase = stage0 + (uint32_t)st * stageBytes;
+            s.texA = stageBase + (uint32_t)(min(xA, P.width - 1) - x0) * 16u;
+            s.texB = stageBase + (uint32_t)(min(xB, P.width - 1) - x0) * 16u;
             f2 roughness, ao;
             {
                 const float4 pa = lds128(s.texA), pb = lds128(s.texB);
@@ -764,16 +741,18 @@ __global__ void __launch_bounds__(FWD_THREADS, FWD_CTAS_PER_SM) forward_kernel(c
             const float4 oA = finish_pixel<ROT>(P, sFace, s.texA, f3(s.Vx.v.x, s.Vy.v.x, s.Vz.v.x), nsnv.v.x,
                                                 f3(Nrx.v.x, Nry.v.x, Nrz.v.x), roughness.v.x, ao.v.x, f3(acc.ax.v.x, acc.ay.v.x, acc.az.v.x), f3(acc.bx.v.x, acc.by.v.x, acc.bz.v.x),
                                                 f3(acc.cx.v.x, acc.cy.v.x, acc.cz.v.x));
-            {   // one STG.128 per destination; peer destinations are mapped NVLink addresses (fused compute + gather)
+            if (validA) {   // one STG.128 per destination; peer destinations are mapped NVLink addresses (fused compute + gather)
                 if (MULTI) { for (int q = 0; q < P.nOut; ++q) st_stream(P.outs[q].row(P.dstRowOffset + y) + xA, oA); }
                 else st_stream_hint(P.outs[0].row(P.dstRowOffset + y) + xA, oA, l2_evict_first_policy());
             }
-            if (validB) {
+            {
                 const float4 oB = finish_pixel<ROT>(P, sFace, s.texB, f3(s.Vx.v.y, s.Vy.v.y, s.Vz.v.y), nsnv.v.y,
                                                     f3(Nrx.v.y, Nry.v.y, Nrz.v.y), roughness.v.y, ao.v.y, f3(acc.ax.v.y, acc.ay.v.y, acc.az.v.y), f3(acc.bx.v.y, acc.by.v.y, acc.bz.v.y),
                                                     f3(acc.cx.v.y, acc.cy.v.y, acc.cz.v.y));
-                if (MULTI) { for (int q = 0; q < P.nOut; ++q) st_stream(P.outs[q].row(P.dstRowOffset + y) + xB, oB); }
-                else st_stream_hint(P.outs[0].row(P.dstRowOffset + y) + xB, oB, l2_evict_first_policy());
+                if (validB) {
+                    if (MULTI) { for (int q = 0; q < P.nOut; ++q) st_stream(P.outs[q].row(P.dstRowOffset + y) + xB, oB); }
+                    else st_stream_hint(P.outs[0].row(P.dstRowOffset + y) + xB, oB, l2_evict_first_policy());
+                }
             }
         }
         mbar_arrive(emptyBar(st));                               // this thread is done with the stage
@@ -965,6 +944,7 @@ extern "C" int vq_forward_lighting(VqContext* ctx, const VqPerFrameData* pf, con
                                    const VqGBuffer* gb, const VqEnvironmentMaps* env, VqImage out,
                                    int row_begin, int row_end, void* stream) {
     int rc = vq_enter(ctx); if (rc) return rc;
+    VQ_MARK("RenderSceneColor");
     return vq_forward_launch(ctx, pf, pv, gb, env, out, row_begin, row_end, (cudaStream_t)stream);
 }
 
@@ -972,6 +952,7 @@ extern "C" int vq_forward_lighting_multi(VqContext* ctx, const VqPerFrameData* p
                                          const VqGBuffer* gb, const VqEnvironmentMaps* env, const VqImage* outs, int n_outs,
                                          int dst_row_offset, int row_begin, int row_end, void* stream) {
     int rc = vq_enter(ctx); if (rc) return rc;
+    VQ_MARK("RenderSceneColor");
     return vq_forward_launch_multi(ctx, pf, pv, gb, env, outs, n_outs, dst_row_offset, row_begin, row_end, nullptr, (cudaStream_t)stream);
 }
 
@@ -980,6 +961,7 @@ extern "C" int vq_forward_lighting_multi_signal(VqContext* ctx, const VqPerFrame
                                                 const VqGBuffer* gb, const VqEnvironmentMaps* env, const VqImage* outs, int n_outs,
                                                 int dst_row_offset, int row_begin, int row_end, const VqPeerSignal* signal, void* stream) {
     int rc = vq_enter(ctx); if (rc) return rc;
+    VQ_MARK("RenderSceneColor");
     return vq_forward_launch_multi(ctx, pf, pv, gb, env, outs, n_outs, dst_row_offset, row_begin, row_end, signal, (cudaStream_t)stream);
 }
 
@@ -989,6 +971,7 @@ extern "C" int vq_forward_lighting_multi_signal(VqContext* ctx, const VqPerFrame
 // Without it vq_forward_lighting rebuilds the copies on every call (always correct, slower: see tools/perf_forward.py).
 extern "C" int vq_environment_prepare(VqContext* ctx, const VqEnvironmentMaps* env, void* stream) {
     int rc = vq_enter(ctx); if (rc) return rc;
+    VQ_MARK("TransitionForSceneRendering");
     VQ_REQUIRE(env, "env is null");
     VQ_REQUIRE(cube_desc_ok(env->irradiance_diffuse), "bad cubemap descriptor (irradiance_diffuse)");
     VqScratchLock lock(ctx);

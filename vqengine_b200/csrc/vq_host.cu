@@ -11,6 +11,7 @@ constexpr int kMaxChunks = 16;
 extern "C" int vq_forward_lighting_host(VqContext* ctx, const VqPerFrameData* pf, const VqPerViewLightingData* pv,
                                         const VqGBuffer* hgb, const VqEnvironmentMaps* denv, VqImage hout) {
     int rc = vq_enter(ctx); if (rc) return rc;
+    VQ_MARK("RenderSceneColor");
     VQ_REQUIRE(pf && pv && hgb && denv, "null parameter block");
     VQ_REQUIRE(vq_image_ok(hgb->position_ao) && vq_image_ok(hgb->normal_roughness) && vq_image_ok(hgb->albedo_metalness) && vq_image_ok(hout),
                "bad host image descriptor");

@@ -333,6 +333,7 @@ __global__ void __launch_bounds__(256) brdf_lut_kernel(const __grid_constant__ L
 // =============================================================================================
 extern "C" int vq_hdri_build_mips(VqContext* ctx, VqPyramid hd, void* stream) {
     int rc = vq_enter(ctx); if (rc) return rc;
+    VQ_MARK("EnvironmentMap");
     VQ_REQUIRE(pyr_ok(hd), "bad HDRI pyramid descriptor");
     if (hd.levels == 1) return VQ_OK;
     // one launch for the whole chain when the image fits the SPD kernel (<= 4096^2, <= 12 destination levels)
@@ -352,6 +353,7 @@ extern "C" int vq_hdri_build_mips(VqContext* ctx, VqPyramid hd, void* stream) {
 extern "C" int vq_diffuse_irradiance(VqContext* ctx, const VqDiffuseIrradianceParams* p, VqPyramid hd, VqCubemap out,
                                      int row_begin, int row_end, void* stream) {
     int rc = vq_enter(ctx); if (rc) return rc;
+    VQ_MARK("DiffuseIrradianceCubemap");
     VQ_REQUIRE(p, "params is null");
     VQ_REQUIRE(pyr_ok(hd), "bad HDRI pyramid descriptor");
     VQ_REQUIRE(out.ptr && out.res >= 2 && out.mips == 1, "diffuse irradiance cubemap must have 1 mip");
@@ -444,6 +446,7 @@ static int specular_launch(VqContext* ctx, VqPyramid hd, const VqCubemap* outs, 
 extern "C" int vq_specular_prefilter(VqContext* ctx, VqPyramid hd, VqCubemap out, int num_samples,
                                      int row_begin, int row_end, void* stream) {
     int rc = vq_enter(ctx); if (rc) return rc;
+    VQ_MARK("SpecularIrradianceCubemap");
     const int range[2] = {row_begin, row_end};
     if (row_begin == row_end && row_begin >= 0) return VQ_OK;
     return specular_launch(ctx, hd, &out, 1, num_samples, range, 1, nullptr, (cudaStream_t)stream);
@@ -455,6 +458,7 @@ extern "C" int vq_specular_prefilter(VqContext* ctx, VqPyramid hd, VqCubemap out
 extern "C" int vq_specular_prefilter_multi(VqContext* ctx, VqPyramid hd, const VqCubemap* outs, int n_outs, int num_samples,
                                            int row_begin, int row_end, void* stream) {
     int rc = vq_enter(ctx); if (rc) return rc;
+    VQ_MARK("SpecularIrradianceCubemap");
     const int range[2] = {row_begin, row_end};
     if (row_begin == row_end && row_begin >= 0) return VQ_OK;
     return specular_launch(ctx, hd, outs, n_outs, num_samples, range, 1, nullptr, (cudaStream_t)stream);
@@ -465,11 +469,13 @@ extern "C" int vq_specular_prefilter_multi(VqContext* ctx, VqPyramid hd, const V
 extern "C" int vq_specular_prefilter_ranges(VqContext* ctx, VqPyramid hd, const VqCubemap* outs, int n_outs, int num_samples,
                                             const int* row_ranges, int n_ranges, const VqPeerSignal* signal, void* stream) {
     int rc = vq_enter(ctx); if (rc) return rc;
+    VQ_MARK("SpecularIrradianceCubemap");
     return specular_launch(ctx, hd, outs, n_outs, num_samples, row_ranges, n_ranges, signal, (cudaStream_t)stream);
 }
 
 extern "C" int vq_brdf_integration_lut(VqContext* ctx, VqImage out, int num_samples, int row_begin, int row_end, void* stream) {
     int rc = vq_enter(ctx); if (rc) return rc;
+    VQ_MARK("CreateBRDFIntegralLUT");
     VQ_REQUIRE(vq_image_ok(out, 8), "bad LUT image descriptor (float2 texels)");
     VQ_REQUIRE(num_samples >= 1 && num_samples <= 8192, "num_samples out of range");
     VQ_REQUIRE(row_begin >= 0 && row_end <= out.height && row_begin <= row_end, "row range out of bounds");

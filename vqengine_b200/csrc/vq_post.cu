@@ -73,6 +73,7 @@ __global__ void __launch_bounds__(TM_THREADS) tonemap_kernel(ImgV in, ImgV out, 
 
 extern "C" int vq_tonemap(VqContext* ctx, const VqTonemapperParams* p, VqImage in, VqImage out, void* stream) {
     int rc = vq_enter(ctx); if (rc) return rc;
+    VQ_MARK("TonemapperCS");
     VQ_REQUIRE(p, "params is null");
     VQ_REQUIRE(vq_image_ok(in) && vq_image_ok(out), "bad image descriptor");
     VQ_REQUIRE(in.width == out.width && in.height == out.height, "tonemap: in/out size mismatch");
@@ -252,8 +253,8 @@ static int blur_common(VqContext* ctx, const VqBlurParams* p, VqImage in, VqImag
     }
     return vq_check_launch(vertical ? "gaussian_blur_y" : "gaussian_blur_x");
 }
-extern "C" int vq_gaussian_blur_x(VqContext* ctx, const VqBlurParams* p, VqImage in, VqImage out, void* stream) { return blur_common(ctx, p, in, out, stream, false); }
-extern "C" int vq_gaussian_blur_y(VqContext* ctx, const VqBlurParams* p, VqImage in, VqImage out, void* stream) { return blur_common(ctx, p, in, out, stream, true); }
+extern "C" int vq_gaussian_blur_x(VqContext* ctx, const VqBlurParams* p, VqImage in, VqImage out, void* stream) { VQ_MARK("BlurX"); return blur_common(ctx, p, in, out, stream, false); }
+extern "C" int vq_gaussian_blur_y(VqContext* ctx, const VqBlurParams* p, VqImage in, VqImage out, void* stream) { VQ_MARK("BlurY"); return blur_common(ctx, p, in, out, stream, true); }
 
 // =============================================================================================
 // FidelityFX scalar helpers — FSR1.0/ffx_a.h:1842-1845 (integer bit tricks: reproduced exactly)
@@ -301,6 +302,7 @@ __global__ void __launch_bounds__(ST_BX * ST_BY) cas_kernel(ImgV in, ImgV out, f
 
 extern "C" int vq_cas(VqContext* ctx, const uint32_t cas_const[8], VqImage in, VqImage out, void* stream) {
     int rc = vq_enter(ctx); if (rc) return rc;
+    VQ_MARK("FFX-CAS CS");
     VQ_REQUIRE(cas_const, "cas_const is null");
     VQ_REQUIRE(vq_image_ok(in) && vq_image_ok(out), "bad image descriptor");
     VQ_REQUIRE(in.width == out.width && in.height == out.height, "cas: sharpen-only path needs equal sizes (FFXCAS_NO_UPSCALING)");
@@ -346,6 +348,7 @@ __global__ void __launch_bounds__(ST_BX * ST_BY) rcas_kernel(ImgV in, ImgV out, 
 
 extern "C" int vq_fsr_rcas(VqContext* ctx, const uint32_t rcas_const[4], VqImage in, VqImage out, void* stream) {
     int rc = vq_enter(ctx); if (rc) return rc;
+    VQ_MARK("FSR-RCAS CS");
     VQ_REQUIRE(rcas_const, "rcas_const is null");
     VQ_REQUIRE(vq_image_ok(in) && vq_image_ok(out), "bad image descriptor");
     VQ_REQUIRE(in.width == out.width && in.height == out.height, "rcas: in/out size mismatch");
@@ -621,8 +624,137 @@ __global__ void __launch_bounds__(EU_BX * EU_BY, EU_BY <= 8 ? 4 : 2) easu_up_ker
     st_stream(out.row(y) + x, make_float4(pix.x, pix.y, pix.z, 1.0f));
 }
 
+// Exact 2x upscale (the FSR1 "performance" preset, BASELINE config 4): con0 = (0.5, 0.5, -0.25, -0.25), so the output pixels
+// (2k+1, 2m+1), (2k+2, 2m+1), (2k+1, 2m+2), (2k+2, 2m+2) all resolve to input texel 'f' = (k, m) with pp = (.25|.75, .25|.75).
+// One THREAD per input texel therefore owns a 2x2 output quad: it reads the 12 texels once, evaluates the four FsrEasuSetF analyses
+// once, and only the blend of the analyses + the 12 tap weights are per pixel — and those run as packed fp32x2 pairs
+// {left pixel, right pixel} (FFMA2/FMUL2/FADD2: one issue slot for two pixels). ncu r01: the one-pixel-per-thread kernel issued
+// 485 instructions per output pixel at 77 % issue utilisation (0.62 ms 4K->8K); this one issues ~150.
+// Texels k = -1 and k = W-1 (m likewise) own quads that hang over the image edge: those stores are predicated off.
+#ifndef E2_BY_D
+#define E2_BY_D 4
+#endif
+#ifndef E2_MINB
+#define E2_MINB 8
+#endif
+constexpr int E2_BX = 32, E2_BY = E2_BY_D;             // input texels ('f' candidates) per CTA -> 64 x 2*E2_BY output pixels
+constexpr int E2_TW = E2_BX + 3, E2_TH = E2_BY + 3;    // staged footprint: columns k-1 .. k+2, rows m-1 .. m+2
+
+struct EasuPx2 { f2 dirx, diry, lenx, leny, lob, clp; };
+// dir/len of an output pair from the four shared analyses and the pair's constant bilinear weights (ffx_fsr1.h:349-384)
+__device__ __forceinline__ EasuPx2 easu2_direction(const EasuSet& S, const EasuSet& T, const EasuSet& U, const EasuSet& V,
+                                                   f2 wS, f2 wT, f2 wU, f2 wV) {
+    f2 dx = bc(S.dirX) * wS, dy = bc(S.dirY) * wS, len = bc(S.lenX) * wS;
+    len = fma2(bc(S.lenY), wS, len);
+    dx = fma2(bc(T.dirX), wT, dx); len = fma2(bc(T.lenX), wT, len); dy = fma2(bc(T.dirY), wT, dy); len = fma2(bc(T.lenY), wT, len);
+    dx = fma2(bc(U.dirX), wU, dx); len = fma2(bc(U.lenX), wU, len); dy = fma2(bc(U.dirY), wU, dy); len = fma2(bc(U.lenY), wU, len);
+    dx = fma2(bc(V.dirX), wV, dx); len = fma2(bc(V.lenX), wV, len); dy = fma2(bc(V.dirY), wV, dy); len = fma2(bc(V.lenY), wV, len);
+    const f2 dirR0 = fma2(dx, dx, dy * dy);
+    const bool z0 = dirR0.v.x < (1.0f / 32768.0f), z1 = dirR0.v.y < (1.0f / 32768.0f);
+    const f2 dirR = mk(z0 ? 1.0f : APrxLoRsqF1(dirR0.v.x), z1 ? 1.0f : APrxLoRsqF1(dirR0.v.y));
+    dx = mk(z0 ? 1.0f : dx.v.x, z1 ? 1.0f : dx.v.y);
+    dx = dx * dirR; dy = dy * dirR;
+    len = len * bc(0.5f);
+    len = len * len;
+    const f2 mxd = mk(APrxLoRcpF1(fmaxf(fabsf(dx.v.x), fabsf(dy.v.x))), APrxLoRcpF1(fmaxf(fabsf(dx.v.y), fabsf(dy.v.y))));
+    const f2 stretch = fma2(dx, dx, dy * dy) * mxd;
+    EasuPx2 r;
+    r.dirx = dx; r.diry = dy;
+    r.lenx = fma2(stretch - bc(1.0f), len, bc(1.0f));
+    r.leny = fma2(bc(-0.5f), len, bc(1.0f));
+    r.lob = fma2(bc((1.0f / 4.0f - 0.04f) - 0.5f), len, bc(0.5f));
+    r.clp = mk(APrxLoRcpF1(r.lob.v.x), APrxLoRcpF1(r.lob.v.y));
+    return r;
+}
+struct EasuAcc2 { f2 r, g, b, w; };
+// one tap for an output pair: weight at the rotated, anisotropically scaled offset (vx, vy) (second half of FsrEasuTapF)
+__device__ __forceinline__ void easu2_tap(EasuAcc2& A, f2 vx, f2 vy, const EasuPx2& P, float4 c) {
+    const f2 d0 = fma2(vx, vx, vy * vy);
+    const f2 d2 = mk(fminf(d0.v.x, P.clp.v.x), fminf(d0.v.y, P.clp.v.y));
+    f2 wB = fma2(bc(2.0f / 5.0f), d2, bc(-1.0f));
+    f2 wA = fma2(P.lob, d2, bc(-1.0f));
+    wB = wB * wB; wA = wA * wA;
+    wB = fma2(bc(25.0f / 16.0f), wB, bc(-(25.0f / 16.0f - 1.0f)));
+    const f2 w = wB * wA;
+    A.r = fma2(bc(c.x), w, A.r); A.g = fma2(bc(c.y), w, A.g); A.b = fma2(bc(c.z), w, A.b);
+    A.w = A.w + w;
+}
+
+template <int ADDR>
+__global__ void __launch_bounds__(E2_BX * E2_BY, E2_MINB) easu_2x_kernel(ImgV in, ImgV out) {
+    __shared__ float4 tile[E2_TH][E2_TW];          // rgb + luma
+    // 'f' texels of this CTA: k in [k0, k0+32), m in [m0, m0+8) with k0 = 32*bx - 1 (k = -1 owns output column 0)
+    const int k0 = (int)blockIdx.x * E2_BX - 1, m0 = (int)blockIdx.y * E2_BY - 1;
+    for (int i = threadIdx.y * E2_BX + threadIdx.x; i < E2_TH * E2_TW; i += E2_BX * E2_BY) {
+        const int ly = i / E2_TW, lx = i - ly * E2_TW;
+        const float3 v = load_addr<ADDR>(in, k0 - 1 + lx, m0 - 1 + ly);
+        tile[ly][lx] = make_float4(v.x, v.y, v.z, luma2(v));
+    }
+    __syncthreads();
+    const int k = k0 + (int)threadIdx.x, m = m0 + (int)threadIdx.y;
+    const int ox = 2 * k + 1, oy = 2 * m + 1;                        // top-left pixel of the quad
+    if (ox >= out.w || oy >= out.h) return;                          // (k, m) beyond the last owning texel
+    const float4* t = &tile[threadIdx.y + 1][threadIdx.x + 1];      // 'f'
+    float3 min4, max4;
+    EasuSet S, T, U, V;
+    {   // the four analyses need only the lumas; the colours are re-read from shared memory tap by tap below, so that the 12
+        // texels are not live in registers across the whole kernel (48 registers: 2 CTAs per SM became 6)
+        const float bL = t[-E2_TW].w, cL = t[-E2_TW + 1].w, eL = t[-1].w, hL = t[2].w;
+        const float iL = t[E2_TW - 1].w, lL = t[E2_TW + 2].w, nL = t[2 * E2_TW].w, oL = t[2 * E2_TW + 1].w;
+        const float4 tf = t[0], tg = t[1], tj = t[E2_TW], tk = t[E2_TW + 1];
+        S = easu_set_shared(bL, eL, tf.w, tg.w, tj.w); T = easu_set_shared(cL, tf.w, tg.w, hL, tk.w);
+        U = easu_set_shared(tf.w, iL, tj.w, tk.w, nL); V = easu_set_shared(tg.w, tj.w, tk.w, lL, oL);
+        // clamp range of the quad: min/max of f, g, j, k (ffx_fsr1.h:395-398)
+        min4 = fmin3(fmin3(xyz(tf), fmin3(xyz(tg), xyz(tj))), xyz(tk));
+        max4 = fmax3(fmax3(xyz(tf), fmax3(xyz(tg), xyz(tj))), xyz(tk));
+    }
+#ifndef E2_ROW_UNROLL
+#define E2_ROW_UNROLL 1          // the two output rows one after the other: one pair's state live at a time (A/B in profiles/r02_post_variants.txt)
+#endif
+    constexpr int kRowUnroll = E2_ROW_UNROLL;
+#pragma unroll kRowUnroll
+    for (int row = 0; row < 2; ++row) {                              // output rows oy (pp.y = .25) and oy+1 (pp.y = .75)
+        const float ppy = row ? 0.75f : 0.25f;
+        const int y = oy + row;
+        if (y < 0 || y >= out.h) continue;
+        // bilinear weights of the four analyses for {left, right}: (1-ppx)(1-ppy), ppx(1-ppy), (1-ppx)ppy, ppx ppy — exact constants
+        const f2 wS = mk(0.75f * (1.0f - ppy), 0.25f * (1.0f - ppy)), wT = mk(0.25f * (1.0f - ppy), 0.75f * (1.0f - ppy));
+        const f2 wU = mk(0.75f * ppy, 0.25f * ppy), wV = mk(0.25f * ppy, 0.75f * ppy);
+        const EasuPx2 P = easu2_direction(S, T, U, V, wS, wT, wU, wV);
+        // rotated + scaled offset of tap (i,j):  vx = ((i-ppx)*dir.x + (j-ppy)*dir.y)*lenx,  vy = (-(i-ppx)*dir.y + (j-ppy)*dir.x)*leny
+        const f2 Ax = P.dirx * P.lenx, Bx = P.diry * P.lenx;         // d vx / d i , d vx / d j
+        const f2 Ay = mk(-P.diry.v.x, -P.diry.v.y) * P.leny, By = P.dirx * P.leny;
+        const f2 nppy = bc(-ppy);
+        const f2 vx00 = fma2(nppy, Bx, mk(-0.25f, -0.75f) * Ax), vy00 = fma2(nppy, By, mk(-0.25f, -0.75f) * Ay);
+        EasuAcc2 A; A.r = A.g = A.b = A.w = bc(0.0f);
+        const f2 vxm = vx00 - Bx, vym = vy00 - By;                                        // (0,-1)
+        easu2_tap(A, vxm, vym, P, t[-E2_TW]);                                                     // b (0,-1)
+        easu2_tap(A, vxm + Ax, vym + Ay, P, t[-E2_TW + 1]);                                           // c (1,-1)
+        easu2_tap(A, vx00 - Ax, vy00 - Ay, P, t[-1]);                                         // e (-1,0)
+        easu2_tap(A, vx00, vy00, P, t[0]);                                                   // f (0,0)
+        easu2_tap(A, vx00 + Ax, vy00 + Ay, P, t[1]);                                         // g (1,0)
+        easu2_tap(A, fma2(bc(2.0f), Ax, vx00), fma2(bc(2.0f), Ay, vy00), P, t[2]);           // h (2,0)
+        const f2 vx1 = vx00 + Bx, vy1 = vy00 + By;                                         // (0,1)
+        easu2_tap(A, vx1 - Ax, vy1 - Ay, P, t[E2_TW - 1]);                                           // i (-1,1)
+        easu2_tap(A, vx1, vy1, P, t[E2_TW]);                                                     // j (0,1)
+        easu2_tap(A, vx1 + Ax, vy1 + Ay, P, t[E2_TW + 1]);                                           // k (1,1)
+        easu2_tap(A, fma2(bc(2.0f), Ax, vx1), fma2(bc(2.0f), Ay, vy1), P, t[E2_TW + 2]);             // l (2,1)
+        const f2 vx2 = fma2(bc(2.0f), Bx, vx00), vy2 = fma2(bc(2.0f), By, vy00);           // (0,2)
+        easu2_tap(A, vx2, vy2, P, t[2 * E2_TW]);                                                     // n (0,2)
+        easu2_tap(A, vx2 + Ax, vy2 + Ay, P, t[2 * E2_TW + 1]);                                           // o (1,2)
+        const f2 rw = rcp2(A.w);                                                           // ARcpF1 = rcp() in the HLSL
+        const f2 cr = A.r * rw, cg = A.g * rw, cb = A.b * rw;
+        float4* dst = out.row(y);
+        if (ox >= 0) st_stream(dst + ox, make_float4(fminf(max4.x, fmaxf(min4.x, cr.v.x)), fminf(max4.y, fmaxf(min4.y, cg.v.x)),
+                                                     fminf(max4.z, fmaxf(min4.z, cb.v.x)), 1.0f));
+        if (ox + 1 < out.w) st_stream(dst + ox + 1, make_float4(fminf(max4.x, fmaxf(min4.x, cr.v.y)), fminf(max4.y, fmaxf(min4.y, cg.v.y)),
+                                                                fminf(max4.z, fmaxf(min4.z, cb.v.y)), 1.0f));
+    }
+}
+
 extern "C" int vq_fsr_easu(VqContext* ctx, const uint32_t con[16], int address_mode, VqImage in, VqImage out, void* stream) {
     int rc = vq_enter(ctx); if (rc) return rc;
+    VQ_MARK("FSR-EASU CS");
     VQ_REQUIRE(con, "easu_const is null");
     VQ_REQUIRE(vq_image_ok(in) && vq_image_ok(out), "bad image descriptor");
     VQ_REQUIRE(address_mode == VQ_ADDRESS_WRAP || address_mode == VQ_ADDRESS_CLAMP, "easu: unknown address mode");
@@ -631,7 +763,14 @@ extern "C" int vq_fsr_easu(VqContext* ctx, const uint32_t con[16], int address_m
     cudaStream_t st = (cudaStream_t)stream;
     // ratio <= 1 (upscale or 1:1) and the footprint of a 32x16 output tile fits the staged tile: shared-memory path
     const bool up = c.c0x > 0.0f && c.c0y > 0.0f && c.c0x <= 1.0f && c.c0y <= 1.0f;
-    if (up) {
+    // exact 2x (FsrEasuCon(w, h, w, h, 2w, 2h)): one thread per input texel, a 2x2 output quad each
+    const bool x2 = c.c0x == 0.5f && c.c0y == 0.5f && c.c0z == -0.25f && c.c0w == -0.25f && out.width == 2 * in.width && out.height == 2 * in.height;
+    if (x2) {
+        // 'f' texels k = -1 .. W-1, m = -1 .. H-1
+        const dim3 grid((in.width + 1 + E2_BX - 1) / E2_BX, (in.height + 1 + E2_BY - 1) / E2_BY);
+        if (address_mode == VQ_ADDRESS_WRAP) easu_2x_kernel<VQ_ADDRESS_WRAP><<<grid, dim3(E2_BX, E2_BY), 0, st>>>(make_view(in), make_view(out));
+        else                                 easu_2x_kernel<VQ_ADDRESS_CLAMP><<<grid, dim3(E2_BX, E2_BY), 0, st>>>(make_view(in), make_view(out));
+    } else if (up) {
         const dim3 grid((out.width + EU_BX - 1) / EU_BX, (out.height + EU_BY - 1) / EU_BY);
         if (address_mode == VQ_ADDRESS_WRAP) easu_up_kernel<VQ_ADDRESS_WRAP><<<grid, dim3(EU_BX, EU_BY), 0, st>>>(make_view(in), make_view(out), c);
         else                                 easu_up_kernel<VQ_ADDRESS_CLAMP><<<grid, dim3(EU_BX, EU_BY), 0, st>>>(make_view(in), make_view(out), c);
@@ -785,6 +924,7 @@ __global__ void __launch_bounds__(256) spd_kernel(ImgV src, SpdLevels L, int mip
 
 extern "C" int vq_spd_downsample(VqContext* ctx, const VqSpdConstants* c, VqImage src, const VqImage* mips, void* stream) {
     int rc = vq_enter(ctx); if (rc) return rc;
+    VQ_MARK("FFX-SPD CS");
     VQ_REQUIRE(c && mips, "constants/mips is null");
     VQ_REQUIRE(vq_image_ok(src), "bad source image");
     VQ_REQUIRE(c->mips >= 1 && c->mips <= 12, "spd: 1..12 destination mips");

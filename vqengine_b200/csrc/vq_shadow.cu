@@ -73,6 +73,7 @@ extern "C" int vq_forward_lighting_shadowed(VqContext* ctx, const VqPerFrameData
                                             const VqGBuffer* gb, const VqEnvironmentMaps* env, const VqShadowMaps* sm,
                                             VqImage out, int row_begin, int row_end, void* stream) {
     int rc = vq_enter(ctx); if (rc) return rc;
+    VQ_MARK("RenderSceneColor");
     VQ_REQUIRE(pf && pv && gb && env && sm, "null parameter block");
     const VqSceneLighting& L = pf->Lights;
     VQ_REQUIRE(L.numPointCasters >= 0 && L.numPointCasters <= VQ_NUM_SHADOWING_LIGHTS_POINT &&
@@ -111,6 +112,7 @@ extern "C" uint64_t vq_depth_pyramid_texel_count(int width, int height, int leve
 
 extern "C" int vq_depth_min_pyramid(VqContext* ctx, VqImage depth, void* levels, int n_levels, void* stream_) {
     int rc = vq_enter(ctx); if (rc) return rc;
+    VQ_MARK("DownsampleDepth");
     cudaStream_t stream = (cudaStream_t)stream_;
     VQ_REQUIRE(vq_image_ok(depth, 4), "bad depth image descriptor (R32F)");
     VQ_REQUIRE(levels && ((uintptr_t)levels % 4) == 0, "levels buffer is null or misaligned");

@@ -446,6 +446,7 @@ extern "C" int vq_gbuffer_from_materials(VqContext* ctx, const VqSurfaceInputs* 
                                          float ambient_factor, int alpha_mask, const VqGBuffer* out,
                                          int row_begin, int row_end, void* stream) {
     int rc = vq_enter(ctx); if (rc) return rc;
+    VQ_MARK("Geometry");
     VQ_REQUIRE(in && table && out, "null argument");
     VQ_REQUIRE(table->dev && table->count >= 1, "empty material table");
     const int W = in->position_u.width, H = in->position_u.height;
