@@ -256,6 +256,7 @@ def extra_passes(ctx, vq, torch, envk, peak):
     out["hdri_min_pyramid"] = {"ms": round(ms, 4), "algorithmic_GBps": round(nb / ms / 1e6, 1)}
     out.update(surface_producer_pass(ctx, vq, torch, peak))
     out.update(frame_format_passes(ctx, vq, torch, envk, peak))
+    out.update(shadow_passes(ctx, vq, torch, envk, peak))
     return out
 
 
@@ -355,6 +356,45 @@ def surface_producer_pass(ctx, vq, torch, peak):
                                     "hbm_frac": round(nb / ms / 1e6 / peak, 3), "launches": (levels - 1 + 5) // 6}
     sc["table"].close()
     return out
+
+
+def shadow_passes(ctx, vq, torch, envk, peak):
+    """the forward pass with shadow maps bound (1 point caster with the 20-tap cube PCF, 1 spot caster and a shadowing
+    directional light with the 5x5 PCF) against the same lights unshadowed, and the MIN depth pyramid of a 4K depth buffer."""
+    import numpy as np
+    from vqengine_b200 import synth
+    w, h = W4K, H4K
+    planes = synth.gbuffer(w, h, seed=synth.SEED_BASE + 3)
+    pf, pv = synth.scene_constants(w, h, envk["spec_mips"], n_point=2, n_spot=1, casters=True)
+    L = pf.Lights
+    m = np.zeros(16, np.float32); m[0] = 1 / 25; m[5] = 1 / 25; m[14] = 0.5; m[15] = 1.0
+    for sc in range(L.numSpotCasters):
+        for k in range(16): L.shadowViews[sc].m[k] = float(m[k])
+    for k in range(16): L.shadowViewDirectional.m[k] = float(m[k])
+    L.directional.shadowing = 1
+    res_pt, res_2d = 1024, 2048
+    pf.f2SpotLightShadowMapDimensions.x = pf.f2SpotLightShadowMapDimensions.y = float(res_2d)
+    pf.f2DirectionalLightShadowMapDimensions.x = pf.f2DirectionalLightShadowMapDimensions.y = float(res_2d)
+    dpl = [torch.from_numpy(p).cuda() for p in planes[:3]]
+    gb = vq.GBuffer(vq.image_of(dpl[0]), vq.image_of(dpl[1]), vq.image_of(dpl[2]), vq.null_image())
+    out = torch.zeros((h, w, 4), dtype=torch.float32, device="cuda")
+    g = torch.Generator(device="cuda"); g.manual_seed(5)
+    cubes = torch.rand((max(L.numPointCasters, 1), 6, res_pt, res_pt), device="cuda", generator=g) * 1.2
+    spots = torch.rand((max(L.numSpotCasters, 1), res_2d, res_2d), device="cuda", generator=g) * 0.4 + 0.3
+    dmap = torch.rand((res_2d, res_2d), device="cuda", generator=g) * 0.4 + 0.3
+    ms0 = time_gpu(torch, lambda: ctx.forward_lighting(pf, pv, gb, envk["env"], out), 10)
+    ms1 = time_gpu(torch, lambda: ctx.forward_lighting_shadowed(pf, pv, gb, envk["env"], out, cubes, spots, dmap), 10)
+    r = {"forward_4k_casters_shadowed": {
+        "ms": round(ms1, 4), "ms_same_lights_unshadowed": round(ms0, 4),
+        "casters": f"{L.numPointCasters} point (20-tap cube PCF, {res_pt}^2 faces) + {L.numSpotCasters} spot + directional (5x5 PCF, {res_2d}^2)",
+        "Mpixels_per_s": round(w * h / ms1 / 1e3, 1), "bound": "instruction issue (PCF taps: 70 point-sampled fetches + their address math per pixel)"}}
+    depth = torch.rand((h, w), device="cuda", generator=g)
+    n = vq.depth_pyramid_level_count(w, h)
+    levels = torch.empty((vq.depth_pyramid_texel_count(w, h, n),), dtype=torch.float32, device="cuda")
+    ms = time_gpu(torch, lambda: ctx.depth_min_pyramid(depth, levels), 10)
+    nb = w * h * 4 * 2 + int(w * h * 4 * (1 / 3 + 2 / 3))     # copy (read + write) + every level written once, padded level read once
+    r["depth_min_pyramid_4k"] = {"ms": round(ms, 4), "levels": n, "algorithmic_GBps": round(nb / ms / 1e6, 1), "hbm_frac": round(nb / ms / 1e6 / peak, 3)}
+    return r
 
 
 class PeerFlags:

@@ -1,6 +1,7 @@
 // vq_context.cu — context lifetime, error plumbing, packed-layout helpers and the host-side
 // FidelityFX constant setup (== the A_CPU functions the engine calls, PostProcess.cpp:39-99).
 #include "vq_common.cuh"
+#include <stdlib.h>
 #include <stdarg.h>
 #include <string.h>
 #include <math.h>
@@ -68,6 +69,17 @@ int vq_ctx_create(int device, VqContext** out_ctx) {
     c->l2_bytes = prop.l2CacheSize;
     if (cudaMalloc(&c->spd_counter, 2 * VQ_SPD_SLOTS * sizeof(uint32_t)) != cudaSuccess) { delete c; vq_set_error("cudaMalloc failed"); return VQ_ERR_OUT_OF_MEMORY; }
     cudaMemset(c->spd_counter, 0, 2 * VQ_SPD_SLOTS * sizeof(uint32_t));
+    {   // persisting-L2 carve-out for K1's sampling copies (vq_forward.cu); the device limit is process-wide state
+        const char* e = getenv("VQ_L2_PERSIST");
+        int maxPersist = 0, maxWindow = 0;
+        cudaDeviceGetAttribute(&maxPersist, cudaDevAttrMaxPersistingL2CacheSize, device);
+        cudaDeviceGetAttribute(&maxWindow, cudaDevAttrMaxAccessPolicyWindowSize, device);
+        if (!(e && e[0] == '0') && maxPersist > 0 && maxWindow > 0 &&
+            cudaDeviceSetLimit(cudaLimitPersistingL2CacheSize, (size_t)maxPersist) == cudaSuccess) {
+            c->l2_persist_bytes = (size_t)maxPersist; c->l2_window_max = maxWindow;
+        }
+        cudaGetLastError();
+    }
     c->spd_next = new std::atomic<uint32_t>(0u);
     c->mu = new std::recursive_mutex();
     *out_ctx = c;
@@ -82,7 +94,7 @@ int vq_ctx_destroy(VqContext* ctx) {
         for (auto& e : ctx->events) cudaEventDestroy(e);
     }
     if (ctx->stage_dev) cudaFree(ctx->stage_dev);
-    for (void* p : {ctx->env_diff, ctx->env_spec, ctx->tmp_diff, ctx->tmp_spec, ctx->env_lut, ctx->tmp_lut, ctx->resize_mid, ctx->resize_tab, ctx->depth_pad}) if (p) cudaFree(p);
+    for (void* p : {ctx->env_all, ctx->tmp_diff, ctx->tmp_spec, ctx->tmp_lut, ctx->resize_mid, ctx->resize_tab, ctx->depth_pad}) if (p) cudaFree(p);
     if (ctx->spd_counter) cudaFree(ctx->spd_counter);
     delete ctx->spd_next; delete ctx->mu;
     delete ctx;
