@@ -148,12 +148,12 @@ def test_c5_specular_full_face_and_random_texels(ctx, vq, orc):
     for m, f in ((1, 3), (1, 0)):
         nn = res >> m
         a = vq.cubemap_offset(res, m, f)
-        check(f"C5 specular mip{m} face{f} ({nn}^2)", np.arange(a, a + nn * nn, dtype=np.int64), 0.03)
+        check(f"C5 specular mip{m} face{f} ({nn}^2)", np.arange(a, a + nn * nn, dtype=np.int64), 0.08)
     # 1 % of all texels, uniformly at random over the packed cube (so mostly mips 0-2, like the work itself)
     rng = np.random.default_rng(0x5EED0005)
-    check("C5 specular 1% random texels", np.sort(rng.choice(n, size=n // 100, replace=False).astype(np.int64)), 0.03)
+    check("C5 specular 1% random texels", np.sort(rng.choice(n, size=n // 100, replace=False).astype(np.int64)), 0.08)
     # and every texel of the small mips (3..8), where one texel integrates a wide lobe
-    check("C5 specular mips 3..8 complete", np.arange(vq.cubemap_offset(res, 3, 0), n, dtype=np.int64), 0.03)
+    check("C5 specular mips 3..8 complete", np.arange(vq.cubemap_offset(res, 3, 0), n, dtype=np.int64), 0.08)
 
 
 def test_c5_forward_8k_row_tiles(ctx, vq, orc, envk):

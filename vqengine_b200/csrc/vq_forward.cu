@@ -926,10 +926,10 @@ int vq_forward_launch_multi(VqContext* ctx, const VqPerFrameData* pf, const VqPe
         VQ_CUDA_OK(cudaFuncSetAttribute(forward_kernel<true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024));
         attrSet.store(true, std::memory_order_release);
     }
-    // L2 residency of the sampling copies (registered environment only): a PERSISTING access-policy window over the one allocation
-    // that holds them, as a per-launch attribute (the caller's stream state is not touched). The G-buffer streams through with
-    // evict_first; without the window the 102 MB of copies lose half their lines to it (ncu r02a: L2 hit rate 48 %, 135 MB of extra
-    // DRAM reads per 4K frame). Opt-out: VQ_L2_PERSIST=0.
+    // Experiment kept behind VQ_L2_PERSIST=1 (off by default: it measured 27 % slower, see vq_context.cu): a PERSISTING access-policy
+    // window over the one allocation that holds the sampling copies, as a per-launch attribute (the caller's stream state is not
+    // touched). Without it the G-buffer streams through with evict_first and the copies keep about half their lines in L2
+    // (ncu r02: L2 hit rate 48 %, 135 MB of extra DRAM reads per 4K frame — latency, not bandwidth, at 27 % DRAM utilisation).
     cudaLaunchAttribute attr[1];
     unsigned nAttr = 0;
     if (prepared && ctx->l2_persist_bytes > 0 && ctx->env_used_bytes > 0) {
