@@ -118,7 +118,7 @@ def test_c5_specular_full_face_and_random_texels(ctx, vq, orc):
     got = host(cube)
     hp = host(pyr_t)
     assert np.isfinite(got).all() and (got[:, 3] == 1.0).all()
-    def check(name, ids, max_frac_relaxed):
+    def check(name, ids):
         """|delta| <= 1e-4 * max(1,|ref|) + 2 * S, S = how far the ORACLE's own texel moves when (a) its look direction is tilted by
         4.8e-7 rad (2^-21: a few ulps) or (b) the length of its un-normalised sample vectors is off by 1-4 ulps
         (oracle_capi.cpp: orc_specular_prefilter_sensitivity). S is ~1e-6 except where an importance sample lands within a few
@@ -126,8 +126,8 @@ def test_c5_specular_full_face_and_random_texels(ctx, vq, orc):
         v = asin(-L.y)/pi + 0.5, whose slope is infinite at the poles, and its WRAP-in-v sampler then blends in the OPPOSITE pole's
         row: one ulp of |L| moves the blend weight by ~0.15 and the texel by 4e-4 (measured: profiles/r02_diag_fullsize.txt, up
         to 2e-3 on the 5 texels around each pole of mips 1-2). Two correct fp32 evaluations cannot agree better than the
-        reference agrees with itself; everywhere else the bound is the strict one, and
-        the texels that get any noticeable relaxation (S > 2e-5 * max(1,|ref|)) must stay a small minority."""
+        reference agrees with itself; everywhere else the bound is the strict one, and independently of S at least 99.5 % of the
+        texels of every set must meet the strict bound (measured: 99.93-99.99 %)."""
         ref = orc.specular_prefilter_texels(hp, hw, hh, levels, res, mips, ids)
         sens = orc.specular_prefilter_sensitivity(hp, hw, hh, levels, res, mips, ids)
         g = got[ids]
@@ -141,19 +141,19 @@ def test_c5_specular_full_face_and_random_texels(ctx, vq, orc):
                  max_scaled_where_strict=float((d / scale)[~relaxed].max()), frac_within_strict=float((d <= 1e-4 * scale).mean()))
         print(r)
         assert (d <= bound).all(), f"{name}: {int((d > bound).sum())} texels outside the bound, worst {float((d - bound).max()):.3e} ({r})"
-        assert relaxed.mean() <= max_frac_relaxed, f"{name}: the sensitivity relaxation must stay an exception ({r})"
-        assert r["frac_within_strict"] >= 0.995, r
+        # the relaxation must stay an exception: whatever S says, at least 99.5 % of the texels meet the STRICT bound
+        assert r["frac_within_strict"] >= 0.995, f"{name}: {r}"
 
     # one full face of one mip: mip 1 (256^2, roughness 1/8); face 3 (-Y) holds a pole, face 0 does not
     for m, f in ((1, 3), (1, 0)):
         nn = res >> m
         a = vq.cubemap_offset(res, m, f)
-        check(f"C5 specular mip{m} face{f} ({nn}^2)", np.arange(a, a + nn * nn, dtype=np.int64), 0.08)
+        check(f"C5 specular mip{m} face{f} ({nn}^2)", np.arange(a, a + nn * nn, dtype=np.int64))
     # 1 % of all texels, uniformly at random over the packed cube (so mostly mips 0-2, like the work itself)
     rng = np.random.default_rng(0x5EED0005)
-    check("C5 specular 1% random texels", np.sort(rng.choice(n, size=n // 100, replace=False).astype(np.int64)), 0.08)
+    check("C5 specular 1% random texels", np.sort(rng.choice(n, size=n // 100, replace=False).astype(np.int64)))
     # and every texel of the small mips (3..8), where one texel integrates a wide lobe
-    check("C5 specular mips 3..8 complete", np.arange(vq.cubemap_offset(res, 3, 0), n, dtype=np.int64), 0.08)
+    check("C5 specular mips 3..8 complete", np.arange(vq.cubemap_offset(res, 3, 0), n, dtype=np.int64))
 
 
 def test_c5_forward_8k_row_tiles(ctx, vq, orc, envk):

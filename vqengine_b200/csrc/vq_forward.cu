@@ -38,8 +38,19 @@ struct CubeV { const float4* p; int res, mips; uint32_t mipOffset[16]; };
 struct LutV { const float4* q; int w, h; };
 struct F8 { float4 a, b; };
 
+struct SPoint { float3 pos; float d2Limit; float3 color; float brightness; };
+struct SDir { float3 wi; float pad0; float3 radiance; float pad1; };
+struct SSpot { float3 pos; float outer; float3 color; float brightness; float3 dir; float inner; float invCone; float pad[3]; };
+constexpr int FWD_MAX_POINT = VQ_NUM_LIGHTS_POINT + VQ_NUM_SHADOWING_LIGHTS_POINT, FWD_MAX_SPOT = VQ_NUM_LIGHTS_SPOT + VQ_NUM_SHADOWING_LIGHTS_SPOT;
+
 struct FwdParams {
-    VqSceneLighting lights;            // 7088 B, read once per block into shared memory
+    // the frame's lights, conditioned on the host (exact range thresholds, normalised directions, radiance) and read by the kernel
+    // straight from the constant bank with warp-uniform indices: no shared-memory staging, no LDS in the light loop (the L1/MIO
+    // pipe that the environment gathers keep busy is left alone)
+    SPoint pts[FWD_MAX_POINT];         // point lights, then (unshadowed) point casters
+    SSpot spots[FWD_MAX_SPOT];         // spot lights, then spot casters
+    SDir dir;
+    int numPoint, numSpot, dirEnabled;
     float3 cam;
     float cosB, sinB;                  // GetHDRIRotationMatrix (Lighting.hlsl:348-358), cos/sin(-offset)
     int maxLod;                        // int(MaxEnvMapLODLevels)
@@ -56,10 +67,6 @@ struct FwdParams {
     uint32_t diffMaxRec, specMaxRec;   // last record a footprint may start at (address clamp for non-finite directions)
     int rowBegin, rows, width;
 };
-
-struct SPoint { float3 pos; float d2Limit; float3 color; float brightness; };
-struct SDir { float3 wi; float pad0; float3 radiance; float pad1; };
-struct SSpot { float3 pos; float outer; float3 color; float brightness; float3 dir; float inner; float invCone; float pad[3]; };
 
 // ---------------------------------------------------------------------------------------------
 // cubemap sampling: bilinear, seamless (identical rule in oracle/oracle_shading.cpp)
@@ -346,12 +353,13 @@ __device__ __forceinline__ LightVec2 light_vector2(const Px2& s, float3 pos) {
 
 // every light of the frame for one pixel pair, in PSMain's order
 template <bool TINY>
-__device__ __forceinline__ void shade_all_lights(const Px2& s, Acc2& acc, float3 cam, const SPoint* __restrict__ sPoint, int numPoint,
-                                                 const SSpot* __restrict__ sSpot, int numSpot, const SDir* __restrict__ sDir, bool dirEnabled) {
+__device__ __forceinline__ void shade_all_lights(const Px2& s, Acc2& acc, const FwdParams& P) {
+    const float3 cam = P.cam;
+    const int numPoint = P.numPoint, numSpot = P.numSpot;
     // ---- point lights, then unshadowed point casters (Lighting.hlsl:308-322; PSMain :310-313,321-340):
     //      in range <=> d2 < d2Limit (== length(Lw-P) < l.range, exactly) ----
     for (int i = 0; i < numPoint; ++i) {
-        const SPoint l = sPoint[i];
+        const SPoint l = P.pts[i];                                       // constant bank, warp-uniform index
         const LightVec2 L = light_vector2(s, l.pos);
         const f2 att = (L.invD * L.invD) * bc(l.brightness);               // AttenuationBRDF = 1/D^2
         const f2 scale = mk(L.d2.v.x < l.d2Limit ? att.v.x : 0.0f, L.d2.v.y < l.d2Limit ? att.v.y : 0.0f);
@@ -359,7 +367,7 @@ __device__ __forceinline__ void shade_all_lights(const Px2& s, Acc2& acc, float3
     }
     // ---- spot lights, then unshadowed spot casters (Lighting.hlsl:57-73,323-333) ----
     for (int k = 0; k < numSpot; ++k) {
-        const SSpot l = sSpot[k];
+        const SSpot l = P.spots[k];
         const LightVec2 L = light_vector2(s, l.pos);
         const f2 cosT = dot3(L.x, L.y, L.z, bc(l.dir.x), bc(l.dir.y), bc(l.dir.z)) * L.invD;   // pixel direction = -Wi
         float inten[2];
@@ -373,8 +381,8 @@ __device__ __forceinline__ void shade_all_lights(const Px2& s, Acc2& acc, float3
         shade_light2<TINY>(s, acc, cam, L.x, L.y, L.z, L.d2, L.invD, scale, l.color);
     }
     // ---- directional (PSMain :360-377 with ShadowingFactor = 1) ----
-    if (dirEnabled) {
-        const SDir d = *sDir;
+    if (P.dirEnabled) {
+        const SDir d = P.dir;
         shade_light2<TINY>(s, acc, cam, bc(d.wi.x), bc(d.wi.y), bc(d.wi.z), bc(1.0f), bc(1.0f), bc(1.0f), d.radiance);
     }
 }
@@ -591,18 +599,12 @@ __device__ __forceinline__ float4 finish_pixel(const FwdParams& P, const FaceRec
 template <bool MULTI, bool ROT>
 __global__ void __launch_bounds__(FWD_THREADS, FWD_CTAS_PER_SM) forward_kernel(const __grid_constant__ FwdParams P) {
     extern __shared__ __align__(128) unsigned char smemRaw[];
-    const VqSceneLighting& L = P.lights;
-    const int nP = L.numPointLights, nPC = L.numPointCasters, nS = L.numSpotLights, nSC = L.numSpotCasters;
-    const int numPoint = nP + nPC, numSpot = nS + nSC;
     const int nPl = P.hasEmissive ? 4 : 3;
     const int tid = threadIdx.x;
-    // shared-memory layout: [FWD_STAGES][nPl][FWD_TILE] float4 | full[S], empty[S] mbarriers | FaceRec[8*16] | SDir | SPoint[] | SSpot[]
+    // shared-memory layout: [FWD_STAGES][nPl][FWD_TILE] float4 | full[S], empty[S] mbarriers | FaceRec[8*16]
     const uint32_t stageBytes = (uint32_t)nPl * FWD_PLANE;
     uint64_t* bars = (uint64_t*)(smemRaw + FWD_STAGES * stageBytes);
     FaceRec* sFace = (FaceRec*)(bars + 2 * FWD_STAGES);
-    SDir* sDir = (SDir*)(sFace + 16 * 8);
-    SPoint* sPoint = (SPoint*)(sDir + 1);
-    SSpot* sSpot = (SSpot*)(sPoint + numPoint);
     const uint32_t stage0 = smem_u32(smemRaw), bar0 = smem_u32(bars);
     auto fullBar = [&](int st) { return bar0 + 8u * (uint32_t)st; };
     auto emptyBar = [&](int st) { return bar0 + 8u * (uint32_t)(FWD_STAGES + st); };
@@ -632,34 +634,7 @@ __global__ void __launch_bounds__(FWD_THREADS, FWD_CTAS_PER_SM) forward_kernel(c
         for (int s = 0; s < FWD_AHEAD; ++s) request((int)blockIdx.y + s * rowStep, s, 0u);   // prologue: FWD_AHEAD tiles in flight
     }
 
-    // ---- stage the light arrays (Scene::GatherLightData layout) and the specular cube's face table, once per CTA ----
-    for (int i = tid; i < numPoint; i += FWD_THREADS) {
-        const VqPointLight& l = i < nP ? L.point_lights[i] : L.point_casters[i - nP];
-        SPoint s;
-        s.pos = f3(l.position.x, l.position.y, l.position.z);
-        s.color = f3(l.color.x, l.color.y, l.color.z);
-        s.brightness = l.brightness;
-        // smallest d2 with sqrt_rn(d2) >= range: then (d2 < limit) == (sqrt_rn(d2) < range) exactly
-        float lim = l.range * l.range;
-        if (!(l.range > 0.0f)) lim = 0.0f;
-        else {
-            while (sqrtf(lim) >= l.range && lim > 0.0f) lim = __uint_as_float(__float_as_uint(lim) - 1u);
-            while (sqrtf(lim) < l.range) lim = __uint_as_float(__float_as_uint(lim) + 1u);
-        }
-        s.d2Limit = lim;
-        sPoint[i] = s;
-    }
-    for (int i = tid; i < numSpot; i += FWD_THREADS) {
-        const VqSpotLight& l = i < nS ? L.spot_lights[i] : L.spot_casters[i - nS];
-        SSpot s;
-        s.pos = f3(l.position.x, l.position.y, l.position.z);
-        s.color = f3(l.color.x, l.color.y, l.color.z);
-        s.brightness = l.brightness;
-        s.dir = normalize_u_generic(f3(l.spotDir.x, l.spotDir.y, l.spotDir.z));   // normalize(l.spotDir), Lighting.hlsl:60
-        s.outer = l.outerConeAngle; s.inner = l.innerConeAngle;
-        s.invCone = 1.0f / (l.outerConeAngle - l.innerConeAngle);
-        sSpot[i] = s;
-    }
+    // ---- stage the specular cube's face table, once per CTA ----
     for (int i = tid; i < 16 * 8; i += FWD_THREADS) {
         // index = face*16 + mip: the lanes of a warp mostly share the face and differ in the mip (per-pixel roughness), so the
         // entries they read are ADJACENT 16-byte words in different banks (mip*8+face measured 19 wavefronts per LDS.128, ideal 4)
@@ -672,15 +647,7 @@ __global__ void __launch_bounds__(FWD_THREADS, FWD_CTAS_PER_SM) forward_kernel(c
         }
         sFace[i] = f;
     }
-    const bool dirEnabled = L.directional.enabled != 0;
-    if (dirEnabled && tid == FWD_THREADS - 1) {                    // Lighting.hlsl:334-345: Wi = normalize(-dir), radiance = color * brightness
-        SDir d;
-        d.wi = normalize_u_generic(f3(-L.directional.lightDirection.x, -L.directional.lightDirection.y, -L.directional.lightDirection.z));
-        d.radiance = f3(L.directional.color.x, L.directional.color.y, L.directional.color.z) * L.directional.brightness;
-        d.pad0 = d.pad1 = 0.0f;
-        *sDir = d;
-    }
-    __syncthreads();                                              // lights staged, mbarriers initialised
+    __syncthreads();                                              // face table staged, mbarriers initialised
 
     int st = 0; uint32_t use = 0;                                 // stage of the current tile, completed uses of that stage
     const int xA = x0 + tid, xB = xA + FWD_THREADS;
@@ -736,9 +703,9 @@ __global__ void __launch_bounds__(FWD_THREADS, FWD_CTAS_PER_SM) forward_kernel(c
             const f2 tmin = bc(1.0f) + mk(fminf(s.a2m1.v.x, 0.0f), fminf(s.a2m1.v.y, 0.0f));
             const f2 dmin = bc(PI) * (tmin * tmin);
             if (__any_sync(0xffffffffu, fminf(dmin.v.x, dmin.v.y) < 2e-12f))
-                shade_all_lights<true>(s, acc, P.cam, sPoint, numPoint, sSpot, numSpot, sDir, dirEnabled);
+                shade_all_lights<true>(s, acc, P);
             else
-                shade_all_lights<false>(s, acc, P.cam, sPoint, numPoint, sSpot, numSpot, sDir, dirEnabled);
+                shade_all_lights<false>(s, acc, P);
 
             const f2 nsnv = mulsat2(s.nsLen, s.nv);                      // saturate(dot(s.N, V)) of the raw normal
             const f2 Nrx = s.Nx * s.nsLen, Nry = s.Ny * s.nsLen, Nrz = s.Nz * s.nsLen;
@@ -827,6 +794,57 @@ int ensure_bytes(void** ptr, size_t* have, size_t need) {
 
 }  // namespace
 
+// Scene::GatherLightData's arrays -> what the kernel reads per light, on the host in IEEE fp32 (every operation rounded on its
+// own: the same bits the oracle's normalize() / length() produce):
+//   point: smallest d2 with sqrt_rn(d2) >= range, so that (d2 < limit) == (sqrt_rn(d2) < range) exactly  (Lighting.hlsl:308-322)
+//   spot : normalize(l.spotDir) (Lighting.hlsl:60), 1/(outer - inner);  directional: Wi = normalize(-dir), radiance = color*brightness
+static void normalize_host(const float v[3], float out[3]) {
+    volatile float xx = v[0] * v[0], yy = v[1] * v[1], zz = v[2] * v[2];
+    volatile float s = xx + yy; s = s + zz;
+    const float l = sqrtf(s);
+    out[0] = v[0] / l; out[1] = v[1] / l; out[2] = v[2] / l;
+}
+static void condition_lights(const VqSceneLighting& L, FwdParams& P) {
+    const int nP = L.numPointLights, nPC = L.numPointCasters, nS = L.numSpotLights, nSC = L.numSpotCasters;
+    P.numPoint = nP + nPC; P.numSpot = nS + nSC;
+    for (int i = 0; i < P.numPoint; ++i) {
+        const VqPointLight& l = i < nP ? L.point_lights[i] : L.point_casters[i - nP];
+        SPoint& s = P.pts[i];
+        s.pos = make_float3(l.position.x, l.position.y, l.position.z);
+        s.color = make_float3(l.color.x, l.color.y, l.color.z);
+        s.brightness = l.brightness;
+        volatile float lim = l.range * l.range;
+        if (!(l.range > 0.0f)) lim = 0.0f;
+        else {
+            auto bits = [](float f) { uint32_t u; memcpy(&u, &f, 4); return u; };
+            auto flt = [](uint32_t u) { float f; memcpy(&f, &u, 4); return f; };
+            while (sqrtf(lim) >= l.range && lim > 0.0f) lim = flt(bits(lim) - 1u);
+            while (sqrtf(lim) < l.range) lim = flt(bits(lim) + 1u);
+        }
+        s.d2Limit = lim;
+    }
+    for (int i = 0; i < P.numSpot; ++i) {
+        const VqSpotLight& l = i < nS ? L.spot_lights[i] : L.spot_casters[i - nS];
+        SSpot& s = P.spots[i];
+        s.pos = make_float3(l.position.x, l.position.y, l.position.z);
+        s.color = make_float3(l.color.x, l.color.y, l.color.z);
+        s.brightness = l.brightness;
+        const float d[3] = {l.spotDir.x, l.spotDir.y, l.spotDir.z};
+        float n[3]; normalize_host(d, n);
+        s.dir = make_float3(n[0], n[1], n[2]);
+        s.outer = l.outerConeAngle; s.inner = l.innerConeAngle;
+        s.invCone = 1.0f / (l.outerConeAngle - l.innerConeAngle);
+    }
+    P.dirEnabled = L.directional.enabled != 0;
+    if (P.dirEnabled) {
+        const float d[3] = {-L.directional.lightDirection.x, -L.directional.lightDirection.y, -L.directional.lightDirection.z};
+        float n[3]; normalize_host(d, n);
+        P.dir.wi = make_float3(n[0], n[1], n[2]);
+        P.dir.radiance = make_float3(L.directional.color.x * L.directional.brightness, L.directional.color.y * L.directional.brightness,
+                                     L.directional.color.z * L.directional.brightness);
+    }
+}
+
 int vq_forward_launch_multi(VqContext* ctx, const VqPerFrameData* pf, const VqPerViewLightingData* pv,
                             const VqGBuffer* gb, const VqEnvironmentMaps* env, const VqImage* outs, int n_outs,
                             int dst_row_offset, int row_begin, int row_end, const VqPeerSignal* sig, cudaStream_t stream) {
@@ -852,7 +870,7 @@ int vq_forward_launch_multi(VqContext* ctx, const VqPerFrameData* pf, const VqPe
 
     FwdParams P;
     memset(&P, 0, sizeof(P));
-    P.lights = L;
+    condition_lights(L, P);
     P.cam = make_float3(pv->CameraPosition.x, pv->CameraPosition.y, pv->CameraPosition.z);
     P.cosB = cosf(-pf->fHDRIOffsetInRadians);
     P.sinB = sinf(-pf->fHDRIOffsetInRadians);
@@ -913,9 +931,7 @@ int vq_forward_launch_multi(VqContext* ctx, const VqPerFrameData* pf, const VqPe
     if (gy > (unsigned)P.rows) gy = (unsigned)P.rows;
     VQ_REQUIRE(gy <= 65535u, "frame too tall for the launch grid");
     const int nPl = P.hasEmissive ? 4 : 3;
-    const size_t smem = (size_t)FWD_STAGES * nPl * FWD_PLANE + 2 * FWD_STAGES * sizeof(uint64_t) + 16 * 8 * sizeof(FaceRec) +
-                       sizeof(SDir) + (size_t)(L.numPointLights + L.numPointCasters) * sizeof(SPoint) +
-                       (size_t)(L.numSpotLights + L.numSpotCasters) * sizeof(SSpot);
+    const size_t smem = (size_t)FWD_STAGES * nPl * FWD_PLANE + 2 * FWD_STAGES * sizeof(uint64_t) + 16 * 8 * sizeof(FaceRec);
     static_assert(sizeof(SPoint) == 32 && sizeof(SSpot) == 64 && sizeof(SDir) == 32, "shared light records are 16-byte multiples");
     const bool rot = P.sinB != 0.0f || P.cosB != 1.0f;            // yaw offset 0 is the common case: compiled out
     static std::atomic<bool> attrSet{false};                      // process-wide and idempotent: every instantiation, once
