@@ -1,107 +1,145 @@
-"""Builds profiles/README.md from the bench JSON lines kept under profiles/ (r01_bench_{1,2,8}gpu.json)."""
-import json, os, sys
+"""Builds profiles/README.md from the round-2 bench JSON lines kept under profiles/ (r02_bench_{1,2,4,8}gpu.json) next to the
+round-1 lines (r01_bench_*.json) they are compared with. Round 1's own report is kept as profiles/r01_README.md."""
+import json
+import os
+
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 P = os.path.join(ROOT, "profiles")
 
+
 def load(name):
     p = os.path.join(P, name)
-    if not os.path.exists(p): return None
+    if not os.path.exists(p):
+        return None
     for line in reversed(open(p).read().splitlines()):
         line = line.strip()
         if line.startswith("{"):
-            try: return json.loads(line)
-            except Exception: pass
+            try:
+                return json.loads(line)
+            except Exception:
+                pass
     return None
 
-b1, b2, b8 = load("r01_bench_1gpu.json"), load("r01_bench_2gpu.json"), load("r01_bench_8gpu.json")
+
+b = {n: load(f"r02_bench_{n}gpu.json") for n in (1, 2, 4, 8)}
+old = {n: load(f"r01_bench_{n}gpu.json") for n in (1, 2, 8)}
+b1 = b[1]
 peak = b1["roofline"]["peak"]
 out = []
-out.append("# profiles/ — round-1 measurements and ncu evidence (B200, sm_100a)\n")
-out.append("All numbers are CUDA-event timings from `bench.py` on a `gpurun` B200 box (no profiler attached); the ncu files are for "
-           "per-kernel shares, DRAM traffic and stall reasons only. Roofline denominator: **measured** HBM copy bandwidth "
-           f"{peak:.0f} GB/s (`MEASURED_PEAKS.json`, \"of measured\").\n")
-out.append("## Headline (BASELINE.json metric: forward-PBR @4K)\n")
-out.append("| N GPUs | Mpixels/s (HBM-resident) | ms/step | HBM frac (algorithmic 64 B/px) | e2e Mpixels/s (host buffers, PCIe inside) | with all-gather of tiles |")
-out.append("|---|---|---|---|---|---|")
-for b in (b1, b2, b8):
-    if not b: continue
-    ag = b.get("allgather")
-    out.append(f"| {b['n_gpus']} | {b['value']:.0f} | {b['ms_per_step']:.4f} | {b['roofline']['frac']:.3f} | {b['e2e']['value']:.0f} | "
-               + (f"{ag['value_with_allgather']:.0f} Mpx/s ({ag['ms_per_step_with_allgather']:.3f} ms/step)" if ag else "—") + " |")
+out.append("# profiles/ — round-2 measurements and ncu evidence (B200, sm_100a)\n")
+out.append("All numbers are CUDA-event timings from `bench.py` on `gpurun` B200 boxes (no profiler attached); the ncu files are for per-kernel "
+           f"shares, DRAM traffic and stall reasons only. Roofline denominator: **measured** HBM copy bandwidth {peak:.0f} GB/s "
+           "(`MEASURED_PEAKS.json`, \"of measured\"). Round 1's report: `r01_README.md`.\n")
+
+out.append("## Headline (BASELINE.json metric: forward-PBR @4K), 1 GPU\n")
+r = b1["roofline"]
+o1 = old[1]
+out.append("| | round 1 | round 2 |")
+out.append("|---|---|---|")
+out.append(f"| K1 4K step | {o1['ms_per_step']:.4f} ms, {o1['value']:.0f} Mpixels/s | **{b1['ms_per_step']:.4f} ms, {b1['value']:.0f} Mpixels/s** |")
+out.append(f"| fraction of the HBM roofline (64 B/px algorithmic, of measured) | {o1['roofline']['frac']:.3f} | **{r['frac']:.3f}** |")
+if r.get("issue"):
+    out.append(f"| warp-instructions per 4K launch (ncu) | 234.2 M (904 per 32 pixels) | {r['issue']['warp_instructions_per_4k_launch'] / 1e6:.1f} M "
+               f"({r['issue']['warp_instructions_per_4k_launch'] / (3840 * 2160 / 32):.0f} per 32 pixels); issue floor {r['issue']['issue_floor_ms_4k']:.4f} ms, "
+               f"the step runs at {r['issue']['frac_of_issue_floor']:.2f} of it |")
+out.append(f"| DRAM traffic per launch (ncu) vs algorithmic | 649.0 MB vs 530.8 MB | {(r.get('traffic') or 0) / 1e6:.1f} MB vs {r['algorithmic_bytes_per_launch'] / 1e6:.1f} MB |")
+out.append(f"| e2e (host buffers, PCIe inside the timed region) | {o1['e2e']['value']:.0f} Mpixels/s | {b1['e2e']['value']:.0f} Mpixels/s (PCIe-bound: {(b1['e2e']['h2d_bytes_per_step'] + b1['e2e']['d2h_bytes_per_step']) / 1e6:.0f} MB per frame) |")
 cb = b1.get("cpu_baseline")
 if cb:
-    out.append(f"\nCPU baseline (scalar C++ oracle = CPU port of the HLSL, all host threads): **{cb['value']:.1f} Mpixels/s on {cb['cores']} cores** — {cb['sample']}.")
-    out.append(f"GPU/CPU = {b1['value'] / cb['value']:.0f}x (HBM-resident), {b1['e2e']['value'] / cb['value']:.0f}x end to end. (A large ratio says nothing about kernel quality; the roofline fraction does.)\n")
-out.append(f"Clocks during the timed region: {b1.get('clocks')}\n")
-out.append("## IBL specular prefilter, strong scaling (BASELINE config 5: 4096x2048 HDRI -> 512^2 x6 x9 mips, 512 samples)\n")
-out.append("| N GPUs | ms (compute + all-gather of the 33.5 MB cubemap) | texels/s | compute only ms | speed-up vs 1 GPU |")
-out.append("|---|---|---|---|---|")
-base = None
-for b in (b1, b2, b8):
-    if not b or "ibl_specular_prefilter_strong" not in b: continue
-    s = b["ibl_specular_prefilter_strong"]
-    base = base or s["ms"]
-    out.append(f"| {b['n_gpus']} | {s['ms']:.3f} | {s['texels_per_s']:.3e} | {s['ms_compute_only']:.3f} | {base / s['ms']:.2f}x |")
+    out.append(f"\nCPU baseline (scalar C++ oracle = CPU port of the HLSL, one process per host core, IBL maps at the GPU arm's sizes): "
+               f"**{cb['value']:.1f} Mpixels/s on {cb.get('processes', '?')} processes = {cb['cores']} effective cores** — {cb['sample']}.")
+    out.append(f"GPU/CPU = {b1['value'] / cb['value']:.0f}x (HBM-resident), {b1['e2e']['value'] / cb['value']:.0f}x end to end. "
+               "(A large ratio says nothing about kernel quality; the roofline fraction does.)\n")
+out.append(f"Clocks during the timed region: {b1.get('clocks')}; host threads pinned: {b1['config'].get('host_numa')}\n")
+
+multi = [n for n in (2, 4, 8) if b[n]]
+if multi:
+    out.append("## Multi-GPU: BASELINE config 5's 7680x4320 frame, strong-scaled; `value` = ONE fused kernel per rank (shade + peer-store assembly + in-kernel rendezvous)\n")
+    out.append("| N | value: fused step, Mpixels/s (ms) | kernel only (no assembly) | kernel + NCCL all-gather | NVLink ingress per rank | = NCCL result | e2e Mpixels/s |")
+    out.append("|---|---|---|---|---|---|---|")
+    for n in multi:
+        x = b[n]; a = x["allgather"]; f = a["fused_p2p"]
+        out.append(f"| {n} | **{x['value']:.0f}** ({x['ms_per_step']:.3f}) | {a['kernel_only']['value']:.0f} ({a['kernel_only']['ms_per_step']:.3f}) | "
+                   f"{a['nccl_allgather']['value']:.0f} ({a['nccl_allgather']['ms_per_step']:.3f}) | {f['nvlink_ingress_bytes_per_rank'] / 1e6:.0f} MB at "
+                   f"{f['nvlink_ingress_GBps_per_rank']:.0f} GB/s (900 nominal) | {f['equals_nccl_allgather']} | {x['e2e']['value']:.0f} |")
+    out.append("\nOne GPU shades the 4K frame at "
+               f"{b1['value']:.0f} Mpixels/s; the assembled-frame throughput is bounded by NVLink ingress from N = 4 on ((N-1)/N x 531 MB must arrive at every rank).\n")
+
+out.append("## IBL specular prefilter, strong scaling (BASELINE config 5: 4096x2048 HDRI -> 512^2 x6 x9 mips, 512 samples; target >= 6x at 8 GPUs)\n")
+out.append("| N | compute only, ms | + NCCL all-gather, ms | fused peer stores + in-kernel rendezvous (ONE kernel), ms | speed-up of the fused step vs 1 GPU | = NCCL result |")
+out.append("|---|---|---|---|---|---|")
+base = b1["ibl_specular_prefilter_strong"]["ms"]
+out.append(f"| 1 | {base:.3f} | — | — | 1.00x | — |")
+for n in multi:
+    s = b[n].get("ibl_specular_prefilter_strong")
+    if not s:
+        continue
+    f = s.get("fused_p2p") or {}
+    fms = f.get("ms")
+    out.append(f"| {n} | {s['ms_compute_only']:.3f} | {s['ms']:.3f} ({base / s['ms']:.2f}x) | " + (f"**{fms:.3f}**" if fms else f"{f}") + " | "
+               + (f"**{base / fms:.2f}x**" if fms else "—") + f" | {f.get('equals_nccl_allgather')} |")
+if old[8] and "ibl_specular_prefilter_strong" in old[8]:
+    so = old[8]["ibl_specular_prefilter_strong"]
+    out.append(f"\nRound 1 at 8 GPUs (one launch per mip, host barrier): {so['ms']:.3f} ms with NCCL; driver's SCALE_r01: 4.97x NCCL / 5.75x fused.")
+
 ex = b1.get("extra", {})
+oex = o1.get("extra", {})
 out.append("\n## Per-kernel table (1 GPU, 3840x2160 unless stated)\n")
-out.append("| pass | ms | algorithmic GB/s | frac of measured HBM peak | note |")
-out.append("|---|---|---|---|---|")
-out.append(f"| K1 forward PBR (4 point + 1 dir + IBL) | {b1['ms_per_step']:.4f} | {b1['roofline']['achieved']:.0f} | {b1['roofline']['frac']:.3f} | bound by the L1 data pipe (gather wavefronts, 64 %) and instruction issue (70 % active, ~880 instr/pixel): r01_forward_g_summary.txt, r01_forward_f_l1bound.txt; DRAM traffic {b1['roofline'].get('traffic')} B vs algorithmic {b1['roofline']['algorithmic_bytes_per_launch']} B |")
+out.append("| pass | ms | algorithmic GB/s | frac of measured HBM peak | round 1 ms | note |")
+out.append("|---|---|---|---|---|---|")
+out.append(f"| K1 forward PBR (4 point + 1 dir + IBL) | {b1['ms_per_step']:.4f} | {r['achieved']:.0f} | {r['frac']:.3f} | {o1['ms_per_step']:.4f} | latency-bound on its gathers: "
+           "issue 56 %, L1 data pipe 55 %, FMA 45 % (r02_forward_b_summary.txt) |")
 names = [("spd", "K10 SPD (11 mips)"), ("blur_x", "K5 blur X"), ("blur_y", "K5 blur Y"), ("tonemap", "K6 tonemap sRGB"), ("cas", "K7 CAS"),
          ("fsr_easu_2x", "K8 EASU 4K->8K"), ("fsr_rcas_8k", "K9 RCAS @8K"), ("post_chain_4k", "post chain total (config 4)")]
+notes = {"fsr_easu_2x": "2x2 output quad per thread, packed fp32x2 (r02_post_variants.txt)",
+         "tonemap": "the 133 MB output is partly still in the 126 MB L2 when the kernel retires: ~0.75 of the real DRAM traffic rate (ncu r01_post_b)",
+         "blur_y": "see tonemap", "cas": "see tonemap", "fsr_rcas_8k": "see tonemap"}
 for k, label in names:
     if k in ex:
         e = ex[k]
-        out.append(f"| {label} | {e['ms']:.4f} | {e['algorithmic_GBps']:.0f} | {e['hbm_frac']:.3f} | |")
+        out.append(f"| {label} | {e['ms']:.4f} | {e['algorithmic_GBps']:.0f} | {e['hbm_frac']:.3f} | {oex.get(k, {}).get('ms', '—')} | {notes.get(k, '')} |")
 for k, label in [("ibl_specular_prefilter", "K3 specular prefilter"), ("ibl_diffuse_irradiance", "K2 diffuse irradiance (config 2)"),
                  ("ibl_diffuse_irradiance_reference_step", "K2 diffuse, engine step 0.010"), ("brdf_lut", "K4 BRDF LUT"), ("hdri_min_pyramid", "K11 HDRI min pyramid")]:
     if k in ex:
         e = ex[k]
         rate = f"{e.get('texels_per_s', 0):.3e} texels/s, " if "texels_per_s" in e else ""
         rate += f"{e.get('samples_per_s', 0):.3e} samples/s" if "samples_per_s" in e else (f"{e.get('algorithmic_GBps')} GB/s" if "algorithmic_GBps" in e else "")
-        out.append(f"| {label} | {e['ms']:.4f} | — | — | {e.get('config', '')}; {rate} (SFU/FP32-bound, HBM % is low by construction) |")
+        out.append(f"| {label} | {e['ms']:.4f} | — | — | {oex.get(k, {}).get('ms', '—')} | {e.get('config', '')}; {rate} (SFU/FP32-bound, HBM % is low by construction) |")
 out.append("\n## SURVEY 8(f) rows (1 GPU)\n")
 out.append("| pass | ms | algorithmic GB/s | frac of measured HBM peak | note |")
 out.append("|---|---|---|---|---|")
 for k, label in [("surface_producer_4k", "(f).1 surface producer 4K"), ("texture_box_mips_4096", "(f).1 RGBA8 box mips 4096^2"),
                  ("hdr_decode_4096x2048", "(f).2 .hdr decode 4096x2048"), ("hdr_encode_rgbe_4096x2048", "(f).2 RGBE encode 4096x2048"),
                  ("image_resize_4096x2048_to_2048x1024", "(f).2 Mitchell downsize 4096x2048 -> 2048x1024"),
-                 ("skydome_4k", "(f).3 skydome 4K"), ("apply_reflections_4k", "(f).3 ApplyReflections 4K")]:
+                 ("skydome_4k", "(f).3 skydome 4K"), ("apply_reflections_4k", "(f).3 ApplyReflections 4K"), ("depth_min_pyramid_4k", "(f).4 MIN depth pyramid 4K")]:
     if k in ex:
         e = ex[k]
         note = e.get("config", "")
         for kk in ("e2e_host_file_to_device_image_ms", "e2e_device_image_to_host_file_ms"):
-            if kk in e: note += f"; {kk} = {e[kk]}"
+            if kk in e:
+                note += f"; {kk} = {e[kk]}"
         out.append(f"| {label} | {e['ms']:.4f} | {e['algorithmic_GBps']:.0f} | {e['hbm_frac']:.3f} | {note} |")
+if "forward_4k_casters_shadowed" in ex:
+    e = ex["forward_4k_casters_shadowed"]
+    out.append(f"| (f).4 forward pass with shadow maps bound 4K | {e['ms']:.4f} | — | — | {e['casters']}; the same lights unshadowed: {e['ms_same_lights_unshadowed']} ms; "
+               "every PCF operation rounded as the oracle does (correctly rounded divisions / square roots): a bit-faithful restatement, not yet a fast one |")
 ric = b1.get("cpu_baseline_image_class")
 if ric and "error" not in ric:
     out.append(f"\nReference CPU path for the (f).2 rows (the engine's own `Image` class compiled unmodified, 1 host core, same 4096x2048 HDRI): "
                f"`Image::LoadFromFile` {ric['image_load_from_file_ms']} ms, `Image::CreateResizedImage` to half size {ric['image_create_resized_half_ms']} ms, "
                f"`Image::SaveToDisk` {ric['image_save_to_disk_ms']} ms.")
-fp = [(b['n_gpus'], b["ibl_specular_prefilter_strong"].get("fused_p2p")) for b in (b2, b8) if b and "ibl_specular_prefilter_strong" in b]
-fp = [(n, f) for n, f in fp if f and "ms" in f]
-if fp:
-    out.append("\nFused compute + gather for the specular prefilter (`vq_specular_prefilter_multi`, peer stores over NVLink): "
-               + ", ".join(f"{n} GPUs {f['ms']:.3f} ms ({base / f['ms']:.2f}x vs 1 GPU, equals NCCL result: {f.get('equals_nccl_allgather')})" for n, f in fp) + ".")
-out.append("\nIs the CPU baseline (`\"kind\": \"port\"`, the scalar oracle) a fair stand-in for the reference's own code? Measured in the build container "
-           "(one core, 256x128 px, 4 textured materials, 3 point + 2 spot + directional lights + IBL; `tests/test_hlsl_ref.py` scene): the oracle "
-           "(surface producer + forward pass) takes 653 ns/pixel, the reference's `ForwardLighting.hlsl` `PSMain` compiled as C++ "
-           "(`oracle/_ref/libhlslref.so`) takes 718 ns/pixel for the identical, bit-identical work: the port is not slower than the reference text. "
-           "`bench.py --impl reference` now times that compiled shader text itself (one process per core), and both CPU arms use processes instead of "
-           "threads: in the build container 8 threads of one process ran at 1.0x of one thread, 8 forked processes at 5x (10.8 Mpixels/s shader text, "
-           "10-12 Mpixels/s port), so the 25.4 Mpixels/s recorded above on the GPU box (threaded form, 128 listed cores) understates what its CPUs can do.")
+
 out.append("\n## How these were produced\n")
 out.append("All on `gpurun` B200 boxes from this tree (scripts under `tools/`):\n")
-out.append("* `bash tools/gpu_full.sh` — `pytest -m gpu` (-> `r01_gpu_tests.txt`), `python bench.py` (-> `r01_bench_1gpu.json`), "
-           "`ncu --set full --clock-control none --import-source on -k regex:forward_kernel -s 8 -c 1` over `tools/perf_forward.py` "
-           "(-> `r01_forward_g_summary.txt` via `tools/ncu_summary.py`), the same over `tools/run_pass.py frame` (-> `r01_frame_a_summary.txt`), "
-           "`ncu --metrics gpu__time_duration.sum --clock-control none -c 700 --csv` over `bench.py --steps 2 --warmup 1` (-> `r01_launches_bench.csv`; "
-           "cold, serialised per-launch times: shares only), `compute-sanitizer --tool memcheck python tools/sanitize_small.py` "
-           "(-> `r01_sanitize_memcheck.txt`), `vq_headless_test -TestFrames=100` (-> `r01_headless_100frames.txt`).")
-out.append("* `bash tools/gpu_2gpu.sh` under `gpurun --gpus 2` — the driver's torchrun command for `bench.py --gpus 2` (-> `r01_bench_2gpu.json`).")
-out.append("* `bash tools/gpu_variants.sh <names>` — A/B timings of K1 builds in `variants/` + the decomposition run (-> `r01_forward_variants.txt`).")
-out.append("* `r01_bench_8gpu.json`, `r01_topo_8gpu.txt`, `r01_forward_d/e_summary.txt`, `r01_post_b_summary.txt`, `r01_ibl_a_summary.txt`, "
-           "`r01_surface_*`: earlier in round 1 (K1 has changed since: its 8-GPU line is from the previous kernel build).")
+out.append("* `bash tools/gpu_full.sh` — `pytest -m gpu` (-> `r02_gpu_tests.txt`), smoke, `python bench.py --gpus 1` (-> `r02_bench_1gpu.json`).")
+out.append("* `bash tools/gpu_2gpu.sh N` under `gpurun --gpus N` — the driver's torchrun command for `bench.py --gpus N` (-> `r02_bench_{2,4,8}gpu.json`).")
+out.append("* `bash tools/gpu_k1.sh [variants]` — K1 at 4K, the forward parity tests, `ncu --set full --clock-control none --import-source on -k regex:forward_kernel` "
+           "over `tools/perf_forward.py` (-> `r02_forward_{a,b}_summary.txt` via `tools/ncu_summary.py`, `forward_traffic.json` via `tools/make_forward_traffic.py`); "
+           "A/B logs `r02_forward_variants_{a,b,c,d}.txt`.")
+out.append("* `bash tools/gpu_ab.sh <variants>` — K1 + 2x EASU A/B over builds in `variants/` (-> `r02_post_variants.txt`); `tools/ubench_gather.cu` "
+           "(-> `r02_ubench_gather.txt`): what a warp-wide gather costs in the L1 data pipe.")
+out.append("* `python tests/diag_fullsize.py` (-> `r02_diag_fullsize.txt`): where the first full-size parity run disagreed with the oracle, and why (DESIGN.md §5).")
+out.append("* `r02_shadow_first_run.txt`, `r02_shadow_a_summary.txt`: the first execution of the (f).4 kernels (15 parity tests, timings, memcheck, ncu).")
 out.append("\n## Files\n")
 for f in sorted(os.listdir(P)):
     if f != "README.md":
