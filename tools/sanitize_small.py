@@ -43,6 +43,27 @@ out2 = torch.zeros((9, 300, 4), device="cuda")
 ctx.forward_lighting(pf2, pv2, vq.GBuffer(vq.image_of(planes2[0]), vq.image_of(planes2[1]), vq.image_of(planes2[2]), vq.null_image()), em, out2)
 ctx.forward_lighting_multi(pf, pv, gb, em, [vq.image_of(out), vq.image_of(torch.zeros_like(out))], 0)
 ctx.specular_prefilter_multi(pyr, [vq.cubemap_of(spec, 16, 4), vq.cubemap_of(torch.zeros_like(spec), 16, 4)], 64)
+# round 2: the persistent range-list launch (two destinations, cuts through mip 0 and the middle of faces) and the in-kernel
+# rendezvous of both fused kernels with the flag arrays of a 2-"rank" world living on this one GPU (rank 0's peer already at epoch 1)
+ctx.specular_prefilter_ranges(pyr, [vq.cubemap_of(spec, 16, 4), vq.cubemap_of(torch.zeros_like(spec), 16, 4)], [(0, 5), (5, 37), (40, 150)], 64)
+flags = torch.zeros((2, 2), dtype=torch.int32, device="cuda"); flags[0, 1] = 1          # [rank][word]: word 1 of rank 0's array set by "rank 1"
+sig = vq.PeerSignal(); sig.flags[0] = flags[0].data_ptr(); sig.flags[1] = flags[1].data_ptr(); sig.n_ranks, sig.my_index, sig.epoch = 2, 0, 1
+ctx.specular_prefilter_ranges(pyr, [vq.cubemap_of(spec, 16, 4), vq.cubemap_of(torch.zeros_like(spec), 16, 4)], [(0, 96)], 64, signal=sig)
+ctx.forward_lighting_multi(pf, pv, gb, em, [vq.image_of(out), vq.image_of(torch.zeros_like(out))], 0, signal=sig)
+torch.cuda.synchronize(); assert int(flags[1, 0]) == 1, "the rendezvous did not signal the peer"
+# the shadowed pass and the depth pyramid
+pfs, pvs = synth.scene_constants(64, 40, 4, n_point=2, n_spot=1, casters=True)
+pfs.Lights.directional.shadowing = 1
+for sc_ in range(pfs.Lights.numSpotCasters):
+    pfs.Lights.shadowViews[sc_].m[0] = pfs.Lights.shadowViews[sc_].m[5] = 0.04; pfs.Lights.shadowViews[sc_].m[14] = 0.5; pfs.Lights.shadowViews[sc_].m[15] = 1.0
+pfs.Lights.shadowViewDirectional.m[0] = pfs.Lights.shadowViewDirectional.m[5] = 0.04; pfs.Lights.shadowViewDirectional.m[14] = 0.5; pfs.Lights.shadowViewDirectional.m[15] = 1.0
+pfs.f2SpotLightShadowMapDimensions.x = pfs.f2SpotLightShadowMapDimensions.y = 16.0
+pfs.f2DirectionalLightShadowMapDimensions.x = pfs.f2DirectionalLightShadowMapDimensions.y = 16.0
+gb3 = vq.GBuffer(vq.image_of(planes[0]), vq.image_of(planes[1]), vq.image_of(planes[2]), vq.null_image())
+ctx.forward_lighting_shadowed(pfs, pvs, gb3, em, out, torch.rand((max(pfs.Lights.numPointCasters, 1), 6, 8, 8), device="cuda"),
+                              torch.rand((max(pfs.Lights.numSpotCasters, 1), 16, 16), device="cuda"), torch.rand((16, 16), device="cuda"))
+depth = torch.rand((37, 53), device="cuda"); nlev = vq.depth_pyramid_level_count(53, 37)
+ctx.depth_min_pyramid(depth, torch.empty((vq.depth_pyramid_texel_count(53, 37, nlev),), device="cuda"))
 # SURVEY 8(f).1 (bench.surface_scene_gpu builds the mip chains with vq_texture_build_mips and a material table)
 import bench
 sc = bench.surface_scene_gpu(ctx, vq, torch, 64, 38, n_materials=3, tex_res=64)
