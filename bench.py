@@ -397,6 +397,51 @@ def shadow_passes(ctx, vq, torch, envk, peak):
     return r
 
 
+def ibl_rows_strong_scaling(ctx, vq, torch, dist, rank, world, envk, iters=20):
+    """the diffuse-irradiance cube (BASELINE config 2 grid; the engine's step 0.010 as well) and the
+    BRDF LUT strong-scaled by contiguous row blocks — every C-ABI pass takes [row_begin,row_end) — with ONE NCCL all-gather of the rows
+    inside the timed region (393 KB / 8 MB: nothing worth fusing)."""
+    from vqengine_b200 import distributed as vd
+    out = {}
+    pyr = envk["pyr"]
+
+    def timed(fn, n):
+        for _ in range(2):
+            fn()
+        torch.cuda.synchronize(); dist.barrier(); torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(n):
+            fn()
+        e1.record(); torch.cuda.synchronize()
+        t = torch.tensor([e0.elapsed_time(e1) / n], dtype=torch.float64, device="cuda")
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t[0])
+
+    res = 64
+    rows = 6 * res
+    if rows % world == 0:
+        cube = torch.zeros((rows * res, 4), dtype=torch.float32, device="cuda")
+        rb, re = vd.equal_tiles(rows, world)[rank]
+        mine = cube[rb * res:re * res]
+        for name, kw, n in (("diffuse_irradiance_config2", dict(n_phi=64, n_theta=16, src_mip=3), iters), ("diffuse_irradiance_step_0.010", dict(step=0.01, src_mip=3), 3)):
+            def step():
+                ctx.diffuse_irradiance(pyr, vq.cubemap_of(cube, res, 1), row_begin=rb, row_end=re, **kw)
+                dist.all_gather_into_tensor(cube, mine)
+            out[name] = {"ms": round(timed(step, n), 4), "rows_per_rank": re - rb}
+    lut = torch.zeros((1024, 1024, 2), dtype=torch.float32, device="cuda")
+    if 1024 % world == 0:
+        rb, re = vd.equal_tiles(1024, world)[rank]
+        mine = lut[rb:re]
+
+        def step():
+            ctx.brdf_integration_lut(lut, 2048, rb, re)
+            dist.all_gather_into_tensor(lut, mine)
+        out["brdf_lut_1024"] = {"ms": round(timed(step, 5), 4), "rows_per_rank": re - rb}
+    out["note"] = "row blocks per rank + one NCCL all-gather per step; 1-GPU times are in the N = 1 line's `extra`"
+    return out
+
+
 class PeerFlags:
     """world 32-bit flag words per rank in symmetric memory + the VqPeerSignal that points at them: the rendezvous a fused
     compute+gather kernel runs in its last CTA (include/vqcuda.h). `next()` advances the epoch for one more step."""
@@ -956,6 +1001,10 @@ def main():
         ibl_strong = ibl_specular_strong_scaling(ctx, vq, torch, dist, rank, world)
     if rank == 0 and ibl_strong is not None:
         line["ibl_specular_prefilter_strong"] = ibl_strong
+    if world > 1 and not args.no_extra:
+        small = ibl_rows_strong_scaling(ctx, vq, torch, dist, rank, world, envk)
+        if rank == 0:
+            line["ibl_rows_strong"] = small
     if world == 1 and rank == 0:
         if not args.no_extra:
             line["extra"] = extra_passes(ctx, vq, torch, envk, peak)
