@@ -358,6 +358,11 @@ __device__ __forceinline__ void shade_all_lights(const Px2& s, Acc2& acc, const 
     const int numPoint = P.numPoint, numSpot = P.numSpot;
     // ---- point lights, then unshadowed point casters (Lighting.hlsl:308-322; PSMain :310-313,321-340):
     //      in range <=> d2 < d2Limit (== length(Lw-P) < l.range, exactly) ----
+#ifndef FWD_LIGHT_UNROLL
+#define FWD_LIGHT_UNROLL 1      // 2: two lights interleaved (more ILP for the dependent MUFU/FMA chains, ~20 more registers)
+#endif
+    constexpr int kLightUnroll = FWD_LIGHT_UNROLL;
+#pragma unroll kLightUnroll
     for (int i = 0; i < numPoint; ++i) {
         const SPoint l = P.pts[i];                                       // constant bank, warp-uniform index
         const LightVec2 L = light_vector2(s, l.pos);
@@ -447,10 +452,10 @@ __device__ __forceinline__ void st_stream_hint(float4* p, float4 v, uint64_t pol
 // stored. Nothing of the G-buffer is live in registers across the light loop: albedo/metalness/ao, the raw
 // normal and the emissive texel are (re-)read from the stage after it.
 #ifndef FWD_STAGES
-#define FWD_STAGES 3           // shared-memory stages
+#define FWD_STAGES 2           // shared-memory stages
 #endif
 #ifndef FWD_AHEAD
-#define FWD_AHEAD 2            // tiles requested ahead of the one being shaded (< FWD_STAGES)
+#define FWD_AHEAD 1            // tiles requested ahead of the one being shaded (< FWD_STAGES)
 #endif
 #ifndef FWD_CTAS_PER_SM
 #define FWD_CTAS_PER_SM 4
@@ -538,38 +543,46 @@ __device__ __forceinline__ float2 lut_finish(const LutLoad& L) {    // record = 
 //   texel : shared-memory address of the pixel's position texel,  V/nsnv : normalize(cam-P), saturate(dot(s.N, V))
 //   la/lb/lc : the light sums  sum w*col*{(1-fc), fc*spec, spec}
 //   Ns : the surface normal as normalize(Ns)*|Ns| (within an ulp of the raw texel; it only steers the two cube lookups)
-// (Tried, A/B on B200: issuing BOTH pixels' ten gathers before either is consumed, so that a thread waits for the L2/HBM latency
-//  once per pair — ncu r02a shows a third of all stall samples on the first use of pixel A's taps and again on pixel B's. Ten
-//  256-bit loads in flight need 159 registers; at the 128 of four CTAs per SM the spills go through the same L1 data pipe that
-//  bounds the kernel. Not kept.)
-template <bool ROT>
-__device__ __forceinline__ float4 finish_pixel(const FwdParams& P, const FaceRec* __restrict__ sFace, uint32_t texel, float3 V, float nsnv,
-                                               float3 Ns, float roughness, float ao, float3 la, float3 lb, float3 lc) {
-    // ---- environment taps. Order tuned on B200 (profiles/r01_forward_variants.txt): the two diffuse-cube loads go out first
-    //      and fly while the specular address math runs; then the specular cube and the LUT. ----
-    float3 specCol = f3(0.0f), diffIrr; float2 sb = make_float2(0.0f, 0.0f);
-    {
-        const float3 Nr = ROT ? f3(Ns.x * P.cosB - Ns.z * P.sinB, Ns.y, Ns.x * P.sinB + Ns.z * P.cosB) : Ns;
-        int face; float sx, sy;
-        dir_to_face(Nr, face, sx, sy);
-        FaceRec fd; fd.P = (uint32_t)P.diff.res + 2u; fd.base = (uint32_t)face * fd.P * fd.P; fd.halfN = P.diffHalfN; fd.c0 = P.diffHalfN - 0.5f;
-        const CubeLoad ldD = cube_issue<FWD_L1_DIFF>(P.diff.p, fd, P.diffMaxRec, sx, sy);
-        if (!P.diffuseOnly) {
-            const float3 R0 = reflect(-V, Ns);
-            const float3 R = ROT ? f3(R0.x * P.cosB - R0.z * P.sinB, R0.y, R0.x * P.sinB + R0.z * P.cosB) : R0;
-            dir_to_face(R, face, sx, sy);
-            const int mip = min(max((int)(roughness * (float)P.maxLod), 0), P.spec.mips - 1);
-            const CubeLoad ldS = cube_issue<FWD_L1_SPEC>(P.spec.p, sFace[face * 16 + mip], P.specMaxRec, sx, sy);
-            const LutLoad ldL = lut_issue(P.lut, nsnv, roughness);               // (saturate(dot(s.N, V)), roughness)
-            specCol = cube_finish(ldS); sb = lut_finish(ldL);
-        }
-        diffIrr = cube_finish(ldD);
+// The environment lookups of one pixel, split into "issue" (the five 256-bit gathers: diffuse cube x2, specular cube x2, LUT, with
+// their bilinear weights) and "compose" (the blends + the final composition), so that the kernel can put BOTH pixels' gathers in
+// flight before it consumes either (FWD_JOINT_ISSUE): a thread then waits for the L2/HBM latency once per pair instead of once per
+// pixel (ncu: a third of all stall samples sit on the first use of pixel A's taps and again on pixel B's). Ten 256-bit loads in
+// flight need ~160 registers, i.e. three CTAs per SM instead of four: A/B in profiles/r02_forward_variants_e.txt.
+//   Ns : the surface normal as normalize(Ns)*|Ns| (within an ulp of the raw texel; it only steers the two cube lookups)
+#ifndef FWD_JOINT_ISSUE
+#define FWD_JOINT_ISSUE 1
+#endif
+struct EnvLoads { CubeLoad D, S; LutLoad L; };
+template <bool ROT, bool SPEC>
+__device__ __forceinline__ void env_issue(EnvLoads& E, const FwdParams& P, const FaceRec* __restrict__ sFace, float3 V, float nsnv, float3 Ns, float roughness) {
+    const float3 Nr = ROT ? f3(Ns.x * P.cosB - Ns.z * P.sinB, Ns.y, Ns.x * P.sinB + Ns.z * P.cosB) : Ns;
+    int face; float sx, sy;
+    dir_to_face(Nr, face, sx, sy);
+    FaceRec fd; fd.P = (uint32_t)P.diff.res + 2u; fd.base = (uint32_t)face * fd.P * fd.P; fd.halfN = P.diffHalfN; fd.c0 = P.diffHalfN - 0.5f;
+    E.D = cube_issue<FWD_L1_DIFF>(P.diff.p, fd, P.diffMaxRec, sx, sy);
+    if (SPEC) {
+        const float3 R0 = reflect(-V, Ns);
+        const float3 R = ROT ? f3(R0.x * P.cosB - R0.z * P.sinB, R0.y, R0.x * P.sinB + R0.z * P.cosB) : R0;
+        dir_to_face(R, face, sx, sy);
+        const int mip = min(max((int)(roughness * (float)P.maxLod), 0), P.spec.mips - 1);
+        E.S = cube_issue<FWD_L1_SPEC>(P.spec.p, sFace[face * 16 + mip], P.specMaxRec, sx, sy);
+        E.L = lut_issue(P.lut, nsnv, roughness);                                 // (saturate(dot(s.N, V)), roughness)
     }
+}
+// the final composition of the pixel (PSMain :290-293, Lighting.hlsl:360-395, BRDF.hlsl:177-207)
+//   texel : shared-memory address of the pixel's position texel,  nsnv : saturate(dot(s.N, V))
+//   la/lb/lc : the light sums  sum w*col*{(1-fc), fc*spec, spec}
+template <bool SPEC>
+__device__ __forceinline__ float4 compose_pixel(const FwdParams& P, uint32_t texel, float nsnv, float roughness, float ao,
+                                                float3 la, float3 lb, float3 lc, const EnvLoads& E) {
+    float3 specCol = f3(0.0f); float2 sb = make_float2(0.0f, 0.0f);
+    if (SPEC) { specCol = cube_finish(E.S); sb = lut_finish(E.L); }
+    const float3 diffIrr = cube_finish(E.D);
     // ---- the rest of the G-buffer texel comes out of the stage only now ----
     const float4 am = lds128(texel + 2u * FWD_PLANE);
     const float3 albedo = xyz(am);
     const float metalness = am.w;
-    float3 I = albedo * ao;                                  // the ambient factor rides in position.w                                  // ForwardLighting.hlsl:290-293
+    float3 I = albedo * ao;                                  // ForwardLighting.hlsl:290-293 (the ambient factor rides in position.w)
     if (P.hasEmissive) {
         const float4 em = lds128(texel + 3u * FWD_PLANE);
         I += xyz(em) * em.w;
@@ -594,6 +607,34 @@ __device__ __forceinline__ float4 finish_pixel(const FwdParams& P, const FaceRec
         I.z += (1.0f - Ks.z) * om * (diffIrr.z * albedo.z) + specCol.z * fmaf(Ks.z, sb.x, sb.y);
     }
     return make_float4(I.x, I.y, I.z, roughness);                // :380
+}
+
+// everything after the light loop for the pixel pair: environment taps, composition, stores
+template <bool MULTI, bool ROT, bool SPEC>
+__device__ __forceinline__ void finish_pair(const FwdParams& P, const FaceRec* __restrict__ sFace, const Px2& s, const Acc2& acc, f2 roughness, f2 ao,
+                                            int y, int xA, int xB, bool validA, bool validB) {
+    const f2 nsnv = mulsat2(s.nsLen, s.nv);                      // saturate(dot(s.N, V)) of the raw normal
+    const f2 Nrx = s.Nx * s.nsLen, Nry = s.Ny * s.nsLen, Nrz = s.Nz * s.nsLen;
+    EnvLoads eA, eB;
+    env_issue<ROT, SPEC>(eA, P, sFace, f3(s.Vx.v.x, s.Vy.v.x, s.Vz.v.x), nsnv.v.x, f3(Nrx.v.x, Nry.v.x, Nrz.v.x), roughness.v.x);
+#if FWD_JOINT_ISSUE
+    env_issue<ROT, SPEC>(eB, P, sFace, f3(s.Vx.v.y, s.Vy.v.y, s.Vz.v.y), nsnv.v.y, f3(Nrx.v.y, Nry.v.y, Nrz.v.y), roughness.v.y);
+#endif
+    const float4 oA = compose_pixel<SPEC>(P, s.texA, nsnv.v.x, roughness.v.x, ao.v.x, f3(acc.ax.v.x, acc.ay.v.x, acc.az.v.x),
+                                          f3(acc.bx.v.x, acc.by.v.x, acc.bz.v.x), f3(acc.cx.v.x, acc.cy.v.x, acc.cz.v.x), eA);
+    if (validA) {   // one STG.128 per destination; peer destinations are mapped NVLink addresses (fused compute + gather)
+        if (MULTI) { for (int q = 0; q < P.nOut; ++q) st_stream(P.outs[q].row(P.dstRowOffset + y) + xA, oA); }
+        else st_stream_hint(P.outs[0].row(P.dstRowOffset + y) + xA, oA, l2_evict_first_policy());
+    }
+#if !FWD_JOINT_ISSUE
+    env_issue<ROT, SPEC>(eB, P, sFace, f3(s.Vx.v.y, s.Vy.v.y, s.Vz.v.y), nsnv.v.y, f3(Nrx.v.y, Nry.v.y, Nrz.v.y), roughness.v.y);
+#endif
+    const float4 oB = compose_pixel<SPEC>(P, s.texB, nsnv.v.y, roughness.v.y, ao.v.y, f3(acc.ax.v.y, acc.ay.v.y, acc.az.v.y),
+                                          f3(acc.bx.v.y, acc.by.v.y, acc.bz.v.y), f3(acc.cx.v.y, acc.cy.v.y, acc.cz.v.y), eB);
+    if (validB) {
+        if (MULTI) { for (int q = 0; q < P.nOut; ++q) st_stream(P.outs[q].row(P.dstRowOffset + y) + xB, oB); }
+        else st_stream_hint(P.outs[0].row(P.dstRowOffset + y) + xB, oB, l2_evict_first_policy());
+    }
 }
 
 template <bool MULTI, bool ROT>
@@ -707,24 +748,8 @@ __global__ void __launch_bounds__(FWD_THREADS, FWD_CTAS_PER_SM) forward_kernel(c
             else
                 shade_all_lights<false>(s, acc, P);
 
-            const f2 nsnv = mulsat2(s.nsLen, s.nv);                      // saturate(dot(s.N, V)) of the raw normal
-            const f2 Nrx = s.Nx * s.nsLen, Nry = s.Ny * s.nsLen, Nrz = s.Nz * s.nsLen;
-            const float4 oA = finish_pixel<ROT>(P, sFace, s.texA, f3(s.Vx.v.x, s.Vy.v.x, s.Vz.v.x), nsnv.v.x,
-                                                f3(Nrx.v.x, Nry.v.x, Nrz.v.x), roughness.v.x, ao.v.x, f3(acc.ax.v.x, acc.ay.v.x, acc.az.v.x), f3(acc.bx.v.x, acc.by.v.x, acc.bz.v.x),
-                                                f3(acc.cx.v.x, acc.cy.v.x, acc.cz.v.x));
-            if (validA) {   // one STG.128 per destination; peer destinations are mapped NVLink addresses (fused compute + gather)
-                if (MULTI) { for (int q = 0; q < P.nOut; ++q) st_stream(P.outs[q].row(P.dstRowOffset + y) + xA, oA); }
-                else st_stream_hint(P.outs[0].row(P.dstRowOffset + y) + xA, oA, l2_evict_first_policy());
-            }
-            {
-                const float4 oB = finish_pixel<ROT>(P, sFace, s.texB, f3(s.Vx.v.y, s.Vy.v.y, s.Vz.v.y), nsnv.v.y,
-                                                    f3(Nrx.v.y, Nry.v.y, Nrz.v.y), roughness.v.y, ao.v.y, f3(acc.ax.v.y, acc.ay.v.y, acc.az.v.y), f3(acc.bx.v.y, acc.by.v.y, acc.bz.v.y),
-                                                    f3(acc.cx.v.y, acc.cy.v.y, acc.cz.v.y));
-                if (validB) {
-                    if (MULTI) { for (int q = 0; q < P.nOut; ++q) st_stream(P.outs[q].row(P.dstRowOffset + y) + xB, oB); }
-                    else st_stream_hint(P.outs[0].row(P.dstRowOffset + y) + xB, oB, l2_evict_first_policy());
-                }
-            }
+            if (P.diffuseOnly) finish_pair<MULTI, ROT, false>(P, sFace, s, acc, roughness, ao, y, xA, xB, validA, validB);
+            else finish_pair<MULTI, ROT, true>(P, sFace, s, acc, roughness, ao, y, xA, xB, validA, validB);
         }
         mbar_arrive(emptyBar(st));                               // this thread is done with the stage
         if (++st == FWD_STAGES) { st = 0; ++use; }
