@@ -777,189 +777,6 @@ __global__ void __launch_bounds__(FWD_THREADS, FWD_CTAS_PER_SM) forward_kernel(c
     }
 }
 
-// =============================================================================================
-// K1, warp-specialised form (VQ_FWD_WS=1): the gathers get their own warps
-// =============================================================================================
-// The decomposition run (profiles/r02_forward_decomp.txt) shows the kernel above as two half-loaded servers — the four schedulers
-// (~143 us of issue slots per 4K frame) and the ONE L1 data pipe per SM (~150 us of gather wavefronts) — that a warp needs strictly
-// one after the other, plus ~900 cycles of L2/HBM latency per pair in between; 16 warps overlap them by a quarter. Here a CTA is two
-// warpgroups that meet only through shared memory:
-//   gather warpgroup  (warps 4-7, `setmaxnreg` down): for every pixel of the tile it normalises N and V, resolves the three
-//                     footprints, issues the five 256-bit gathers, blends them and parks {diffIrr, specCol, scale/bias} (32 bytes per
-//                     pixel) in the stage; it never touches a light and runs a tile ahead of the shaders;
-//   shading warpgroup (warps 0-3, `setmaxnreg` up): two pixels per thread, packed fp32x2 light loops as above, then the composition
-//                     from the parked values — it never waits for a global load.
-// Three CTAs per SM = 12 + 12 warps. Stage = the TMA'd G-buffer planes + the 8 KB of environment results; three mbarriers per stage
-// (planes landed / environment parked / everybody done). Every wait carries a watchdog (a lost arrival must trap, not hang).
-constexpr int WS_THREADS = 256, WS_STAGES = 3;
-#ifndef WS_REGS_SHADE
-#define WS_REGS_SHADE 104
-#endif
-#ifndef WS_REGS_GATHER
-#define WS_REGS_GATHER 56
-#endif
-#ifndef WS_CTAS_PER_SM
-#define WS_CTAS_PER_SM 3
-#endif
-constexpr uint32_t WS_ENV_BYTES = FWD_TILE * 32u;          // two planes of 256 float4: {diffIrr.rgb, scale}, {specCol.rgb, bias}
-
-__device__ __forceinline__ void mbar_wait_watchdog(uint32_t bar, uint32_t parity) {
-    unsigned long long t0 = 0;
-    for (uint32_t spins = 0;; ++spins) {
-        uint32_t done;
-        asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}"
-                     : "=r"(done) : "r"(bar), "r"(parity) : "memory");
-        if (done) return;
-        if ((spins & 1023u) == 1023u) {
-            unsigned long long t; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
-            if (t0 == 0) t0 = t; else if (t - t0 > 4000000000ull) __trap();       // 4 s: a lost arrival, fail the launch
-        }
-    }
-}
-
-template <bool ROT, bool SPEC>
-__device__ __forceinline__ void ws_gather_pixel(const FwdParams& P, const FaceRec* __restrict__ sFace, uint32_t texel, uint32_t envSlot) {
-    const float4 pa = lds128(texel), nr = lds128(texel + FWD_PLANE);
-    const float3 Ns = xyz(nr);
-    const float roughness = nr.w;
-    const float3 Vv = P.cam - xyz(pa);
-    const float3 V = Vv * rsqrt_fast(dot(Vv, Vv));                      // ForwardLighting.hlsl:285
-    const float nsnv = saturate(dot(Ns, V));                            // saturate(dot(s.N, V)), Lighting.hlsl:368
-    EnvLoads E;
-    env_issue<ROT, SPEC>(E, P, sFace, V, nsnv, Ns, roughness);
-    float3 specCol = f3(0.0f); float2 sb = make_float2(0.0f, 0.0f);
-    if (SPEC) { specCol = cube_finish(E.S); sb = lut_finish(E.L); }
-    const float3 diffIrr = cube_finish(E.D);
-    asm volatile("st.shared.v4.f32 [%0], {%1,%2,%3,%4};" :: "r"(envSlot), "f"(diffIrr.x), "f"(diffIrr.y), "f"(diffIrr.z), "f"(sb.x) : "memory");
-    asm volatile("st.shared.v4.f32 [%0], {%1,%2,%3,%4};" :: "r"(envSlot + FWD_PLANE), "f"(specCol.x), "f"(specCol.y), "f"(specCol.z), "f"(sb.y) : "memory");
-}
-
-template <bool MULTI, bool ROT>
-__global__ void __launch_bounds__(WS_THREADS, WS_CTAS_PER_SM) forward_ws_kernel(const __grid_constant__ FwdParams P) {
-    extern __shared__ __align__(128) unsigned char smemRaw[];
-    const int nPl = P.hasEmissive ? 4 : 3;
-    const int tid = threadIdx.x;
-    const bool gatherWG = tid >= 128;
-    const int t = tid & 127;
-    // shared-memory layout: [WS_STAGES]{[nPl][FWD_TILE] float4 planes | [2][FWD_TILE] float4 environment results} | mbarriers | FaceRec[8*16]
-    const uint32_t stageBytes = (uint32_t)nPl * FWD_PLANE + WS_ENV_BYTES;
-    uint64_t* bars = (uint64_t*)(smemRaw + WS_STAGES * stageBytes);
-    FaceRec* sFace = (FaceRec*)(bars + 3 * WS_STAGES);
-    const uint32_t stage0 = smem_u32(smemRaw), bar0 = smem_u32(bars);
-    auto gfullBar = [&](int st) { return bar0 + 8u * (uint32_t)st; };                       // planes landed (TMA bytes)
-    auto efullBar = [&](int st) { return bar0 + 8u * (uint32_t)(WS_STAGES + st); };          // environment parked (128 gather threads)
-    auto emptyBar = [&](int st) { return bar0 + 8u * (uint32_t)(2 * WS_STAGES + st); };      // everybody done (256 threads)
-
-    const int x0 = (int)blockIdx.x * FWD_TILE;
-    const int rowStep = (int)gridDim.y;
-    const uint32_t tileBytes = (uint32_t)min(FWD_TILE, P.width - x0) * 16u;
-    // the producer (first gather thread): request the tile of row `r` into stage `sIdx`, which has been used `useCount` times before
-    auto request = [&](int r, int sIdx, uint32_t useCount) {
-        if (r >= P.rows) return;
-        if (useCount > 0) mbar_wait_watchdog(emptyBar(sIdx), (useCount - 1u) & 1u);
-        const uint64_t pol = l2_evict_first_policy();
-        const uint32_t dst = stage0 + (uint32_t)sIdx * stageBytes, bar = gfullBar(sIdx);
-        const size_t y = (size_t)(P.rowBegin + r);
-        mbar_expect_tx(bar, tileBytes * (uint32_t)nPl);
-        tma_load_row(dst, P.pos.p + y * P.pos.pitch4 + x0, tileBytes, bar, pol);
-        tma_load_row(dst + FWD_PLANE, P.nrm.p + y * P.nrm.pitch4 + x0, tileBytes, bar, pol);
-        tma_load_row(dst + 2u * FWD_PLANE, P.alb.p + y * P.alb.pitch4 + x0, tileBytes, bar, pol);
-        if (nPl == 4) tma_load_row(dst + 3u * FWD_PLANE, P.emi.p + y * P.emi.pitch4 + x0, tileBytes, bar, pol);
-    };
-    if (tid == 128) {
-        for (int s = 0; s < WS_STAGES; ++s) { mbar_init(gfullBar(s), 1u); mbar_init(efullBar(s), 128u); mbar_init(emptyBar(s), (uint32_t)WS_THREADS); }
-        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
-        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
-        request((int)blockIdx.y, 0, 0u);                                   // prologue: the first tile
-    }
-    for (int i = tid; i < 16 * 8; i += WS_THREADS) {                        // the specular cube's face table (see forward_kernel)
-        const int mip = i & 15, face = i >> 4;
-        FaceRec f; f.base = 0u; f.P = 3u; f.halfN = 0.5f; f.c0 = 0.0f;
-        if (!P.diffuseOnly && mip < P.spec.mips && face < 6) {
-            const int N = P.spec.res >> mip;
-            f.P = (uint32_t)N + 2u; f.base = P.spec.mipOffset[mip] + (uint32_t)face * f.P * f.P;
-            f.halfN = 0.5f * (float)N; f.c0 = f.halfN - 0.5f;
-        }
-        sFace[i] = f;
-    }
-    __syncthreads();                                                        // face table staged, mbarriers initialised
-
-    const int xA = x0 + t, xB = xA + 128;
-    const bool validA = xA < P.width, validB = xB < P.width;
-    const uint32_t offA = (uint32_t)(min(xA, P.width - 1) - x0) * 16u, offB = (uint32_t)(min(xB, P.width - 1) - x0) * 16u;
-    int st = 0; uint32_t use = 0;
-    if (gatherWG) {
-        asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" :: "n"(WS_REGS_GATHER));
-        for (int row = (int)blockIdx.y; row < P.rows; row += rowStep) {
-            if (tid == 128) {                                               // request the NEXT tile: its stage was released two tiles ago
-                const int ps = st + 1;
-                if (ps < WS_STAGES) request(row + rowStep, ps, use); else request(row + rowStep, 0, use + 1u);
-            }
-            mbar_wait_watchdog(gfullBar(st), use & 1u);
-            const uint32_t stageBase = stage0 + (uint32_t)st * stageBytes;
-            const uint32_t envBase = stageBase + (uint32_t)nPl * FWD_PLANE;
-            if (P.diffuseOnly) {
-                ws_gather_pixel<ROT, false>(P, sFace, stageBase + offA, envBase + (uint32_t)t * 16u);
-                ws_gather_pixel<ROT, false>(P, sFace, stageBase + offB, envBase + (uint32_t)(t + 128) * 16u);
-            } else {
-                ws_gather_pixel<ROT, true>(P, sFace, stageBase + offA, envBase + (uint32_t)t * 16u);
-                ws_gather_pixel<ROT, true>(P, sFace, stageBase + offB, envBase + (uint32_t)(t + 128) * 16u);
-            }
-            mbar_arrive(efullBar(st));                                      // release semantics: the parked values are visible to the waiters
-            mbar_arrive(emptyBar(st));
-            if (++st == WS_STAGES) { st = 0; ++use; }
-        }
-    } else {
-        asm volatile("setmaxnreg.inc.sync.aligned.u32 %0;" :: "n"(WS_REGS_SHADE));
-        for (int row = (int)blockIdx.y; row < P.rows; row += rowStep) {
-            mbar_wait_watchdog(gfullBar(st), use & 1u);
-            const int y = P.rowBegin + row;
-            const uint32_t stageBase = stage0 + (uint32_t)st * stageBytes;
-            const uint32_t envBase = stageBase + (uint32_t)nPl * FWD_PLANE;
-            Px2 s;
-            s.texA = stageBase + offA; s.texB = stageBase + offB;
-            f2 roughness, ao; Acc2 acc;
-            shade_pair_lights(P, s, acc, roughness, ao);
-            const f2 nsnv = mulsat2(s.nsLen, s.nv);                         // saturate(dot(s.N, V)) of the raw normal
-            mbar_wait_watchdog(efullBar(st), use & 1u);                     // the gather warpgroup has parked this tile's environment values
-            {
-                const float4 e0 = lds128(envBase + (uint32_t)t * 16u), e1 = lds128(envBase + FWD_PLANE + (uint32_t)t * 16u);
-                const float4 oA = compose_values(P, s.texA, nsnv.v.x, roughness.v.x, ao.v.x, f3(acc.ax.v.x, acc.ay.v.x, acc.az.v.x),
-                                                 f3(acc.bx.v.x, acc.by.v.x, acc.bz.v.x), f3(acc.cx.v.x, acc.cy.v.x, acc.cz.v.x),
-                                                 xyz(e0), xyz(e1), make_float2(e0.w, e1.w));
-                if (validA) {
-                    if (MULTI) { for (int q = 0; q < P.nOut; ++q) st_stream(P.outs[q].row(P.dstRowOffset + y) + xA, oA); }
-                    else st_stream_hint(P.outs[0].row(P.dstRowOffset + y) + xA, oA, l2_evict_first_policy());
-                }
-            }
-            {
-                const float4 e0 = lds128(envBase + (uint32_t)(t + 128) * 16u), e1 = lds128(envBase + FWD_PLANE + (uint32_t)(t + 128) * 16u);
-                const float4 oB = compose_values(P, s.texB, nsnv.v.y, roughness.v.y, ao.v.y, f3(acc.ax.v.y, acc.ay.v.y, acc.az.v.y),
-                                                 f3(acc.bx.v.y, acc.by.v.y, acc.bz.v.y), f3(acc.cx.v.y, acc.cy.v.y, acc.cz.v.y),
-                                                 xyz(e0), xyz(e1), make_float2(e0.w, e1.w));
-                if (validB) {
-                    if (MULTI) { for (int q = 0; q < P.nOut; ++q) st_stream(P.outs[q].row(P.dstRowOffset + y) + xB, oB); }
-                    else st_stream_hint(P.outs[0].row(P.dstRowOffset + y) + xB, oB, l2_evict_first_policy());
-                }
-            }
-            mbar_arrive(emptyBar(st));
-            if (++st == WS_STAGES) { st = 0; ++use; }
-        }
-    }
-    if (MULTI && P.sync.n > 1) {       // fused gather: the last CTA to retire signals the peers and waits for theirs (one kernel = one step)
-        __threadfence_system();
-        __syncthreads();
-        if (tid == 0) {
-            const uint32_t done = atomicAdd(P.ticket, 1u);
-            if (done == gridDim.x * gridDim.y - 1u) {
-                *P.ticket = 0u;
-                __threadfence_system();
-                peer_rendezvous(P.sync);
-            }
-        }
-    }
-}
-
 uint64_t padded_texels(int res, int mips) {
     uint64_t n = 0;
     for (int m = 0; m < mips; ++m) { const uint64_t p = (uint64_t)(res >> m) + 2; n += 6 * p * p; }
@@ -1142,15 +959,13 @@ int vq_forward_launch_multi(VqContext* ctx, const VqPerFrameData* pf, const VqPe
     P.specMaxRec = P.diffuseOnly ? 0u : (uint32_t)padded_texels(env->irradiance_specular.res, env->irradiance_specular.mips) - 1u;
 
     // persistent grid: x = the row's 256-pixel tiles, y = row groups striding the rows
-    static const int useWS = [] { const char* e = getenv("VQ_FWD_WS"); return (e && e[0] == '1') ? 1 : 0; }();   // A/B: the warp-specialised form
     const unsigned gx = (unsigned)((W + FWD_TILE - 1) / FWD_TILE);
-    unsigned gy = (unsigned)(ctx->sm_count * (useWS ? WS_CTAS_PER_SM : FWD_CTAS_PER_SM)) / gx;
+    unsigned gy = (unsigned)(ctx->sm_count * FWD_CTAS_PER_SM) / gx;
     if (gy < 1) gy = 1;
     if (gy > (unsigned)P.rows) gy = (unsigned)P.rows;
     VQ_REQUIRE(gy <= 65535u, "frame too tall for the launch grid");
     const int nPl = P.hasEmissive ? 4 : 3;
-    const size_t smem = useWS ? (size_t)WS_STAGES * (nPl * FWD_PLANE + WS_ENV_BYTES) + 3 * WS_STAGES * sizeof(uint64_t) + 16 * 8 * sizeof(FaceRec)
-                              : (size_t)FWD_STAGES * nPl * FWD_PLANE + 2 * FWD_STAGES * sizeof(uint64_t) + 16 * 8 * sizeof(FaceRec);
+    const size_t smem = (size_t)FWD_STAGES * nPl * FWD_PLANE + 2 * FWD_STAGES * sizeof(uint64_t) + 16 * 8 * sizeof(FaceRec);
     const bool rot = P.sinB != 0.0f || P.cosB != 1.0f;            // yaw offset 0 is the common case: compiled out
     static std::atomic<bool> attrSet{false};                      // process-wide and idempotent: every instantiation, once
     if (!attrSet.load(std::memory_order_acquire)) {
@@ -1158,10 +973,6 @@ int vq_forward_launch_multi(VqContext* ctx, const VqPerFrameData* pf, const VqPe
         VQ_CUDA_OK(cudaFuncSetAttribute(forward_kernel<false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024));
         VQ_CUDA_OK(cudaFuncSetAttribute(forward_kernel<true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024));
         VQ_CUDA_OK(cudaFuncSetAttribute(forward_kernel<true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024));
-        VQ_CUDA_OK(cudaFuncSetAttribute(forward_ws_kernel<false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024));
-        VQ_CUDA_OK(cudaFuncSetAttribute(forward_ws_kernel<false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024));
-        VQ_CUDA_OK(cudaFuncSetAttribute(forward_ws_kernel<true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024));
-        VQ_CUDA_OK(cudaFuncSetAttribute(forward_ws_kernel<true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024));
         attrSet.store(true, std::memory_order_release);
     }
     // Experiment kept behind VQ_L2_PERSIST=1 (off by default: it measured 27 % slower, see vq_context.cu): a PERSISTING access-policy
@@ -1185,19 +996,14 @@ int vq_forward_launch_multi(VqContext* ctx, const VqPerFrameData* pf, const VqPe
     auto launch = [&](auto kernel) -> int {
         cudaLaunchConfig_t cfg;
         memset(&cfg, 0, sizeof(cfg));
-        cfg.gridDim = dim3(gx, gy); cfg.blockDim = dim3(useWS ? WS_THREADS : FWD_THREADS); cfg.dynamicSmemBytes = smem; cfg.stream = stream;
+        cfg.gridDim = dim3(gx, gy); cfg.blockDim = dim3(FWD_THREADS); cfg.dynamicSmemBytes = smem; cfg.stream = stream;
         cfg.attrs = attr; cfg.numAttrs = nAttr;
         VQ_CUDA_OK(cudaLaunchKernelEx(&cfg, kernel, P));
         return VQ_OK;
     };
     VQ_REQUIRE(smem <= 96 * 1024, "stage layout exceeds the shared-memory budget");
-    if (useWS) {
-        if (n_outs > 1) rc = rot ? launch(forward_ws_kernel<true, true>) : launch(forward_ws_kernel<true, false>);
-        else rc = rot ? launch(forward_ws_kernel<false, true>) : launch(forward_ws_kernel<false, false>);
-    } else {
-        if (n_outs > 1) rc = rot ? launch(forward_kernel<true, true>) : launch(forward_kernel<true, false>);
-        else rc = rot ? launch(forward_kernel<false, true>) : launch(forward_kernel<false, false>);
-    }
+    if (n_outs > 1) rc = rot ? launch(forward_kernel<true, true>) : launch(forward_kernel<true, false>);
+    else rc = rot ? launch(forward_kernel<false, true>) : launch(forward_kernel<false, false>);
     if (rc) return rc;
     return vq_check_launch("forward_lighting");
 }
