@@ -331,7 +331,7 @@ def surface_scene_gpu(ctx, vq, torch, w, h, n_materials=4, tex_res=1024):
     planes = [torch.from_numpy(p).cuda() for p in synth.surface_inputs(w, h, n_materials)]
     si = vq.SurfaceInputs(vq.image_of(planes[0]), vq.image_of(planes[1]), vq.image_of(planes[2]), vq.image_of(planes[3], 1))
     return {"table": table, "inputs": si, "keep": keep + planes, "texture_bytes": tex_bytes, "n_materials": n_materials,
-            "tex_res": tex_res}
+            "tex_res": tex_res, "mats": mats, "mts": mts}
 
 
 def surface_producer_pass(ctx, vq, torch, peak):
@@ -340,11 +340,21 @@ def surface_producer_pass(ctx, vq, torch, peak):
     g = [torch.empty((h, w, 4), dtype=torch.float32, device="cuda") for _ in range(4)]
     gb = vq.GBuffer(*(vq.image_of(t) for t in g))
     ms = time_gpu(torch, lambda: ctx.gbuffer_from_materials(sc["inputs"], sc["table"], 0.3, gb), 10)
+    # the same frame with the texel records switched off (every Sample() = 8 x LDG.32 of its own map): what the records buy
+    prev = os.environ.get("VQ_SURFACE_RECORDS")
+    os.environ["VQ_SURFACE_RECORDS"] = "0"
+    try:
+        t2 = ctx.material_table(sc["mats"], sc["mts"])
+    finally:
+        if prev is None: os.environ.pop("VQ_SURFACE_RECORDS", None)
+        else: os.environ["VQ_SURFACE_RECORDS"] = prev
+    ms_maps = time_gpu(torch, lambda: ctx.gbuffer_from_materials(sc["inputs"], t2, 0.3, gb), 10)
+    t2.close()
     nbytes = w * h * (48 + 4 + 64)          # 3 float4 interpolant planes + SSAO in, 4 float4 G-buffer planes out
     out = {"surface_producer_4k": {
         "config": f"{sc['n_materials']} materials (separate maps / ORM / constants / tiled non-pow2), {sc['tex_res']}^2 RGBA8 "
                   f"maps = {sc['texture_bytes'] / 1e6:.1f} MB (L2-resident side data), SSAO + emissive planes",
-        "ms": round(ms, 4), "Mpixels_per_s": round(w * h / ms / 1e3, 1), "algorithmic_bytes_per_px": 116,
+        "ms": round(ms, 4), "ms_map_by_map": round(ms_maps, 4), "Mpixels_per_s": round(w * h / ms / 1e3, 1), "algorithmic_bytes_per_px": 116,
         "algorithmic_GBps": round(nbytes / ms / 1e6, 1), "hbm_frac": round(nbytes / ms / 1e6 / peak, 3)}}
     tw = 4096
     levels = vq.mip_level_count(tw, tw)

@@ -18,6 +18,7 @@
  *       vq_forward_lighting* with an environment that is NOT registered by
  *       vq_environment_prepare (the sampling copies are rebuilt into per-context scratch),
  *       vq_environment_prepare itself, vq_image_resize, vq_depth_min_pyramid,
+ *       vq_forward_lighting_shadowed (per-pixel PCF records),
  *       vq_forward_lighting_host.
  *     Synchronisation is the caller's (cudaStreamSynchronize == fence wait), except the
  *     *_host convenience calls which block.
@@ -339,7 +340,13 @@ typedef struct VqMaterialTable VqMaterialTable;   /* device-resident copy of the
 VQ_API int vq_texture_build_mips(VqContext* ctx, VqTexture2D tex, void* stream);
 
 /* Uploads `count` materials (constants + texture descriptors, both HOST arrays; the texel pointers inside are DEVICE
- * pointers that must outlive the table). Material::GetCBufferData + the SRV table built at AssetLoader.cpp:406-420. */
+ * pointers that must outlive the table). Material::GetCBufferData + the SRV table built at AssetLoader.cpp:406-420.
+ * A material whose bound maps all have the same width, height and level count (>= 2 maps) also gets a SAMPLING COPY:
+ * one 16-byte record per texel holding the bytes PSMain reads of every map, so a trilinear tap is one 128-bit load for
+ * all maps (like the bordered cubemap copies of vq_environment_prepare). The copy is taken HERE, synchronously (the call
+ * waits for the device first, so mip chains still being built on other streams are complete): fill the textures, mips
+ * included, before creating the table, and re-create the table when texels change. Costs 16 B per texel of the shared
+ * size; if that allocation fails, or with VQ_SURFACE_RECORDS=0 in the environment, the maps are sampled one by one. */
 VQ_API int vq_material_table_create(VqContext* ctx, const VqMaterialData* materials,
                                     const VqMaterialTextures* textures, int count, VqMaterialTable** out_table);
 VQ_API int vq_material_table_destroy(VqContext* ctx, VqMaterialTable* table);
@@ -425,6 +432,9 @@ VQ_API int vq_apply_reflections(VqContext* ctx, VqImage scene_color, VqImage ref
  *       directional_map  [y][x]                                                   (Texture2D, t13)
  *     A NULL map lights that light type unshadowed (factor 1). shadowViews / shadowViewDirectional and the
  *     f2*ShadowMapDimensions fields of per_frame are read as the shader reads them.
+ *     Two launches: a PCF kernel that stores the shadowed-tap counts of every caster per pixel (8 B/pixel of scratch owned
+ *     by the context), then the forward kernel, which weights the caster lights with them. Because of that scratch, calls
+ *     on ONE context must be issued on one stream at a time (like vq_depth_min_pyramid).
  *   vq_depth_min_pyramid: replaces CSMain (DownsampleDepth.hlsl:85-119 = FidelityFX SPD with a MIN reduction): level 0 is
  *     a copy of the R32F depth image, level l = max(1, w>>l) x max(1, h>>l) holds the 2x2 minimum of the zero-padded
  *     level above; `levels` receives n_levels (<= vq_depth_pyramid_level_count = 1 + floor(log2(max(w,h))), at most 13)

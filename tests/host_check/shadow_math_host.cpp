@@ -18,6 +18,16 @@ void hostcheck_shade_casters(const VqPerFrameData* pf, const VqPerViewLightingDa
         out[4 * i] = o.x; out[4 * i + 1] = o.y; out[4 * i + 2] = o.z; out[4 * i + 3] = o.w;
     }
 }
+// the per-pixel PCF records the device kernel stores (5 bits per caster)
+void hostcheck_pcf_records(const VqPerFrameData* pf, const VqPerViewLightingData* pv, const VqShadowMaps* sm,
+                           const float* pos, const float* nrm, int n_pixels, unsigned long long* out) {
+    vqshadow::ShadowLights L;
+    vqshadow::fill_shadow_lights(L, *pf, *pv, *sm);
+    for (int i = 0; i < n_pixels; ++i) {
+        auto ld = [&](const float* p) { vqshadow::Px4 r; r.x = p[4 * i]; r.y = p[4 * i + 1]; r.z = p[4 * i + 2]; r.w = p[4 * i + 3]; return r; };
+        out[i] = vqshadow::pcf_record(L, ld(pos), ld(nrm));
+    }
+}
 void hostcheck_per_frame_without_casters(const VqPerFrameData* pf, VqPerFrameData* out) { *out = vqshadow::per_frame_without_casters(*pf); }
 
 // the launcher's sequence (vq_depth_min_pyramid) with the kernels' texel function run in loops

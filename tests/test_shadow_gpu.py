@@ -73,6 +73,26 @@ def test_shadowed_pass_matches_oracle(ctx, vq, orc, w, h):
     assert (got[..., 3] == ref[..., 3]).all()
 
 
+def test_shadowed_pass_full_caster_lists(ctx, vq, orc):
+    """5 point + 5 spot casters + the directional light: all eleven 5-bit slots of the per-pixel PCF record, non-square
+    non-power-of-two spot maps, a rotated HDRI (the ROT instantiation of the shadowed kernel) and a ragged row tile"""
+    from shadow_util import fill_casters
+    w, h = 300, 41
+    env, planes, pf, pv = _scene(w, h, 21)
+    fill_casters(pf, 5, 5, seed=2)
+    pf.fHDRIOffsetInRadians = 0.7
+    rng = np.random.default_rng(7)
+    cubes = rng.uniform(0.0, 1.2, (5, 6, 8, 8)).astype(np.float32)
+    spots = rng.uniform(0.3, 0.7, (5, 12, 20)).astype(np.float32)
+    dmap = rng.uniform(0.3, 0.7, (16, 16)).astype(np.float32)
+    pf.f2SpotLightShadowMapDimensions.x, pf.f2SpotLightShadowMapDimensions.y = 20.0, 12.0
+    got = _device_pass(ctx, vq, env, planes, pf, pv, cubes, spots, dmap)
+    ref = _oracle_pass(orc, env, planes, pf, pv, cubes, spots, dmap)
+    print(_assert_pcf("shadowed_full_lists", got, ref))
+    lit = orc.forward_lighting(pf, pv, planes, env["diff"], env["diff_res"], env["spec"], env["spec_res"], env["spec_mips"], env["lut"])
+    assert np.abs(lit - ref).max() > 1e-2                                  # the shadow tests bite
+
+
 def test_nothing_occluded_equals_the_unshadowed_kernel(ctx, vq, orc):
     """all maps at 'nothing in front': the caster terms carry factor 1, so the result must agree with K1's own (factor 1) path"""
     w, h = 64, 36
@@ -118,7 +138,8 @@ def test_row_range_only_touches_its_rows(ctx, vq, orc):
     assert (part[:5] == 0).all() and (part[13:] == 0).all()
 
 
-@pytest.mark.parametrize("w,h", [(128, 128), (200, 120), (65, 33), (31, 70), (256, 16), (5, 3), (1, 1), (1920, 1080)])
+@pytest.mark.parametrize("w,h", [(128, 128), (200, 120), (65, 33), (31, 70), (256, 16), (5, 3), (1, 1), (1920, 1080), (3840, 2160),
+                                 (4097, 3), (8192, 66), (63, 129), (64, 64)])
 def test_depth_min_pyramid_bit_exact(ctx, vq, orc, w, h):
     rng = np.random.default_rng(160 + w)
     depth = rng.uniform(0.05, 1.0, (h, w)).astype(np.float32)

@@ -83,6 +83,35 @@ def test_caster_math_equals_oracle_bit_for_bit(hostlib, seed, n_point, n_spot):
     assert not np.array_equal(lit, want)                                      # the shadow tests bite
 
 
+def test_caster_math_full_caster_lists_bit_for_bit(hostlib):
+    """5 point casters + 5 spot casters + the directional light: every slot of the per-pixel record in use"""
+    from shadow_util import fill_casters
+    w, h = 80, 45
+    vq, env, planes, pf, pv = _scene(w, h, 21, 1, 1)
+    fill_casters(pf, 5, 5, seed=2)
+    rng = np.random.default_rng(7)
+    cubes = rng.uniform(0.0, 1.2, (5, 6, 8, 8)).astype(np.float32)
+    spots = rng.uniform(0.3, 0.7, (5, 12, 20)).astype(np.float32)        # non-square, not a power of two
+    dmap = rng.uniform(0.3, 0.7, (16, 16)).astype(np.float32)
+    pf.f2SpotLightShadowMapDimensions.x, pf.f2SpotLightShadowMapDimensions.y = 20.0, 12.0
+    got = _host_pass(hostlib, vq, env, planes, pf, pv, cubes, spots, dmap)
+    want = orc.forward_lighting_shadowed(pf, pv, planes, *_args(env), point_cubes=cubes, point_res=8, spot_maps=spots, dir_map=dmap)
+    assert np.array_equal(got.view(np.uint32), want.view(np.uint32))
+    # the records the device stores: 5 bits per slot, counts within their tap numbers, something in every slot somewhere
+    sm = vq.ShadowMaps()
+    sm.point_cubes, sm.point_res = cubes.ctypes.data, 8
+    sm.spot_maps, sm.spot_width, sm.spot_height = spots.ctypes.data, 20, 12
+    sm.directional_map, sm.directional_width, sm.directional_height = dmap.ctypes.data, 16, 16
+    rec = np.zeros(w * h, np.uint64)
+    p = [np.ascontiguousarray(a, np.float32) for a in planes[:2]]
+    hostlib.hostcheck_pcf_records(C.byref(pf), C.byref(pv), C.byref(sm), orc._p(p[0]), orc._p(p[1]), C.c_int(w * h),
+                                  rec.ctypes.data_as(C.c_void_p))
+    assert (rec >> np.uint64(55)).max() == 0
+    for slot in range(11):
+        c = (rec >> np.uint64(5 * slot)) & np.uint64(31)
+        assert c.max() <= (20 if slot < 5 else 25) and c.max() > 0, slot
+
+
 def test_caster_math_without_maps_equals_unshadowed_pass(hostlib):
     vq, env, planes, pf, pv = _scene(64, 36, 3)
     got = _host_pass(hostlib, vq, env, planes, pf, pv, None, None, None)

@@ -86,6 +86,77 @@ def test_surface_parity_uniform_map_sizes(ctx, vq, orc, uv_scale):
     _check(f"surface_uniform@{uv_scale}", got, ref)
 
 
+def _record_material_set(vq, w=100, h=60, seed=77):
+    """two materials whose maps all share one (non-power-of-two) size, so both take the texel-record path: every texture flag at
+    once (separate roughness/metalness/AO maps AND an ORM map), uv tiling, a biased normal map on one, a null emissive SRV with
+    the flag set on the other"""
+    from vqengine_b200 import synth
+    from vqengine_b200.shader_data import (TEXCFG_DIFFUSE, TEXCFG_NORMAL, TEXCFG_AO, TEXCFG_ROUGHNESS, TEXCFG_METALLIC,
+                                           TEXCFG_EMISSIVE, TEXCFG_ORM)
+    base, _ = synth.materials(2, 16)
+    kinds = {"diffuse": "albedo", "normals": "normal", "emissive": "emissive", "metalness": "scalar", "roughness": "scalar",
+             "occl_rough_metal": "orm", "local_ao": "scalar"}
+    mats, chains = [], []
+    for i, m in enumerate(base):
+        m.textureConfig = float(TEXCFG_DIFFUSE | TEXCFG_NORMAL | TEXCFG_AO | TEXCFG_ROUGHNESS | TEXCFG_METALLIC | TEXCFG_EMISSIVE | TEXCFG_ORM)
+        m.emissiveIntensity = 1.5
+        m.normalMapMipBias = 0.75 if i == 0 else 0.0
+        m.uvScaleOffset.x, m.uvScaleOffset.y, m.uvScaleOffset.z, m.uvScaleOffset.w = (2.5, 1.5, 0.2, -0.3) if i == 0 else (1.0, 1.0, 0.0, 0.0)
+        levels = vq.mip_level_count(w, h)
+        d = {}
+        for k, (slot, kind) in enumerate(kinds.items()):
+            if i == 1 and slot == "emissive":
+                d[slot] = None                                        # flag set, SRV null: reads 0
+                continue
+            lvl0 = synth.material_texture(kind, w, h, seed + 10 * i + k)
+            import oracle_lib
+            d[slot] = (oracle_lib.texture_mip_chain(lvl0, levels), w, h, levels)
+        mats.append(m); chains.append(d)
+    return mats, chains
+
+
+def _run_custom(ctx, vq, mats, chains, planes, w, h, alpha_mask=False):
+    table, keep = _upload_materials(ctx, vq, mats, chains)
+    dp = [dev(p) for p in planes]
+    si = vq.SurfaceInputs(vq.image_of(dp[0]), vq.image_of(dp[1]), vq.image_of(dp[2]), vq.image_of(dp[3], 1))
+    init = [np.full((h, w, 4), -7.0, np.float32) for _ in range(4)]
+    outs = [dev(i) for i in init]
+    ctx.gbuffer_from_materials(si, table, 0.3, vq.GBuffer(*(vq.image_of(o) for o in outs)), alpha_mask=alpha_mask)
+    got = [host(o) for o in outs]
+    table.close()
+    return got, init
+
+
+@pytest.mark.parametrize("uv_scale,alpha_mask", [(0.02, False), (0.3, False), (0.004, True)])
+def test_surface_record_path_every_flag(ctx, vq, orc, uv_scale, alpha_mask):
+    """texel records (one 16-byte record per texel holding all seven maps): non-pow2 maps, all flags, biased normal, null SRV"""
+    from vqengine_b200 import synth
+    w, h = 160, 90
+    mats, chains = _record_material_set(vq)
+    planes = synth.surface_inputs(w, h, 2, uv_scale=uv_scale)
+    got, init = _run_custom(ctx, vq, mats, chains, planes, w, h, alpha_mask)
+    ref = orc.gbuffer_from_materials(planes, mats, chains, 0.3, alpha_mask=alpha_mask, init=init)
+    _check(f"surface_records@{uv_scale}", got, ref)
+
+
+@pytest.mark.parametrize("uniform", [True, False])
+def test_surface_record_path_equals_map_by_map(ctx, vq, orc, uniform, monkeypatch):
+    """the record path performs the map-by-map path's operations in the same order: bit-identical G-buffers"""
+    from vqengine_b200 import synth
+    w, h = 192, 108
+    if uniform:
+        mats, texs, chains = material_set(4, 128, uniform=True)
+        planes = synth.surface_inputs(w, h, 4, uv_scale=0.05)
+    else:
+        mats, chains = _record_material_set(vq)
+        planes = synth.surface_inputs(w, h, 2, uv_scale=0.05)
+    a, _ = _run_custom(ctx, vq, mats, chains, planes, w, h)
+    monkeypatch.setenv("VQ_SURFACE_RECORDS", "0")
+    b, _ = _run_custom(ctx, vq, mats, chains, planes, w, h)
+    for name, x, y in zip(NAMES, a, b):
+        assert np.array_equal(x, y), f"{name}: records differ from map-by-map sampling"
+
+
 def test_surface_without_optional_planes(ctx, vq, orc):
     got, ref, _, _ = _run(ctx, vq, orc, 96, 54, ssao=False, emissive=False)
     _check("surface_no_ssao_no_emissive", got, ref)

@@ -96,7 +96,7 @@ int vq_ctx_destroy(VqContext* ctx) {
         for (auto& e : ctx->events) cudaEventDestroy(e);
     }
     if (ctx->stage_dev) cudaFree(ctx->stage_dev);
-    for (void* p : {ctx->env_all, ctx->tmp_diff, ctx->tmp_spec, ctx->tmp_lut, ctx->resize_mid, ctx->resize_tab, ctx->depth_pad}) if (p) cudaFree(p);
+    for (void* p : {ctx->env_all, ctx->tmp_diff, ctx->tmp_spec, ctx->tmp_lut, ctx->resize_mid, ctx->resize_tab, ctx->depth_pad, ctx->shadow_rec}) if (p) cudaFree(p);
     if (ctx->spd_counter) cudaFree(ctx->spd_counter);
     delete ctx->spd_next; delete ctx->mu;
     delete ctx;

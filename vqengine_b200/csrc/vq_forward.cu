@@ -67,6 +67,9 @@ struct FwdParams {
     float diffHalfN;                   // res/2 of the diffuse cube
     uint32_t diffMaxRec, specMaxRec;   // last record a footprint may start at (address clamp for non-finite directions)
     int rowBegin, rows, width;
+    // SHADOWED instantiation only (vq_forward_lighting_shadowed): PCF tap counts per pixel and caster; the caster lights are the
+    // LAST nPointCasters / nSpotCasters entries of pts[] / spots[]
+    ShadowRecV shadow;
 };
 
 // ---------------------------------------------------------------------------------------------
@@ -195,6 +198,7 @@ struct Px2 {
     f2 a2gV, gV;                  // a2 * G1(V), G1(V) = Smith-Schlick-GGX of the view vector (BRDF.hlsl:82-97)
     f2 k4, omk;                   // k + 0.0001, 1 - k with k = (roughness+1)^2 / 8
     uint32_t texA, texB;          // shared-memory addresses of the two pixels' position texels (planes follow at FWD_PLANE)
+    uint64_t recA, recB;          // SHADOWED only: the two pixels' PCF records (ShadowRecV, vq_common.cuh)
 };
 struct Acc2 { f2 ax, ay, az, bx, by, bz, cx, cy, cz; };   // sum over lights of w*col * {(1-fc), fc*spec, spec}
 
@@ -209,30 +213,7 @@ struct Acc2 { f2 ax, ay, az, bx, by, bz, cx, cy, cz; };   // sum over lights of 
 #endif
 constexpr float T_EXACT = FWD_T_EXACT;
 
-__device__ __forceinline__ float dot_u(float3 a, float3 b) {     // (x*x' + y*y') + z*z', every op rounded
-    return __fadd_rn(__fadd_rn(__fmul_rn(a.x, b.x), __fmul_rn(a.y, b.y)), __fmul_rn(a.z, b.z));
-}
-// Correctly rounded sqrt and division WITHOUT the range check + slow-path call that __fsqrt_rn / __fdiv_rn carry
-// (FCHK, BSSY/BSYNC and a CALL per operation: ~3x the instructions). These are the same MUFU-seeded FMA
-// sequences the CUDA intrinsics execute for in-range operands, so they return the same bits; callers guarantee
-// the range (the divisor is a vector length checked against [1e-18, 1e18]; a numerator so small that the quotient
-// is denormal can be off by one denormal ulp, 1e-45, which no consumer of a unit vector can see).
-__device__ __forceinline__ float sqrt_rn_inrange(float x) {
-    const float r = rsqrt_fast(x);
-    const float s = __fmul_rn(x, r), h = __fmul_rn(r, 0.5f);
-    return __fmaf_rn(__fmaf_rn(-s, s, x), h, s);
-}
-struct RcpRn { float r, nb; };                               // refined reciprocal of b and -b
-__device__ __forceinline__ RcpRn rcp_rn_prepare(float b) {
-    const float r0 = rcp_fast(b);
-    RcpRn q; q.nb = -b; q.r = __fmaf_rn(r0, __fmaf_rn(r0, q.nb, 1.0f), r0);
-    return q;
-}
-__device__ __forceinline__ float div_rn_inrange(float a, RcpRn d) {
-    const float q = __fmul_rn(a, d.r);
-    return __fmaf_rn(d.r, __fmaf_rn(q, d.nb, a), q);
-}
-__device__ __forceinline__ bool len2_inrange(float d) { return d > 1e-30f && d < 1e30f; }   // squared length
+// dot_u, sqrt_rn_inrange, rcp_rn_prepare / div_rn_inrange, len2_inrange: vq_common.cuh (shared with the PCF kernel)
 // v / sqrt(dot(v,v)) with correctly rounded sqrt and divisions (== the oracle's normalize)
 __device__ __noinline__ float3 normalize_u_generic(float3 v) {
     const float l = __fsqrt_rn(dot_u(v, v));
@@ -352,12 +333,19 @@ __device__ __forceinline__ LightVec2 light_vector2(const Px2& s, float3 pos) {
     return L;
 }
 
+// SHADOWED: the shadow factor pair {pixel A, pixel B} of caster slot c = 1 - taps/n (Lighting.hlsl:162-164, :207-209), taps from the
+// pixels' PCF records; a continuous factor of the light's weight, so one FFMA2 instead of the reference's division
+__device__ __forceinline__ f2 shadow_factor2(const Px2& s, int slot, float invTaps) {
+    const float ca = (float)((uint32_t)(s.recA >> (5 * slot)) & 31u), cb = (float)((uint32_t)(s.recB >> (5 * slot)) & 31u);
+    return fma2(mk(ca, cb), bc(-invTaps), bc(1.0f));
+}
+
 // every light of the frame for one pixel pair, in PSMain's order
-template <bool TINY>
+template <bool TINY, bool SHADOWED>
 __device__ __forceinline__ void shade_all_lights(const Px2& s, Acc2& acc, const FwdParams& P) {
     const float3 cam = P.cam;
     const int numPoint = P.numPoint, numSpot = P.numSpot;
-    // ---- point lights, then unshadowed point casters (Lighting.hlsl:308-322; PSMain :310-313,321-340):
+    // ---- point lights, then point casters (Lighting.hlsl:308-322; PSMain :310-313,321-340):
     //      in range <=> d2 < d2Limit (== length(Lw-P) < l.range, exactly) ----
 #ifndef FWD_LIGHT_UNROLL
 #define FWD_LIGHT_UNROLL 1      // 2: two lights interleaved (more ILP for the dependent MUFU/FMA chains, ~20 more registers)
@@ -368,10 +356,14 @@ __device__ __forceinline__ void shade_all_lights(const Px2& s, Acc2& acc, const 
         const SPoint l = P.pts[i];                                       // constant bank, warp-uniform index
         const LightVec2 L = light_vector2(s, l.pos);
         const f2 att = (L.invD * L.invD) * bc(l.brightness);               // AttenuationBRDF = 1/D^2
-        const f2 scale = mk(L.d2.v.x < l.d2Limit ? att.v.x : 0.0f, L.d2.v.y < l.d2Limit ? att.v.y : 0.0f);
+        f2 scale = mk(L.d2.v.x < l.d2Limit ? att.v.x : 0.0f, L.d2.v.y < l.d2Limit ? att.v.y : 0.0f);
+        if (SHADOWED) {                                                   // OmnidirectionalShadowTestPCF: 20 taps
+            const int c = i - (numPoint - P.shadow.nPointCasters);
+            if (c >= 0) scale = scale * shadow_factor2(s, c, 1.0f / 20.0f);
+        }
         shade_light2<TINY>(s, acc, cam, L.x, L.y, L.z, L.d2, L.invD, scale, l.color);
     }
-    // ---- spot lights, then unshadowed spot casters (Lighting.hlsl:57-73,323-333) ----
+    // ---- spot lights, then spot casters (Lighting.hlsl:57-73,323-333) ----
     for (int k = 0; k < numSpot; ++k) {
         const SSpot l = P.spots[k];
         const LightVec2 L = light_vector2(s, l.pos);
@@ -383,13 +375,19 @@ __device__ __forceinline__ void shade_all_lights(const Px2& s, Acc2& acc, const 
             const float lin = 1.0f - (theta - l.inner) * l.invCone;
             inten[q] = theta > l.outer ? 0.0f : (theta <= l.inner ? 1.0f : lin);
         }
-        const f2 scale = mk(inten[0], inten[1]) * bc(l.brightness) * (L.invD * L.invD);
+        f2 scale = mk(inten[0], inten[1]) * bc(l.brightness) * (L.invD * L.invD);
+        if (SHADOWED) {                                                   // ShadowTestPCF: 5x5 taps
+            const int c = k - (numSpot - P.shadow.nSpotCasters);
+            if (c >= 0) scale = scale * shadow_factor2(s, P.shadow.nPointCasters + c, 1.0f / 25.0f);
+        }
         shade_light2<TINY>(s, acc, cam, L.x, L.y, L.z, L.d2, L.invD, scale, l.color);
     }
-    // ---- directional (PSMain :360-377 with ShadowingFactor = 1) ----
+    // ---- directional (PSMain :360-377; ShadowingFactor = 1 unless SHADOWED and the light casts) ----
     if (P.dirEnabled) {
         const SDir d = P.dir;
-        shade_light2<TINY>(s, acc, cam, bc(d.wi.x), bc(d.wi.y), bc(d.wi.z), bc(1.0f), bc(1.0f), bc(1.0f), d.radiance);
+        f2 scale = bc(1.0f);
+        if (SHADOWED) { if (P.shadow.dirSlot >= 0) scale = shadow_factor2(s, P.shadow.dirSlot, 1.0f / 25.0f); }
+        shade_light2<TINY>(s, acc, cam, bc(d.wi.x), bc(d.wi.y), bc(d.wi.z), bc(1.0f), bc(1.0f), scale, d.radiance);
     }
 }
 
@@ -643,6 +641,7 @@ __device__ __forceinline__ void finish_pair(const FwdParams& P, const FaceRec* _
 }
 
 // per-pixel-pair set-up (everything the lights share) and the light loops: fills s, acc, roughness, ao from the staged texels
+template <bool SHADOWED>
 __device__ __forceinline__ void shade_pair_lights(const FwdParams& P, Px2& s, Acc2& acc, f2& roughness, f2& ao) {
     {
         const float4 pa = lds128(s.texA), pb = lds128(s.texB);
@@ -679,12 +678,12 @@ __device__ __forceinline__ void shade_pair_lights(const FwdParams& P, Px2& s, Ac
     const f2 tmin = bc(1.0f) + mk(fminf(s.a2m1.v.x, 0.0f), fminf(s.a2m1.v.y, 0.0f));
     const f2 dmin = bc(PI) * (tmin * tmin);
     if (__any_sync(0xffffffffu, fminf(dmin.v.x, dmin.v.y) < 2e-12f))
-        shade_all_lights<true>(s, acc, P);
+        shade_all_lights<true, SHADOWED>(s, acc, P);
     else
-        shade_all_lights<false>(s, acc, P);
+        shade_all_lights<false, SHADOWED>(s, acc, P);
 }
 
-template <bool MULTI, bool ROT>
+template <bool MULTI, bool ROT, bool SHADOWED = false>
 __global__ void __launch_bounds__(FWD_THREADS, FWD_CTAS_PER_SM) forward_kernel(const __grid_constant__ FwdParams P) {
     extern __shared__ __align__(128) unsigned char smemRaw[];
     const int nPl = P.hasEmissive ? 4 : 3;
@@ -756,7 +755,12 @@ __global__ void __launch_bounds__(FWD_THREADS, FWD_CTAS_PER_SM) forward_kernel(c
             s.texB = stageBase + (uint32_t)(min(xB, P.width - 1) - x0) * 16u;
             f2 roughness, ao;
             Acc2 acc;
-            shade_pair_lights(P, s, acc, roughness, ao);
+            if (SHADOWED) {                                       // the pair's PCF records: two coalesced 8-byte loads, consumed in the light loop
+                const uint2* rr = P.shadow.p + (size_t)row * P.shadow.pitch;
+                const uint2 ra = __ldg(rr + min(xA, P.width - 1)), rb = __ldg(rr + min(xB, P.width - 1));
+                s.recA = ((uint64_t)ra.y << 32) | ra.x; s.recB = ((uint64_t)rb.y << 32) | rb.x;
+            }
+            shade_pair_lights<SHADOWED>(P, s, acc, roughness, ao);
             if (P.diffuseOnly) finish_pair<MULTI, ROT, false>(P, sFace, s, acc, roughness, ao, y, xA, xB, validA, validB);
             else finish_pair<MULTI, ROT, true>(P, sFace, s, acc, roughness, ao, y, xA, xB, validA, validB);
         }
@@ -881,7 +885,8 @@ static void condition_lights(const VqSceneLighting& L, FwdParams& P) {
 
 int vq_forward_launch_multi(VqContext* ctx, const VqPerFrameData* pf, const VqPerViewLightingData* pv,
                             const VqGBuffer* gb, const VqEnvironmentMaps* env, const VqImage* outs, int n_outs,
-                            int dst_row_offset, int row_begin, int row_end, const VqPeerSignal* sig, cudaStream_t stream) {
+                            int dst_row_offset, int row_begin, int row_end, const VqPeerSignal* sig, cudaStream_t stream,
+                            const ShadowRecV* shadow = nullptr) {
     VQ_REQUIRE(pf && pv && gb && env && outs, "null parameter block");
     VQ_REQUIRE(n_outs >= 1 && n_outs <= 8, "1..8 destinations");
     VQ_REQUIRE(vq_image_ok(gb->position_ao) && vq_image_ok(gb->normal_roughness) && vq_image_ok(gb->albedo_metalness), "bad image descriptor");
@@ -950,6 +955,13 @@ int vq_forward_launch_multi(VqContext* ctx, const VqPerFrameData* pf, const VqPe
         }
     }
     P.rowBegin = row_begin; P.rows = row_end - row_begin; P.width = W;
+    const bool shadowed = shadow && shadow->p;
+    if (shadowed) {
+        VQ_REQUIRE(n_outs == 1, "the shadowed pass writes one destination");
+        VQ_REQUIRE(shadow->nPointCasters == L.numPointCasters && shadow->nSpotCasters == L.numSpotCasters && shadow->pitch >= W,
+                   "PCF records do not match the frame's caster lists");
+        P.shadow = *shadow;
+    }
 
     rc = vq_fill_peer_sync(sig, &P.sync); if (rc) return rc;
     VQ_REQUIRE(P.sync.n == 0 || n_outs > 1, "a rendezvous only makes sense with peer destinations");
@@ -973,6 +985,8 @@ int vq_forward_launch_multi(VqContext* ctx, const VqPerFrameData* pf, const VqPe
         VQ_CUDA_OK(cudaFuncSetAttribute(forward_kernel<false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024));
         VQ_CUDA_OK(cudaFuncSetAttribute(forward_kernel<true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024));
         VQ_CUDA_OK(cudaFuncSetAttribute(forward_kernel<true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024));
+        VQ_CUDA_OK(cudaFuncSetAttribute(forward_kernel<false, false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024));
+        VQ_CUDA_OK(cudaFuncSetAttribute(forward_kernel<false, true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024));
         attrSet.store(true, std::memory_order_release);
     }
     // Experiment kept behind VQ_L2_PERSIST=1 (off by default: it measured 27 % slower, see vq_context.cu): a PERSISTING access-policy
@@ -1002,7 +1016,8 @@ int vq_forward_launch_multi(VqContext* ctx, const VqPerFrameData* pf, const VqPe
         return VQ_OK;
     };
     VQ_REQUIRE(smem <= 96 * 1024, "stage layout exceeds the shared-memory budget");
-    if (n_outs > 1) rc = rot ? launch(forward_kernel<true, true>) : launch(forward_kernel<true, false>);
+    if (shadowed) rc = rot ? launch(forward_kernel<false, true, true>) : launch(forward_kernel<false, false, true>);
+    else if (n_outs > 1) rc = rot ? launch(forward_kernel<true, true>) : launch(forward_kernel<true, false>);
     else rc = rot ? launch(forward_kernel<false, true>) : launch(forward_kernel<false, false>);
     if (rc) return rc;
     return vq_check_launch("forward_lighting");
@@ -1010,9 +1025,9 @@ int vq_forward_launch_multi(VqContext* ctx, const VqPerFrameData* pf, const VqPe
 
 int vq_forward_launch(VqContext* ctx, const VqPerFrameData* pf, const VqPerViewLightingData* pv,
                       const VqGBuffer* gb, const VqEnvironmentMaps* env, VqImage out,
-                      int row_begin, int row_end, cudaStream_t stream) {
+                      int row_begin, int row_end, cudaStream_t stream, const ShadowRecV* shadow) {
     VQ_REQUIRE(gb && vq_image_ok(out) && out.height == gb->position_ao.height, "G-buffer planes and output must have the same size");
-    return vq_forward_launch_multi(ctx, pf, pv, gb, env, &out, 1, 0, row_begin, row_end, nullptr, stream);
+    return vq_forward_launch_multi(ctx, pf, pv, gb, env, &out, 1, 0, row_begin, row_end, nullptr, stream, shadow);
 }
 
 extern "C" int vq_forward_lighting(VqContext* ctx, const VqPerFrameData* pf, const VqPerViewLightingData* pv,

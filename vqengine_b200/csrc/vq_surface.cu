@@ -9,6 +9,7 @@
 // differences inside the pixel's aligned 2x2 quad, exchanged with warp shuffles (a warp shades a 16x2 pixel strip, so
 // lane^1 is the horizontal and lane^16 the vertical quad partner); isotropic trilinear, WRAP; texel = byte/255.
 #include "vq_common.cuh"
+#include <stdlib.h>
 
 using namespace vq;
 
@@ -23,17 +24,25 @@ struct DevTex {
 };
 static_assert(sizeof(DevTex) == 16, "DevTex layout");
 
-struct DevMaterial {         // 80 + 7*16 = 192 B
+// One 16-byte RECORD per texel of a material whose maps all have the same size (how shipped material sets look): the bytes
+// PSMain reads of every map, interleaved, so that one LDG.128 per trilinear tap fetches the texel of ALL maps:
+//   x = diffuse RGBA | y = normal RGB, local-AO R | z = emissive RGB, roughness R | w = metalness R, ORM G, ORM B, 0
+// (a null map contributes zeros, which is what a null SRV reads). Built once per table by record_build_kernel from the maps'
+// own mip chains, level by level (same packed-level offsets); the K1 sampling copies of the cubemaps are the same idea.
+struct DevMaterial {         // 80 + 7*16 + 16 = 208 B
     VqMaterialData c;
     DevTex t[7];
+    DevTex rec;              // p = uint4 records (nullptr: this material samples its maps one by one), w, h_levels
 };
-static_assert(sizeof(DevMaterial) == 192, "DevMaterial layout");
+static_assert(sizeof(DevMaterial) == 208, "DevMaterial layout");
 
 }  // namespace
 
 struct VqMaterialTable {
     DevMaterial* dev;
     int count;
+    void* records;           // one allocation holding every material's texel records (nullptr: none)
+    size_t record_bytes;
 };
 
 namespace {
@@ -124,7 +133,7 @@ __device__ __forceinline__ int wrap_index(int i, int n) {           // general m
 }
 
 #ifndef SURF_MIN_BLOCKS
-#define SURF_MIN_BLOCKS 4
+#define SURF_MIN_BLOCKS 3
 #endif
 struct TexR { const uint32_t* p; int w, h, levels; };               // a descriptor in registers
 __device__ __forceinline__ TexR load_tex(const DevTex* d) {
@@ -256,6 +265,51 @@ __device__ __forceinline__ void sample8(Taps& T, const TexR& t, float u, float v
     for (int c = 0; c < NCH; ++c) out[c] = fmaf(T.f, hi[c] - out[c], out[c]) * (1.0f / 255.0f);
 }
 
+// ---- record path: every map of the material in one 16-byte texel record ---------------------------------------------------
+// byte C of a texel word as the float 2^23 + byte (PRMT only); differences of two such values are the exact byte differences,
+// so only the lerp's base operand needs the bias removed — and the arithmetic runs on channel PAIRS (FADD2 / FFMA2).
+template <int C>
+__device__ __forceinline__ float byte_biased(uint32_t texel) { return __uint_as_float(__byte_perm(texel, 0x4B000000u, 0x7650 + C)); }
+
+// bilinear blend of channels (C0, C1) of four texel words, in [0,255]; the same operations, in the same order, as bilinear_lerp
+template <int C0, int C1>
+__device__ __forceinline__ f2 bilinear2(uint32_t t00, uint32_t t10, uint32_t t01, uint32_t t11, f2 fx, f2 fy) {
+    const f2 unbias = bc(-8388608.0f);
+    const f2 a = mk(byte_biased<C0>(t00), byte_biased<C1>(t00)), b = mk(byte_biased<C0>(t10), byte_biased<C1>(t10));
+    const f2 d = mk(byte_biased<C0>(t01), byte_biased<C1>(t01)), e = mk(byte_biased<C0>(t11), byte_biased<C1>(t11));
+    const f2 top = fma2(fx, b - a, a + unbias), bot = fma2(fx, e - d, d + unbias);
+    return fma2(fy, bot - top, top);
+}
+// trilinear sample of the four channels of one record word -> [0,1]; w0[] = the word at the four taps of the lower level,
+// w1[] = of the upper one (read only when the fraction is not 0: f == 0 returns the lower level's blend unchanged, as sample8 does)
+__device__ __forceinline__ void sample_word(const uint32_t (&w0)[4], const uint32_t (&w1)[4], const Taps& T, bool two, float (&out)[4]) {
+    f2 lo01 = bilinear2<0, 1>(w0[0], w0[1], w0[2], w0[3], bc(T.fx[0]), bc(T.fy[0]));
+    f2 lo23 = bilinear2<2, 3>(w0[0], w0[1], w0[2], w0[3], bc(T.fx[0]), bc(T.fy[0]));
+    if (two) {
+        const f2 hi01 = bilinear2<0, 1>(w1[0], w1[1], w1[2], w1[3], bc(T.fx[1]), bc(T.fy[1]));
+        const f2 hi23 = bilinear2<2, 3>(w1[0], w1[1], w1[2], w1[3], bc(T.fx[1]), bc(T.fy[1]));
+        lo01 = fma2(bc(T.f), hi01 - lo01, lo01);
+        lo23 = fma2(bc(T.f), hi23 - lo23, lo23);
+    }
+    lo01 = lo01 * bc(1.0f / 255.0f); lo23 = lo23 * bc(1.0f / 255.0f);
+    out[0] = lo01.v.x; out[1] = lo01.v.y; out[2] = lo23.v.x; out[3] = lo23.v.y;
+}
+__device__ __forceinline__ uint4 ld_record(const uint4* p, uint64_t pol) {
+    uint4 r;
+    asm volatile("ld.global.nc.L2::cache_hint.v4.u32 {%0,%1,%2,%3}, [%4], %5;" : "=r"(r.x), "=r"(r.y), "=r"(r.z), "=r"(r.w) : "l"(p), "l"(pol));
+    return r;
+}
+
+// what PSMain's Sample() calls return for one pixel (zeros where a map is not sampled or its SRV is null)
+struct Sampled {
+    float d[4];              // diffuse RGBA
+    float n[3];              // tangent-space normal RGB
+    float e[3];              // emissive RGB
+    float ao, rg, mt;        // local AO .r, roughness .r, metalness .r
+    float og, ob;            // ORM .g, .b
+    bool nrm;                // a normal map is bound
+};
+
 __device__ __forceinline__ float pow22(float c) {                   // SRGBToLinear, ShadingMath.hlsl:65; c in [0,1]
     return exp2f(2.2f * __log2f(c));                                // log2(0) = -inf -> exp2 = 0
 }
@@ -299,6 +353,7 @@ __global__ void __launch_bounds__(256, SURF_MIN_BLOCKS) surface_kernel(const __g
     const DevMaterial& M = A.mats[mi];
     const float4 c0 = __ldg((const float4*)&M.c), c1 = __ldg((const float4*)&M.c + 1);
     const float4 c2 = __ldg((const float4*)&M.c + 2), c3 = __ldg((const float4*)&M.c + 3), c4 = __ldg((const float4*)&M.c + 4);
+    const uint4 rd = __ldg((const uint4*)&M.rec);                   // texel records of this material (pointer 0: none)
     // c0 = diffuse.rgb, alpha | c1 = emissiveColor.rgb, emissiveIntensity | c2 = specular.rgb, normalMapMipBias
     // c3 = uvScaleOffset | c4 = roughness, metalness, displacement, textureConfig
     const int cfg = (int)c4.w;
@@ -306,29 +361,106 @@ __global__ void __launch_bounds__(256, SURF_MIN_BLOCKS) surface_kernel(const __g
     const float u = __fadd_rn(__fmul_rn(ru, c3.x), c3.z), v = __fadd_rn(__fmul_rn(rv, c3.y), c3.w);   // :226
     const float dudx = dRawUdx * c3.x, dvdx = dRawVdx * c3.y, dudy = dRawUdy * c3.x, dvdy = dRawVdy * c3.y;
 
+    Sampled S;
+    S.d[0] = S.d[1] = S.d[2] = S.d[3] = 0.0f; S.n[0] = S.n[1] = S.n[2] = 0.0f; S.e[0] = S.e[1] = S.e[2] = 0.0f;
+    S.ao = S.rg = S.mt = S.og = S.ob = 0.0f; S.nrm = false;
     Taps T;
     T.w = T.h = T.levels = -1; T.bias = 0.0f; T.f = 0.0f;
+
+    if (rd.x | rd.y) {
+        // ---- record path: the maps share one size, so ONE sampler state and 8 x LDG.128 serve every Sample() of the pixel ----
+        TexR tr;
+        tr.p = nullptr; tr.w = (int)(rd.z & 0x00ffffffu); tr.h = (int)(rd.w & 0x07ffffffu); tr.levels = (int)(rd.w >> 27);
+        const uint4* R = (const uint4*)(((uint64_t)rd.y << 32) | rd.x);
+        const uint32_t present = rd.z >> 24;                                // bit k: map k is bound
+        S.nrm = (present & 2u) != 0u;
+        make_taps(T, tr, u, v, dudx, dvdx, dudy, dvdy, 0.0f);
+        const uint64_t keep = l2_policy_evict_last();
+        const bool two = T.f != 0.0f;
+        uint4 q[8];
+#pragma unroll
+        for (int k = 0; k < 4; ++k) q[k] = ld_record(R + T.i[0][k], keep);
+        if (two) {
+#pragma unroll
+            for (int k = 0; k < 4; ++k) q[4 + k] = ld_record(R + T.i[1][k], keep);
+        } else {
+#pragma unroll
+            for (int k = 0; k < 4; ++k) q[4 + k] = q[k];
+        }
+        const bool biasedNormal = S.nrm && c2.w != 0.0f;                    // SampleBias with its own LOD: a second set of taps
+        uint32_t nq[8];
+        Taps TN;
+        bool twoN = false;
+        if (biasedNormal) {
+            TN.w = -1; TN.h = TN.levels = -1; TN.bias = 0.0f; TN.f = 0.0f;
+            make_taps(TN, tr, u, v, dudx, dvdx, dudy, dvdy, c2.w);
+            twoN = TN.f != 0.0f;
+            const uint32_t* Rw = (const uint32_t*)R + 1;                    // word y of a record
+#pragma unroll
+            for (int k = 0; k < 4; ++k) { nq[k] = ld_texel(Rw + 4 * (size_t)TN.i[0][k], keep); nq[4 + k] = ld_texel(Rw + 4 * (size_t)TN.i[1][k], keep); }
+        }
+        float o[4];
+        if (cfg & VQ_TEXCFG_DIFFUSE) {
+            const uint32_t w0[4] = {q[0].x, q[1].x, q[2].x, q[3].x}, w1[4] = {q[4].x, q[5].x, q[6].x, q[7].x};
+            sample_word(w0, w1, T, two, o);
+            S.d[0] = o[0]; S.d[1] = o[1]; S.d[2] = o[2]; S.d[3] = o[3];
+        }
+        if ((S.nrm && !biasedNormal) || (cfg & VQ_TEXCFG_AO)) {
+            const uint32_t w0[4] = {q[0].y, q[1].y, q[2].y, q[3].y}, w1[4] = {q[4].y, q[5].y, q[6].y, q[7].y};
+            sample_word(w0, w1, T, two, o);
+            S.n[0] = o[0]; S.n[1] = o[1]; S.n[2] = o[2]; S.ao = o[3];
+        }
+        if (biasedNormal) {
+            const uint32_t w0[4] = {nq[0], nq[1], nq[2], nq[3]}, w1[4] = {nq[4], nq[5], nq[6], nq[7]};
+            sample_word(w0, w1, TN, twoN, o);
+            S.n[0] = o[0]; S.n[1] = o[1]; S.n[2] = o[2];
+        }
+        if (cfg & (VQ_TEXCFG_EMISSIVE | VQ_TEXCFG_ROUGHNESS)) {
+            const uint32_t w0[4] = {q[0].z, q[1].z, q[2].z, q[3].z}, w1[4] = {q[4].z, q[5].z, q[6].z, q[7].z};
+            sample_word(w0, w1, T, two, o);
+            S.e[0] = o[0]; S.e[1] = o[1]; S.e[2] = o[2]; S.rg = o[3];
+        }
+        if (cfg & (VQ_TEXCFG_METALLIC | VQ_TEXCFG_ORM)) {
+            const uint32_t w0[4] = {q[0].w, q[1].w, q[2].w, q[3].w}, w1[4] = {q[4].w, q[5].w, q[6].w, q[7].w};
+            sample_word(w0, w1, T, two, o);
+            S.mt = o[0]; S.og = o[1]; S.ob = o[2];
+        }
+    } else {
+        // ---- one map at a time (maps of different sizes): a Sample() = 8 x LDG.32 ----
+        if (cfg & VQ_TEXCFG_DIFFUSE) {
+            const TexR tDiff = load_tex(&M.t[0]);
+            if (tDiff.p) {
+                if (A.alphaMask) sample8<4>(T, tDiff, u, v, dudx, dvdx, dudy, dvdy, 0.0f, S.d);
+                else { float s3[3]; sample8<3>(T, tDiff, u, v, dudx, dvdx, dudy, dvdy, 0.0f, s3); S.d[0] = s3[0]; S.d[1] = s3[1]; S.d[2] = s3[2]; }
+            }
+            if (A.alphaMask && S.d[3] < 0.01f) return;                                                // discard before the other maps are read
+        }
+        if (cfg & VQ_TEXCFG_EMISSIVE) {
+            const TexR tEmi = load_tex(&M.t[2]);
+            if (tEmi.p) sample8<3>(T, tEmi, u, v, dudx, dvdx, dudy, dvdy, 0.0f, S.e);
+        }
+        const TexR tNrm = load_tex(&M.t[1]);                                                          // sampled whatever the config says
+        if (tNrm.p) { S.nrm = true; sample8<3>(T, tNrm, u, v, dudx, dvdx, dudy, dvdy, c2.w, S.n); }
+        if (cfg & VQ_TEXCFG_AO)        { float s[1] = {0.f}; const TexR t = load_tex(&M.t[6]); if (t.p) sample8<1>(T, t, u, v, dudx, dvdx, dudy, dvdy, 0.0f, s); S.ao = s[0]; }
+        if (cfg & VQ_TEXCFG_ROUGHNESS) { float s[1] = {0.f}; const TexR t = load_tex(&M.t[4]); if (t.p) sample8<1>(T, t, u, v, dudx, dvdx, dudy, dvdy, 0.0f, s); S.rg = s[0]; }
+        if (cfg & VQ_TEXCFG_METALLIC)  { float s[1] = {0.f}; const TexR t = load_tex(&M.t[3]); if (t.p) sample8<1>(T, t, u, v, dudx, dvdx, dudy, dvdy, 0.0f, s); S.mt = s[0]; }
+        if (cfg & VQ_TEXCFG_ORM) {
+            float s[3] = {0.f, 0.f, 0.f};
+            const TexR t = load_tex(&M.t[5]);
+            if (t.p) sample8<3>(T, t, u, v, dudx, dvdx, dudy, dvdy, 0.0f, s);
+            S.og = s[1]; S.ob = s[2];
+        }
+    }
 
     // --- diffuse (+alpha for the ENABLE_ALPHA_MASK variant, :237-240) ---
     float3 diffuseColor = f3(c0.x, c0.y, c0.z);
     if (cfg & VQ_TEXCFG_DIFFUSE) {
-        const TexR tDiff = load_tex(&M.t[0]);
-        float s[4] = {0.f, 0.f, 0.f, 0.f};
-        if (tDiff.p) {
-            if (A.alphaMask) sample8<4>(T, tDiff, u, v, dudx, dvdx, dudy, dvdy, 0.0f, s);
-            else { float s3[3]; sample8<3>(T, tDiff, u, v, dudx, dvdx, dudy, dvdy, 0.0f, s3); s[0] = s3[0]; s[1] = s3[1]; s[2] = s3[2]; }
-        }
-        if (A.alphaMask && s[3] < 0.01f) return;                                                      // discard
-        diffuseColor = f3(pow22(s[0]) * c0.x, pow22(s[1]) * c0.y, pow22(s[2]) * c0.z);                // :243,249
+        if (A.alphaMask && S.d[3] < 0.01f) return;                                                    // discard
+        diffuseColor = f3(pow22(S.d[0]) * c0.x, pow22(S.d[1]) * c0.y, pow22(S.d[2]) * c0.z);          // :243,249
     }
     // --- emissive ---
     float3 emissiveColor = f3(c1.x, c1.y, c1.z);
-    if (cfg & VQ_TEXCFG_EMISSIVE) {
-        const TexR tEmi = load_tex(&M.t[2]);
-        float s[3] = {0.f, 0.f, 0.f};
-        if (tEmi.p) sample8<3>(T, tEmi, u, v, dudx, dvdx, dudy, dvdy, 0.0f, s);
-        emissiveColor = f3(pow22(s[0]) * c1.x, pow22(s[1]) * c1.y, pow22(s[2]) * c1.z);               // :244,250
-    }
+    if (cfg & VQ_TEXCFG_EMISSIVE) emissiveColor = f3(pow22(S.e[0]) * c1.x, pow22(S.e[1]) * c1.y, pow22(S.e[2]) * c1.z);   // :244,250
     float roughness = c4.x, metalness = c4.y;                                                         // :252-253
     float ao = A.ambient;                                                                             // :247
 
@@ -336,10 +468,8 @@ __global__ void __launch_bounds__(256, SURF_MIN_BLOCKS) surface_kernel(const __g
     const float3 Nw = f3(nv.x, nv.y, nv.z), Tw = f3(tm.x, tm.y, tm.z);
     const float3 N = Nw * rsqrtf(dot(Nw, Nw));
     float3 Nout = N;
-    const TexR tNrm = load_tex(&M.t[1]);                                                              // sampled whatever the config says
-    if (tNrm.p) {
-        float s[3];
-        sample8<3>(T, tNrm, u, v, dudx, dvdx, dudy, dvdy, c2.w, s);
+    if (S.nrm) {
+        const float* s = S.n;
         if (sqrtf(s[0] * s[0] + s[1] * s[1] + s[2] * s[2]) >= 0.01f) {
             const float3 T0 = Tw * rsqrtf(dot(Tw, Tw));
             float3 sn = f3(s[0] * 2.0f - 1.0f, s[1] * 2.0f - 1.0f, s[2] * 2.0f - 1.0f);               // ShadingMath.hlsl:46
@@ -352,15 +482,10 @@ __global__ void __launch_bounds__(256, SURF_MIN_BLOCKS) surface_kernel(const __g
             Nout = T * sn.x + B * sn.y + Nn * sn.z;                                                   // :50-51
         }
     }
-    if (cfg & VQ_TEXCFG_AO)        { float s[1] = {0.f}; const TexR tAo = load_tex(&M.t[6]); if (tAo.p) sample8<1>(T, tAo, u, v, dudx, dvdx, dudy, dvdy, 0.0f, s); ao *= s[0]; }        // :269
-    if (cfg & VQ_TEXCFG_ROUGHNESS) { float s[1] = {0.f}; const TexR tRgh = load_tex(&M.t[4]); if (tRgh.p) sample8<1>(T, tRgh, u, v, dudx, dvdx, dudy, dvdy, 0.0f, s); roughness *= s[0]; } // :270
-    if (cfg & VQ_TEXCFG_METALLIC)  { float s[1] = {0.f}; const TexR tMet = load_tex(&M.t[3]); if (tMet.p) sample8<1>(T, tMet, u, v, dudx, dvdx, dudy, dvdy, 0.0f, s); metalness *= s[0]; } // :271
-    if (cfg & VQ_TEXCFG_ORM) {                                                                                                                        // :272-277
-        float s[3] = {0.f, 0.f, 0.f};
-        const TexR tOrm = load_tex(&M.t[5]);
-        if (tOrm.p) sample8<3>(T, tOrm, u, v, dudx, dvdx, dudy, dvdy, 0.0f, s);
-        roughness *= s[1]; metalness *= s[2];
-    }
+    if (cfg & VQ_TEXCFG_AO)        ao *= S.ao;                                                        // :269
+    if (cfg & VQ_TEXCFG_ROUGHNESS) roughness *= S.rg;                                                 // :270
+    if (cfg & VQ_TEXCFG_METALLIC)  metalness *= S.mt;                                                 // :271
+    if (cfg & VQ_TEXCFG_ORM) { roughness *= S.og; metalness *= S.ob; }                                // :272-277
     if (A.ssao) {                                                                                     // :280-281 (texel x+1,y+1, WRAP)
         const int sxp = x + 1 == W ? 0 : x + 1, syp = y + 1 == H ? 0 : y + 1;
         ao *= __ldg(A.ssao + (size_t)syp * A.ssaoPitch + sxp);
@@ -370,6 +495,18 @@ __global__ void __launch_bounds__(256, SURF_MIN_BLOCKS) surface_kernel(const __g
     st_once(A.outNrm.row(y) + x, make_float4(Nout.x, Nout.y, Nout.z, roughness), once);
     st_once(A.outAlb.row(y) + x, make_float4(diffuseColor.x, diffuseColor.y, diffuseColor.z, metalness), once);
     if (A.outEmi.p) st_once(A.outEmi.row(y) + x, make_float4(emissiveColor.x, emissiveColor.y, emissiveColor.z, c1.w), once);
+}
+
+// interleaves the texels of a material's seven maps (same size, same level count; nullptr = null SRV = zeros) into records
+struct RecBuildArgs { const uint32_t* src[7]; uint4* dst; uint32_t n; };
+__global__ void __launch_bounds__(256) record_build_kernel(const __grid_constant__ RecBuildArgs A) {
+    const uint32_t i = blockIdx.x * 256u + threadIdx.x;
+    if (i >= A.n) return;
+    uint32_t t[7];
+#pragma unroll
+    for (int k = 0; k < 7; ++k) t[k] = A.src[k] ? __ldg(A.src[k] + i) : 0u;
+    // slots: 0 diffuse, 1 normals, 2 emissive, 3 metalness, 4 roughness, 5 occl_rough_metal, 6 local_ao
+    A.dst[i] = make_uint4(t[0], (t[1] & 0x00ffffffu) | (t[6] << 24), (t[2] & 0x00ffffffu) | (t[4] << 24), (t[3] & 0xffu) | (t[5] & 0x00ffff00u));
 }
 
 static bool tex_ok(const VqTexture2D& t) {
@@ -418,13 +555,61 @@ extern "C" int vq_material_table_create(VqContext* ctx, const VqMaterialData* ma
             d.h_levels = (uint32_t)src[k].height | ((uint32_t)src[k].levels << 27);
         }
     }
+    // texel records (see DevMaterial): a material qualifies when at least two maps are bound and every bound map has the same
+    // width, height and level count. VQ_SURFACE_RECORDS=0 in the environment keeps every material on the map-by-map path.
+    const char* recEnv = getenv("VQ_SURFACE_RECORDS");
+    const bool wantRecords = !(recEnv && recEnv[0] == '0');
+    uint64_t recTexels = 0;
+    uint64_t* recOffset = (uint64_t*)calloc((size_t)count, sizeof(uint64_t));
+    uint64_t* recCount = (uint64_t*)calloc((size_t)count, sizeof(uint64_t));
+    if (!recOffset || !recCount) { free(host); free(recOffset); free(recCount); vq_set_error("out of host memory"); return VQ_ERR_OUT_OF_MEMORY; }
+    for (int i = 0; wantRecords && i < count; ++i) {
+        const VqTexture2D* src = &textures[i].diffuse;
+        int bound = 0, first = -1; bool same = true;
+        for (int k = 0; k < 7; ++k) {
+            if (!src[k].ptr) continue;
+            if (first < 0) first = k;
+            else same = same && src[k].width == src[first].width && src[k].height == src[first].height && src[k].levels == src[first].levels;
+            ++bound;
+        }
+        if (bound < 2 || !same || src[first].width >= (1 << 24)) continue;
+        recOffset[i] = recTexels;
+        recCount[i] = vq_pyramid_texel_count(src[first].width, src[first].height, src[first].levels);
+        recTexels += recCount[i];
+    }
     VqMaterialTable* t = (VqMaterialTable*)calloc(1, sizeof(VqMaterialTable));
-    if (!t) { free(host); vq_set_error("out of host memory"); return VQ_ERR_OUT_OF_MEMORY; }
-    cudaError_t e = cudaMalloc(&t->dev, (size_t)count * sizeof(DevMaterial));
+    if (!t) { free(host); free(recOffset); free(recCount); vq_set_error("out of host memory"); return VQ_ERR_OUT_OF_MEMORY; }
+    cudaError_t e = cudaSuccess;
+    if (recTexels) {
+        // a sampling copy is an optimisation: when it does not fit, the materials simply stay on the map-by-map path
+        if (cudaMalloc(&t->records, (size_t)recTexels * 16) != cudaSuccess) { cudaGetLastError(); t->records = nullptr; recTexels = 0; }
+        else t->record_bytes = (size_t)recTexels * 16;
+    }
+    if (t->records) {
+        e = cudaDeviceSynchronize();                                    // mip chains may still be in flight on the caller's streams
+        for (int i = 0; e == cudaSuccess && i < count; ++i) {
+            if (!recCount[i]) continue;
+            const VqTexture2D* src = &textures[i].diffuse;
+            RecBuildArgs B;
+            uint32_t present = 0; int first = -1;
+            for (int k = 0; k < 7; ++k) { B.src[k] = (const uint32_t*)src[k].ptr; if (src[k].ptr) { present |= 1u << k; if (first < 0) first = k; } }
+            B.dst = (uint4*)t->records + recOffset[i]; B.n = (uint32_t)recCount[i];
+            record_build_kernel<<<(unsigned)((recCount[i] + 255) / 256), 256>>>(B);
+            vq_count_launch();
+            e = cudaGetLastError();
+            host[i].rec.p = (const uint32_t*)B.dst;
+            host[i].rec.w = src[first].width | (int32_t)(present << 24);
+            host[i].rec.h_levels = (uint32_t)src[first].height | ((uint32_t)src[first].levels << 27);
+        }
+        if (e == cudaSuccess) e = cudaDeviceSynchronize();
+    }
+    free(recOffset); free(recCount);
+    if (e == cudaSuccess) e = cudaMalloc(&t->dev, (size_t)count * sizeof(DevMaterial));
     if (e == cudaSuccess) e = cudaMemcpy(t->dev, host, (size_t)count * sizeof(DevMaterial), cudaMemcpyHostToDevice);
     free(host);
     if (e != cudaSuccess) {
         if (t->dev) cudaFree(t->dev);
+        if (t->records) cudaFree(t->records);
         free(t);
         vq_set_error("material table upload failed: %s", cudaGetErrorString(e));
         return e == cudaErrorMemoryAllocation ? VQ_ERR_OUT_OF_MEMORY : VQ_ERR_CUDA;
@@ -438,6 +623,7 @@ extern "C" int vq_material_table_destroy(VqContext* ctx, VqMaterialTable* table)
     int rc = vq_enter(ctx); if (rc) return rc;
     if (!table) return VQ_OK;
     if (table->dev) cudaFree(table->dev);
+    if (table->records) cudaFree(table->records);
     free(table);
     return VQ_OK;
 }
