@@ -72,7 +72,8 @@ def test_texture_mip_chain_bit_exact(ctx, vq, orc, w, h):
     assert np.array_equal(t.cpu().numpy(), ref)
 
 
-@pytest.mark.parametrize("w,h,uv_scale", [(96, 54, 0.02), (96, 54, 0.1), (96, 54, 0.004), (251, 141, 0.03), (33, 7, 0.5), (1, 1, 0.1)])
+@pytest.mark.parametrize("w,h,uv_scale", [(96, 54, 0.02), (96, 54, 0.1), (96, 54, 0.004), (251, 141, 0.03), (33, 7, 0.5), (1, 1, 0.1),
+                                          (257, 9, 0.05), (640, 5, 0.02), (128, 2, 0.1)])
 def test_surface_parity(ctx, vq, orc, w, h, uv_scale):
     """every texture configuration (separate maps / ORM / constants only / tiled non-pow2), magnified to heavily minified"""
     got, ref, _, _ = _run(ctx, vq, orc, w, h, uv_scale=uv_scale)

@@ -36,12 +36,12 @@ __device__ __forceinline__ vqshadow::Px4 px4(float4 v) { vqshadow::Px4 r; r.x = 
 // quotients, texel address, depth comparison), ~10 per 2-D tap.
 __global__ void __launch_bounds__(128) shadow_pcf_kernel(const __grid_constant__ PcfParams P) {
     const int x = blockIdx.x * blockDim.x + threadIdx.x;
-    if (x >= P.width) return;
-    for (int r = blockIdx.y; r < P.rows; r += gridDim.y) {
+    const int cx = min(x, P.width - 1);          // whole warps stay alive (pcf_record votes across the warp): a lane past the row's end
+    for (int r = blockIdx.y; r < P.rows; r += gridDim.y) {   // re-computes the last pixel and stores nothing
         const int y = P.rowBegin + r;
-        const float4 p4 = vq::ld_stream(P.pos.row(y) + x), n4 = vq::ld_stream(P.nrm.row(y) + x);
+        const float4 p4 = vq::ld_stream(P.pos.row(y) + cx), n4 = vq::ld_stream(P.nrm.row(y) + cx);
         const unsigned long long rec = vqshadow::pcf_record(P.L, px4(p4), px4(n4));
-        P.rec[(size_t)r * P.recPitch + x] = make_uint2((uint32_t)rec, (uint32_t)(rec >> 32));
+        if (x < P.width) P.rec[(size_t)r * P.recPitch + x] = make_uint2((uint32_t)rec, (uint32_t)(rec >> 32));
     }
 }
 

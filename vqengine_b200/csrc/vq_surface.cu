@@ -133,7 +133,7 @@ __device__ __forceinline__ int wrap_index(int i, int n) {           // general m
 }
 
 #ifndef SURF_MIN_BLOCKS
-#define SURF_MIN_BLOCKS 3
+#define SURF_MIN_BLOCKS 4
 #endif
 struct TexR { const uint32_t* p; int w, h, levels; };               // a descriptor in registers
 __device__ __forceinline__ TexR load_tex(const DevTex* d) {
@@ -182,7 +182,12 @@ __device__ __forceinline__ void make_taps(Taps& T, const TexR& t, float u, float
     const int l0 = (int)l0f;
     T.f = (l0 + 1 < t.levels) ? lod - l0f : 0.0f;
     uint32_t o = 0;                                                   // texel offset of level l0 (vq_pyramid_offset)
-    for (int l = 0; l < l0; ++l) o += (uint32_t)((t.w >> l) * (t.h >> l));
+    if (t.w == t.h && (t.w & (t.w - 1)) == 0 && t.w <= 16384) {       // square power of two: sum_{l<l0} (w>>l)^2 = 4 (w^2 - (w>>l0)^2) / 3
+        const uint32_t wl = (uint32_t)t.w >> l0;
+        o = (4u * ((uint32_t)t.w * (uint32_t)t.w - wl * wl)) / 3u;
+    } else {
+        for (int l = 0; l < l0; ++l) o += (uint32_t)((t.w >> l) * (t.h >> l));
+    }
     const int W0 = t.w >> l0, H0 = t.h >> l0;
     level_taps(W0, H0, o, u, v, T.i[0], T.fx[0], T.fy[0]);
     // the second level is fetched unconditionally so that all 8 taps of a Sample() are independent loads in flight at once;
@@ -248,23 +253,6 @@ __device__ __forceinline__ void st_once(float4* p, float4 v, uint64_t pol) {
 }
 #endif
 
-// Texture2D.Sample / SampleBias: isotropic trilinear, WRAP; channels in [0,1]
-template <int NCH>
-__device__ __forceinline__ void sample8(Taps& T, const TexR& t, float u, float v, float dudx, float dvdx, float dudy,
-                                        float dvdy, float bias, float (&out)[NCH]) {
-    make_taps(T, t, u, v, dudx, dvdx, dudy, dvdy, bias);
-    const uint32_t* p = t.p;
-    const uint64_t keep = l2_policy_evict_last();
-    uint32_t q[8];
-#pragma unroll
-    for (int k = 0; k < 4; ++k) { q[k] = ld_texel(p + T.i[0][k], keep); q[4 + k] = ld_texel(p + T.i[1][k], keep); }
-    float hi[NCH];
-    bilinear_lerp<NCH>(q[0], q[1], q[2], q[3], T.fx[0], T.fy[0], out);
-    bilinear_lerp<NCH>(q[4], q[5], q[6], q[7], T.fx[1], T.fy[1], hi);
-#pragma unroll
-    for (int c = 0; c < NCH; ++c) out[c] = fmaf(T.f, hi[c] - out[c], out[c]) * (1.0f / 255.0f);
-}
-
 // ---- record path: every map of the material in one 16-byte texel record ---------------------------------------------------
 // byte C of a texel word as the float 2^23 + byte (PRMT only); differences of two such values are the exact byte differences,
 // so only the lerp's base operand needs the bias removed — and the arithmetic runs on channel PAIRS (FADD2 / FFMA2).
@@ -300,6 +288,31 @@ __device__ __forceinline__ uint4 ld_record(const uint4* p, uint64_t pol) {
     return r;
 }
 
+// Texture2D.Sample / SampleBias of ONE RGBA8 map: isotropic trilinear, WRAP; channels in [0,1]. Two or more channels are
+// filtered as packed pairs (bilinear2); the operations per channel are those of bilinear_lerp either way.
+template <int NCH>
+__device__ __forceinline__ void sample8(Taps& T, const TexR& t, float u, float v, float dudx, float dvdx, float dudy,
+                                        float dvdy, float bias, float (&out)[NCH]) {
+    make_taps(T, t, u, v, dudx, dvdx, dudy, dvdy, bias);
+    const uint32_t* p = t.p;
+    const uint64_t keep = l2_policy_evict_last();
+    uint32_t q[8];
+#pragma unroll
+    for (int k = 0; k < 4; ++k) { q[k] = ld_texel(p + T.i[0][k], keep); q[4 + k] = ld_texel(p + T.i[1][k], keep); }
+    if (NCH == 1) {
+        float lo[1], hi[1];
+        bilinear_lerp<1>(q[0], q[1], q[2], q[3], T.fx[0], T.fy[0], lo);
+        bilinear_lerp<1>(q[4], q[5], q[6], q[7], T.fx[1], T.fy[1], hi);
+        out[0] = fmaf(T.f, hi[0] - lo[0], lo[0]) * (1.0f / 255.0f);
+    } else {
+        const uint32_t w0[4] = {q[0], q[1], q[2], q[3]}, w1[4] = {q[4], q[5], q[6], q[7]};
+        float o[4];
+        sample_word(w0, w1, T, true, o);                             // f == 0: the upper level repeats the lower one's taps
+#pragma unroll
+        for (int c = 0; c < NCH; ++c) out[c] = o[c];
+    }
+}
+
 // what PSMain's Sample() calls return for one pixel (zeros where a map is not sampled or its SRV is null)
 struct Sampled {
     float d[4];              // diffuse RGBA
@@ -324,32 +337,11 @@ struct SurfArgs {
     int rowBegin, rowEnd, tileY0;           // tileY0 = rowBegin & ~1 (quads are aligned to absolute even rows)
 };
 
-// block = 256 threads = 8 warps; a warp shades 16x2 pixels (one row of 2x2 quads), a block 32x8
-__global__ void __launch_bounds__(256, SURF_MIN_BLOCKS) surface_kernel(const __grid_constant__ SurfArgs A) {
-    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    const int x = blockIdx.x * 32 + (warp & 1) * 16 + (lane & 15);
-    const int y = A.tileY0 + blockIdx.y * 8 + (warp >> 1) * 2 + (lane >> 4);
-    const int W = A.posU.w, H = A.posU.h;
-    // threads outside the image re-read the clamped texel: their uv equals the in-image partner's -> derivative 0,
-    // exactly the oracle's "partner clamped to the image"
-    const int cx = min(x, W - 1), cy = min(y, H - 1);
-    const uint64_t once = l2_policy_evict_first();
-    const float4 pu = ld_once(A.posU.row(cy) + cx, once);
-    const float4 nv = ld_once(A.nrmV.row(cy) + cx, once);
-    const float4 tm = ld_once(A.tanM.row(cy) + cx, once);
+// One pixel of PSMain before lighting, from its interpolants (pu, nv, tm), its material index and the fine quad derivatives of
+// the raw uv. Early returns = the alpha-mask discard.
+__device__ __forceinline__ void shade_surface_pixel(const SurfArgs& A, int x, int y, int mi, float4 pu, float4 nv, float4 tm, float ssao,
+                                                    float dRawUdx, float dRawVdx, float dRawUdy, float dRawVdy, uint64_t once) {
     const float ru = pu.w, rv = nv.w;
-
-    // fine quad derivatives of the RAW uv: horizontal partner = lane^1, vertical = lane^16
-    const float ruX = __shfl_xor_sync(0xffffffffu, ru, 1), rvX = __shfl_xor_sync(0xffffffffu, rv, 1);
-    const float ruY = __shfl_xor_sync(0xffffffffu, ru, 16), rvY = __shfl_xor_sync(0xffffffffu, rv, 16);
-    const float sx = (lane & 1) ? -1.0f : 1.0f, sy = (lane & 16) ? -1.0f : 1.0f;   // (odd - even) regardless of which I am
-    const float dRawUdx = (ruX - ru) * sx, dRawVdx = (rvX - rv) * sx;
-    const float dRawUdy = (ruY - ru) * sy, dRawVdy = (rvY - rv) * sy;
-
-    if (x >= W || y >= H || y < A.rowBegin || y >= A.rowEnd) return;
-
-    int mi = (int)tm.w;
-    mi = min(max(mi, 0), A.nMats - 1);
     const DevMaterial& M = A.mats[mi];
     const float4 c0 = __ldg((const float4*)&M.c), c1 = __ldg((const float4*)&M.c + 1);
     const float4 c2 = __ldg((const float4*)&M.c + 2), c3 = __ldg((const float4*)&M.c + 3), c4 = __ldg((const float4*)&M.c + 4);
@@ -427,6 +419,8 @@ __global__ void __launch_bounds__(256, SURF_MIN_BLOCKS) surface_kernel(const __g
         }
     } else {
         // ---- one map at a time (maps of different sizes): a Sample() = 8 x LDG.32 ----
+        // (one looped copy of the sampler instead of these seven inlined ones shrinks the kernel from 92 KB to 36 KB of code but
+        //  executes 11 % more instructions — four channels for every map, routing by slot: 0.415 ms against 0.371, not kept)
         if (cfg & VQ_TEXCFG_DIFFUSE) {
             const TexR tDiff = load_tex(&M.t[0]);
             if (tDiff.p) {
@@ -486,15 +480,49 @@ __global__ void __launch_bounds__(256, SURF_MIN_BLOCKS) surface_kernel(const __g
     if (cfg & VQ_TEXCFG_ROUGHNESS) roughness *= S.rg;                                                 // :270
     if (cfg & VQ_TEXCFG_METALLIC)  metalness *= S.mt;                                                 // :271
     if (cfg & VQ_TEXCFG_ORM) { roughness *= S.og; metalness *= S.ob; }                                // :272-277
-    if (A.ssao) {                                                                                     // :280-281 (texel x+1,y+1, WRAP)
-        const int sxp = x + 1 == W ? 0 : x + 1, syp = y + 1 == H ? 0 : y + 1;
-        ao *= __ldg(A.ssao + (size_t)syp * A.ssaoPitch + sxp);
-    }
+    ao *= ssao;                                                                                       // :280-281 (1 when no SSAO plane is bound)
 
     st_once(A.outPos.row(y) + x, make_float4(pu.x, pu.y, pu.z, ao), once);
     st_once(A.outNrm.row(y) + x, make_float4(Nout.x, Nout.y, Nout.z, roughness), once);
     st_once(A.outAlb.row(y) + x, make_float4(diffuseColor.x, diffuseColor.y, diffuseColor.z, metalness), once);
     if (A.outEmi.p) st_once(A.outEmi.row(y) + x, make_float4(emissiveColor.x, emissiveColor.y, emissiveColor.z, c1.w), once);
+}
+
+// block = 256 threads = 8 warps; a warp shades 16x2 pixels (one row of 2x2 quads), a block 32x8.
+// Three restructurings of this launch were measured and NOT kept (profiles/r02_surface_variants.txt): queueing a warp's minority-
+// material pixels for a second pass inside the block (0.49 ms) or for a second small launch (0.45 ms) against 0.37 ms in place —
+// the majority paths dominate the instruction count, not the stray lanes; and a persistent kernel with the interpolant planes on a
+// TMA / mbarrier ring like K1's (0.49 ms) — the waits are on the texel and SSAO loads, not on the interpolants, and 92 KB of code
+// with every warp of an SM somewhere else in it stalls on instruction fetch.
+__global__ void __launch_bounds__(256, SURF_MIN_BLOCKS) surface_kernel(const __grid_constant__ SurfArgs A) {
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int x = blockIdx.x * 32 + (warp & 1) * 16 + (lane & 15);
+    const int y = A.tileY0 + blockIdx.y * 8 + (warp >> 1) * 2 + (lane >> 4);
+    const int W = A.posU.w, H = A.posU.h;
+    // threads outside the image re-read the clamped texel: their uv equals the in-image partner's -> derivative 0,
+    // exactly the oracle's "partner clamped to the image"
+    const int cx = min(x, W - 1), cy = min(y, H - 1);
+    const uint64_t once = l2_policy_evict_first();
+    const float4 pu = ld_once(A.posU.row(cy) + cx, once);
+    const float4 nv = ld_once(A.nrmV.row(cy) + cx, once);
+    const float4 tm = ld_once(A.tanM.row(cy) + cx, once);
+    // the SSAO texel (x+1, y+1, WRAP; :280-281) depends on nothing but the pixel: fetched with the interpolants, not at the point
+    // of use after the whole sampling chain (where it was 17 % of the kernel's long-scoreboard stalls)
+    float ssao = 1.0f;
+    if (A.ssao) {
+        const int sxp = cx + 1 == W ? 0 : cx + 1, syp = cy + 1 == H ? 0 : cy + 1;
+        ssao = __ldg(A.ssao + (size_t)syp * A.ssaoPitch + sxp);
+    }
+    const float ru = pu.w, rv = nv.w;
+    // fine quad derivatives of the RAW uv: horizontal partner = lane^1, vertical = lane^16
+    const float ruX = __shfl_xor_sync(0xffffffffu, ru, 1), rvX = __shfl_xor_sync(0xffffffffu, rv, 1);
+    const float ruY = __shfl_xor_sync(0xffffffffu, ru, 16), rvY = __shfl_xor_sync(0xffffffffu, rv, 16);
+    const float sx = (lane & 1) ? -1.0f : 1.0f, sy = (lane & 16) ? -1.0f : 1.0f;   // (odd - even) regardless of which I am
+    const float dRawUdx = (ruX - ru) * sx, dRawVdx = (rvX - rv) * sx;
+    const float dRawUdy = (ruY - ru) * sy, dRawVdy = (rvY - rv) * sy;
+    if (x >= W || y >= H || y < A.rowBegin || y >= A.rowEnd) return;
+    const int mi = min(max((int)tm.w, 0), A.nMats - 1);
+    shade_surface_pixel(A, x, y, mi, pu, nv, tm, ssao, dRawUdx, dRawVdx, dRawUdy, dRawVdy, once);
 }
 
 // interleaves the texels of a material's seven maps (same size, same level count; nullptr = null SRV = zeros) into records
