@@ -949,6 +949,34 @@ def main():
     kernel_only(); torch.cuda.synchronize()
     assert torch.equal(hout.cuda(), out), "host-buffer path and device path disagree"
     h2d, d2h = 3 * FW * rows * 16, FW * rows * 16
+    # what the link itself does on this box with the same pinned buffers: plain copies of one plane, each direction alone and both
+    # at once — the floor of the e2e step is max(h2d_bytes / h2d rate, d2h_bytes / d2h rate) with the two directions overlapped
+    pcie = None
+    try:
+        dbuf = torch.empty_like(out)
+        s2 = torch.cuda.Stream()
+        def link(fn, reps=4):
+            fn(); torch.cuda.synchronize()
+            t0 = time.perf_counter()
+            for _ in range(reps): fn()
+            torch.cuda.synchronize()
+            return (time.perf_counter() - t0) / reps
+        nbytes = dbuf.numel() * 4
+        t_up = link(lambda: dbuf.copy_(hpl[0], non_blocking=True))
+        t_dn = link(lambda: hout.copy_(dbuf, non_blocking=True))
+        dbuf2 = torch.empty_like(out)
+        def both():
+            dbuf.copy_(hpl[0], non_blocking=True)
+            with torch.cuda.stream(s2): hout.copy_(dbuf2, non_blocking=True)
+        t_both = link(both)
+        up, dn = nbytes / t_up / 1e9, nbytes / t_dn / 1e9
+        floor_s = max(h2d / (up * 1e9), d2h / (dn * 1e9))
+        pcie = {"h2d_GBps": round(up, 1), "d2h_GBps": round(dn, 1), "both_directions_GBps_each": round(nbytes / t_both / 1e9, 1),
+                "link_floor_ms_per_step": round(floor_s * 1e3, 3), "e2e_ms_per_step": round(float(t.item()) * 1e3, 3),
+                "e2e_frac_of_link_floor": round(floor_s / float(t.item()), 3)}
+        del dbuf, dbuf2
+    except Exception as ex:          # a side measurement: never let it cost the bench line
+        pcie = {"error": repr(ex)[:200]}
 
     # ---- multi-GPU: the NCCL baseline of the same step (kernel, then one all-gather of the tiles) and the identity check ----
     gather = None
@@ -1001,7 +1029,7 @@ def main():
                              "frac": round(achieved / peak, 4), "traffic": traffic, "traffic_source": cap, "peak_source": peak_src,
                              "algorithmic_bytes_per_launch": BYTES_PER_PX * FW * rows, "issue": issue},
                 "e2e": {"value": round(e2e_val, 1), "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
-                        "api": "vq_forward_lighting_host (pinned host buffers, 16 row chunks pipelined over 3 streams)"},
+                        "api": "vq_forward_lighting_host (pinned host buffers, 16 row chunks pipelined over 3 streams)", "pcie": pcie},
                 "gpu_launches": int(timed_launches), "clocks": clocks}
         if gather: line["allgather"] = gather
     ibl_strong = None

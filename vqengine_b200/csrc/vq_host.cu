@@ -3,6 +3,7 @@
 // (upload | shade | download) so that PCIe traffic in both directions overlaps the kernel; with pinned
 // host memory (cudaHostRegister / cudaMallocHost) the copies are truly asynchronous.
 #include "vq_common.cuh"
+#include <stdlib.h>
 
 namespace {
 constexpr int kMaxChunks = 16;
@@ -45,6 +46,7 @@ extern "C" int vq_forward_lighting_host(VqContext* ctx, const VqPerFrameData* pf
     dgb.emissive = hasEm ? VqImage{base + 4 * planeBytes, W, H, rowBytes} : VqImage{nullptr, 0, 0, 0};
 
     int chunks = H >= 256 ? kMaxChunks : (H >= 16 ? 4 : 1);
+    if (const char* e = getenv("VQ_HOST_CHUNKS")) { const int c = atoi(e); if (c >= 1 && c <= kMaxChunks && c <= H) chunks = c; }   // tuning knob
     const int rowsPer = (H + chunks - 1) / chunks;
     cudaStream_t sUp = ctx->streams[0], sRun = ctx->streams[1], sDown = ctx->streams[2];
     const VqImage* hp[4] = {&hgb->position_ao, &hgb->normal_roughness, &hgb->albedo_metalness, &hgb->emissive};
@@ -52,18 +54,28 @@ extern "C" int vq_forward_lighting_host(VqContext* ctx, const VqPerFrameData* pf
     for (int c = 0; c < chunks; ++c) {
         const int r0 = c * rowsPer, r1 = (r0 + rowsPer < H) ? r0 + rowsPer : H;
         if (r0 >= r1) break;
-        for (int k = 0; k < (hasEm ? 4 : 3); ++k)
-            VQ_CUDA_OK(cudaMemcpy2DAsync((char*)dp[k]->ptr + (size_t)r0 * rowBytes, rowBytes,
-                                         (const char*)hp[k]->ptr + (size_t)r0 * hp[k]->pitch_bytes, hp[k]->pitch_bytes,
-                                         rowBytes, r1 - r0, cudaMemcpyHostToDevice, sUp));
+        for (int k = 0; k < (hasEm ? 4 : 3); ++k) {
+            // tightly packed host rows (the usual case): one linear copy; pitched rows: a 2-D copy
+            if (hp[k]->pitch_bytes == rowBytes)
+                VQ_CUDA_OK(cudaMemcpyAsync((char*)dp[k]->ptr + (size_t)r0 * rowBytes, (const char*)hp[k]->ptr + (size_t)r0 * rowBytes,
+                                           rowBytes * (size_t)(r1 - r0), cudaMemcpyHostToDevice, sUp));
+            else
+                VQ_CUDA_OK(cudaMemcpy2DAsync((char*)dp[k]->ptr + (size_t)r0 * rowBytes, rowBytes,
+                                             (const char*)hp[k]->ptr + (size_t)r0 * hp[k]->pitch_bytes, hp[k]->pitch_bytes,
+                                             rowBytes, r1 - r0, cudaMemcpyHostToDevice, sUp));
+        }
         VQ_CUDA_OK(cudaEventRecord(ctx->events[2 * c], sUp));
         VQ_CUDA_OK(cudaStreamWaitEvent(sRun, ctx->events[2 * c], 0));
         rc = vq_forward_launch(ctx, pf, pv, &dgb, denv, dout, r0, r1, sRun); if (rc) return rc;
         VQ_CUDA_OK(cudaEventRecord(ctx->events[2 * c + 1], sRun));
         VQ_CUDA_OK(cudaStreamWaitEvent(sDown, ctx->events[2 * c + 1], 0));
-        VQ_CUDA_OK(cudaMemcpy2DAsync((char*)hout.ptr + (size_t)r0 * hout.pitch_bytes, hout.pitch_bytes,
-                                     (const char*)dout.ptr + (size_t)r0 * rowBytes, rowBytes,
-                                     rowBytes, r1 - r0, cudaMemcpyDeviceToHost, sDown));
+        if (hout.pitch_bytes == rowBytes)
+            VQ_CUDA_OK(cudaMemcpyAsync((char*)hout.ptr + (size_t)r0 * rowBytes, (const char*)dout.ptr + (size_t)r0 * rowBytes,
+                                       rowBytes * (size_t)(r1 - r0), cudaMemcpyDeviceToHost, sDown));
+        else
+            VQ_CUDA_OK(cudaMemcpy2DAsync((char*)hout.ptr + (size_t)r0 * hout.pitch_bytes, hout.pitch_bytes,
+                                         (const char*)dout.ptr + (size_t)r0 * rowBytes, rowBytes,
+                                         rowBytes, r1 - r0, cudaMemcpyDeviceToHost, sDown));
     }
     VQ_CUDA_OK(cudaStreamSynchronize(sDown));
     VQ_CUDA_OK(cudaStreamSynchronize(sRun));
