@@ -397,7 +397,8 @@ def shadow_passes(ctx, vq, torch, envk, peak):
     r = {"forward_4k_casters_shadowed": {
         "ms": round(ms1, 4), "ms_same_lights_unshadowed": round(ms0, 4),
         "casters": f"{L.numPointCasters} point (20-tap cube PCF, {res_pt}^2 faces) + {L.numSpotCasters} spot + directional (5x5 PCF, {res_2d}^2)",
-        "Mpixels_per_s": round(w * h / ms1 / 1e3, 1), "bound": "instruction issue (PCF taps: 70 point-sampled fetches + their address math per pixel)"}}
+        "Mpixels_per_s": round(w * h / ms1 / 1e3, 1), "structure": "shadow_pcf_kernel (shadowed-tap counts per caster, 5 bits each, 8 B/pixel) + forward_kernel<SHADOWED> (caster lights weighted by 1 - taps/N)",
+        "bound": "PCF kernel: instruction issue on the ALU pipe (about 50 instructions per cube tap, 6 per planar tap; 70 taps per pixel)"}}
     depth = torch.rand((h, w), device="cuda", generator=g)
     n = vq.depth_pyramid_level_count(w, h)
     levels = torch.empty((vq.depth_pyramid_texel_count(w, h, n),), dtype=torch.float32, device="cuda")
@@ -1029,7 +1030,7 @@ def main():
                              "frac": round(achieved / peak, 4), "traffic": traffic, "traffic_source": cap, "peak_source": peak_src,
                              "algorithmic_bytes_per_launch": BYTES_PER_PX * FW * rows, "issue": issue},
                 "e2e": {"value": round(e2e_val, 1), "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
-                        "api": "vq_forward_lighting_host (pinned host buffers, 16 row chunks pipelined over 3 streams)", "pcie": pcie},
+                        "api": "vq_forward_lighting_host (pinned host buffers, 8 row chunks pipelined over 3 streams)", "pcie": pcie},
                 "gpu_launches": int(timed_launches), "clocks": clocks}
         if gather: line["allgather"] = gather
     ibl_strong = None

@@ -122,7 +122,7 @@ for k, label in [("surface_producer_4k", "(f).1 surface producer 4K"), ("texture
 if "forward_4k_casters_shadowed" in ex:
     e = ex["forward_4k_casters_shadowed"]
     out.append(f"| (f).4 forward pass with shadow maps bound 4K | {e['ms']:.4f} | — | — | {e['casters']}; the same lights unshadowed: {e['ms_same_lights_unshadowed']} ms; "
-               "every PCF operation rounded as the oracle does (correctly rounded divisions / square roots): a bit-faithful restatement, not yet a fast one |")
+               "two launches: the PCF kernel (every decision rounded as the oracle rounds it, tap counts per caster into 8 B/pixel) + the SHADOWED instantiation of K1, which weights the caster lights with them; round 2 began at 2.26 ms with a second full-BRDF pass (r02_shadow_variants.txt) |")
 ric = b1.get("cpu_baseline_image_class")
 if ric and "error" not in ric:
     out.append(f"\nReference CPU path for the (f).2 rows (the engine's own `Image` class compiled unmodified, 1 host core, same 4096x2048 HDRI): "

@@ -45,7 +45,9 @@ extern "C" int vq_forward_lighting_host(VqContext* ctx, const VqPerFrameData* pf
     VqImage dout         = VqImage{base + 3 * planeBytes, W, H, rowBytes};
     dgb.emissive = hasEm ? VqImage{base + 4 * planeBytes, W, H, rowBytes} : VqImage{nullptr, 0, 0, 0};
 
-    int chunks = H >= 256 ? kMaxChunks : (H >= 16 ? 4 : 1);
+    // 8 chunks measured best at 4K (8.16 ms; 16: 8.32, 4: 8.24, 2: 8.71; the link alone moves the 398 MB in 7.19 ms and loses 12 %
+    // per direction while both directions are busy: profiles/r02_e2e_link.txt)
+    int chunks = H >= 256 ? 8 : (H >= 16 ? 4 : 1);
     if (const char* e = getenv("VQ_HOST_CHUNKS")) { const int c = atoi(e); if (c >= 1 && c <= kMaxChunks && c <= H) chunks = c; }   // tuning knob
     const int rowsPer = (H + chunks - 1) / chunks;
     cudaStream_t sUp = ctx->streams[0], sRun = ctx->streams[1], sDown = ctx->streams[2];
