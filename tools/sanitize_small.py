@@ -64,11 +64,16 @@ ctx.forward_lighting_shadowed(pfs, pvs, gb3, em, out, torch.rand((max(pfs.Lights
                               torch.rand((max(pfs.Lights.numSpotCasters, 1), 16, 16), device="cuda"), torch.rand((16, 16), device="cuda"))
 depth = torch.rand((37, 53), device="cuda"); nlev = vq.depth_pyramid_level_count(53, 37)
 ctx.depth_min_pyramid(depth, torch.empty((vq.depth_pyramid_texel_count(53, 37, nlev),), device="cuda"))
+depth2 = torch.rand((131, 203), device="cuda"); nlev2 = vq.depth_pyramid_level_count(203, 131)      # 8 levels: two launches, padded level 6 in between
+ctx.depth_min_pyramid(depth2, torch.empty((vq.depth_pyramid_texel_count(203, 131, nlev2),), device="cuda"))
 # SURVEY 8(f).1 (bench.surface_scene_gpu builds the mip chains with vq_texture_build_mips and a material table)
 import bench
 sc = bench.surface_scene_gpu(ctx, vq, torch, 64, 38, n_materials=3, tex_res=64)
 g4 = [torch.empty((38, 64, 4), device="cuda") for _ in range(4)]
-ctx.gbuffer_from_materials(sc["inputs"], sc["table"], 0.3, vq.GBuffer(*(vq.image_of(t) for t in g4)))
+ctx.gbuffer_from_materials(sc["inputs"], sc["table"], 0.3, vq.GBuffer(*(vq.image_of(t) for t in g4)))      # texel records
+os.environ["VQ_SURFACE_RECORDS"] = "0"
+t_maps = ctx.material_table(sc["mats"], sc["mts"]); os.environ.pop("VQ_SURFACE_RECORDS")
+ctx.gbuffer_from_materials(sc["inputs"], t_maps, 0.3, vq.GBuffer(*(vq.image_of(t) for t in g4)), alpha_mask=True)   # map by map
 # SURVEY 8(f).2 / (f).3
 src = dev(synth.hdri(96, 20)); src8 = dev(synth.hdri(6, 5))
 for im in (src, src8):
