@@ -496,35 +496,56 @@ __device__ __forceinline__ void shade_surface_pixel(const SurfArgs& A, int x, in
 // the majority paths dominate the instruction count, not the stray lanes; and a persistent kernel with the interpolant planes on a
 // TMA / mbarrier ring like K1's (0.49 ms) — the waits are on the texel and SSAO loads, not on the interpolants, and 92 KB of code
 // with every warp of an SM somewhere else in it stalls on instruction fetch.
-__global__ void __launch_bounds__(256, SURF_MIN_BLOCKS) surface_kernel(const __grid_constant__ SurfArgs A) {
-    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    const int x = blockIdx.x * 32 + (warp & 1) * 16 + (lane & 15);
-    const int y = A.tileY0 + blockIdx.y * 8 + (warp >> 1) * 2 + (lane >> 4);
+// SURF_TILES consecutive 32x8 tiles (stacked in y) per block: the interpolants and the SSAO texel of the NEXT tile are requested
+// before the current tile is shaded, so their HBM latency (43 % of the kernel's long-scoreboard stalls with one tile per block)
+// runs under a whole tile of sampling and filtering instead of in front of it.
+#ifndef SURF_TILES
+#define SURF_TILES 2
+#endif
+struct SurfTexels { float4 pu, nv, tm; float ssao; };
+__device__ __forceinline__ SurfTexels surface_fetch(const SurfArgs& A, int x, int y, uint64_t once) {
     const int W = A.posU.w, H = A.posU.h;
     // threads outside the image re-read the clamped texel: their uv equals the in-image partner's -> derivative 0,
     // exactly the oracle's "partner clamped to the image"
     const int cx = min(x, W - 1), cy = min(y, H - 1);
-    const uint64_t once = l2_policy_evict_first();
-    const float4 pu = ld_once(A.posU.row(cy) + cx, once);
-    const float4 nv = ld_once(A.nrmV.row(cy) + cx, once);
-    const float4 tm = ld_once(A.tanM.row(cy) + cx, once);
+    SurfTexels t;
+    t.pu = ld_once(A.posU.row(cy) + cx, once);
+    t.nv = ld_once(A.nrmV.row(cy) + cx, once);
+    t.tm = ld_once(A.tanM.row(cy) + cx, once);
     // the SSAO texel (x+1, y+1, WRAP; :280-281) depends on nothing but the pixel: fetched with the interpolants, not at the point
     // of use after the whole sampling chain (where it was 17 % of the kernel's long-scoreboard stalls)
-    float ssao = 1.0f;
+    t.ssao = 1.0f;
     if (A.ssao) {
         const int sxp = cx + 1 == W ? 0 : cx + 1, syp = cy + 1 == H ? 0 : cy + 1;
-        ssao = __ldg(A.ssao + (size_t)syp * A.ssaoPitch + sxp);
+        t.ssao = __ldg(A.ssao + (size_t)syp * A.ssaoPitch + sxp);
     }
-    const float ru = pu.w, rv = nv.w;
-    // fine quad derivatives of the RAW uv: horizontal partner = lane^1, vertical = lane^16
-    const float ruX = __shfl_xor_sync(0xffffffffu, ru, 1), rvX = __shfl_xor_sync(0xffffffffu, rv, 1);
-    const float ruY = __shfl_xor_sync(0xffffffffu, ru, 16), rvY = __shfl_xor_sync(0xffffffffu, rv, 16);
-    const float sx = (lane & 1) ? -1.0f : 1.0f, sy = (lane & 16) ? -1.0f : 1.0f;   // (odd - even) regardless of which I am
-    const float dRawUdx = (ruX - ru) * sx, dRawVdx = (rvX - rv) * sx;
-    const float dRawUdy = (ruY - ru) * sy, dRawVdy = (rvY - rv) * sy;
-    if (x >= W || y >= H || y < A.rowBegin || y >= A.rowEnd) return;
-    const int mi = min(max((int)tm.w, 0), A.nMats - 1);
-    shade_surface_pixel(A, x, y, mi, pu, nv, tm, ssao, dRawUdx, dRawVdx, dRawUdy, dRawVdy, once);
+    return t;
+}
+
+__global__ void __launch_bounds__(256, SURF_MIN_BLOCKS) surface_kernel(const __grid_constant__ SurfArgs A) {
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int x = blockIdx.x * 32 + (warp & 1) * 16 + (lane & 15);
+    const int yBase = A.tileY0 + blockIdx.y * (8 * SURF_TILES) + (warp >> 1) * 2 + (lane >> 4);
+    const int W = A.posU.w, H = A.posU.h;
+    const uint64_t once = l2_policy_evict_first();
+    SurfTexels nxt = surface_fetch(A, x, yBase, once);
+#pragma unroll 1
+    for (int it = 0; it < SURF_TILES; ++it) {
+        const int y = yBase + 8 * it;
+        const SurfTexels cur = nxt;
+        if (it + 1 < SURF_TILES && y + 8 - (lane >> 4) - (warp >> 1) * 2 < A.rowEnd) nxt = surface_fetch(A, x, y + 8, once);   // block-uniform test
+        const float ru = cur.pu.w, rv = cur.nv.w;
+        // fine quad derivatives of the RAW uv: horizontal partner = lane^1, vertical = lane^16
+        const float ruX = __shfl_xor_sync(0xffffffffu, ru, 1), rvX = __shfl_xor_sync(0xffffffffu, rv, 1);
+        const float ruY = __shfl_xor_sync(0xffffffffu, ru, 16), rvY = __shfl_xor_sync(0xffffffffu, rv, 16);
+        const float sx = (lane & 1) ? -1.0f : 1.0f, sy = (lane & 16) ? -1.0f : 1.0f;   // (odd - even) regardless of which I am
+        const float dRawUdx = (ruX - ru) * sx, dRawVdx = (rvX - rv) * sx;
+        const float dRawUdy = (ruY - ru) * sy, dRawVdy = (rvY - rv) * sy;
+        if (x < W && y < H && y >= A.rowBegin && y < A.rowEnd) {
+            const int mi = min(max((int)cur.tm.w, 0), A.nMats - 1);
+            shade_surface_pixel(A, x, y, mi, cur.pu, cur.nv, cur.tm, cur.ssao, dRawUdx, dRawVdx, dRawUdy, dRawVdy, once);
+        }
+    }
 }
 
 // interleaves the texels of a material's seven maps (same size, same level count; nullptr = null SRV = zeros) into records
@@ -688,7 +709,7 @@ extern "C" int vq_gbuffer_from_materials(VqContext* ctx, const VqSurfaceInputs* 
     A.mats = table->dev; A.nMats = table->count;
     A.ambient = ambient_factor; A.alphaMask = alpha_mask;
     A.rowBegin = row_begin; A.rowEnd = row_end; A.tileY0 = row_begin & ~1;
-    const dim3 grid((W + 31) / 32, (row_end - A.tileY0 + 7) / 8);
+    const dim3 grid((W + 31) / 32, (row_end - A.tileY0 + 8 * SURF_TILES - 1) / (8 * SURF_TILES));
     surface_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(A);
     return vq_check_launch("gbuffer_from_materials");
 }
