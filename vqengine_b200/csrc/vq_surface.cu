@@ -496,11 +496,12 @@ __device__ __forceinline__ void shade_surface_pixel(const SurfArgs& A, int x, in
 // the majority paths dominate the instruction count, not the stray lanes; and a persistent kernel with the interpolant planes on a
 // TMA / mbarrier ring like K1's (0.49 ms) — the waits are on the texel and SSAO loads, not on the interpolants, and 92 KB of code
 // with every warp of an SM somewhere else in it stalls on instruction fetch.
-// SURF_TILES consecutive 32x8 tiles (stacked in y) per block: the interpolants and the SSAO texel of the NEXT tile are requested
-// before the current tile is shaded, so their HBM latency (43 % of the kernel's long-scoreboard stalls with one tile per block)
-// runs under a whole tile of sampling and filtering instead of in front of it.
+// SURF_TILES > 1: consecutive 32x8 tiles (stacked in y) per block, the interpolants and the SSAO texel of the NEXT tile requested
+// before the current tile is shaded, so that their HBM latency (43 % of the kernel's long-scoreboard stalls) runs under a tile of
+// sampling and filtering. Measured and NOT the default: 13 more live registers cost more in spills than the overlap returns
+// (2 tiles: 0.412 ms at 64 registers, 0.397 at 80; 4 tiles: 0.401; 1 tile: 0.383).
 #ifndef SURF_TILES
-#define SURF_TILES 2
+#define SURF_TILES 1
 #endif
 struct SurfTexels { float4 pu, nv, tm; float ssao; };
 __device__ __forceinline__ SurfTexels surface_fetch(const SurfArgs& A, int x, int y, uint64_t once) {
