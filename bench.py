@@ -353,7 +353,7 @@ def surface_producer_pass(ctx, vq, torch, peak):
     nbytes = w * h * (48 + 4 + 64)          # 3 float4 interpolant planes + SSAO in, 4 float4 G-buffer planes out
     out = {"surface_producer_4k": {
         "config": f"{sc['n_materials']} materials (separate maps / ORM / constants / tiled non-pow2), {sc['tex_res']}^2 RGBA8 "
-                  f"maps = {sc['texture_bytes'] / 1e6:.1f} MB (L2-resident side data), SSAO + emissive planes",
+                  f"maps = {sc['texture_bytes'] / 1e6:.1f} MB (L2-resident side data; materials with same-size maps sampled from 16-byte texel records), SSAO + emissive planes",
         "ms": round(ms, 4), "ms_map_by_map": round(ms_maps, 4), "Mpixels_per_s": round(w * h / ms / 1e3, 1), "algorithmic_bytes_per_px": 116,
         "algorithmic_GBps": round(nbytes / ms / 1e6, 1), "hbm_frac": round(nbytes / ms / 1e6 / peak, 3)}}
     tw = 4096

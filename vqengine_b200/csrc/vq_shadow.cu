@@ -34,7 +34,10 @@ __device__ __forceinline__ vqshadow::Px4 px4(float4 v) { vqshadow::Px4 r; r.x = 
 // One thread per pixel; rows strided over the grid. 32 B/pixel in (position, normal), 8 B/pixel out; the shadow maps are
 // L2-resident side data. Bound by instruction issue: ~45 instructions per cube tap (face selection, two correctly rounded
 // quotients, texel address, depth comparison), ~10 per 2-D tap.
-__global__ void __launch_bounds__(128) shadow_pcf_kernel(const __grid_constant__ PcfParams P) {
+#ifndef PCF_MIN_BLOCKS
+#define PCF_MIN_BLOCKS 8
+#endif
+__global__ void __launch_bounds__(128, PCF_MIN_BLOCKS) shadow_pcf_kernel(const __grid_constant__ PcfParams P) {
     const int x = blockIdx.x * blockDim.x + threadIdx.x;
     const int cx = min(x, P.width - 1);          // whole warps stay alive (pcf_record votes across the warp): a lane past the row's end
     for (int r = blockIdx.y; r < P.rows; r += gridDim.y) {   // re-computes the last pixel and stores nothing
@@ -173,7 +176,7 @@ extern "C" int vq_forward_lighting_shadowed(VqContext* ctx, const VqPerFrameData
     P.rec = (uint2*)ctx->shadow_rec; P.recPitch = P.width;
 
     const unsigned gx = (unsigned)((P.width + 127) / 128);
-    unsigned gy = (unsigned)(ctx->sm_count * 8) / gx;
+    unsigned gy = (unsigned)(ctx->sm_count * PCF_MIN_BLOCKS) / gx;
     if (gy < 1) gy = 1;
     if (gy > (unsigned)P.rows) gy = (unsigned)P.rows;
     if (gy > 65535u) gy = 65535u;
