@@ -141,6 +141,35 @@ def test_skydome_matches_oracle(ctx, vq, orc, w, h, yaw, pitch):
     print(r)
 
 
+@pytest.mark.parametrize("w,h,rows,masked", [(257, 33, None, False), (160, 91, (7, 60), True), (64, 1, None, False), (3840, 17, (2, 17), False)])
+def test_skydome_pair_kernel_equals_single_pixel_kernel(ctx, vq, orc, w, h, rows, masked, monkeypatch):
+    """two pixels per thread on packed fp32x2 (the default) against one pixel per thread: the same operations per pixel, so the frames agree
+    to rounding noise of the rsqrt seeds at most; odd row counts, a row range starting on an odd row, a mask"""
+    from vqengine_b200 import synth
+    hw, hh = 512, 256
+    pyr, levels = _sky_setup(hw, hh, smooth=False)
+    _, inv = synth.sky_view_proj(-0.9, 0.3, 1.0, w / h)
+    inv32 = inv.astype(np.float32).reshape(16)
+    rng = np.random.default_rng(3)
+    mask = rng.random((h, w, 4), dtype=np.float32) + 0.1
+    mask[rng.random((h, w)) < 0.5, :3] = 0.0
+    base = rng.random((h, w, 4), dtype=np.float32)
+    dpyr = dev(pyr)
+
+    def run():
+        out = dev(base)
+        kw = {"normal_mask": dev(mask)} if masked else {}
+        if rows: kw.update(row_begin=rows[0], row_end=rows[1])
+        ctx.skydome(inv32, vq.pyramid_of(dpyr, hw, hh, levels), out, **kw)
+        return host(out)
+
+    pair = run()
+    monkeypatch.setenv("VQ_SKYDOME_PAIR", "0")
+    single = run()
+    assert np.array_equal(pair == base, single == base)                   # the same pixels written
+    assert np.abs(pair - single).max() <= 1e-5 * max(1.0, float(np.abs(single).max()))
+
+
 def test_skydome_noisy_hdri_mask_and_rows(ctx, vq, orc):
     """the BASELINE-style HDRI (per-texel noise, peaks of 16): a single bilinear sample amplifies the 1e-7 difference
     between the kernel's polynomial atan and the oracle's libm atan2 by the texel-to-texel contrast, so the bound is
